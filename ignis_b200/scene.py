@@ -1,0 +1,622 @@
+"""Scene ingest: Ignis scene JSON -> the binary tables and descriptors the device boundary takes.
+
+This is the caller side of the hot path (what the reference's Loader hands to
+`IRenderDevice::assignScene`), restated as data producers:
+
+* `entities` fix-table, 36 f32 per entity           (src/runtime/loader/LoaderEntity.cpp:150-162)
+* `shapes` dyn-table: 16-byte lookups + data blob    (src/runtime/shape/TriMeshProvider.cpp:575-596,
+                                                      src/runtime/shape/SphereProvider.cpp:42-47,
+                                                      src/runtime/table/DynTable.h:6-36)
+* scene-BVH leaves `EntityLeaf1`, 96 B per entity    (src/artic/traversal/bvh.art:52-61,
+                                                      src/runtime/bvh/SceneBVHAdapter.h:68-100)
+* `entity_per_material`                              (src/runtime/loader/LoaderEntity.cpp:42-97)
+* material / light / camera / technique descriptors = the arguments of the constructor calls the
+  reference's generators emit as shader text (DiffuseBSDF.cpp:13-27, DielectricBSDF.cpp:13-41,
+  AreaLight.cpp:115-220, PointLight.cpp:44-62, EnvironmentLight.cpp:44-110,
+  PerspectiveCamera.cpp:26-67, PathTechnique.cpp:35-79).
+
+Entity and light order: the reference iterates `std::unordered_map`s (Scene.h:59), i.e. an
+implementation-defined order; this loader uses file order.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import re
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import meshes
+from .meshes import TriMesh
+
+F = np.float32
+PI = float(F(3.14159265358979323846))
+DEG2RAD = float(F(PI) / F(180.0))
+
+SHAPE_TRIMESH = 0
+SHAPE_SPHERE = 1
+
+BSDF_DIFFUSE = 0      # make_lambertian_bsdf (bsdf/diffuse.art:2-12)
+BSDF_DIELECTRIC = 1   # make_pure_dielectric_bsdf (bsdf/dielectric.art:15-37)
+
+LIGHT_ENV_CONST = 0   # make_environment_light -> ..._function_spherical (light/env.art:75-100,161-164)
+LIGHT_POINT = 1       # make_point_light (light/point.art:1-18)
+LIGHT_PLANE_AREA = 2  # make_area_light + make_plane_area_emitter (light/area.art:10-43,124-258)
+LIGHT_SHAPE_AREA = 3  # make_area_light + make_shape_area_emitter (light/area.art:62-107)
+
+LOOKUP_DTYPE = np.dtype([("type_id", "<u4"), ("flags", "<u4"), ("offset", "<u8")])
+LEAF_DTYPE = np.dtype([("min", "<f4", 3), ("entity_id", "<i4"), ("max", "<f4", 3), ("shape_id", "<i4"),
+                       ("local", "<f4", 12), ("flags", "<u4"), ("mat_id", "<i4"), ("user1", "<i4"), ("user2", "<i4")])
+MATERIAL_DTYPE = np.dtype([("bsdf", "<i4"), ("light_id", "<i4"), ("p", "<f4", 14)])
+LIGHT_DTYPE = np.dtype([("type", "<i4"), ("entity_id", "<i4"), ("p", "<f4", 30)])
+CAMERA_DTYPE = np.dtype([("eye", "<f4", 3), ("dir", "<f4", 3), ("up", "<f4", 3), ("fov", "<f4"),
+                         ("fov_vertical", "<i4"), ("aspect", "<f4"), ("tmin", "<f4"), ("tmax", "<f4")])
+TECHNIQUE_DTYPE = np.dtype([("max_depth", "<i4"), ("min_depth", "<i4"), ("clamp", "<f4"), ("nee", "<i4")])
+assert LOOKUP_DTYPE.itemsize == 16 and LEAF_DTYPE.itemsize == 96
+assert MATERIAL_DTYPE.itemsize == 64 and LIGHT_DTYPE.itemsize == 128
+assert CAMERA_DTYPE.itemsize == 56 and TECHNIQUE_DTYPE.itemsize == 16
+
+
+class SceneError(RuntimeError):
+    pass
+
+
+@dataclass
+class SceneTables:
+    """Everything `igb200_set_scene` / the oracle take. All arrays are C-contiguous little-endian."""
+    entities: np.ndarray            # (n_entities, 36) f32
+    shape_lookups: np.ndarray       # (n_shapes,) LOOKUP_DTYPE
+    shape_data: np.ndarray          # (bytes,) u8
+    leaves: np.ndarray              # (n_entities,) LEAF_DTYPE
+    entity_per_material: np.ndarray  # (n_materials,) i32
+    materials: np.ndarray           # (n_materials,) MATERIAL_DTYPE
+    infinite_lights: np.ndarray     # LIGHT_DTYPE
+    finite_lights: np.ndarray       # LIGHT_DTYPE
+    camera: np.ndarray              # () CAMERA_DTYPE
+    technique: np.ndarray           # () TECHNIQUE_DTYPE
+    bbox_min: np.ndarray            # (3,) f32
+    bbox_max: np.ndarray            # (3,) f32
+    film_size: tuple[int, int]
+    entity_names: list[str] = field(default_factory=list)
+    material_names: list[str] = field(default_factory=list)
+
+    @property
+    def n_entities(self) -> int:
+        return int(self.entities.shape[0])
+
+    @property
+    def n_triangles(self) -> int:
+        """Instanced triangle count (per entity, not per shape)."""
+        total = 0
+        for leaf in self.leaves:
+            lk = self.shape_lookups[int(leaf["shape_id"])]
+            if int(lk["type_id"]) == SHAPE_TRIMESH:
+                total += int(np.frombuffer(self.shape_data, "<u4", 1, int(lk["offset"]))[0])
+        return total
+
+
+# ------------------------------------------------------------------ JSON helpers
+def _load_json(path: str) -> dict:
+    with open(path, "r") as fh:
+        doc = json.load(fh)
+    base = os.path.dirname(os.path.abspath(path))
+    merged: dict = {}
+    # Parser.cpp:453-463: externals first, the including file overrides/extends afterwards
+    for ext in doc.get("externals", []):
+        sub = _load_json(os.path.join(base, ext["filename"]))
+        _merge(merged, sub)
+    doc = {k: v for k, v in doc.items() if k != "externals"}
+    _tag_paths(doc, base)
+    _merge(merged, doc)
+    return merged
+
+
+def _tag_paths(doc: dict, base: str) -> None:
+    for sec in ("shapes", "textures"):
+        for obj in doc.get(sec, []):
+            if isinstance(obj, dict) and "filename" in obj and not os.path.isabs(obj["filename"]):
+                obj["filename"] = os.path.normpath(os.path.join(base, obj["filename"]))
+
+
+def _merge(dst: dict, src: dict) -> None:
+    for k, v in src.items():
+        if k in ("bsdfs", "shapes", "entities", "lights", "textures", "media", "parameters"):
+            cur = dst.setdefault(k, [])
+            names = {o.get("name"): i for i, o in enumerate(cur) if isinstance(o, dict)}
+            for o in v:
+                if isinstance(o, dict) and o.get("name") in names:
+                    cur[names[o["name"]]] = o
+                else:
+                    cur.append(o)
+        else:
+            dst[k] = v
+
+
+def _vec3(v, default=None) -> np.ndarray:
+    if v is None:
+        return np.asarray(default, F)
+    if isinstance(v, (int, float)):
+        return np.asarray([v, v, v], F)
+    if len(v) == 2:
+        return np.asarray([v[0], v[1], 0], F)
+    if len(v) != 3:
+        raise SceneError("Expected vector of length 3")
+    return np.asarray(v, F)
+
+
+def _color(v, default) -> np.ndarray:
+    if v is None:
+        return np.asarray(default, F)
+    if isinstance(v, str):
+        m = re.fullmatch(r"\s*color\(([^()]*)\)\s*", v)   # constant PExpr colour literal, e.g. "color(0.8, 0.8, 0.8, 1.0)"
+        if m:
+            parts = [float(x) for x in m.group(1).split(",")]
+            if len(parts) in (3, 4):
+                return np.asarray(parts[:3], F)
+            if len(parts) == 1:
+                return np.asarray(parts * 3, F)
+        raise SceneError(f"textured / expression colour '{v}' is outside the supported path (SURVEY §8f)")
+    return _vec3(v)
+
+
+def _look_at(eye, center, up) -> np.ndarray:
+    """Parser.cpp:144-171."""
+    eye, center, up = (np.asarray(x, np.float64) for x in (eye, center, up))
+    f = center - eye
+    fl = np.linalg.norm(f)
+    f = f / fl if fl > 0 else np.array([0.0, 0.0, 1.0])
+    u = up / np.linalg.norm(up)
+    s = np.cross(f, u)
+    s /= np.linalg.norm(s)
+    u = np.cross(s, f)
+    m = np.eye(4)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = s, u, f, eye
+    return m
+
+
+def _rot(axis: int, deg: float) -> np.ndarray:
+    a = deg * math.pi / 180.0
+    c, s = math.cos(a), math.sin(a)
+    m = np.eye(4)
+    i, j = [(1, 2), (2, 0), (0, 1)][axis]
+    m[i, i], m[i, j], m[j, i], m[j, j] = c, -s, s, c
+    return m
+
+
+def _matrix(vals) -> np.ndarray:
+    n = len(vals)
+    m = np.eye(4)
+    if n == 9:
+        m[:3, :3] = np.asarray(vals, np.float64).reshape(3, 3)
+    elif n in (12, 16):
+        m[: n // 4, :] = np.asarray(vals, np.float64).reshape(n // 4, 4)
+    else:
+        raise SceneError("Expected transform matrix of size 9, 12 or 16")
+    return m
+
+
+def _apply_op(t: np.ndarray, op: dict) -> np.ndarray:
+    """Parser.cpp:173-232: every operation right-multiplies."""
+    for name, val in op.items():
+        if name == "translate":
+            m = np.eye(4)
+            m[:3, 3] = _vec3(val).astype(np.float64)
+        elif name == "scale":
+            m = np.eye(4)
+            s = [val] * 3 if isinstance(val, (int, float)) else list(_vec3(val))
+            m[0, 0], m[1, 1], m[2, 2] = (float(x) for x in s)
+        elif name == "rotate":
+            a = _vec3(val)
+            m = _rot(0, float(a[0])) @ _rot(1, float(a[1])) @ _rot(2, float(a[2]))
+        elif name == "qrotate":
+            w, x, y, z = (float(q) for q in val)
+            m = np.eye(4)
+            m[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+        elif name == "lookat":
+            origin = _vec3(val.get("origin"), (0, 0, 0))
+            up = _vec3(val.get("up"), (0, 0, 1))
+            if "direction" in val:
+                target = _vec3(val["direction"]) + origin
+            else:
+                target = _vec3(val.get("target"), (0, 1, 0))
+            m = _look_at(origin, target, up)
+        elif name == "matrix":
+            m = _matrix(val)
+        else:
+            raise SceneError(f"Transform property got unknown entry type '{name}'")
+        t = t @ m
+    return t
+
+
+def parse_transform(v) -> np.ndarray:
+    """Parser.cpp:285-320: array of numbers (row-major 3x3 / 3x4 / 4x4), list of operations, or one operation object."""
+    if v is None:
+        return np.eye(4)
+    if isinstance(v, dict):
+        return _apply_op(np.eye(4), v)
+    if isinstance(v, list) and v and isinstance(v[0], dict):
+        t = np.eye(4)
+        for op in v:
+            t = _apply_op(t, op)
+        return t
+    return _matrix(v)
+
+
+def _bbox_transformed(lo, hi, m) -> tuple[np.ndarray, np.ndarray]:
+    c = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])], np.float64)
+    c = c @ m[:3, :3].T + m[:3, 3]
+    return c.min(axis=0).astype(F), c.max(axis=0).astype(F)
+
+
+# ------------------------------------------------------------------ shapes
+def _build_trimesh(obj: dict) -> TriMesh:
+    """TriMeshProvider.cpp:17-104,478-548."""
+    t = obj["type"].lower()
+    g = obj.get
+    if t == "triangle":
+        m = meshes.make_triangle(_vec3(g("p0"), (0, 0, 0)), _vec3(g("p1"), (1, 0, 0)), _vec3(g("p2"), (0, 1, 0)))
+    elif t == "rectangle":
+        if "p0" not in obj:
+            w, h = float(g("width", 2.0)), float(g("height", 2.0))
+            origin = _vec3(g("origin"), (-w / 2, -h / 2, 0))
+            m = meshes.make_plane(origin, (w, 0, 0), (0, h, 0))
+        else:
+            m = meshes.make_rectangle(_vec3(g("p0"), (-1, -1, 0)), _vec3(g("p1"), (1, -1, 0)),
+                                      _vec3(g("p2"), (1, 1, 0)), _vec3(g("p3"), (-1, 1, 0)))
+    elif t in ("cube", "box"):
+        w, h, d = float(g("width", 2.0)), float(g("height", 2.0)), float(g("depth", 2.0))
+        origin = _vec3(g("origin"), (-w / 2, -h / 2, -d / 2))
+        m = meshes.make_box(origin, (w, 0, 0), (0, h, 0), (0, 0, d))
+    elif t == "icosphere":
+        m = meshes.make_ico_sphere(_vec3(g("center"), (0, 0, 0)), float(g("radius", 1.0)), int(g("subdivisions", 4)))
+    elif t == "uvsphere":
+        m = meshes.make_uv_sphere(_vec3(g("center"), (0, 0, 0)), float(g("radius", 1.0)), int(g("stacks", 32)), int(g("slices", 16)))
+    elif t == "cylinder":
+        if "radius" in obj:
+            br = tr = float(g("radius", 1.0))
+        else:
+            br = float(g("bottom_radius", 1.0))
+            tr = float(g("top_radius", br))
+        m = meshes.make_cylinder(_vec3(g("p0"), (0, 0, 0)), br, _vec3(g("p1"), (0, 0, 1)), tr, int(g("sections", 32)), bool(g("filled", True)))
+    elif t == "cone":
+        m = meshes.make_cone(_vec3(g("p0"), (0, 0, 0)), float(g("radius", 1.0)), _vec3(g("p1"), (0, 0, 1)), int(g("sections", 32)), bool(g("filled", True)))
+    elif t == "disk":
+        m = meshes.make_disk(_vec3(g("origin"), (0, 0, 0)), _vec3(g("normal"), (0, 0, 1)), float(g("radius", 1.0)), int(g("sections", 32)))
+    elif t in ("obj", "ply", "external"):
+        si = g("shape_index", -1)
+        m = meshes.load_external(obj["filename"], None if si is None or si < 0 else int(si))
+    elif t == "inline":
+        idx = np.asarray(g("indices"), np.int64).reshape(-1, 3)
+        m = TriMesh()
+        m.vertices = np.asarray(g("vertices"), F).reshape(-1, 3)
+        m.indices = np.concatenate([idx, np.zeros((len(idx), 1), np.int64)], axis=1).astype(np.uint32)
+        if "normals" in obj:
+            m.normals = np.asarray(g("normals"), F).reshape(-1, 3)
+        else:
+            m.compute_vertex_normals()
+        if "texcoords" in obj:
+            m.texcoords = np.asarray(g("texcoords"), F).reshape(-1, 2)
+        else:
+            m.make_texcoords_normalized()
+    else:
+        raise SceneError(f"Can not load shape type '{t}'")
+    if m.face_count == 0 or len(m.vertices) == 0:
+        raise SceneError(f"Shape '{obj.get('name')}': no geometry generated")
+    if g("flip_normals", False):
+        m.flip_normals()
+    if g("face_normals", False):
+        m.setup_face_normals_as_vertex_normals()
+    elif g("smooth_normals", False):
+        m.compute_vertex_normals()
+    if g("generic_uv", False):
+        m.make_texcoords_normalized()
+    m.transform(parse_transform(g("transform")))
+    # handleModification, TriMeshProvider.cpp:431-476
+    sub = int(g("subdivision", 0))
+    if float(g("refinement", 0)) > 0 or g("displacement"):
+        raise SceneError("refinement / displacement are outside the supported path")
+    if sub > 0:
+        for _ in range(sub):
+            m.subdivide()
+        if g("smooth_normals", False):
+            m.compute_vertex_normals()
+        else:
+            m.setup_face_normals_as_vertex_normals()
+    return m
+
+
+def _serialize_trimesh(m: TriMesh, lo: np.ndarray, hi: np.ndarray) -> bytes:
+    """TriMeshProvider.cpp:575-596."""
+    nf, nv, nn, nt = m.face_count, len(m.vertices), len(m.normals), len(m.texcoords)
+    head = np.asarray([nf, nv, nn, nt], "<u4").tobytes()
+    box = np.asarray([lo[0], lo[1], lo[2], 0, hi[0], hi[1], hi[2], 0], "<f4").tobytes()
+    v4 = np.zeros((nv, 4), "<f4")
+    v4[:, :3] = m.vertices
+    n4 = np.zeros((nn, 4), "<f4")
+    n4[:, :3] = m.normals
+    return head + box + v4.tobytes() + n4.tobytes() + m.indices.astype("<u4").tobytes() + m.texcoords.astype("<f4").tobytes()
+
+
+# ------------------------------------------------------------------ loader
+def load_scene(path, width: int | None = None, height: int | None = None,
+               max_depth: int | None = None, base_dir: str | None = None) -> SceneTables:
+    """`path` is a scene file name or an already parsed scene dict (the reference's `loadFromString`)."""
+    if isinstance(path, dict):
+        doc = json.loads(json.dumps(path))
+        base = base_dir or os.getcwd()
+        merged: dict = {}
+        for ext in doc.get("externals", []):
+            _merge(merged, _load_json(os.path.join(base, ext["filename"])))
+        doc = {k: v for k, v in doc.items() if k != "externals"}
+        _tag_paths(doc, base)
+        _merge(merged, doc)
+        doc = merged
+    else:
+        doc = _load_json(path)
+    film = doc.get("film", {})
+    fsize = film.get("size", [800, 600])
+    fw = int(width if width is not None else fsize[0])
+    fh = int(height if height is not None else fsize[1])
+
+    tech = doc.get("technique", {"type": "path"})
+    if tech.get("type", "path") != "path":
+        raise SceneError(f"technique '{tech.get('type')}' is outside the supported path (only 'path')")
+    if tech.get("aov_mis", False):
+        raise SceneError("aov_mis (advanced shadow handling) is outside the supported path")
+    sel = str(tech.get("light_selector", "") or "uniform").lower()
+    if sel not in ("uniform", ""):
+        raise SceneError(f"light_selector '{sel}' is outside the supported path (only 'uniform')")
+    technique = np.zeros((), TECHNIQUE_DTYPE)
+    technique["max_depth"] = int(max_depth if max_depth is not None else tech.get("max_depth", 64))
+    technique["min_depth"] = int(tech.get("min_depth", 2))
+    technique["clamp"] = float(tech.get("clamp", 0.0))
+    technique["nee"] = 1 if tech.get("nee", True) else 0
+
+    bsdfs = {b["name"]: b for b in doc.get("bsdfs", [])}
+    shapes_json = {s["name"]: s for s in doc.get("shapes", [])}
+    entities_json = doc.get("entities", [])
+    lights_json = doc.get("lights", [])
+
+    # LoaderLight.cpp:263-277: entities referenced by an area light are emissive
+    emissive = {l["entity"]: l for l in lights_json if l.get("type") == "area" and l.get("entity")}
+
+    # ---- shapes actually used, in file order (LoaderShape.cpp prepare: only referenced shapes are loaded)
+    used = []
+    for e in entities_json:
+        s = e.get("shape")
+        if s in shapes_json and s not in used:
+            used.append(s)
+    shape_ids, shape_info = {}, []
+    lookups, blob = [], bytearray()
+    for name in used:
+        sj = shapes_json[name]
+        off = len(blob)
+        if sj["type"].lower() == "sphere":
+            origin = _vec3(sj.get("center"), (0, 0, 0))
+            radius = F(sj.get("radius", 1.0))
+            if radius <= 0:
+                raise SceneError(f"Shape '{name}': invalid radius")
+            lo, hi = (origin - radius - F(1e-5)).astype(F), (origin + radius + F(1e-5)).astype(F)
+            blob += np.asarray([origin[0], origin[1], origin[2], radius], "<f4").tobytes()
+            lookups.append((SHAPE_SPHERE, 0, off))
+            shape_info.append(dict(type=SHAPE_SPHERE, lo=lo, hi=hi, mesh=None, plane=None))
+        else:
+            mesh = _build_trimesh(sj)
+            lo = (mesh.vertices.min(axis=0) - F(1e-5)).astype(F)
+            hi = (mesh.vertices.max(axis=0) + F(1e-5)).astype(F)
+            blob += _serialize_trimesh(mesh, lo, hi)
+            lookups.append((SHAPE_TRIMESH, 0, off))
+            shape_info.append(dict(type=SHAPE_TRIMESH, lo=lo, hi=hi, mesh=mesh, plane=mesh.get_as_plane()))
+        while len(blob) % 16:
+            blob += b"\0"
+        shape_ids[name] = len(shape_ids)
+
+    # ---- material grouping (LoaderEntity.cpp:42-97): one material per distinct bsdf, one per emissive entity
+    mat_keys: list[tuple] = []
+    groups: list[list[dict]] = []
+    for e in entities_json:
+        bname = e.get("bsdf", "")
+        if not bname or bname not in bsdfs:
+            raise SceneError(f"Entity {e.get('name')} has no/unknown bsdf '{bname}'")
+        if e.get("inner_medium") or e.get("outer_medium"):
+            raise SceneError("participating media are outside the supported path")
+        if e["name"] in emissive:
+            mat_keys.append((bname, e["name"]))
+            groups.append([e])
+        else:
+            key = (bname, None)
+            if key in mat_keys:
+                groups[mat_keys.index(key)].append(e)
+            else:
+                mat_keys.append(key)
+                groups.append([e])
+
+    n_ent = sum(len(g) for g in groups)
+    ent_table = np.zeros((n_ent, 36), F)
+    leaves = np.zeros(n_ent, LEAF_DTYPE)
+    names, ent_info = [], {}
+    bb_lo = np.full(3, np.inf, F)
+    bb_hi = np.full(3, -np.inf, F)
+    eid = 0
+    for mat_id, grp in enumerate(groups):
+        for e in grp:
+            sname = e.get("shape", "")
+            if sname not in shape_ids:
+                raise SceneError(f"Entity {e.get('name')} has unknown shape '{sname}'")
+            sid = shape_ids[sname]
+            flags = 0
+            for bit, key in ((1, "camera_visible"), (2, "light_visible"), (4, "bounce_visible"), (8, "shadow_visible")):
+                if e.get(key, True):
+                    flags |= bit
+            t = parse_transform(e.get("transform"))
+            t[3, :] = (0, 0, 0, 1)
+            inv = np.linalg.inv(t)
+            lo, hi = _bbox_transformed(shape_info[sid]["lo"], shape_info[sid]["hi"], t)
+            bb_lo, bb_hi = np.minimum(bb_lo, lo), np.maximum(bb_hi, hi)
+            to_local = inv[:3, :4].astype(F)
+            to_global = t[:3, :4].astype(F)
+            to_normal = np.linalg.inv(t[:3, :3]).T.astype(F)
+            row = ent_table[eid]
+            row[0:12] = to_local.T.reshape(-1)      # column-major
+            row[12:24] = to_global.T.reshape(-1)
+            row[24:33] = to_normal.T.reshape(-1)
+            row[33:36].view(np.uint32)[:] = (sid, mat_id, 0)
+            lf = leaves[eid]
+            lf["min"], lf["max"] = lo, hi
+            lf["entity_id"], lf["shape_id"] = eid, sid
+            lf["local"] = to_local.T.reshape(-1)
+            lf["flags"], lf["mat_id"] = flags, mat_id
+            names.append(e["name"])
+            ent_info[e["name"]] = dict(id=eid, transform=t, shape_id=sid, mat_id=mat_id)
+            eid += 1
+
+    # ---- lights (LoaderLight.cpp:263-300: infinite and finite lights have separate id spaces)
+    inf_l, fin_l = [], []
+    fin_of_entity: dict[str, int] = {}
+    for lj in lights_json:
+        lt = lj.get("type", "").lower()
+        rec = np.zeros((), LIGHT_DTYPE)
+        rec["entity_id"] = -1
+        if lt in ("env", "constant", "uniform", "envmap"):
+            rad = lj.get("radiance", [1, 1, 1])
+            scale = _color(lj.get("scale"), (1, 1, 1))
+            rec["type"] = LIGHT_ENV_CONST
+            rec["p"][0:3] = (scale * _color(rad, (1, 1, 1))).astype(F)   # color_mul(scale, tex)
+            inf_l.append(rec)
+        elif lt == "point":
+            rec["type"] = LIGHT_POINT
+            rec["p"][0:3] = _vec3(lj.get("position"), (0, 0, 0))
+            if "power" in lj:
+                rec["p"][3:6] = (_color(lj["power"], (0, 0, 0)) * F(1.0 / (4 * PI))).astype(F)
+            else:
+                rec["p"][3:6] = _color(lj.get("intensity"), (1, 1, 1))
+            fin_l.append(rec)
+        elif lt == "area":
+            ename = lj.get("entity", "")
+            if ename not in ent_info:
+                raise SceneError(f"No entity named '{ename}' exists for area light")
+            ei = ent_info[ename]
+            info = shape_info[ei["shape_id"]]
+            if info["type"] != SHAPE_TRIMESH:
+                raise SceneError("sphere area lights are outside the supported path (SURVEY §8f)")
+            t = ei["transform"]
+            plane = info["plane"] if lj.get("optimize", True) else None
+            if plane is not None:
+                origin = (t[:3, :3] @ plane["origin"].astype(np.float64) + t[:3, 3]).astype(F)
+                xa = (t[:3, :3] @ plane["x_axis"].astype(np.float64)).astype(F)
+                ya = (t[:3, :3] @ plane["y_axis"].astype(np.float64)).astype(F)
+                cr = np.cross(xa.astype(np.float64), ya.astype(np.float64))
+                area = float(np.linalg.norm(cr))
+                rec["type"] = LIGHT_PLANE_AREA
+                rec["p"][0:3], rec["p"][3:6], rec["p"][6:9] = origin, xa, ya
+                rec["p"][9:12] = (cr / area).astype(F)
+                rec["p"][12] = area
+                rec["p"][13:21] = plane["texcoords"].reshape(-1)
+                rad_off = 21
+            else:
+                mesh = info["mesh"]
+                d = (info["hi"] - info["lo"]).astype(np.float64)
+                w = np.linalg.norm(t[:3, 0] * d[0])
+                h = np.linalg.norm(t[:3, 1] * d[1])
+                dd = np.linalg.norm(t[:3, 2] * d[2])
+                half = d[0] * d[1] + d[0] * d[2] + d[1] * d[2]
+                area = mesh.compute_area() * (w * h + w * dd + h * dd) / half
+                rec["type"] = LIGHT_SHAPE_AREA
+                rad_off = 0
+            rec["entity_id"] = ei["id"]
+            if "power" in lj:
+                rec["p"][rad_off:rad_off + 3] = (_color(lj["power"], (0, 0, 0)) * F(1.0 / PI / area)).astype(F)
+            else:
+                rec["p"][rad_off:rad_off + 3] = _color(lj.get("radiance"), (1, 1, 1))
+            fin_of_entity[ename] = len(fin_l)
+            fin_l.append(rec)
+        else:
+            raise SceneError(f"light type '{lt}' is outside the supported path (SURVEY §8f)")
+
+    # ---- materials
+    materials = np.zeros(len(groups), MATERIAL_DTYPE)
+    for mid, (bname, emis) in enumerate(mat_keys):
+        bj = bsdfs[bname]
+        bt = bj.get("type", "").lower()
+        rec = materials[mid]
+        rec["light_id"] = fin_of_entity[emis] if emis is not None else -1
+        if bt in ("diffuse", "roughdiffuse"):
+            alpha = bj.get("alpha", bj.get("roughness", 0.0))
+            if isinstance(alpha, str) or float(alpha) > 1.1920928955e-07:
+                raise SceneError("Oren-Nayar (rough) diffuse is outside the supported path")
+            rec["bsdf"] = BSDF_DIFFUSE
+            rec["p"][0:3] = _color(bj.get("reflectance"), (0.8, 0.8, 0.8))
+        elif bt in ("dielectric", "glass", "roughdielectric", "thindielectric"):
+            rough = [bj.get(k, 0) or 0 for k in ("roughness", "alpha", "roughness_u", "roughness_v", "alpha_u", "alpha_v")]
+            if bj.get("thin", False) or any(isinstance(r, str) or float(r) > 0 for r in rough):
+                raise SceneError("thin / rough dielectrics are outside the supported path")
+            iors = {"vacuum": 1.0, "bk7": 1.5046}
+            ext = bj.get("ext_ior", iors.get(str(bj.get("ext_ior_material", "")).lower(), 1.0))
+            int_ = bj.get("int_ior", iors.get(str(bj.get("int_ior_material", "")).lower(), 1.5046))
+            rec["bsdf"] = BSDF_DIELECTRIC
+            rec["p"][0], rec["p"][1] = float(ext), float(int_)
+            rec["p"][2:5] = _color(bj.get("specular_reflectance"), (1, 1, 1))
+            rec["p"][5:8] = _color(bj.get("specular_transmittance"), (1, 1, 1))
+        else:
+            raise SceneError(f"bsdf type '{bt}' is outside the supported path (SURVEY §8f)")
+
+    # ---- camera (PerspectiveCamera.cpp:11-107, Camera.cpp:5-15)
+    cj = doc.get("camera", {"type": "perspective"})
+    if cj.get("type", "perspective") != "perspective":
+        raise SceneError(f"camera type '{cj.get('type')}' is outside the supported path")
+    if float(cj.get("aperture_radius", 0)) > 1.1920928955e-07:
+        raise SceneError("depth of field is outside the supported path")
+    cam = np.zeros((), CAMERA_DTYPE)
+    if "vfov" in cj:
+        vertical, fov = 1, float(cj["vfov"])
+    elif "hfov" in cj:
+        vertical, fov = 0, float(cj["hfov"])
+    else:
+        vertical, fov = 0, float(cj.get("fov", 60.0))
+    # the generator streams the value into shader text with 6 significant digits
+    cam["fov"] = float("%g" % float(F(fov) * F(DEG2RAD)))
+    cam["fov_vertical"] = vertical
+    cam["aspect"] = float("%f" % float(cj["aspect_ratio"])) if "aspect_ratio" in cj else 0.0
+    near = float(cj.get("near_clip", 0.0))
+    far = float(cj.get("far_clip", np.finfo(np.float32).max))
+    if far < near:
+        near, far = far, near
+    cam["tmin"], cam["tmax"] = float("%g" % near), float("%g" % far)
+    if "transform" in cj:
+        t = parse_transform(cj["transform"])
+        cam["eye"] = t[:3, 3].astype(F)
+        cam["dir"] = t[:3, 2].astype(F)
+        cam["up"] = t[:3, 1].astype(F)
+    elif n_ent == 0:
+        cam["eye"], cam["dir"], cam["up"] = (0, 0, 0), (0, 0, -1), (0, 1, 0)
+    else:
+        aspect = float(cam["aspect"]) if cam["aspect"] > 0 else fw / fh
+        d3 = (bb_hi - bb_lo).astype(np.float64)
+        a = d3[0] / (2 * (aspect if vertical else 1))
+        b = d3[1] / (2 * (aspect if not vertical else 1))
+        s = math.sin(float(cam["fov"]) / 2)
+        d = 0.0 if abs(s) <= 1.1920928955e-07 else max(a, b) * math.sqrt(1 / (s * s) - 1)
+        c = (bb_lo.astype(np.float64) + bb_hi.astype(np.float64)) / 2
+        cam["eye"], cam["dir"], cam["up"] = (c[0], c[1], bb_hi[2] + d), (0, 0, -1), (0, 1, 0)
+
+    if n_ent == 0:
+        bb_lo = np.zeros(3, F)
+        bb_hi = np.zeros(3, F)
+
+    def _arr(lst):
+        return np.asarray(lst, LIGHT_DTYPE) if lst else np.zeros(0, LIGHT_DTYPE)
+
+    lk = np.zeros(len(lookups), LOOKUP_DTYPE)
+    for i, (ty, fl, off) in enumerate(lookups):
+        lk[i] = (ty, fl, off)
+    return SceneTables(
+        entities=np.ascontiguousarray(ent_table), shape_lookups=lk,
+        shape_data=np.frombuffer(bytes(blob), np.uint8).copy(), leaves=leaves,
+        entity_per_material=np.asarray([len(g) for g in groups], np.int32), materials=materials,
+        infinite_lights=_arr(inf_l), finite_lights=_arr(fin_l), camera=cam, technique=technique,
+        bbox_min=bb_lo.astype(F), bbox_max=bb_hi.astype(F), film_size=(fw, fh),
+        entity_names=names, material_names=[f"{b}{'@' + e if e else ''}" for b, e in mat_keys])

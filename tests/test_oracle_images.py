@@ -1,0 +1,44 @@
+"""Pins the CPU oracle against the reference's converged evaluation images (scenes/evaluation/references/*.exr,
+copied to tests/golden/ref_images.npz by tools/make_golden.py) with the RelMSE rule of the reference's
+scripts/RunEvaluations.py:83-92. The reference thresholds (default 1e-3, cbox 5e-3, multilight 3e-4; :95-123) are
+stated for 1024 spp; CI runs fewer samples, so thresholds are scaled by the sample ratio (variance ~ 1/spp).
+tools/eval_oracle.py runs the full 1024 spp version (results recorded in DESIGN.md)."""
+import os
+
+import numpy as np
+import pytest
+
+from ignis_b200.scene import load_scene
+from oracle.oracle import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EPS_1024 = {"plane-d1": 1e-3, "plane-d6": 1e-3, "point": 1e-3, "emissive-plane": 1e-3, "cbox-d1": 5e-3, "cbox-d6": 5e-3,
+            "multilight-uniform": 3e-4}
+
+
+def relmse(img, ref):
+    mask = ref != 0
+    err = np.zeros_like(ref)
+    err[mask] = np.square((img[mask] - ref[mask]) / ref[mask])
+    err[~mask] = np.square(img[~mask])
+    mx = np.percentile(err, 99)
+    return float(np.average(np.clip(err, 0, mx)))
+
+
+@pytest.mark.parametrize("name,spp", [("plane-d1", 128), ("plane-d6", 128), ("point", 64), ("emissive-plane", 256),
+                                      ("cbox-d1", 128), ("cbox-d6", 512), ("multilight-uniform", 512)])
+def test_oracle_matches_reference_image(name, spp):
+    refs = np.load(os.path.join(ROOT, "tests", "golden", "ref_images.npz"))
+    ref = refs[name].astype(np.float32)
+    t = load_scene(os.path.join(ROOT, "scenes", "evaluation", name + ".json"))
+    w, h = t.film_size
+    assert ref.shape == (h, w, 3)
+    o = Oracle(t)
+    fb = np.zeros((h, w, 3), np.float32)
+    spi = 8
+    for it in range(spp // spi):
+        o.render(w, h, spi=spi, iteration=it, fb=fb)
+    img = fb / (spp // spi)
+    # noise variance scales with 1/spp; a systematic error does not, so the scaled bound still catches a wrong estimator
+    assert relmse(img, ref) < EPS_1024[name] * (1024 / spp) * 1.5
+    assert img.mean() == pytest.approx(ref.mean(), rel=0.02)

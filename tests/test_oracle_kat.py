@@ -1,0 +1,152 @@
+"""Pins the CPU oracle against the reference's own known-answer tests and analytic scene averages.
+
+Sources in the reference: src/tests/artic/test_intersection.art (triangle :1-69, box :71-122),
+src/tests/integrator/test_lights.py:5-44, test_init.py:9-12, test_reproducibility.py:5-20,
+src/artic/core/random.art (FNV / TEA definitions).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import flat_scene
+from ignis_b200.scene import load_scene
+from oracle.oracle import Oracle, detmath, lib
+
+
+def f3(*v):
+    return (C.c_float * 3)(*v)
+
+
+def kat_tri(org, dirv, cull=0, tmin=0.0, tmax=10.0):
+    out = f3(0, 0, 0)
+    # test_intersection.art:2-5: v0=(0,0,0), e1=(0,1,0), e2=(-1,0,0), n=(0,0,1)
+    hit = lib().igo_kat_tri(f3(0, 0, 0), f3(0, 1, 0), f3(-1, 0, 0), f3(0, 0, 1), f3(*org), f3(*dirv), tmin, tmax, cull, out)
+    return hit, tuple(out)
+
+
+def test_tri_hit_exact_values():
+    hit, (t, u, v) = kat_tri((0.2, 0.4, 1), (0, 0, -1))
+    assert hit == 1
+    assert t == pytest.approx(1.0, abs=1e-7) and u == pytest.approx(0.2, abs=1e-7) and v == pytest.approx(0.4, abs=1e-7)
+
+
+def test_tri_miss():
+    assert kat_tri((0.2, 4.4, 1), (0, 0, -1))[0] == 0
+
+
+def test_tri_backface_without_and_with_culling():
+    hit, (t, u, v) = kat_tri((0.2, 0.4, -1), (0, 0, 1), cull=0)
+    assert hit == 1 and t == pytest.approx(1.0, abs=1e-7)
+    assert kat_tri((0.2, 0.4, -1), (0, 0, 1), cull=1)[0] == 0
+
+
+def kat_box(bmin, bmax, org, dirv):
+    out = f3(0, 0, 0)
+    hit = lib().igo_kat_box(f3(*bmin), f3(*bmax), f3(*org), f3(*dirv), 0.0, 10.0, out)
+    return hit, out[0], out[1]
+
+
+def test_box_hit_miss_flat():
+    hit, entry, _ = kat_box((0, 0, 0), (1, 1, 1), (0.2, 0.4, 2), (0, 0, -1))
+    assert hit == 1 and entry == pytest.approx(1.0, abs=1e-6)
+    assert kat_box((0, 0, 0), (1, 1, 1), (0.2, 3.4, 2), (0, 0, -1))[0] == 0
+    hit, entry, _ = kat_box((0, 0, 0), (1, 1, 0), (0.2, 0.4, 1), (0, 0, -1))
+    assert hit == 1 and entry == pytest.approx(1.0, abs=1e-6)
+
+
+def test_rng_definitions():
+    # FNV-1a style hash over 6 little-endian u32 and 4-round TEA, evaluated independently in Python ints
+    def hc(h, d):
+        for s in (0, 8, 16, 24):
+            h = ((h * 16777619) & 0xFFFFFFFF) ^ ((d >> s) & 0xFF)
+        return h
+
+    def seed(*a):
+        h = 0x811C9DC5
+        for d in a:
+            h = hc(h, d & 0xFFFFFFFF)
+        return h
+
+    def tea(v0, v1):
+        s, M = 0, 0xFFFFFFFF
+        for _ in range(4):
+            s = (s + 0x9E3779B9) & M
+            v0 = (v0 + ((((v1 << 4) + 0xA341316C) & M) ^ ((v1 + s) & M) ^ (((v1 >> 5) + 0xC8013EA4) & M))) & M
+            v1 = (v1 + ((((v0 << 4) + 0xAD90777D) & M) ^ ((v0 + s) & M) ^ (((v0 >> 5) + 0x7E95761E) & M))) & M
+        return v1
+
+    for args in [(0, 0, 0, 0, 0, 0), (3, 7, 1, 1919, 1079, 42), (1, 2, 3, 4, 5, -1)]:
+        assert lib().igo_random_seed(*args) == seed(*args)
+    for v0, v1 in [(0, 1), (0x811C9DC5, 2), (123456789, 0xFFFFFFFF)]:
+        assert lib().igo_tea(v0, v1) == tea(v0, v1)
+    x = tea(77, 1)
+    assert lib().igo_next_f32(77, 1) == np.frombuffer(np.uint32((x & 0x7FFFFF) | 0x3F800000).tobytes(), np.float32)[0] - np.float32(1)
+
+
+def test_detmath_against_libm():
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-10, 10, 200000).astype(np.float32)
+    assert np.abs(detmath("sin", x) - np.sin(x.astype(np.float64))).max() < 2e-7
+    assert np.abs(detmath("cos", x) - np.cos(x.astype(np.float64))).max() < 2e-7
+    a = np.concatenate([rng.uniform(-1, 1, 200000), [-1, 1, 0, 0.5, -0.5]]).astype(np.float32)
+    ref = np.arccos(a.astype(np.float64))
+    assert (np.abs(detmath("acos", a) - ref) <= 4 * np.spacing(ref.astype(np.float32))).all()
+    y = rng.uniform(-3, 3, 200000).astype(np.float32)
+    assert np.abs(detmath("atan2", y, x) - np.arctan2(y.astype(np.float64), x.astype(np.float64))).max() < 6e-7
+
+
+def scene_average(scene, size=1000, iters=8, spi=2, seed=0):
+    t = load_scene(scene)
+    o = Oracle(t)
+    fb = np.zeros((size, size, 3), np.float32)
+    for it in range(iters):
+        o.render(size, size, spi=spi, iteration=it, seed=seed, fb=fb)
+    return float((fb / iters).mean()), fb / iters
+
+
+def test_empty_scene_is_black():
+    assert scene_average({}, size=64, iters=1)[0] == 0.0
+
+
+def test_no_light_is_black():
+    assert scene_average(flat_scene(), size=128, iters=2)[0] == pytest.approx(0, abs=1e-8)
+
+
+def test_point_light_scene_average():
+    s = flat_scene()
+    s["lights"].append({"type": "point", "name": "_light", "position": [0, 0, -2], "power": 1})
+    assert scene_average(s)[0] == pytest.approx(0.005100456, abs=1e-4)
+
+
+def test_env_light_scene_average():
+    s = flat_scene()
+    s["lights"].append({"type": "env", "name": "_light", "radiance": [1, 1, 1]})
+    assert scene_average(s)[0] == pytest.approx(1, rel=1e-4)
+
+
+def test_reproducibility():
+    s = flat_scene()
+    s["lights"].append({"type": "point", "name": "_light", "position": [0, 0, -2], "intensity": [1, 1, 1]})
+    a = scene_average(s, size=128, iters=1, spi=1, seed=42)[1]
+    b = scene_average(s, size=128, iters=1, spi=1, seed=42)[1]
+    np.testing.assert_array_equal(a, b)
+    c = scene_average(s, size=128, iters=1, spi=4, seed=42)[1]
+    assert not np.allclose(a, c)
+
+
+def test_bvh_and_brute_force_agree_on_hits(scenes_dir):
+    t = load_scene(f"{scenes_dir}/diamond_scene.json")
+    o = Oracle(t)
+    rng = np.random.default_rng(5)
+    from oracle.oracle import RAY_DTYPE
+    rays = np.zeros(20000, RAY_DTYPE)
+    rays["org"] = rng.uniform(-0.9, 0.9, (20000, 3))
+    d = rng.normal(size=(20000, 3))
+    rays["dir"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays["tmin"], rays["tmax"] = 1e-3, 100
+    a = o.trace_closest(rays, use_bvh=True)
+    b = o.trace_closest(rays, use_bvh=False)
+    np.testing.assert_array_equal(a, b)
+    assert (a["prim_id"] >= 0).mean() > 0.99   # closed box
+    np.testing.assert_array_equal(o.trace_any(rays, use_bvh=True), o.trace_any(rays, use_bvh=False))

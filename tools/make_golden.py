@@ -1,0 +1,61 @@
+"""Copies the reference's evaluation fixtures this repo's tests need into tests/golden/ and scenes/.
+
+Run once in the build container (where /root/reference is mounted); the outputs are committed so that tests and
+bench.py never read /root/reference at run time (it does not exist on the GPU box).
+
+ * tests/golden/ref_images.npz : the converged reference images of scenes/evaluation/references/*.exr that lie
+   inside the supported path, stored as float16 RGB (256x256), keyed by scene name.
+ * scenes/ : the scene description files + meshes of the benchmark / parity configurations (data, not source).
+"""
+import os
+import shutil
+import sys
+
+os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+import cv2  # noqa: E402
+import numpy as np  # noqa: E402
+
+REF = "/root/reference/scenes"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+IMAGES = {
+    "plane-d1": "ref-plane-d1-4096.exr", "plane-d6": "ref-plane-d6-4096.exr", "point": "ref-point-4096.exr",
+    "emissive-plane": "ref-emissive-plane-4096.exr", "cbox-d1": "ref-cbox-d1-4096.exr", "cbox-d6": "ref-cbox-d6-4096.exr",
+    "multilight-uniform": "ref-multilight-4096.exr",
+}
+SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "primitives_data.json", "flipped_prim.json",
+          "meshes/Bottom.ply", "meshes/Top.ply", "meshes/Left.ply", "meshes/Right.ply", "meshes/Back.ply", "meshes/Diamond.ply"]
+EVAL = ["plane-base.json", "plane-d1.json", "plane-d6.json", "point.json", "emissive-plane.json", "cbox-base.json", "cbox-d1.json",
+        "cbox-d6.json", "multilight.json", "multilight-uniform.json", "flipped-prim-base.json", "flipped-prim-diffuse.json"]
+
+
+def main():
+    out = {}
+    for key, fn in IMAGES.items():
+        img = cv2.imread(os.path.join(REF, "evaluation", "references", fn), cv2.IMREAD_UNCHANGED)
+        if img is None:
+            print("skip", fn)
+            continue
+        out[key] = img[..., 2::-1][..., :3].astype(np.float16) if img.shape[-1] >= 3 else img.astype(np.float16)
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_images.npz"), **out)
+    for f in SCENES:
+        dst = os.path.join(ROOT, "scenes", f)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if os.path.exists(os.path.join(REF, f)):
+            shutil.copyfile(os.path.join(REF, f), dst)
+    for f in EVAL:
+        dst = os.path.join(ROOT, "scenes", "evaluation", f)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if os.path.exists(os.path.join(REF, "evaluation", f)):
+            shutil.copyfile(os.path.join(REF, "evaluation", f), dst)
+    mdir = os.path.join(REF, "evaluation", "meshes")
+    for f in os.listdir(mdir):
+        if True:
+            os.makedirs(os.path.join(ROOT, "scenes", "evaluation", "meshes"), exist_ok=True)
+            shutil.copyfile(os.path.join(mdir, f), os.path.join(ROOT, "scenes", "evaluation", "meshes", f))
+    print({k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    sys.exit(main())
