@@ -148,5 +148,5 @@ def test_bvh_and_brute_force_agree_on_hits(scenes_dir):
     a = o.trace_closest(rays, use_bvh=True)
     b = o.trace_closest(rays, use_bvh=False)
     np.testing.assert_array_equal(a, b)
-    assert (a["prim_id"] >= 0).mean() > 0.99   # closed box
+    assert (a["prim_id"] >= 0).mean() > 0.8    # five-sided box
     np.testing.assert_array_equal(o.trace_any(rays, use_bvh=True), o.trace_any(rays, use_bvh=False))
