@@ -1,0 +1,52 @@
+"""Builds ignis_b200/libigb200.so (C ABI + sm_100a kernels) in-tree with nvcc.
+
+-fmad=false: the only fused multiply-adds in device code are explicit (see csrc/device_math.cuh).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libigb200.so")
+SOURCES = ["api.cu"]
+DEPS = ["api.cu", "kernels.cuh", "device_math.cuh", "bvh8.h", "../../include/igb200.h", "../build.py"]
+
+
+def nvcc_path() -> str:
+    for p in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if p and os.path.exists(p):
+            return p
+    raise RuntimeError("nvcc not found")
+
+
+def flags(extra=()):
+    return ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
+            "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-Xcompiler", "-O2", *extra]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(os.path.join(SRC, d)) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return OUT
+    cmd = [nvcc_path(), *flags(["-Xptxas", "-v"] if verbose else []), "-shared", "-o", OUT,
+           *[os.path.join(SRC, s) for s in SOURCES]]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

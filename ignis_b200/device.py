@@ -1,0 +1,314 @@
+"""Host-side mirror of the reference's render-device interface over the C ABI (include/igb200.h).
+
+`B200Device` has the method set of `IG::IRenderDevice` (src/runtime/device/IRenderDevice.h:14-81) with the same
+names and argument meaning; `Runtime` mirrors the part of `IG::Runtime` that drives the hot path
+(src/runtime/Runtime.cpp:71-79 SPI policy, :334-387 step, :389-446 trace, :794-833 framebuffer scaling) so that
+tests read like the reference's integrator tests. There is no CPU fallback: if the CUDA library is missing or no
+sm_100 device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from .scene import SceneTables, load_scene
+
+_LIB = None
+
+
+class DeviceError(RuntimeError):
+    pass
+
+
+class LookupEntry(C.Structure):
+    _fields_ = [("type_id", C.c_uint32), ("flags", C.c_uint32), ("offset", C.c_uint64)]
+
+
+class CameraDesc(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("dir", C.c_float * 3), ("up", C.c_float * 3), ("fov", C.c_float),
+                ("fov_vertical", C.c_int32), ("aspect", C.c_float), ("tmin", C.c_float), ("tmax", C.c_float)]
+
+
+class TechniqueDesc(C.Structure):
+    _fields_ = [("max_depth", C.c_int32), ("min_depth", C.c_int32), ("clamp", C.c_float), ("nee", C.c_int32)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("entities", C.c_void_p), ("n_entities", C.c_int32),
+                ("shape_lookups", C.c_void_p), ("n_shapes", C.c_int32),
+                ("shape_data", C.c_void_p), ("shape_data_bytes", C.c_uint64),
+                ("leaves", C.c_void_p), ("n_leaves", C.c_int32),
+                ("entity_per_material", C.c_void_p), ("n_materials", C.c_int32),
+                ("materials", C.c_void_p),
+                ("infinite_lights", C.c_void_p), ("n_infinite", C.c_int32),
+                ("finite_lights", C.c_void_p), ("n_finite", C.c_int32),
+                ("camera", CameraDesc), ("technique", TechniqueDesc),
+                ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3)]
+
+
+class Settings(C.Structure):
+    _fields_ = [("device", C.c_int32), ("thread_count", C.c_int32), ("spi", C.c_int32), ("frame", C.c_int32),
+                ("iter", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("seed", C.c_int32)]
+
+
+RAY_DTYPE = np.dtype([("org", "<f4", 3), ("dir", "<f4", 3), ("tmin", "<f4"), ("tmax", "<f4")])
+HIT_DTYPE = np.dtype([("ent_id", "<i4"), ("prim_id", "<i4"), ("t", "<f4"), ("u", "<f4"), ("v", "<f4")])
+
+# every symbol include/igb200.h declares (checked by tests/test_abi.py)
+SYMBOLS = ["igb200_last_error", "igb200_version", "igb200_create", "igb200_destroy", "igb200_set_scene", "igb200_resize",
+           "igb200_set_partition", "igb200_render", "igb200_framebuffer", "igb200_framebuffer_device", "igb200_clear",
+           "igb200_upload_framebuffer", "igb200_stats", "igb200_reset_stats", "igb200_kernel_times", "igb200_set_option",
+           "igb200_trace_closest", "igb200_trace_any", "igb200_bench_trace", "igb200_test_detmath"]
+
+
+def library_path() -> str:
+    return _build.OUT
+
+
+def lib():
+    """Loads libigb200.so (building it with nvcc if the in-tree binary is missing or stale)."""
+    global _LIB
+    if _LIB is None:
+        try:
+            path = _build.build()
+        except Exception as e:  # no nvcc: use the prebuilt in-tree library as is
+            path = _build.OUT
+            if not os.path.exists(path):
+                raise DeviceError(f"libigb200.so is missing and cannot be built: {e}") from e
+        L = C.CDLL(path)
+        L.igb200_last_error.restype = C.c_char_p
+        vp, ip = C.c_void_p, C.POINTER(C.c_int)
+        L.igb200_version.argtypes = [ip, ip]
+        L.igb200_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.igb200_destroy.argtypes = [vp]
+        L.igb200_set_scene.argtypes = [vp, C.POINTER(SceneDesc)]
+        L.igb200_resize.argtypes = [vp, C.c_int, C.c_int]
+        L.igb200_set_partition.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        L.igb200_render.argtypes = [vp, C.POINTER(Settings), vp, C.c_size_t]
+        L.igb200_framebuffer.argtypes = [vp, C.c_char_p, C.POINTER(C.POINTER(C.c_float))]
+        L.igb200_framebuffer_device.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+        L.igb200_clear.argtypes = [vp, C.c_char_p]
+        L.igb200_upload_framebuffer.argtypes = [vp, C.c_char_p, vp]
+        L.igb200_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+        L.igb200_reset_stats.argtypes = [vp]
+        L.igb200_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        L.igb200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+        L.igb200_trace_closest.argtypes = [vp, vp, vp, C.c_size_t, vp]
+        L.igb200_trace_any.argtypes = [vp, vp, vp, C.c_size_t, vp]
+        L.igb200_bench_trace.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.igb200_test_detmath.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise DeviceError(f"igb200 error {rc}: {lib().igb200_last_error().decode()}")
+
+
+def make_scene_desc(tables: SceneTables):
+    keep = [np.ascontiguousarray(tables.entities, np.float32), np.ascontiguousarray(tables.shape_lookups),
+            np.ascontiguousarray(tables.shape_data), np.ascontiguousarray(tables.leaves),
+            np.ascontiguousarray(tables.entity_per_material, np.int32), np.ascontiguousarray(tables.materials),
+            np.ascontiguousarray(tables.infinite_lights), np.ascontiguousarray(tables.finite_lights)]
+    d = SceneDesc()
+    d.entities, d.n_entities = keep[0].ctypes.data, keep[0].shape[0]
+    d.shape_lookups, d.n_shapes = keep[1].ctypes.data, keep[1].shape[0]
+    d.shape_data, d.shape_data_bytes = keep[2].ctypes.data, keep[2].nbytes
+    d.leaves, d.n_leaves = keep[3].ctypes.data, keep[3].shape[0]
+    d.entity_per_material, d.n_materials = keep[4].ctypes.data, keep[4].shape[0]
+    d.materials = keep[5].ctypes.data
+    d.infinite_lights, d.n_infinite = keep[6].ctypes.data, keep[6].shape[0]
+    d.finite_lights, d.n_finite = keep[7].ctypes.data, keep[7].shape[0]
+    C.memmove(C.byref(d.camera), tables.camera.tobytes(), C.sizeof(CameraDesc))
+    C.memmove(C.byref(d.technique), tables.technique.tobytes(), C.sizeof(TechniqueDesc))
+    d.bbox_min[:] = [float(x) for x in tables.bbox_min]
+    d.bbox_max[:] = [float(x) for x in tables.bbox_max]
+    return d, keep
+
+
+class B200Device:
+    """IRenderDevice over the C ABI. Method names follow src/runtime/device/IRenderDevice.h."""
+
+    def __init__(self, cuda_device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().igb200_create(cuda_device, C.byref(self._h)))
+        self._w = self._h_ = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().igb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- IRenderDevice
+    def assignScene(self, tables: SceneTables):
+        desc, keep = make_scene_desc(tables)
+        _check(lib().igb200_set_scene(self._h, C.byref(desc)))
+        del keep
+
+    def resize(self, width: int, height: int):
+        _check(lib().igb200_resize(self._h, width, height))
+        self._w, self._h_ = width, height
+
+    def framebufferWidth(self):
+        return self._w
+
+    def framebufferHeight(self):
+        return self._h_
+
+    def render(self, spi: int, width: int, height: int, iteration: int, frame: int = 0, user_seed: int = 0, rays=None):
+        st = Settings(0, 0, spi, frame, iteration, width, height, user_seed)
+        if rays is None:
+            _check(lib().igb200_render(self._h, C.byref(st), None, 0))
+            self._w, self._h_ = width, height
+        else:
+            rays = np.ascontiguousarray(rays, RAY_DTYPE)
+            _check(lib().igb200_render(self._h, C.byref(st), rays.ctypes.data, rays.shape[0]))
+            self._w, self._h_ = rays.shape[0], 1
+
+    def getFramebufferForHost(self, name: str = "") -> np.ndarray:
+        """Borrowed view (H, W, 3) of the context-owned host buffer; valid until the next resize."""
+        p = C.POINTER(C.c_float)()
+        _check(lib().igb200_framebuffer(self._h, name.encode(), C.byref(p)))
+        return np.ctypeslib.as_array(p, shape=(self._h_, self._w, 3))
+
+    def getFramebufferForDevice(self, name: str = "") -> int:
+        p = C.c_void_p()
+        _check(lib().igb200_framebuffer_device(self._h, name.encode(), C.byref(p)))
+        return int(p.value)
+
+    def clearFramebuffer(self, name: str = ""):
+        _check(lib().igb200_clear(self._h, name.encode()))
+
+    def clearAllFramebuffer(self):
+        _check(lib().igb200_clear(self._h, None))
+
+    def syncFramebufferHostToDevice(self, host_rgb: np.ndarray, name: str = ""):
+        a = np.ascontiguousarray(host_rgb, np.float32)
+        assert a.size == self._w * self._h_ * 3
+        _check(lib().igb200_upload_framebuffer(self._h, name.encode(), a.ctypes.data))
+
+    def getStatistics(self):
+        out = (C.c_uint64 * 3)()
+        ms = C.c_double()
+        _check(lib().igb200_stats(self._h, out, C.byref(ms)))
+        return {"CameraRayCount": int(out[0]), "ShadowRayCount": int(out[1]), "BounceRayCount": int(out[2]),
+                "PrimaryRays": int(out[0] + out[2]), "TotalRays": int(out[0] + out[1] + out[2]), "render_ms": ms.value}
+
+    def resetStatistics(self):
+        _check(lib().igb200_reset_stats(self._h))
+
+    # -- device-specific
+    def setPartition(self, rank: int, world: int, tile: int = 32):
+        _check(lib().igb200_set_partition(self._h, rank, world, tile))
+
+    def setOption(self, name: str, value: int):
+        _check(lib().igb200_set_option(self._h, name.encode(), int(value)))
+
+    def kernelTimes(self):
+        ms = (C.c_double * 4)()
+        n = (C.c_uint64 * 4)()
+        _check(lib().igb200_kernel_times(self._h, ms, n))
+        names = ("generate", "traverse_primary", "shade", "traverse_secondary")
+        return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(names)}
+
+    def traceClosest(self, rays, flags=None) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        out = np.zeros(rays.shape[0], HIT_DTYPE)
+        fl = None if flags is None else np.ascontiguousarray(flags, np.uint32)
+        _check(lib().igb200_trace_closest(self._h, rays.ctypes.data, None if fl is None else fl.ctypes.data, rays.shape[0], out.ctypes.data))
+        return out
+
+    def traceAny(self, rays, flags=None) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        out = np.zeros(rays.shape[0], np.int32)
+        fl = None if flags is None else np.ascontiguousarray(flags, np.uint32)
+        _check(lib().igb200_trace_any(self._h, rays.ctypes.data, None if fl is None else fl.ctypes.data, rays.shape[0], out.ctypes.data))
+        return out
+
+    def benchTrace(self, rays, any_hit=False, repeat=10) -> float:
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        ms = C.c_double()
+        _check(lib().igb200_bench_trace(self._h, rays.ctypes.data, rays.shape[0], 1 if any_hit else 0, repeat, C.byref(ms)))
+        return ms.value
+
+    def testDetmath(self, fn: str, a, b=None) -> np.ndarray:
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(a if b is None else b, np.float32)
+        out = np.zeros_like(a)
+        _check(lib().igb200_test_detmath(self._h, {"sin": 0, "cos": 1, "acos": 2, "atan2": 3}[fn], a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size))
+        return out
+
+
+def recommend_spi(width: int, height: int, gpu: bool = True) -> int:
+    """Runtime.cpp:71-79: the "best case" was measured with a 1000 x 1000 film."""
+    spi_f = 8 if gpu else 2
+    spi = int(min(64, max(1.0, np.ceil(spi_f / ((width / 1000.0) * (height / 1000.0))))))
+    return spi
+
+
+class Runtime:
+    """The slice of IG::Runtime that drives the device: load, step, trace, framebuffer (sum / iterations)."""
+
+    def __init__(self, scene, width=None, height=None, spi=0, seed=0, cuda_device=0, max_depth=None, device=None):
+        self.tables = scene if isinstance(scene, SceneTables) else load_scene(scene, width, height, max_depth)
+        self.width = int(width if width is not None else self.tables.film_size[0])
+        self.height = int(height if height is not None else self.tables.film_size[1])
+        self.spi = int(spi) if spi and spi > 0 else recommend_spi(self.width, self.height, True)
+        self.seed = seed
+        self.device = device or B200Device(cuda_device)
+        self.device.assignScene(self.tables)
+        self.device.resize(self.width, self.height)
+        self.IterationCount = 0
+        self.SampleCount = 0
+        self.FrameCount = 0
+
+    def close(self):
+        self.device.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def step(self):
+        # Runtime::stepVariant, Runtime.cpp:366-387
+        self.device.render(self.spi, self.width, self.height, self.IterationCount, self.FrameCount, self.seed)
+        self.IterationCount += 1
+        self.SampleCount += self.spi
+
+    def trace(self, rays) -> np.ndarray:
+        # Runtime::trace, Runtime.cpp:389-446: spi 1, film = rays x 1, returns radiance per ray
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        self.device.clearAllFramebuffer() if self.device.framebufferWidth() else None
+        self.device.render(1, rays.shape[0], 1, self.IterationCount, self.FrameCount, self.seed, rays=rays)
+        self.IterationCount += 1
+        return self.device.getFramebufferForHost().reshape(-1, 3).copy()
+
+    def reset(self):
+        self.device.clearAllFramebuffer()
+        self.IterationCount = 0
+        self.SampleCount = 0
+
+    def getFramebufferForHost(self) -> np.ndarray:
+        return self.device.getFramebufferForHost()
+
+    def image(self) -> np.ndarray:
+        """Framebuffer scaled by 1 / iterations, as Runtime::saveFramebuffer does (Runtime.cpp:808)."""
+        return self.device.getFramebufferForHost() / max(1, self.IterationCount)

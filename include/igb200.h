@@ -1,0 +1,182 @@
+/* igb200.h -- C ABI of the B200-native render device for the Ignis `path` hot path.
+ *
+ * This is the drop-in boundary: the reference's device is a C++ plugin
+ * (`ig_get_interface()` -> IDeviceInterface -> IRenderDevice, src/device/Interface.cpp:70-76,
+ * src/runtime/device/IRenderDevice.h:14-81). A plugin shim (`B200Device : IRenderDevice`,
+ * ignis_b200/csrc/b200_device.h) forwards each IRenderDevice method to one entry point below;
+ * everything else in this repository (Python harness, tests, bench) calls the same entry points.
+ *
+ * Conventions: every function returns 0 on success and a negative code on failure, with a message available from
+ * igb200_last_error() (the reference logs and returns false/nullptr, src/device/Device.cpp:303-306). Calls are
+ * synchronous and not thread-safe per context (all IRenderDevice calls come from the runtime's caller thread,
+ * src/device/Device.cpp:1632). The caller owns every input buffer (they may be freed after the call returns);
+ * the context owns every output buffer. Plain pointers and sizes only.
+ */
+#ifndef IGB200_H
+#define IGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGB200_VERSION_MAJOR 0
+#define IGB200_VERSION_MINOR 3 /* must match the runtime's Build::getVersion(): DeviceManager.cpp:180-194 */
+
+typedef struct igb200_ctx igb200_ctx;
+
+/* ---- binary tables, exactly as the reference runtime produces them --------------------------------------- */
+
+/* DynTable lookup entry: src/runtime/table/DynTable.h:6-10, src/artic/driver/data.art:1-5 */
+typedef struct igb200_lookup_entry {
+    uint32_t type_id; /* shape provider: IGB200_SHAPE_* */
+    uint32_t flags;
+    uint64_t offset;  /* byte offset of the entry inside the dyn-table data blob */
+} igb200_lookup_entry;
+
+/* Scene-BVH leaf `EntityLeaf1`: src/artic/traversal/bvh.art:52-61, writer src/runtime/bvh/SceneBVHAdapter.h:68-100.
+ * The device rebuilds its own BVH8, so user1/user2 (offset of the reference's pre-baked prim BVH) are ignored. */
+typedef struct igb200_entity_leaf {
+    float    min[3];
+    int32_t  entity_id; /* bit 31 = last-in-leaf marker in the reference; masked off here */
+    float    max[3];
+    int32_t  shape_id;
+    float    local[12]; /* world -> local 3x4, column major */
+    uint32_t flags;     /* visibility: 1 camera, 2 light, 4 bounce, 8 shadow (LoaderEntity.cpp:122-131) */
+    int32_t  mat_id;
+    int32_t  user1, user2;
+} igb200_entity_leaf;
+
+enum { IGB200_SHAPE_TRIMESH = 0, IGB200_SHAPE_SPHERE = 1 };
+
+/* ---- descriptors: the arguments of the constructor calls in the reference's generated stage shaders ------- */
+
+enum { IGB200_BSDF_DIFFUSE = 0,    /* make_diffuse_bsdf(surf, 0, kd) -> make_lambertian_bsdf  (bsdf/diffuse.art:2-12,55-61) */
+       IGB200_BSDF_DIELECTRIC = 1  /* make_dielectric_bsdf(..., delta, thin=false) -> make_pure_dielectric_bsdf (bsdf/dielectric.art:15-37) */ };
+
+typedef struct igb200_material {
+    int32_t bsdf;     /* IGB200_BSDF_* */
+    int32_t light_id; /* finite-light index if the entity is an area emitter (make_emissive_material), else -1 */
+    float   p[14];    /* DIFFUSE: kd rgb | DIELECTRIC: ext_ior, int_ior, ks rgb, kt rgb */
+} igb200_material;
+
+enum { IGB200_LIGHT_ENV_CONST = 0,  /* make_environment_light (constant radiance), light/env.art:75-100,161-164 */
+       IGB200_LIGHT_POINT = 1,      /* make_point_light, light/point.art:1-18 */
+       IGB200_LIGHT_PLANE_AREA = 2, /* make_area_light(make_plane_area_emitter), light/area.art:10-43,124-258 */
+       IGB200_LIGHT_SHAPE_AREA = 3  /* make_area_light(make_shape_area_emitter), light/area.art:62-107 */ };
+
+typedef struct igb200_light {
+    int32_t type;      /* IGB200_LIGHT_* */
+    int32_t entity_id; /* area lights: the emissive entity */
+    float   p[30];     /* ENV_CONST: radiance rgb | POINT: position xyz, intensity rgb |
+                          PLANE_AREA: origin, x_axis, y_axis, normal (3 each), area, t0..t3 (2 each), radiance rgb |
+                          SHAPE_AREA: radiance rgb */
+} igb200_light;
+
+/* make_perspective_camera(eye, dir, up, compute_scale_from_{h,v}fov(fov, aspect), w, h, tmin, tmax):
+ * src/runtime/camera/PerspectiveCamera.cpp:26-67, src/artic/camera/perspective.art:2-42 */
+typedef struct igb200_camera {
+    float   eye[3], dir[3], up[3];
+    float   fov;          /* radians, as printed into the shader text */
+    int32_t fov_vertical; /* 0: horizontal fov */
+    float   aspect;       /* <= 0: settings.width / settings.height */
+    float   tmin, tmax;   /* near / far clip */
+} igb200_camera;
+
+/* make_path_renderer(max_depth, min_depth, light_selector(uniform), aovs(none), clamp, nee): PathTechnique.cpp:35-79 */
+typedef struct igb200_technique {
+    int32_t max_depth, min_depth;
+    float   clamp;
+    int32_t nee;
+} igb200_technique;
+
+/* What IRenderDevice::assignScene receives (SceneDatabase + entity_per_material, IRenderDevice.h:22-28,
+ * src/runtime/table/SceneDatabase.h:8-21) plus the per-stage descriptors. */
+typedef struct igb200_scene_desc {
+    const float*               entities;      /* FixTables["entities"]: n_entities x 36 f32 (LoaderEntity.cpp:150-162) */
+    int32_t                    n_entities;
+    const igb200_lookup_entry* shape_lookups; /* DynTables["shapes"] lookups */
+    int32_t                    n_shapes;
+    const uint8_t*             shape_data;    /* DynTables["shapes"] data (TriMeshProvider.cpp:575-596, SphereProvider.cpp:42-47) */
+    uint64_t                   shape_data_bytes;
+    const igb200_entity_leaf*  leaves;        /* SceneBVHs[*].Leaves of all providers, concatenated */
+    int32_t                    n_leaves;
+    const int32_t*             entity_per_material; /* Runtime.cpp:306-310 */
+    int32_t                    n_materials;
+    const igb200_material*     materials;     /* n_materials */
+    const igb200_light*        infinite_lights;
+    int32_t                    n_infinite;
+    const igb200_light*        finite_lights;
+    int32_t                    n_finite;
+    igb200_camera              camera;
+    igb200_technique           technique;
+    float                      bbox_min[3], bbox_max[3]; /* __scene_bbox_lower / upper */
+} igb200_scene_desc;
+
+/* `Settings`, src/artic/driver/settings.art:2-11, filled by the device at src/device/Device.cpp:384-397 */
+typedef struct igb200_settings {
+    int32_t device, thread_count, spi, frame, iter, width, height, seed;
+} igb200_settings;
+
+/* `StreamRay`, src/artic/traversal/ray.art:2-7 */
+typedef struct igb200_ray {
+    float org[3], dir[3], tmin, tmax;
+} igb200_ray;
+
+typedef struct igb200_hit {
+    int32_t ent_id, prim_id; /* -1: no hit */
+    float   t, u, v;
+} igb200_hit;
+
+/* ---- entry points (each names the IRenderDevice / Device.cpp member it stands for) ------------------------ */
+
+const char* igb200_last_error(void);
+int igb200_version(int* major, int* minor);                       /* IDeviceInterface::getVersion, Interface.cpp:24-27 */
+
+int igb200_create(int cuda_device, igb200_ctx** out);             /* IDeviceInterface::createRenderDevice, Interface.cpp:34-57 */
+int igb200_destroy(igb200_ctx* ctx);                              /* IRenderDevice::~IRenderDevice */
+
+int igb200_set_scene(igb200_ctx* ctx, const igb200_scene_desc* scene); /* IRenderDevice::assignScene, Device.cpp:1667-1670 */
+int igb200_resize(igb200_ctx* ctx, int width, int height);        /* IRenderDevice::resize, Device.cpp:1692-1695 */
+
+/* Multi-GPU: this context renders only the tile_size x tile_size framebuffer tiles t with t % world == rank
+ * (tiles enumerated row-major). No reference counterpart (the reference is single-device, Device.cpp:1632). */
+int igb200_set_partition(igb200_ctx* ctx, int rank, int world, int tile_size);
+
+/* One iteration: IRenderDevice::render, Device.cpp:1672-1682. `rays` non-null selects the list emitter of igtrace
+ * (Runtime::trace, Runtime.cpp:389-446): width = n_rays, height = 1. Accumulates into the device framebuffer. */
+int igb200_render(igb200_ctx* ctx, const igb200_settings* settings, const igb200_ray* rays, size_t n_rays);
+
+/* IRenderDevice::getFramebufferForHost, Device.cpp:1419-1451: copies the device framebuffer into a context-owned
+ * pinned host buffer (RGB f32, width*height*3, row-major, sum over iterations). aov NULL/""/"Color" = main image. */
+int igb200_framebuffer(igb200_ctx* ctx, const char* aov, float** host_ptr);
+int igb200_framebuffer_device(igb200_ctx* ctx, const char* aov, float** device_ptr); /* getFramebufferForDevice */
+int igb200_clear(igb200_ctx* ctx, const char* aov_or_null);       /* clearFramebuffer / clearAllFramebuffer */
+int igb200_upload_framebuffer(igb200_ctx* ctx, const char* aov, const float* host_rgb); /* syncFramebufferHostToDevice */
+
+/* IRenderDevice::getStatistics (ray counters of src/runtime/Statistics.h:57-64): out = {camera, shadow, bounce}
+ * rays since creation; render_ms = device time spent in igb200_render since creation. */
+int igb200_stats(igb200_ctx* ctx, uint64_t out[3], double* render_ms);
+int igb200_reset_stats(igb200_ctx* ctx);
+
+/* Time of the dominant kernel classes inside igb200_render since the last reset, measured with CUDA events on the
+ * render stream: out_ms = {generate, traverse_primary, shade, traverse_secondary}, out_launches likewise. */
+int igb200_kernel_times(igb200_ctx* ctx, double out_ms[4], uint64_t out_launches[4]);
+int igb200_set_option(igb200_ctx* ctx, const char* name, int64_t value); /* "capacity", "profile_kernels", ... */
+
+/* Parity / micro-benchmark hooks on the traversal kernels: closest hit and any hit for a host ray list. flags may be
+ * NULL (camera rays / shadow rays respectively). */
+int igb200_trace_closest(igb200_ctx* ctx, const igb200_ray* rays, const uint32_t* flags, size_t n, igb200_hit* out);
+int igb200_trace_any(igb200_ctx* ctx, const igb200_ray* rays, const uint32_t* flags, size_t n, int32_t* occluded);
+/* Same, device-resident rays (n repeated `repeat` times), returns average milliseconds per pass. */
+int igb200_bench_trace(igb200_ctx* ctx, const igb200_ray* rays, size_t n, int any_hit, int repeat, double* ms_per_pass);
+
+/* Test hook: evaluates the device's deterministic transcendental (0 sin, 1 cos, 2 acos, 3 atan2(a,b)) on the GPU. */
+int igb200_test_detmath(igb200_ctx* ctx, int fn, const float* a, const float* b, float* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGB200_H */
