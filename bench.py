@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s of the path-tracing hot path on BASELINE.json's headline workload.
+
+Workload (BASELINE.json configs[1]): scenes/diamond_scene.json forced to 1920x1080, `path` integrator, max_depth 64,
+spi 4, seed 0. One STEP = one `IRenderDevice::render()` call = one iteration = 4 samples per pixel over the whole
+frame (8 294 400 camera rays and every bounce / shadow ray they spawn); 16 steps = the 64 spp of the reference's
+own harness (scripts/Benchmark.py). Mrays/s = (camera + bounce + shadow rays) / time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            this repository's CUDA device
+    python bench.py --impl reference [...]                         CPU restatement of the reference's CPU device
+
+For N > 1 it is launched by torchrun (one rank per GPU): the framebuffer is split into 32x32 tiles dealt round-robin
+to the ranks (scene replicated, no data-path collective), and the accumulation buffers are summed onto rank 0 with
+one NCCL reduce at the end of the K steps (inside the timed region). Total work is fixed => "scaling": "strong".
+
+Timed regions: `value` = K steps issued back to back with the scene resident in HBM, timed with CUDA events on the
+device's render stream between barriers, max over ranks. `e2e` = the same K steps through the public host API
+(B200Device.render + getFramebufferForHost over the C ABI): every step uploads its Settings and reads the whole
+accumulated framebuffer back into pinned host memory (after the NCCL reduce for N > 1).
+
+The oracle (oracle/) is executed here only for `cpu_baseline` and `--impl reference`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SCENE = "scenes/diamond_scene.json"
+# algorithmic bytes per unit of work of the wavefront hand-off
+B_PRIMARY, B_SHADOW, B_SPLAT = 216, 108, 24
+# the same figure split by pipeline stage (DESIGN.md "Algorithmic bytes")
+B_STAGE = {"generate": 68, "traverse_primary": 60, "shade_read": 88, "shade_bounce_write": 68, "shade_shadow_write": 56,
+           "traverse_secondary": 52}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed region runs (NVML)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv = self._nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake", nv.nvmlClocksEventReasonApplicationsClocksSetting: "applications_clocks"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def algorithmic_bytes(st):
+    return B_PRIMARY * (st["CameraRayCount"] + st["BounceRayCount"]) + B_SHADOW * st["ShadowRayCount"] + B_SPLAT * st["Splats"]
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle)
+def build_timing_oracle():
+    """The oracle compiled the way the reference compiles its CPU device (CMakeLists.txt:93-98: -O3 -march=native
+    -ffast-math), on this box. Falls back to the parity build (-O2, no contraction) if that fails."""
+    from oracle import oracle as o
+    src = os.path.join(ROOT, "oracle", "oracle.cpp")
+    # -march=native code must never travel between machines: always built on the spot, outside the tree
+    import tempfile
+    out = os.path.join(tempfile.gettempdir(), f"igb200_oracle_native_{os.getuid()}_{os.getpid()}.so")
+    try:
+        if True:
+            subprocess.run(["g++", "-O3", "-march=native", "-ffast-math", "-std=c++17", "-fPIC", "-shared", "-o", out, src, "-lpthread"],
+                           check=True, capture_output=True)
+        o._LIB = None
+        real_build = o.build
+        o.build = lambda force=False: out
+        try:
+            o.lib()
+        finally:
+            o.build = real_build
+        return "-O3 -march=native -ffast-math"
+    except Exception:
+        o._LIB = None
+        o.lib()
+        return "-O2 -ffp-contract=off (parity build)"
+
+
+def cpu_render_steps(tables, w, h, spi, steps, first_iter=0):
+    """Runs `steps` full-frame iterations of the oracle on all host threads; returns (seconds, rays)."""
+    from oracle.oracle import Oracle
+    o = Oracle(tables)
+    fb = np.zeros((h, w, 3), np.float32)
+    t0 = time.perf_counter()
+    for it in range(steps):
+        o.render(w, h, spi=spi, iteration=first_iter + it, fb=fb)
+    dt = time.perf_counter() - t0
+    rays = int(o.counters.sum())
+    o.close()
+    return dt, rays
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from ignis_b200.scene import load_scene
+    from oracle import oracle as o
+    flags = build_timing_oracle()
+    cores = int(o.lib().igo_hardware_threads())
+    tables = load_scene(os.path.join(ROOT, SCENE), args.width, args.height)
+    w, h, spi = args.width, args.height, args.spi
+    if args.warmup > 0:
+        cpu_render_steps(tables, w, h, spi, args.warmup)
+    dt, rays = cpu_render_steps(tables, w, h, spi, args.steps, first_iter=args.warmup)
+    value = rays / dt / 1e6
+    line = {"impl": "reference", "metric": "Mrays/s (camera+bounce+shadow) @1920x1080 diamond_scene path", "value": value, "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} full-frame iterations ({w}x{h}, spi {spi}) of the CPU restatement of the reference's CPU device "
+                                       f"(oracle/oracle.cpp, scalar, 16x16 tiles, {cores} threads, built {flags}); the reference itself needs the AnyDSL JIT and cannot be built"},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "msamples_per_s": w * h * spi * args.steps / dt / 1e6}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world):
+    return {"workload": f"{SCENE} {args.width}x{args.height}, path integrator max_depth 64, spi {args.spi}, seed 0; 1 step = 1 render() iteration "
+                        f"({args.spi} spp, {args.width * args.height * args.spi} camera rays); 16 steps = 64 spp (BASELINE.json configs[1])",
+            "spi": args.spi, "width": args.width, "height": args.height,
+            "parallelism": f"framebuffer tiles 32x32 round-robin over {world} GPU(s), scene replicated, one NCCL reduce of the accumulation buffer",
+            "l2": "no flush needed: every step streams its ray queues through HBM (> 800 MB per step per GPU at N=1, L2 is 126 MB)"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from ignis_b200.device import Runtime
+    from ignis_b200.scene import load_scene
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w, h, spi = args.width, args.height, args.spi
+    tables = load_scene(os.path.join(ROOT, SCENE), w, h)
+    rt = Runtime(tables, w, h, spi=spi, seed=0, cuda_device=local_rank)
+    dev = rt.device
+    dev.setPartition(rank, world, 32)
+    stream = torch.cuda.ExternalStream(dev.stream(), device=torch.device("cuda", local_rank))
+
+    class _FB:  # device framebuffer as a torch tensor (no copy)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    fb_t = torch.as_tensor(_FB(dev.getFramebufferForDevice(), w * h * 3), device=torch.device("cuda", local_rank))
+    scratch = torch.empty_like(fb_t) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_to_root():
+        # disjoint tile support: the sum is a gather of the per-rank tiles
+        with torch.cuda.stream(stream):
+            scratch.copy_(fb_t)
+            dist.reduce(scratch, dst=0, op=dist.ReduceOp.SUM)
+
+    # ---- warm-up (also sizes the ray queues and warms NCCL)
+    for _ in range(max(args.warmup, 0)):
+        rt.step()
+    if world > 1:
+        reduce_to_root()
+    barrier()
+
+    def timed(e2e: bool):
+        rt.reset()
+        dev.resetStatistics()
+        rt.IterationCount = 0
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        with ClockSampler(local_rank) as clk:
+            ev0.record(stream)
+            host = None
+            for _ in range(args.steps):
+                rt.step()
+                if e2e:
+                    if world > 1:
+                        reduce_to_root()
+                        if rank == 0:
+                            with torch.cuda.stream(stream):
+                                host_t.copy_(scratch, non_blocking=True)
+                            stream.synchronize()
+                    else:
+                        host = dev.getFramebufferForHost()   # D2H of the accumulated frame into pinned memory
+            if not e2e and world > 1:
+                reduce_to_root()
+            ev1.record(stream)
+            stream.synchronize()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        dev_ms = ev0.elapsed_time(ev1)
+        ms = max(dev_ms, 0.0)
+        st = dev.getStatistics()
+        vals = torch.tensor([ms, wall_ms, st["CameraRayCount"], st["ShadowRayCount"], st["BounceRayCount"], st["Splats"], st["KernelLaunches"]],
+                            dtype=torch.float64, device="cuda")
+        if world > 1:
+            mx = vals.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = vals.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms, wall_ms = float(mx[0]), float(mx[1])
+            tot = {"CameraRayCount": int(sm[2]), "ShadowRayCount": int(sm[3]), "BounceRayCount": int(sm[4]), "Splats": int(sm[5]), "KernelLaunches": int(sm[6])}
+        else:
+            tot = {k: st[k] for k in ("CameraRayCount", "ShadowRayCount", "BounceRayCount", "Splats", "KernelLaunches")}
+        tot["TotalRays"] = tot["CameraRayCount"] + tot["ShadowRayCount"] + tot["BounceRayCount"]
+        return ms, wall_ms, tot, clk.summary(), host
+
+    host_t = torch.empty(w * h * 3, dtype=torch.float32, pin_memory=True) if (world > 1 and rank == 0) else None
+
+    ms, wall_ms, tot, clocks, _ = timed(e2e=False)
+    ms_e, wall_e, tot_e, _, host = timed(e2e=True)
+
+    # ---- per-kernel-class timing (separate pass: each launch bracketed by CUDA events on the render stream)
+    kt = None
+    if world == 1:
+        rt.reset()
+        dev.resetStatistics()
+        dev.setOption("profile_kernels", 1)
+        for _ in range(min(args.steps, 4)):
+            rt.step()
+        kt = dev.kernelTimes()
+        kst = dev.getStatistics()
+        dev.setOption("profile_kernels", 0)
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        value = tot["TotalRays"] / (ms * 1e-3) / 1e6
+        e2e_value = tot_e["TotalRays"] / (wall_e * 1e-3) / 1e6
+        line = {"metric": "Mrays/s (camera+bounce+shadow) @1920x1080 diamond_scene path", "value": value, "unit": "Mrays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+                "clocks": clocks, "gpu_launches": tot["KernelLaunches"],
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": w * h * 12,
+                        "ms_per_step": wall_e / args.steps, "timed": "host wall clock between barriers, max over ranks"},
+                "rays": tot, "msamples_per_s": w * h * spi * args.steps / (ms * 1e-3) / 1e6, "wall_ms_per_step": wall_ms / args.steps}
+        step_bytes = algorithmic_bytes(tot)
+        line["roofline_step"] = {"bound": "hbm", "achieved": step_bytes / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
+                                 "frac": step_bytes / (ms * 1e-3) / 1e9 / world / peak, "traffic": None,
+                                 "what": f"whole wavefront step per GPU: {B_PRIMARY} B x primary + {B_SHADOW} B x shadow + {B_SPLAT} B x splat (SURVEY.md 8d), peak {peak_src}"}
+        if kt is not None:
+            prim = kst["CameraRayCount"] + kst["BounceRayCount"]
+            per_class_bytes = {"generate": B_STAGE["generate"] * kst["CameraRayCount"],
+                               "traverse_primary": B_STAGE["traverse_primary"] * prim,
+                               "shade": B_STAGE["shade_read"] * prim + B_STAGE["shade_bounce_write"] * kst["BounceRayCount"] + B_STAGE["shade_shadow_write"] * kst["ShadowRayCount"],
+                               "traverse_secondary": B_STAGE["traverse_secondary"] * kst["ShadowRayCount"] + B_SPLAT * kst["Splats"]}
+            total_k = sum(v["ms"] for v in kt.values()) or 1.0
+            dom = max(kt, key=lambda k: kt[k]["ms"])
+            n_l = max(kt[dom]["launches"], 1)
+            avg_ms = kt[dom]["ms"] / n_l
+            ach = per_class_bytes[dom] / n_l / (avg_ms * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                "kernel": dom, "avg_launch_ms": avg_ms, "launches": n_l, "share_of_step": kt[dom]["ms"] / total_k,
+                                "algorithmic_bytes_per_launch": per_class_bytes[dom] / n_l, "peak_source": peak_src}
+            line["kernel_ms"] = {k: {"ms": v["ms"], "launches": v["launches"], "share": v["ms"] / total_k} for k, v in kt.items()}
+        if host is not None:
+            line["image_mean"] = float(np.asarray(host).mean() / args.steps)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as o
+        flags = build_timing_oracle()
+        cores = int(o.lib().igo_hardware_threads())
+        n_it = args.cpu_iters
+        dt, rays = cpu_render_steps(tables, w, h, spi, n_it)
+        line["cpu_baseline"] = {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                                "sample": f"{n_it} full-frame iteration(s) of the same workload ({w}x{h}, spi {spi}; {rays} rays, {dt:.1f} s) on {cores} threads, "
+                                          f"CPU restatement of the reference's CPU device built {flags}"}
+    if rank == 0:
+        print(json.dumps(line))
+    rt.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--spi", type=int, default=4)
+    ap.add_argument("--cpu-iters", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

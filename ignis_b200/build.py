@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libigb200.so")
 SOURCES = ["api.cu"]
-DEPS = ["api.cu", "kernels.cuh", "device_math.cuh", "bvh8.h", "../../include/igb200.h", "../build.py"]
+DEPS = ["api.cu", "wavefront.cuh", "traverse.cuh", "shade.cuh", "types.cuh", "device_math.cuh", "bvh8.h", "../../include/igb200.h", "../build.py"]
 
 
 def nvcc_path() -> str:
@@ -36,9 +36,14 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    global OUT
+    if os.environ.get("IGB200_STEP_STATS"):   # diagnostics build: counts BVH visits per ray (slow), separate binary
+        OUT = os.path.join(HERE, "libigb200_stats.so")
+        force = force or not os.path.exists(OUT)
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc_path(), *flags(["-Xptxas", "-v"] if verbose else []), "-shared", "-o", OUT,
+    extra = (["-Xptxas", "-v"] if verbose else []) + (["-DIGB_STEP_STATS"] if os.environ.get("IGB200_STEP_STATS") else [])
+    cmd = [nvcc_path(), *flags(extra), "-shared", "-o", OUT,
            *[os.path.join(SRC, s) for s in SOURCES]]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -7,7 +7,7 @@
 // 128-byte lines per node; the child encoding is this device's own:
 //   child > 0 : inner node, index child-1 (relative to the tree's first node)
 //   child < 0 : leaf, r = -child-1, first primitive slot = r >> 2, primitive count = (r & 3) + 1
-//   child = 0 : empty lane (children are packed to the front)
+//   child = 0 : empty lane (children are packed to the front); its box is inverted with finite bounds (+-FLT_MAX)
 #pragma once
 
 #include <algorithm>
@@ -81,7 +81,8 @@ struct Builder2 {
         nodes[id].box = bb;
         const int n = e - b;
         auto make_leaf = [&]() { nodes[id].first = b; nodes[id].count = n; nodes[id].left = nodes[id].right = -1; return id; };
-        if (n <= 1) return make_leaf();
+        // SIMT traversal pays a fixed price per visit, so leaves are filled up to max_leaf primitives (no SAH leaf test)
+        if (n <= max_leaf) return make_leaf();
         // binned SAH over the three axes
         constexpr int NB = 16;
         float best_cost = std::numeric_limits<float>::infinity();
@@ -110,11 +111,8 @@ struct Builder2 {
         }
         int mid;
         if (best_axis < 0) {
-            if (n <= max_leaf) return make_leaf();
             mid = (b + e) / 2;  // identical centroids: split in input order
         } else {
-            const float leaf_cost = bb.half_area() * (float)n;
-            if (n <= max_leaf && !(best_cost + bb.half_area() * 0.5f < leaf_cost)) return make_leaf();
             const float lo = cb.lo[best_axis], scale = NB / (cb.hi[best_axis] - cb.lo[best_axis]);
             auto it = std::partition(order.begin() + b, order.begin() + e, [&](int p) {
                 int k = (int)((cen[3 * p + best_axis] - lo) * scale);
@@ -142,7 +140,9 @@ inline Bvh8 build_bvh8(const std::vector<Box3>& boxes, int max_leaf) {
     detail::Builder2 b2(boxes, max_leaf);
     out.order = b2.order;
     const auto& n2 = b2.nodes;
-    const float inf = std::numeric_limits<float>::infinity();
+    // empty child lanes hold an inverted box with FINITE bounds: the slab test then misses without a `child != 0`
+    // check and without 0 * inf / inf - inf NaNs (traverse.cuh)
+    const float inf = std::numeric_limits<float>::max();
 
     struct Work { int n2; int n8; int depth; };
     std::vector<Work> stack;

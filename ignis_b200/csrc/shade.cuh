@@ -1,0 +1,368 @@
+// Shading of one primary-queue record: surface element, emission, next-event estimation, BSDF sample, roulette.
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "types.cuh"
+
+namespace igb {
+
+struct Surf { bool is_entering; V3 point, face_normal; float area, inv_area; float pu, pv; M33 local; };
+struct Pdf { float value; int measure; };   // 0 solid, 1 area, 2 delta  (driver/pdf.art:16-46)
+__device__ __forceinline__ float pdf_as_solid(Pdf p, float cos, float dist2) { return p.measure == 1 ? p.value * dist2 / cos : (p.measure == 2 ? 1.0f : p.value); }
+
+__device__ __forceinline__ C3 cmul(C3 a, C3 b) { return c3(a.r * b.r, a.g * b.g, a.b * b.b); }
+__device__ __forceinline__ C3 cmulf(C3 a, float f) { return c3(a.r * f, a.g * f, a.b * f); }
+__device__ __forceinline__ C3 cadd(C3 a, C3 b) { return c3(a.r + b.r, a.g + b.g, a.b + b.b); }
+__device__ __forceinline__ C3 handle_color(const DevScene& sc, C3 c) { return sc.clamp_value > 0 ? c3(fminf(c.r, sc.clamp_value), fminf(c.g, sc.clamp_value), fminf(c.b, sc.clamp_value)) : c; }
+
+// core/triangle.art:12-43
+__device__ __forceinline__ void make_triangle(V3 v0, V3 v1, V3 v2, V3& n, float& area) {
+    const V3 e1 = v2 - v0, e2 = v0 - v1, e3 = v1 - v2;
+    const float x12 = e1.z * e2.y, y12 = e1.x * e2.z, z12 = e1.y * e2.x;
+    const float x23 = e2.z * e3.y, y23 = e2.x * e3.z, z23 = e2.y * e3.x;
+    const V3 c12 = v3(e1.y * e2.z - x12, e1.z * e2.x - y12, e1.x * e2.y - z12);
+    const V3 c23 = v3(e2.y * e3.z - x23, e2.z * e3.x - y23, e2.x * e3.y - z23);
+    const V3 nn = v3(fabsf(x12) < fabsf(x23) ? c12.x : c23.x, fabsf(y12) < fabsf(y23) ? c12.y : c23.y, fabsf(z12) < fabsf(z23) ? c12.z : c23.z);
+    const float l = len(nn);
+    n = mulf(nn, 1 / l); area = l / 2;
+}
+
+__device__ __forceinline__ V3 f4v(float4 f) { return v3(f.x, f.y, f.z); }
+
+// shapes/trimesh.art:14-40 (for_point = false) and :41-68 (for_point = true)
+__device__ __forceinline__ void trimesh_surface(const DevScene& sc, int ent, int shape, int prim, float u, float v, bool for_point,
+                                                V3 rorg, V3 rdir, float dist, Surf& s) {
+    const int4 si = __ldg(sc.shape_info + 2 * shape);
+    const int4 idx = __ldg(reinterpret_cast<const int4*>(sc.blob + si.w + prim));
+    const float4* E = sc.ent_shade + (size_t)ent * 6;
+    const float4 g0 = ldg4(E), g1 = ldg4(E + 1), g2 = ldg4(E + 2), n0 = ldg4(E + 3), n1 = ldg4(E + 4), n2 = ldg4(E + 5);
+    const V3 p0 = xform_point(g0, g1, g2, f4v(ldg4(sc.blob + si.y + idx.x)));
+    const V3 p1 = xform_point(g0, g1, g2, f4v(ldg4(sc.blob + si.y + idx.y)));
+    const V3 p2 = xform_point(g0, g1, g2, f4v(ldg4(sc.blob + si.y + idx.z)));
+    V3 fn; float area;
+    make_triangle(p0, p1, p2, fn, area);
+    const V3 ln = lerp2(f4v(ldg4(sc.blob + si.z + idx.x)), f4v(ldg4(sc.blob + si.z + idx.y)), f4v(ldg4(sc.blob + si.z + idx.z)), u, v);
+    const V3 normal = normalize(v3(dot(v3(n0.x, n0.y, n0.z), ln), dot(v3(n1.x, n1.y, n1.z), ln), dot(v3(n2.x, n2.y, n2.z), ln)));
+    s.area = area; s.inv_area = safe_div(1, area); s.pu = u; s.pv = v;
+    if (for_point) {
+        s.is_entering = true;
+        s.point = lerp2(p0, p1, p2, u, v);
+        s.face_normal = fn;
+        s.local = make_orthonormal(normal);
+    } else {
+        const bool entering = dot(rdir, fn) <= 0;
+        s.is_entering = entering;
+        s.point = rorg + mulf(rdir, dist);
+        s.face_normal = entering ? fn : neg(fn);
+        s.local = make_orthonormal(entering ? normal : neg(normal));
+    }
+}
+
+// core/sampling.art:13-21,62-69
+__device__ __forceinline__ void sample_cosine_hemisphere(float u, float v, V3& dir, float& pdf) {
+    const float c = safe_sqrt(v), s = safe_sqrt(1 - v);
+    const float phi = 2 * IGB_FLT_PI * u;
+    float sn, cs; dm_sincosf(phi, &sn, &cs);
+    dir = v3(s * cs, s * sn, c); pdf = c / IGB_FLT_PI;
+}
+// core/warp.art:63-91
+__device__ __forceinline__ V3 equal_area_square_to_sphere(float px, float py) {
+    const float u = 2 * px - 1, v = 2 * py - 1;
+    const float au = fabsf(u), av = fabsf(v);
+    const float sd = 1 - (au + av);
+    const float d = fabsf(sd);
+    const float r = 1 - d;
+    const float phi = (r == 0 ? 1.0f : (av - au) / r + 1) * IGB_FLT_PI / 4;
+    const float cosTheta = copysignf(1 - r * r, sd);
+    const float sinTheta = safe_sqrt(2 - r * r) * r;
+    float sn, cs; dm_sincosf(phi, &sn, &cs);
+    return v3(copysignf(cs, u) * sinTheta, copysignf(sn, v) * sinTheta, cosTheta);
+}
+
+// core/fresnel.art:7-27
+__device__ __forceinline__ bool fresnel(float eta, float cos_i, float& cos_t_out, float& factor) {
+    const float eta2 = cos_i < 0 ? 1 / eta : eta;
+    const float cos2_t = 1 - (1 - cos_i * cos_i) * eta2 * eta2;
+    if (cos2_t <= 0.0f) return false;
+    const float cos_t = sqrtf(cos2_t);
+    cos_t_out = cos_i < 0 ? -cos_t : cos_t;
+    const float ci = fabsf(cos_i);
+    const float R_s = safe_div(eta2 * ci - cos_t, eta2 * ci + cos_t);
+    const float R_p = safe_div(ci - eta2 * cos_t, ci + eta2 * cos_t);
+    factor = clampf((R_s * R_s + R_p * R_p) * 0.5f, 0, 1);
+    return true;
+}
+
+// light/area.art:124-190: spherical rectangle (Urena et al. 2013)
+struct PlaneEm { V3 origin, normal, ex, ey; float area, inv_area, width, height; };
+struct SQ { V3 o, n; float x0, y0, z0, x1, y1, b0, b1, k, s; };
+__device__ __forceinline__ PlaneEm load_plane(const float* L) {
+    PlaneEm e;
+    e.origin = v3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));
+    const V3 xa = v3(__ldg(L + 5), __ldg(L + 6), __ldg(L + 7)), ya = v3(__ldg(L + 8), __ldg(L + 9), __ldg(L + 10));
+    e.normal = v3(__ldg(L + 11), __ldg(L + 12), __ldg(L + 13));
+    e.area = __ldg(L + 14);
+    e.inv_area = safe_div(1, e.area);
+    e.width = len(xa); e.height = len(ya);
+    e.ex = mulf(xa, 1 / e.width); e.ey = mulf(ya, 1 / e.height);
+    return e;
+}
+__device__ __forceinline__ SQ compute_sq(const PlaneEm& e, V3 from_point) {
+    const V3 dir = e.origin - from_point;
+    const float x0 = dot(dir, e.ex), y0 = dot(dir, e.ey), z0_ = dot(dir, e.normal);
+    const float x1 = x0 + e.width, y1 = y0 + e.height;
+    const bool pos = !signbit(z0_);
+    const float z0 = pos ? -z0_ : z0_;
+    const float df[4] = {x0 - x1, y1 - y0, x1 - x0, y0 - y1};
+    const float a[4] = {y0, x1, y1, x0};
+    float nz[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float nz_ = a[i] * df[i];
+        nz[i] = nz_ / sqrtf((df[i] * df[i]) * (z0 * z0) + nz_ * nz_);
+    }
+    const float g0 = dm_acosf(clampf(-nz[0] * nz[1], -1, 1)), g1 = dm_acosf(clampf(-nz[1] * nz[2], -1, 1));
+    const float g2 = dm_acosf(clampf(-nz[2] * nz[3], -1, 1)), g3 = dm_acosf(clampf(-nz[3] * nz[0], -1, 1));
+    SQ q;
+    q.o = from_point; q.n = pos ? neg(e.normal) : e.normal;
+    q.x0 = x0; q.y0 = y0; q.z0 = z0; q.x1 = x1; q.y1 = y1;
+    q.b0 = nz[0]; q.b1 = nz[2];
+    q.k = 2 * IGB_FLT_PI - g2 - g3;
+    q.s = g0 + g1 - q.k;
+    return q;
+}
+
+struct LightSample { V3 pos, dir; C3 intensity; Pdf pdf; float cos, dist; };
+
+// light/area.art:62-107 (shape emitter over a triangle mesh entity)
+__device__ __forceinline__ void shape_emitter_sample(const DevScene& sc, int entity, float uvx, float uvy, Surf& surf, float& pdfv, float& weight) {
+    const float4* E = sc.ent_shade + (size_t)entity * 6;
+    const int shape = __float_as_int(ldg4(E + 3).w);
+    const int count = __ldg(sc.shape_info + 2 * shape + 1).y;
+    const float ux = uvx * (float)count;
+    const int f = min((int)ux, count - 1);
+    float u = ux - (float)f, v = uvy;
+    if (u + v > 1) { u = 1 - u; v = 1 - v; }
+    trimesh_surface(sc, entity, shape, f, u, v, true, v3(0, 0, 0), v3(0, 0, 0), 0, surf);
+    pdfv = surf.inv_area / (float)count;
+    weight = surf.area * (float)count;
+}
+
+__device__ __forceinline__ LightSample light_sample_direct(const DevScene& sc, const float* L, int type, Rng& rnd, const Surf& from) {
+    LightSample o;
+    if (type == 0) {          // light/env.art:84-88
+        const float u = rnd.next_f32(); const float v = rnd.next_f32();
+        const V3 dir = equal_area_square_to_sphere(u, v);
+        const float pdf = 1 / (4 * IGB_FLT_PI);
+        o.pos = from.point + mulf(dir, sc.scene_radius); o.dir = dir;
+        o.intensity = cmulf(c3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4)), 1 / pdf);
+        o.pdf.value = pdf; o.pdf.measure = 0; o.cos = 1.0f; o.dist = sc.scene_radius;
+    } else if (type == 1) {   // light/point.art:3-8
+        const V3 pos = v3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));
+        const V3 d_ = pos - from.point;
+        const float dist = len(d_);
+        o.pos = pos; o.dir = mulf(d_, safe_div(1, dist));
+        o.intensity = c3(__ldg(L + 5), __ldg(L + 6), __ldg(L + 7));
+        o.pdf.value = 1; o.pdf.measure = 1; o.cos = 1; o.dist = dist;
+    } else {                  // light/area.art:12-25
+        const float u = rnd.next_f32(); const float v = rnd.next_f32();
+        V3 to_point, to_normal; float weight; C3 radiance;
+        if (type == 2) {
+            const PlaneEm e = load_plane(L);
+            const SQ sq = compute_sq(e, from.point);
+            const float au = fma_(u, sq.s, sq.k);
+            float sn, cs; dm_sincosf(au, &sn, &cs);
+            const float fu = fma_(cs, sq.b0, -sq.b1) / sn;
+            const float cu = clampf(copysignf(1.0f, fu) / sqrtf(sum_of_prod(fu, fu, sq.b0, sq.b0)), -1, 1);
+            const float xu = clampf(-(cu * sq.z0) / sqrtf(fma_(-cu, cu, 1.0f)), sq.x0, sq.x1);
+            const float d = sqrtf(sum_of_prod(xu, xu, sq.z0, sq.z0));
+            const float h0 = sq.y0 / sqrtf(sum_of_prod(d, d, sq.y0, sq.y0));
+            const float h1 = sq.y1 / sqrtf(sum_of_prod(d, d, sq.y1, sq.y1));
+            const float hv = fma_(v, h1 - h0, h0);
+            const float hv2 = hv * hv;
+            const float yv = (hv2 < 1 - 1e-6f) ? (hv * d) / sqrtf(1 - hv2) : sq.y1;
+            to_point = sq.o + (mulf(e.ex, xu) + (mulf(e.ey, yv) + mulf(sq.n, sq.z0)));
+            to_normal = e.normal;
+            o.pdf.value = safe_div(1, sq.s); o.pdf.measure = 0;
+            weight = sq.s;
+            radiance = c3(__ldg(L + 23), __ldg(L + 24), __ldg(L + 25));
+        } else {
+            Surf to; float pdfv;
+            shape_emitter_sample(sc, __float_as_int(__ldg(L + 1)), u, v, to, pdfv, weight);
+            to_point = to.point; to_normal = to.face_normal;
+            o.pdf.value = pdfv; o.pdf.measure = 1;
+            radiance = c3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));
+        }
+        const V3 d_ = to_point - from.point;
+        const float dist = len(d_);
+        const V3 dir = mulf(d_, safe_div(1, dist));
+        o.pos = to_point; o.dir = dir;
+        o.cos = dot(dir, to_normal) * (from.is_entering ? -1.0f : 1.0f);
+        o.intensity = cmulf(radiance, weight);
+        o.dist = dist;
+    }
+    return o;
+}
+
+// Where shading puts its results: the next primary queue, the shadow queue and their counters. Records are appended
+// from inside divergent code with one atomic per coalesced group of lanes (cooperative_groups::coalesced_threads), at
+// the point where they are computed, so that nothing has to stay live until a common exit.
+struct ShadeSink {
+    PrimaryQueue nq; int* next_count;
+    ShadowQueue sq;  int* shadow_count;
+};
+__device__ __forceinline__ int coalesced_append(int* counter) {
+    const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+    int base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, (int)g.size());
+    return g.shfl(base, 0) + (int)g.thread_rank();
+}
+
+// Hit and miss shading of primary-queue record i (gpu_hit_shade / gpu_miss_shade, driver/mapping_gpu.art:123-290;
+// technique/pathtracer.art:40-228). Splats emission / environment contributions (returns how many), appends the
+// shadow ray of the next-event estimate and the continuation ray, if any.
+__device__ __forceinline__ int shade_record(const DevScene& sc, const RenderParams& rp, const PrimaryQueue& q, int i, float* __restrict__ fb, const ShadeSink& sink) {
+    int n_splat = 0;
+    const float4 o = q.org_tmin[i], d = q.dir_tmax[i];
+    const uint4 st = q.state[i];
+    const float4 pc = q.contrib[i];
+    const int ent = q.ent[i];
+    const V3 rorg = v3(o.x, o.y, o.z), rdir = v3(d.x, d.y, d.z);
+    const int ray_id = (int)st.x;
+    const int sample = ray_id % rp.spi;
+    const int pixel = ray_id / rp.spi;
+    const int depth = (int)st.z;
+    const float eta = __uint_as_float(st.w);
+    const C3 contrib = c3(pc.x, pc.y, pc.z);
+    const float inv_pdf = pc.w;
+    const int n_lights = sc.n_inf + sc.n_fin;
+    const float pdf_lights = n_lights == 0 ? 1.0f : 1 / (float)n_lights;          // light_selector.art:26-29
+    const bool nee = sc.nee != 0;
+    if (ent < 0) {
+        // ---- on_miss, pathtracer.art:141-168
+        int inflights = 0; C3 color = c3(0, 0, 0);
+        for (int l = 0; l < sc.n_inf; ++l) {
+            const float* L = sc.inf_lights + 32 * l;
+            ++inflights;
+            const C3 emit = c3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));           // env.art:96
+            const float pdf_s = 1 / (4 * IGB_FLT_PI);                                // env.art:97
+            const float mis = nee ? 1 / (1 + inv_pdf * pdf_lights * pdf_s) : 1.0f;
+            color = cadd(color, handle_color(sc, cmulf(cmul(contrib, emit), mis)));
+        }
+        if (inflights > 0) { splat(fb, pixel, color, rp.inv_spi); ++n_splat; }
+    } else {
+        const float4 hh = q.hit[i];
+        const int prim = __float_as_int(hh.w);
+        const float dist = hh.x;
+        const float4* E = sc.ent_shade + (size_t)ent * 6;
+        const int shape = __float_as_int(ldg4(E + 3).w);
+        const int mat_id = __float_as_int(ldg4(E + 4).w);
+        const int4 si = __ldg(sc.shape_info + 2 * shape);
+        Surf surf;
+        if (si.x == 0) trimesh_surface(sc, ent, shape, prim, hh.y, hh.z, false, rorg, rdir, dist, surf);
+        else {  // shapes/sphere.art:52-76
+            const float4 g0 = ldg4(E), g1 = ldg4(E + 1), g2 = ldg4(E + 2);
+            const float4 sph = ldg4(sc.blob + si.y);
+            const V3 point = rorg + mulf(rdir, dist);
+            const V3 dd = point - xform_point(g0, g1, g2, v3(sph.x, sph.y, sph.z));
+            const float l = len(dd);
+            const V3 normal = mulf(dd, 1 / l);
+            surf.is_entering = true; surf.point = point; surf.face_normal = normal; surf.area = 0; surf.inv_area = 0;
+            surf.pu = hh.y; surf.pv = hh.z; surf.local = make_orthonormal(normal);
+        }
+        const float4 m0 = ldg4(sc.materials + 4 * mat_id), m1 = ldg4(sc.materials + 4 * mat_id + 1), m2 = ldg4(sc.materials + 4 * mat_id + 2);
+        const int bsdf = __float_as_int(m0.x);
+        const int light_id = __float_as_int(m0.y);
+        const V3 N = surf.local.c2;
+        Rng rnd; rnd.seed = random_seed(sample, rp.iter, rp.frame, pixel % rp.width, pixel / rp.width, rp.seed); rnd.counter = st.y;
+
+        // ---- on_hit, pathtracer.art:119-139
+        if (light_id >= 0 && surf.is_entering) {
+            const float dt = -dot(rdir, N);
+            if (dt > IGB_FLT_EPS) {
+                const float* L = sc.fin_lights + 32 * light_id;
+                const int lt = __float_as_int(__ldg(L));
+                C3 intensity; Pdf pdf;
+                if (lt == 2) {
+                    intensity = c3(__ldg(L + 23), __ldg(L + 24), __ldg(L + 25));
+                    const PlaneEm e = load_plane(L);
+                    const SQ sqv = compute_sq(e, rorg);
+                    pdf.value = safe_div(1, sqv.s); pdf.measure = 0;
+                } else {
+                    intensity = c3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));
+                    Surf es; float pdfv, w;
+                    shape_emitter_sample(sc, __float_as_int(__ldg(L + 1)), surf.pu, surf.pv, es, pdfv, w);
+                    pdf.value = pdfv; pdf.measure = 1;
+                }
+                const float pdf_s = pdf_as_solid(pdf, dt, dist * dist);
+                const float mis = nee ? 1 / (1 + inv_pdf * pdf_lights * pdf_s) : 1.0f;
+                splat(fb, pixel, handle_color(sc, cmulf(cmul(contrib, intensity), mis)), rp.inv_spi); ++n_splat;
+            }
+        }
+        const C3 kd = c3(m0.z, m0.w, m1.x);
+        const V3 out_dir = neg(rdir);
+        // ---- on_shadow, pathtracer.art:52-117
+        if (nee && bsdf == 0 && n_lights != 0 && !(depth + 1 > sc.max_depth)) {
+            const int id = n_lights <= 1 ? 0 : rnd.next_i32(0, n_lights - 1);            // light_selector.art:18-24
+            const float* L = id < sc.n_inf ? sc.inf_lights + 32 * id : sc.fin_lights + 32 * (id - sc.n_inf);
+            const int lt = __float_as_int(__ldg(L));
+            const LightSample ls = light_sample_direct(sc, L, lt, rnd, surf);
+            const float pdf_l_s = pdf_as_solid(ls.pdf, ls.cos, ls.dist * ls.dist) * pdf_lights;
+            if (!(pdf_l_s <= IGB_FLT_EPS) && ls.cos > IGB_FLT_EPS) {
+                float mis;
+                if (lt == 1) mis = 1.0f;
+                else { const float pdf_e_s = positive_cos(ls.dir, N) / IGB_FLT_PI; mis = 1 / (1 + pdf_e_s / pdf_l_s); }
+                const float factor = ls.pdf.value / pdf_l_s;
+                const C3 ev = cmulf(kd, positive_cos(ls.dir, N) * IGB_FLT_INV_PI);     // diffuse.art:3
+                const C3 cc = handle_color(sc, cmulf(cmul(ls.intensity, cmul(contrib, ev)), mis * factor));
+                if (!((cc.r + cc.g + cc.b) / 3 <= IGB_FLT_EPS)) {
+                    V3 s_dir; float s_tmax;
+                    if (lt == 0) { s_dir = ls.dir; s_tmax = IGB_FLT_MAX; }
+                    else { s_dir = ls.pos - surf.point; s_tmax = 1 - 0.001f; }
+                    const int ss = coalesced_append(sink.shadow_count);
+                    sink.sq.org_tmin[ss] = make_float4(surf.point.x, surf.point.y, surf.point.z, 0.001f);
+                    sink.sq.dir_tmax[ss] = make_float4(s_dir.x, s_dir.y, s_dir.z, s_tmax);
+                    sink.sq.color_pix[ss] = make_float4(cc.r, cc.g, cc.b, __int_as_float(pixel));
+                }
+            }
+        }
+        // ---- on_bounce, pathtracer.art:170-210
+        if (!(depth + 1 > sc.max_depth)) {
+            V3 in_dir; float s_pdf, s_eta; C3 s_color; bool is_delta;
+            if (bsdf == 0) {  // diffuse.art:5-9
+                const float u = rnd.next_f32(); const float v = rnd.next_f32();
+                V3 ld;
+                sample_cosine_hemisphere(u, v, ld, s_pdf);
+                in_dir = m33_mul(surf.local, ld); s_color = kd; s_eta = 1; is_delta = false;
+            } else {          // dielectric.art:18-34
+                const float n1 = m0.z, n2 = m0.w;
+                const C3 ks = c3(m1.x, m1.y, m1.z), kt = c3(m1.w, m2.x, m2.y);
+                const float k = surf.is_entering ? n1 / n2 : n2 / n1;
+                const float cos_o = dot(out_dir, N);
+                float cos_t = 0, factor = 1;
+                if (!fresnel(k, cos_o, cos_t, factor)) { cos_t = 0; factor = 1; }
+                if (rnd.next_f32() > factor) { in_dir = mulf(N, k * cos_o - cos_t) - mulf(out_dir, k); s_color = kt; s_eta = k; }   // vector.art:127
+                else { in_dir = mulf(N, 2 * dot(N, out_dir)) - out_dir; s_color = ks; s_eta = 1; }                                 // vector.art:124
+                s_pdf = 1; is_delta = true;
+            }
+            if (!(s_pdf <= IGB_FLT_EPS)) {
+                const C3 nc = cmul(contrib, s_color);
+                const C3 sc2 = cmulf(nc, eta * eta);
+                const float rr = (depth + 1 > sc.min_depth) ? clampf(fmaxf(fmaxf(sc2.r, sc2.g), sc2.b), 0.05f, 0.95f) : 1.0f;
+                if (!(rnd.next_f32() >= rr)) {
+                    const C3 fc = cmulf(nc, 1 / rr);
+                    const int bs = coalesced_append(sink.next_count);
+                    sink.nq.org_tmin[bs] = make_float4(surf.point.x, surf.point.y, surf.point.z, 0.001f);
+                    sink.nq.dir_tmax[bs] = make_float4(in_dir.x, in_dir.y, in_dir.z, IGB_FLT_MAX);
+                    sink.nq.state[bs] = make_uint4(st.x, rnd.counter, (uint32_t)(depth + 1), __float_as_uint(eta * s_eta));
+                    sink.nq.contrib[bs] = make_float4(fc.r, fc.g, fc.b, is_delta ? 0.0f : 1 / s_pdf);
+                    sink.nq.ent[bs] = (int)RAY_BOUNCE;
+                }
+            }
+        }
+    }
+    return n_splat;
+}
+
+}  // namespace igb

@@ -1,0 +1,320 @@
+// Two-level BVH8 traversal as a resumable per-lane state machine (one `step` = one node, entity or leaf visit).
+//
+// Reference behaviour implemented (paths relative to the reference's src/artic):
+//   traversal/mapping_cpu.art:421-518 (top level), :282-412 (bottom level), traversal/mapping_gpu.art:67-219,
+//   traversal/intersection.art:74-106 (Moeller-Trumbore), :223-256 (slabs), traversal/ray.art:27-59,
+//   shapes/trimesh.art:124-144, shapes/sphere.art:108-147.
+//
+// B200 design:
+//  * One loop walks both levels: an entity leaf of the top-level tree switches the ray to the entity's local space
+//    (ray.art:53-59) and pushes a sentinel that switches back when popped, so lanes in either level execute the
+//    same node and triangle code. Entities whose local matrix is exactly the identity keep the world ray (the
+//    transform is the exact map x -> x + 0), shapes of <= 4 triangles have no inner node at all.
+//  * The state machine is resumable so that the persistent trace phase (wavefront.cuh) can refill finished lanes
+//    of a warp with new rays while the others are still walking ("persistent threads", Aila & Laine 2009).
+//  * The traversal stack lives in shared memory, interleaved by thread (entry k of thread t at [k * stride + t]),
+//    so a push/pop is one conflict-free wavefront whatever the lanes' stack depths are; entries beyond SMEM_STACK
+//    spill to a per-thread local array. Nodes, triangles and entity leaves are read from a shared-memory copy
+//    staged by TMA bulk copies when the scene (or its first part) fits, else from global memory.
+//  * Pruning against the running closest hit is CONSERVATIVE (DESIGN.md "Ties and conservative culling"): slab
+//    distances are widened by a bound of their rounding error (|inv_org| * 2^-20 per axis) and compared with
+//    t_closest * (1 + 2^-16), so a box test can never hide a primitive whose Moeller-Trumbore distance is <= the
+//    current one. The result is a pure function of the ray -- min over all primitives ordered by (t, entity,
+//    primitive) -- and equals the oracle's brute-force answer whatever the tree looks like. The entity-box test
+//    of the reference (mapping_cpu.art:480, intersection.art:247-256) is part of the semantics and kept bit for bit.
+#pragma once
+
+#include "types.cuh"
+
+namespace igb {
+
+// Candidate ordering: nearer wins; exactly equal distance -> larger (entity, primitive) id. See DESIGN.md "Ties".
+__device__ __forceinline__ bool better(float t, int ent, int prim, const HitR& h) {
+    if (t < h.t) return true;
+    if (t > h.t) return false;
+    if (h.prim < 0) return true;
+    return ent > h.ent || (ent == h.ent && prim > h.prim);
+}
+
+// traversal/intersection.art:74-106 with the precomputed triangle of runtime/bvh/TriBVHAdapter.h:40-61
+__device__ __forceinline__ bool intersect_tri(const V3 org, const V3 dir, float tmin, float tmax, float4 a, float4 b, float4 c,
+                                              float& ot, float& ou, float& ov) {
+    const V3 v0 = v3(a.x, a.y, a.z), e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z), n = v3(a.w, b.w, c.w);
+    const V3 cc = v0 - org;
+    const V3 r = cross(cc, dir);
+    const float det = dot(n, dir);
+    const float abs_det = fabsf(det);
+    const uint32_t sgn = __float_as_uint(det) & 0x80000000u;
+    const float u = __uint_as_float(__float_as_uint(dot(r, e1)) ^ sgn);
+    const float v = __uint_as_float(__float_as_uint(dot(r, e2)) ^ sgn);
+    if (!(u >= 0 && v >= 0 && u + v <= abs_det && det != 0)) return false;
+    const float t = __uint_as_float(__float_as_uint(dot(cc, n)) ^ sgn);
+    if (!(t >= abs_det * tmin && t <= abs_det * tmax)) return false;
+    const float rcp = 1 / abs_det;
+    ot = t * rcp; ou = fmaxf(u * rcp, 0.0f); ov = fmaxf(v * rcp, 0.0f);
+    return true;
+}
+
+// shapes/sphere.art:1-6
+__device__ __forceinline__ void sphere_map_uv(V3 dir, float& u, float& v) {
+    const V3 d = v3(dir.y, -dir.x, dir.z);
+    const float theta = dm_acosf(d.z);
+    float phi = dm_atan2f(d.y, d.x);
+    if (phi < 0) phi = phi + 2 * IGB_FLT_PI;
+    u = phi / (2 * IGB_FLT_PI); v = theta / IGB_FLT_PI;
+}
+// shapes/sphere.art:108-136
+__device__ __forceinline__ bool intersect_sphere(V3 origin, float radius, V3 org, V3 dir, float rtmin, float rtmax, float& ot, float& ou, float& ov) {
+    const V3 L = org - origin;
+    const float S = -dot(L, dir);
+    const float D2 = len2(dir);
+    const float L2 = len2(L);
+    const float R2 = radius * radius * D2;
+    const float M2 = L2 * D2 - S * S;
+    if ((S < 0) || (M2 > R2)) return false;
+    const float Q = sqrtf(R2 - M2);
+    const float t0_ = (S - Q) / D2, t1_ = (S + Q) / D2;
+    const float t0 = t0_ > t1_ ? t1_ : t0_, t1 = t0_ > t1_ ? t0_ : t1_;
+    const float tmin = t0 < rtmin ? t1 : t0;
+    if (tmin >= rtmin && tmin <= rtmax) {
+        const V3 d = mulf(L + mulf(dir, tmin), 1 / radius);
+        ot = tmin; sphere_map_uv(d, ou, ov);
+        return true;
+    }
+    return false;
+}
+
+
+// ---- stack -----------------------------------------------------------------------------------------------------
+constexpr int SMEM_STACK  = 16;                       // entries per thread held in shared memory
+constexpr int LOCAL_STACK = 80;                       // overflow entries per thread (local memory)
+constexpr int STACK_SIZE  = SMEM_STACK + LOCAL_STACK;
+constexpr int   SENTINEL_RESTORE = (int)0x80000000;   // pop: back to world space, reload the ray
+constexpr int   SENTINEL_KEEP    = (int)0x80000001;   // pop: back to the top level, ray unchanged (identity instance)
+constexpr float CULL_SLACK = 9.5367431640625e-07f;    // 2^-20
+constexpr float CULL_TMAX  = 1.0000152587890625f;     // 1 + 2^-16
+
+struct Stack {
+    uint2* s;       // this thread's column in shared memory
+    int    stride;  // threads per block
+    uint2* l;       // this thread's local overflow array
+    __device__ __forceinline__ void push(int& sp, int node, float t) {
+        const uint2 e = make_uint2((uint32_t)node, __float_as_uint(t));
+        if (sp < SMEM_STACK) s[sp * stride] = e; else l[sp - SMEM_STACK] = e;
+        ++sp;
+    }
+    __device__ __forceinline__ uint2 pop(int& sp) {
+        --sp;
+        return sp < SMEM_STACK ? s[sp * stride] : l[sp - SMEM_STACK];
+    }
+    __device__ __forceinline__ void set(int slot, uint2 e) {
+        if (slot < SMEM_STACK) s[slot * stride] = e; else l[slot - SMEM_STACK] = e;
+    }
+};
+
+// Scene arrays (or their first part) staged in shared memory; indices beyond the staged count read global memory.
+struct Staged {
+    const float4* nodes;    int n_nodes;
+    const float4* tris;     int n_tris;
+    const float4* ent_leaf; int n_ent;
+};
+__device__ __forceinline__ const float4* node_ptr(const DevScene& sc, const Staged& sg, int node) {
+    return node < sg.n_nodes ? sg.nodes + node * 16 : sc.nodes + (size_t)node * 16;
+}
+__device__ __forceinline__ const float4* tri_ptr(const DevScene& sc, const Staged& sg, int slot) {
+    return slot < sg.n_tris ? sg.tris + slot * 3 : sc.tris + (size_t)slot * 3;
+}
+__device__ __forceinline__ const float4* leaf_ptr(const DevScene& sc, const Staged& sg, int slot) {
+    return slot < sg.n_ent ? sg.ent_leaf + slot * 8 : sc.ent_leaf + (size_t)slot * 8;
+}
+
+// Ray state bits
+constexpr uint32_t TB_ANY = 1u << 8, TB_NEGZERO = 1u << 9, TB_SX = 1u << 10, TB_SY = 1u << 11, TB_SZ = 1u << 12, TB_DONE = 1u << 13;
+
+// One slab test of child lane K of a group of four; the entry is written to the stack slot above the ones pushed so far
+// and only kept (n advances) if the child is hit, so there is no branch per child. `nearer` uses "not >=" so that the
+// first hit child replaces the NaN the running minimum starts from.
+#define IGB_CHILD(K)                                                                                                     \
+    {                                                                                                                    \
+        const float tn = fmaxf(fmaxf(fma_(idir.x, nx.K, ilo.x), fma_(idir.y, ny.K, ilo.y)), fmaxf(fma_(idir.z, nz.K, ilo.z), tmin));   \
+        const float tf = fminf(fminf(fma_(idir.x, fx.K, ihi.x), fma_(idir.y, fy.K, ihi.y)), fminf(fma_(idir.z, fz.K, ihi.z), tcull));  \
+        const bool hit_ = tn <= tf;                                                                                      \
+        IGB_STORE(ch.K, tn)                                                                                              \
+        const bool nearer = hit_ && !(tn >= best_t);                                                                     \
+        best_t = nearer ? tn : best_t; best = nearer ? ch.K : best; best_slot = nearer ? n : best_slot;                  \
+        n += hit_ ? 1 : 0;                                                                                               \
+    }
+
+struct Traversal {
+    V3 org, dir;              // ray in the current space (world, or local to `ent`)
+    float tmin, tmax;         // the ray's own interval (never shrunk: the triangle test uses it, see header)
+    V3 idir, ilo, ihi;        // 1/dir, -(org/dir) minus / plus its error bound (conservative slabs)
+    float tcull;              // hit.t * CULL_TMAX
+    HitR hit;
+    int cur, ent, sp;         // node code (0: pop next); entity whose bottom-level tree is walked (-1: top level)
+    uint32_t bits;            // ray type flags (ray.art:51) | TB_*
+#ifdef IGB_STEP_STATS
+    int n_node, n_leaf, n_ent;   // diagnostics build only: visits of each kind
+#endif
+
+    __device__ __forceinline__ void set_ray(V3 o, V3 d) {
+        org = o; dir = d;
+        idir = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));                 // traversal/ray.art:27-39
+        const V3 iorg = neg(o * idir);
+        const float inf = __int_as_float(0x7f800000);
+        const float ax = fabsf(iorg.x), ay = fabsf(iorg.y), az = fabsf(iorg.z);
+        // |iorg| = inf: org * flt_max overflowed (axis-parallel ray) -> no bound from that axis
+        ilo = v3(ax == inf ? -inf : iorg.x - ax * CULL_SLACK, ay == inf ? -inf : iorg.y - ay * CULL_SLACK, az == inf ? -inf : iorg.z - az * CULL_SLACK);
+        ihi = v3(ax == inf ? inf : iorg.x + ax * CULL_SLACK, ay == inf ? inf : iorg.y + ay * CULL_SLACK, az == inf ? inf : iorg.z + az * CULL_SLACK);
+        bits = (bits & ~(TB_SX | TB_SY | TB_SZ)) | (idir.x < 0 ? TB_SX : 0u) | (idir.y < 0 ? TB_SY : 0u) | (idir.z < 0 ? TB_SZ : 0u);
+    }
+
+    // po / pd: the ray record (org.xyz,tmin / dir.xyz,tmax). Returns false if there is nothing to traverse.
+    __device__ __forceinline__ bool begin(const DevScene& sc, const float4* po, const float4* pd, uint32_t ray_flags, bool any_hit) {
+        const float4 o = *po, d = *pd;
+        tmin = o.w; tmax = d.w;
+        hit.t = tmax; hit.u = 0; hit.v = 0; hit.prim = -1; hit.ent = -1;
+        tcull = hit.t * CULL_TMAX;
+        cur = 1; ent = -1; sp = 0;
+#ifdef IGB_STEP_STATS
+        n_node = n_leaf = n_ent = 0;
+#endif
+        const bool nz = ((__float_as_uint(o.x) == 0x80000000u) | (__float_as_uint(o.y) == 0x80000000u) | (__float_as_uint(o.z) == 0x80000000u) |
+                         (__float_as_uint(d.x) == 0x80000000u) | (__float_as_uint(d.y) == 0x80000000u) | (__float_as_uint(d.z) == 0x80000000u));
+        bits = (ray_flags & RAY_TYPE_MASK) | (any_hit ? TB_ANY : 0u) | (nz ? TB_NEGZERO : 0u);
+        if (sc.n_ent == 0) return false;
+        set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
+        return true;
+    }
+
+    __device__ __forceinline__ void accept(float t, float u, float v, int prim, int e) {
+        hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.ent = e; tcull = t * CULL_TMAX;
+        if (bits & TB_ANY) bits |= TB_DONE;
+    }
+
+    // ---- P: pop the next node. Returns true when the stack is empty (traversal finished).
+    __device__ __forceinline__ bool pop_step(Stack& st, const float4* po, const float4* pd) {
+        for (;;) {
+            if (sp == 0) return true;
+            const uint2 e = st.pop(sp);
+            cur = (int)e.x;
+            if (cur > SENTINEL_KEEP) { if (__uint_as_float(e.y) <= tcull) return false; continue; }
+            ent = -1;
+            if (cur == SENTINEL_RESTORE) { const float4 o = *po, d = *pd; set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)); }
+        }
+    }
+
+    // ---- N: inner node. Eight branch-free slab tests; the nearest hit child becomes `cur`, the others stay pushed.
+    __device__ __forceinline__ void node_step(const DevScene& sc, const Staged& sg, Stack& st) {
+#ifdef IGB_STEP_STATS
+        ++n_node;
+#endif
+        const float4* N = node_ptr(sc, sg, cur - 1);
+        // rows of the node: lo_x hi_x lo_y hi_y lo_z hi_z, two float4 each; the octant picks near / far by address
+        const int ox = (bits & TB_SX) ? 2 : 0, oy = (bits & TB_SY) ? 2 : 0, oz = (bits & TB_SZ) ? 2 : 0;
+        int n = 0, best = 0, best_slot = 0;
+        float best_t = __int_as_float(0x7fc00000);
+        if (sp + 8 <= SMEM_STACK) {
+            uint2* base = st.s + sp * st.stride;
+#define IGB_STORE(C, T) base[n * st.stride] = make_uint2((uint32_t)(C), __float_as_uint(T));
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int4 ch = *reinterpret_cast<const int4*>(N + 12 + g);
+                if (g == 1 && ch.x == 0) break;   // children are packed to the front
+                const float4 nx = N[ox + g], fx = N[2 - ox + g], ny = N[4 + oy + g], fy = N[6 - oy + g], nz = N[8 + oz + g], fz = N[10 - oz + g];
+                IGB_CHILD(x) IGB_CHILD(y) IGB_CHILD(z) IGB_CHILD(w)
+            }
+#undef IGB_STORE
+            if (n == 0) { cur = 0; return; }
+            --n;
+            if (best_slot != n) base[best_slot * st.stride] = base[n * st.stride];
+            sp += n; cur = best;
+        } else {
+            // deep stack: same tests, entries go through the overflow-aware push (rare)
+            const int sp0 = sp;
+#define IGB_STORE(C, T) if (hit_ && sp < STACK_SIZE) st.push(sp, (C), (T));
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                const int4 ch = *reinterpret_cast<const int4*>(N + 12 + g);
+                if (g == 1 && ch.x == 0) break;
+                const float4 nx = N[ox + g], fx = N[2 - ox + g], ny = N[4 + oy + g], fy = N[6 - oy + g], nz = N[8 + oz + g], fz = N[10 - oz + g];
+                IGB_CHILD(x) IGB_CHILD(y) IGB_CHILD(z) IGB_CHILD(w)
+            }
+#undef IGB_STORE
+            if (sp == sp0) { cur = 0; return; }
+            const uint2 top = st.pop(sp);
+            if (sp0 + best_slot != sp) st.set(sp0 + best_slot, top);
+            cur = best;
+        }
+    }
+
+    // ---- E: top-level leaf = one entity (traversal/mapping_cpu.art:470-500)
+    __device__ __forceinline__ void entity_step(const DevScene& sc, const Staged& sg, Stack& st) {
+#ifdef IGB_STEP_STATS
+        ++n_ent;
+#endif
+        const float4* L = leaf_ptr(sc, sg, (-cur - 1) >> 2);
+        const float4 l0 = L[0], l1 = L[1];
+        cur = 0;
+        const uint32_t eflags = __float_as_uint(l0.w);
+        if ((bits & RAY_TYPE_MASK) != ((bits & eflags) & RAY_TYPE_MASK)) return;                      // ray.art:51
+        {   // intersect_ray_box_single_section, intersection.art:247-256, against the ray's own tmax (exact reference form)
+            const V3 iorg = neg(org * idir);
+            const float t0x = fma_(idir.x, l0.x, iorg.x), t1x = fma_(idir.x, l1.x, iorg.x);
+            const float t0y = fma_(idir.y, l0.y, iorg.y), t1y = fma_(idir.y, l1.y, iorg.y);
+            const float t0z = fma_(idir.z, l0.z, iorg.z), t1z = fma_(idir.z, l1.z, iorg.z);
+            const float en = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+            const float ex = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
+            if (!((en <= ex) & (ex >= 0))) return;
+        }
+        const float4 l5 = L[5];
+        const int kind = __float_as_int(l1.w);    // bit 0: analytic sphere, bit 1: identity local matrix
+        const int e = __float_as_int(l5.x);
+        if (kind & 1) {
+            const float4 r0 = L[2], r1 = L[3], r2 = L[4], s = L[6];
+            float t, u, v;
+            if (intersect_sphere(v3(s.x, s.y, s.z), s.w, xform_point(r0, r1, r2, org), xform_dir(r0, r1, r2, dir), tmin, tmax, t, u, v) && better(t, e, 0, hit))
+                accept(t, u, v, 0, e);
+            return;
+        }
+        ent = e;
+        cur = __float_as_int(l5.y);               // root of the shape's tree (a leaf code for shapes of <= 4 triangles)
+        if ((kind & 2) && !(bits & TB_NEGZERO)) { st.push(sp, SENTINEL_KEEP, -1.0f); return; }
+        const float4 r0 = L[2], r1 = L[3], r2 = L[4];
+        set_ray(xform_point(r0, r1, r2, org), xform_dir(r0, r1, r2, dir));                            // ray.art:53-59
+        st.push(sp, SENTINEL_RESTORE, -1.0f);
+    }
+
+    // ---- L: bottom-level leaf = up to four triangles (shapes/trimesh.art:124-144)
+    __device__ __forceinline__ void leaf_step(const DevScene& sc, const Staged& sg) {
+#ifdef IGB_STEP_STATS
+        ++n_leaf;
+#endif
+        const int r = -cur - 1;
+        const int first = r >> 2, cnt = (r & 3) + 1;
+        cur = 0;
+        for (int j = 0; j < cnt; ++j) {
+            const float4* T = tri_ptr(sc, sg, first + j);
+            const float4 a = T[0], b = T[1], c = T[2];
+            float t, u, v;
+            if (intersect_tri(org, dir, tmin, tmax, a, b, c, t, u, v)) {
+                const int prim = __ldg(sc.tri_prim + first + j);
+                if (better(t, ent, prim, hit)) accept(t, u, v, prim, ent);
+            }
+        }
+    }
+
+    // One turn of the pipeline P -> N -> E -> L: a lane performs every visit its state allows, in that order, so that
+    // a fresh ray does root node, entity and triangle leaf in one turn and lanes of a warp stay aligned.
+    // Returns true when the traversal is finished (hit holds the result).
+    __device__ __forceinline__ bool turn(const DevScene& sc, const Staged& sg, Stack& st, const float4* po, const float4* pd) {
+        if (cur == 0 && pop_step(st, po, pd)) return true;
+        if (cur > 0) node_step(sc, sg, st);
+        if (cur < 0 && ent < 0) entity_step(sc, sg, st);
+        if (cur < 0 && ent >= 0) leaf_step(sc, sg);
+        return (bits & TB_DONE) != 0;
+    }
+};
+#undef IGB_CHILD
+
+}  // namespace igb

@@ -60,8 +60,8 @@ HIT_DTYPE = np.dtype([("ent_id", "<i4"), ("prim_id", "<i4"), ("t", "<f4"), ("u",
 # every symbol include/igb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["igb200_last_error", "igb200_version", "igb200_create", "igb200_destroy", "igb200_set_scene", "igb200_resize",
            "igb200_set_partition", "igb200_render", "igb200_framebuffer", "igb200_framebuffer_device", "igb200_clear",
-           "igb200_upload_framebuffer", "igb200_stats", "igb200_reset_stats", "igb200_kernel_times", "igb200_set_option",
-           "igb200_trace_closest", "igb200_trace_any", "igb200_bench_trace", "igb200_test_detmath"]
+           "igb200_upload_framebuffer", "igb200_stats", "igb200_reset_stats", "igb200_kernel_times", "igb200_turn_log", "igb200_step_stats", "igb200_set_option",
+           "igb200_stream", "igb200_trace_closest", "igb200_trace_any", "igb200_bench_trace", "igb200_test_detmath"]
 
 
 def library_path() -> str:
@@ -95,9 +95,12 @@ def lib():
         L.igb200_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         L.igb200_reset_stats.argtypes = [vp]
         L.igb200_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        L.igb200_turn_log.argtypes = [vp, vp, vp, vp, C.c_int, ip]
+        L.igb200_step_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.igb200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+        L.igb200_stream.argtypes = [vp, C.POINTER(vp)]
         L.igb200_trace_closest.argtypes = [vp, vp, vp, C.c_size_t, vp]
-        L.igb200_trace_any.argtypes = [vp, vp, vp, C.c_size_t, vp]
+        L.igb200_trace_any.argtypes = [vp, vp, C.c_size_t, vp]
         L.igb200_bench_trace.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.igb200_test_detmath.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t]
         _LIB = L
@@ -204,11 +207,12 @@ class B200Device:
         _check(lib().igb200_upload_framebuffer(self._h, name.encode(), a.ctypes.data))
 
     def getStatistics(self):
-        out = (C.c_uint64 * 3)()
+        out = (C.c_uint64 * 5)()
         ms = C.c_double()
         _check(lib().igb200_stats(self._h, out, C.byref(ms)))
         return {"CameraRayCount": int(out[0]), "ShadowRayCount": int(out[1]), "BounceRayCount": int(out[2]),
-                "PrimaryRays": int(out[0] + out[2]), "TotalRays": int(out[0] + out[1] + out[2]), "render_ms": ms.value}
+                "PrimaryRays": int(out[0] + out[2]), "TotalRays": int(out[0] + out[1] + out[2]),
+                "Splats": int(out[3]), "KernelLaunches": int(out[4]), "render_ms": ms.value}
 
     def resetStatistics(self):
         _check(lib().igb200_reset_stats(self._h))
@@ -220,12 +224,29 @@ class B200Device:
     def setOption(self, name: str, value: int):
         _check(lib().igb200_set_option(self._h, name.encode(), int(value)))
 
+    def turnLog(self):
+        """Per loop turn of the last render(): (rays traced, trace-phase ns, shade-phase ns)."""
+        a, b, c = (np.zeros(128, np.uint32) for _ in range(3))
+        n = C.c_int()
+        _check(lib().igb200_turn_log(self._h, a.ctypes.data, b.ctypes.data, c.ctypes.data, 128, C.byref(n)))
+        return a[:n.value].copy(), b[:n.value].copy(), c[:n.value].copy()
+
+    def stepStats(self):
+        out = (C.c_uint64 * 16)()
+        _check(lib().igb200_step_stats(self._h, out))
+        names = ("node_visits", "leaf_visits", "entity_visits", "max_visits_per_ray", "rays")
+        return {"turns<16": {n: int(out[i]) for i, n in enumerate(names)}, "turns>=16": {n: int(out[8 + i]) for i, n in enumerate(names)}}
+
+    def stream(self) -> int:
+        p = C.c_void_p()
+        _check(lib().igb200_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
+
     def kernelTimes(self):
         ms = (C.c_double * 4)()
         n = (C.c_uint64 * 4)()
         _check(lib().igb200_kernel_times(self._h, ms, n))
-        names = ("generate", "traverse_primary", "shade", "traverse_secondary")
-        return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(names)}
+        return {"trace": {"ms": ms[1], "launches": int(n[1])}, "shade_generate": {"ms": ms[2], "launches": int(n[2])}}
 
     def traceClosest(self, rays, flags=None) -> np.ndarray:
         rays = np.ascontiguousarray(rays, RAY_DTYPE)
@@ -234,11 +255,10 @@ class B200Device:
         _check(lib().igb200_trace_closest(self._h, rays.ctypes.data, None if fl is None else fl.ctypes.data, rays.shape[0], out.ctypes.data))
         return out
 
-    def traceAny(self, rays, flags=None) -> np.ndarray:
+    def traceAny(self, rays) -> np.ndarray:
         rays = np.ascontiguousarray(rays, RAY_DTYPE)
         out = np.zeros(rays.shape[0], np.int32)
-        fl = None if flags is None else np.ascontiguousarray(flags, np.uint32)
-        _check(lib().igb200_trace_any(self._h, rays.ctypes.data, None if fl is None else fl.ctypes.data, rays.shape[0], out.ctypes.data))
+        _check(lib().igb200_trace_any(self._h, rays.ctypes.data, rays.shape[0], out.ctypes.data))
         return out
 
     def benchTrace(self, rays, any_hit=False, repeat=10) -> float:

@@ -156,20 +156,31 @@ int igb200_framebuffer_device(igb200_ctx* ctx, const char* aov, float** device_p
 int igb200_clear(igb200_ctx* ctx, const char* aov_or_null);       /* clearFramebuffer / clearAllFramebuffer */
 int igb200_upload_framebuffer(igb200_ctx* ctx, const char* aov, const float* host_rgb); /* syncFramebufferHostToDevice */
 
-/* IRenderDevice::getStatistics (ray counters of src/runtime/Statistics.h:57-64): out = {camera, shadow, bounce}
- * rays since creation; render_ms = device time spent in igb200_render since creation. */
-int igb200_stats(igb200_ctx* ctx, uint64_t out[3], double* render_ms);
+/* IRenderDevice::getStatistics (ray counters of src/runtime/Statistics.h:57-64): out = {camera rays, shadow rays,
+ * bounce rays, framebuffer splats, kernel launches} since the last reset; render_ms = device time spent in
+ * igb200_render (CUDA events on the render stream) since the last reset. */
+int igb200_stats(igb200_ctx* ctx, uint64_t out[5], double* render_ms);
 int igb200_reset_stats(igb200_ctx* ctx);
 
-/* Time of the dominant kernel classes inside igb200_render since the last reset, measured with CUDA events on the
- * render stream: out_ms = {generate, traverse_primary, shade, traverse_secondary}, out_launches likewise. */
+/* Time spent in the phases of the persistent wavefront kernel since the last reset, measured on the device
+ * (%globaltimer at the grid barriers): out_ms = {0, trace phase (closest + any hit), shade + generate phase, 0},
+ * out_launches = number of phases. */
 int igb200_kernel_times(igb200_ctx* ctx, double out_ms[4], uint64_t out_launches[4]);
-int igb200_set_option(igb200_ctx* ctx, const char* name, int64_t value); /* "capacity", "profile_kernels", ... */
+/* Diagnostics of the LAST igb200_render: for each loop turn of the persistent kernel (at most max_turns, at most 128)
+ * the number of rays traced and the duration of its trace phase and of the shade + generate phase before it. */
+int igb200_turn_log(igb200_ctx* ctx, uint32_t* items, uint32_t* trace_ns, uint32_t* shade_ns, int max_turns, int* n_turns);
+/* Diagnostics build only (-DIGB_STEP_STATS; zeros otherwise), LAST igb200_render: for loop turns < 16 (out[0..7]) and
+ * >= 16 (out[8..15]): inner-node visits, triangle-leaf visits, entity visits, max visits of one ray, rays traced. */
+int igb200_step_stats(igb200_ctx* ctx, uint64_t out[16]);
+int igb200_set_option(igb200_ctx* ctx, const char* name, int64_t value); /* "capacity", "refill", "stage_budget" */
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a caller can record
+ * its own events on it or order a collective after a render (the reference has one implicit device queue). */
+int igb200_stream(igb200_ctx* ctx, void** cuda_stream);
 
-/* Parity / micro-benchmark hooks on the traversal kernels: closest hit and any hit for a host ray list. flags may be
- * NULL (camera rays / shadow rays respectively). */
+/* Parity / micro-benchmark hooks on the trace phase of the pipeline: closest hit for a host ray list (ray type
+ * flags may be NULL = camera rays) and any hit (always shadow rays, through the shadow queue and the fused splat). */
 int igb200_trace_closest(igb200_ctx* ctx, const igb200_ray* rays, const uint32_t* flags, size_t n, igb200_hit* out);
-int igb200_trace_any(igb200_ctx* ctx, const igb200_ray* rays, const uint32_t* flags, size_t n, int32_t* occluded);
+int igb200_trace_any(igb200_ctx* ctx, const igb200_ray* rays, size_t n, int32_t* occluded);
 /* Same, device-resident rays (n repeated `repeat` times), returns average milliseconds per pass. */
 int igb200_bench_trace(igb200_ctx* ctx, const igb200_ray* rays, size_t n, int any_hit, int repeat, double* ms_per_pass);
 

@@ -19,7 +19,11 @@
 //  * exact-distance ties between two primitives are resolved by (entity id, primitive id) instead of by BVH
 //    visiting order, because the reference's order depends on an un-pinned third-party builder
 //    (madmann91/bvh master, cmake/GetDependencies.cmake:53-58); for the same reason the upper distance bound
-//    of the triangle test is the ray's own tmax and the running closest hit is applied afterwards;
+//    of the triangle test is the ray's own tmax and the running closest hit is applied afterwards, and the
+//    running hit prunes nodes only through a conservative box test (cull_box) -- never through the leaf's
+//    `tmin <= hit.distance` shortcut (traversal/mapping_cpu.art:481), whose outcome under rounding depends on the
+//    visiting order. The closest hit is thereby a pure function of the ray: min over all primitives of
+//    entities that pass the visibility and entity-box tests, ordered by (t, entity, primitive);
 //  * the BVH is this file's own median-split BVH2 (or none at all: brute force), because closest-hit
 //    results do not depend on topology once ties are ordered;
 //  * streams are sorted with a stable counting sort instead of the in-place cycle sort
@@ -219,6 +223,27 @@ inline void intersect_ray_box(const Ray& ray, const BBox& b, float tmax, float& 
     const float t0z = fmaf_(ray.inv_dir.z, b.min.z, ray.inv_org.z), t1z = fmaf_(ray.inv_dir.z, b.max.z, ray.inv_org.z);
     entry = fmax_sel(fmax_sel(fmin_sel(t0x, t1x), fmin_sel(t0y, t1y)), fmax_sel(fmin_sel(t0z, t1z), ray.tmin));
     exit  = fmin_sel(fmin_sel(fmax_sel(t0x, t1x), fmax_sel(t0y, t1y)), fmin_sel(fmax_sel(t0z, t1z), tmax));
+}
+
+// Conservative node culling used by this file's own BVH (not part of the reference's arithmetic): a node is skipped
+// only if the slab interval, widened by a bound of its rounding error (|inv_org| * 2^-20 per axis) misses
+// [tmin, t_closest * (1 + 2^-16)]. A candidate is therefore never lost to the rounding of a box test, and the
+// closest hit equals the brute-force answer ordered by (t, entity, primitive) whatever the tree looks like.
+inline bool cull_box(const Ray& ray, const BBox& b, float t_closest) {
+    const float k = 9.5367431640625e-07f;  // 2^-20
+    float entry = ray.tmin, exit = t_closest * 1.0000152587890625f;  // 1 + 2^-16
+    auto axis = [&](float inv_dir, float inv_org, float lo, float hi) {
+        const float a = fabsf(inv_org);
+        if (a == INFINITY) return;   // org * flt_max overflowed (axis-parallel ray): no bound from this axis
+        const float t0 = fmaf_(inv_dir, lo, inv_org), t1 = fmaf_(inv_dir, hi, inv_org);
+        const float tn = fmin_sel(t0, t1) - a * k, tf = fmax_sel(t0, t1) + a * k;
+        if (tn > entry) entry = tn;
+        if (tf < exit) exit = tf;
+    };
+    axis(ray.inv_dir.x, ray.inv_org.x, b.min.x, b.max.x);
+    axis(ray.inv_dir.y, ray.inv_org.y, b.min.y, b.max.y);
+    axis(ray.inv_dir.z, ray.inv_org.z, b.min.z, b.max.z);
+    return exit < entry;
 }
 
 // shapes/sphere.art:1-6 with core/warp.art:50-54
@@ -464,9 +489,7 @@ inline void intersect_entity(const Scene& sc, const EntityLeaf& leaf, const Ray&
     stack[sp++] = 0;
     while (sp && !done) {
         const Bvh2::Node& n = sh.bvh.nodes[stack[--sp]];
-        float en, ex;
-        intersect_ray_box(lray, n.box, hit.distance, en, ex);
-        if (ex < en) continue;
+        if (cull_box(lray, n.box, hit.distance)) continue;
         if (n.count) { for (int i = 0; i < n.count && !done; ++i) test_tri(sh.bvh.order[n.first + i]); }
         else { stack[sp++] = n.left; stack[sp++] = n.right; }
     }
@@ -481,7 +504,8 @@ inline Hit traverse(const Scene& sc, const Ray& ray, bool any_hit, bool use_bvh)
         float en, ex;                                                               // :480 intersect_ray_box_single_section
         intersect_ray_box(ray, BBox{v3(leaf.min[0], leaf.min[1], leaf.min[2]), v3(leaf.max[0], leaf.max[1], leaf.max[2])}, ray.tmax, en, ex);
         if (!((en <= ex) & (ex >= 0))) return;
-        if (!(en <= hit.distance)) return;                                          // :481
+        // :481 culls on `tmin <= hit.distance`; with rounding that makes the result depend on the visiting order
+        // (header, "ties"), so the running hit is only ever used through cull_box below
         intersect_entity(sc, leaf, ray, any_hit, use_bvh, hit, done);
     };
     if (!use_bvh) {
@@ -493,9 +517,7 @@ inline Hit traverse(const Scene& sc, const Ray& ray, bool any_hit, bool use_bvh)
     stack[sp++] = 0;
     while (sp && !done) {
         const Bvh2::Node& n = sc.top.nodes[stack[--sp]];
-        float en, ex;
-        intersect_ray_box(ray, n.box, hit.distance, en, ex);
-        if (ex < en) continue;
+        if (cull_box(ray, n.box, hit.distance)) continue;
         if (n.count) { for (int i = 0; i < n.count && !done; ++i) visit_leaf(sc.leaves[sc.top.order[n.first + i]]); }
         else { stack[sp++] = n.left; stack[sp++] = n.right; }
     }

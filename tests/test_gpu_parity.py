@@ -78,7 +78,7 @@ def test_closest_hit_records_match_oracle(scene, w, h):
     with B200Device() as dev:
         dev.assignScene(t)
         got = dev.traceClosest(rays)
-        occ = dev.traceAny(rays, flags=np.full(len(rays), 8, np.uint32))
+        occ = dev.traceAny(rays)
     assert (got["ent_id"] == ref["ent_id"]).all()
     assert (got["prim_id"] == ref["prim_id"]).all()
     for k in ("t", "u", "v"):
