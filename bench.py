@@ -40,6 +40,9 @@ SCENE = "scenes/diamond_scene.json"
 # algorithmic bytes per unit of work of the wavefront hand-off
 B_PRIMARY, B_SHADOW, B_SPLAT = 216, 108, 24
 # the same figure split by pipeline stage (DESIGN.md "Algorithmic bytes")
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_wavefront launch of this workload (ncu --set full, profiles/)
+NCU_TRAFFIC_BYTES = 7.615e9
+NCU_TRAFFIC_SOURCE = "profiles/r1a_k_wavefront_full.csv (4.047 GB read + 3.567 GB written per launch)"
 B_STAGE = {"generate": 68, "traverse_primary": 60, "shade_read": 88, "shade_bounce_write": 68, "shade_shadow_write": 56,
            "traverse_secondary": 52}
 
@@ -311,20 +314,23 @@ def run_b200(args):
                                  "frac": step_bytes / (ms * 1e-3) / 1e9 / world / peak, "traffic": None,
                                  "what": f"whole wavefront step per GPU: {B_PRIMARY} B x primary + {B_SHADOW} B x shadow + {B_SPLAT} B x splat (SURVEY.md 8d), peak {peak_src}"}
         if kt is not None:
+            # the step IS one launch of the persistent kernel k_wavefront: its algorithmic bytes are the step's
+            n_l = max(kst["KernelLaunches"], 1)
+            avg_ms = kst["render_ms"] / n_l
+            kbytes = algorithmic_bytes(kst) / n_l
+            ach = kbytes / (avg_ms * 1e-3) / 1e9
             prim = kst["CameraRayCount"] + kst["BounceRayCount"]
-            per_class_bytes = {"generate": B_STAGE["generate"] * kst["CameraRayCount"],
-                               "traverse_primary": B_STAGE["traverse_primary"] * prim,
-                               "shade": B_STAGE["shade_read"] * prim + B_STAGE["shade_bounce_write"] * kst["BounceRayCount"] + B_STAGE["shade_shadow_write"] * kst["ShadowRayCount"],
-                               "traverse_secondary": B_STAGE["traverse_secondary"] * kst["ShadowRayCount"] + B_SPLAT * kst["Splats"]}
+            phase_bytes = {"trace": B_STAGE["traverse_primary"] * prim + B_STAGE["traverse_secondary"] * kst["ShadowRayCount"] + B_SPLAT * kst["Splats"],
+                           "shade_generate": B_STAGE["generate"] * kst["CameraRayCount"] + B_STAGE["shade_read"] * prim
+                                             + B_STAGE["shade_bounce_write"] * kst["BounceRayCount"] + B_STAGE["shade_shadow_write"] * kst["ShadowRayCount"]}
             total_k = sum(v["ms"] for v in kt.values()) or 1.0
-            dom = max(kt, key=lambda k: kt[k]["ms"])
-            n_l = max(kt[dom]["launches"], 1)
-            avg_ms = kt[dom]["ms"] / n_l
-            ach = per_class_bytes[dom] / n_l / (avg_ms * 1e-3) / 1e9
-            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                                "kernel": dom, "avg_launch_ms": avg_ms, "launches": n_l, "share_of_step": kt[dom]["ms"] / total_k,
-                                "algorithmic_bytes_per_launch": per_class_bytes[dom] / n_l, "peak_source": peak_src}
-            line["kernel_ms"] = {k: {"ms": v["ms"], "launches": v["launches"], "share": v["ms"] / total_k} for k, v in kt.items()}
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES,
+                                "kernel": "k_wavefront (persistent cooperative kernel: one launch = one render() iteration)",
+                                "avg_launch_ms": avg_ms, "launches": n_l, "share_of_step": 1.0,
+                                "algorithmic_bytes_per_launch": kbytes, "peak_source": peak_src,
+                                "traffic_source": NCU_TRAFFIC_SOURCE}
+            line["phase_ms"] = {k: {"ms_per_step": v["ms"] / n_l, "share": v["ms"] / total_k,
+                                    "algorithmic_GBps": phase_bytes[k] / max(v["ms"], 1e-9) / 1e6} for k, v in kt.items()}
         if host is not None:
             line["image_mean"] = float(np.asarray(host).mean() / args.steps)
 
