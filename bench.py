@@ -193,6 +193,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from ignis_b200.device import Runtime
+    from ignis_b200.partition import TILE, reduce_framebuffer
     from ignis_b200.scene import load_scene
 
     rank = int(os.environ.get("RANK", "0"))
@@ -209,7 +210,7 @@ def run_b200(args):
     tables = load_scene(os.path.join(ROOT, SCENE), w, h)
     rt = Runtime(tables, w, h, spi=spi, seed=0, cuda_device=local_rank)
     dev = rt.device
-    dev.setPartition(rank, world, 32)
+    dev.setPartition(rank, world, TILE)
     stream = torch.cuda.ExternalStream(dev.stream(), device=torch.device("cuda", local_rank))
 
     class _FB:  # device framebuffer as a torch tensor (no copy)
@@ -227,7 +228,7 @@ def run_b200(args):
         # disjoint tile support: the sum is a gather of the per-rank tiles
         with torch.cuda.stream(stream):
             scratch.copy_(fb_t)
-            dist.reduce(scratch, dst=0, op=dist.ReduceOp.SUM)
+            reduce_framebuffer(scratch, dst=0)
 
     # ---- warm-up (also sizes the ray queues and warms NCCL)
     for _ in range(max(args.warmup, 0)):

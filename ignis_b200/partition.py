@@ -1,0 +1,36 @@
+"""Multi-GPU partition of the framebuffer and the one exchange step of the path.
+
+The reference is single-device (src/device/Device.cpp:1632). Pixels are independent and the RNG is keyed by
+(sample, iter, frame, x, y, seed) (src/artic/core/random.art:34-43), so a rank that renders only a subset of the pixels
+produces exactly the values the single device would have produced there. The frame is cut into tile x tile blocks,
+enumerated row-major and dealt round-robin: rank r owns the blocks t with t % world == r (the rule igb200_set_partition
+implements on the device). The only exchange is a sum of the f32 accumulation buffers onto rank 0: the supports are
+disjoint, so the sum is a gather and the result equals the single-device image bit for bit.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+TILE = 32
+
+
+def tile_owner(width: int, height: int, world: int, tile: int = TILE) -> np.ndarray:
+    """(H, W) int32 map: which rank renders each pixel."""
+    tx = (width + tile - 1) // tile
+    ys, xs = np.mgrid[0:height, 0:width]
+    return (((ys // tile) * tx + (xs // tile)) % world).astype(np.int32)
+
+
+def local_ray_domain(width: int, height: int, spi: int, rank: int, world: int, tile: int = TILE) -> int:
+    """Size of the padded camera-ray domain of one rank (whole tiles, igb200_render: `total`)."""
+    tiles = ((width + tile - 1) // tile) * ((height + tile - 1) // tile)
+    local = (tiles - rank + world - 1) // world if tiles > rank else 0
+    return local * tile * tile * spi
+
+
+def reduce_framebuffer(fb, dst: int = 0, group=None):
+    """Sums the per-rank accumulation buffers onto `dst` (torch tensor, CPU/gloo or CUDA/NCCL). In place on dst."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.reduce(fb, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return fb
