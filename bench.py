@@ -251,6 +251,7 @@ def run_b200(args):
                 rt.step()
                 if e2e:
                     if world > 1:
+                        dev.sync()
                         reduce_to_root()
                         if rank == 0:
                             with torch.cuda.stream(stream):
@@ -258,8 +259,10 @@ def run_b200(args):
                             stream.synchronize()
                     else:
                         host = dev.getFramebufferForHost()   # D2H of the accumulated frame into pinned memory
-            if not e2e and world > 1:
-                reduce_to_root()
+            if not e2e:
+                dev.sync()           # finishes the deferred tail of the last steps: all work of the K steps is inside the timed region
+                if world > 1:
+                    reduce_to_root()
             ev1.record(stream)
             stream.synchronize()
         barrier()
@@ -291,12 +294,10 @@ def run_b200(args):
     if world == 1:
         rt.reset()
         dev.resetStatistics()
-        dev.setOption("profile_kernels", 1)
         for _ in range(min(args.steps, 4)):
             rt.step()
         kt = dev.kernelTimes()
         kst = dev.getStatistics()
-        dev.setOption("profile_kernels", 0)
 
     line = None
     if rank == 0:
@@ -314,23 +315,25 @@ def run_b200(args):
         line["roofline_step"] = {"bound": "hbm", "achieved": step_bytes / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
                                  "frac": step_bytes / (ms * 1e-3) / 1e9 / world / peak, "traffic": None,
                                  "what": f"whole wavefront step per GPU: {B_PRIMARY} B x primary + {B_SHADOW} B x shadow + {B_SPLAT} B x splat (SURVEY.md 8d), peak {peak_src}"}
+        # the step IS one launch of the persistent kernel k_wavefront (plus one drain launch at the end of the K steps):
+        # algorithmic bytes and duration of the average launch, from the CUDA-event-timed region above
+        n_l = max(tot["KernelLaunches"] // world, 1)
+        avg_ms = ms / n_l
+        kbytes = step_bytes / world / n_l
+        ach = kbytes / (avg_ms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES,
+                            "kernel": "k_wavefront (persistent cooperative kernel: one launch = one render() iteration)",
+                            "avg_launch_ms": avg_ms, "launches": n_l, "share_of_step": 1.0,
+                            "algorithmic_bytes_per_launch": kbytes, "peak_source": peak_src,
+                            "traffic_source": NCU_TRAFFIC_SOURCE}
         if kt is not None:
-            # the step IS one launch of the persistent kernel k_wavefront: its algorithmic bytes are the step's
-            n_l = max(kst["KernelLaunches"], 1)
-            avg_ms = kst["render_ms"] / n_l
-            kbytes = algorithmic_bytes(kst) / n_l
-            ach = kbytes / (avg_ms * 1e-3) / 1e9
             prim = kst["CameraRayCount"] + kst["BounceRayCount"]
             phase_bytes = {"trace": B_STAGE["traverse_primary"] * prim + B_STAGE["traverse_secondary"] * kst["ShadowRayCount"] + B_SPLAT * kst["Splats"],
                            "shade_generate": B_STAGE["generate"] * kst["CameraRayCount"] + B_STAGE["shade_read"] * prim
                                              + B_STAGE["shade_bounce_write"] * kst["BounceRayCount"] + B_STAGE["shade_shadow_write"] * kst["ShadowRayCount"]}
             total_k = sum(v["ms"] for v in kt.values()) or 1.0
-            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES,
-                                "kernel": "k_wavefront (persistent cooperative kernel: one launch = one render() iteration)",
-                                "avg_launch_ms": avg_ms, "launches": n_l, "share_of_step": 1.0,
-                                "algorithmic_bytes_per_launch": kbytes, "peak_source": peak_src,
-                                "traffic_source": NCU_TRAFFIC_SOURCE}
-            line["phase_ms"] = {k: {"ms_per_step": v["ms"] / n_l, "share": v["ms"] / total_k,
+            n_k = max(kst["KernelLaunches"], 1)
+            line["phase_ms"] = {k: {"ms_per_launch": v["ms"] / n_k, "share": v["ms"] / total_k,
                                     "algorithmic_GBps": phase_bytes[k] / max(v["ms"], 1e-9) / 1e6} for k, v in kt.items()}
         if host is not None:
             line["image_mean"] = float(np.asarray(host).mean() / args.steps)

@@ -22,10 +22,17 @@ namespace {
 constexpr int WF_BLOCK = 256;       // threads per CTA of the persistent kernels
 // CTAs per SM the register budget is compiled for: 3 -> 80 registers / thread, 2 -> 128. Both variants are built; the
 // "min_blocks" option picks one (DESIGN.md "Occupancy").
+// "vote" picks the scheduling of the traversal visit kinds (traverse.cuh turn / turn_vote); all variants are built.
 using WaveKernel = void (*)(const WaveParams);
 using TraceKernel = void (*)(const DevScene, const PrimaryQueue, int, const ShadowQueue, int, float*, int*, unsigned long long*, int, int, int, int);
-static WaveKernel wave_kernel(int min_blocks) { return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3> : k_wavefront<WF_BLOCK, 2>; }
-static TraceKernel trace_kernel(int min_blocks) { return min_blocks >= 3 ? k_trace<WF_BLOCK, 3> : k_trace<WF_BLOCK, 2>; }
+static WaveKernel wave_kernel(int min_blocks, int vote) {
+    if (vote) return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 2> : k_wavefront<WF_BLOCK, 2, 2>;
+    return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 0> : k_wavefront<WF_BLOCK, 2, 0>;
+}
+static TraceKernel trace_kernel(int min_blocks, int vote) {
+    if (vote) return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 2> : k_trace<WF_BLOCK, 2, 2>;
+    return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 0> : k_trace<WF_BLOCK, 2, 0>;
+}
 
 __global__ void k_detmath(int fn, const float* a, const float* b, float* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,14 +105,19 @@ struct igb200_ctx {
     int stage_nodes = 0, stage_tris = 0, stage_ent = 0;
     size_t smem_bytes = 0;
     int64_t stage_budget = 40 * 1024;  // bytes of shared memory per CTA for the staged scene copy
-    int refill = 24, min_blocks = 3;
+    int refill = 24, min_blocks = 2, vote = 2;
+    // deferred tail: a launch ends once at most defer_permille/1000 of the iteration's camera rays are still alive as paths;
+    // they are carried into the next launch (render) or finished by a drain launch before anything is observed
+    int defer_permille = 50;
+    bool pending = false;              // launches issued since the last synchronisation with the device
+    bool maybe_carry = false;          // the last launch may have left paths behind
+    igb200_settings carry_settings{};  // settings the carried paths were generated with
+    int carry_rank = 0, carry_world = 1, carry_tile = 0;
+    RenderParams last_rp{}; DevScene last_sc{};
     // partition
     int rank = 0, world = 1, tile = 32;
     // stats
-    uint64_t rays[4] = {0, 0, 0, 0};   // camera, shadow, bounce rays; framebuffer splats
-    uint64_t launches = 0;             // kernels launched by igb200_render since the last reset
-    double render_ms = 0;
-    double k_ms[4] = {0, 0, 0, 0}; uint64_t k_launch[4] = {0, 0, 0, 0};
+    uint64_t launches = 0;             // kernels launched by igb200_render (and its drains) since the last reset
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf<igb200_ray> list_rays;
 };
@@ -129,12 +141,62 @@ static int configure_kernels(igb200_ctx* c) {
     c->stage_nodes = (int)std::min<int64_t>(s.n_nodes, left / 256); left -= (int64_t)c->stage_nodes * 256;
     c->stage_tris = (int)std::min<int64_t>(s.n_tris, left / 48);
     c->smem_bytes = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)c->stage_ent * 128 + (size_t)c->stage_nodes * 256 + (size_t)c->stage_tris * 48;
-    CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-    CU(cudaFuncSetAttribute((const void*)trace_kernel(c->min_blocks), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CU(cudaFuncSetAttribute((const void*)trace_kernel(c->min_blocks, c->vote), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     int nb = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)wave_kernel(c->min_blocks), WF_BLOCK, c->smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)wave_kernel(c->min_blocks, c->vote), WF_BLOCK, c->smem_bytes));
     if (nb < 1) return fail(-2, "k_wavefront does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
     c->blocks_per_sm = nb;
+    return 0;
+}
+
+static WaveParams make_params(igb200_ctx* c, const RenderParams& rp, const DevScene& sc, long long total, const igb200_ray* d_rays, int defer) {
+    WaveParams P;
+    P.sc = sc; P.rp = rp;
+    P.q[0] = c->qa.view(); P.q[1] = c->qb.view();
+    P.sq = ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p};
+    P.fb = c->fb.p; P.ctl = c->control.p;
+    P.total = total; P.capacity = (int)c->capacity; P.list_rays = d_rays;
+    P.stage_nodes = c->stage_nodes; P.stage_tris = c->stage_tris; P.stage_ent = c->stage_ent;
+    P.refill = c->refill; P.defer = defer;
+    return P;
+}
+
+
+// One cooperative launch of the persistent kernel on the context's stream; asynchronous.
+static int launch_wave(igb200_ctx* c, const RenderParams& rp, const DevScene& sc, long long total, const igb200_ray* d_rays, int defer) {
+    WaveParams P = make_params(c, rp, sc, total, d_rays, defer);
+    CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
+    void* args[] = {&P};
+    CU(cudaLaunchCooperativeKernel((const void*)wave_kernel(c->min_blocks, c->vote), dim3((unsigned)(c->blocks_per_sm * c->n_sm)), dim3(WF_BLOCK), args, c->smem_bytes, c->stream));
+    c->launches += 1;
+    c->pending = true;
+    return 0;
+}
+
+// Finishes the paths earlier launches left behind (deferred tail): one more launch without camera rays that runs every
+// path to its end. Everything that observes results (framebuffer, statistics) or changes what carried records refer to
+// (scene, size, partition, spi) calls this first.
+static int drain(igb200_ctx* c) {
+    if (c->maybe_carry) {
+        CU(cudaSetDevice(c->device));
+        const int r = launch_wave(c, c->last_rp, c->last_sc, 0, nullptr, 0);
+        if (r) return r;
+        c->maybe_carry = false;
+    }
+    return 0;
+}
+
+// drain + wait for the device + fetch the control block (statistics, logs)
+static int sync_control(igb200_ctx* c) {
+    { const int r = drain(c); if (r) return r; }
+    if (c->pending) {
+        CU(cudaSetDevice(c->device));
+        CU(cudaMemcpyAsync(c->host_control, c->control.p, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        c->pending = false;
+    }
     return 0;
 }
 
@@ -166,6 +228,7 @@ int igb200_create(int cuda_device, igb200_ctx** out) {
     CU(c->control.alloc(1));
     CU(cudaMemset(c->control.p, 0, sizeof(Control)));
     CU(cudaMallocHost(&c->host_control, sizeof(Control)));
+    std::memset(c->host_control, 0, sizeof(Control));
     CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
     *out = c;
     return 0;
@@ -185,7 +248,10 @@ int igb200_destroy(igb200_ctx* c) {
 
 int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return fail(-1, "igb200_set_option: null argument");
+    { const int r = sync_control(c); if (r) return r; }
     if (!strcmp(name, "capacity")) { if (value < 1024) return fail(-1, "capacity must be >= 1024"); c->want_capacity = (size_t)value; c->capacity = 0; return 0; }
+    if (!strcmp(name, "vote")) { if (value < 0 || value > 2) return fail(-1, "vote must be 0 or 2"); c->vote = value ? 2 : 0; if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); } return 0; }
+    if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 1000) return fail(-1, "defer_permille must be in [0, 1000]"); c->defer_permille = (int)value; return 0; }
     if (!strcmp(name, "profile_kernels")) return 0;   // phase times are always recorded by the persistent kernel
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
     if (!strcmp(name, "min_blocks")) {
@@ -206,6 +272,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
 int igb200_set_partition(igb200_ctx* c, int rank, int world, int tile_size) {
     if (!c) return fail(-1, "null context");
     if (world < 1 || rank < 0 || rank >= world || tile_size < 1) return fail(-1, "igb200_set_partition: invalid rank %d / world %d / tile %d", rank, world, tile_size);
+    { const int r = sync_control(c); if (r) return r; }
     c->rank = rank; c->world = world; c->tile = tile_size;
     return 0;
 }
@@ -213,6 +280,8 @@ int igb200_set_partition(igb200_ctx* c, int rank, int world, int tile_size) {
 int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     if (!c || !d) return fail(-1, "igb200_set_scene: null argument");
     CU(cudaSetDevice(c->device));
+    { const int r = sync_control(c); if (r) return r; }
+    if (d->technique.max_depth > 254) return fail(-4, "igb200_set_scene: max_depth %d > 254 is not supported (the depth travels in 8 bits of the ray record)", d->technique.max_depth);
     if (d->n_leaves != d->n_entities) return fail(-1, "igb200_set_scene: %d leaves for %d entities (one EntityLeaf1 per entity expected)", d->n_leaves, d->n_entities);
     if (d->shape_data_bytes % 16) return fail(-1, "igb200_set_scene: shapes dyn-table data must be a multiple of 16 bytes");
     for (int m = 0; m < d->n_materials; ++m)
@@ -378,7 +447,7 @@ int igb200_resize(igb200_ctx* c, int width, int height) {
     if (width < 1 || height < 1) return fail(-1, "igb200_resize: invalid size %dx%d", width, height);
     CU(cudaSetDevice(c->device));
     if (width == c->width && height == c->height) return 0;
-    CU(cudaStreamSynchronize(c->stream));
+    { const int r = sync_control(c); if (r) return r; }
     c->width = width; c->height = height;
     const size_t n = (size_t)width * height * 3;
     CU(c->fb.alloc(n));
@@ -395,6 +464,8 @@ int igb200_clear(igb200_ctx* c, const char* aov) {
     if (!c) return fail(-1, "null context");
     if (!is_color(aov)) return fail(-4, "igb200_clear: AOV '%s' does not exist (only the colour framebuffer is supported)", aov);
     CU(cudaSetDevice(c->device));
+    // paths still in flight belong to the image that is being thrown away: finish them first, then clear
+    { const int r = drain(c); if (r) return r; }
     if (c->fb.p) CU(cudaMemsetAsync(c->fb.p, 0, c->fb.n * sizeof(float), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -405,6 +476,7 @@ int igb200_framebuffer(igb200_ctx* c, const char* aov, float** host_ptr) {
     if (!is_color(aov)) return fail(-4, "igb200_framebuffer: AOV '%s' does not exist", aov);
     if (!c->fb.p) return fail(-1, "igb200_framebuffer: no framebuffer (call igb200_resize first)");
     CU(cudaSetDevice(c->device));
+    { const int r = drain(c); if (r) return r; }
     CU(cudaMemcpyAsync(c->host_fb, c->fb.p, c->fb.n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     *host_ptr = c->host_fb;
@@ -416,6 +488,7 @@ int igb200_framebuffer_device(igb200_ctx* c, const char* aov, float** device_ptr
     if (!is_color(aov)) return fail(-4, "igb200_framebuffer_device: AOV '%s' does not exist", aov);
     if (!c->fb.p) return fail(-1, "igb200_framebuffer_device: no framebuffer");
     CU(cudaSetDevice(c->device));
+    { const int r = drain(c); if (r) return r; }
     CU(cudaStreamSynchronize(c->stream));
     *device_ptr = c->fb.p;
     return 0;
@@ -426,6 +499,7 @@ int igb200_upload_framebuffer(igb200_ctx* c, const char* aov, const float* host_
     if (!is_color(aov)) return fail(-4, "igb200_upload_framebuffer: AOV '%s' does not exist", aov);
     if (!c->fb.p) return fail(-1, "igb200_upload_framebuffer: no framebuffer");
     CU(cudaSetDevice(c->device));
+    { const int r = drain(c); if (r) return r; }
     CU(cudaMemcpyAsync(c->fb.p, host_rgb, c->fb.n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -437,23 +511,41 @@ int igb200_stream(igb200_ctx* c, void** cuda_stream) {
     return 0;
 }
 
+int igb200_sync(igb200_ctx* c) {
+    if (!c) return fail(-1, "null context");
+    return sync_control(c);
+}
+
 int igb200_stats(igb200_ctx* c, uint64_t out[5], double* render_ms) {
     if (!c) return fail(-1, "null context");
-    if (out) { out[0] = c->rays[0]; out[1] = c->rays[1]; out[2] = c->rays[2]; out[3] = c->rays[3]; out[4] = c->launches; }
-    if (render_ms) *render_ms = c->render_ms;
+    { const int r = sync_control(c); if (r) return r; }
+    const Control& h = *c->host_control;
+    if (out) { out[0] = h.stat[0]; out[1] = h.stat[1]; out[2] = h.stat[2]; out[3] = h.stat[3]; out[4] = c->launches; }
+    if (render_ms) *render_ms = (double)h.kernel_ns * 1e-6;
     return 0;
 }
 
 int igb200_reset_stats(igb200_ctx* c) {
     if (!c) return fail(-1, "null context");
-    c->rays[0] = c->rays[1] = c->rays[2] = c->rays[3] = 0; c->launches = 0; c->render_ms = 0;
-    for (int k = 0; k < 4; ++k) { c->k_ms[k] = 0; c->k_launch[k] = 0; }
+    { const int r = sync_control(c); if (r) return r; }
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->control.p, 0, sizeof(Control), c->stream));   // nothing is carried after a drain
+    CU(cudaStreamSynchronize(c->stream));
+    std::memset(c->host_control, 0, sizeof(Control));
+    c->launches = 0;
     return 0;
 }
 
 int igb200_turn_log(igb200_ctx* c, uint32_t* items, uint32_t* trace_ns, uint32_t* shade_ns, int max_turns, int* n_turns) {
     if (!c || !items || !trace_ns || !shade_ns || !n_turns) return fail(-1, "igb200_turn_log: null argument");
-    if (!c->host_control) return fail(-1, "igb200_turn_log: no render yet");
+    // no drain here: the log describes the last launch as it ran (a drain would overwrite it)
+    if (c->pending) {
+        CU(cudaSetDevice(c->device));
+        CU(cudaMemcpyAsync(c->host_control, c->control.p, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        c->pending = c->maybe_carry;
+    }
     const Control& h = *c->host_control;
     const int n = (int)std::min<unsigned long long>(std::min<unsigned long long>(h.turns, TURN_LOG), (unsigned long long)std::max(max_turns, 0));
     for (int k = 0; k < n; ++k) { items[k] = h.turn_items[k]; trace_ns[k] = h.turn_trace_ns[k]; shade_ns[k] = h.turn_shade_ns[k]; }
@@ -462,27 +554,20 @@ int igb200_turn_log(igb200_ctx* c, uint32_t* items, uint32_t* trace_ns, uint32_t
 }
 
 int igb200_step_stats(igb200_ctx* c, uint64_t out[16]) {
-    if (!c || !out || !c->host_control) return fail(-1, "igb200_step_stats: null argument");
+    if (!c || !out) return fail(-1, "igb200_step_stats: null argument");
+    { const int r = sync_control(c); if (r) return r; }
     for (int k = 0; k < 16; ++k) out[k] = c->host_control->step_stats[k / 8][k % 8];
     return 0;
 }
 
 int igb200_kernel_times(igb200_ctx* c, double out_ms[4], uint64_t out_launches[4]) {
     if (!c) return fail(-1, "null context");
-    for (int k = 0; k < 4; ++k) { if (out_ms) out_ms[k] = c->k_ms[k]; if (out_launches) out_launches[k] = c->k_launch[k]; }
+    { const int r = sync_control(c); if (r) return r; }
+    const Control& h = *c->host_control;
+    const double ms[4] = {0, (double)h.phase_ns[0] * 1e-6, (double)h.phase_ns[1] * 1e-6, 0};
+    const uint64_t n[4] = {0, h.phases[0], h.phases[1], 0};
+    for (int k = 0; k < 4; ++k) { if (out_ms) out_ms[k] = ms[k]; if (out_launches) out_launches[k] = n[k]; }
     return 0;
-}
-
-static WaveParams make_params(igb200_ctx* c, const RenderParams& rp, const DevScene& sc, long long total, const igb200_ray* d_rays) {
-    WaveParams P;
-    P.sc = sc; P.rp = rp;
-    P.q[0] = c->qa.view(); P.q[1] = c->qb.view();
-    P.sq = ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p};
-    P.fb = c->fb.p; P.ctl = c->control.p;
-    P.total = total; P.capacity = (int)c->capacity; P.list_rays = d_rays;
-    P.stage_nodes = c->stage_nodes; P.stage_tris = c->stage_tris; P.stage_ent = c->stage_ent;
-    P.refill = c->refill;
-    return P;
 }
 
 int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* rays, size_t n_rays) {
@@ -521,47 +606,52 @@ int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* ra
         else { const float sw = tanf(cam.fov / 2); sc.scale_x = sw; sc.scale_y = sw / aspect; }
         sc.cam_tmin = cam.tmin; sc.cam_tmax = cam.tmax;
     }
+    // Paths carried over from the previous launch are shaded with this launch's parameters: anything they depend on
+    // must be unchanged, else they are finished first.
+    const igb200_settings& cs = c->carry_settings;
+    const bool compatible = !rays && cs.spi == st->spi && cs.width == W && cs.height == H && cs.frame == st->frame && cs.seed == st->seed &&
+                            c->carry_rank == rp.rank && c->carry_world == rp.world && c->carry_tile == rp.tile_w;
+    if (c->maybe_carry && !compatible) { const int r = drain(c); if (r) return r; }
+    if (st->iter < 0 || st->iter >= (1 << 24)) return fail(-1, "igb200_render: iteration %d out of range [0, 2^24)", st->iter);
     const igb200_ray* d_rays = nullptr;
     if (rays) {
+        { const int r = sync_control(c); if (r) return r; }   // the previous list may still be read
         CU(c->list_rays.alloc(n_rays));
         CU(cudaMemcpyAsync(c->list_rays.p, rays, n_rays * sizeof(igb200_ray), cudaMemcpyHostToDevice, c->stream));
         d_rays = c->list_rays.p;
     }
-    { const int r = ensure_queues(c, (size_t)std::max<long long>(total, 1)); if (r) return r; }
+    if ((size_t)std::max<long long>(total, 1) > c->capacity) {   // the queues are about to be reallocated
+        { const int r = sync_control(c); if (r) return r; }
+        { const int r = ensure_queues(c, (size_t)std::max<long long>(total, 1)); if (r) return r; }
+    }
 
-    // One cooperative launch runs the whole iteration; the only thing that comes back is the statistics block.
-    WaveParams P = make_params(c, rp, sc, total, d_rays);
-    CU(cudaMemsetAsync(c->control.p, 0, sizeof(Control), c->stream));
-    CU(cudaEventRecord(c->ev0, c->stream));
-    void* args[] = {&P};
-    CU(cudaLaunchCooperativeKernel((const void*)wave_kernel(c->min_blocks), dim3((unsigned)(c->blocks_per_sm * c->n_sm)), dim3(WF_BLOCK), args, c->smem_bytes, c->stream));
-    CU(cudaMemcpyAsync(c->host_control, c->control.p, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaEventRecord(c->ev1, c->stream));
-    CU(cudaEventSynchronize(c->ev1));
-    CU(cudaGetLastError());
-    float ms = 0; CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    c->render_ms += ms;
-    c->launches += 1;
-    const Control& h = *c->host_control;
-    c->rays[0] += h.stat[0]; c->rays[1] += h.stat[1]; c->rays[2] += h.stat[2]; c->rays[3] += h.stat[3];
-    c->k_ms[1] += (double)h.phase_ns[0] * 1e-6; c->k_launch[1] += h.phases[0];
-    c->k_ms[2] += (double)h.phase_ns[1] * 1e-6; c->k_launch[2] += h.phases[1];
+    // One cooperative launch runs the iteration (asynchronously: nothing comes back to the host). With a deferred tail
+    // the launch returns once at most `defer` paths are alive; they continue in the next launch or in a drain launch.
+    const long long cam_rays = (long long)W * H * st->spi / std::max(rp.world, 1);
+    const int defer = rays ? 0 : (int)std::min<long long>(cam_rays * c->defer_permille / 1000, (long long)c->capacity / 4);
+    { const int r = launch_wave(c, rp, sc, total, d_rays, defer); if (r) return r; }
+    c->maybe_carry = defer > 0;
+    c->carry_settings = *st; c->carry_settings.width = W; c->carry_settings.height = H;
+    c->carry_rank = rp.rank; c->carry_world = rp.world; c->carry_tile = rp.tile_w;
+    c->last_rp = rp; c->last_sc = sc;
+    if (rays) { const int r = sync_control(c); if (r) return r; }   // the caller may free `rays` after the call
     return 0;
 }
 
 // Runs the stand-alone trace phase over n imported rays. any_hit: rays go through the shadow queue and the fused splat
 // (unoccluded ray i adds 1 to fb[3 i]); else through the primary queue.
 static int run_trace(igb200_ctx* c, const igb200_ray* d_rays, const uint32_t* d_flags, size_t n, int any_hit, float* d_fb, int repeat, double* ms_per_pass) {
+    { const int r = sync_control(c); if (r) return r; }   // the hooks borrow the render queues
     { const int r = ensure_queues(c, n); if (r) return r; }
     if (n > c->capacity) return fail(-1, "igb200_trace_*: %zu rays exceed the queue capacity %zu", n, c->capacity);
     const int grid = c->blocks_per_sm * c->n_sm;
     k_import_rays<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(d_rays, d_flags, any_hit ? RAY_SHADOW : RAY_CAMERA, (int)n, c->qa.view(), ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, any_hit);
     for (int r = 0; r < repeat + (ms_per_pass ? 3 : 0); ++r) {
         if (ms_per_pass && r == 3) CU(cudaEventRecord(c->ev0, c->stream));
-        CU(cudaMemsetAsync(c->control.p, 0, sizeof(Control), c->stream));
+        CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
         if (!any_hit && r > 0) k_import_rays<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(d_rays, d_flags, RAY_CAMERA, (int)n, c->qa.view(), ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, 0);
-        trace_kernel(c->min_blocks)<<<grid, WF_BLOCK, c->smem_bytes, c->stream>>>(c->dev, c->qa.view(), any_hit ? 0 : (int)n, ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, any_hit ? (int)n : 0, d_fb,
-                                                                                     &c->control.p->fetch_trace, &c->control.p->stat[3], c->stage_nodes, c->stage_tris, c->stage_ent, c->refill);
+        trace_kernel(c->min_blocks, c->vote)<<<grid, WF_BLOCK, c->smem_bytes, c->stream>>>(c->dev, c->qa.view(), any_hit ? 0 : (int)n, ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, any_hit ? (int)n : 0, d_fb,
+                                                                                     &c->control.p->fetch_trace, &c->control.p->cam_launch, c->stage_nodes, c->stage_tris, c->stage_ent, c->refill);
     }
     if (ms_per_pass) {
         CU(cudaEventRecord(c->ev1, c->stream));

@@ -232,7 +232,8 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
     const int ray_id = (int)st.x;
     const int sample = ray_id % rp.spi;
     const int pixel = ray_id / rp.spi;
-    const int depth = (int)st.z;
+    const int depth = (int)(st.z & 0xFFu);
+    const int iter = (int)(st.z >> 8);   // the iteration that generated the path: it may be shaded by a later launch (deferred tail)
     const float eta = __uint_as_float(st.w);
     const C3 contrib = c3(pc.x, pc.y, pc.z);
     const float inv_pdf = pc.w;
@@ -275,7 +276,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
         const int bsdf = __float_as_int(m0.x);
         const int light_id = __float_as_int(m0.y);
         const V3 N = surf.local.c2;
-        Rng rnd; rnd.seed = random_seed(sample, rp.iter, rp.frame, pixel % rp.width, pixel / rp.width, rp.seed); rnd.counter = st.y;
+        Rng rnd; rnd.seed = random_seed(sample, iter, rp.frame, pixel % rp.width, pixel / rp.width, rp.seed); rnd.counter = st.y;
 
         // ---- on_hit, pathtracer.art:119-139
         if (light_id >= 0 && surf.is_entering) {
@@ -355,7 +356,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
                     const int bs = coalesced_append(sink.next_count);
                     sink.nq.org_tmin[bs] = make_float4(surf.point.x, surf.point.y, surf.point.z, 0.001f);
                     sink.nq.dir_tmax[bs] = make_float4(in_dir.x, in_dir.y, in_dir.z, IGB_FLT_MAX);
-                    sink.nq.state[bs] = make_uint4(st.x, rnd.counter, (uint32_t)(depth + 1), __float_as_uint(eta * s_eta));
+                    sink.nq.state[bs] = make_uint4(st.x, rnd.counter, st.z + 1u, __float_as_uint(eta * s_eta));
                     sink.nq.contrib[bs] = make_float4(fc.r, fc.g, fc.b, is_delta ? 0.0f : 1 / s_pdf);
                     sink.nq.ent[bs] = (int)RAY_BOUNCE;
                 }

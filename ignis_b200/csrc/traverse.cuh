@@ -314,6 +314,24 @@ struct Traversal {
         if (cur < 0 && ent >= 0) leaf_step(sc, sg);
         return (bits & TB_DONE) != 0;
     }
+
+    // The same pipeline scheduled by warp vote: lanes pop, then ONE visit kind (vote 1: the most wanted; vote 2: every
+    // kind wanted by at least half as many lanes as the most wanted) runs, lanes waiting for another kind keep their
+    // state. The kinds then run 2-3x wider than when all three sections execute back to back for whoever needs them.
+    // Must be called by all 32 lanes; `active` false lanes only vote. Returns true when this lane's traversal finished.
+    __device__ __forceinline__ bool turn_vote(const DevScene& sc, const Staged& sg, Stack& st, const float4* po, const float4* pd, bool active, int vote) {
+        bool fin = false;
+        if (active && cur == 0) fin = pop_step(st, po, pd);
+        const bool live = active && !fin;
+        const bool wN = live && cur > 0, wE = live && cur < 0 && ent < 0, wL = live && cur < 0 && ent >= 0;
+        const int nN = __popc(__ballot_sync(0xffffffffu, wN)), nE = __popc(__ballot_sync(0xffffffffu, wE)), nL = __popc(__ballot_sync(0xffffffffu, wL));
+        const int mx = max(nN, max(nE, nL));
+        const int need = vote >= 2 ? max(1, (mx + 1) >> 1) : max(1, mx);
+        if (nN >= need) { if (wN) node_step(sc, sg, st); }
+        if (nE >= need) { if (cur < 0 && ent < 0 && live) entity_step(sc, sg, st); }
+        if (nL >= need) { if (cur < 0 && ent >= 0 && live) leaf_step(sc, sg); }
+        return fin || (live && (bits & TB_DONE) != 0);
+    }
 };
 #undef IGB_CHILD
 

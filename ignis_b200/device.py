@@ -59,7 +59,7 @@ HIT_DTYPE = np.dtype([("ent_id", "<i4"), ("prim_id", "<i4"), ("t", "<f4"), ("u",
 
 # every symbol include/igb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["igb200_last_error", "igb200_version", "igb200_create", "igb200_destroy", "igb200_set_scene", "igb200_resize",
-           "igb200_set_partition", "igb200_render", "igb200_framebuffer", "igb200_framebuffer_device", "igb200_clear",
+           "igb200_set_partition", "igb200_render", "igb200_sync", "igb200_framebuffer", "igb200_framebuffer_device", "igb200_clear",
            "igb200_upload_framebuffer", "igb200_stats", "igb200_reset_stats", "igb200_kernel_times", "igb200_turn_log", "igb200_step_stats", "igb200_set_option",
            "igb200_stream", "igb200_trace_closest", "igb200_trace_any", "igb200_bench_trace", "igb200_test_detmath"]
 
@@ -88,6 +88,7 @@ def lib():
         L.igb200_resize.argtypes = [vp, C.c_int, C.c_int]
         L.igb200_set_partition.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         L.igb200_render.argtypes = [vp, C.POINTER(Settings), vp, C.c_size_t]
+        L.igb200_sync.argtypes = [vp]
         L.igb200_framebuffer.argtypes = [vp, C.c_char_p, C.POINTER(C.POINTER(C.c_float))]
         L.igb200_framebuffer_device.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
         L.igb200_clear.argtypes = [vp, C.c_char_p]
@@ -183,6 +184,10 @@ class B200Device:
             rays = np.ascontiguousarray(rays, RAY_DTYPE)
             _check(lib().igb200_render(self._h, C.byref(st), rays.ctypes.data, rays.shape[0]))
             self._w, self._h_ = rays.shape[0], 1
+
+    def sync(self):
+        """Finishes every outstanding path of earlier render() calls (deferred tail) and waits for the device."""
+        _check(lib().igb200_sync(self._h))
 
     def getFramebufferForHost(self, name: str = "") -> np.ndarray:
         """Borrowed view (H, W, 3) of the context-owned host buffer; valid until the next resize."""

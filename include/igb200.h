@@ -146,8 +146,16 @@ int igb200_resize(igb200_ctx* ctx, int width, int height);        /* IRenderDevi
 int igb200_set_partition(igb200_ctx* ctx, int rank, int world, int tile_size);
 
 /* One iteration: IRenderDevice::render, Device.cpp:1672-1682. `rays` non-null selects the list emitter of igtrace
- * (Runtime::trace, Runtime.cpp:389-446): width = n_rays, height = 1. Accumulates into the device framebuffer. */
+ * (Runtime::trace, Runtime.cpp:389-446): width = n_rays, height = 1. Accumulates into the device framebuffer.
+ * The call is ASYNCHRONOUS on the context's stream (the reference's GPU device ends every iteration with acc.sync(),
+ * driver/mapping_gpu.art:865): it returns once the iteration's kernel is enqueued, and the kernel itself may leave the
+ * last few deep paths of the iteration to be finished together with the next one ("deferred tail").
+ * Every entry point that observes results (igb200_framebuffer*, igb200_stats, igb200_sync, ...) or changes what
+ * in-flight paths refer to (scene, size, partition, spi, seed) first finishes all outstanding paths, so the
+ * observable behaviour is that of a synchronous render. */
 int igb200_render(igb200_ctx* ctx, const igb200_settings* settings, const igb200_ray* rays, size_t n_rays);
+/* Finishes every outstanding path of earlier igb200_render calls and waits for the device. */
+int igb200_sync(igb200_ctx* ctx);
 
 /* IRenderDevice::getFramebufferForHost, Device.cpp:1419-1451: copies the device framebuffer into a context-owned
  * pinned host buffer (RGB f32, width*height*3, row-major, sum over iterations). aov NULL/""/"Color" = main image. */
@@ -157,8 +165,8 @@ int igb200_clear(igb200_ctx* ctx, const char* aov_or_null);       /* clearFrameb
 int igb200_upload_framebuffer(igb200_ctx* ctx, const char* aov, const float* host_rgb); /* syncFramebufferHostToDevice */
 
 /* IRenderDevice::getStatistics (ray counters of src/runtime/Statistics.h:57-64): out = {camera rays, shadow rays,
- * bounce rays, framebuffer splats, kernel launches} since the last reset; render_ms = device time spent in
- * igb200_render (CUDA events on the render stream) since the last reset. */
+ * bounce rays, framebuffer splats, kernel launches} since the last reset; render_ms = device time spent in the
+ * kernels of igb200_render (sum of their durations, measured on the device with %globaltimer) since the last reset. */
 int igb200_stats(igb200_ctx* ctx, uint64_t out[5], double* render_ms);
 int igb200_reset_stats(igb200_ctx* ctx);
 
@@ -172,7 +180,9 @@ int igb200_turn_log(igb200_ctx* ctx, uint32_t* items, uint32_t* trace_ns, uint32
 /* Diagnostics build only (-DIGB_STEP_STATS; zeros otherwise), LAST igb200_render: for loop turns < 16 (out[0..7]) and
  * >= 16 (out[8..15]): inner-node visits, triangle-leaf visits, entity visits, max visits of one ray, rays traced. */
 int igb200_step_stats(igb200_ctx* ctx, uint64_t out[16]);
-int igb200_set_option(igb200_ctx* ctx, const char* name, int64_t value); /* "capacity", "refill", "stage_budget" */
+/* Tunables: "capacity" (records per ray queue), "refill" (lanes), "stage_budget" (bytes of shared memory for the staged
+ * scene), "min_blocks" (2|3 CTAs per SM), "vote" (0|2), "defer_permille" (deferred tail threshold, 0 = off). */
+int igb200_set_option(igb200_ctx* ctx, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a caller can record
  * its own events on it or order a collective after a render (the reference has one implicit device queue). */
 int igb200_stream(igb200_ctx* ctx, void** cuda_stream);
