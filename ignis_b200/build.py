@@ -53,5 +53,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+HOST_OUT = os.path.join(HERE, "libigb200_host.so")
+HOST_SOURCES = ["host/script_recognizer.cpp", "host/b200_device.cpp", "host/host_capi.cpp"]
+HOST_DEPS = HOST_SOURCES + ["host/script_recognizer.h", "host/b200_device.h", "host/ig_mirror.h", "../../include/igb200.h"]
+
+
+def build_host(force: bool = False) -> str:
+    """Builds ignis_b200/libigb200_host.so: the C++ plugin classes (IRenderDevice / ICompilerDevice / ig_get_interface)
+    over the C ABI, plus the C shim the tests drive them through. Host-only C++17, links libigb200.so."""
+    build()
+    if not force and os.path.exists(HOST_OUT):
+        t = os.path.getmtime(HOST_OUT)
+        if not any(os.path.getmtime(os.path.join(SRC, d)) > t for d in HOST_DEPS):
+            return HOST_OUT
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", "-o", HOST_OUT,
+           *[os.path.join(SRC, s) for s in HOST_SOURCES], "-L" + HERE, "-l:libigb200.so", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return HOST_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

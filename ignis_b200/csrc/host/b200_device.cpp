@@ -1,0 +1,212 @@
+// b200_device.cpp -- see b200_device.h. Host-only C++17; every device operation goes through the C ABI.
+#include "b200_device.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace igbh {
+
+// ------------------------------------------------------------------------------------------------ compiler device
+// The reference JIT-compiles `script` and returns the address of `function` (src/device/Compiler.cpp:13-46,53-64); failure
+// is nullptr / false and aborts the load (src/runtime/shader/ShaderManager.cpp:60-64). Here the stage body is parsed into a
+// StageDescriptor (script_recognizer.h); the handle is that descriptor. Unrecognised constructs fail the same way.
+bool B200CompilerDevice::compile(const Settings& settings, const std::string& script) const {
+    // the runtime only uses compile() to warm the JIT cache from `igc` (src/compiler/main.cpp); there is nothing to warm
+    (void)settings; (void)script;
+    return true;
+}
+
+void* B200CompilerDevice::compileAndGet(const Settings& settings, const std::string& script, const std::string& function) const {
+    (void)settings;
+    try {
+        std::unique_ptr<StageDescriptor> d(parse_stage(script, function));
+        std::lock_guard<std::mutex> lock(mMutex);
+        mStages.push_back(std::move(d));
+        return mStages.back().get();
+    } catch (const RecognizeError& e) {
+        set_last_error(function + ": " + e.what);
+        std::fprintf(stderr, "[igb200] cannot compile %s: %s\n", function.c_str(), e.what.c_str());
+        return nullptr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ render device
+void B200Device::error(const std::string& what) {
+    mError = what;
+    std::fprintf(stderr, "[igb200] %s\n", what.c_str());   // the reference logs with IG_LOG(L_ERROR) and carries on
+}
+
+B200Device::B200Device(const SetupSettings& settings) : mSetup(settings) {
+    if (igb200_create((int)settings.target.device(), &mCtx) != 0) { error(std::string("cannot create the device: ") + igb200_last_error()); mCtx = nullptr; }
+}
+
+B200Device::~B200Device() { if (mCtx) igb200_destroy(mCtx); }
+
+// Device.cpp:1667-1670: borrowed pointers, valid for the device's lifetime (Runtime.cpp:532-541). The upload itself waits
+// for the first render(): the material / light / camera descriptors only arrive with the shader set.
+void B200Device::assignScene(const SceneSettings& settings) { mScene = settings; mSceneDirty = true; }
+
+void B200Device::resize(size_t width, size_t height) {
+    if (!mCtx) return;
+    if (igb200_resize(mCtx, (int)width, (int)height) != 0) { error(igb200_last_error()); return; }
+    mWidth = width; mHeight = height; mHostPtr = nullptr;
+}
+
+// Device.cpp:1684-1690 drops cached uploads; the next render() re-uploads the scene.
+void B200Device::releaseAll() { mSceneDirty = true; }
+
+bool B200Device::setPartition(int rank, int world, int tile) {
+    if (!mCtx || igb200_set_partition(mCtx, rank, world, tile) != 0) { error(igb200_last_error()); return false; }
+    return true;
+}
+
+static void append(std::vector<uint8_t>& v, const void* p, size_t n) { const uint8_t* b = static_cast<const uint8_t*>(p); v.insert(v.end(), b, b + n); }
+
+// Turns (SceneDatabase, shader set, registries) into igb200_scene_desc and uploads it when anything changed.
+bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG::ParameterSet* global) {
+    if (!mScene.database || !mScene.entity_per_material) { error("render() before assignScene()"); return false; }
+    std::vector<igb200_material> materials;
+    std::vector<igb200_light> inf, fin;
+    igb200_camera camera; std::memset(&camera, 0, sizeof(camera));
+    igb200_technique technique{};
+    try {
+        if (set.HitShaders.size() != mScene.entity_per_material->size()) throw RecognizeError{"one hit shader per material expected"};
+        const StageDescriptor* light_stage = nullptr; const IG::ParameterSet* light_local = nullptr;
+        for (const auto& hs : set.HitShaders) {
+            const StageDescriptor* d = static_cast<const StageDescriptor*>(hs.Exec);
+            if (!d) throw RecognizeError{"null hit shader"};
+            materials.push_back(resolve_material(*d, Registries{hs.LocalRegistry.get(), global}));
+            if (!light_stage && d->has_lights) { light_stage = d; light_local = hs.LocalRegistry.get(); }
+        }
+        const StageDescriptor* miss = static_cast<const StageDescriptor*>(set.MissShader.Exec);
+        if (miss && miss->has_lights) { light_stage = miss; light_local = set.MissShader.LocalRegistry.get(); }
+        if (!light_stage) throw RecognizeError{"no stage carries the light tables"};
+        resolve_lights(*light_stage, Registries{light_local, global}, inf, fin);
+        technique = resolve_technique(*light_stage, Registries{light_local, global});
+        const StageDescriptor* rg = static_cast<const StageDescriptor*>(set.RayGenerationShader.Exec);
+        if (!rg) throw RecognizeError{"null ray generation shader"};
+        if (rg->has_camera) camera = resolve_camera(*rg, Registries{set.RayGenerationShader.LocalRegistry.get(), global});
+    } catch (const RecognizeError& e) { error("cannot bind the shader set: " + e.what); return false; }
+
+    std::vector<uint8_t> bytes;
+    append(bytes, materials.data(), materials.size() * sizeof(igb200_material));
+    append(bytes, inf.data(), inf.size() * sizeof(igb200_light));
+    append(bytes, fin.data(), fin.size() * sizeof(igb200_light));
+    append(bytes, &camera, sizeof(camera));
+    append(bytes, &technique, sizeof(technique));
+    if (!mSceneDirty && bytes == mDescriptorBytes) return true;
+
+    const IG::SceneDatabase& db = *mScene.database;
+    const auto ent = db.FixTables.find("entities");
+    const auto shp = db.DynTables.find("shapes");
+    if (ent == db.FixTables.end() || shp == db.DynTables.end()) { error("scene database without 'entities' / 'shapes' tables"); return false; }
+    std::vector<uint8_t> leaves;   // EntityLeaf1 of every provider's scene BVH (src/runtime/bvh/SceneBVHAdapter.h:68-100)
+    for (const auto& kv : db.SceneBVHs) append(leaves, kv.second.Leaves.data(), kv.second.Leaves.size());
+    static_assert(sizeof(igb200_entity_leaf) == 96 && sizeof(igb200_lookup_entry) == sizeof(IG::LookupEntry), "layout");
+
+    igb200_scene_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.entities = reinterpret_cast<const float*>(ent->second.data().data());
+    d.n_entities = (int32_t)(ent->second.data().size() / (36 * sizeof(float)));
+    d.shape_lookups = reinterpret_cast<const igb200_lookup_entry*>(shp->second.lookups().data());
+    d.n_shapes = (int32_t)shp->second.lookups().size();
+    d.shape_data = shp->second.data().data();
+    d.shape_data_bytes = shp->second.data().size();
+    d.leaves = reinterpret_cast<const igb200_entity_leaf*>(leaves.data());
+    d.n_leaves = (int32_t)(leaves.size() / sizeof(igb200_entity_leaf));
+    d.entity_per_material = mScene.entity_per_material->data();
+    d.n_materials = (int32_t)materials.size();
+    d.materials = materials.data();
+    d.infinite_lights = inf.data(); d.n_infinite = (int32_t)inf.size();
+    d.finite_lights = fin.data(); d.n_finite = (int32_t)fin.size();
+    d.camera = camera; d.technique = technique;
+    for (int k = 0; k < 3; ++k) { d.bbox_min[k] = db.SceneBBox.min.v[k]; d.bbox_max[k] = db.SceneBBox.max.v[k]; }
+    if (igb200_set_scene(mCtx, &d) != 0) { error(std::string("scene upload failed: ") + igb200_last_error()); return false; }
+    mDescriptorBytes.swap(bytes);
+    mSceneDirty = false;
+    return true;
+}
+
+// Device.cpp:1672-1682. One iteration, accumulated into the framebuffer. Asynchronous on the device (igb200.h).
+void B200Device::render(const IG::TechniqueVariantShaderSet& shader_set, const RenderSettings& settings, IG::ParameterSet* parameter_set) {
+    if (!mCtx) { error("render() on an invalid device"); return; }
+    if (!uploadScene(shader_set, parameter_set)) return;
+    igb200_settings st;
+    st.device = (int32_t)mSetup.target.device(); st.thread_count = 0; st.spi = (int32_t)settings.spi; st.frame = (int32_t)settings.frame;
+    st.iter = (int32_t)settings.iteration; st.width = (int32_t)settings.width; st.height = (int32_t)settings.height; st.seed = (int32_t)settings.user_seed;
+    int rc;
+    if (settings.rays) {   // Device.cpp:602-643: directions are normalised on upload
+        std::vector<igb200_ray> rays(settings.width);
+        for (size_t i = 0; i < settings.width; ++i) {
+            const IG::Ray& r = settings.rays[i];
+            const float dx = r.Direction.v[0], dy = r.Direction.v[1], dz = r.Direction.v[2];
+            const float n = std::sqrt(dx * dx + dy * dy + dz * dz);
+            igb200_ray& o = rays[i];
+            o.org[0] = r.Origin.v[0]; o.org[1] = r.Origin.v[1]; o.org[2] = r.Origin.v[2];
+            o.dir[0] = dx / n; o.dir[1] = dy / n; o.dir[2] = dz / n;
+            o.tmin = r.Range.v[0]; o.tmax = r.Range.v[1];
+        }
+        rc = igb200_render(mCtx, &st, rays.data(), rays.size());
+        mWidth = settings.width; mHeight = 1;
+    } else {
+        rc = igb200_render(mCtx, &st, nullptr, 0);
+        mWidth = settings.width; mHeight = settings.height;
+    }
+    if (rc != 0) error(std::string("render failed: ") + igb200_last_error());
+}
+
+static const char* aov_name(const std::string& name) { return (name.empty() || name == "Color") ? nullptr : name.c_str(); }
+
+// Device.cpp:1419-1451: RGB f32, W*H*3, owned by the device, valid until resize.
+IG::IRenderDevice::AOVAccessor B200Device::getFramebufferForHost(const std::string& name, bool) {
+    float* p = nullptr;
+    if (!mCtx || igb200_framebuffer(mCtx, aov_name(name), &p) != 0) { error(igb200_last_error()); return AOVAccessor{nullptr}; }
+    mHostPtr = p;
+    return AOVAccessor{p};
+}
+IG::IRenderDevice::AOVAccessor B200Device::getFramebufferForDevice(const std::string& name, bool) {
+    float* p = nullptr;
+    if (!mCtx || igb200_framebuffer_device(mCtx, aov_name(name), &p) != 0) { error(igb200_last_error()); return AOVAccessor{nullptr}; }
+    return AOVAccessor{p};
+}
+void B200Device::clearFramebuffer(const std::string& name) { if (mCtx && igb200_clear(mCtx, aov_name(name)) != 0) error(igb200_last_error()); }
+void B200Device::clearAllFramebuffer() { if (mCtx && igb200_clear(mCtx, nullptr) != 0) error(igb200_last_error()); }
+// Device.cpp:1724-1736: pushes the host copy the caller may have modified back to the device
+void B200Device::syncFramebufferHostToDevice(const std::string& name) {
+    if (!mCtx || !mHostPtr) return;
+    if (igb200_upload_framebuffer(mCtx, aov_name(name), mHostPtr) != 0) error(igb200_last_error());
+}
+void B200Device::syncAllFramebufferHostToDevice() { syncFramebufferHostToDevice(""); }
+
+// Named scratch buffers belong to techniques outside this path (photon mapper, AEPT): none exist here.
+size_t B200Device::getBufferSizeInBytes(const std::string&) { return 0; }
+bool B200Device::copyBufferToHost(const std::string& name, void*, size_t) { error("buffer '" + name + "' does not exist on this device"); return false; }
+IG::IRenderDevice::BufferAccessor B200Device::getBufferForDevice(const std::string&) { return BufferAccessor{nullptr, 0}; }
+
+const IG::Statistics* B200Device::getStatistics() {
+    uint64_t s[5]; double ms = 0;
+    if (!mCtx || igb200_stats(mCtx, s, &ms) != 0) return nullptr;
+    mStats.CameraRayCount = s[0]; mStats.ShadowRayCount = s[1]; mStats.BounceRayCount = s[2]; mStats.RenderMilliseconds = ms;
+    return &mStats;
+}
+
+// Post kernels are outside the hot path: reported, never silently emulated.
+void B200Device::tonemap(uint32_t*, const IG::TonemapSettings&) { error("tonemap is not supported by the B200 device (viewer-only post kernel)"); }
+IG::ImageInfoOutput B200Device::imageinfo(const IG::ImageInfoSettings&) { error("imageinfo is not supported by the B200 device"); return IG::ImageInfoOutput{}; }
+void B200Device::bake(const IG::ShaderOutput<void*>&, const std::vector<std::string>*, float*) { error("bake is not supported by the B200 device"); }
+void B200Device::runPass(const IG::ShaderOutput<void*>&) { error("runPass is not supported by the B200 device"); }
+
+IG::IRenderDevice* B200DeviceInterface::createRenderDevice(const IG::IRenderDevice::SetupSettings& settings) const {
+    B200Device* d = new B200Device(settings);
+    if (!d->valid()) { delete d; return nullptr; }
+    return d;
+}
+
+}  // namespace igbh
+
+// src/device/Interface.cpp:70-76
+extern "C" const IG::IDeviceInterface* ig_get_interface() {
+    static const igbh::B200DeviceInterface interface;
+    return &interface;
+}

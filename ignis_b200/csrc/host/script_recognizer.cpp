@@ -1,0 +1,525 @@
+// script_recognizer.cpp -- see script_recognizer.h. Host-only C++17, no CUDA.
+#include "script_recognizer.h"
+
+#include <cctype>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+
+namespace igbh {
+
+static thread_local std::string g_last_error;
+const std::string& last_error() { return g_last_error; }
+void set_last_error(const std::string& e) { g_last_error = e; }
+
+[[noreturn]] static void fail(const std::string& what) { throw RecognizeError{what}; }
+
+// ============================================================================================== stage body -> lets
+static bool ident_char(char c) { return std::isalnum((unsigned char)c) || c == '_'; }
+
+static std::string trim(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && std::isspace((unsigned char)s[a])) ++a;
+    while (b > a && std::isspace((unsigned char)s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+
+// Body of the LAST definition of `fn <function>(` in the script (the generated stage follows the standard library,
+// src/runtime/shader/ScriptCompiler.cpp:36-51).
+static std::string function_body(const std::string& script, const std::string& function) {
+    const std::string key = "fn " + function + "(";
+    const size_t at = script.rfind(key);
+    if (at == std::string::npos) fail("function '" + function + "' not found in the script");
+    // skip the parameter list, then the return type up to the opening brace of the body
+    size_t p = at + key.size();
+    int depth = 1;
+    while (p < script.size() && depth > 0) { if (script[p] == '(') ++depth; else if (script[p] == ')') --depth; ++p; }
+    while (p < script.size() && script[p] != '{') ++p;
+    if (p >= script.size()) fail("function '" + function + "' has no body");
+    const size_t open = p;
+    depth = 0;
+    for (; p < script.size(); ++p) {
+        const char c = script[p];
+        if (c == '"') { ++p; while (p < script.size() && script[p] != '"') ++p; continue; }
+        if (c == '{') ++depth;
+        else if (c == '}') { if (--depth == 0) return script.substr(open + 1, p - open - 1); }
+    }
+    fail("unbalanced braces in '" + function + "'");
+}
+
+// Splits a block body into statements at top-level ';' (strings, (), {}, [] respected; `//` comments dropped).
+static std::vector<std::string> statements(const std::string& body) {
+    std::vector<std::string> out;
+    std::string cur;
+    int depth = 0;
+    for (size_t i = 0; i < body.size(); ++i) {
+        const char c = body[i];
+        if (c == '/' && i + 1 < body.size() && body[i + 1] == '/') { while (i < body.size() && body[i] != '\n') ++i; continue; }
+        if (c == '"') { cur += c; ++i; while (i < body.size() && body[i] != '"') cur += body[i++]; cur += '"'; continue; }
+        if (c == '(' || c == '{' || c == '[') ++depth;
+        if (c == ')' || c == '}' || c == ']') --depth;
+        if (c == ';' && depth == 0) { const std::string t = trim(cur); if (!t.empty()) out.push_back(t); cur.clear(); continue; }
+        cur += c;
+    }
+    const std::string t = trim(cur);
+    if (!t.empty()) out.push_back(t);
+    return out;
+}
+
+static StageKind kind_of(const std::string& function) {
+    static const struct { const char* name; StageKind k; } table[] = {   // src/runtime/Runtime.cpp:631-657,779
+        {"ig_ray_generation_shader", StageKind::RayGeneration}, {"ig_miss_shader", StageKind::Miss}, {"ig_hit_shader", StageKind::Hit},
+        {"ig_traversal_shader", StageKind::Traversal}, {"ig_callback_shader", StageKind::Callback}, {"ig_advanced_shadow_shader", StageKind::AdvancedShadow},
+        {"ig_tonemap_shader", StageKind::Tonemap}, {"ig_imageinfo_shader", StageKind::ImageInfo}, {"ig_pass_main", StageKind::Pass}, {"ig_bake_shader", StageKind::Bake}};
+    for (const auto& e : table) if (function == e.name) return e.k;
+    fail("unknown stage entry point '" + function + "'");
+}
+
+// `LightTable { count = N, get = @|id:i32| { match(id) { 0 => light_a, ... _ => make_null_light(id) } }}` (LoaderLight.cpp:131-148,199-246)
+static std::vector<std::string> light_table(const std::string& expr, const std::string& which) {
+    std::vector<std::string> names;
+    const std::string e = trim(expr);
+    if (e.rfind("LightTable", 0) != 0) {
+        // embedded fix-table lights (>= 10 simple lights, LoaderLight.h:27) and proxies are not on the supported path
+        fail(which + " is not a LightTable literal ('" + e.substr(0, 60) + "...'): embedded / proxy light tables are not supported by this device");
+    }
+    const size_t cnt = e.find("count");
+    if (cnt == std::string::npos) fail(which + ": LightTable without count");
+    size_t p = e.find('=', cnt);
+    const long count = std::strtol(e.c_str() + p + 1, nullptr, 10);
+    const size_t m = e.find("match");
+    if (m == std::string::npos) { if (count == 0) return names; fail(which + ": LightTable without match"); }
+    p = e.find('{', m);
+    while (p != std::string::npos) {
+        const size_t arrow = e.find("=>", p);
+        if (arrow == std::string::npos) break;
+        size_t k = arrow;   // key = token before "=>"
+        while (k > 0 && std::isspace((unsigned char)e[k - 1])) --k;
+        size_t k0 = k;
+        while (k0 > 0 && (ident_char(e[k0 - 1]))) --k0;
+        const std::string key = e.substr(k0, k - k0);
+        size_t v = arrow + 2;
+        while (v < e.size() && std::isspace((unsigned char)e[v])) ++v;
+        size_t v1 = v;
+        while (v1 < e.size() && ident_char(e[v1])) ++v1;
+        const std::string val = e.substr(v, v1 - v);
+        if (key != "_") {
+            if ((long)names.size() != std::strtol(key.c_str(), nullptr, 10)) fail(which + ": LightTable ids are not consecutive");
+            names.push_back(val);
+        }
+        p = v1;
+    }
+    if ((long)names.size() != count) fail(which + ": LightTable count does not match its entries");
+    return names;
+}
+
+StageDescriptor* parse_stage(const std::string& script, const std::string& function) {
+    auto d = std::make_unique<StageDescriptor>();
+    d->kind = kind_of(function);
+    d->function = function;
+    const std::string body = function_body(script, function);
+    for (const std::string& st : statements(body)) {
+        if (st.rfind("let ", 0) != 0) continue;   // calls (`device.handle_hit_shader(...)`, `maybe_unused(x)`) carry no parameters
+        size_t p = 4;
+        while (p < st.size() && std::isspace((unsigned char)st[p])) ++p;
+        size_t q = p;
+        if (st[p] == '(') { while (q < st.size() && st[q] != ')') ++q; ++q; }   // tuple pattern: kept under its text
+        else while (q < st.size() && ident_char(st[q])) ++q;
+        const std::string name = st.substr(p, q - p);
+        // skip an optional `: Type` up to the '=' of the binding (types contain no '=')
+        const size_t eq = st.find('=', q);
+        if (eq == std::string::npos) continue;
+        d->index[name] = d->lets.size();
+        d->lets.push_back(Binding{name, trim(st.substr(eq + 1))});
+    }
+    auto has = [&](const char* n) { return d->index.count(n) != 0; };
+    auto expr = [&](const char* n) -> const std::string& { return d->lets[d->index.at(n)].expr; };
+    if (has("infinite_lights")) { d->infinite_lights = light_table(expr("infinite_lights"), "infinite_lights"); d->has_lights = true; }
+    if (has("finite_lights")) d->finite_lights = light_table(expr("finite_lights"), "finite_lights");
+    d->has_technique = has("technique");
+    d->has_camera = has("camera");
+    if (has("emitter")) d->list_emitter = expr("emitter").rfind("make_list_emitter", 0) == 0;   // RayGenerationShader.cpp:59-60
+    if (d->kind == StageKind::Hit) {
+        if (!has("shader")) fail("ig_hit_shader without a material shader binding");
+        const std::string& sh = expr("shader");   // ShaderUtils.cpp:127-142
+        d->emissive = sh.find("make_emissive_material") != std::string::npos;
+        if (!d->emissive && sh.find("make_material") == std::string::npos) fail("unrecognised material shader '" + sh + "'");
+        const size_t b = sh.find("bsdf_");
+        if (b == std::string::npos) fail("material shader without a bsdf binding: '" + sh + "'");
+        size_t e = b;
+        while (e < sh.size() && ident_char(sh[e])) ++e;
+        d->bsdf_binding = sh.substr(b, e - b);
+        if (!has(d->bsdf_binding.c_str())) fail("material shader uses undefined '" + d->bsdf_binding + "'");
+        if (sh.find("no_medium_interface") == std::string::npos && has("medium_interface") && expr("medium_interface").find("no_medium_interface") == std::string::npos)
+            fail("participating media are not supported by this device");
+        if (!d->has_technique) fail("ig_hit_shader without a technique");
+    }
+    if (d->kind == StageKind::RayGeneration && !d->has_camera && !d->list_emitter) fail("ig_ray_generation_shader without camera or list emitter");
+    if (d->kind == StageKind::RayGeneration && has("pixel_sampler") && expr("pixel_sampler").find("make_uniform_pixel_sampler") == std::string::npos)
+        fail("pixel sampler '" + expr("pixel_sampler") + "' is not supported (uniform only)");
+    return d.release();
+}
+
+// ============================================================================================== expression evaluator
+namespace {
+
+struct Val {
+    enum Kind { Num, Vec, Sym, Ctor } kind = Num;
+    float f[4] = {0, 0, 0, 0};
+    int n = 1;                    // Vec: number of components
+    std::string name;             // Sym: the identifier; Ctor: constructor name
+    std::vector<Val> args;        // Ctor
+    static Val num(float x) { Val v; v.kind = Num; v.f[0] = x; return v; }
+    static Val vec(float x, float y, float z) { Val v; v.kind = Vec; v.n = 3; v.f[0] = x; v.f[1] = y; v.f[2] = z; return v; }
+    static Val sym(const std::string& s) { Val v; v.kind = Sym; v.name = s; return v; }
+};
+
+struct Eval {
+    const StageDescriptor& st;
+    const Registries& reg;
+    int depth = 0;
+
+    // ---- lexer over one expression string
+    struct Cursor { const std::string* s; size_t p; };
+    static void ws(Cursor& c) { while (c.p < c.s->size() && std::isspace((unsigned char)(*c.s)[c.p])) ++c.p; }
+    static bool eat(Cursor& c, const char* tok) {
+        ws(c);
+        const size_t n = std::strlen(tok);
+        if (c.s->compare(c.p, n, tok) == 0) { c.p += n; return true; }
+        return false;
+    }
+    static bool peek(Cursor& c, const char* tok) { ws(c); return c.s->compare(c.p, std::strlen(tok), tok) == 0; }
+    static bool at_end(Cursor& c) { ws(c); return c.p >= c.s->size(); }
+
+    static std::string path(Cursor& c) {   // ident (:: ident | . ident)*
+        ws(c);
+        std::string out;
+        for (;;) {
+            const size_t b = c.p;
+            while (c.p < c.s->size() && ident_char((*c.s)[c.p])) ++c.p;
+            if (c.p == b) fail("identifier expected at '" + c.s->substr(b, 30) + "'");
+            out += c.s->substr(b, c.p - b);
+            if (c.s->compare(c.p, 2, "::") == 0) { out += "::"; c.p += 2; continue; }
+            if (c.p + 1 < c.s->size() && (*c.s)[c.p] == '.' && (std::isalpha((unsigned char)(*c.s)[c.p + 1]) || (*c.s)[c.p + 1] == '_')) { out += '.'; ++c.p; continue; }
+            break;
+        }
+        return out;
+    }
+
+    static void skip_type(Cursor& c) {   // after ':' or '->' or 'as': a type name, possibly with generics / & prefixes
+        ws(c);
+        while (c.p < c.s->size() && ((*c.s)[c.p] == '&' || std::isspace((unsigned char)(*c.s)[c.p]))) ++c.p;
+        while (c.p < c.s->size() && (ident_char((*c.s)[c.p]) || (*c.s)[c.p] == ':' )) { if ((*c.s)[c.p] == ':' && c.s->compare(c.p, 2, "::") != 0) break; ++c.p; }
+    }
+
+    Val expr(Cursor& c) {
+        Val l = term(c);
+        for (;;) {
+            if (peek(c, "->") ) break;
+            if (eat(c, "+")) { l = arith('+', l, term(c)); continue; }
+            if (peek(c, "-") && !peek(c, "->")) { eat(c, "-"); l = arith('-', l, term(c)); continue; }
+            break;
+        }
+        return l;
+    }
+    Val term(Cursor& c) {
+        Val l = unary(c);
+        for (;;) {
+            if (eat(c, "*")) { l = arith('*', l, unary(c)); continue; }
+            if (peek(c, "/") && !peek(c, "//")) { eat(c, "/"); l = arith('/', l, unary(c)); continue; }
+            break;
+        }
+        return l;
+    }
+    Val unary(Cursor& c) {
+        if (peek(c, "-") && !peek(c, "->")) { eat(c, "-"); return arith('*', Val::num(-1.0f), unary(c)); }
+        Val v = primary(c);
+        for (;;) {   // `x as f32`
+            ws(c);
+            if (c.s->compare(c.p, 3, "as ") == 0) { c.p += 3; skip_type(c); continue; }
+            break;
+        }
+        return v;
+    }
+
+    static Val arith(char op, const Val& a, const Val& b) {
+        if (a.kind == Val::Sym || b.kind == Val::Sym || a.kind == Val::Ctor || b.kind == Val::Ctor) {
+            // an expression over run-time quantities (e.g. settings.width as f32 / settings.height as f32): stays symbolic
+            Val v; v.kind = Val::Sym; v.name = "(" + (a.kind == Val::Sym ? a.name : std::string("?")) + op + (b.kind == Val::Sym ? b.name : std::string("?")) + ")";
+            return v;
+        }
+        auto f = [&](float x, float y) { return op == '+' ? x + y : op == '-' ? x - y : op == '*' ? x * y : x / y; };   // f32 arithmetic, as Artic evaluates it
+        if (a.kind == Val::Num && b.kind == Val::Num) return Val::num(f(a.f[0], b.f[0]));
+        Val v; v.kind = Val::Vec; v.n = a.kind == Val::Vec ? a.n : b.n;
+        for (int i = 0; i < v.n; ++i) v.f[i] = f(a.kind == Val::Vec ? a.f[i] : a.f[0], b.kind == Val::Vec ? b.f[i] : b.f[0]);
+        return v;
+    }
+
+    Val closure(Cursor& c) {   // |params| [-> Type] (block | expr): the value of a closure is the value of its body
+        if (!eat(c, "|")) fail("closure expected");
+        while (c.p < c.s->size() && (*c.s)[c.p] != '|') ++c.p;
+        eat(c, "|");
+        if (eat(c, "->")) skip_type(c);
+        if (peek(c, "{")) return block(c);
+        return expr(c);
+    }
+
+    Val block(Cursor& c) {   // { stmt; stmt; expr }: statements other than the trailing expression are ignored
+        if (!eat(c, "{")) fail("block expected");
+        const size_t b = c.p;
+        int d = 1;
+        while (c.p < c.s->size() && d > 0) { const char ch = (*c.s)[c.p]; if (ch == '{') ++d; else if (ch == '}') --d; ++c.p; }
+        if (d != 0) fail("unbalanced block");
+        const std::string body = c.s->substr(b, c.p - 1 - b);
+        const std::vector<std::string> sts = statements(body);
+        if (sts.empty()) fail("empty block");
+        const std::string& last = sts.back();
+        if (last.rfind("let ", 0) == 0) fail("block ends in a binding: '" + last + "'");
+        // bodies that are real code (the `match` of a light table or of the AOV selector) stay opaque: they are only an
+        // error if a descriptor needs their value, which as_num / as_vec then report
+        try { return eval_text(last); } catch (const RecognizeError&) { return Val::sym("<code>"); }
+    }
+
+    Val primary(Cursor& c) {
+        ws(c);
+        if (at_end(c)) fail("unexpected end of expression");
+        const char ch = (*c.s)[c.p];
+        if (ch == '(') { eat(c, "("); Val v = expr(c); if (!eat(c, ")")) fail("')' expected in '" + *c.s + "'"); return v; }
+        if (ch == '@') { ++c.p; ws(c); if (peek(c, "|")) return closure(c); return primary(c); }   // `@|ctx| ...` or `@name(...)` (a PE annotation)
+        if (ch == '|') return closure(c);
+        if (ch == '{') return block(c);
+        if (ch == '"') { const size_t b = ++c.p; while (c.p < c.s->size() && (*c.s)[c.p] != '"') ++c.p; Val v = Val::sym(c.s->substr(b, c.p - b)); ++c.p; v.name = "\"" + v.name; return v; }
+        if (std::isdigit((unsigned char)ch) || (ch == '.' && c.p + 1 < c.s->size() && std::isdigit((unsigned char)(*c.s)[c.p + 1]))) {
+            char* end = nullptr;
+            const float x = std::strtof(c.s->c_str() + c.p, &end);   // literals are f32 (or i32) in the generated code
+            c.p = (size_t)(end - c.s->c_str());
+            if (c.p < c.s->size() && (*c.s)[c.p] == ':') { ++c.p; skip_type(c); }   // `0:f32`, `8:i32`
+            return Val::num(x);
+        }
+        std::string name = path(c);
+        if (name == "match") fail("match expressions are only understood inside LightTable literals");
+        ws(c);
+        if (peek(c, "(")) {
+            eat(c, "(");
+            std::vector<Val> args;
+            if (!peek(c, ")")) { do { args.push_back(expr(c)); } while (eat(c, ",")); }
+            if (!eat(c, ")")) fail("')' expected after the arguments of " + name);
+            return call(name, args);
+        }
+        if (peek(c, "{") && !name.empty() && std::isupper((unsigned char)name[0])) {   // struct literal: Name{ a = x, b = y }
+            eat(c, "{");
+            Val v; v.kind = Val::Ctor; v.name = name;
+            while (!peek(c, "}")) { path(c); if (!eat(c, "=")) fail("'=' expected in " + name + "{...}"); v.args.push_back(expr(c)); if (!eat(c, ",")) break; }
+            if (!eat(c, "}")) fail("'}' expected after " + name + "{...");
+            return v;
+        }
+        return identifier(name);
+    }
+
+    Val identifier(const std::string& name) {
+        if (name == "true") return Val::num(1.0f);
+        if (name == "false") return Val::num(0.0f);
+        if (name == "flt_pi") return Val::num(3.14159265359f);                     // core/common.art:3-8
+        if (name == "flt_inv_pi") return Val::num(0.31830988618379067154f);
+        if (name == "flt_eps") return Val::num(1.1920928955e-07f);
+        if (name == "flt_max") return Val::num(3.4028234664e+38f);
+        if (name == "color_builtins::black") return Val::vec(0, 0, 0);
+        if (name == "color_builtins::white") return Val::vec(1, 1, 1);
+        const auto it = st.index.find(name);
+        if (it != st.index.end()) {
+            if (++depth > 64) fail("binding '" + name + "' is recursive");
+            Val v = eval_text(st.lets[it->second].expr);
+            --depth;
+            return v;
+        }
+        return Val::sym(name);   // run-time quantity: settings.width, ctx.surf, device, entities, mat_id, ...
+    }
+
+    static float num_arg(const std::string& fn, const std::vector<Val>& a, size_t i) {
+        if (i >= a.size() || a[i].kind != Val::Num) fail(fn + ": argument " + std::to_string(i) + " is not a number");
+        return a[i].f[0];
+    }
+    static const Val& vec_arg(const std::string& fn, const std::vector<Val>& a, size_t i) {
+        if (i >= a.size() || a[i].kind != Val::Vec) fail(fn + ": argument " + std::to_string(i) + " is not a vector / colour");
+        return a[i];
+    }
+    static std::string key_arg(const std::string& fn, const std::vector<Val>& a) {
+        if (a.empty() || a[0].kind != Val::Sym || a[0].name.empty() || a[0].name[0] != '"') fail(fn + ": parameter name expected");
+        return a[0].name.substr(1);
+    }
+
+    Val call(const std::string& fn, const std::vector<Val>& a) {
+        // ---- registry look-ups (src/artic/driver/registry.art; values stored by ShadingTree.cpp:933-981, defaults as written in the script)
+        const bool local = fn.rfind("registry::get_local_parameter_", 0) == 0, global = fn.rfind("registry::get_global_parameter_", 0) == 0;
+        if (local || global) {
+            const IG::ParameterSet* ps = local ? reg.local : reg.global;
+            const std::string key = key_arg(fn, a);
+            const std::string ty = fn.substr(fn.rfind('_') + 1);
+            if (ps) {
+                if (ty == "i32") { const auto it = ps->IntParameters.find(key); if (it != ps->IntParameters.end()) return Val::num((float)it->second); }
+                else if (ty == "f32") { const auto it = ps->FloatParameters.find(key); if (it != ps->FloatParameters.end()) return Val::num(it->second); }
+                else if (ty == "vec3") { const auto it = ps->VectorParameters.find(key); if (it != ps->VectorParameters.end()) return Val::vec(it->second.v[0], it->second.v[1], it->second.v[2]); }
+                else if (ty == "color") { const auto it = ps->ColorParameters.find(key); if (it != ps->ColorParameters.end()) return Val::vec(it->second.v[0], it->second.v[1], it->second.v[2]); }
+                else fail("unsupported registry type in " + fn);
+            }
+            if (a.size() < 2) fail(fn + ": default value expected");
+            return a[1];   // not in the registry: the default written in the script, as the reference does
+        }
+        if (fn == "make_color") return Val::vec(num_arg(fn, a, 0), num_arg(fn, a, 1), num_arg(fn, a, 2));
+        if (fn == "make_gray_color") { const float g = num_arg(fn, a, 0); return Val::vec(g, g, g); }
+        if (fn == "make_vec3") return Val::vec(num_arg(fn, a, 0), num_arg(fn, a, 1), num_arg(fn, a, 2));
+        if (fn == "make_vec2") { Val v = Val::vec(num_arg(fn, a, 0), num_arg(fn, a, 1), 0); v.n = 2; return v; }
+        if (fn == "vec3_expand" || fn == "color_expand") { const float g = num_arg(fn, a, 0); return Val::vec(g, g, g); }
+        if (fn == "vec3_to_2") { Val v = vec_arg(fn, a, 0); v.n = 2; return v; }
+        if (fn == "color_mulf" || fn == "vec3_mulf") return arith('*', vec_arg(fn, a, 0), Val::num(num_arg(fn, a, 1)));
+        if (fn == "color_mul") return arith('*', vec_arg(fn, a, 0), vec_arg(fn, a, 1));
+        if (fn == "make_constant_texture") return vec_arg(fn, a, 0);   // texture/constant: the colour itself on this path
+        if (fn == "maybe_unused") return Val::num(0);
+        // a let-bound closure applied to run-time arguments (`bsdf_3(ctx)`, `md_3(ctx)`): its body
+        const auto it = st.index.find(fn);
+        if (it != st.index.end()) {
+            if (++depth > 64) fail("binding '" + fn + "' is recursive");
+            Val v = eval_text(st.lets[it->second].expr);
+            --depth;
+            return v;
+        }
+        Val v; v.kind = Val::Ctor; v.name = fn; v.args = a;
+        return v;
+    }
+
+    Val eval_text(const std::string& text) {
+        Cursor c{&text, 0};
+        Val v = expr(c);
+        if (!at_end(c)) fail("trailing text '" + text.substr(c.p, 40) + "' in expression '" + text.substr(0, 80) + "'");
+        return v;
+    }
+    Val binding(const std::string& name) {
+        const auto it = st.index.find(name);
+        if (it == st.index.end()) fail("binding '" + name + "' not found in " + st.function);
+        return eval_text(st.lets[it->second].expr);
+    }
+};
+
+const Val& ctor_arg(const Val& c, size_t i) {
+    if (i >= c.args.size()) fail(c.name + ": argument " + std::to_string(i) + " missing");
+    return c.args[i];
+}
+float as_num(const Val& v, const std::string& what) { if (v.kind != Val::Num) fail(what + " is not a compile-time number"); return v.f[0]; }
+const Val& as_vec(const Val& v, const std::string& what) { if (v.kind != Val::Vec) fail(what + " is not a compile-time vector / colour"); return v; }
+void put3(float* dst, const Val& v) { dst[0] = v.f[0]; dst[1] = v.f[1]; dst[2] = v.f[2]; }
+
+}  // namespace
+
+// ============================================================================================== descriptors
+igb200_material resolve_material(const StageDescriptor& hit, const Registries& r) {
+    if (hit.kind != StageKind::Hit) fail("resolve_material: not a hit stage");
+    Eval ev{hit, r};
+    const Val b = ev.binding(hit.bsdf_binding);
+    if (b.kind != Val::Ctor) fail(hit.bsdf_binding + " is not a BSDF constructor");
+    igb200_material m;
+    std::memset(&m, 0, sizeof(m));
+    m.light_id = -1;
+    if (hit.emissive) {   // ShaderUtils.cpp:127-136: the light id lives in the stage's LocalRegistry
+        if (!r.local || !r.local->IntParameters.count("_light_id")) fail("emissive material without '_light_id' in its local registry");
+        m.light_id = r.local->IntParameters.at("_light_id");
+    }
+    if (b.name == "make_diffuse_bsdf") {            // DiffuseBSDF.cpp:13-27; bsdf/diffuse.art:55-61
+        const float rough = as_num(ctor_arg(b, 1), "diffuse roughness");
+        if (rough > 1.1920928955e-07f) fail("rough (Oren-Nayar) diffuse BSDFs are not supported by this device");
+        m.bsdf = IGB200_BSDF_DIFFUSE;
+        put3(m.p, as_vec(ctor_arg(b, 2), "diffuse reflectance"));
+    } else if (b.name == "make_dielectric_bsdf") {  // DielectricBSDF.cpp:13-41; bsdf/dielectric.art:15-37,195
+        const Val& md = ctor_arg(b, 5);
+        if (md.kind != Val::Ctor || md.name != "microfacet::make_delta_distribution") fail("rough dielectric BSDFs are not supported by this device");
+        if (as_num(ctor_arg(b, 6), "dielectric thin flag") != 0) fail("thin dielectric BSDFs are not supported by this device");
+        m.bsdf = IGB200_BSDF_DIELECTRIC;
+        m.p[0] = as_num(ctor_arg(b, 1), "ext_ior"); m.p[1] = as_num(ctor_arg(b, 2), "int_ior");
+        put3(m.p + 2, as_vec(ctor_arg(b, 3), "specular_reflectance"));
+        put3(m.p + 5, as_vec(ctor_arg(b, 4), "specular_transmittance"));
+    } else {
+        fail("BSDF constructor '" + b.name + "' is not supported by this device");
+    }
+    return m;
+}
+
+static igb200_light resolve_light(Eval& ev, const std::string& binding) {
+    const Val l = ev.binding(binding);
+    if (l.kind != Val::Ctor) fail(binding + " is not a light constructor");
+    igb200_light out;
+    std::memset(&out, 0, sizeof(out));
+    out.entity_id = -1;
+    if (l.name == "make_environment_light") {       // EnvironmentLight.cpp:103-110; light/env.art:161-164: colour = scale * texture
+        const Val c = Eval::arith('*', as_vec(ctor_arg(l, 2), "environment scale"), as_vec(ctor_arg(l, 3), "environment radiance"));
+        out.type = IGB200_LIGHT_ENV_CONST;
+        put3(out.p, c);
+    } else if (l.name == "make_point_light") {      // PointLight.cpp:44-62
+        out.type = IGB200_LIGHT_POINT;
+        put3(out.p, as_vec(ctor_arg(l, 1), "point light origin"));
+        put3(out.p + 3, as_vec(ctor_arg(l, 2), "point light intensity"));
+    } else if (l.name == "make_area_light") {       // AreaLight.cpp:115-220
+        const Val& ae = ctor_arg(l, 1);
+        const Val rad = as_vec(ctor_arg(l, 2), "area light radiance");
+        if (ae.kind != Val::Ctor) fail("area light emitter is not a constructor");
+        if (ae.name == "make_plane_area_emitter") {
+            out.type = IGB200_LIGHT_PLANE_AREA;
+            put3(out.p, as_vec(ctor_arg(ae, 0), "plane origin")); put3(out.p + 3, as_vec(ctor_arg(ae, 1), "plane tangent"));
+            put3(out.p + 6, as_vec(ctor_arg(ae, 2), "plane bitangent")); put3(out.p + 9, as_vec(ctor_arg(ae, 3), "plane normal"));
+            out.p[12] = as_num(ctor_arg(ae, 4), "plane area");
+            for (int k = 0; k < 4; ++k) { const Val t = as_vec(ctor_arg(ae, 5 + k), "plane texcoord"); out.p[13 + 2 * k] = t.f[0]; out.p[14 + 2 * k] = t.f[1]; }
+            put3(out.p + 21, rad);
+        } else if (ae.name == "make_shape_area_emitter_proxy") {
+            out.type = IGB200_LIGHT_SHAPE_AREA;
+            out.entity_id = (int32_t)as_num(ctor_arg(ae, 0), "area light entity id");
+            put3(out.p, rad);
+        } else {
+            fail("area emitter '" + ae.name + "' is not supported by this device");
+        }
+    } else {
+        fail("light constructor '" + l.name + "' is not supported by this device");
+    }
+    return out;
+}
+
+void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vector<igb200_light>& infinite, std::vector<igb200_light>& finite) {
+    if (!stage.has_lights) fail(stage.function + " carries no light tables");
+    Eval ev{stage, r};
+    infinite.clear(); finite.clear();
+    for (const std::string& b : stage.infinite_lights) infinite.push_back(resolve_light(ev, b));
+    for (const std::string& b : stage.finite_lights) finite.push_back(resolve_light(ev, b));
+}
+
+igb200_technique resolve_technique(const StageDescriptor& stage, const Registries& r) {
+    if (!stage.has_technique) fail(stage.function + " carries no technique");
+    Eval ev{stage, r};
+    const Val t = ev.binding("technique");   // PathTechnique.cpp:35-79
+    if (t.kind != Val::Ctor || t.name != "make_path_renderer") fail("technique '" + (t.kind == Val::Ctor ? t.name : std::string("?")) + "' is not supported by this device (path only)");
+    const Val& sel = ctor_arg(t, 2);
+    if (sel.kind != Val::Ctor || sel.name != "make_uniform_light_selector") fail("light selector '" + sel.name + "' is not supported by this device (uniform only)");
+    igb200_technique out;
+    out.max_depth = (int32_t)as_num(ctor_arg(t, 0), "max_depth");
+    out.min_depth = (int32_t)as_num(ctor_arg(t, 1), "min_depth");
+    out.clamp = as_num(ctor_arg(t, 4), "clamp");
+    out.nee = as_num(ctor_arg(t, 5), "nee flag") != 0 ? 1 : 0;
+    return out;
+}
+
+igb200_camera resolve_camera(const StageDescriptor& raygen, const Registries& r) {
+    if (!raygen.has_camera) fail(raygen.function + " carries no camera");
+    Eval ev{raygen, r};
+    const Val c = ev.binding("camera");      // PerspectiveCamera.cpp:26-67
+    if (c.kind != Val::Ctor || c.name != "make_perspective_camera") fail("camera '" + (c.kind == Val::Ctor ? c.name : std::string("?")) + "' is not supported by this device (perspective only)");
+    igb200_camera out;
+    std::memset(&out, 0, sizeof(out));
+    put3(out.eye, as_vec(ctor_arg(c, 0), "camera eye")); put3(out.dir, as_vec(ctor_arg(c, 1), "camera dir")); put3(out.up, as_vec(ctor_arg(c, 2), "camera up"));
+    const Val& sc = ctor_arg(c, 3);
+    if (sc.kind != Val::Ctor || (sc.name != "compute_scale_from_hfov" && sc.name != "compute_scale_from_vfov")) fail("camera scale is not compute_scale_from_{h,v}fov");
+    out.fov_vertical = sc.name == "compute_scale_from_vfov";
+    out.fov = as_num(ctor_arg(sc, 0), "camera fov");
+    const Val& asp = ctor_arg(sc, 1);
+    out.aspect = asp.kind == Val::Num ? asp.f[0] : 0.0f;   // symbolic = settings.width / settings.height
+    out.tmin = as_num(ctor_arg(c, 6), "near clip"); out.tmax = as_num(ctor_arg(c, 7), "far clip");
+    return out;
+}
+
+}  // namespace igbh

@@ -1,0 +1,62 @@
+// script_recognizer.h -- the B200 device's replacement for the reference's JIT compiler device.
+//
+// The reference hands its device plugin *program text*: `ICompilerDevice::compileAndGet(settings, script, function)`
+// (src/runtime/device/ICompilerDevice.h:15, called from src/runtime/Runtime.cpp:631-657) receives the whole Artic
+// standard library followed by ONE generated stage function (`ig_hit_shader`, `ig_ray_generation_shader`, ...), and the
+// AnyDSL plugin JIT-compiles it (src/device/Compiler.cpp:13-46). A native device has no Artic compiler. What it needs
+// from the text is small and regular: the generators (src/runtime/shader/*.cpp, src/runtime/bsdf/*.cpp,
+// src/runtime/light/*.cpp, src/runtime/camera/PerspectiveCamera.cpp, src/runtime/technique/PathTechnique.cpp) only
+// ever emit `let` bindings whose right-hand sides are constructor calls with literal or registry-lookup arguments
+// (SURVEY.md Appendix D). This module parses the stage body into those bindings and evaluates the constructor
+// arguments against the stage's LocalRegistry and the global registry, yielding the plain descriptors of
+// include/igb200.h. Anything it does not recognise is an error (never a silent default): the stage handle is null
+// and the reason is in last_error(), which is how the reference reports a failed compile (ShaderManager.cpp:60-64).
+#pragma once
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../../include/igb200.h"
+#include "ig_mirror.h"
+
+namespace igbh {
+
+enum class StageKind { RayGeneration, Miss, Hit, Traversal, Device, Callback, AdvancedShadow, Tonemap, ImageInfo, Pass, Bake };
+
+// One `let name [: type] = expr;` of the stage body, expression kept as text until the registries are known.
+struct Binding { std::string name, expr; };
+
+// Opaque handle returned by compileAndGet: the parsed stage. Owned by the compiler device's cache.
+struct StageDescriptor {
+    StageKind kind;
+    std::string function;
+    std::vector<Binding> lets;                 // in source order
+    std::map<std::string, size_t> index;       // name -> position in lets (last definition wins)
+    // structure found at parse time (names of bindings; values are resolved later)
+    std::string bsdf_binding;                  // hit: `bsdf_<id>` used by the material shader
+    bool emissive = false;                     // hit: make_emissive_material(..., @finite_lights.get(light_id))
+    std::vector<std::string> infinite_lights;  // hit / miss: `light_<id>` bindings in table order
+    std::vector<std::string> finite_lights;
+    bool has_lights = false, has_technique = false, has_camera = false, list_emitter = false;
+};
+
+// Thrown by the evaluator; caught at the API boundary and turned into a null handle / false + last_error().
+struct RecognizeError { std::string what; };
+
+// ---- parse ---------------------------------------------------------------------------------------------------------
+// Finds `fn <function>(` in `script` (the stage function is the last one in the text) and parses its body.
+StageDescriptor* parse_stage(const std::string& script, const std::string& function);   // throws RecognizeError
+
+// ---- resolve against registries ------------------------------------------------------------------------------------
+struct Registries { const IG::ParameterSet* local; const IG::ParameterSet* global; };
+
+igb200_material resolve_material(const StageDescriptor& hit, const Registries& r);     // throws RecognizeError
+void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vector<igb200_light>& infinite, std::vector<igb200_light>& finite);
+igb200_technique resolve_technique(const StageDescriptor& stage, const Registries& r);
+igb200_camera resolve_camera(const StageDescriptor& raygen, const Registries& r);
+
+const std::string& last_error();
+void set_last_error(const std::string& e);
+
+}  // namespace igbh

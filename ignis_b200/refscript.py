@@ -1,0 +1,284 @@
+"""Stage scripts + registries as the reference's runtime would hand them to a device plugin.
+
+The reference's `Runtime` never gives a device descriptors: it gives it *program text* per pipeline stage plus parameter
+registries (`TechniqueVariantShaderSet` + `LocalRegistry`, src/runtime/technique/TechniqueVariant.h:12-35;
+`ICompilerDevice::compileAndGet(script, function)`, src/runtime/Runtime.cpp:631-657). The B200 plugin's compiler device
+(`csrc/host/script_recognizer.cpp`) parses that text back into descriptors. To test it without the reference's loader
+(which cannot be built here) this module RECONSTRUCTS the text from `SceneTables`, statement by statement
+after the generators:
+
+  stage prologue / database / scene     src/runtime/shader/ShaderUtils.cpp:13-53,55-62,101-141,174-204,206-216
+  ig_ray_generation_shader              src/runtime/shader/RayGenerationShader.cpp:12-70, camera/PerspectiveCamera.cpp:26-67
+  ig_hit_shader / ig_miss_shader        src/runtime/shader/HitShader.cpp:16-53, MissShader.cpp:15-47
+  BSDFs                                 src/runtime/bsdf/DiffuseBSDF.cpp:13-27, DielectricBSDF.cpp:13-41, BSDF.cpp:53-63
+  lights + tables                       src/runtime/light/{AreaLight.cpp:115-220, PointLight.cpp:44-62, EnvironmentLight.cpp:103-110},
+                                        src/runtime/loader/LoaderLight.cpp:106-247,423-453
+  technique                             src/runtime/technique/PathTechnique.cpp:35-79
+  value inlining rules                  src/runtime/loader/ShadingTree.cpp:868-981 (default specialisation: only all-zero / all-one
+                                        values are printed into the text, with std::to_string's 6 decimals; everything else goes
+                                        to the stage's LocalRegistry at full precision)
+
+It is a reconstruction, not a captured `--dump-shader` output: whitespace may differ, the grammar does not.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .scene import (BSDF_DIELECTRIC, BSDF_DIFFUSE, LIGHT_ENV_CONST, LIGHT_PLANE_AREA, LIGHT_POINT, LIGHT_SHAPE_AREA,
+                    SHAPE_SPHERE, SceneTables)
+
+STD_LIB_STUB = "// <the Artic standard library (ig_api[], ScriptCompiler.cpp:36-51) precedes every stage>\nfn @make_dummy() = 0;\n\n"
+
+
+@dataclass
+class Registry:
+    """ParameterSet, src/runtime/ParameterSet.h:6-12"""
+    ints: dict = field(default_factory=dict)
+    floats: dict = field(default_factory=dict)
+    vectors: dict = field(default_factory=dict)
+    colors: dict = field(default_factory=dict)
+
+
+@dataclass
+class Stage:
+    function: str
+    script: str
+    local: Registry
+
+
+@dataclass
+class StageSet:
+    raygen: Stage
+    miss: Stage
+    hits: list
+    global_registry: Registry
+
+
+def _ts(x: float) -> str:
+    return f"{float(x):.6f}"   # std::to_string(float)
+
+
+def _stream(x: float) -> str:
+    return f"{float(x):.6g}"   # operator<<(ostream&, float), default precision
+
+
+class _Tree:
+    """ShadingTree: closure ids + the inline-or-registry decision."""
+
+    def __init__(self, local: Registry, specialization: str):
+        self.local, self.mode, self.ids, self.header = local, specialization, {}, []
+
+    def closure(self, name: str) -> str:
+        return str(self.ids.setdefault(name, len(self.ids)))
+
+    def _embed(self, vals, zero=True, one=True) -> bool:
+        if self.mode == "force":
+            return True
+        if self.mode == "disable":
+            return False
+        v = np.asarray(vals, np.float32).ravel()
+        return bool((zero and np.all(np.abs(v) <= 1.1920929e-07)) or (one and np.all(np.abs(v - 1) <= 1.1920929e-07)))
+
+    def number(self, cid, prop, val, dynamic=False) -> str:
+        if not dynamic and self._embed([val]):
+            return _ts(val)
+        key = f"{cid}_{prop}"
+        self.local.floats[key] = float(np.float32(val))
+        self.header.append(f'  let var_num_{key} = registry::get_local_parameter_f32("{key}", 0);\n')
+        return f"var_num_{key}"
+
+    def integer(self, cid, prop, val) -> str:
+        key = f"{cid}_{prop}"
+        self.local.ints[key] = int(val)
+        self.header.append(f'  let var_int_{key} = registry::get_local_parameter_i32("{key}", 0);\n')
+        return f"var_int_{key}"
+
+    def color(self, cid, prop, rgb) -> str:
+        if self._embed(rgb):
+            return f"make_color({_ts(rgb[0])}, {_ts(rgb[1])}, {_ts(rgb[2])}, 1)"
+        key = f"{cid}_{prop}"
+        self.local.colors[key] = tuple(float(np.float32(c)) for c in rgb) + (1.0,)
+        self.header.append(f'  let var_color_{key} = registry::get_local_parameter_color("{key}", color_builtins::black);\n')
+        return f"var_color_{key}"
+
+    def vector(self, cid, prop, xyz, dynamic=False) -> str:
+        if not dynamic and self._embed(xyz):
+            return f"make_vec3({_ts(xyz[0])}, {_ts(xyz[1])}, {_ts(xyz[2])})"
+        key = f"{cid}_{prop}"
+        self.local.vectors[key] = tuple(float(np.float32(c)) for c in xyz)
+        self.header.append(f'  let var_vec_{key} = registry::get_local_parameter_vec3("{key}", vec3_expand(0));\n')
+        return f"var_vec_{key}"
+
+    def pull_header(self) -> str:
+        h, self.header = "".join(self.header), []
+        return h
+
+
+def _prologue(t: SceneTables) -> str:
+    has_sphere = any(int(lk["type_id"]) == SHAPE_SPHERE for lk in t.shape_lookups)
+    s = ("  let spi = settings.spi;\n"
+         "  let render_config = make_render_config_from_settings(settings, spi);\n"
+         "  let device = make_nvvm_device(settings.device, render_config, make_default_gpu_kernel_config());\n"
+         "  let payload_info = PayloadInfo{ primary_count = 6, secondary_count = 0 };\n"
+         '  let scene_bbox = make_bbox(registry::get_global_parameter_vec3("__scene_bbox_lower", vec3_expand(0)), '
+         'registry::get_global_parameter_vec3("__scene_bbox_upper", vec3_expand(0))); maybe_unused(scene_bbox);\n\n')
+    return s, has_sphere
+
+
+def _database(has_sphere: bool) -> str:
+    s = ("  let entities = load_entity_table(device); maybe_unused(entities);\n"
+         "  let shapes_trimesh = load_shape_table(device, @|_, data| { \n    make_trimesh_shape(load_trimesh(data))\n  });\n  maybe_unused(shapes_trimesh);\n")
+    if has_sphere:
+        s += ("  let shapes_sphere = load_shape_table(device, @|_, data| { \n    make_sphere_shape(load_sphere(data))\n  });\n  maybe_unused(shapes_sphere);\n"
+              "  let shapes = load_shape_table(device, @|type_id, data| { match type_id {\n    0 => make_trimesh_shape(load_trimesh(data)),\n"
+              "    _ => make_sphere_shape(load_sphere(data))\n  }});\n")
+    else:
+        s += "  let shapes = shapes_trimesh;\n"
+    s += "  maybe_unused(shapes);\n"
+    s += ('  let scene  = Scene {\n    num_entities  = registry::get_global_parameter_i32("__entity_count", 0),\n'
+          '    num_materials = registry::get_global_parameter_i32("__material_count", 0),\n    shapes   = shapes,\n    entities = entities,\n  };\n')
+    return s
+
+
+def _lights(t: SceneTables, tree: _Tree) -> str:
+    s = ""
+    bbox = ('make_bbox(registry::get_global_parameter_vec3("__scene_bbox_lower", vec3_expand(0)), '
+            'registry::get_global_parameter_vec3("__scene_bbox_upper", vec3_expand(0)))')
+    inf_names, fin_names = [], []
+    for i, l in enumerate(t.infinite_lights):
+        assert int(l["type"]) == LIGHT_ENV_CONST
+        cid = tree.closure(f"__inf_light_{i}")
+        scale = tree.color(cid, "scale", (1, 1, 1))
+        rad = "make_constant_texture(" + tree.color(cid, "radiance", l["p"][0:3]) + ")"
+        ident = "make_mat3x3(make_vec3(1.000000, 0.000000, 0.000000),make_vec3(0.000000, 1.000000, 0.000000),make_vec3(0.000000, 0.000000, 1.000000))"
+        s += tree.pull_header() + f"  let light_{cid} = make_environment_light({i}, {bbox}, {scale}, {rad}, {ident});\n"
+        inf_names.append(f"light_{cid}")
+    s += f"  let infinite_lights = LightTable {{\n    count = {len(inf_names)},\n    get   = @|id:i32| {{\n      match(id) {{\n"
+    for i, n in enumerate(inf_names):
+        s += f"      {i} => {n},\n"
+    s += "      _ => make_null_light(id)\n    }\n  }};\n  maybe_unused(infinite_lights);\n"
+    for i, l in enumerate(t.finite_lights):
+        cid = tree.closure(f"__fin_light_{i}")
+        ty, p = int(l["type"]), l["p"]
+        if ty == LIGHT_POINT:
+            origin = tree.vector(cid, "origin", p[0:3])
+            inten = tree.color(cid, "intensity", p[3:6])
+            s += tree.pull_header() + f"  let light_{cid} = make_point_light({i}, {origin}, {inten});\n"
+        elif ty == LIGHT_PLANE_AREA:
+            pre = f"ae_{cid}"
+            rad = tree.color(cid, "radiance", p[21:24])
+            args = [tree.vector(cid, pre + "_origin", p[0:3], dynamic=True), tree.vector(cid, pre + "_tangent", p[3:6]),
+                    tree.vector(cid, pre + "_bitangent", p[6:9]), tree.vector(cid, pre + "_normal", p[9:12]), tree.number(cid, pre + "_area", p[12])]
+            tcs = [tree.vector(cid, f"{pre}_t{k}", (p[13 + 2 * k], p[14 + 2 * k], 0), dynamic=True) for k in range(4)]
+            s += tree.pull_header() + f"  let ae_{cid} = make_plane_area_emitter({', '.join(args)}, " + ", ".join(f"vec3_to_2({x})" for x in tcs) + ");\n"
+            s += f"  let light_{cid} = make_area_light({i}, ae_{cid}, @|ctx| {{ maybe_unused(ctx); {rad} }});\n"
+        elif ty == LIGHT_SHAPE_AREA:
+            rad = tree.color(cid, "radiance", p[0:3])
+            ent = tree.integer(cid, f"ae_{cid}_ent_id", int(l["entity_id"]))
+            s += tree.pull_header() + f"  let ae_{cid} = make_shape_area_emitter_proxy({ent}, entities, shapes_trimesh);\n"
+            s += f"  let light_{cid} = make_area_light({i}, ae_{cid}, @|ctx| {{ maybe_unused(ctx); {rad} }});\n"
+        else:
+            raise ValueError(ty)
+        fin_names.append(f"light_{cid}")
+    s += "\n" if fin_names else ""
+    s += f"  let finite_lights = LightTable {{\n    count = {len(fin_names)},\n    get   = @|id:i32| {{\n    match(id) {{\n"
+    for i, n in enumerate(fin_names):
+        s += f"      {i} => {n},\n"
+    s += "      _ => make_null_light(id)\n    }\n  }};\n  maybe_unused(finite_lights);\n"
+    return s
+
+
+def _technique(t: SceneTables, std_aovs: bool) -> str:
+    tech = t.technique
+    s = ('  let tech_max_depth = registry::get_global_parameter_i32("__tech_max_depth", 8);\n' if int(tech["max_depth"]) >= 2 else f"  let tech_max_depth = {int(tech['max_depth'])}:i32;\n")
+    s += ('  let tech_min_depth = registry::get_global_parameter_i32("__tech_min_depth", 2);\n' if int(tech["min_depth"]) >= 2 else f"  let tech_min_depth = {int(tech['min_depth'])}:i32;\n")
+    s += ('  let tech_clamp = registry::get_global_parameter_f32("__tech_clamp", 0);\n' if float(tech["clamp"]) > 0 else f"  let tech_clamp = {_stream(tech['clamp'])}:f32;\n")
+    s += "  let aovs = @|id:i32| -> AOVImage {\n    match(id) {\n      _ => make_empty_aov_image(0, 0)\n    }\n  };\n"
+    s += "  let light_selector = make_uniform_light_selector(infinite_lights, finite_lights);\n"
+    s += f"  let technique = make_path_renderer(tech_max_depth, tech_min_depth, light_selector, aovs, tech_clamp,{'true' if int(tech['nee']) else 'false'});\n"
+    s += ("  let full_technique = wrap_infobuffer_renderer(device, settings.iter, spi, technique);\n" if std_aovs else "  let full_technique = technique;\n")
+    return s
+
+
+def _bsdf(t: SceneTables, mat_id: int, tree: _Tree) -> str:
+    m = t.materials[mat_id]
+    cid = tree.closure(f"__bsdf_{mat_id}")
+    p = m["p"]
+    if int(m["bsdf"]) == BSDF_DIFFUSE:
+        refl = tree.color(cid, "reflectance", p[0:3])
+        rough = tree.number(cid, "roughness", 0.0)
+        s = tree.pull_header() + f"  let bsdf_{cid} : BSDFShader = @|ctx| make_diffuse_bsdf(ctx.surf, {rough}, {refl});\n"
+    elif int(m["bsdf"]) == BSDF_DIELECTRIC:
+        ks = tree.color(cid, "specular_reflectance", p[2:5])
+        kt = tree.color(cid, "specular_transmittance", p[5:8])
+        ext = tree.number(cid, "ext_ior", p[0])
+        int_ = tree.number(cid, "int_ior", p[1])
+        s = f"  let md_{cid} = @|ctx : ShadingContext| microfacet::make_delta_distribution(ctx.surf.local);\n"
+        s += tree.pull_header() + (f"  let bsdf_{cid} : BSDFShader = @|ctx| make_dielectric_bsdf(ctx.surf, {ext}, {int_}, {ks}, {kt}, md_{cid}(ctx), false);\n")
+    else:
+        raise ValueError(int(m["bsdf"]))
+    s += "  let medium_interface = no_medium_interface();\n"
+    if int(m["light_id"]) >= 0:
+        tree.local.ints["_light_id"] = int(m["light_id"])
+        s += '  let light_id = registry::get_local_parameter_i32("_light_id", 0);\n'
+        s += f"  let shader : MaterialShader = @|ctx| make_emissive_material(mat_id, bsdf_{cid}(ctx), medium_interface, @finite_lights.get(light_id));\n\n"
+    else:
+        s += f"  let shader : MaterialShader = @|ctx| make_material(mat_id, bsdf_{cid}(ctx), medium_interface);\n\n"
+    return s
+
+
+def generate(t: SceneTables, specialization: str = "default", std_aovs: bool = True, tracer: bool = False) -> StageSet:
+    """The stage scripts + registries of one technique variant for `t`."""
+    g = Registry()
+    cam = t.camera
+    g.vectors["__camera_eye"] = tuple(float(x) for x in cam["eye"])
+    g.vectors["__camera_dir"] = tuple(float(x) for x in cam["dir"])
+    g.vectors["__camera_up"] = tuple(float(x) for x in cam["up"])
+    g.vectors["__scene_bbox_lower"] = tuple(float(x) for x in t.bbox_min)
+    g.vectors["__scene_bbox_upper"] = tuple(float(x) for x in t.bbox_max)
+    g.ints["__entity_count"] = t.n_entities
+    g.ints["__material_count"] = int(t.materials.shape[0])
+    g.ints["__tech_max_depth"] = int(t.technique["max_depth"])
+    g.ints["__tech_min_depth"] = int(t.technique["min_depth"])
+    g.floats["__tech_clamp"] = float(t.technique["clamp"])
+    prologue, has_sphere = _prologue(t)
+
+    # ---- ray generation
+    local = Registry()
+    s = STD_LIB_STUB + "#[export] fn ig_ray_generation_shader(settings: &Settings, next_id: i32, size: i32, xmin: i32, ymin: i32, xmax: i32, ymax: i32) -> i32 {\n" + prologue
+    s += "  let init_raypayload = make_simple_payload_initializer(init_pt_raypayload);\n"
+    if tracer:
+        s += "  let emitter = make_list_emitter(device.load_rays(), render_config, init_raypayload);\n"
+    else:
+        aspect = "(settings.width as f32 / settings.height as f32)" if float(cam["aspect"]) <= 0 else _ts(cam["aspect"])
+        fov_gen = "compute_scale_from_vfov" if int(cam["fov_vertical"]) else "compute_scale_from_hfov"
+        s += ('  let camera_eye = registry::get_global_parameter_vec3("__camera_eye", vec3_expand(0));\n'
+              '  let camera_dir = registry::get_global_parameter_vec3("__camera_dir", vec3_expand(0));\n'
+              '  let camera_up  = registry::get_global_parameter_vec3("__camera_up" , vec3_expand(0));\n')
+        s += (f"  let camera = make_perspective_camera(camera_eye, \n    camera_dir, \n    camera_up, \n    {fov_gen}({_stream(cam['fov'])}, {aspect}), \n"
+              f"    settings.width, \n    settings.height, \n    {_stream(cam['tmin'])}, \n    {_stream(cam['tmax'])});\n\n")
+        s += "  let pixel_sampler = make_uniform_pixel_sampler();\n\n"
+        s += "  let emitter = make_camera_emitter(camera, render_config, pixel_sampler, init_raypayload);\n"
+    s += "  device.generate_rays(emitter, payload_info, GenerateRayInfo{ next_id=next_id, size=size, xmin=xmin, ymin=ymin, xmax=xmax, ymax=ymax })\n}\n"
+    raygen = Stage("ig_ray_generation_shader", s, local)
+
+    # ---- miss
+    local = Registry()
+    tree = _Tree(local, specialization)
+    s = STD_LIB_STUB + "#[export] fn ig_miss_shader(settings: &Settings, first: i32, last: i32) -> () {\n" + prologue
+    s += _lights(t, tree) + "\n" + _technique(t, std_aovs) + "\n"
+    s += "  let use_framebuffer = true;\n  device.handle_miss_shader(full_technique, payload_info, first, last, use_framebuffer);\n}\n"
+    miss = Stage("ig_miss_shader", s, local)
+
+    # ---- one hit shader per material
+    hits = []
+    for mat_id in range(int(t.materials.shape[0])):
+        local = Registry()
+        tree = _Tree(local, specialization)
+        s = STD_LIB_STUB + "#[export] fn ig_hit_shader(settings: &Settings, mat_id: i32, first: i32, last: i32) -> () {\n" + prologue
+        s += _database(has_sphere) + _lights(t, tree) + "\n" + _bsdf(t, mat_id, tree) + _technique(t, std_aovs) + "\n"
+        s += "  let use_framebuffer = true;\n  device.handle_hit_shader(shader, scene, full_technique, payload_info, first, last, use_framebuffer);\n}\n"
+        hits.append(Stage("ig_hit_shader", s, local))
+    return StageSet(raygen, miss, hits, g)

@@ -1,0 +1,125 @@
+"""The C++ plugin layer (csrc/host): the compiler device recognises the reference's stage scripts, the render device binds
+them to the C ABI. CPU part: script text -> descriptors must reproduce, bit for bit, the descriptors the scene loader
+computed directly. GPU part (`-m gpu`): rendering through ig_get_interface() / IRenderDevice equals the oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from ignis_b200 import plugin, refscript
+from ignis_b200.scene import load_scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "evaluation/cbox-d6.json", "evaluation/multilight-uniform.json",
+          "evaluation/emissive-plane.json", "evaluation/point.json", "evaluation/plane-d1.json"]
+
+
+def scene(name):
+    return load_scene(os.path.join(ROOT, "scenes", name))
+
+
+def test_host_library_exports_plugin_entry_points():
+    L = plugin.lib()
+    for s in plugin.SYMBOLS:
+        assert hasattr(L, s), s
+    major, minor = C.c_int(), C.c_int()
+    assert L.igbh_interface_version(C.byref(major), C.byref(minor)) == 0   # architecture = Nvidia (replaces ig_device_cuda)
+    assert (major.value, minor.value) == (0, 3)                            # Build::getVersion() check of DeviceManager.cpp:180-194
+
+
+@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("mode", ["default", "disable", "force"])
+def test_recognised_descriptors_equal_loader_descriptors(name, mode):
+    t = scene(name)
+    st = refscript.generate(t, specialization=mode)
+    g = plugin.Params(st.global_registry)
+    exact = mode != "force"   # `force` prints every value with std::to_string's 6 decimals (ShadingTree.cpp:933-981): lossy by design
+    hits = [plugin.CompiledStage(s) for s in st.hits]
+    for i, h in enumerate(hits):
+        m = h.material(g)
+        assert int(m["bsdf"]) == int(t.materials[i]["bsdf"]) and int(m["light_id"]) == int(t.materials[i]["light_id"])
+        if exact:
+            np.testing.assert_array_equal(m["p"].view(np.uint32), t.materials[i]["p"].view(np.uint32))
+        else:
+            np.testing.assert_allclose(m["p"], t.materials[i]["p"], atol=1e-6)
+    for stage in [plugin.CompiledStage(st.miss)] + hits[:1]:
+        inf, fin = stage.lights(g)
+        assert len(inf) == len(t.infinite_lights) and len(fin) == len(t.finite_lights)
+        for got, ref in list(zip(inf, t.infinite_lights)) + list(zip(fin, t.finite_lights)):
+            assert int(got["type"]) == int(ref["type"])
+            if int(ref["type"]) == 3:
+                assert int(got["entity_id"]) == int(ref["entity_id"])
+            if exact:
+                np.testing.assert_array_equal(got["p"].view(np.uint32), ref["p"].view(np.uint32))
+            else:
+                np.testing.assert_allclose(got["p"], ref["p"], rtol=1e-5, atol=1e-6)
+        tech = stage.technique(g)
+        assert tech.tobytes() == t.technique.tobytes()
+    cam = plugin.CompiledStage(st.raygen).camera(g)
+    assert cam.tobytes() == t.camera.tobytes()
+
+
+def test_unknown_constructs_fail_loudly():
+    t = scene("diamond_scene.json")
+    st = refscript.generate(t)
+    g = plugin.Params(st.global_registry)
+    # a BSDF the device does not implement must not be rendered as something else
+    bad = refscript.Stage("ig_hit_shader", st.hits[0].script.replace("make_diffuse_bsdf(ctx.surf,", "make_principled_bsdf(ctx.surf,"), st.hits[0].local)
+    with pytest.raises(plugin.DeviceError, match="make_principled_bsdf"):
+        plugin.CompiledStage(bad).material(g)
+    # another light selector
+    bad = refscript.Stage("ig_miss_shader", st.miss.script.replace("make_uniform_light_selector(infinite_lights, finite_lights)", 'make_hierarchy_light_selector(infinite_lights, finite_lights, device.load_buffer("x"))'), st.miss.local)
+    with pytest.raises(plugin.DeviceError, match="selector"):
+        plugin.CompiledStage(bad).technique(g)
+    # embedded light tables (>= 10 simple lights) are rejected at compile time
+    bad = refscript.Stage("ig_miss_shader", st.miss.script.replace("let finite_lights = LightTable {", "let finite_lights = load_simple_point_lights(12, 0, device); let unused_table = LightTable {"), st.miss.local)
+    with pytest.raises(plugin.DeviceError, match="LightTable"):
+        plugin.CompiledStage(bad)
+    # entry points that do not exist
+    with pytest.raises(plugin.DeviceError, match="not found"):
+        plugin.CompiledStage(refscript.Stage("ig_hit_shader", "fn other() -> () { }", refscript.Registry()))
+    # stages of the pipeline that carry no parameters still yield a non-null handle (Runtime.cpp:631-657)
+    trav = refscript.Stage("ig_traversal_shader", "#[export] fn ig_traversal_shader(settings: &Settings, size: i32, is_secondary: bool) -> () {\n  let spi = settings.spi;\n}\n", refscript.Registry())
+    assert plugin.CompiledStage(trav).handle
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,w,h,spi", [("diamond_scene.json", 160, 90, 2), ("primitives.json", 160, 90, 2), ("evaluation/multilight-uniform.json", 96, 96, 2)])
+def test_render_through_cpp_plugin_matches_oracle(name, w, h, spi):
+    from oracle.oracle import Oracle
+    t = scene(name)
+    o = Oracle(t)
+    ref = np.zeros((h, w, 3), np.float32)
+    for it in range(2):
+        o.render(w, h, spi=spi, iteration=it, fb=ref)
+    with plugin.PluginRuntime(t, w, h, spi) as rt:
+        rt.step()
+        rt.step()
+        got = rt.getFramebufferForHost().copy()
+        stats = rt.getStatistics()
+    err = float(np.linalg.norm((got - ref).ravel()) / np.linalg.norm(ref.ravel()))
+    assert err <= 1e-4, err
+    assert (stats["CameraRayCount"], stats["ShadowRayCount"], stats["BounceRayCount"]) == tuple(int(x) for x in o.counters)
+
+
+@pytest.mark.gpu
+def test_trace_through_cpp_plugin_matches_direct_abi():
+    from ignis_b200.device import RAY_DTYPE, Runtime
+    t = scene("diamond_scene.json")
+    rng = np.random.default_rng(5)
+    rays = np.zeros(4096, RAY_DTYPE)
+    rays["org"] = rng.uniform(t.bbox_min, t.bbox_max, (4096, 3))
+    d = rng.normal(size=(4096, 3))
+    rays["dir"] = d * rng.uniform(0.5, 2.0, (4096, 1))   # unnormalised: the device normalises (Device.cpp:617-640)
+    rays["tmin"], rays["tmax"] = 1e-3, 1e30
+    with plugin.PluginRuntime(t, 4096, 1, 1, tracer=True) as rt:
+        got = rt.trace(rays)
+    n = rays.copy()
+    dd = rays["dir"].astype(np.float32)
+    n["dir"] = dd / np.sqrt((dd * dd).sum(1, dtype=np.float32))[:, None]
+    with Runtime(t, 4096, 1, spi=1) as rt2:
+        ref = rt2.trace(n)
+    assert np.isfinite(got).all() and ref.sum() > 0
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5)
