@@ -196,3 +196,38 @@ def test_full_size_properties_diamond():
         o.render(240, 135, spi=4, iteration=it, fb=ref)
     small = a.reshape(135, 8, 240, 8, 3).mean(axis=(1, 3))
     assert small.mean() == pytest.approx((ref / 4).mean(), rel=0.05)
+
+
+def test_deferred_tail_is_invisible():
+    """render() may leave the deepest paths of an iteration to the next launch (igb200.h): every observation must still
+    see the result of a synchronous render -- same image, exactly the same ray counters, also across a clear."""
+    t = load_scene(scene_path("diamond_scene.json"))
+    w, h, spi = 320, 180, 4
+    out = {}
+    for permille in (0, 50, 500):
+        with Runtime(t, w, h, spi=spi) as rt:
+            rt.device.setOption("defer_permille", permille)
+            for _ in range(3):
+                rt.step()
+            img = rt.getFramebufferForHost().copy()
+            st = rt.device.getStatistics()
+            rt.step()                       # leaves paths in flight ...
+            rt.device.clearAllFramebuffer()  # ... which belong to the image being thrown away
+            assert not rt.getFramebufferForHost().any()
+            rt.IterationCount = 0
+            rt.step()
+            again = rt.getFramebufferForHost().copy()
+        out[permille] = (img, st, again)
+    ref_img, ref_st, ref_again = out[0]
+    assert ref_st["KernelLaunches"] == 3
+    for permille in (50, 500):
+        img, st, again = out[permille]
+        assert rel_l2(img, ref_img) <= 1e-6
+        assert rel_l2(again, ref_again) <= 1e-6
+        for k in ("CameraRayCount", "ShadowRayCount", "BounceRayCount", "Splats"):
+            assert st[k] == ref_st[k], k
+    o = Oracle(t)
+    ref = np.zeros((h, w, 3), np.float32)
+    for it in range(3):
+        o.render(w, h, spi=spi, iteration=it, fb=ref)
+    assert rel_l2(out[500][0], ref) <= REL_L2_TOL
