@@ -349,9 +349,15 @@ def run_b200(args):
                                 "sample": f"{n_it} full-frame iteration(s) of the same workload ({w}x{h}, spi {spi}; {rays} rays, {dt:.1f} s) on {cores} threads, "
                                           f"CPU restatement of the reference's CPU device built {flags}"}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    # tear down in dependency order: tensors that alias or were used on the device's stream go first, then the device
+    # (which owns that stream), then NCCL; otherwise the allocator records events on a stream that no longer exists at exit
+    torch.cuda.synchronize()
+    del fb_t, scratch, host_t, stream
+    torch.cuda.synchronize()
     rt.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
