@@ -24,7 +24,7 @@ constexpr int WF_BLOCK = 256;       // threads per CTA of the persistent kernels
 // "min_blocks" option picks one (DESIGN.md "Occupancy").
 // "vote" picks the scheduling of the traversal visit kinds (traverse.cuh turn / turn_vote); all variants are built.
 using WaveKernel = void (*)(const WaveParams);
-using TraceKernel = void (*)(const DevScene, const PrimaryQueue, int, const ShadowQueue, int, float*, int*, unsigned long long*, int, int, int, int);
+using TraceKernel = void (*)(const DevScene, const PrimaryQueue, int, const ShadowQueue, int, float*, int*, unsigned long long*, int, int, int, int, int);
 static WaveKernel wave_kernel(int min_blocks, int vote) {
     if (vote) return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 2> : k_wavefront<WF_BLOCK, 2, 2>;
     return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 0> : k_wavefront<WF_BLOCK, 2, 0>;
@@ -109,6 +109,7 @@ struct igb200_ctx {
     // deferred tail: a launch ends once at most defer_permille/1000 of the iteration's camera rays are still alive as paths;
     // they are carried into the next launch (render) or finished by a drain launch before anything is observed
     int defer_permille = 50;
+    int64_t wide_rays_per_group = 2;   // trace phases with at most this many rays per group of 8 lanes use the wide walk (0: never)
     bool pending = false;              // launches issued since the last synchronisation with the device
     bool maybe_carry = false;          // the last launch may have left paths behind
     igb200_settings carry_settings{};  // settings the carried paths were generated with
@@ -159,6 +160,7 @@ static WaveParams make_params(igb200_ctx* c, const RenderParams& rp, const DevSc
     P.total = total; P.capacity = (int)c->capacity; P.list_rays = d_rays;
     P.stage_nodes = c->stage_nodes; P.stage_tris = c->stage_tris; P.stage_ent = c->stage_ent;
     P.refill = c->refill; P.defer = defer;
+    P.wide_limit = (int)std::min<int64_t>(c->wide_rays_per_group * c->blocks_per_sm * c->n_sm * (WF_BLOCK / 8), (int64_t)1 << 30);
     return P;
 }
 
@@ -251,6 +253,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     { const int r = sync_control(c); if (r) return r; }
     if (!strcmp(name, "capacity")) { if (value < 1024) return fail(-1, "capacity must be >= 1024"); c->want_capacity = (size_t)value; c->capacity = 0; return 0; }
     if (!strcmp(name, "vote")) { if (value < 0 || value > 2) return fail(-1, "vote must be 0 or 2"); c->vote = value ? 2 : 0; if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); } return 0; }
+    if (!strcmp(name, "wide_rays_per_group")) { if (value < 0) return fail(-1, "wide_rays_per_group must be >= 0"); c->wide_rays_per_group = value; return 0; }
     if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 1000) return fail(-1, "defer_permille must be in [0, 1000]"); c->defer_permille = (int)value; return 0; }
     if (!strcmp(name, "profile_kernels")) return 0;   // phase times are always recorded by the persistent kernel
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
@@ -651,7 +654,8 @@ static int run_trace(igb200_ctx* c, const igb200_ray* d_rays, const uint32_t* d_
         CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
         if (!any_hit && r > 0) k_import_rays<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(d_rays, d_flags, RAY_CAMERA, (int)n, c->qa.view(), ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, 0);
         trace_kernel(c->min_blocks, c->vote)<<<grid, WF_BLOCK, c->smem_bytes, c->stream>>>(c->dev, c->qa.view(), any_hit ? 0 : (int)n, ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, any_hit ? (int)n : 0, d_fb,
-                                                                                     &c->control.p->fetch_trace, &c->control.p->cam_launch, c->stage_nodes, c->stage_tris, c->stage_ent, c->refill);
+                                                                                     &c->control.p->fetch_trace, &c->control.p->cam_launch, c->stage_nodes, c->stage_tris, c->stage_ent, c->refill,
+                                                                                     (int)std::min<int64_t>(c->wide_rays_per_group * grid * (WF_BLOCK / 8), (int64_t)1 << 30));
     }
     if (ms_per_pass) {
         CU(cudaEventRecord(c->ev1, c->stream));

@@ -335,4 +335,111 @@ struct Traversal {
 };
 #undef IGB_CHILD
 
+// ---- wide traversal: EIGHT lanes walk ONE ray --------------------------------------------------------------------
+// Used for small queues (the deep-path tail of an iteration, wavefront.cuh): there the trace phase lasts exactly as long
+// as the slowest single ray, and a scalar lane needs ~600 dependent instructions per loop turn (eight slab tests, up to
+// four triangle tests). With a BVH8, lane j of a group of eight tests child j of the node / triangle j of the leaf, the
+// nearest child is found with three shuffles, and the critical path per visit shrinks by the same factor.
+// The closest hit is a pure function of the ray (see the header of this file), so the visiting order -- which differs
+// from the scalar walk -- cannot change the result; tests/test_gpu_parity.py checks both walks against the oracle.
+// All state is replicated in the eight lanes; control flow is uniform within a group and divergent between groups,
+// hence every warp primitive below uses the group's 8-lane mask.
+struct WideStack {
+    uint2* base;   // shared memory: the stack columns of the group's first thread (16 rows x 8 columns = 128 entries)
+    int stride;
+    __device__ __forceinline__ uint2& at(int k) const { return base[(k >> 3) * stride + (k & 7)]; }
+};
+constexpr int WIDE_STACK = SMEM_STACK * 8;
+
+__device__ __forceinline__ HitR trace_wide(const DevScene& sc, const Staged& sg, const WideStack& ws, unsigned gmask, int j,
+                                           const float4* po, const float4* pd, uint32_t ray_flags, bool any_hit) {
+    Traversal T;
+    if (!T.begin(sc, po, pd, ray_flags, any_hit)) return T.hit;
+    const int gshift = __ffs(gmask) - 1;
+    for (;;) {
+        // ---- pop
+        if (T.cur == 0) {
+            bool empty = false;
+            for (;;) {
+                if (T.sp == 0) { empty = true; break; }
+                const uint2 e = ws.at(--T.sp);
+                T.cur = (int)e.x;
+                if (T.cur > SENTINEL_KEEP) { if (__uint_as_float(e.y) <= T.tcull) break; continue; }
+                T.ent = -1;
+                if (T.cur == SENTINEL_RESTORE) { const float4 o = *po, d = *pd; T.set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)); }
+            }
+            if (empty) break;
+        }
+        if (T.cur > 0) {
+            // ---- inner node: lane j tests child j
+            const float* N = reinterpret_cast<const float*>(node_ptr(sc, sg, T.cur - 1));
+            const int c = reinterpret_cast<const int*>(N)[48 + j];
+            const float lx = N[j], hx = N[8 + j], ly = N[16 + j], hy = N[24 + j], lz = N[32 + j], hz = N[40 + j];
+            const bool sx = (T.bits & TB_SX) != 0, sy = (T.bits & TB_SY) != 0, sz = (T.bits & TB_SZ) != 0;
+            const float tn = fmaxf(fmaxf(fma_(T.idir.x, sx ? hx : lx, T.ilo.x), fma_(T.idir.y, sy ? hy : ly, T.ilo.y)), fmaxf(fma_(T.idir.z, sz ? hz : lz, T.ilo.z), T.tmin));
+            const float tf = fminf(fminf(fma_(T.idir.x, sx ? lx : hx, T.ihi.x), fma_(T.idir.y, sy ? ly : hy, T.ihi.y)), fminf(fma_(T.idir.z, sz ? lz : hz, T.ihi.z), T.tcull));
+            const bool hit = c != 0 && tn <= tf;
+            const unsigned m = (__ballot_sync(gmask, hit) >> gshift) & 0xFFu;
+            if (m == 0) { T.cur = 0; continue; }
+            // nearest hit child: min over (tn, lane)
+            float bt = hit ? tn : __int_as_float(0x7f800000); int bj = j;
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const float ot = __shfl_xor_sync(gmask, bt, d); const int oj = __shfl_xor_sync(gmask, bj, d);
+                if (ot < bt || (ot == bt && oj < bj)) { bt = ot; bj = oj; }
+            }
+            const unsigned others = m & ~(1u << bj);
+            if (hit && j != bj) { const int pos = T.sp + __popc(others & ((1u << j) - 1u)); if (pos < WIDE_STACK) ws.at(pos) = make_uint2((uint32_t)c, __float_as_uint(tn)); }
+            T.sp = min(T.sp + __popc(others), WIDE_STACK);
+            T.cur = __shfl_sync(gmask, c, gshift + bj);
+            __syncwarp(gmask);
+        }
+        if (T.cur < 0 && T.ent < 0) {
+            // ---- entity: every lane runs the scalar step on its copy; one lane owns the stack write
+            const int sp0 = T.sp;
+            uint2 lst[1];
+            Stack one; one.s = lst; one.stride = 0; one.l = lst;   // captures the single sentinel push of entity_step
+            int spx = 0;
+            {
+                // entity_step pushes at most one entry (a sentinel) at index T.sp: redirect it into `lst`
+                const int keep = T.sp; T.sp = 0;
+                T.entity_step(sc, sg, one);
+                spx = T.sp; T.sp = keep;
+            }
+            if (spx > 0) { if (j == 0 && sp0 < WIDE_STACK) ws.at(sp0) = lst[0]; T.sp = min(sp0 + 1, WIDE_STACK); __syncwarp(gmask); }
+        }
+        if (T.cur < 0 && T.ent >= 0) {
+            // ---- leaf: lane j tests triangle j
+            const int r = -T.cur - 1;
+            const int first = r >> 2, cnt = (r & 3) + 1;
+            T.cur = 0;
+            float t = __int_as_float(0x7f800000), u = 0, v = 0; int prim = -1;
+            if (j < cnt) {
+                const float4* P = tri_ptr(sc, sg, first + j);
+                float tt, uu, vv;
+                if (intersect_tri(T.org, T.dir, T.tmin, T.tmax, P[0], P[1], P[2], tt, uu, vv)) {
+                    const int pp = __ldg(sc.tri_prim + first + j);
+                    if (better(tt, T.ent, pp, T.hit)) { t = tt; u = uu; v = vv; prim = pp; }
+                }
+            }
+            // best candidate of the group: smaller t, then larger primitive id (the order of `better`)
+            float bt = t; int bp = prim, bj = j;
+#pragma unroll
+            for (int d = 1; d < 4; d <<= 1) {
+                const float ot = __shfl_xor_sync(gmask, bt, d); const int op = __shfl_xor_sync(gmask, bp, d); const int oj = __shfl_xor_sync(gmask, bj, d);
+                if (op >= 0 && (bp < 0 || ot < bt || (ot == bt && op > bp))) { bt = ot; bp = op; bj = oj; }
+            }
+            // lanes 0-3 agree; lanes 4-7 take the result from lane 0 of the group
+            bj = __shfl_sync(gmask, bj, gshift); bp = __shfl_sync(gmask, bp, gshift);
+            if (bp >= 0) {
+                const float wt = __shfl_sync(gmask, t, gshift + bj), wu = __shfl_sync(gmask, u, gshift + bj), wv = __shfl_sync(gmask, v, gshift + bj);
+                T.accept(wt, wu, wv, bp, T.ent);
+                if (T.bits & TB_DONE) break;
+            }
+        }
+        if (T.bits & TB_DONE) break;
+    }
+    return T.hit;
+}
+
 }  // namespace igb

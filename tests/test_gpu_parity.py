@@ -75,15 +75,19 @@ def test_closest_hit_records_match_oracle(scene, w, h):
     rays = np.concatenate([rays, extra])
     o = Oracle(t)
     ref = o.trace_closest(rays, use_bvh=True)
-    with B200Device() as dev:
-        dev.assignScene(t)
-        got = dev.traceClosest(rays)
-        occ = dev.traceAny(rays)
-    assert (got["ent_id"] == ref["ent_id"]).all()
-    assert (got["prim_id"] == ref["prim_id"]).all()
-    for k in ("t", "u", "v"):
-        np.testing.assert_array_equal(got[k].view(np.uint32), ref[k].view(np.uint32))
-    np.testing.assert_array_equal(occ, o.trace_any(rays, flags=np.full(len(rays), 8, np.uint32)))
+    ref_occ = o.trace_any(rays, flags=np.full(len(rays), 8, np.uint32))
+    # both walks of the device: one lane per ray (large queues) and eight lanes per ray (small queues, traverse.cuh trace_wide)
+    for wide in (0, 1 << 20):
+        with B200Device() as dev:
+            dev.assignScene(t)
+            dev.setOption("wide_rays_per_group", wide)
+            got = dev.traceClosest(rays)
+            occ = dev.traceAny(rays)
+        assert (got["ent_id"] == ref["ent_id"]).all(), wide
+        assert (got["prim_id"] == ref["prim_id"]).all(), wide
+        for k in ("t", "u", "v"):
+            np.testing.assert_array_equal(got[k].view(np.uint32), ref[k].view(np.uint32))
+        np.testing.assert_array_equal(occ, ref_occ)
     assert (ref["prim_id"] >= 0).any()
 
 
