@@ -41,8 +41,8 @@ SCENE = "scenes/diamond_scene.json"
 B_PRIMARY, B_SHADOW, B_SPLAT = 216, 108, 24
 # the same figure split by pipeline stage (DESIGN.md "Algorithmic bytes")
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_wavefront launch of this workload (ncu --set full, profiles/)
-NCU_TRAFFIC_BYTES = 7.615e9
-NCU_TRAFFIC_SOURCE = "profiles/r1a_k_wavefront_full.csv (4.047 GB read + 3.567 GB written per launch)"
+NCU_TRAFFIC_BYTES = 7.044e9
+NCU_TRAFFIC_SOURCE = "profiles/r1p_k_wavefront_full.csv (3.910 GB read + 3.134 GB written by the launch of one iteration)"
 B_STAGE = {"generate": 68, "traverse_primary": 60, "shade_read": 88, "shade_bounce_write": 68, "shade_shadow_write": 56,
            "traverse_secondary": 52}
 

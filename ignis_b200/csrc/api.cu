@@ -30,6 +30,7 @@ static WaveKernel wave_kernel(int min_blocks, int vote) {
     return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 0> : k_wavefront<WF_BLOCK, 2, 0>;
 }
 static TraceKernel trace_kernel(int min_blocks, int vote) {
+    if (min_blocks >= 4) return vote ? k_trace<WF_BLOCK, 4, 2> : k_trace<WF_BLOCK, 4, 0>;   // 64 registers: stand-alone trace phase only
     if (vote) return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 2> : k_trace<WF_BLOCK, 2, 2>;
     return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 0> : k_trace<WF_BLOCK, 2, 0>;
 }
@@ -106,6 +107,7 @@ struct igb200_ctx {
     size_t smem_bytes = 0;
     int64_t stage_budget = 40 * 1024;  // bytes of shared memory per CTA for the staged scene copy
     int refill = 24, min_blocks = 2, vote = 2;
+    int trace_blocks = 0;              // stand-alone trace hooks: CTAs per SM the kernel is compiled for (0: as min_blocks)
     // deferred tail: a launch ends once at most defer_permille/1000 of the iteration's camera rays are still alive as paths;
     // they are carried into the next launch (render) or finished by a drain launch before anything is observed
     int defer_permille = 50;
@@ -257,6 +259,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 1000) return fail(-1, "defer_permille must be in [0, 1000]"); c->defer_permille = (int)value; return 0; }
     if (!strcmp(name, "profile_kernels")) return 0;   // phase times are always recorded by the persistent kernel
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
+    if (!strcmp(name, "trace_blocks")) { if (value != 0 && (value < 2 || value > 4)) return fail(-1, "trace_blocks must be 0, 2, 3 or 4"); c->trace_blocks = (int)value; return 0; }
     if (!strcmp(name, "min_blocks")) {
         if (value != 2 && value != 3) return fail(-1, "min_blocks must be 2 or 3");
         c->min_blocks = (int)value;
@@ -647,13 +650,19 @@ static int run_trace(igb200_ctx* c, const igb200_ray* d_rays, const uint32_t* d_
     { const int r = sync_control(c); if (r) return r; }   // the hooks borrow the render queues
     { const int r = ensure_queues(c, n); if (r) return r; }
     if (n > c->capacity) return fail(-1, "igb200_trace_*: %zu rays exceed the queue capacity %zu", n, c->capacity);
-    const int grid = c->blocks_per_sm * c->n_sm;
+    const int tb = c->trace_blocks ? c->trace_blocks : c->min_blocks;
+    const TraceKernel tk = trace_kernel(tb, c->vote);
+    CU(cudaFuncSetAttribute((const void*)tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    int nb = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)tk, WF_BLOCK, c->smem_bytes));
+    if (nb < 1) return fail(-2, "k_trace does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
+    const int grid = nb * c->n_sm;
     k_import_rays<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(d_rays, d_flags, any_hit ? RAY_SHADOW : RAY_CAMERA, (int)n, c->qa.view(), ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, any_hit);
     for (int r = 0; r < repeat + (ms_per_pass ? 3 : 0); ++r) {
         if (ms_per_pass && r == 3) CU(cudaEventRecord(c->ev0, c->stream));
         CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
         if (!any_hit && r > 0) k_import_rays<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(d_rays, d_flags, RAY_CAMERA, (int)n, c->qa.view(), ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, 0);
-        trace_kernel(c->min_blocks, c->vote)<<<grid, WF_BLOCK, c->smem_bytes, c->stream>>>(c->dev, c->qa.view(), any_hit ? 0 : (int)n, ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, any_hit ? (int)n : 0, d_fb,
+        tk<<<grid, WF_BLOCK, c->smem_bytes, c->stream>>>(c->dev, c->qa.view(), any_hit ? 0 : (int)n, ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, any_hit ? (int)n : 0, d_fb,
                                                                                      &c->control.p->fetch_trace, &c->control.p->cam_launch, c->stage_nodes, c->stage_tris, c->stage_ent, c->refill,
                                                                                      (int)std::min<int64_t>(c->wide_rays_per_group * grid * (WF_BLOCK / 8), (int64_t)1 << 30));
     }

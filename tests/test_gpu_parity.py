@@ -60,7 +60,7 @@ def test_detmath_bit_exact():
 
 
 @pytest.mark.parametrize("scene,w,h", [("single_triangle.json", 256, 256), ("diamond_scene.json", 320, 180), ("primitives.json", 320, 180),
-                                       ("evaluation/cbox-d6.json", 128, 128)])
+                                       ("evaluation/cbox-d6.json", 128, 128), ("synthetic_room.json", 192, 108)])
 def test_closest_hit_records_match_oracle(scene, w, h):
     t = load_scene(scene_path(scene))
     rays = camera_rays(t, w, h)
@@ -112,6 +112,7 @@ def render_both(tables, w, h, spi, iters, seed=0):
     ("evaluation/multilight-uniform.json", 128, 128, 2, 1),
     ("evaluation/emissive-plane.json", 128, 128, 1, 1),
     ("evaluation/point.json", 64, 64, 1, 1),
+    ("synthetic_room.json", 192, 108, 2, 2),             # stand-in for C4: 1.8 M instanced triangles, geometry read through L2
 ])
 def test_radiance_matches_oracle(scene, w, h, spi, iters):
     t = load_scene(scene_path(scene))
