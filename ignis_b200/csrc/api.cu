@@ -96,7 +96,7 @@ struct igb200_ctx {
     DevBuf<float> fb;
     float* host_fb = nullptr; size_t host_fb_n = 0;
     // queues
-    size_t capacity = 0, want_capacity = (size_t)1 << 23;
+    size_t capacity = 0, want_capacity = (size_t)1 << 25;   // upper bound of records per queue (84 B each, two queues + 48 B shadow)
     QueueMem qa, qb;
     DevBuf<float4> sq_org, sq_dir, sq_col;
     DevBuf<Control> control;
@@ -110,7 +110,7 @@ struct igb200_ctx {
     int trace_blocks = 0;              // stand-alone trace hooks: CTAs per SM the kernel is compiled for (0: as min_blocks)
     // deferred tail: a launch ends once at most defer_permille/1000 of the iteration's camera rays are still alive as paths;
     // they are carried into the next launch (render) or finished by a drain launch before anything is observed
-    int defer_permille = 50;
+    int defer_permille = 1000;
     int64_t wide_rays_per_group = 2;   // trace phases with at most this many rays per group of 8 lanes use the wide walk (0: never)
     bool pending = false;              // launches issued since the last synchronisation with the device
     bool maybe_carry = false;          // the last launch may have left paths behind
@@ -256,7 +256,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "capacity")) { if (value < 1024) return fail(-1, "capacity must be >= 1024"); c->want_capacity = (size_t)value; c->capacity = 0; return 0; }
     if (!strcmp(name, "vote")) { if (value < 0 || value > 2) return fail(-1, "vote must be 0 or 2"); c->vote = value ? 2 : 0; if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); } return 0; }
     if (!strcmp(name, "wide_rays_per_group")) { if (value < 0) return fail(-1, "wide_rays_per_group must be >= 0"); c->wide_rays_per_group = value; return 0; }
-    if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 1000) return fail(-1, "defer_permille must be in [0, 1000]"); c->defer_permille = (int)value; return 0; }
+    if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 8000) return fail(-1, "defer_permille must be in [0, 8000]"); c->defer_permille = (int)value; return 0; }
     if (!strcmp(name, "profile_kernels")) return 0;   // phase times are always recorded by the persistent kernel
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
     if (!strcmp(name, "trace_blocks")) { if (value != 0 && (value < 2 || value > 4)) return fail(-1, "trace_blocks must be 0, 2, 3 or 4"); c->trace_blocks = (int)value; return 0; }
@@ -626,15 +626,18 @@ int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* ra
         CU(cudaMemcpyAsync(c->list_rays.p, rays, n_rays * sizeof(igb200_ray), cudaMemcpyHostToDevice, c->stream));
         d_rays = c->list_rays.p;
     }
-    if ((size_t)std::max<long long>(total, 1) > c->capacity) {   // the queues are about to be reallocated
-        { const int r = sync_control(c); if (r) return r; }
-        { const int r = ensure_queues(c, (size_t)std::max<long long>(total, 1)); if (r) return r; }
-    }
-
-    // One cooperative launch runs the iteration (asynchronously: nothing comes back to the host). With a deferred tail
-    // the launch returns once at most `defer` paths are alive; they continue in the next launch or in a drain launch.
+    // With a deferred tail the launch returns once at most `defer` paths are alive; they continue in the next launch or in
+    // a drain launch. The queues are sized so that the carried records and all new camera rays fit the first turn.
     const long long cam_rays = (long long)W * H * st->spi / std::max(rp.world, 1);
-    const int defer = rays ? 0 : (int)std::min<long long>(cam_rays * c->defer_permille / 1000, (long long)c->capacity / 4);
+    const long long want_defer = rays ? 0 : cam_rays * c->defer_permille / 1000;
+    const size_t need = (size_t)std::max<long long>(total + want_defer, 1);
+    if (std::min(need, c->want_capacity) > c->capacity) {   // the queues are about to be reallocated
+        { const int r = sync_control(c); if (r) return r; }
+        { const int r = ensure_queues(c, need); if (r) return r; }
+    }
+    const int defer = (int)std::min<long long>(want_defer, (long long)c->capacity - 1024);
+
+    // One cooperative launch runs the iteration (asynchronously: nothing comes back to the host).
     { const int r = launch_wave(c, rp, sc, total, d_rays, defer); if (r) return r; }
     c->maybe_carry = defer > 0;
     c->carry_settings = *st; c->carry_settings.width = W; c->carry_settings.height = H;
