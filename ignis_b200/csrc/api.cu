@@ -29,6 +29,10 @@ static WaveKernel wave_kernel(int min_blocks, int vote) {
     if (vote) return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 2> : k_wavefront<WF_BLOCK, 2, 2>;
     return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 0> : k_wavefront<WF_BLOCK, 2, 0>;
 }
+static WaveKernel turn_trace_kernel(int blocks, int vote) {
+    if (vote) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2> : k_turn_trace<WF_BLOCK, 2, 2>;
+    return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 0> : k_turn_trace<WF_BLOCK, 2, 0>;
+}
 static TraceKernel trace_kernel(int min_blocks, int vote) {
     if (min_blocks >= 4) return vote ? k_trace<WF_BLOCK, 4, 2> : k_trace<WF_BLOCK, 4, 0>;   // 64 registers: stand-alone trace phase only
     if (vote) return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 2> : k_trace<WF_BLOCK, 2, 2>;
@@ -107,6 +111,9 @@ struct igb200_ctx {
     size_t smem_bytes = 0;
     int64_t stage_budget = 40 * 1024;  // bytes of shared memory per CTA for the staged scene copy
     int refill = 24, min_blocks = 2, vote = 2;
+    int split_turns = 3;               // leading turns of an iteration run as separate shade / trace launches (0: all in the persistent kernel)
+    int turn_trace_blocks = 3;         // CTAs per SM the trace kernel of a split turn is compiled for
+    int grid_turn_shade = 0, grid_turn_trace = 0;
     int trace_blocks = 0;              // stand-alone trace hooks: CTAs per SM the kernel is compiled for (0: as min_blocks)
     // deferred tail: a launch ends once at most defer_permille/1000 of the iteration's camera rays are still alive as paths;
     // they are carried into the next launch (render) or finished by a drain launch before anything is observed
@@ -150,6 +157,14 @@ static int configure_kernels(igb200_ctx* c) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)wave_kernel(c->min_blocks, c->vote), WF_BLOCK, c->smem_bytes));
     if (nb < 1) return fail(-2, "k_wavefront does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
     c->blocks_per_sm = nb;
+    // split turn kernels
+    CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote), WF_BLOCK, c->smem_bytes));
+    if (nb < 1) return fail(-2, "k_turn_trace does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
+    c->grid_turn_trace = nb * c->n_sm;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_turn_shade<WF_BLOCK>, WF_BLOCK, 0));
+    if (nb < 1) return fail(-2, "k_turn_shade does not fit an SM");
+    c->grid_turn_shade = nb * c->n_sm;
     return 0;
 }
 
@@ -231,6 +246,7 @@ int igb200_create(int cuda_device, igb200_ctx** out) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(c->control.alloc(1));
     CU(cudaMemset(c->control.p, 0, sizeof(Control)));
+    CU(cudaMemset(&c->control.p->turn_t0, 0xFF, 2 * sizeof(unsigned long long)));
     CU(cudaMallocHost(&c->host_control, sizeof(Control)));
     std::memset(c->host_control, 0, sizeof(Control));
     CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
@@ -259,6 +275,13 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 8000) return fail(-1, "defer_permille must be in [0, 8000]"); c->defer_permille = (int)value; return 0; }
     if (!strcmp(name, "profile_kernels")) return 0;   // phase times are always recorded by the persistent kernel
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
+    if (!strcmp(name, "split_turns")) { if (value < 0 || value > 64) return fail(-1, "split_turns must be in [0, 64]"); c->split_turns = (int)value; return 0; }
+    if (!strcmp(name, "turn_trace_blocks")) {
+        if (value != 2 && value != 3) return fail(-1, "turn_trace_blocks must be 2 or 3");
+        c->turn_trace_blocks = (int)value;
+        if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); }
+        return 0;
+    }
     if (!strcmp(name, "trace_blocks")) { if (value != 0 && (value < 2 || value > 4)) return fail(-1, "trace_blocks must be 0, 2, 3 or 4"); c->trace_blocks = (int)value; return 0; }
     if (!strcmp(name, "min_blocks")) {
         if (value != 2 && value != 3) return fail(-1, "min_blocks must be 2 or 3");
@@ -536,6 +559,7 @@ int igb200_reset_stats(igb200_ctx* c) {
     { const int r = sync_control(c); if (r) return r; }
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(c->control.p, 0, sizeof(Control), c->stream));   // nothing is carried after a drain
+    CU(cudaMemsetAsync(&c->control.p->turn_t0, 0xFF, 2 * sizeof(unsigned long long), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     std::memset(c->host_control, 0, sizeof(Control));
     c->launches = 0;
@@ -637,7 +661,21 @@ int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* ra
     }
     const int defer = (int)std::min<long long>(want_defer, (long long)c->capacity - 1024);
 
-    // One cooperative launch runs the iteration (asynchronously: nothing comes back to the host).
+    // The iteration (asynchronously: nothing comes back to the host): its first, big turns as split launches, then one
+    // cooperative launch of the persistent kernel that generates whatever camera rays did not fit yet and runs until at
+    // most `defer` paths are alive.
+    CU(cudaMemsetAsync(&c->control.p->next_cam, 0, sizeof(long long), c->stream));
+    if (!rays && c->split_turns > 0) {
+        const WaveParams P = make_params(c, rp, sc, total, nullptr, defer);
+        CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
+        for (int t = 0; t < c->split_turns; ++t) {
+            k_turn_shade<WF_BLOCK><<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
+            turn_trace_kernel(c->turn_trace_blocks, c->vote)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
+            k_turn_end<<<1, 1, 0, c->stream>>>(P);
+            c->launches += 3;
+        }
+        CU(cudaGetLastError());
+    }
     { const int r = launch_wave(c, rp, sc, total, d_rays, defer); if (r) return r; }
     c->maybe_carry = defer > 0;
     c->carry_settings = *st; c->carry_settings.width = W; c->carry_settings.height = H;

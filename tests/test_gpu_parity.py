@@ -209,9 +209,10 @@ def test_deferred_tail_is_invisible():
     t = load_scene(scene_path("diamond_scene.json"))
     w, h, spi = 320, 180, 4
     out = {}
-    for permille in (0, 50, 500):
+    for permille, split in ((0, 0), (50, 2), (500, 0), (4000, 3)):
         with Runtime(t, w, h, spi=spi) as rt:
             rt.device.setOption("defer_permille", permille)
+            rt.device.setOption("split_turns", split)   # leading turns as separate shade / trace launches
             for _ in range(3):
                 rt.step()
             img = rt.getFramebufferForHost().copy()
@@ -225,7 +226,7 @@ def test_deferred_tail_is_invisible():
         out[permille] = (img, st, again)
     ref_img, ref_st, ref_again = out[0]
     assert ref_st["KernelLaunches"] == 3
-    for permille in (50, 500):
+    for permille in (50, 500, 4000):
         img, st, again = out[permille]
         assert rel_l2(img, ref_img) <= 1e-6
         assert rel_l2(again, ref_again) <= 1e-6
@@ -235,4 +236,4 @@ def test_deferred_tail_is_invisible():
     ref = np.zeros((h, w, 3), np.float32)
     for it in range(3):
         o.render(w, h, spi=spi, iteration=it, fb=ref)
-    assert rel_l2(out[500][0], ref) <= REL_L2_TOL
+    assert rel_l2(out[4000][0], ref) <= REL_L2_TOL
