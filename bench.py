@@ -289,15 +289,19 @@ def run_b200(args):
     ms, wall_ms, tot, clocks, _ = timed(e2e=False)
     ms_e, wall_e, tot_e, _, host = timed(e2e=True)
 
-    # ---- per-kernel-class timing (separate pass: each launch bracketed by CUDA events on the render stream)
+    # ---- per-kernel timing (separate pass, N = 1): every launch bracketed by CUDA events on the render stream
     kt = None
     if world == 1:
         rt.reset()
         dev.resetStatistics()
-        for _ in range(min(args.steps, 4)):
+        dev.setOption("profile_kernels", 1)
+        for _ in range(args.steps):
             rt.step()
+        dev.sync()
+        prof = dev.launchProfile()
         kt = dev.kernelTimes()
         kst = dev.getStatistics()
+        dev.setOption("profile_kernels", 0)
 
     line = None
     if rank == 0:
@@ -315,25 +319,30 @@ def run_b200(args):
         line["roofline_step"] = {"bound": "hbm", "achieved": step_bytes / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
                                  "frac": step_bytes / (ms * 1e-3) / 1e9 / world / peak, "traffic": None,
                                  "what": f"whole wavefront step per GPU: {B_PRIMARY} B x primary + {B_SHADOW} B x shadow + {B_SPLAT} B x splat (SURVEY.md 8d), peak {peak_src}"}
-        # the step IS one launch of the persistent kernel k_wavefront (plus one drain launch at the end of the K steps):
-        # algorithmic bytes and duration of the average launch, from the CUDA-event-timed region above
-        n_l = max(tot["KernelLaunches"] // world, 1)
-        avg_ms = ms / n_l
-        kbytes = step_bytes / world / n_l
-        ach = kbytes / (avg_ms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES,
-                            "kernel": "k_wavefront (persistent cooperative kernel: one launch = one render() iteration)",
-                            "avg_launch_ms": avg_ms, "launches": n_l, "share_of_step": 1.0,
-                            "algorithmic_bytes_per_launch": kbytes, "peak_source": peak_src,
-                            "traffic_source": NCU_TRAFFIC_SOURCE}
+        line["roofline"] = dict(line["roofline_step"], kernel="whole step, all kernels (per-kernel figures are measured at N = 1)")
         if kt is not None:
+            # Dominant kernel of the step: k_turn_trace<256,3,2>, the trace phase of the split turns. Algorithmic bytes of a launch
+            # (trace share): 40 B ray read + 20 B hit write per primary ray, 52 B per shadow ray, 24 B per splat.
+            kern = prof["kernels"]
+            total_ms = sum(v["ms"] for v in kern.values()) or 1.0
+            w_ = prof["k_turn_trace_work"]
+            n_l = max(kern["k_turn_trace"]["launches"], 1)
+            avg_ms = kern["k_turn_trace"]["ms"] / n_l
+            kbytes = (B_STAGE["traverse_primary"] * w_["primary"] + B_STAGE["traverse_secondary"] * w_["shadow"] + B_SPLAT * w_["splats"]) / n_l
+            ach = kbytes / (avg_ms * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES,
+                                "kernel": "k_turn_trace<256,3,2> (closest-hit + any-hit/splat phase of a split wavefront turn)",
+                                "avg_launch_ms": avg_ms, "launches": n_l, "share_of_step": kern["k_turn_trace"]["ms"] / total_ms,
+                                "algorithmic_bytes_per_launch": kbytes, "rays_per_launch": (w_["primary"] + w_["shadow"]) / n_l,
+                                "peak_source": peak_src, "traffic_source": NCU_TRAFFIC_SOURCE,
+                                "timing": "CUDA events around every launch on the render stream, separate pass of the same K steps"}
+            line["kernels"] = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps, "share": v["ms"] / total_ms} for k, v in kern.items()}
             prim = kst["CameraRayCount"] + kst["BounceRayCount"]
             phase_bytes = {"trace": B_STAGE["traverse_primary"] * prim + B_STAGE["traverse_secondary"] * kst["ShadowRayCount"] + B_SPLAT * kst["Splats"],
                            "shade_generate": B_STAGE["generate"] * kst["CameraRayCount"] + B_STAGE["shade_read"] * prim
                                              + B_STAGE["shade_bounce_write"] * kst["BounceRayCount"] + B_STAGE["shade_shadow_write"] * kst["ShadowRayCount"]}
             total_k = sum(v["ms"] for v in kt.values()) or 1.0
-            n_k = max(kst["KernelLaunches"], 1)
-            line["phase_ms"] = {k: {"ms_per_launch": v["ms"] / n_k, "share": v["ms"] / total_k,
+            line["phase_ms"] = {k: {"ms_per_step": v["ms"] / args.steps, "share": v["ms"] / total_k,
                                     "algorithmic_GBps": phase_bytes[k] / max(v["ms"], 1e-9) / 1e6} for k, v in kt.items()}
         if host is not None:
             line["image_mean"] = float(np.asarray(host).mean() / args.steps)

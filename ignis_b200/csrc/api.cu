@@ -29,6 +29,7 @@ static WaveKernel wave_kernel(int min_blocks, int vote) {
     if (vote) return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 2> : k_wavefront<WF_BLOCK, 2, 2>;
     return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 0> : k_wavefront<WF_BLOCK, 2, 0>;
 }
+static WaveKernel turn_shade_kernel(int blocks) { return blocks >= 4 ? k_turn_shade<WF_BLOCK, 4> : blocks == 3 ? k_turn_shade<WF_BLOCK, 3> : k_turn_shade<WF_BLOCK, 2>; }
 static WaveKernel turn_trace_kernel(int blocks, int vote) {
     if (vote) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2> : k_turn_trace<WF_BLOCK, 2, 2>;
     return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 0> : k_turn_trace<WF_BLOCK, 2, 0>;
@@ -111,8 +112,9 @@ struct igb200_ctx {
     size_t smem_bytes = 0;
     int64_t stage_budget = 40 * 1024;  // bytes of shared memory per CTA for the staged scene copy
     int refill = 24, min_blocks = 2, vote = 2;
-    int split_turns = 3;               // leading turns of an iteration run as separate shade / trace launches (0: all in the persistent kernel)
+    int split_turns = 4;               // leading turns of an iteration run as separate shade / trace launches (0: all in the persistent kernel)
     int turn_trace_blocks = 3;         // CTAs per SM the trace kernel of a split turn is compiled for
+    int turn_shade_blocks = 3;         // ... and the shade + generate kernel
     int grid_turn_shade = 0, grid_turn_trace = 0;
     int trace_blocks = 0;              // stand-alone trace hooks: CTAs per SM the kernel is compiled for (0: as min_blocks)
     // deferred tail: a launch ends once at most defer_permille/1000 of the iteration's camera rays are still alive as paths;
@@ -129,6 +131,12 @@ struct igb200_ctx {
     // stats
     uint64_t launches = 0;             // kernels launched by igb200_render (and its drains) since the last reset
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // "profile_kernels": every launch of igb200_render is bracketed by CUDA events on the stream (kind: 0 k_wavefront, 1 k_turn_trace,
+    // 2 k_turn_shade, 3 k_turn_end); elapsed times are summed at the next synchronisation
+    bool profile = false;
+    struct Timed { cudaEvent_t a, b; int kind; };
+    std::vector<Timed> timed;
+    double prof_ms[4] = {0, 0, 0, 0}; uint64_t prof_n[4] = {0, 0, 0, 0};
     DevBuf<igb200_ray> list_rays;
 };
 
@@ -162,7 +170,7 @@ static int configure_kernels(igb200_ctx* c) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote), WF_BLOCK, c->smem_bytes));
     if (nb < 1) return fail(-2, "k_turn_trace does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
     c->grid_turn_trace = nb * c->n_sm;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_turn_shade<WF_BLOCK>, WF_BLOCK, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)turn_shade_kernel(c->turn_shade_blocks), WF_BLOCK, 0));
     if (nb < 1) return fail(-2, "k_turn_shade does not fit an SM");
     c->grid_turn_shade = nb * c->n_sm;
     return 0;
@@ -182,12 +190,37 @@ static WaveParams make_params(igb200_ctx* c, const RenderParams& rp, const DevSc
 }
 
 
+static int prof_begin(igb200_ctx* c, int kind) {
+    if (!c->profile) return 0;
+    igb200_ctx::Timed t; t.kind = kind;
+    CU(cudaEventCreate(&t.a)); CU(cudaEventCreate(&t.b));
+    CU(cudaEventRecord(t.a, c->stream));
+    c->timed.push_back(t);
+    return 0;
+}
+static int prof_end(igb200_ctx* c) {
+    if (!c->profile) return 0;
+    CU(cudaEventRecord(c->timed.back().b, c->stream));
+    return 0;
+}
+static int prof_collect(igb200_ctx* c) {   // after a stream synchronisation
+    for (const igb200_ctx::Timed& t : c->timed) {
+        float ms = 0; CU(cudaEventElapsedTime(&ms, t.a, t.b));
+        c->prof_ms[t.kind] += ms; c->prof_n[t.kind] += 1;
+        cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+    }
+    c->timed.clear();
+    return 0;
+}
+
 // One cooperative launch of the persistent kernel on the context's stream; asynchronous.
 static int launch_wave(igb200_ctx* c, const RenderParams& rp, const DevScene& sc, long long total, const igb200_ray* d_rays, int defer) {
     WaveParams P = make_params(c, rp, sc, total, d_rays, defer);
     CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
     void* args[] = {&P};
+    { const int r = prof_begin(c, 0); if (r) return r; }
     CU(cudaLaunchCooperativeKernel((const void*)wave_kernel(c->min_blocks, c->vote), dim3((unsigned)(c->blocks_per_sm * c->n_sm)), dim3(WF_BLOCK), args, c->smem_bytes, c->stream));
+    { const int r = prof_end(c); if (r) return r; }
     c->launches += 1;
     c->pending = true;
     return 0;
@@ -215,6 +248,7 @@ static int sync_control(igb200_ctx* c) {
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaGetLastError());
         c->pending = false;
+        { const int r = prof_collect(c); if (r) return r; }
     }
     return 0;
 }
@@ -273,9 +307,15 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "vote")) { if (value < 0 || value > 2) return fail(-1, "vote must be 0 or 2"); c->vote = value ? 2 : 0; if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); } return 0; }
     if (!strcmp(name, "wide_rays_per_group")) { if (value < 0) return fail(-1, "wide_rays_per_group must be >= 0"); c->wide_rays_per_group = value; return 0; }
     if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 8000) return fail(-1, "defer_permille must be in [0, 8000]"); c->defer_permille = (int)value; return 0; }
-    if (!strcmp(name, "profile_kernels")) return 0;   // phase times are always recorded by the persistent kernel
+    if (!strcmp(name, "profile_kernels")) { c->profile = value != 0; return 0; }
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
     if (!strcmp(name, "split_turns")) { if (value < 0 || value > 64) return fail(-1, "split_turns must be in [0, 64]"); c->split_turns = (int)value; return 0; }
+    if (!strcmp(name, "turn_shade_blocks")) {
+        if (value < 2 || value > 4) return fail(-1, "turn_shade_blocks must be 2, 3 or 4");
+        c->turn_shade_blocks = (int)value;
+        if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); }
+        return 0;
+    }
     if (!strcmp(name, "turn_trace_blocks")) {
         if (value != 2 && value != 3) return fail(-1, "turn_trace_blocks must be 2 or 3");
         c->turn_trace_blocks = (int)value;
@@ -549,7 +589,7 @@ int igb200_stats(igb200_ctx* c, uint64_t out[5], double* render_ms) {
     if (!c) return fail(-1, "null context");
     { const int r = sync_control(c); if (r) return r; }
     const Control& h = *c->host_control;
-    if (out) { out[0] = h.stat[0]; out[1] = h.stat[1]; out[2] = h.stat[2]; out[3] = h.stat[3]; out[4] = c->launches; }
+    if (out) { out[0] = h.stat[0]; out[1] = h.stat[1]; out[2] = h.stat[2]; out[3] = h.stat[3] + h.trace_splats; out[4] = c->launches; }
     if (render_ms) *render_ms = (double)h.kernel_ns * 1e-6;
     return 0;
 }
@@ -563,6 +603,15 @@ int igb200_reset_stats(igb200_ctx* c) {
     CU(cudaStreamSynchronize(c->stream));
     std::memset(c->host_control, 0, sizeof(Control));
     c->launches = 0;
+    for (int k = 0; k < 4; ++k) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
+    return 0;
+}
+
+int igb200_launch_profile(igb200_ctx* c, double ms[4], uint64_t launches[4], uint64_t split_work[3]) {
+    if (!c) return fail(-1, "null context");
+    { const int r = sync_control(c); if (r) return r; }
+    for (int k = 0; k < 4; ++k) { if (ms) ms[k] = c->prof_ms[k]; if (launches) launches[k] = c->prof_n[k]; }
+    if (split_work) for (int k = 0; k < 3; ++k) split_work[k] = c->host_control->split[k];
     return 0;
 }
 
@@ -669,9 +718,15 @@ int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* ra
         const WaveParams P = make_params(c, rp, sc, total, nullptr, defer);
         CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
         for (int t = 0; t < c->split_turns; ++t) {
-            k_turn_shade<WF_BLOCK><<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
+            { const int r = prof_begin(c, 2); if (r) return r; }
+            turn_shade_kernel(c->turn_shade_blocks)<<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
+            { const int r = prof_end(c); if (r) return r; }
+            { const int r = prof_begin(c, 1); if (r) return r; }
             turn_trace_kernel(c->turn_trace_blocks, c->vote)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
+            { const int r = prof_end(c); if (r) return r; }
+            { const int r = prof_begin(c, 3); if (r) return r; }
             k_turn_end<<<1, 1, 0, c->stream>>>(P);
+            { const int r = prof_end(c); if (r) return r; }
             c->launches += 3;
         }
         CU(cudaGetLastError());

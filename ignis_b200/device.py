@@ -60,7 +60,7 @@ HIT_DTYPE = np.dtype([("ent_id", "<i4"), ("prim_id", "<i4"), ("t", "<f4"), ("u",
 # every symbol include/igb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["igb200_last_error", "igb200_version", "igb200_create", "igb200_destroy", "igb200_set_scene", "igb200_resize",
            "igb200_set_partition", "igb200_render", "igb200_sync", "igb200_framebuffer", "igb200_framebuffer_device", "igb200_clear",
-           "igb200_upload_framebuffer", "igb200_stats", "igb200_reset_stats", "igb200_kernel_times", "igb200_turn_log", "igb200_step_stats", "igb200_set_option",
+           "igb200_upload_framebuffer", "igb200_stats", "igb200_reset_stats", "igb200_kernel_times", "igb200_launch_profile", "igb200_turn_log", "igb200_step_stats", "igb200_set_option",
            "igb200_stream", "igb200_trace_closest", "igb200_trace_any", "igb200_bench_trace", "igb200_test_detmath"]
 
 
@@ -96,6 +96,7 @@ def lib():
         L.igb200_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         L.igb200_reset_stats.argtypes = [vp]
         L.igb200_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        L.igb200_launch_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.igb200_turn_log.argtypes = [vp, vp, vp, vp, C.c_int, ip]
         L.igb200_step_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.igb200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
@@ -252,6 +253,14 @@ class B200Device:
         n = (C.c_uint64 * 4)()
         _check(lib().igb200_kernel_times(self._h, ms, n))
         return {"trace": {"ms": ms[1], "launches": int(n[1])}, "shade_generate": {"ms": ms[2], "launches": int(n[2])}}
+
+    def launchProfile(self):
+        """Per-kernel CUDA-event times (needs setOption("profile_kernels", 1)) and the work of the k_turn_trace launches."""
+        ms, n, w = (C.c_double * 4)(), (C.c_uint64 * 4)(), (C.c_uint64 * 3)()
+        _check(lib().igb200_launch_profile(self._h, ms, n, w))
+        names = ("k_wavefront", "k_turn_trace", "k_turn_shade", "k_turn_end")
+        return {"kernels": {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(names)},
+                "k_turn_trace_work": {"primary": int(w[0]), "shadow": int(w[1]), "splats": int(w[2])}}
 
     def traceClosest(self, rays, flags=None) -> np.ndarray:
         rays = np.ascontiguousarray(rays, RAY_DTYPE)

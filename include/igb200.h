@@ -174,6 +174,10 @@ int igb200_reset_stats(igb200_ctx* ctx);
  * (%globaltimer at the grid barriers): out_ms = {0, trace phase (closest + any hit), shade + generate phase, 0},
  * out_launches = number of phases. */
 int igb200_kernel_times(igb200_ctx* ctx, double out_ms[4], uint64_t out_launches[4]);
+/* With the option "profile_kernels" = 1 every kernel launch of igb200_render is bracketed by CUDA events on the context's
+ * stream; this returns, since the last reset, the summed durations and launch counts per kernel (0 k_wavefront, 1 k_turn_trace,
+ * 2 k_turn_shade, 3 k_turn_end) and the work the k_turn_trace launches did: {primary rays, shadow rays, framebuffer splats}. */
+int igb200_launch_profile(igb200_ctx* ctx, double ms[4], uint64_t launches[4], uint64_t split_work[3]);
 /* Diagnostics of the LAST igb200_render: for each loop turn of the persistent kernel (at most max_turns, at most 128)
  * the number of rays traced and the duration of its trace phase and of the shade + generate phase before it. */
 int igb200_turn_log(igb200_ctx* ctx, uint32_t* items, uint32_t* trace_ns, uint32_t* shade_ns, int max_turns, int* n_turns);
@@ -181,7 +185,8 @@ int igb200_turn_log(igb200_ctx* ctx, uint32_t* items, uint32_t* trace_ns, uint32
  * >= 16 (out[8..15]): inner-node visits, triangle-leaf visits, entity visits, max visits of one ray, rays traced. */
 int igb200_step_stats(igb200_ctx* ctx, uint64_t out[16]);
 /* Tunables: "capacity" (records per ray queue), "refill" (lanes), "stage_budget" (bytes of shared memory for the staged
- * scene), "min_blocks" (2|3 CTAs per SM), "vote" (0|2), "defer_permille" (deferred tail threshold, 0 = off). */
+ * scene), "min_blocks" (2|3 CTAs per SM), "vote" (0|2), "defer_permille" (deferred tail threshold, 0 = off), "split_turns"
+ * (leading turns run as separate shade / trace launches), "turn_trace_blocks" (2|3), "wide_rays_per_group", "profile_kernels". */
 int igb200_set_option(igb200_ctx* ctx, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a caller can record
  * its own events on it or order a collective after a render (the reference has one implicit device queue). */
