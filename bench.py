@@ -40,9 +40,10 @@ SCENE = "scenes/diamond_scene.json"
 # algorithmic bytes per unit of work of the wavefront hand-off
 B_PRIMARY, B_SHADOW, B_SPLAT = 216, 108, 24
 # the same figure split by pipeline stage (DESIGN.md "Algorithmic bytes")
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_wavefront launch of this workload (ncu --set full, profiles/)
-NCU_TRAFFIC_BYTES = 7.044e9
-NCU_TRAFFIC_SOURCE = "profiles/r1p_k_wavefront_full.csv (3.910 GB read + 3.134 GB written by the launch of one iteration)"
+# dram__bytes_read.sum + dram__bytes_write.sum per k_turn_trace launch of this workload (ncu --set full, profiles/)
+NCU_TRAFFIC_BYTES = 5.384e8
+NCU_TRAFFIC_SOURCE = ("profiles/r2b_k_turn_trace_full.csv: dram read + write of the three k_turn_trace launches of the first iteration "
+                      "(437 + 750 + 429 MB) / 3; later iterations also trace the carried paths, hence the larger algorithmic figure")
 B_STAGE = {"generate": 68, "traverse_primary": 60, "shade_read": 88, "shade_bounce_write": 68, "shade_shadow_write": 56,
            "traverse_secondary": 52}
 
