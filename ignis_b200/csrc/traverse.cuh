@@ -279,7 +279,17 @@ struct Traversal {
         }
         ent = e;
         cur = __float_as_int(l5.y);               // root of the shape's tree (a leaf code for shapes of <= 4 triangles)
-        if ((kind & 2) && !(bits & TB_NEGZERO)) { st.push(sp, SENTINEL_KEEP, -1.0f); return; }
+        if ((kind & 2) && !(bits & TB_NEGZERO)) {
+            if (cur < 0) {
+                // untransformed shape of <= 4 triangles (walls, area lights): test them right here -- no sentinel to push and
+                // pop, no separate leaf visit, and one visit kind less for the warp to diverge over
+                leaf_step(sc, sg);
+                ent = -1;
+                return;
+            }
+            st.push(sp, SENTINEL_KEEP, -1.0f);
+            return;
+        }
         const float4 r0 = L[2], r1 = L[3], r2 = L[4];
         set_ray(xform_point(r0, r1, r2, org), xform_dir(r0, r1, r2, dir));                            // ray.art:53-59
         st.push(sp, SENTINEL_RESTORE, -1.0f);
