@@ -112,7 +112,7 @@ struct igb200_ctx {
     size_t smem_bytes = 0;
     int64_t stage_budget = 40 * 1024;  // bytes of shared memory per CTA for the staged scene copy
     int refill = 24, min_blocks = 2, vote = 2;
-    int split_turns = 4;               // leading turns of an iteration run as separate shade / trace launches (0: all in the persistent kernel)
+    int split_turns = -1;               // leading turns of an iteration run as separate shade / trace launches (0: all in the persistent kernel)
     int turn_trace_blocks = 3;         // CTAs per SM the trace kernel of a split turn is compiled for
     int turn_shade_blocks = 3;         // ... and the shade + generate kernel
     int grid_turn_shade = 0, grid_turn_trace = 0;
@@ -309,7 +309,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 8000) return fail(-1, "defer_permille must be in [0, 8000]"); c->defer_permille = (int)value; return 0; }
     if (!strcmp(name, "profile_kernels")) { c->profile = value != 0; return 0; }
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
-    if (!strcmp(name, "split_turns")) { if (value < 0 || value > 64) return fail(-1, "split_turns must be in [0, 64]"); c->split_turns = (int)value; return 0; }
+    if (!strcmp(name, "split_turns")) { if (value < -1 || value > 64) return fail(-1, "split_turns must be in [-1, 64] (-1: chosen from the number of camera rays)"); c->split_turns = (int)value; return 0; }
     if (!strcmp(name, "turn_shade_blocks")) {
         if (value < 2 || value > 4) return fail(-1, "turn_shade_blocks must be 2, 3 or 4");
         c->turn_shade_blocks = (int)value;
@@ -714,10 +714,12 @@ int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* ra
     // cooperative launch of the persistent kernel that generates whatever camera rays did not fit yet and runs until at
     // most `defer` paths are alive.
     CU(cudaMemsetAsync(&c->control.p->next_cam, 0, sizeof(long long), c->stream));
-    if (!rays && c->split_turns > 0) {
+    // split turns pay three launches each: worth it while a turn holds millions of rays (4 at 8 M camera rays, 2 at 1 M)
+    const int split_turns = c->split_turns >= 0 ? c->split_turns : (int)std::min<long long>(4, std::max<long long>(1, cam_rays >> 19));
+    if (!rays && split_turns > 0) {
         const WaveParams P = make_params(c, rp, sc, total, nullptr, defer);
         CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
-        for (int t = 0; t < c->split_turns; ++t) {
+        for (int t = 0; t < split_turns; ++t) {
             { const int r = prof_begin(c, 2); if (r) return r; }
             turn_shade_kernel(c->turn_shade_blocks)<<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
             { const int r = prof_end(c); if (r) return r; }

@@ -13,6 +13,9 @@ for a in sys.argv[2:]:
 keys = list(opts)
 t = load_scene(os.path.join(ROOT, "scenes", scene), 1920, 1080)
 with Runtime(t, 1920, 1080, spi=4) as rt:
+    if os.environ.get("PART"):   # emulate one rank of a multi-GPU run: PART=rank,world
+        r_, w_ = (int(x) for x in os.environ["PART"].split(","))
+        rt.device.setPartition(r_, w_, 32)
     for combo in itertools.product(*[opts[k] for k in keys]):
         for k, v in zip(keys, combo):
             rt.device.setOption(k, v)
