@@ -379,6 +379,7 @@ __device__ __forceinline__ HitR trace_wide(const DevScene& sc, const Staged& sg,
                 if (T.cur == SENTINEL_RESTORE) { const float4 o = *po, d = *pd; T.set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)); }
             }
             if (empty) break;
+            __syncwarp(gmask);   // every lane has read the popped entries before any lane pushes over them
         }
         if (T.cur > 0) {
             // ---- inner node: lane j tests child j
