@@ -122,6 +122,10 @@ struct igb200_ctx {
     int defer_permille = 1000;
     int64_t wide_rays_per_group = 2;   // trace phases with at most this many rays per group of 8 lanes use the wide walk (0: never)
     bool pending = false;              // launches issued since the last synchronisation with the device
+    // fused iterations: consecutive render() calls are collected and generated by ONE launch when a single iteration is too
+    // small to fill the GPU (a 1/8 share of the frame at 8 GPUs); flushed by anything that observes or changes state
+    std::vector<igb200_settings> queued;
+    int fuse = 0;                      // iterations per launch (0: chosen so that a launch generates ~8 M camera rays, at most 8)
     bool maybe_carry = false;          // the last launch may have left paths behind
     igb200_settings carry_settings{};  // settings the carried paths were generated with
     int carry_rank = 0, carry_world = 1, carry_tile = 0;
@@ -229,7 +233,23 @@ static int launch_wave(igb200_ctx* c, const RenderParams& rp, const DevScene& sc
 // Finishes the paths earlier launches left behind (deferred tail): one more launch without camera rays that runs every
 // path to its end. Everything that observes results (framebuffer, statistics) or changes what carried records refer to
 // (scene, size, partition, spi) calls this first.
+// iterations per launch: enough to generate ~8 M camera rays, at most 8 (option "fuse" overrides)
+static int fuse_factor(const igb200_ctx* c, const igb200_settings* st) {
+    if (c->fuse > 0) return c->fuse;
+    const long long cam_rays = std::max<long long>((long long)st->width * st->height * st->spi / std::max(c->world, 1), 1);
+    return (int)std::min<long long>(8, std::max<long long>(1, ((long long)1 << 23) / cam_rays));
+}
+extern "C" { static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_iter, const igb200_ray* rays, size_t n_rays); }
+static int flush_queued(igb200_ctx* c) {
+    if (c->queued.empty()) return 0;
+    const igb200_settings first = c->queued.front();
+    const int n = (int)c->queued.size();
+    c->queued.clear();   // before the launch: it may call drain / sync_control itself
+    return launch_iterations(c, &first, n, nullptr, 0);
+}
+
 static int drain(igb200_ctx* c) {
+    { const int r = flush_queued(c); if (r) return r; }
     if (c->maybe_carry) {
         CU(cudaSetDevice(c->device));
         const int r = launch_wave(c, c->last_rp, c->last_sc, 0, nullptr, 0);
@@ -309,6 +329,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 8000) return fail(-1, "defer_permille must be in [0, 8000]"); c->defer_permille = (int)value; return 0; }
     if (!strcmp(name, "profile_kernels")) { c->profile = value != 0; return 0; }
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
+    if (!strcmp(name, "fuse")) { if (value < 0 || value > 64) return fail(-1, "fuse must be in [0, 64]"); c->fuse = (int)value; return 0; }
     if (!strcmp(name, "split_turns")) { if (value < -1 || value > 64) return fail(-1, "split_turns must be in [-1, 64] (-1: chosen from the number of camera rays)"); c->split_turns = (int)value; return 0; }
     if (!strcmp(name, "turn_shade_blocks")) {
         if (value < 2 || value > 4) return fail(-1, "turn_shade_blocks must be 2, 3 or 4");
@@ -576,6 +597,7 @@ int igb200_upload_framebuffer(igb200_ctx* c, const char* aov, const float* host_
 
 int igb200_stream(igb200_ctx* c, void** cuda_stream) {
     if (!c || !cuda_stream) return fail(-1, "igb200_stream: null argument");
+    { const int r = flush_queued(c); if (r) return r; }   // whatever the caller enqueues next is ordered after every render() so far
     *cuda_stream = (void*)c->stream;
     return 0;
 }
@@ -618,6 +640,7 @@ int igb200_launch_profile(igb200_ctx* c, double ms[4], uint64_t launches[4], uin
 int igb200_turn_log(igb200_ctx* c, uint32_t* items, uint32_t* trace_ns, uint32_t* shade_ns, int max_turns, int* n_turns) {
     if (!c || !items || !trace_ns || !shade_ns || !n_turns) return fail(-1, "igb200_turn_log: null argument");
     // no drain here: the log describes the last launch as it ran (a drain would overwrite it)
+    { const int r = flush_queued(c); if (r) return r; }
     if (c->pending) {
         CU(cudaSetDevice(c->device));
         CU(cudaMemcpyAsync(c->host_control, c->control.p, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
@@ -649,7 +672,7 @@ int igb200_kernel_times(igb200_ctx* c, double out_ms[4], uint64_t out_launches[4
     return 0;
 }
 
-int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* rays, size_t n_rays) {
+static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_iter, const igb200_ray* rays, size_t n_rays) {
     if (!c || !st) return fail(-1, "igb200_render: null argument");
     if (!c->has_scene) return fail(-1, "igb200_render: no scene assigned");
     if (st->spi < 1) return fail(-1, "igb200_render: spi must be >= 1");
@@ -667,7 +690,8 @@ int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* ra
     const int tiles_y = (H + rp.tile_h - 1) / rp.tile_h;
     const long long tiles_total = (long long)rp.tiles_x * tiles_y;
     const long long local_tiles = tiles_total > rp.rank ? (tiles_total - rp.rank + rp.world - 1) / rp.world : 0;
-    const long long total = local_tiles * rp.tile_w * rp.tile_h * rp.spi;   // padded ray domain of this rank
+    rp.per_iter = local_tiles * rp.tile_w * rp.tile_h * rp.spi;             // padded ray domain of this rank, one iteration
+    const long long total = rp.per_iter * n_iter;                          // ... of the launch (n_iter consecutive iterations)
 
     // camera: camera/perspective.art:2-6,29-35
     DevScene sc = c->dev;
@@ -691,7 +715,7 @@ int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* ra
     const bool compatible = !rays && cs.spi == st->spi && cs.width == W && cs.height == H && cs.frame == st->frame && cs.seed == st->seed &&
                             c->carry_rank == rp.rank && c->carry_world == rp.world && c->carry_tile == rp.tile_w;
     if (c->maybe_carry && !compatible) { const int r = drain(c); if (r) return r; }
-    if (st->iter < 0 || st->iter >= (1 << 24)) return fail(-1, "igb200_render: iteration %d out of range [0, 2^24)", st->iter);
+    if (st->iter < 0 || st->iter + n_iter > (1 << 24)) return fail(-1, "igb200_render: iteration %d out of range [0, 2^24)", st->iter);
     const igb200_ray* d_rays = nullptr;
     if (rays) {
         { const int r = sync_control(c); if (r) return r; }   // the previous list may still be read
@@ -701,9 +725,11 @@ int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* ra
     }
     // With a deferred tail the launch returns once at most `defer` paths are alive; they continue in the next launch or in
     // a drain launch. The queues are sized so that the carried records and all new camera rays fit the first turn.
-    const long long cam_rays = (long long)W * H * st->spi / std::max(rp.world, 1);
+    const long long cam_rays = (long long)W * H * st->spi / std::max(rp.world, 1) * n_iter;
     const long long want_defer = rays ? 0 : cam_rays * c->defer_permille / 1000;
-    const size_t need = (size_t)std::max<long long>(total + want_defer, 1);
+    // queues sized for a full batch of fused iterations from the start (a reallocation costs tens of milliseconds)
+    const int f_full = rays ? 1 : std::max(n_iter, fuse_factor(c, st));
+    const size_t need = (size_t)std::max<long long>((total / n_iter + want_defer / n_iter) * f_full, 1);
     if (std::min(need, c->want_capacity) > c->capacity) {   // the queues are about to be reallocated
         { const int r = sync_control(c); if (r) return r; }
         { const int r = ensure_queues(c, need); if (r) return r; }
@@ -735,10 +761,31 @@ int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* ra
     }
     { const int r = launch_wave(c, rp, sc, total, d_rays, defer); if (r) return r; }
     c->maybe_carry = defer > 0;
-    c->carry_settings = *st; c->carry_settings.width = W; c->carry_settings.height = H;
+    c->carry_settings = *st; c->carry_settings.width = W; c->carry_settings.height = H; c->carry_settings.iter = st->iter + n_iter - 1;
     c->carry_rank = rp.rank; c->carry_world = rp.world; c->carry_tile = rp.tile_w;
     c->last_rp = rp; c->last_sc = sc;
     if (rays) { const int r = sync_control(c); if (r) return r; }   // the caller may free `rays` after the call
+    return 0;
+}
+
+int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* rays, size_t n_rays) {
+    if (!c || !st) return fail(-1, "igb200_render: null argument");
+    if (!c->has_scene) return fail(-1, "igb200_render: no scene assigned");
+    if (st->spi < 1) return fail(-1, "igb200_render: spi must be >= 1");
+    if (rays) {   // igtrace: synchronous, never fused
+        { const int r = flush_queued(c); if (r) return r; }
+        return launch_iterations(c, st, 1, rays, n_rays);
+    }
+    if (st->width < 1 || st->height < 1) return fail(-1, "igb200_render: invalid size %dx%d", st->width, st->height);
+    // Fused iterations: a launch generates the camera rays of up to F consecutive iterations (same settings, iter + 1 each).
+    if (!c->queued.empty()) {
+        const igb200_settings& l = c->queued.back();
+        const bool follows = l.spi == st->spi && l.width == st->width && l.height == st->height && l.frame == st->frame && l.seed == st->seed &&
+                             l.device == st->device && st->iter == l.iter + 1;
+        if (!follows) { const int r = flush_queued(c); if (r) return r; }
+    }
+    c->queued.push_back(*st);
+    if ((int)c->queued.size() >= fuse_factor(c, st)) return flush_queued(c);
     return 0;
 }
 

@@ -149,7 +149,9 @@ int igb200_set_partition(igb200_ctx* ctx, int rank, int world, int tile_size);
  * (Runtime::trace, Runtime.cpp:389-446): width = n_rays, height = 1. Accumulates into the device framebuffer.
  * The call is ASYNCHRONOUS on the context's stream (the reference's GPU device ends every iteration with acc.sync(),
  * driver/mapping_gpu.art:865): it returns once the iteration's kernel is enqueued, and the kernel itself may leave the
- * last few deep paths of the iteration to be finished together with the next one ("deferred tail").
+ * last few deep paths of the iteration to be finished together with the next one ("deferred tail"). When one
+ * iteration is too small to fill the GPU (a rank's share of the frame in a multi-GPU run), consecutive calls with the same
+ * settings and iter = previous + 1 are collected and their camera rays generated by ONE launch ("fused iterations").
  * Every entry point that observes results (igb200_framebuffer*, igb200_stats, igb200_sync, ...) or changes what
  * in-flight paths refer to (scene, size, partition, spi, seed) first finishes all outstanding paths, so the
  * observable behaviour is that of a synchronous render. */
@@ -186,7 +188,7 @@ int igb200_turn_log(igb200_ctx* ctx, uint32_t* items, uint32_t* trace_ns, uint32
 int igb200_step_stats(igb200_ctx* ctx, uint64_t out[16]);
 /* Tunables: "capacity" (records per ray queue), "refill" (lanes), "stage_budget" (bytes of shared memory for the staged
  * scene), "min_blocks" (2|3 CTAs per SM), "vote" (0|2), "defer_permille" (deferred tail threshold, 0 = off), "split_turns"
- * (leading turns run as separate shade / trace launches), "turn_trace_blocks" (2|3), "wide_rays_per_group", "profile_kernels". */
+ * (leading turns run as separate shade / trace launches), "turn_trace_blocks" (2|3), "wide_rays_per_group", "fuse" (iterations per launch, 0 = automatic), "profile_kernels". */
 int igb200_set_option(igb200_ctx* ctx, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a caller can record
  * its own events on it or order a collective after a render (the reference has one implicit device queue). */

@@ -209,10 +209,11 @@ def test_deferred_tail_is_invisible():
     t = load_scene(scene_path("diamond_scene.json"))
     w, h, spi = 320, 180, 4
     out = {}
-    for permille, split in ((0, 0), (50, 2), (500, 0), (4000, 3)):
+    for permille, split, fuse in ((0, 0, 1), (50, 2, 1), (500, 0, 3), (4000, 3, 2)):
         with Runtime(t, w, h, spi=spi) as rt:
             rt.device.setOption("defer_permille", permille)
             rt.device.setOption("split_turns", split)   # leading turns as separate shade / trace launches
+            rt.device.setOption("fuse", fuse)           # consecutive iterations generated by one launch
             for _ in range(3):
                 rt.step()
             img = rt.getFramebufferForHost().copy()
