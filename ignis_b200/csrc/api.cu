@@ -127,6 +127,7 @@ struct igb200_ctx {
     std::vector<igb200_settings> queued;
     int fuse = 0;                      // iterations per launch (0: chosen so that a launch generates ~8 M camera rays, at most 8)
     bool maybe_carry = false;          // the last launch may have left paths behind
+    long long last_defer = 0;          // ... at most this many
     igb200_settings carry_settings{};  // settings the carried paths were generated with
     int carry_rank = 0, carry_world = 1, carry_tile = 0;
     RenderParams last_rp{}; DevScene last_sc{};
@@ -233,6 +234,27 @@ static int launch_wave(igb200_ctx* c, const RenderParams& rp, const DevScene& sc
 // Finishes the paths earlier launches left behind (deferred tail): one more launch without camera rays that runs every
 // path to its end. Everything that observes results (framebuffer, statistics) or changes what carried records refer to
 // (scene, size, partition, spi) calls this first.
+// `turns` wavefront turns as ordinary launches (shade + generate, trace, hand-over), see wavefront.cuh
+static int launch_split_turns(igb200_ctx* c, const WaveParams& P, int turns) {
+    if (turns <= 0) return 0;
+    CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
+    for (int t = 0; t < turns; ++t) {
+        { const int r = prof_begin(c, 2); if (r) return r; }
+        turn_shade_kernel(c->turn_shade_blocks)<<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
+        { const int r = prof_end(c); if (r) return r; }
+        { const int r = prof_begin(c, 1); if (r) return r; }
+        turn_trace_kernel(c->turn_trace_blocks, c->vote)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
+        { const int r = prof_end(c); if (r) return r; }
+        { const int r = prof_begin(c, 3); if (r) return r; }
+        k_turn_end<<<1, 1, 0, c->stream>>>(P);
+        { const int r = prof_end(c); if (r) return r; }
+        c->launches += 3;
+    }
+    CU(cudaGetLastError());
+    c->pending = true;
+    return 0;
+}
+
 // iterations per launch: enough to generate ~8 M camera rays, at most 8 (option "fuse" overrides)
 static int fuse_factor(const igb200_ctx* c, const igb200_settings* st) {
     if (c->fuse > 0) return c->fuse;
@@ -252,6 +274,9 @@ static int drain(igb200_ctx* c) {
     { const int r = flush_queued(c); if (r) return r; }
     if (c->maybe_carry) {
         CU(cudaSetDevice(c->device));
+        // up to `last_defer` paths may be waiting: their first turns are still big enough for the split kernels
+        const int turns = c->split_turns >= 0 ? std::min(c->split_turns, 4) : (int)std::min<long long>(4, c->last_defer >> 19);
+        { const int r = launch_split_turns(c, make_params(c, c->last_rp, c->last_sc, 0, nullptr, 0), turns); if (r) return r; }
         const int r = launch_wave(c, c->last_rp, c->last_sc, 0, nullptr, 0);
         if (r) return r;
         c->maybe_carry = false;
@@ -742,25 +767,9 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
     CU(cudaMemsetAsync(&c->control.p->next_cam, 0, sizeof(long long), c->stream));
     // split turns pay three launches each: worth it while a turn holds millions of rays (4 at 8 M camera rays, 2 at 1 M)
     const int split_turns = c->split_turns >= 0 ? c->split_turns : (int)std::min<long long>(4, std::max<long long>(1, cam_rays >> 19));
-    if (!rays && split_turns > 0) {
-        const WaveParams P = make_params(c, rp, sc, total, nullptr, defer);
-        CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
-        for (int t = 0; t < split_turns; ++t) {
-            { const int r = prof_begin(c, 2); if (r) return r; }
-            turn_shade_kernel(c->turn_shade_blocks)<<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
-            { const int r = prof_end(c); if (r) return r; }
-            { const int r = prof_begin(c, 1); if (r) return r; }
-            turn_trace_kernel(c->turn_trace_blocks, c->vote)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
-            { const int r = prof_end(c); if (r) return r; }
-            { const int r = prof_begin(c, 3); if (r) return r; }
-            k_turn_end<<<1, 1, 0, c->stream>>>(P);
-            { const int r = prof_end(c); if (r) return r; }
-            c->launches += 3;
-        }
-        CU(cudaGetLastError());
-    }
+    if (!rays) { const int r = launch_split_turns(c, make_params(c, rp, sc, total, nullptr, defer), split_turns); if (r) return r; }
     { const int r = launch_wave(c, rp, sc, total, d_rays, defer); if (r) return r; }
-    c->maybe_carry = defer > 0;
+    c->maybe_carry = defer > 0; c->last_defer = defer;
     c->carry_settings = *st; c->carry_settings.width = W; c->carry_settings.height = H; c->carry_settings.iter = st->iter + n_iter - 1;
     c->carry_rank = rp.rank; c->carry_world = rp.world; c->carry_tile = rp.tile_w;
     c->last_rp = rp; c->last_sc = sc;
