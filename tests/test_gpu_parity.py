@@ -181,9 +181,12 @@ def test_tile_partition_sums_to_full_frame():
     assert rel_l2(acc, full) <= 1e-6
 
 
-def test_full_size_properties_diamond():
-    """BASELINE config C2 at full size (1920x1080, spi 4): size-independent properties instead of the slow oracle."""
-    t = load_scene(scene_path("diamond_scene.json"))
+@pytest.mark.parametrize("scene", ["diamond_scene.json", "primitives.json", "synthetic_room.json"])
+def test_full_size_properties(scene):
+    """BASELINE configs C2 / C3 / C4 (stand-in) at full size (1920x1080, spi 4): size-independent properties instead of the
+    slow oracle -- exact camera-ray count, finite non-negative image, same seed => same image, and agreement of the
+    down-sampled frame with the oracle rendered at 1/8 resolution."""
+    t = load_scene(scene_path(scene))
     with Runtime(t, 1920, 1080, spi=4) as rt:
         rt.step()
         a = rt.getFramebufferForHost().copy()
@@ -194,13 +197,16 @@ def test_full_size_properties_diamond():
     assert st["CameraRayCount"] == 1920 * 1080 * 4
     assert np.isfinite(a).all() and (a >= 0).all()
     assert rel_l2(a, b) <= 1e-6                              # same seed, same iteration -> same image (up to atomics order)
-    # downsampled full-size image agrees statistically with the oracle at low resolution
     o = Oracle(t)
     ref = np.zeros((135, 240, 3), np.float32)
     for it in range(4):
         o.render(240, 135, spi=4, iteration=it, fb=ref)
     small = a.reshape(135, 8, 240, 8, 3).mean(axis=(1, 3))
     assert small.mean() == pytest.approx((ref / 4).mean(), rel=0.05)
+    # rays per camera ray are a property of the scene, not of the resolution
+    per_cam = (st["ShadowRayCount"] + st["BounceRayCount"]) / st["CameraRayCount"]
+    per_cam_ref = float(o.counters[1] + o.counters[2]) / float(o.counters[0])
+    assert per_cam == pytest.approx(per_cam_ref, rel=0.03)
 
 
 def test_deferred_tail_is_invisible():
