@@ -472,6 +472,24 @@ static igb200_light resolve_light(Eval& ev, const std::string& binding) {
             out.type = IGB200_LIGHT_SHAPE_AREA;
             out.entity_id = (int32_t)as_num(ctor_arg(ae, 0), "area light entity id");
             put3(out.p, rad);
+        } else if (ae.name == "make_sphere_area_emitter") {   // AreaLight.cpp:166-190; light/area.art:260-316
+            const Val& ent = ctor_arg(ae, 0);
+            const Val& sph = ctor_arg(ae, 1);
+            if (ent.kind != Val::Ctor || ent.name != "Entity" || sph.kind != Val::Ctor || sph.name != "Sphere") fail("make_sphere_area_emitter: Entity{...}, Sphere{...} expected");
+            out.type = IGB200_LIGHT_SPHERE_AREA;
+            out.entity_id = (int32_t)as_num(ctor_arg(ent, 0), "sphere light entity id");
+            put3(out.p, rad);
+            put3(out.p + 3, as_vec(ctor_arg(sph, 0), "sphere origin"));
+            const float radius = as_num(ctor_arg(sph, 1), "sphere radius");
+            out.p[6] = radius;
+            // compute_ellipsoid_area (shapes/sphere.art:21-27) from the columns of the entity's global matrix: a per-light constant,
+            // evaluated in double and rounded once (ignis_b200/scene.py: ellipsoid_area does the same)
+            const Val& gm = ctor_arg(ent, 3);
+            if (gm.kind != Val::Ctor || gm.name != "make_mat3x4") fail("sphere light: global_mat is not make_mat3x4(...)");
+            double l[3];
+            for (int k = 0; k < 3; ++k) { const Val c = as_vec(ctor_arg(gm, k), "global matrix column"); l[k] = 0; for (int i = 0; i < 3; ++i) { const double x = (double)c.f[i] * (double)radius; l[k] += x * x; } }
+            const double P = (double)1.6f;
+            out.p[7] = (float)(4 * (double)3.14159265359f * std::pow((std::pow(l[0] * l[1], P / 2) + std::pow(l[0] * l[2], P / 2) + std::pow(l[1] * l[2], P / 2)) / 3, 1 / P));
         } else {
             fail("area emitter '" + ae.name + "' is not supported by this device");
         }

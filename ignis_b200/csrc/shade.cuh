@@ -149,6 +149,32 @@ __device__ __forceinline__ void shape_emitter_sample(const DevScene& sc, int ent
     weight = surf.area * (float)count;
 }
 
+// shapes/sphere.art:29-45 (only what the light sample needs: point and normal)
+__device__ __forceinline__ void sphere_point_for_normal(const float4* E, V3 origin, float radius, V3 normal, V3& point, V3& gn) {
+    const float4 g0 = ldg4(E), g1 = ldg4(E + 1), g2 = ldg4(E + 2), n0 = ldg4(E + 3), n1 = ldg4(E + 4), n2 = ldg4(E + 5);
+    point = xform_point(g0, g1, g2, origin + mulf(normal, radius));
+    gn = normalize(v3(dot(v3(n0.x, n0.y, n0.z), normal), dot(v3(n1.x, n1.y, n1.z), normal), dot(v3(n2.x, n2.y, n2.z), normal)));
+}
+// light/area.art:268-294
+__device__ __forceinline__ void sphere_emitter_sample(const DevScene& sc, const float* L, float u, float v, V3 from_point, V3& to_point, V3& to_normal) {
+    const float4* E = sc.ent_shade + (size_t)__float_as_int(__ldg(L + 1)) * 6;
+    const V3 origin = v3(__ldg(L + 5), __ldg(L + 6), __ldg(L + 7)); const float radius = __ldg(L + 8);
+    const float4 g0 = ldg4(E), g1 = ldg4(E + 1), g2 = ldg4(E + 2);
+    const V3 glb_org = xform_point(g0, g1, g2, origin);
+    sphere_point_for_normal(E, origin, radius, equal_area_square_to_sphere(u, v), to_point, to_normal);
+    const V3 os = from_point - glb_org, ps = from_point - to_point;
+    if (!(len2(ps) <= len2(os))) {
+        const V3 po = glb_org - to_point;
+        const V3 np = to_point + mulf(po, 2);
+        const V3 norm = normalize(np - glb_org);
+        const float4 n0 = ldg4(E + 3), n1 = ldg4(E + 4), n2 = ldg4(E + 5);   // rows of normal_mat
+        // pointmapper.art:33: (normal_mat^T n) / |diag(normal_mat)|^2
+        const V3 c0 = v3(n0.x, n1.x, n2.x), c1 = v3(n0.y, n1.y, n2.y), c2 = v3(n0.z, n1.z, n2.z);
+        const V3 ln = mulf(v3(dot(c0, norm), dot(c1, norm), dot(c2, norm)), 1 / len2(v3(n0.x, n1.y, n2.z)));
+        sphere_point_for_normal(E, origin, radius, ln, to_point, to_normal);
+    }
+}
+
 __device__ __forceinline__ LightSample light_sample_direct(const DevScene& sc, const float* L, int type, Rng& rnd, const Surf& from) {
     LightSample o;
     if (type == 0) {          // light/env.art:84-88
@@ -187,6 +213,12 @@ __device__ __forceinline__ LightSample light_sample_direct(const DevScene& sc, c
             o.pdf.value = safe_div(1, sq.s); o.pdf.measure = 0;
             weight = sq.s;
             radiance = c3(__ldg(L + 23), __ldg(L + 24), __ldg(L + 25));
+        } else if (type == 4) {   // sphere emitter
+            sphere_emitter_sample(sc, L, u, v, from.point, to_point, to_normal);
+            const float area = __ldg(L + 9);
+            o.pdf.value = safe_div(1, area); o.pdf.measure = 1;
+            weight = area;
+            radiance = c3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));
         } else {
             Surf to; float pdfv;
             shape_emitter_sample(sc, __float_as_int(__ldg(L + 1)), u, v, to, pdfv, weight);
@@ -290,6 +322,9 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
                     const PlaneEm e = load_plane(L);
                     const SQ sqv = compute_sq(e, rorg);
                     pdf.value = safe_div(1, sqv.s); pdf.measure = 0;
+                } else if (lt == 4) {   // light/area.art:301-303
+                    intensity = c3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));
+                    pdf.value = safe_div(1, __ldg(L + 9)); pdf.measure = 1;
                 } else {
                     intensity = c3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));
                     Surf es; float pdfv, w;

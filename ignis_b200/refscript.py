@@ -26,7 +26,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .scene import (BSDF_DIELECTRIC, BSDF_DIFFUSE, LIGHT_ENV_CONST, LIGHT_PLANE_AREA, LIGHT_POINT, LIGHT_SHAPE_AREA,
+from .scene import (BSDF_DIELECTRIC, BSDF_DIFFUSE, LIGHT_ENV_CONST, LIGHT_PLANE_AREA, LIGHT_POINT, LIGHT_SHAPE_AREA, LIGHT_SPHERE_AREA,
                     SHAPE_SPHERE, SceneTables)
 
 STD_LIB_STUB = "// <the Artic standard library (ig_api[], ScriptCompiler.cpp:36-51) precedes every stage>\nfn @make_dummy() = 0;\n\n"
@@ -178,6 +178,21 @@ def _lights(t: SceneTables, tree: _Tree) -> str:
             rad = tree.color(cid, "radiance", p[0:3])
             ent = tree.integer(cid, f"ae_{cid}_ent_id", int(l["entity_id"]))
             s += tree.pull_header() + f"  let ae_{cid} = make_shape_area_emitter_proxy({ent}, entities, shapes_trimesh);\n"
+            s += f"  let light_{cid} = make_area_light({i}, ae_{cid}, @|ctx| {{ maybe_unused(ctx); {rad} }});\n"
+        elif ty == LIGHT_SPHERE_AREA:   # AreaLight.cpp:166-190: every entity field is a Dynamic (registry) parameter
+            pre = f"ae_{cid}"
+            rad = tree.color(cid, "radiance", p[0:3])
+            ent = t.entities[int(l["entity_id"])]
+            def mat(name, cols):
+                return "make_mat%s(%s)" % ("3x4" if len(cols) == 4 else "3x3", ",".join(tree.vector(cid, f"{pre}_{name}_c{k}", c, dynamic=True) for k, c in enumerate(cols)))
+            local = mat("local", [ent[3 * k:3 * k + 3] for k in range(4)])
+            glob = mat("global", [ent[12 + 3 * k:12 + 3 * k + 3] for k in range(4)])
+            norm = mat("normal", [ent[24 + 3 * k:24 + 3 * k + 3] for k in range(3)])
+            eid, mid, sid = (tree.integer(cid, f"{pre}_{n}", v) for n, v in (("ent_id", int(l["entity_id"])), ("ent_mat_id", int(ent[34:35].view(np.int32)[0])), ("ent_shp_id", int(ent[33:34].view(np.int32)[0]))))
+            org = tree.vector(cid, pre + "_origin", p[3:6], dynamic=True)
+            radius = tree.number(cid, pre + "_radius", p[6], dynamic=True)
+            s += tree.pull_header() + (f"  let ae_{cid} = make_sphere_area_emitter(Entity{{ id = {eid}, mat_id = {mid}, local_mat = {local}, global_mat = {glob}, "
+                                       f"normal_mat = {norm}, shape_id = {sid} }},  Sphere{{ origin = {org}, radius = {radius} }});\n")
             s += f"  let light_{cid} = make_area_light({i}, ae_{cid}, @|ctx| {{ maybe_unused(ctx); {rad} }});\n"
         else:
             raise ValueError(ty)

@@ -45,6 +45,7 @@ LIGHT_ENV_CONST = 0   # make_environment_light -> ..._function_spherical (light/
 LIGHT_POINT = 1       # make_point_light (light/point.art:1-18)
 LIGHT_PLANE_AREA = 2  # make_area_light + make_plane_area_emitter (light/area.art:10-43,124-258)
 LIGHT_SHAPE_AREA = 3  # make_area_light + make_shape_area_emitter (light/area.art:62-107)
+LIGHT_SPHERE_AREA = 4  # make_area_light + make_sphere_area_emitter (light/area.art:260-316)
 
 LOOKUP_DTYPE = np.dtype([("type_id", "<u4"), ("flags", "<u4"), ("offset", "<u8")])
 LEAF_DTYPE = np.dtype([("min", "<f4", 3), ("entity_id", "<i4"), ("max", "<f4", 3), ("shape_id", "<i4"),
@@ -95,6 +96,16 @@ class SceneTables:
             if int(lk["type_id"]) == SHAPE_TRIMESH:
                 total += int(np.frombuffer(self.shape_data, "<u4", 1, int(lk["offset"]))[0])
         return total
+
+
+def ellipsoid_area(global_linear, radius: float) -> float:
+    """compute_ellipsoid_area (src/artic/shapes/sphere.art:21-27): Knud Thomsen's formula on the squared axis lengths, as the
+    reference writes it. A per-light constant: evaluated here in double and rounded once (the C++ recogniser does the same)."""
+    m = np.asarray(global_linear, np.float32).astype(np.float64)
+    r = float(np.float32(radius))
+    l1, l2, l3 = (float(np.dot(m[:, k] * r, m[:, k] * r)) for k in range(3))
+    p = float(np.float32(1.6))
+    return float(F(4 * float(np.float32(3.14159265359)) * math.pow((math.pow(l1 * l2, p / 2) + math.pow(l1 * l3, p / 2) + math.pow(l2 * l3, p / 2)) / 3, 1 / p)))
 
 
 # ------------------------------------------------------------------ JSON helpers
@@ -403,7 +414,7 @@ def load_scene(path, width: int | None = None, height: int | None = None,
             lo, hi = (origin - radius - F(1e-5)).astype(F), (origin + radius + F(1e-5)).astype(F)
             blob += np.asarray([origin[0], origin[1], origin[2], radius], "<f4").tobytes()
             lookups.append((SHAPE_SPHERE, 0, off))
-            shape_info.append(dict(type=SHAPE_SPHERE, lo=lo, hi=hi, mesh=None, plane=None))
+            shape_info.append(dict(type=SHAPE_SPHERE, lo=lo, hi=hi, mesh=None, plane=None, origin=origin, radius=radius))
         else:
             mesh = _build_trimesh(sj)
             lo = (mesh.vertices.min(axis=0) - F(1e-5)).astype(F)
@@ -501,9 +512,21 @@ def load_scene(path, width: int | None = None, height: int | None = None,
                 raise SceneError(f"No entity named '{ename}' exists for area light")
             ei = ent_info[ename]
             info = shape_info[ei["shape_id"]]
-            if info["type"] != SHAPE_TRIMESH:
-                raise SceneError("sphere area lights are outside the supported path (SURVEY §8f)")
             t = ei["transform"]
+            if info["type"] != SHAPE_TRIMESH:
+                # analytic sphere: AreaLight.cpp:166-190 (RepresentationType::Sphere), light/area.art:260-316
+                org, radius = info["origin"], float(info["radius"])
+                area = ellipsoid_area(t[:3, :3].astype(F), radius)
+                rec["type"] = LIGHT_SPHERE_AREA
+                rec["entity_id"] = ei["id"]
+                if "power" in lj:
+                    rec["p"][0:3] = (_color(lj["power"], (0, 0, 0)) * F(1.0 / PI / area)).astype(F)
+                else:
+                    rec["p"][0:3] = _color(lj.get("radiance"), (1, 1, 1))
+                rec["p"][3:6], rec["p"][6], rec["p"][7] = org, radius, area
+                fin_of_entity[ename] = len(fin_l)
+                fin_l.append(rec)
+                continue
             plane = info["plane"] if lj.get("optimize", True) else None
             if plane is not None:
                 origin = (t[:3, :3] @ plane["origin"].astype(np.float64) + t[:3, 3]).astype(F)

@@ -65,14 +65,16 @@ typedef struct igb200_material {
 enum { IGB200_LIGHT_ENV_CONST = 0,  /* make_environment_light (constant radiance), light/env.art:75-100,161-164 */
        IGB200_LIGHT_POINT = 1,      /* make_point_light, light/point.art:1-18 */
        IGB200_LIGHT_PLANE_AREA = 2, /* make_area_light(make_plane_area_emitter), light/area.art:10-43,124-258 */
-       IGB200_LIGHT_SHAPE_AREA = 3  /* make_area_light(make_shape_area_emitter), light/area.art:62-107 */ };
+       IGB200_LIGHT_SHAPE_AREA = 3, /* make_area_light(make_shape_area_emitter), light/area.art:62-107 */
+       IGB200_LIGHT_SPHERE_AREA = 4 /* make_area_light(make_sphere_area_emitter), light/area.art:260-316 */ };
 
 typedef struct igb200_light {
     int32_t type;      /* IGB200_LIGHT_* */
     int32_t entity_id; /* area lights: the emissive entity */
     float   p[30];     /* ENV_CONST: radiance rgb | POINT: position xyz, intensity rgb |
                           PLANE_AREA: origin, x_axis, y_axis, normal (3 each), area, t0..t3 (2 each), radiance rgb |
-                          SHAPE_AREA: radiance rgb */
+                          SHAPE_AREA: radiance rgb |
+                          SPHERE_AREA: radiance rgb, sphere origin xyz (local), radius, area (compute_ellipsoid_area, shapes/sphere.art:21-27) */
 } igb200_light;
 
 /* make_perspective_camera(eye, dir, up, compute_scale_from_{h,v}fov(fov, aspect), w, h, tmin, tmax):

@@ -303,7 +303,7 @@ static_assert(sizeof(EntityLeaf) == 96 && sizeof(MaterialDesc) == 64 && sizeof(L
 
 enum { SHAPE_TRIMESH = 0, SHAPE_SPHERE = 1 };
 enum { BSDF_DIFFUSE = 0, BSDF_DIELECTRIC = 1 };
-enum { LIGHT_ENV_CONST = 0, LIGHT_POINT = 1, LIGHT_PLANE_AREA = 2, LIGHT_SHAPE_AREA = 3 };
+enum { LIGHT_ENV_CONST = 0, LIGHT_POINT = 1, LIGHT_PLANE_AREA = 2, LIGHT_SHAPE_AREA = 3, LIGHT_SPHERE_AREA = 4 };
 
 // ------------------------------------------------------------------------------------------ own BVH2 (median split)
 struct Bvh2 {
@@ -751,6 +751,39 @@ inline void shape_emitter_sample(const Scene& sc, int entity_id, Vec2 uv, Surfac
     weight = surf.area * (float)count;
 }
 
+// light/area.art:260-316 sphere emitter; p = radiance rgb, sphere origin (local) xyz, radius, area. The area is
+// compute_ellipsoid_area (shapes/sphere.art:21-27), three pow() calls on per-light constants: evaluated once by the host
+// (ignis_b200/scene.py, csrc/host/script_recognizer.cpp) and passed in, so that no transcendental sits on the parity path.
+// shapes/sphere.art:29-45
+inline SurfaceElement sphere_surface_for_normal(const Entity& e, Vec3 origin, float radius, float area, Vec3 normal) {
+    const Vec3 point = origin + mulf(normal, radius);
+    const Vec2 uv = sphere_map_uv(normal);
+    const Vec3 gn = normalize(mat3x3_mul(e.normal_mat, normal));
+    SurfaceElement s;
+    s.is_entering = true; s.point = transform_point(e.global_mat, point); s.face_normal = gn; s.area = area; s.inv_area = safe_div(1, area);
+    s.prim_coords = uv; s.tex_coords = uv; s.local = make_orthonormal(gn);
+    return s;
+}
+inline void sphere_emitter_sample(const Scene& sc, const LightDesc& l, Vec2 uv, Vec3 from_point, SurfaceElement& surf, Pdf& pdf, float& weight) {
+    const Entity& e = sc.entities[l.entity_id];
+    const Vec3 origin = v3(l.p[3], l.p[4], l.p[5]); const float radius = l.p[6], area = l.p[7];
+    const Vec3 glb_org = transform_point(e.global_mat, origin);
+    surf = sphere_surface_for_normal(e, origin, radius, area, equal_area_square_to_sphere(uv.x, uv.y));
+    const Vec3 p = surf.point;
+    const Vec3 os = from_point - glb_org, ps = from_point - p;
+    if (!(len2(ps) <= len2(os))) {   // the sampled point is on the far side: mirror it through the centre (:285-292)
+        const Vec3 po = glb_org - p;
+        const Vec3 np = p + mulf(po, 2);
+        const Vec3 norm = normalize(np - glb_org);
+        // pointmapper.art:33 to_local_normal = (normal_mat^T n) / |diag(normal_mat)|^2
+        const Mat3x3& m = e.normal_mat;
+        const Vec3 ln = mulf(v3(dot(m.c0, norm), dot(m.c1, norm), dot(m.c2, norm)), 1 / len2(v3(m.c0.x, m.c1.y, m.c2.z)));
+        surf = sphere_surface_for_normal(e, origin, radius, area, ln);
+    }
+    pdf = Pdf{safe_div(1, area), PDF_AREA};
+    weight = area;
+}
+
 struct LightRef { const LightDesc* d; bool infinite; int id; };
 
 inline bool light_delta(const LightDesc& l) { return l.type == LIGHT_POINT; }
@@ -779,6 +812,9 @@ inline DirectLightSample light_sample_direct(const Scene& sc, const LightDesc& l
         if (l.type == LIGHT_PLANE_AREA) {
             PlaneEmitter(l).sample_direct(Vec2{u, v}, from.point, to, pdf, weight);
             radiance = col(l.p[21], l.p[22], l.p[23]);
+        } else if (l.type == LIGHT_SPHERE_AREA) {
+            sphere_emitter_sample(sc, l, Vec2{u, v}, from.point, to, pdf, weight);
+            radiance = col(l.p[0], l.p[1], l.p[2]);
         } else {
             float pdfv;
             shape_emitter_sample(sc, l.entity_id, Vec2{u, v}, to, pdfv, weight);
@@ -860,6 +896,9 @@ struct PathTracer {
                 if (l.type == LIGHT_PLANE_AREA) {
                     intensity = col(l.p[21], l.p[22], l.p[23]);
                     pdf = PlaneEmitter(l).pdf_direct(ctx.ray.org);
+                } else if (l.type == LIGHT_SPHERE_AREA) {   // light/area.art:301-303
+                    intensity = col(l.p[0], l.p[1], l.p[2]);
+                    pdf = Pdf{safe_div(1, l.p[7]), PDF_AREA};
                 } else {  // shape emitter: light/area.art:77-86,105
                     intensity = col(l.p[0], l.p[1], l.p[2]);
                     SurfaceElement s; float pdfv, w;
@@ -1155,6 +1194,22 @@ void igo_detmath(int fn, const float* a, const float* b, float* out, int64_t n) 
         default: out[i] = 0;
         }
     }
+}
+// One sample of the pure dielectric BSDF (bsdf/dielectric.art:15-37) on a surface with normal `n` (unit), seen from out_dir
+// (unit, pointing away from the surface); `entering`: the ray comes from the n1 side. seed/counter select the random number.
+// out = in_dir xyz, eta, colour r (ks = 0.25, kt = 0.5 so that the branch taken is visible), Fresnel factor.
+void igo_dielectric_sample(float n1, float n2, const float n[3], const float out_dir[3], int entering, uint32_t seed, uint32_t counter, float out[6]) {
+    SurfaceElement surf{};
+    surf.is_entering = entering != 0;
+    surf.local = make_orthonormal(v3(n[0], n[1], n[2]));
+    Bsdf b{}; b.type = BSDF_DIELECTRIC; b.surf = &surf; b.n1 = n1; b.n2 = n2; b.ks = col(0.25f, 0.25f, 0.25f); b.kt = col(0.5f, 0.5f, 0.5f);
+    Rng rnd{seed, counter};
+    BsdfSample sm{};
+    b.sample(rnd, v3(out_dir[0], out_dir[1], out_dir[2]), false, sm);
+    const float k = surf.is_entering ? n1 / n2 : n2 / n1;
+    FresnelTerm ft{0, 1};
+    if (!fresnel(k, dot(v3(out_dir[0], out_dir[1], out_dir[2]), surf.local.c2), ft)) ft = FresnelTerm{0, 1};
+    out[0] = sm.in_dir.x; out[1] = sm.in_dir.y; out[2] = sm.in_dir.z; out[3] = sm.eta; out[4] = sm.color.r; out[5] = ft.factor;
 }
 void igo_cosine_hemisphere(float u, float v, float out[4]) { const DirSample d = sample_cosine_hemisphere(u, v); out[0] = d.dir.x; out[1] = d.dir.y; out[2] = d.dir.z; out[3] = d.pdf; }
 void igo_equal_area_sphere(float u, float v, float out[3]) { const Vec3 d = equal_area_square_to_sphere(u, v); out[0] = d.x; out[1] = d.y; out[2] = d.z; }

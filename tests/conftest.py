@@ -31,3 +31,16 @@ def flat_scene():
         "entities": [{"name": "Bottom", "shape": "Bottom", "bsdf": "ground"}],
         "lights": [],
     }
+
+
+def furnace_scene():
+    """White furnace: a non-absorbing glass box under a constant white environment; every pixel converges to 1."""
+    return {
+        "technique": {"type": "path", "max_depth": 64},
+        "camera": {"type": "perspective", "fov": 40, "near_clip": 0.01, "far_clip": 100, "transform": {"lookat": {"origin": [2.2, -3.1, 1.7], "target": [0, 0, 0], "up": [0, 0, 1]}}},
+        "film": {"size": [96, 96]},
+        "bsdfs": [{"type": "dielectric", "name": "glass", "int_ior": 1.5, "ext_ior": 1.0}],
+        "shapes": [{"type": "cube", "name": "Box", "width": 1.6, "height": 1.2, "depth": 1.0, "origin": [-0.8, -0.6, -0.5]}],
+        "entities": [{"name": "Box", "shape": "Box", "bsdf": "glass", "transform": {"rotate": [15, 25, 35]}}],
+        "lights": [{"type": "env", "name": "env", "radiance": [1, 1, 1]}],
+    }

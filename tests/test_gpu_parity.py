@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import flat_scene
+from conftest import flat_scene, furnace_scene
 from ignis_b200.device import B200Device, RAY_DTYPE, Runtime
 from ignis_b200.scene import load_scene
 from oracle.oracle import Oracle, detmath
@@ -112,6 +112,7 @@ def render_both(tables, w, h, spi, iters, seed=0):
     ("evaluation/multilight-uniform.json", 128, 128, 2, 1),
     ("evaluation/emissive-plane.json", 128, 128, 1, 1),
     ("evaluation/point.json", 64, 64, 1, 1),
+    ("evaluation/sphere-light-pure.json", 128, 128, 2, 2),   # analytic sphere area light (light/area.art:260-316)
     ("synthetic_room.json", 192, 108, 2, 2),             # stand-in for C4: 1.8 M instanced triangles, geometry read through L2
 ])
 def test_radiance_matches_oracle(scene, w, h, spi, iters):
@@ -244,3 +245,16 @@ def test_deferred_tail_is_invisible():
     for it in range(3):
         o.render(w, h, spi=spi, iteration=it, fb=ref)
     assert rel_l2(out[4000][0], ref) <= REL_L2_TOL
+
+
+def test_white_furnace_through_glass_on_gpu():
+    """Energy conservation of the whole device pipeline on delta paths (tests/test_oracle_kat.py has the oracle's)."""
+    t = load_scene(furnace_scene())
+    with Runtime(t, 256, 256, spi=8) as rt:
+        for _ in range(8):
+            rt.step()
+        img = rt.image()
+        st = rt.device.getStatistics()
+    assert st["BounceRayCount"] > 0.2 * st["CameraRayCount"]
+    assert float(img.mean()) == pytest.approx(1.0, abs=2e-3)
+    assert np.abs(img.reshape(16, 16, 16, 16, 3).mean(axis=(1, 3, 4)) - 1).max() < 0.05

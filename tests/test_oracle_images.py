@@ -13,7 +13,7 @@ from oracle.oracle import Oracle
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EPS_1024 = {"plane-d1": 1e-3, "plane-d6": 1e-3, "point": 1e-3, "emissive-plane": 1e-3, "cbox-d1": 5e-3, "cbox-d6": 5e-3,
-            "multilight-uniform": 3e-4}
+            "multilight-uniform": 3e-4, "sphere-light-pure": 3e-3}
 
 
 def relmse(img, ref):
@@ -26,7 +26,7 @@ def relmse(img, ref):
 
 
 @pytest.mark.parametrize("name,spp", [("plane-d1", 128), ("plane-d6", 128), ("point", 64), ("emissive-plane", 256),
-                                      ("cbox-d1", 128), ("cbox-d6", 512), ("multilight-uniform", 512)])
+                                      ("cbox-d1", 128), ("cbox-d6", 512), ("multilight-uniform", 512), ("sphere-light-pure", 256)])
 def test_oracle_matches_reference_image(name, spp):
     refs = np.load(os.path.join(ROOT, "tests", "golden", "ref_images.npz"))
     ref = refs[name].astype(np.float32)

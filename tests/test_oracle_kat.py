@@ -173,3 +173,79 @@ def test_oracle_bvh_equals_brute_force_on_coplanar_geometry():
         assert a.tobytes() == b.tobytes()
         fl = np.full(len(rays), 8, np.uint32)
         np.testing.assert_array_equal(o.trace_any(rays, flags=fl, use_bvh=True), o.trace_any(rays, flags=fl, use_bvh=False))
+
+
+# ---- pure dielectric BSDF (bsdf/dielectric.art:15-37, core/fresnel.art:7-27): the reference holds no test or image for it
+# (its only dielectric reference image is a Radiance rendering its own algorithm does not reproduce, tools/make_golden.py),
+# so it is pinned by the physics it implements: Snell's law, the law of reflection, the unpolarised Fresnel reflectance, and
+# energy conservation of the whole path loop (white furnace).
+def _dielectric_sample(n1, n2, normal, out_dir, entering, seed, counter=1):
+    import ctypes as C
+    from oracle import oracle as o
+    f3 = C.c_float * 3
+    out = (C.c_float * 6)()
+    o.lib().igo_dielectric_sample(n1, n2, f3(*normal), f3(*out_dir), int(entering), seed, counter, out)
+    return np.array(out[0:3], np.float64), float(out[3]), float(out[4]), float(out[5])
+
+
+@pytest.mark.parametrize("n1,n2,entering", [(1.0, 1.5, True), (1.0, 1.5, False), (1.0, 2.417, True), (1.33, 1.0, True)])
+def test_dielectric_obeys_snell_reflection_and_fresnel(n1, n2, entering):
+    rng = np.random.default_rng(7)
+    n = np.array([0.0, 0.0, 1.0])
+    k = n1 / n2 if entering else n2 / n1
+    n_reflect = n_refract = 0
+    for trial in range(400):
+        theta = rng.uniform(0, np.pi / 2 * 0.98)
+        phi = rng.uniform(0, 2 * np.pi)
+        wo = np.array([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)])
+        wi, eta, colour, F = _dielectric_sample(n1, n2, n, wo.astype(np.float32), entering, 1234 + trial)
+        sin_o, sin2_t = np.sin(theta), (k * np.sin(theta)) ** 2
+        # unpolarised Fresnel reflectance from the textbook formula (total internal reflection -> 1)
+        if sin2_t >= 1:
+            F_ref = 1.0
+        else:
+            cos_o, cos_t = np.cos(theta), np.sqrt(1 - sin2_t)
+            rs = (k * cos_o - cos_t) / (k * cos_o + cos_t)
+            rp = (cos_o - k * cos_t) / (cos_o + k * cos_t)
+            F_ref = 0.5 * (rs * rs + rp * rp)
+        assert F == pytest.approx(F_ref, abs=2e-5)
+        assert np.linalg.norm(wi) == pytest.approx(1.0, abs=1e-5)
+        assert abs(np.dot(np.cross(wi, wo), n)) < 1e-5               # incident, outgoing and normal are coplanar
+        if colour == pytest.approx(0.25):                            # reflected: mirror image about the normal
+            n_reflect += 1
+            np.testing.assert_allclose(wi, [-wo[0], -wo[1], wo[2]], atol=1e-5)
+            assert eta == 1.0
+        else:                                                        # refracted: Snell, on the other side, opposite azimuth
+            n_refract += 1
+            assert colour == pytest.approx(0.5) and eta == pytest.approx(k)
+            assert wi[2] < 0
+            assert np.hypot(wi[0], wi[1]) == pytest.approx(k * sin_o, abs=2e-5)
+            assert np.dot(wi[:2], wo[:2]) <= 1e-7
+    assert n_reflect > 0 and n_refract > 0
+
+
+def test_dielectric_reflection_frequency_is_the_fresnel_factor():
+    n = np.array([0.0, 0.0, 1.0], np.float32)
+    wo = np.array([np.sin(1.1), 0.0, np.cos(1.1)], np.float32)       # 63 degrees: F ~ 0.10 for glass
+    _, _, _, F = _dielectric_sample(1.0, 1.5, n, wo, True, 1)
+    hits = sum(_dielectric_sample(1.0, 1.5, n, wo, True, 99, counter=c)[2] == pytest.approx(0.25) for c in range(1, 4001))
+    assert hits / 4000 == pytest.approx(F, abs=4 * np.sqrt(F * (1 - F) / 4000))
+
+
+def test_white_furnace_through_glass():
+    """A white, non-absorbing glass cube and sphere-free scene under a constant white environment: whatever a path does --
+    reflect, refract, total internal reflection, Russian roulette -- it ends in the environment with throughput 1, so every
+    pixel converges to exactly 1 (max_depth 64 truncates a negligible tail). Catches wrong Fresnel weights, a missing or
+    spurious eta^2 factor, biased roulette and wrong MIS on the delta lobe."""
+    from conftest import furnace_scene
+    scene = furnace_scene()
+    t = load_scene(scene)
+    o = Oracle(t)
+    fb = np.zeros((96, 96, 3), np.float32)
+    n_it = 16
+    for it in range(n_it):
+        o.render(96, 96, spi=8, iteration=it, fb=fb)
+    img = fb / n_it
+    assert int(o.counters[2]) > 5 * int(o.counters[0]) * 0.05       # the cube is actually hit and paths bounce inside it
+    assert img.mean() == pytest.approx(1.0, abs=3e-3)
+    assert np.abs(img.reshape(12, 8, 12, 8, 3).mean(axis=(1, 3, 4)) - 1).max() < 0.05   # ... everywhere, not only on average

@@ -13,7 +13,7 @@ from ignis_b200.scene import load_scene
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "evaluation/cbox-d6.json", "evaluation/multilight-uniform.json",
-          "evaluation/emissive-plane.json", "evaluation/point.json", "evaluation/plane-d1.json"]
+          "evaluation/emissive-plane.json", "evaluation/point.json", "evaluation/plane-d1.json", "evaluation/sphere-light-pure.json"]
 
 
 def scene(name):
@@ -49,7 +49,7 @@ def test_recognised_descriptors_equal_loader_descriptors(name, mode):
         assert len(inf) == len(t.infinite_lights) and len(fin) == len(t.finite_lights)
         for got, ref in list(zip(inf, t.infinite_lights)) + list(zip(fin, t.finite_lights)):
             assert int(got["type"]) == int(ref["type"])
-            if int(ref["type"]) == 3:
+            if int(ref["type"]) in (3, 4):
                 assert int(got["entity_id"]) == int(ref["entity_id"])
             if exact:
                 np.testing.assert_array_equal(got["p"].view(np.uint32), ref["p"].view(np.uint32))
