@@ -6,6 +6,9 @@ import time
 
 import numpy as np
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from make_golden import IMAGES  # noqa: E402
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from ignis_b200.scene import load_scene  # noqa: E402
@@ -37,7 +40,7 @@ def main():
         for it in range(spp // spi):
             o.render(w, h, spi=spi, iteration=it, fb=fb)
         img = fb / (spp // spi)
-        ref = refs[name].astype(np.float32)
+        ref = refs[IMAGES[name][:-4]].astype(np.float32)
         e = relmse(img, ref)
         eps = EPS.get(name, 1e-3)
         print(f"{name:24s} spp={spp} relmse={e:.3e} eps={eps:.0e} {'OK' if e < eps else 'FAIL'} mean={img.mean():.5f} ref_mean={ref.mean():.5f} "

@@ -27,22 +27,27 @@ IMAGES = {
     # radiance scaling in the non-adjoint direction, so the reference's algorithm itself does not reproduce that image -- it is
     # not a pin for a restatement of that algorithm. The dielectric is pinned analytically instead: tests/test_oracle_kat.py.)
     "sphere-light-pure": "ref-sphere-light-4096.exr",
+    # the same references rendered with other shape providers / without the plane optimisation: pins the shape (trimesh) emitter
+    "sphere-light-ico": "ref-sphere-light-4096.exr", "sphere-light-uv": "ref-sphere-light-4096.exr", "sphere-light-ico-nopt": "ref-sphere-light-4096.exr",
+    "emissive-plane-nopt": "ref-emissive-plane-4096.exr", "emissive-plane-scale": "ref-emissive-plane-scale-4096.exr",
+    "emissive-plane-scale-nopt": "ref-emissive-plane-scale-4096.exr",
 }
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "primitives_data.json", "flipped_prim.json",
           "meshes/Bottom.ply", "meshes/Top.ply", "meshes/Left.ply", "meshes/Right.ply", "meshes/Back.ply", "meshes/Diamond.ply"]
 EVAL = ["plane-base.json", "plane-d1.json", "plane-d6.json", "point.json", "emissive-plane.json", "cbox-base.json", "cbox-d1.json",
         "cbox-d6.json", "multilight.json", "multilight-uniform.json", "flipped-prim-base.json", "flipped-prim-diffuse.json",
-        "sphere-light-base.json", "sphere-light-pure.json"]
+        "sphere-light-base.json", "sphere-light-pure.json", "sphere-light-ico.json", "sphere-light-uv.json", "sphere-light-ico-nopt.json",
+        "emissive-plane-nopt.json", "emissive-plane-scale.json", "emissive-plane-scale-nopt.json"]
 
 
 def main():
     out = {}
-    for key, fn in IMAGES.items():
+    for fn in sorted(set(IMAGES.values())):   # one array per reference file, keyed by its name; tests map scene -> file with IMAGES
         img = cv2.imread(os.path.join(REF, "evaluation", "references", fn), cv2.IMREAD_UNCHANGED)
         if img is None:
             print("skip", fn)
             continue
-        out[key] = img[..., 2::-1][..., :3].astype(np.float16) if img.shape[-1] >= 3 else img.astype(np.float16)
+        out[fn[:-4]] = img[..., 2::-1][..., :3].astype(np.float16) if img.shape[-1] >= 3 else img.astype(np.float16)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_images.npz"), **out)
     for f in SCENES:
