@@ -258,3 +258,25 @@ def test_white_furnace_through_glass_on_gpu():
     assert st["BounceRayCount"] > 0.2 * st["CameraRayCount"]
     assert float(img.mean()) == pytest.approx(1.0, abs=2e-3)
     assert np.abs(img.reshape(16, 16, 16, 16, 3).mean(axis=(1, 3, 4)) - 1).max() < 0.05
+
+
+@pytest.mark.parametrize("w,h,spi,seed,world", [(97, 53, 3, 7, 1), (33, 129, 5, 123, 3), (1, 1, 1, 0, 1), (300, 7, 2, 99, 2)])
+def test_odd_sizes_seeds_and_partitions(w, h, spi, seed, world):
+    """Ragged frames (not multiples of the 32-pixel tile), odd spi, user seeds, ranks with unequal tile counts, fused iterations."""
+    t = load_scene(scene_path("diamond_scene.json"))
+    o = Oracle(t)
+    ref = np.zeros((h, w, 3), np.float32)
+    for it in range(3):
+        o.render(w, h, spi=spi, iteration=it, seed=seed, fb=ref)
+    acc = np.zeros_like(ref)
+    cam = 0
+    for r in range(world):
+        with Runtime(t, w, h, spi=spi, seed=seed) as rt:
+            rt.device.setPartition(r, world, 32)
+            rt.device.setOption("fuse", 2)
+            for _ in range(3):
+                rt.step()
+            acc += rt.getFramebufferForHost()
+            cam += rt.device.getStatistics()["CameraRayCount"]
+    assert cam == w * h * spi * 3
+    assert rel_l2(acc, ref) <= REL_L2_TOL
