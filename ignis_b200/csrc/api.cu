@@ -589,6 +589,7 @@ int igb200_clear(igb200_ctx* c, const char* aov) {
 int igb200_framebuffer(igb200_ctx* c, const char* aov, float** host_ptr) {
     if (!c || !host_ptr) return fail(-1, "igb200_framebuffer: null argument");
     if (!is_color(aov)) return fail(-4, "igb200_framebuffer: AOV '%s' does not exist", aov);
+    { const int r = flush_queued(c); if (r) return r; }   // a queued first render creates the framebuffer
     if (!c->fb.p) return fail(-1, "igb200_framebuffer: no framebuffer (call igb200_resize first)");
     CU(cudaSetDevice(c->device));
     { const int r = drain(c); if (r) return r; }
@@ -601,6 +602,7 @@ int igb200_framebuffer(igb200_ctx* c, const char* aov, float** host_ptr) {
 int igb200_framebuffer_device(igb200_ctx* c, const char* aov, float** device_ptr) {
     if (!c || !device_ptr) return fail(-1, "igb200_framebuffer_device: null argument");
     if (!is_color(aov)) return fail(-4, "igb200_framebuffer_device: AOV '%s' does not exist", aov);
+    { const int r = flush_queued(c); if (r) return r; }
     if (!c->fb.p) return fail(-1, "igb200_framebuffer_device: no framebuffer");
     CU(cudaSetDevice(c->device));
     { const int r = drain(c); if (r) return r; }
@@ -612,6 +614,7 @@ int igb200_framebuffer_device(igb200_ctx* c, const char* aov, float** device_ptr
 int igb200_upload_framebuffer(igb200_ctx* c, const char* aov, const float* host_rgb) {
     if (!c || !host_rgb) return fail(-1, "igb200_upload_framebuffer: null argument");
     if (!is_color(aov)) return fail(-4, "igb200_upload_framebuffer: AOV '%s' does not exist", aov);
+    { const int r = flush_queued(c); if (r) return r; }
     if (!c->fb.p) return fail(-1, "igb200_upload_framebuffer: no framebuffer");
     CU(cudaSetDevice(c->device));
     { const int r = drain(c); if (r) return r; }
@@ -786,6 +789,8 @@ int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* ra
         return launch_iterations(c, st, 1, rays, n_rays);
     }
     if (st->width < 1 || st->height < 1) return fail(-1, "igb200_render: invalid size %dx%d", st->width, st->height);
+    // the ray id (y * width + x) * spi + sample is a 32-bit integer in the stream, as in the reference (driver/mapping_cpu.art:351)
+    if ((long long)st->width * st->height * st->spi >= ((long long)1 << 31)) return fail(-1, "igb200_render: %dx%d at %d samples per iteration overflows the 32-bit ray id", st->width, st->height, st->spi);
     // Fused iterations: a launch generates the camera rays of up to F consecutive iterations (same settings, iter + 1 each).
     if (!c->queued.empty()) {
         const igb200_settings& l = c->queued.back();

@@ -280,3 +280,23 @@ def test_odd_sizes_seeds_and_partitions(w, h, spi, seed, world):
             cam += rt.device.getStatistics()["CameraRayCount"]
     assert cam == w * h * spi * 3
     assert rel_l2(acc, ref) <= REL_L2_TOL
+
+
+def test_errors_are_reported_not_rendered():
+    t = load_scene(scene_path("single_triangle.json"))
+    with B200Device() as dev:
+        with pytest.raises(Exception, match="no scene"):
+            dev.render(1, 8, 8, 0)
+        dev.assignScene(t)
+        with pytest.raises(Exception, match="overflows"):
+            dev.render(1 << 20, 4096, 4096, 0)
+        with pytest.raises(Exception, match="spi"):
+            dev.render(0, 8, 8, 0)
+        with pytest.raises(Exception, match="AOV"):
+            dev.getFramebufferForHost("Normals")
+        bad = load_scene(scene_path("single_triangle.json"))
+        bad.materials["bsdf"][0] = 7
+        with pytest.raises(Exception, match="unsupported bsdf"):
+            dev.assignScene(bad)
+        dev.render(1, 8, 8, 0)   # the device is still usable after the errors
+        assert np.isfinite(dev.getFramebufferForHost()).all()
