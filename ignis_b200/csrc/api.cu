@@ -400,7 +400,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     if (d->n_leaves != d->n_entities) return fail(-1, "igb200_set_scene: %d leaves for %d entities (one EntityLeaf1 per entity expected)", d->n_leaves, d->n_entities);
     if (d->shape_data_bytes % 16) return fail(-1, "igb200_set_scene: shapes dyn-table data must be a multiple of 16 bytes");
     for (int m = 0; m < d->n_materials; ++m)
-        if (d->materials[m].bsdf != IGB200_BSDF_DIFFUSE && d->materials[m].bsdf != IGB200_BSDF_DIELECTRIC) return fail(-4, "igb200_set_scene: material %d has unsupported bsdf %d", m, d->materials[m].bsdf);
+        if (d->materials[m].bsdf < IGB200_BSDF_DIFFUSE || d->materials[m].bsdf > IGB200_BSDF_CONDUCTOR) return fail(-4, "igb200_set_scene: material %d has unsupported bsdf %d", m, d->materials[m].bsdf);
     for (int l = 0; l < d->n_infinite; ++l)
         if (d->infinite_lights[l].type != IGB200_LIGHT_ENV_CONST) return fail(-4, "igb200_set_scene: infinite light %d has unsupported type %d", l, d->infinite_lights[l].type);
     for (int l = 0; l < d->n_finite; ++l) {

@@ -170,6 +170,7 @@ struct Val {
     int n = 1;                    // Vec: number of components
     std::string name;             // Sym: the identifier; Ctor: constructor name
     std::vector<Val> args;        // Ctor
+    bool known = true;            // built from literals of the script only (Artic's `?x`: known at specialisation time); registry values are not
     static Val num(float x) { Val v; v.kind = Num; v.f[0] = x; return v; }
     static Val vec(float x, float y, float z) { Val v; v.kind = Vec; v.n = 3; v.f[0] = x; v.f[1] = y; v.f[2] = z; return v; }
     static Val sym(const std::string& s) { Val v; v.kind = Sym; v.name = s; return v; }
@@ -250,8 +251,8 @@ struct Eval {
             return v;
         }
         auto f = [&](float x, float y) { return op == '+' ? x + y : op == '-' ? x - y : op == '*' ? x * y : x / y; };   // f32 arithmetic, as Artic evaluates it
-        if (a.kind == Val::Num && b.kind == Val::Num) return Val::num(f(a.f[0], b.f[0]));
-        Val v; v.kind = Val::Vec; v.n = a.kind == Val::Vec ? a.n : b.n;
+        if (a.kind == Val::Num && b.kind == Val::Num) { Val v = Val::num(f(a.f[0], b.f[0])); v.known = a.known && b.known; return v; }
+        Val v; v.kind = Val::Vec; v.n = a.kind == Val::Vec ? a.n : b.n; v.known = a.known && b.known;
         for (int i = 0; i < v.n; ++i) v.f[i] = f(a.kind == Val::Vec ? a.f[i] : a.f[0], b.kind == Val::Vec ? b.f[i] : b.f[0]);
         return v;
     }
@@ -357,16 +358,18 @@ struct Eval {
             const std::string key = key_arg(fn, a);
             const std::string ty = fn.substr(fn.rfind('_') + 1);
             if (ps) {
-                if (ty == "i32") { const auto it = ps->IntParameters.find(key); if (it != ps->IntParameters.end()) return Val::num((float)it->second); }
-                else if (ty == "f32") { const auto it = ps->FloatParameters.find(key); if (it != ps->FloatParameters.end()) return Val::num(it->second); }
-                else if (ty == "vec3") { const auto it = ps->VectorParameters.find(key); if (it != ps->VectorParameters.end()) return Val::vec(it->second.v[0], it->second.v[1], it->second.v[2]); }
-                else if (ty == "color") { const auto it = ps->ColorParameters.find(key); if (it != ps->ColorParameters.end()) return Val::vec(it->second.v[0], it->second.v[1], it->second.v[2]); }
+                auto dyn = [](Val v) { v.known = false; return v; };
+                if (ty == "i32") { const auto it = ps->IntParameters.find(key); if (it != ps->IntParameters.end()) return dyn(Val::num((float)it->second)); }
+                else if (ty == "f32") { const auto it = ps->FloatParameters.find(key); if (it != ps->FloatParameters.end()) return dyn(Val::num(it->second)); }
+                else if (ty == "vec3") { const auto it = ps->VectorParameters.find(key); if (it != ps->VectorParameters.end()) return dyn(Val::vec(it->second.v[0], it->second.v[1], it->second.v[2])); }
+                else if (ty == "color") { const auto it = ps->ColorParameters.find(key); if (it != ps->ColorParameters.end()) return dyn(Val::vec(it->second.v[0], it->second.v[1], it->second.v[2])); }
                 else fail("unsupported registry type in " + fn);
             }
             if (a.size() < 2) fail(fn + ": default value expected");
-            return a[1];   // not in the registry: the default written in the script, as the reference does
+            Val v = a[1]; v.known = false;   // not in the registry: the default written in the script, as the reference does
+            return v;
         }
-        if (fn == "make_color") return Val::vec(num_arg(fn, a, 0), num_arg(fn, a, 1), num_arg(fn, a, 2));
+        if (fn == "make_color") { Val v = Val::vec(num_arg(fn, a, 0), num_arg(fn, a, 1), num_arg(fn, a, 2)); v.known = a[0].known && a[1].known && a[2].known; return v; }
         if (fn == "make_gray_color") { const float g = num_arg(fn, a, 0); return Val::vec(g, g, g); }
         if (fn == "make_vec3") return Val::vec(num_arg(fn, a, 0), num_arg(fn, a, 1), num_arg(fn, a, 2));
         if (fn == "make_vec2") { Val v = Val::vec(num_arg(fn, a, 0), num_arg(fn, a, 1), 0); v.n = 2; return v; }
@@ -437,6 +440,18 @@ igb200_material resolve_material(const StageDescriptor& hit, const Registries& r
         m.p[0] = as_num(ctor_arg(b, 1), "ext_ior"); m.p[1] = as_num(ctor_arg(b, 2), "int_ior");
         put3(m.p + 2, as_vec(ctor_arg(b, 3), "specular_reflectance"));
         put3(m.p + 5, as_vec(ctor_arg(b, 4), "specular_transmittance"));
+    } else if (b.name == "make_conductor_bsdf") {   // ConductorBSDF.cpp:13-35; bsdf/conductor.art:2-27,131-141
+        const Val& md = ctor_arg(b, 4);
+        if (md.kind != Val::Ctor || md.name != "microfacet::make_delta_distribution") fail("rough conductor BSDFs are not supported by this device");
+        const Val& eta = as_vec(ctor_arg(b, 1), "conductor eta");
+        const Val& kk = as_vec(ctor_arg(b, 2), "conductor k");
+        m.bsdf = IGB200_BSDF_CONDUCTOR;
+        put3(m.p, eta); put3(m.p + 3, kk);
+        put3(m.p + 6, as_vec(ctor_arg(b, 3), "specular_reflectance"));
+        // conductor.art:133-135: `?eta && ?k && is_black_eps(eta, 1e-4) && is_white_eps(k, 1e-4)` -> make_mirror_bsdf
+        bool mirror = eta.known && kk.known;
+        for (int i = 0; i < 3; ++i) mirror = mirror && std::fabs(eta.f[i]) <= 1e-4f && std::fabs(kk.f[i] - 1) <= 1e-4f;
+        m.p[9] = mirror ? 1.0f : 0.0f;
     } else {
         fail("BSDF constructor '" + b.name + "' is not supported by this device");
     }

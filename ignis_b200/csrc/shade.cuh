@@ -94,6 +94,16 @@ __device__ __forceinline__ bool fresnel(float eta, float cos_i, float& cos_t_out
     return true;
 }
 
+// core/fresnel.art:29-36
+__device__ __forceinline__ float conductor_factor(float n, float k, float cos_i) {
+    const float f = n * n + k * k;
+    const float d1 = f * cos_i * cos_i;
+    const float d2 = 2.0f * n * cos_i;
+    const float R_s = safe_div(d1 - d2, d1 + d2);
+    const float R_p = safe_div(f - d2 + cos_i * cos_i, f + d2 + cos_i * cos_i);
+    return clampf((R_s * R_s + R_p * R_p) * 0.5f, 0, 1);
+}
+
 // light/area.art:124-190: spherical rectangle (Urena et al. 2013)
 struct PlaneEm { V3 origin, normal, ex, ey; float area, inv_area, width, height; };
 struct SQ { V3 o, n; float x0, y0, z0, x1, y1, b0, b1, k, s; };
@@ -371,6 +381,15 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
                 V3 ld;
                 sample_cosine_hemisphere(u, v, ld, s_pdf);
                 in_dir = m33_mul(surf.local, ld); s_color = kd; s_eta = 1; is_delta = false;
+            } else if (bsdf == 2) {   // conductor.art:2-27: mirror / smooth conductor; p = eta rgb, k rgb, ks rgb, mirror flag
+                const C3 ks = c3(m2.x, m2.y, m2.z);
+                in_dir = mulf(N, 2 * dot(N, out_dir)) - out_dir;                                                                   // vector.art:124
+                if (m2.w != 0.0f) s_color = ks;
+                else {
+                    const float cos_i = dot(out_dir, N);
+                    s_color = cmul(ks, c3(conductor_factor(m0.z, m1.y, cos_i), conductor_factor(m0.w, m1.z, cos_i), conductor_factor(m1.x, m1.w, cos_i)));
+                }
+                s_eta = 1; s_pdf = 1; is_delta = true;
             } else {          // dielectric.art:18-34
                 const float n1 = m0.z, n2 = m0.w;
                 const C3 ks = c3(m1.x, m1.y, m1.z), kt = c3(m1.w, m2.x, m2.y);

@@ -26,7 +26,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .scene import (BSDF_DIELECTRIC, BSDF_DIFFUSE, LIGHT_ENV_CONST, LIGHT_PLANE_AREA, LIGHT_POINT, LIGHT_SHAPE_AREA, LIGHT_SPHERE_AREA,
+from .scene import (BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_DIFFUSE, LIGHT_ENV_CONST, LIGHT_PLANE_AREA, LIGHT_POINT, LIGHT_SHAPE_AREA, LIGHT_SPHERE_AREA,
                     SHAPE_SPHERE, SceneTables)
 
 STD_LIB_STUB = "// <the Artic standard library (ig_api[], ScriptCompiler.cpp:36-51) precedes every stage>\nfn @make_dummy() = 0;\n\n"
@@ -95,8 +95,8 @@ class _Tree:
         self.header.append(f'  let var_int_{key} = registry::get_local_parameter_i32("{key}", 0);\n')
         return f"var_int_{key}"
 
-    def color(self, cid, prop, rgb) -> str:
-        if self._embed(rgb):
+    def color(self, cid, prop, rgb, zero=True, one=True) -> str:
+        if self._embed(rgb, zero, one):
             return f"make_color({_ts(rgb[0])}, {_ts(rgb[1])}, {_ts(rgb[2])}, 1)"
         key = f"{cid}_{prop}"
         self.local.colors[key] = tuple(float(np.float32(c)) for c in rgb) + (1.0,)
@@ -232,6 +232,12 @@ def _bsdf(t: SceneTables, mat_id: int, tree: _Tree) -> str:
         int_ = tree.number(cid, "int_ior", p[1])
         s = f"  let md_{cid} = @|ctx : ShadingContext| microfacet::make_delta_distribution(ctx.surf.local);\n"
         s += tree.pull_header() + (f"  let bsdf_{cid} : BSDFShader = @|ctx| make_dielectric_bsdf(ctx.surf, {ext}, {int_}, {ks}, {kt}, md_{cid}(ctx), false);\n")
+    elif int(m["bsdf"]) == BSDF_CONDUCTOR:   # ConductorBSDF.cpp:13-35 (eta: ColorOptions::Black, k: ColorOptions::White)
+        ks = tree.color(cid, "specular_reflectance", p[6:9])
+        eta = tree.color(cid, "eta", p[0:3], one=False)    # ColorOptions::Black(): only black is printed into the text
+        kk = tree.color(cid, "k", p[3:6], zero=False)       # ColorOptions::White()
+        s = f"  let md_{cid} = @|ctx : ShadingContext| microfacet::make_delta_distribution(ctx.surf.local);\n"
+        s += tree.pull_header() + f"  let bsdf_{cid} : BSDFShader = @|ctx| make_conductor_bsdf(ctx.surf, {eta}, {kk}, {ks}, md_{cid}(ctx));\n"
     else:
         raise ValueError(int(m["bsdf"]))
     s += "  let medium_interface = no_medium_interface();\n"

@@ -40,6 +40,7 @@ SHAPE_SPHERE = 1
 
 BSDF_DIFFUSE = 0      # make_lambertian_bsdf (bsdf/diffuse.art:2-12)
 BSDF_DIELECTRIC = 1   # make_pure_dielectric_bsdf (bsdf/dielectric.art:15-37)
+BSDF_CONDUCTOR = 2    # make_mirror_bsdf / make_pure_conductor_bsdf (bsdf/conductor.art:2-27,131-141): smooth conductors only
 
 LIGHT_ENV_CONST = 0   # make_environment_light -> ..._function_spherical (light/env.art:75-100,161-164)
 LIGHT_POINT = 1       # make_point_light (light/point.art:1-18)
@@ -584,6 +585,24 @@ def load_scene(path, width: int | None = None, height: int | None = None,
             rec["p"][0], rec["p"][1] = float(ext), float(int_)
             rec["p"][2:5] = _color(bj.get("specular_reflectance"), (1, 1, 1))
             rec["p"][5:8] = _color(bj.get("specular_transmittance"), (1, 1, 1))
+        elif bt in ("mirror", "conductor", "roughconductor"):
+            # ConductorBSDF.cpp:13-35: smooth only (no roughness property -> microfacet::make_delta_distribution)
+            if any(k in bj for k in ("roughness", "alpha", "roughness_u", "roughness_v", "alpha_u", "alpha_v")):
+                raise SceneError("rough conductors are outside the supported path (SURVEY §8f)")
+            conductors = {"none": ((0.0, 0.0, 0.0), (1.0, 1.0, 1.0)), "aluminum": ((1.34560, 0.96521, 0.61722), (7.47460, 6.39950, 5.30310)),
+                          "brass": ((0.44400, 0.52700, 1.09400), (3.69500, 2.76500, 1.82900)), "copper": ((0.27105, 0.67693, 1.31640), (3.60920, 2.62480, 2.29210)),
+                          "gold": ((0.18299, 0.42108, 1.37340), (3.4242, 2.34590, 1.77040)), "iron": ((2.91140, 2.94970, 2.58450), (3.08930, 2.93180, 2.76700)),
+                          "lead": ((1.91000, 1.83000, 1.44000), (3.51000, 3.40000, 3.18000)), "mercury": ((2.07330, 1.55230, 1.06060), (5.33830, 4.65100, 3.86280)),
+                          "platinum": ((2.37570, 2.08470, 1.84530), (4.26550, 3.71530, 3.13650)), "silver": ((0.15943, 0.14512, 0.13547), (3.92910, 3.19000, 2.38080)),
+                          "titanium": ((2.74070, 2.54180, 2.26700), (3.81430, 3.43450, 3.03850))}   # BSDF.cpp:29-42
+            d_eta, d_k = conductors.get(str(bj.get("material", "")).lower(), conductors["none"])
+            eta, kk = _color(bj.get("eta"), d_eta), _color(bj.get("k"), d_k)
+            rec["bsdf"] = BSDF_CONDUCTOR
+            rec["p"][0:3], rec["p"][3:6] = eta, kk
+            rec["p"][6:9] = _color(bj.get("specular_reflectance"), (1, 1, 1))
+            # conductor.art:133-135: the mirror is chosen when eta and k are constants the generator printed into the text, i.e.
+            # (default specialisation, ShadingTree.cpp:868-884) eta black and k white
+            rec["p"][9] = 1.0 if (np.all(np.abs(eta) <= 1.1920929e-07) and np.all(np.abs(kk - 1) <= 1.1920929e-07)) else 0.0
         else:
             raise SceneError(f"bsdf type '{bt}' is outside the supported path (SURVEY §8f)")
 

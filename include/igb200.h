@@ -54,12 +54,14 @@ enum { IGB200_SHAPE_TRIMESH = 0, IGB200_SHAPE_SPHERE = 1 };
 /* ---- descriptors: the arguments of the constructor calls in the reference's generated stage shaders ------- */
 
 enum { IGB200_BSDF_DIFFUSE = 0,    /* make_diffuse_bsdf(surf, 0, kd) -> make_lambertian_bsdf  (bsdf/diffuse.art:2-12,55-61) */
-       IGB200_BSDF_DIELECTRIC = 1  /* make_dielectric_bsdf(..., delta, thin=false) -> make_pure_dielectric_bsdf (bsdf/dielectric.art:15-37) */ };
+       IGB200_BSDF_DIELECTRIC = 1, /* make_dielectric_bsdf(..., delta, thin=false) -> make_pure_dielectric_bsdf (bsdf/dielectric.art:15-37) */
+       IGB200_BSDF_CONDUCTOR = 2   /* make_conductor_bsdf(..., delta) -> make_mirror_bsdf / make_pure_conductor_bsdf (bsdf/conductor.art:2-27,131-141) */ };
 
 typedef struct igb200_material {
     int32_t bsdf;     /* IGB200_BSDF_* */
     int32_t light_id; /* finite-light index if the entity is an area emitter (make_emissive_material), else -1 */
-    float   p[14];    /* DIFFUSE: kd rgb | DIELECTRIC: ext_ior, int_ior, ks rgb, kt rgb */
+    float   p[14];    /* DIFFUSE: kd rgb | DIELECTRIC: ext_ior, int_ior, ks rgb, kt rgb |
+                         CONDUCTOR: eta rgb, k rgb, ks rgb, mirror flag (eta, k were compile-time constants ~ (0, 1)) */
 } igb200_material;
 
 enum { IGB200_LIGHT_ENV_CONST = 0,  /* make_environment_light (constant radiance), light/env.art:75-100,161-164 */

@@ -302,7 +302,7 @@ struct HitRecord { int32_t ent_id, prim_id; float t, u, v; };
 static_assert(sizeof(EntityLeaf) == 96 && sizeof(MaterialDesc) == 64 && sizeof(LightDesc) == 128, "layout");
 
 enum { SHAPE_TRIMESH = 0, SHAPE_SPHERE = 1 };
-enum { BSDF_DIFFUSE = 0, BSDF_DIELECTRIC = 1 };
+enum { BSDF_DIFFUSE = 0, BSDF_DIELECTRIC = 1, BSDF_CONDUCTOR = 2 };
 enum { LIGHT_ENV_CONST = 0, LIGHT_POINT = 1, LIGHT_PLANE_AREA = 2, LIGHT_SHAPE_AREA = 3, LIGHT_SPHERE_AREA = 4 };
 
 // ------------------------------------------------------------------------------------------ own BVH2 (median split)
@@ -637,11 +637,21 @@ inline bool fresnel(float eta, float cos_i, FresnelTerm& out) {
     return true;
 }
 
+// core/fresnel.art:29-36
+inline float conductor_factor(float n, float k, float cos_i) {
+    const float f = n * n + k * k;
+    const float d1 = f * cos_i * cos_i;
+    const float d2 = 2.0f * n * cos_i;
+    const float R_s = safe_div(d1 - d2, d1 + d2);
+    const float R_p = safe_div(f - d2 + cos_i * cos_i, f + d2 + cos_i * cos_i);
+    return clampf((R_s * R_s + R_p * R_p) * 0.5f, 0, 1);
+}
+
 // ------------------------------------------------------------------------------------------ BSDFs
 struct BsdfSample { Vec3 in_dir; float pdf; Color color; float eta; bool is_delta; };
 struct Bsdf {
-    int type; const SurfaceElement* surf; Color kd; float n1, n2; Color ks, kt;
-    bool is_all_delta() const { return type == BSDF_DIELECTRIC; }
+    int type; const SurfaceElement* surf; Color kd; float n1, n2; Color ks, kt; Color c_eta, c_k; bool mirror;
+    bool is_all_delta() const { return type != BSDF_DIFFUSE; }
     // bsdf/diffuse.art:2-12 ; bsdf/dielectric.art:15-37
     Color eval(Vec3 in_dir, Vec3) const { return type == BSDF_DIFFUSE ? cmulf(kd, positive_cos(in_dir, surf->local.c2) * flt_inv_pi) : col(0, 0, 0); }
     float pdf(Vec3 in_dir, Vec3) const { return type == BSDF_DIFFUSE ? positive_cos(in_dir, surf->local.c2) / flt_pi : 0.0f; }
@@ -650,6 +660,17 @@ struct Bsdf {
             const float u = rnd.next_f32(); const float v = rnd.next_f32();
             const DirSample ds = sample_cosine_hemisphere(u, v);
             s = BsdfSample{mat3x3_mul(surf->local, ds.dir), ds.pdf, kd, 1, false};
+            return true;
+        }
+        if (type == BSDF_CONDUCTOR) {
+            // bsdf/conductor.art:2-10 (make_mirror_bsdf) and :14-27 (make_pure_conductor_bsdf); which one is the generator's
+            // partial-evaluation decision (conductor.art:131-141: eta, k known constants ~ (0, 1))
+            const Vec3 nn = surf->local.c2;
+            const Vec3 r = mulf(nn, 2 * dot(nn, out_dir)) - out_dir;   // core/vector.art:124
+            if (mirror) { s = BsdfSample{r, 1, ks, 1, true}; return true; }
+            const float cos_i = dot(out_dir, nn);
+            const Color f = col(conductor_factor(c_eta.r, c_k.r, cos_i), conductor_factor(c_eta.g, c_k.g, cos_i), conductor_factor(c_eta.b, c_k.b, cos_i));
+            s = BsdfSample{r, 1, cmul(ks, f), 1, true};
             return true;
         }
         const float k = surf->is_entering ? n1 / n2 : n2 / n1;
@@ -1082,6 +1103,10 @@ void trace_tile(const Scene& sc, const Settings& st, const StreamRay* list_rays,
                     mat.bsdf.kd = col(md.p[0], md.p[1], md.p[2]);
                     mat.bsdf.n1 = md.p[0]; mat.bsdf.n2 = md.p[1];
                     mat.bsdf.ks = col(md.p[2], md.p[3], md.p[4]); mat.bsdf.kt = col(md.p[5], md.p[6], md.p[7]);
+                    if (md.bsdf == BSDF_CONDUCTOR) {   // p = eta rgb, k rgb, ks rgb, mirror flag
+                        mat.bsdf.c_eta = col(md.p[0], md.p[1], md.p[2]); mat.bsdf.c_k = col(md.p[3], md.p[4], md.p[5]);
+                        mat.bsdf.ks = col(md.p[6], md.p[7], md.p[8]); mat.bsdf.mirror = md.p[9] != 0.0f;
+                    }
                     mat.is_emissive = md.light_id >= 0;
                     mat.light = mat.is_emissive ? &sc.fin_lights[md.light_id] : nullptr;
                     Color hc;

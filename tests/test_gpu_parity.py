@@ -112,7 +112,8 @@ def render_both(tables, w, h, spi, iters, seed=0):
     ("evaluation/multilight-uniform.json", 128, 128, 2, 1),
     ("evaluation/emissive-plane.json", 128, 128, 1, 1),
     ("evaluation/point.json", 64, 64, 1, 1),
-    ("evaluation/sphere-light-pure.json", 128, 128, 2, 2),   # analytic sphere area light (light/area.art:260-316)
+    ("evaluation/sphere-light-pure.json", 128, 128, 2, 2),
+    ("evaluation/two-planes-mirror.json", 128, 128, 4, 2),    # mirror (smooth conductor) + tiny sphere light   # analytic sphere area light (light/area.art:260-316)
     ("synthetic_room.json", 192, 108, 2, 2),             # stand-in for C4: 1.8 M instanced triangles, geometry read through L2
 ])
 def test_radiance_matches_oracle(scene, w, h, spi, iters):
@@ -300,3 +301,13 @@ def test_errors_are_reported_not_rendered():
             dev.assignScene(bad)
         dev.render(1, 8, 8, 0)   # the device is still usable after the errors
         assert np.isfinite(dev.getFramebufferForHost()).all()
+
+
+def test_gold_conductor_matches_oracle():
+    scene = furnace_scene()
+    scene["bsdfs"] = [{"type": "conductor", "name": "glass", "material": "gold"}]
+    scene["lights"].append({"type": "point", "name": "p", "position": [3, -2, 4], "intensity": [20, 20, 20]})
+    t = load_scene(scene)
+    got, ref, stats, cnt = render_both(t, 128, 128, 4, 2)
+    assert rel_l2(got, ref) <= REL_L2_TOL
+    assert (stats["CameraRayCount"], stats["ShadowRayCount"], stats["BounceRayCount"]) == tuple(int(x) for x in cnt)

@@ -19,7 +19,7 @@ from make_golden import IMAGES  # noqa: E402  scene name -> reference file (seve
 # thresholds of scripts/RunEvaluations.py:95-123 (default 1e-3)
 EPS_1024 = {"plane-d1": 1e-3, "plane-d6": 1e-3, "point": 1e-3, "emissive-plane": 1e-3, "cbox-d1": 5e-3, "cbox-d6": 5e-3,
             "multilight-uniform": 3e-4, "sphere-light-pure": 3e-3, "sphere-light-ico": 2e-3, "sphere-light-uv": 2e-3,
-            "sphere-light-ico-nopt": 2e-3, "emissive-plane-nopt": 1e-3, "emissive-plane-scale": 1e-3, "emissive-plane-scale-nopt": 1e-3}
+            "sphere-light-ico-nopt": 2e-3, "emissive-plane-nopt": 1e-3, "emissive-plane-scale": 1e-3, "emissive-plane-scale-nopt": 1e-3, "two-planes-base": 1e-3}
 # a 64 x 32 uv-sphere has ~2 % less area than the sphere the reference image was rendered with
 MEAN_TOL = {"sphere-light-uv": 0.035}
 
@@ -36,7 +36,8 @@ def relmse(img, ref):
 @pytest.mark.parametrize("name,spp", [("plane-d1", 128), ("plane-d6", 128), ("point", 64), ("emissive-plane", 256),
                                       ("cbox-d1", 128), ("cbox-d6", 512), ("multilight-uniform", 512), ("sphere-light-pure", 256),
                                       ("sphere-light-ico", 256), ("sphere-light-uv", 256), ("sphere-light-ico-nopt", 256),
-                                      ("emissive-plane-nopt", 256), ("emissive-plane-scale", 256), ("emissive-plane-scale-nopt", 256)])
+                                      ("emissive-plane-nopt", 256), ("emissive-plane-scale", 256), ("emissive-plane-scale-nopt", 256),
+                                      ("two-planes-base", 256)])
 def test_oracle_matches_reference_image(name, spp):
     refs = np.load(os.path.join(ROOT, "tests", "golden", "ref_images.npz"))
     ref = refs[IMAGES[name][:-4]].astype(np.float32)
@@ -51,4 +52,7 @@ def test_oracle_matches_reference_image(name, spp):
     img = fb / (spp // spi)
     # noise variance scales with 1/spp; a systematic error does not, so the scaled bound still catches a wrong estimator
     assert relmse(img, ref) < EPS_1024[name] * (1024 / spp) * 1.5
-    assert img.mean() == pytest.approx(ref.mean(), rel=MEAN_TOL.get(name, 0.02))
+    # mean over everything but the brightest 0.1 % of the reference (directly visible sub-pixel emitters are filtered differently
+    # by every renderer)
+    keep = ref.mean(axis=2) <= np.percentile(ref.mean(axis=2), 99.9)
+    assert img[keep].mean() == pytest.approx(ref[keep].mean(), rel=MEAN_TOL.get(name, 0.02))

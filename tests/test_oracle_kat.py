@@ -232,6 +232,42 @@ def test_dielectric_reflection_frequency_is_the_fresnel_factor():
     assert hits / 4000 == pytest.approx(F, abs=4 * np.sqrt(F * (1 - F) / 4000))
 
 
+def test_conductor_factor_and_mirror_furnace():
+    """Smooth conductors (bsdf/conductor.art:2-27, core/fresnel.art:29-36): a white mirror box under a white environment
+    converges to 1; a gold box converges to something darker and warm-tinted (R > G > B), never brighter than 1."""
+    from conftest import furnace_scene
+    for bsdf, check in (({"type": "mirror", "name": "glass"}, "one"), ({"type": "conductor", "name": "glass", "material": "gold"}, "gold")):
+        scene = furnace_scene()
+        scene["bsdfs"] = [bsdf]
+        t = load_scene(scene)
+        assert int(t.materials[0]["bsdf"]) == 2 and float(t.materials[0]["p"][9]) == (1.0 if check == "one" else 0.0)
+        o = Oracle(t)
+        fb = np.zeros((96, 96, 3), np.float32)
+        for it in range(4):
+            o.render(96, 96, spi=8, iteration=it, fb=fb)
+        img = fb / 4
+        if check == "one":
+            assert np.abs(img - 1).max() < 1e-5      # a mirror path carries throughput exactly 1 into the environment
+        else:
+            box = img[(img < 0.999).any(axis=2)]
+            assert len(box) > 500 and (box <= 1 + 1e-6).all()
+            # every pixel is the reference's conductor_factor (core/fresnel.art:29-36; note that it squares the amplitude ratios
+            # once more than the textbook formula) at that face's angle of incidence
+            def cf(n, k, c):
+                f = n * n + k * k
+                rs, rp = (f * c * c - 2 * n * c) / (f * c * c + 2 * n * c), (f - 2 * n * c + c * c) / (f + 2 * n * c + c * c)
+                return (rs * rs + rp * rp) / 2
+            cs = np.linspace(0.02, 1, 200)
+            for ch, (n, k) in enumerate(((0.18299, 3.4242), (0.42108, 2.3459), (1.3734, 1.7704))):
+                lo, hi = cf(n, k, cs).min(), cf(n, k, cs).max()
+                m = (img < 0.999).any(axis=2)
+                m[1:-1, 1:-1] &= m[:-2, 1:-1] & m[2:, 1:-1] & m[1:-1, :-2] & m[1:-1, 2:] & m[:-2, :-2] & m[2:, 2:] & m[:-2, 2:] & m[2:, :-2]
+                inner = img[m][:, ch]                                  # pixels whose whole neighbourhood is covered by the box
+                assert len(inner) > 500 and inner.min() >= lo - 1e-3 and inner.max() <= hi + 1e-3
+            r, g, b = box.mean(axis=0)
+            assert r > g > b
+
+
 def test_white_furnace_through_glass():
     """A white, non-absorbing glass cube and sphere-free scene under a constant white environment: whatever a path does --
     reflect, refract, total internal reflection, Russian roulette -- it ends in the environment with throughput 1, so every

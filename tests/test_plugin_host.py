@@ -13,7 +13,8 @@ from ignis_b200.scene import load_scene
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "evaluation/cbox-d6.json", "evaluation/multilight-uniform.json",
-          "evaluation/emissive-plane.json", "evaluation/point.json", "evaluation/plane-d1.json", "evaluation/sphere-light-pure.json"]
+          "evaluation/emissive-plane.json", "evaluation/point.json", "evaluation/plane-d1.json", "evaluation/sphere-light-pure.json",
+          "evaluation/two-planes-mirror.json"]
 
 
 def scene(name):
@@ -40,10 +41,13 @@ def test_recognised_descriptors_equal_loader_descriptors(name, mode):
     for i, h in enumerate(hits):
         m = h.material(g)
         assert int(m["bsdf"]) == int(t.materials[i]["bsdf"]) and int(m["light_id"]) == int(t.materials[i]["light_id"])
+        ref_p = t.materials[i]["p"].copy()
+        if int(m["bsdf"]) == 2 and mode == "disable":
+            ref_p[9] = 0   # eta / k come from the registry, Artic's `?eta` is false: the reference itself takes make_pure_conductor_bsdf then
         if exact:
-            np.testing.assert_array_equal(m["p"].view(np.uint32), t.materials[i]["p"].view(np.uint32))
+            np.testing.assert_array_equal(m["p"].view(np.uint32), ref_p.view(np.uint32))
         else:
-            np.testing.assert_allclose(m["p"], t.materials[i]["p"], atol=1e-6)
+            np.testing.assert_allclose(m["p"], ref_p, atol=1e-6)
     for stage in [plugin.CompiledStage(st.miss)] + hits[:1]:
         inf, fin = stage.lights(g)
         assert len(inf) == len(t.infinite_lights) and len(fin) == len(t.finite_lights)

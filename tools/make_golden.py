@@ -31,13 +31,15 @@ IMAGES = {
     "sphere-light-ico": "ref-sphere-light-4096.exr", "sphere-light-uv": "ref-sphere-light-4096.exr", "sphere-light-ico-nopt": "ref-sphere-light-4096.exr",
     "emissive-plane-nopt": "ref-emissive-plane-4096.exr", "emissive-plane-scale": "ref-emissive-plane-scale-4096.exr",
     "emissive-plane-scale-nopt": "ref-emissive-plane-scale-4096.exr",
+    # Radiance rendering of two diffuse planes lit by a tiny analytic sphere light (radius 0.01, radiance 10^4)
+    "two-planes-base": "ref-two-planes-rad.exr",
 }
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "primitives_data.json", "flipped_prim.json",
           "meshes/Bottom.ply", "meshes/Top.ply", "meshes/Left.ply", "meshes/Right.ply", "meshes/Back.ply", "meshes/Diamond.ply"]
 EVAL = ["plane-base.json", "plane-d1.json", "plane-d6.json", "point.json", "emissive-plane.json", "cbox-base.json", "cbox-d1.json",
         "cbox-d6.json", "multilight.json", "multilight-uniform.json", "flipped-prim-base.json", "flipped-prim-diffuse.json",
         "sphere-light-base.json", "sphere-light-pure.json", "sphere-light-ico.json", "sphere-light-uv.json", "sphere-light-ico-nopt.json",
-        "emissive-plane-nopt.json", "emissive-plane-scale.json", "emissive-plane-scale-nopt.json"]
+        "emissive-plane-nopt.json", "emissive-plane-scale.json", "emissive-plane-scale-nopt.json", "two-planes-base.json", "two-planes-mirror.json"]
 
 
 def main():
