@@ -405,7 +405,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
         if (d->infinite_lights[l].type != IGB200_LIGHT_ENV_CONST) return fail(-4, "igb200_set_scene: infinite light %d has unsupported type %d", l, d->infinite_lights[l].type);
     for (int l = 0; l < d->n_finite; ++l) {
         const int t = d->finite_lights[l].type;
-        if (t != IGB200_LIGHT_POINT && t != IGB200_LIGHT_PLANE_AREA && t != IGB200_LIGHT_SHAPE_AREA && t != IGB200_LIGHT_SPHERE_AREA) return fail(-4, "igb200_set_scene: finite light %d has unsupported type %d", l, t);
+        if (t != IGB200_LIGHT_POINT && t != IGB200_LIGHT_PLANE_AREA && t != IGB200_LIGHT_SHAPE_AREA && t != IGB200_LIGHT_SPHERE_AREA && t != IGB200_LIGHT_SPOT) return fail(-4, "igb200_set_scene: finite light %d has unsupported type %d", l, t);
     }
 
     // ---- per-shape geometry: triangles in BVH leaf order + BVH8 (replaces the reference's pre-baked trimesh_primbvh table)

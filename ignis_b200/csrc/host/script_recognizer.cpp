@@ -379,6 +379,12 @@ struct Eval {
         if (fn == "color_mul") return arith('*', vec_arg(fn, a, 0), vec_arg(fn, a, 1));
         if (fn == "make_constant_texture") return vec_arg(fn, a, 0);   // texture/constant: the colour itself on this path
         if (fn == "maybe_unused") return Val::num(0);
+        if (fn == "rad") { Val v = Val::num(num_arg(fn, a, 0) / 180 * 3.14159265359f); v.known = a[0].known; return v; }   // core/common.art:20
+        if (fn == "spot_from_power") {   // light/spot.art:1-6; the cosines as in resolve_light
+            const float cc = (float)std::cos((double)num_arg(fn, a, 1)), cf = (float)std::cos((double)num_arg(fn, a, 2));
+            const float factor = 2 * 3.14159265359f * (1 - 0.5f * cf - 0.5f * cc);
+            return arith('*', vec_arg(fn, a, 0), Val::num(1 / factor));
+        }
         // a let-bound closure applied to run-time arguments (`bsdf_3(ctx)`, `md_3(ctx)`): its body
         const auto it = st.index.find(fn);
         if (it != st.index.end()) {
@@ -472,6 +478,15 @@ static igb200_light resolve_light(Eval& ev, const std::string& binding) {
         out.type = IGB200_LIGHT_POINT;
         put3(out.p, as_vec(ctor_arg(l, 1), "point light origin"));
         put3(out.p + 3, as_vec(ctor_arg(l, 2), "point light intensity"));
+    } else if (l.name == "make_spot_light") {       // SpotLight.cpp:62-90; light/spot.art:8-44
+        out.type = IGB200_LIGHT_SPOT;
+        put3(out.p, as_vec(ctor_arg(l, 1), "spot light origin"));
+        const Val d = as_vec(ctor_arg(l, 2), "spot light direction");
+        put3(out.p + 3, d);
+        // cos(cutoff), cos(falloff): per-light constants, evaluated in double and rounded once (ignis_b200/scene.py: spot_cosines)
+        out.p[6] = (float)std::cos((double)as_num(ctor_arg(l, 3), "spot cutoff"));
+        out.p[7] = (float)std::cos((double)as_num(ctor_arg(l, 4), "spot falloff"));
+        put3(out.p + 8, as_vec(ctor_arg(l, 5), "spot light intensity"));
     } else if (l.name == "make_area_light") {       // AreaLight.cpp:115-220
         const Val& ae = ctor_arg(l, 1);
         const Val rad = as_vec(ctor_arg(l, 2), "area light radiance");

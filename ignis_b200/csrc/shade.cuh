@@ -201,6 +201,21 @@ __device__ __forceinline__ LightSample light_sample_direct(const DevScene& sc, c
         o.pos = pos; o.dir = mulf(d_, safe_div(1, dist));
         o.intensity = c3(__ldg(L + 5), __ldg(L + 6), __ldg(L + 7));
         o.pdf.value = 1; o.pdf.measure = 1; o.cos = 1; o.dist = dist;
+    } else if (type == 5) {   // light/spot.art:8-44
+        const V3 pos = v3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4)), sdir = v3(__ldg(L + 5), __ldg(L + 6), __ldg(L + 7));
+        const float cos_cutoff = __ldg(L + 8), cos_falloff = __ldg(L + 9);
+        const float blend = cos_falloff - cos_cutoff;
+        const V3 d_ = pos - from.point;
+        const float dist = len(d_);
+        const V3 out_dir = mulf(d_, safe_div(1, dist));
+        const float cos_angle = dot(neg(out_dir), sdir);
+        float factor;
+        if (blend <= IGB_FLT_EPS) factor = cos_angle <= cos_cutoff ? 0.0f : 1.0f;
+        else { const float x = clampf((cos_angle - cos_cutoff) / blend, 0, 1); factor = x * x * (3 - 2 * x); }
+        o.pos = pos; o.dir = out_dir;
+        o.intensity = cmulf(c3(__ldg(L + 10), __ldg(L + 11), __ldg(L + 12)), factor);
+        o.pdf.value = cos_angle > cos_cutoff ? 1.0f : 0.0f; o.pdf.measure = 1;
+        o.cos = -dot(out_dir, sdir); o.dist = dist;
     } else {                  // light/area.art:12-25
         const float u = rnd.next_f32(); const float v = rnd.next_f32();
         V3 to_point, to_normal; float weight; C3 radiance;
@@ -357,7 +372,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
             const float pdf_l_s = pdf_as_solid(ls.pdf, ls.cos, ls.dist * ls.dist) * pdf_lights;
             if (!(pdf_l_s <= IGB_FLT_EPS) && ls.cos > IGB_FLT_EPS) {
                 float mis;
-                if (lt == 1) mis = 1.0f;
+                if (lt == 1 || lt == 5) mis = 1.0f;   // delta lights
                 else { const float pdf_e_s = positive_cos(ls.dir, N) / IGB_FLT_PI; mis = 1 / (1 + pdf_e_s / pdf_l_s); }
                 const float factor = ls.pdf.value / pdf_l_s;
                 const C3 ev = cmulf(kd, positive_cos(ls.dir, N) * IGB_FLT_INV_PI);     // diffuse.art:3

@@ -26,7 +26,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .scene import (BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_DIFFUSE, LIGHT_ENV_CONST, LIGHT_PLANE_AREA, LIGHT_POINT, LIGHT_SHAPE_AREA, LIGHT_SPHERE_AREA,
+from .scene import (BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_DIFFUSE, LIGHT_ENV_CONST, LIGHT_PLANE_AREA, LIGHT_POINT, LIGHT_SHAPE_AREA, LIGHT_SPHERE_AREA, LIGHT_SPOT,
                     SHAPE_SPHERE, SceneTables)
 
 STD_LIB_STUB = "// <the Artic standard library (ig_api[], ScriptCompiler.cpp:36-51) precedes every stage>\nfn @make_dummy() = 0;\n\n"
@@ -179,6 +179,16 @@ def _lights(t: SceneTables, tree: _Tree) -> str:
             ent = tree.integer(cid, f"ae_{cid}_ent_id", int(l["entity_id"]))
             s += tree.pull_header() + f"  let ae_{cid} = make_shape_area_emitter_proxy({ent}, entities, shapes_trimesh);\n"
             s += f"  let light_{cid} = make_area_light({i}, ae_{cid}, @|ctx| {{ maybe_unused(ctx); {rad} }});\n"
+        elif ty == LIGHT_SPOT:   # SpotLight.cpp:62-90
+            cut, fall, use_power, power = t.spot_angles[i]
+            origin = tree.vector(cid, "origin", p[0:3])
+            direction = tree.vector(cid, "direction", p[3:6])
+            c_, f_ = tree.number(cid, "cutoff", cut), tree.number(cid, "falloff", fall)
+            if use_power:
+                last = f"spot_from_power({tree.color(cid, 'power', power)}, rad({c_}), rad({f_}))"
+            else:
+                last = tree.color(cid, "intensity", p[8:11])
+            s += tree.pull_header() + f"  let light_{cid} = make_spot_light({i}, {origin}, {direction}, rad({c_}), rad({f_}), {last});\n"
         elif ty == LIGHT_SPHERE_AREA:   # AreaLight.cpp:166-190: every entity field is a Dynamic (registry) parameter
             pre = f"ae_{cid}"
             rad = tree.color(cid, "radiance", p[0:3])

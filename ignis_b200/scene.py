@@ -47,6 +47,7 @@ LIGHT_POINT = 1       # make_point_light (light/point.art:1-18)
 LIGHT_PLANE_AREA = 2  # make_area_light + make_plane_area_emitter (light/area.art:10-43,124-258)
 LIGHT_SHAPE_AREA = 3  # make_area_light + make_shape_area_emitter (light/area.art:62-107)
 LIGHT_SPHERE_AREA = 4  # make_area_light + make_sphere_area_emitter (light/area.art:260-316)
+LIGHT_SPOT = 5         # make_spot_light (light/spot.art:8-44)
 
 LOOKUP_DTYPE = np.dtype([("type_id", "<u4"), ("flags", "<u4"), ("offset", "<u8")])
 LEAF_DTYPE = np.dtype([("min", "<f4", 3), ("entity_id", "<i4"), ("max", "<f4", 3), ("shape_id", "<i4"),
@@ -83,6 +84,7 @@ class SceneTables:
     film_size: tuple[int, int]
     entity_names: list[str] = field(default_factory=list)
     material_names: list[str] = field(default_factory=list)
+    spot_angles: dict = field(default_factory=dict)   # finite light index -> (cutoff, falloff) in degrees (the descriptors hold the cosines)
 
     @property
     def n_entities(self) -> int:
@@ -97,6 +99,14 @@ class SceneTables:
             if int(lk["type_id"]) == SHAPE_TRIMESH:
                 total += int(np.frombuffer(self.shape_data, "<u4", 1, int(lk["offset"]))[0])
         return total
+
+
+def spot_cosines(cutoff_deg: float, falloff_deg: float):
+    """cos(rad(cutoff)), cos(rad(falloff)) of make_spot_light (light/spot.art:10-11) as f32: rad() in f32, cos in double."""
+    def one(deg):
+        r = F(F(deg) / F(180) * F(3.14159265359))
+        return float(F(math.cos(float(r))))
+    return one(cutoff_deg), one(falloff_deg)
 
 
 def ellipsoid_area(global_linear, radius: float) -> float:
@@ -488,6 +498,7 @@ def load_scene(path, width: int | None = None, height: int | None = None,
 
     # ---- lights (LoaderLight.cpp:263-300: infinite and finite lights have separate id spaces)
     inf_l, fin_l = [], []
+    spot_angles: dict = {}
     fin_of_entity: dict[str, int] = {}
     for lj in lights_json:
         lt = lj.get("type", "").lower()
@@ -506,6 +517,22 @@ def load_scene(path, width: int | None = None, height: int | None = None,
                 rec["p"][3:6] = (_color(lj["power"], (0, 0, 0)) * F(1.0 / (4 * PI))).astype(F)
             else:
                 rec["p"][3:6] = _color(lj.get("intensity"), (1, 1, 1))
+            fin_l.append(rec)
+        elif lt == "spot":
+            # SpotLight.cpp:11-20,62-90: cutoff / falloff in degrees; rad(x) = x / 180 * pi in f32 (core/common.art:20); the two
+            # cosines are per-light constants, evaluated here (double, rounded once) exactly as the C++ recogniser does
+            cut, fall = spot_cosines(float(lj.get("cutoff", 30.0)), float(lj.get("falloff", 20.0)))
+            d = _vec3(lj.get("direction"), (0, 0, 1)).astype(np.float64)
+            rec["type"] = LIGHT_SPOT
+            rec["p"][0:3] = _vec3(lj.get("position"), (0, 0, 0))
+            rec["p"][3:6] = (d / np.linalg.norm(d)).astype(F)
+            rec["p"][6], rec["p"][7] = cut, fall
+            if "power" in lj:   # spot_from_power, light/spot.art:1-6
+                factor = F(F(2) * F(3.14159265359) * (F(1) - F(0.5) * F(fall) - F(0.5) * F(cut)))
+                rec["p"][8:11] = (_color(lj["power"], (0, 0, 0)) * (F(1) / factor)).astype(F)
+            else:
+                rec["p"][8:11] = _color(lj.get("intensity"), (1, 1, 1))
+            spot_angles[len(fin_l)] = (float(lj.get("cutoff", 30.0)), float(lj.get("falloff", 20.0)), "power" in lj, _color(lj["power"], (0, 0, 0)) if "power" in lj else None)
             fin_l.append(rec)
         elif lt == "area":
             ename = lj.get("entity", "")
@@ -661,4 +688,4 @@ def load_scene(path, width: int | None = None, height: int | None = None,
         entity_per_material=np.asarray([len(g) for g in groups], np.int32), materials=materials,
         infinite_lights=_arr(inf_l), finite_lights=_arr(fin_l), camera=cam, technique=technique,
         bbox_min=bb_lo.astype(F), bbox_max=bb_hi.astype(F), film_size=(fw, fh),
-        entity_names=names, material_names=[f"{b}{'@' + e if e else ''}" for b, e in mat_keys])
+        entity_names=names, material_names=[f"{b}{'@' + e if e else ''}" for b, e in mat_keys], spot_angles=spot_angles)

@@ -68,7 +68,8 @@ enum { IGB200_LIGHT_ENV_CONST = 0,  /* make_environment_light (constant radiance
        IGB200_LIGHT_POINT = 1,      /* make_point_light, light/point.art:1-18 */
        IGB200_LIGHT_PLANE_AREA = 2, /* make_area_light(make_plane_area_emitter), light/area.art:10-43,124-258 */
        IGB200_LIGHT_SHAPE_AREA = 3, /* make_area_light(make_shape_area_emitter), light/area.art:62-107 */
-       IGB200_LIGHT_SPHERE_AREA = 4 /* make_area_light(make_sphere_area_emitter), light/area.art:260-316 */ };
+       IGB200_LIGHT_SPHERE_AREA = 4, /* make_area_light(make_sphere_area_emitter), light/area.art:260-316 */
+       IGB200_LIGHT_SPOT = 5        /* make_spot_light, light/spot.art:8-44 */ };
 
 typedef struct igb200_light {
     int32_t type;      /* IGB200_LIGHT_* */
@@ -76,6 +77,7 @@ typedef struct igb200_light {
     float   p[30];     /* ENV_CONST: radiance rgb | POINT: position xyz, intensity rgb |
                           PLANE_AREA: origin, x_axis, y_axis, normal (3 each), area, t0..t3 (2 each), radiance rgb |
                           SHAPE_AREA: radiance rgb |
+                          SPOT: position xyz, direction xyz, cos(cutoff), cos(falloff), intensity rgb |
                           SPHERE_AREA: radiance rgb, sphere origin xyz (local), radius, area (compute_ellipsoid_area, shapes/sphere.art:21-27) */
 } igb200_light;
 

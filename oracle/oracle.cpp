@@ -303,7 +303,7 @@ static_assert(sizeof(EntityLeaf) == 96 && sizeof(MaterialDesc) == 64 && sizeof(L
 
 enum { SHAPE_TRIMESH = 0, SHAPE_SPHERE = 1 };
 enum { BSDF_DIFFUSE = 0, BSDF_DIELECTRIC = 1, BSDF_CONDUCTOR = 2 };
-enum { LIGHT_ENV_CONST = 0, LIGHT_POINT = 1, LIGHT_PLANE_AREA = 2, LIGHT_SHAPE_AREA = 3, LIGHT_SPHERE_AREA = 4 };
+enum { LIGHT_ENV_CONST = 0, LIGHT_POINT = 1, LIGHT_PLANE_AREA = 2, LIGHT_SHAPE_AREA = 3, LIGHT_SPHERE_AREA = 4, LIGHT_SPOT = 5 };
 
 // ------------------------------------------------------------------------------------------ own BVH2 (median split)
 struct Bvh2 {
@@ -807,7 +807,7 @@ inline void sphere_emitter_sample(const Scene& sc, const LightDesc& l, Vec2 uv, 
 
 struct LightRef { const LightDesc* d; bool infinite; int id; };
 
-inline bool light_delta(const LightDesc& l) { return l.type == LIGHT_POINT; }
+inline bool light_delta(const LightDesc& l) { return l.type == LIGHT_POINT || l.type == LIGHT_SPOT; }
 inline bool light_infinite(const LightDesc& l) { return l.type == LIGHT_ENV_CONST; }
 
 inline DirectLightSample light_sample_direct(const Scene& sc, const LightDesc& l, Rng& rnd, const SurfaceElement& from) {
@@ -826,6 +826,21 @@ inline DirectLightSample light_sample_direct(const Scene& sc, const LightDesc& l
         const float dist = len(dir_);
         const Vec3 dir = mulf(dir_, safe_div(1, dist));
         return DirectLightSample{pos, dir, col(l.p[3], l.p[4], l.p[5]), Pdf{1, PDF_AREA}, 1, dist};
+    }
+    case LIGHT_SPOT: {  // light/spot.art:8-44; p = pos, dir, cos(cutoff), cos(falloff), intensity (the cosines are host constants)
+        const Vec3 pos = v3(l.p[0], l.p[1], l.p[2]), sdir = v3(l.p[3], l.p[4], l.p[5]);
+        const float cos_cutoff = l.p[6], cos_falloff = l.p[7];
+        const float blend = cos_falloff - cos_cutoff;
+        const Vec3 out_dir_ = pos - from.point;
+        const float dist = len(out_dir_);
+        const Vec3 out_dir = mulf(out_dir_, safe_div(1, dist));
+        const float cos_angle = dot(neg(out_dir), sdir);
+        float factor;
+        if (blend <= flt_eps) factor = cos_angle <= cos_cutoff ? 0.0f : 1.0f;
+        else { const float x = clampf((cos_angle - cos_cutoff) / blend, 0, 1); factor = x * x * (3 - 2 * x); }   // core/common.art:241
+        const float cos = -dot(out_dir, sdir);
+        const float area_pdf = dot(neg(out_dir), sdir) > cos_cutoff ? 1.0f : 0.0f;
+        return DirectLightSample{pos, out_dir, cmulf(col(l.p[8], l.p[9], l.p[10]), factor), Pdf{area_pdf, PDF_AREA}, cos, dist};
     }
     default: {  // light/area.art:12-25
         const float u = rnd.next_f32(); const float v = rnd.next_f32();

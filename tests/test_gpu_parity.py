@@ -150,6 +150,9 @@ def test_analytic_scene_averages_on_gpu():
     s["lights"].append({"type": "point", "name": "_light", "position": [0, 0, -2], "power": 1})
     assert avg(s) == pytest.approx(0.005100456, abs=1e-4)
     s = flat_scene()
+    s["lights"].append({"type": "spot", "name": "_light", "cutoff": 45, "falloff": 45, "position": [0, 0, -2], "direction": [0, 0, 1], "power": 1})
+    assert avg(s) == pytest.approx(0.0348280902, abs=2.5e-3)
+    s = flat_scene()
     s["lights"].append({"type": "env", "name": "_light", "radiance": [1, 1, 1]})
     assert avg(s) == pytest.approx(1, rel=1e-4)
     assert avg({}) == 0.0                                     # test_init.py:9-12
@@ -309,5 +312,16 @@ def test_gold_conductor_matches_oracle():
     scene["lights"].append({"type": "point", "name": "p", "position": [3, -2, 4], "intensity": [20, 20, 20]})
     t = load_scene(scene)
     got, ref, stats, cnt = render_both(t, 128, 128, 4, 2)
+    assert rel_l2(got, ref) <= REL_L2_TOL
+    assert (stats["CameraRayCount"], stats["ShadowRayCount"], stats["BounceRayCount"]) == tuple(int(x) for x in cnt)
+
+
+def test_spot_lights_match_oracle():
+    s = flat_scene()
+    s["lights"].append({"type": "spot", "name": "a", "cutoff": 45, "falloff": 30, "position": [0, 0, -2], "direction": [0.1, 0, 1], "power": [1, 2, 3]})
+    s["lights"].append({"type": "spot", "name": "b", "cutoff": 20, "falloff": 20, "position": [0.5, 0, -2], "direction": [0, 0, 1], "intensity": [1, 1, 1]})
+    s["lights"].append({"type": "point", "name": "c", "position": [-0.5, 0.3, -1], "intensity": [0.2, 0.2, 0.2]})
+    t = load_scene(s)
+    got, ref, stats, cnt = render_both(t, 200, 200, 2, 2)
     assert rel_l2(got, ref) <= REL_L2_TOL
     assert (stats["CameraRayCount"], stats["ShadowRayCount"], stats["BounceRayCount"]) == tuple(int(x) for x in cnt)

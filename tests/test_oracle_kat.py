@@ -119,6 +119,13 @@ def test_point_light_scene_average():
     assert scene_average(s)[0] == pytest.approx(0.005100456, abs=1e-4)
 
 
+def test_spot_light_scene_average():
+    # src/tests/integrator/test_lights.py:25-37: 0.005100456 * 4 pi / (2 pi (1 - cos 45 deg)) = 0.0348280902, abs 2.5e-3
+    s = flat_scene()
+    s["lights"].append({"type": "spot", "name": "_light", "cutoff": 45, "falloff": 45, "position": [0, 0, -2], "direction": [0, 0, 1], "power": 1})
+    assert scene_average(s)[0] == pytest.approx(0.0348280902, abs=2.5e-3)
+
+
 def test_env_light_scene_average():
     s = flat_scene()
     s["lights"].append({"type": "env", "name": "_light", "radiance": [1, 1, 1]})

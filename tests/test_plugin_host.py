@@ -14,10 +14,16 @@ from ignis_b200.scene import load_scene
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "evaluation/cbox-d6.json", "evaluation/multilight-uniform.json",
           "evaluation/emissive-plane.json", "evaluation/point.json", "evaluation/plane-d1.json", "evaluation/sphere-light-pure.json",
-          "evaluation/two-planes-mirror.json"]
+          "evaluation/two-planes-mirror.json", "<spot>"]
 
 
 def scene(name):
+    if name == "<spot>":   # the spot-light scene of the reference's integrator tests (src/tests/integrator/test_lights.py:25-37)
+        from conftest import flat_scene
+        s = flat_scene()
+        s["lights"].append({"type": "spot", "name": "_light", "cutoff": 45, "falloff": 30, "position": [0, 0, -2], "direction": [0.1, 0, 1], "power": [1, 2, 3]})
+        s["lights"].append({"type": "spot", "name": "_light2", "cutoff": 20, "falloff": 20, "position": [0.5, 0, -2], "direction": [0, 0, 1], "intensity": [1, 1, 1]})
+        return load_scene(s)
     return load_scene(os.path.join(ROOT, "scenes", name))
 
 
