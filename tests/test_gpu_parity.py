@@ -113,7 +113,8 @@ def render_both(tables, w, h, spi, iters, seed=0):
     ("evaluation/emissive-plane.json", 128, 128, 1, 1),
     ("evaluation/point.json", 64, 64, 1, 1),
     ("evaluation/sphere-light-pure.json", 128, 128, 2, 2),
-    ("evaluation/two-planes-mirror.json", 128, 128, 4, 2),    # mirror (smooth conductor) + tiny sphere light   # analytic sphere area light (light/area.art:260-316)
+    ("evaluation/two-planes-mirror.json", 128, 128, 4, 2),
+    ("evaluation/room.json", 128, 128, 4, 1),                 # OBJ mesh, constant light    # mirror (smooth conductor) + tiny sphere light   # analytic sphere area light (light/area.art:260-316)
     ("synthetic_room.json", 192, 108, 2, 2),             # stand-in for C4: 1.8 M instanced triangles, geometry read through L2
 ])
 def test_radiance_matches_oracle(scene, w, h, spi, iters):

@@ -33,13 +33,17 @@ IMAGES = {
     "emissive-plane-scale-nopt": "ref-emissive-plane-scale-4096.exr",
     # Radiance rendering of two diffuse planes lit by a tiny analytic sphere light (radius 0.01, radiance 10^4)
     "two-planes-base": "ref-two-planes-rad.exr",
+    # OBJ room under a constant light. (Not used: ref-flipped-prim-diffuse-4096.exr -- a convex Lambertian cylinder of albedo 0.8
+    # under a uniform environment of radiance 0.8 has radiance 0.64 wherever only the environment lights it; the oracle gives 0.635,
+    # that image 0.496 = 0.8 * 0.8^2.2, i.e. it was rendered with the albedo taken as an sRGB value.)
+    "room": "ref-room-4096.exr",
 }
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "primitives_data.json", "flipped_prim.json",
-          "meshes/Bottom.ply", "meshes/Top.ply", "meshes/Left.ply", "meshes/Right.ply", "meshes/Back.ply", "meshes/Diamond.ply"]
+          "meshes/Room.obj", "meshes/Bottom.ply", "meshes/Top.ply", "meshes/Left.ply", "meshes/Right.ply", "meshes/Back.ply", "meshes/Diamond.ply"]
 EVAL = ["plane-base.json", "plane-d1.json", "plane-d6.json", "point.json", "emissive-plane.json", "cbox-base.json", "cbox-d1.json",
         "cbox-d6.json", "multilight.json", "multilight-uniform.json", "flipped-prim-base.json", "flipped-prim-diffuse.json",
         "sphere-light-base.json", "sphere-light-pure.json", "sphere-light-ico.json", "sphere-light-uv.json", "sphere-light-ico-nopt.json",
-        "emissive-plane-nopt.json", "emissive-plane-scale.json", "emissive-plane-scale-nopt.json", "two-planes-base.json", "two-planes-mirror.json"]
+        "emissive-plane-nopt.json", "emissive-plane-scale.json", "emissive-plane-scale-nopt.json", "two-planes-base.json", "two-planes-mirror.json", "room.json"]
 
 
 def main():
