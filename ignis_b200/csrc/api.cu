@@ -100,6 +100,10 @@ struct igb200_ctx {
     int width = 0, height = 0;
     DevBuf<float> fb;
     float* host_fb = nullptr; size_t host_fb_n = 0;
+    // standard AOVs of the reference's infobuffer wrapper (technique/internal/infobuffer.art): [0] Normals, [1] Albedo; option "std_aovs"
+    bool std_aovs = false;
+    DevBuf<float> aov[2];
+    float* host_aov[2] = {nullptr, nullptr};
     // queues
     size_t capacity = 0, want_capacity = (size_t)1 << 25;   // upper bound of records per queue (84 B each, two queues + 48 B shadow)
     QueueMem qa, qb;
@@ -234,6 +238,18 @@ static int launch_wave(igb200_ctx* c, const RenderParams& rp, const DevScene& sc
 // Finishes the paths earlier launches left behind (deferred tail): one more launch without camera rays that runs every
 // path to its end. Everything that observes results (framebuffer, statistics) or changes what carried records refer to
 // (scene, size, partition, spi) calls this first.
+static int ensure_aovs(igb200_ctx* c) {
+    if (!c->std_aovs || !c->fb.n) return 0;
+    for (int k = 0; k < 2; ++k) {
+        if (c->aov[k].n == c->fb.n) continue;
+        CU(c->aov[k].alloc(c->fb.n));
+        CU(cudaMemset(c->aov[k].p, 0, c->fb.n * sizeof(float)));
+        if (c->host_aov[k]) { cudaFreeHost(c->host_aov[k]); c->host_aov[k] = nullptr; }
+        CU(cudaMallocHost(&c->host_aov[k], c->fb.n * sizeof(float)));
+    }
+    return 0;
+}
+
 // `turns` wavefront turns as ordinary launches (shade + generate, trace, hand-over), see wavefront.cuh
 static int launch_split_turns(igb200_ctx* c, const WaveParams& P, int turns) {
     if (turns <= 0) return 0;
@@ -338,6 +354,7 @@ int igb200_destroy(igb200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->host_fb) cudaFreeHost(c->host_fb);
+    for (int k = 0; k < 2; ++k) if (c->host_aov[k]) cudaFreeHost(c->host_aov[k]);
     if (c->host_control) cudaFreeHost(c->host_control);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -354,6 +371,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 8000) return fail(-1, "defer_permille must be in [0, 8000]"); c->defer_permille = (int)value; return 0; }
     if (!strcmp(name, "profile_kernels")) { c->profile = value != 0; return 0; }
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
+    if (!strcmp(name, "std_aovs")) { c->std_aovs = value != 0; CU(cudaSetDevice(c->device)); return ensure_aovs(c); }
     if (!strcmp(name, "fuse")) { if (value < 0 || value > 64) return fail(-1, "fuse must be in [0, 64]"); c->fuse = (int)value; return 0; }
     if (!strcmp(name, "split_turns")) { if (value < -1 || value > 64) return fail(-1, "split_turns must be in [-1, 64] (-1: chosen from the number of camera rays)"); c->split_turns = (int)value; return 0; }
     if (!strcmp(name, "turn_shade_blocks")) {
@@ -570,55 +588,75 @@ int igb200_resize(igb200_ctx* c, int width, int height) {
     if (c->host_fb) { cudaFreeHost(c->host_fb); c->host_fb = nullptr; }
     CU(cudaMallocHost(&c->host_fb, n * sizeof(float)));
     c->host_fb_n = n;
+    for (int k = 0; k < 2; ++k) {
+        c->aov[k].release();
+        if (c->host_aov[k]) { cudaFreeHost(c->host_aov[k]); c->host_aov[k] = nullptr; }
+    }
+    { const int r = ensure_aovs(c); if (r) return r; }
     return 0;
 }
 
 static bool is_color(const char* aov) { return !aov || !*aov || !strcmp(aov, "Color"); }
+// 0: colour, 1: Normals, 2: Albedo (when "std_aovs" is on), -1: no such AOV
+static int aov_index(const igb200_ctx* c, const char* aov) {
+    if (is_color(aov)) return 0;
+    if (c->std_aovs && !strcmp(aov, "Normals")) return 1;
+    if (c->std_aovs && !strcmp(aov, "Albedo")) return 2;
+    return -1;
+}
 
 int igb200_clear(igb200_ctx* c, const char* aov) {
     if (!c) return fail(-1, "null context");
-    if (!is_color(aov)) return fail(-4, "igb200_clear: AOV '%s' does not exist (only the colour framebuffer is supported)", aov);
+    const int which = aov ? aov_index(c, aov) : 0;   // NULL: clearAllFramebuffer
+    if (which < 0) return fail(-4, "igb200_clear: AOV '%s' does not exist", aov);
     CU(cudaSetDevice(c->device));
     // paths still in flight belong to the image that is being thrown away: finish them first, then clear
     { const int r = drain(c); if (r) return r; }
-    if (c->fb.p) CU(cudaMemsetAsync(c->fb.p, 0, c->fb.n * sizeof(float), c->stream));
+    if (c->fb.p && (!aov || which == 0)) CU(cudaMemsetAsync(c->fb.p, 0, c->fb.n * sizeof(float), c->stream));
+    for (int k = 0; k < 2; ++k) if (c->aov[k].p && (!aov || which == k + 1)) CU(cudaMemsetAsync(c->aov[k].p, 0, c->aov[k].n * sizeof(float), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 int igb200_framebuffer(igb200_ctx* c, const char* aov, float** host_ptr) {
     if (!c || !host_ptr) return fail(-1, "igb200_framebuffer: null argument");
-    if (!is_color(aov)) return fail(-4, "igb200_framebuffer: AOV '%s' does not exist", aov);
+    const int which = aov_index(c, aov);
+    if (which < 0) return fail(-4, "igb200_framebuffer: AOV '%s' does not exist", aov);
     { const int r = flush_queued(c); if (r) return r; }   // a queued first render creates the framebuffer
     if (!c->fb.p) return fail(-1, "igb200_framebuffer: no framebuffer (call igb200_resize first)");
     CU(cudaSetDevice(c->device));
     { const int r = drain(c); if (r) return r; }
-    CU(cudaMemcpyAsync(c->host_fb, c->fb.p, c->fb.n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    float* dst = which == 0 ? c->host_fb : c->host_aov[which - 1];
+    const float* src = which == 0 ? c->fb.p : c->aov[which - 1].p;
+    if (!src || !dst) return fail(-1, "igb200_framebuffer: AOV '%s' is not allocated", aov);
+    CU(cudaMemcpyAsync(dst, src, c->fb.n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    *host_ptr = c->host_fb;
+    *host_ptr = dst;
     return 0;
 }
 
 int igb200_framebuffer_device(igb200_ctx* c, const char* aov, float** device_ptr) {
     if (!c || !device_ptr) return fail(-1, "igb200_framebuffer_device: null argument");
-    if (!is_color(aov)) return fail(-4, "igb200_framebuffer_device: AOV '%s' does not exist", aov);
+    const int which = aov_index(c, aov);
+    if (which < 0) return fail(-4, "igb200_framebuffer_device: AOV '%s' does not exist", aov);
     { const int r = flush_queued(c); if (r) return r; }
     if (!c->fb.p) return fail(-1, "igb200_framebuffer_device: no framebuffer");
     CU(cudaSetDevice(c->device));
     { const int r = drain(c); if (r) return r; }
     CU(cudaStreamSynchronize(c->stream));
-    *device_ptr = c->fb.p;
+    *device_ptr = which == 0 ? c->fb.p : c->aov[which - 1].p;
     return 0;
 }
 
 int igb200_upload_framebuffer(igb200_ctx* c, const char* aov, const float* host_rgb) {
     if (!c || !host_rgb) return fail(-1, "igb200_upload_framebuffer: null argument");
-    if (!is_color(aov)) return fail(-4, "igb200_upload_framebuffer: AOV '%s' does not exist", aov);
+    const int which = aov_index(c, aov);
+    if (which < 0) return fail(-4, "igb200_upload_framebuffer: AOV '%s' does not exist", aov);
     { const int r = flush_queued(c); if (r) return r; }
     if (!c->fb.p) return fail(-1, "igb200_upload_framebuffer: no framebuffer");
     CU(cudaSetDevice(c->device));
     { const int r = drain(c); if (r) return r; }
-    CU(cudaMemcpyAsync(c->fb.p, host_rgb, c->fb.n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(which == 0 ? c->fb.p : c->aov[which - 1].p, host_rgb, c->fb.n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -712,6 +750,8 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
     RenderParams rp;
     rp.spi = st->spi; rp.iter = st->iter; rp.frame = st->frame; rp.seed = st->seed; rp.width = W; rp.height = H;
     rp.inv_spi = 1 / (float)st->spi;
+    { const int r = ensure_aovs(c); if (r) return r; }
+    rp.aov_normals = (c->std_aovs && !rays) ? c->aov[0].p : nullptr; rp.aov_albedo = (c->std_aovs && !rays) ? c->aov[1].p : nullptr;
     if (rays) { rp.tile_w = W; rp.tile_h = 1; rp.rank = 0; rp.world = 1; }
     else { rp.tile_w = c->tile; rp.tile_h = c->tile; rp.rank = c->rank; rp.world = c->world; }
     rp.tiles_x = (W + rp.tile_w - 1) / rp.tile_w;

@@ -82,6 +82,11 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
         const StageDescriptor* miss = static_cast<const StageDescriptor*>(set.MissShader.Exec);
         if (miss && miss->has_lights) { light_stage = miss; light_local = set.MissShader.LocalRegistry.get(); }
         if (!light_stage) throw RecognizeError{"no stage carries the light tables"};
+        // Normals / Albedo AOVs requested by the wrapped technique (runtime flag --no-std-aovs removes the wrapper)
+        if ((int)light_stage->std_aovs != mStdAovs) {   // only on a change: setting an option synchronises the device
+            if (igb200_set_option(mCtx, "std_aovs", light_stage->std_aovs ? 1 : 0) != 0) throw RecognizeError{igb200_last_error()};
+            mStdAovs = (int)light_stage->std_aovs;
+        }
         resolve_lights(*light_stage, Registries{light_local, global}, inf, fin);
         technique = resolve_technique(*light_stage, Registries{light_local, global});
         const StageDescriptor* rg = static_cast<const StageDescriptor*>(set.RayGenerationShader.Exec);

@@ -73,6 +73,7 @@ private:
     igb200_ctx* mCtx = nullptr;
     size_t mWidth = 0, mHeight = 0;
     bool mSceneDirty = true;
+    int mStdAovs = -1;                       // Normals / Albedo AOVs currently enabled on the device (-1: not set yet)
     std::vector<uint8_t> mDescriptorBytes;   // materials + lights + camera + technique of the scene on the device
     std::vector<float> mHostFramebuffer;     // what getFramebufferForHost handed out, for syncFramebufferHostToDevice
     float* mHostPtr = nullptr;

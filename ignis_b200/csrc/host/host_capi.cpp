@@ -121,7 +121,11 @@ int igbh_device_render(IRenderDevice* d, ShaderSet* s, ParameterSet* global, int
     return 0;
 }
 void igbh_device_resize(IRenderDevice* d, int w, int h) { d->resize((size_t)w, (size_t)h); }
-float* igbh_device_framebuffer(IRenderDevice* d, const char* name) { return d->getFramebufferForHost(name ? name : "").Data; }
+float* igbh_device_framebuffer(IRenderDevice* d, const char* name) {
+    float* p = d->getFramebufferForHost(name ? name : "").Data;
+    if (!p) igbh::set_last_error(static_cast<igbh::B200Device*>(d)->lastError());
+    return p;
+}
 void igbh_device_clear(IRenderDevice* d) { d->clearAllFramebuffer(); }
 int igbh_device_stats(IRenderDevice* d, uint64_t out[3]) {
     const Statistics* s = d->getStatistics();

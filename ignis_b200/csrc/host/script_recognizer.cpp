@@ -138,6 +138,7 @@ StageDescriptor* parse_stage(const std::string& script, const std::string& funct
     if (has("infinite_lights")) { d->infinite_lights = light_table(expr("infinite_lights"), "infinite_lights"); d->has_lights = true; }
     if (has("finite_lights")) d->finite_lights = light_table(expr("finite_lights"), "finite_lights");
     d->has_technique = has("technique");
+    d->std_aovs = has("full_technique") && expr("full_technique").find("wrap_infobuffer_renderer") != std::string::npos;
     d->has_camera = has("camera");
     if (has("emitter")) d->list_emitter = expr("emitter").rfind("make_list_emitter", 0) == 0;   // RayGenerationShader.cpp:59-60
     if (d->kind == StageKind::Hit) {

@@ -39,6 +39,7 @@ struct StageDescriptor {
     std::vector<std::string> infinite_lights;  // hit / miss: `light_<id>` bindings in table order
     std::vector<std::string> finite_lights;
     bool has_lights = false, has_technique = false, has_camera = false, list_emitter = false;
+    bool std_aovs = false;                     // the technique is wrapped: wrap_infobuffer_renderer (Normals / Albedo AOVs, InfoBufferTechnique.cpp:13-17)
 };
 
 // Thrown by the evaluator; caught at the API boundary and turned into a null handle / false + last_error().

@@ -335,6 +335,16 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
         const V3 N = surf.local.c2;
         Rng rnd; rnd.seed = random_seed(sample, iter, rp.frame, pixel % rp.width, pixel / rp.width, rp.seed); rnd.counter = st.y;
 
+        // ---- wrap_infobuffer_renderer, technique/internal/infobuffer.art:9-24: Normals / Albedo of the first hit, iteration 0 only
+        if (rp.aov_normals && depth == 1 && iter == 0) {
+            C3 albedo;
+            if (bsdf == 0) albedo = c3(m0.z, m0.w, m1.x);                                                       // diffuse.art:10 (kd)
+            else if (bsdf == 1) albedo = c3(lerp1(m1.x, m1.w, 0.5f), lerp1(m1.y, m2.x, 0.5f), lerp1(m1.z, m2.y, 0.5f));   // dielectric.art:35 color_lerp(ks, kt, 0.5)
+            else if (m2.w != 0.0f) albedo = c3(m2.x, m2.y, m2.z);                                               // conductor.art:9 (ks)
+            else { const float ci = dot(neg(rdir), N); albedo = cmul(c3(m2.x, m2.y, m2.z), c3(conductor_factor(m0.z, m1.y, ci), conductor_factor(m0.w, m1.z, ci), conductor_factor(m1.x, m1.w, ci))); }   // conductor.art:28-38
+            splat(rp.aov_normals, pixel, c3(N.x, N.y, N.z), rp.inv_spi);
+            splat(rp.aov_albedo, pixel, c3(fminf(albedo.r, 1.0f), fminf(albedo.g, 1.0f), fminf(albedo.b, 1.0f)), rp.inv_spi);   // color_saturate(albedo, 1)
+        }
         // ---- on_hit, pathtracer.art:119-139
         if (light_id >= 0 && surf.is_entering) {
             const float dt = -dot(rdir, N);

@@ -140,10 +140,10 @@ class PluginRuntime:
     """What IG::Runtime does with a device plugin (Runtime.cpp:81-142,334-446,532-668), through the C++ classes."""
 
     def __init__(self, tables: SceneTables, width: int, height: int, spi: int, seed: int = 0, cuda_device: int = 0,
-                 specialization: str = "default", tracer: bool = False):
+                 specialization: str = "default", tracer: bool = False, std_aovs: bool = True):
         L = lib()
         self.tables, self.width, self.height, self.spi, self.seed = tables, int(width), int(height), int(spi), seed
-        self.stages = refscript.generate(tables, specialization=specialization, tracer=tracer)
+        self.stages = refscript.generate(tables, specialization=specialization, tracer=tracer, std_aovs=std_aovs)
         # compileShaders (Runtime.cpp:596-668)
         self.global_params = Params(self.stages.global_registry)
         self.raygen = CompiledStage(self.stages.raygen)
@@ -190,8 +190,8 @@ class PluginRuntime:
         p = lib().igbh_device_framebuffer(self.dev, b"")
         return np.ctypeslib.as_array(p, shape=(len(rays), 3)).copy()
 
-    def getFramebufferForHost(self) -> np.ndarray:
-        p = lib().igbh_device_framebuffer(self.dev, b"")
+    def getFramebufferForHost(self, name: str = "") -> np.ndarray:
+        p = lib().igbh_device_framebuffer(self.dev, name.encode())
         if not p:
             raise DeviceError(_err())
         return np.ctypeslib.as_array(p, shape=(self.height, self.width, 3))

@@ -166,7 +166,8 @@ int igb200_render(igb200_ctx* ctx, const igb200_settings* settings, const igb200
 int igb200_sync(igb200_ctx* ctx);
 
 /* IRenderDevice::getFramebufferForHost, Device.cpp:1419-1451: copies the device framebuffer into a context-owned
- * pinned host buffer (RGB f32, width*height*3, row-major, sum over iterations). aov NULL/""/"Color" = main image. */
+ * pinned host buffer (RGB f32, width*height*3, row-major, sum over iterations). aov NULL/""/"Color" = main image;
+ * "Normals" / "Albedo" with the option "std_aovs". */
 int igb200_framebuffer(igb200_ctx* ctx, const char* aov, float** host_ptr);
 int igb200_framebuffer_device(igb200_ctx* ctx, const char* aov, float** device_ptr); /* getFramebufferForDevice */
 int igb200_clear(igb200_ctx* ctx, const char* aov_or_null);       /* clearFramebuffer / clearAllFramebuffer */
@@ -194,7 +195,8 @@ int igb200_turn_log(igb200_ctx* ctx, uint32_t* items, uint32_t* trace_ns, uint32
 int igb200_step_stats(igb200_ctx* ctx, uint64_t out[16]);
 /* Tunables: "capacity" (records per ray queue), "refill" (lanes), "stage_budget" (bytes of shared memory for the staged
  * scene), "min_blocks" (2|3 CTAs per SM), "vote" (0|2), "defer_permille" (deferred tail threshold, 0 = off), "split_turns"
- * (leading turns run as separate shade / trace launches), "turn_trace_blocks" (2|3), "wide_rays_per_group", "fuse" (iterations per launch, 0 = automatic), "profile_kernels". */
+ * (leading turns run as separate shade / trace launches), "turn_trace_blocks" (2|3), "wide_rays_per_group", "fuse" (iterations per launch, 0 = automatic), "profile_kernels", "std_aovs" (1: the "Normals" and
+ * "Albedo" AOVs of the reference's infobuffer wrapper, technique/internal/infobuffer.art, exist and are written at iteration 0). */
 int igb200_set_option(igb200_ctx* ctx, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a caller can record
  * its own events on it or order a collective after a render (the reference has one implicit device queue). */

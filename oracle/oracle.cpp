@@ -1017,12 +1017,13 @@ struct Camera {  // camera/perspective.art:2-6,29-42
 
 struct Oracle {
     Scene scene;
+    float* aov_normals = nullptr; float* aov_albedo = nullptr;   // standard AOVs (technique/internal/infobuffer.art), set by igo_set_aovs
     explicit Oracle(const SceneDesc& d) : scene(d) {}
 };
 
 // One tile: driver/mapping_cpu.art:719-861
 void trace_tile(const Scene& sc, const Settings& st, const StreamRay* list_rays, int xmin, int ymin, int xmax, int ymax,
-                float* fb, bool use_bvh, uint64_t counters[3]) {
+                float* fb, bool use_bvh, uint64_t counters[3], float* aov_normals = nullptr, float* aov_albedo = nullptr) {
     const int spi = st.spi;
     const int capacity = spi * 16 * 16;                         // :717
     const int W = st.width, H = st.height;
@@ -1125,6 +1126,18 @@ void trace_tile(const Scene& sc, const Settings& st, const StreamRay* list_rays,
                     mat.is_emissive = md.light_id >= 0;
                     mat.light = mat.is_emissive ? &sc.fin_lights[md.light_id] : nullptr;
                     Color hc;
+                    // wrap_infobuffer_renderer, technique/internal/infobuffer.art:9-24
+                    if (aov_normals && st.iter == 0 && (ray.flags & ray_flag_camera) == ray_flag_camera) {
+                        const Vec3 n = ctx.surf.local.c2;
+                        Color alb;
+                        if (mat.bsdf.type == BSDF_DIFFUSE) alb = mat.bsdf.kd;                                                         // diffuse.art:10
+                        else if (mat.bsdf.type == BSDF_DIELECTRIC) alb = col(lerp(mat.bsdf.ks.r, mat.bsdf.kt.r, 0.5f), lerp(mat.bsdf.ks.g, mat.bsdf.kt.g, 0.5f), lerp(mat.bsdf.ks.b, mat.bsdf.kt.b, 0.5f));   // dielectric.art:35
+                        else if (mat.bsdf.mirror) alb = mat.bsdf.ks;                                                                  // conductor.art:9
+                        else { const float ci = dot(neg(ray.dir), n); alb = cmul(mat.bsdf.ks, col(conductor_factor(mat.bsdf.c_eta.r, mat.bsdf.c_k.r, ci), conductor_factor(mat.bsdf.c_eta.g, mat.bsdf.c_k.g, ci), conductor_factor(mat.bsdf.c_eta.b, mat.bsdf.c_k.b, ci))); }   // conductor.art:28-38
+                        const int px = ray_id / spi;
+                        aov_normals[px * 3 + 0] += n.x * inv_spi; aov_normals[px * 3 + 1] += n.y * inv_spi; aov_normals[px * 3 + 2] += n.z * inv_spi;
+                        aov_albedo[px * 3 + 0] += fminf(alb.r, 1.0f) * inv_spi; aov_albedo[px * 3 + 1] += fminf(alb.g, 1.0f) * inv_spi; aov_albedo[px * 3 + 2] += fminf(alb.b, 1.0f) * inv_spi;
+                    }
                     if (tech.on_hit(ctx, primary.payload[i], mat, hc)) splat(ray_id, hc);
                     Ray sray; Color scol;
                     if (tech.on_shadow(ctx, rnd, primary.payload[i], mat, sray, scol)) {
@@ -1162,6 +1175,8 @@ extern "C" {
 
 void* igo_create(const SceneDesc* d) { return new Oracle(*d); }
 void igo_destroy(void* o) { delete (Oracle*)o; }
+// Enables the Normals / Albedo AOVs for subsequent igo_render calls (W*H*3 floats each, accumulated; null disables)
+void igo_set_aovs(void* o, float* normals, float* albedo) { ((Oracle*)o)->aov_normals = normals; ((Oracle*)o)->aov_albedo = albedo; }
 
 // Renders one iteration (driver/mapping_cpu.art cpu_trace) over 16x16 tiles with `n_threads` workers into `fb`
 // (W*H*3, accumulated). Only tiles with (tile_index % part_world == part_rank) are rendered when part_world > 1,
@@ -1183,7 +1198,7 @@ void igo_render(void* o, const Settings* st, const StreamRay* rays, float* fb, i
                 const int pidx = (y0 / part_tile) * ptx + (x0 / part_tile);
                 if (pidx % part_world != part_rank) continue;
             }
-            trace_tile(sc, *st, rays, x0, y0, std::min(W, x0 + T), std::min(H, y0 + T), fb, use_bvh != 0, cnt[tid].data());
+            trace_tile(sc, *st, rays, x0, y0, std::min(W, x0 + T), std::min(H, y0 + T), fb, use_bvh != 0, cnt[tid].data(), rays ? nullptr : ((Oracle*)o)->aov_normals, rays ? nullptr : ((Oracle*)o)->aov_albedo);
         }
     };
     if (n_threads <= 1) worker(0);

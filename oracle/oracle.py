@@ -87,6 +87,7 @@ def lib():
         L.igo_create.restype = C.c_void_p
         L.igo_create.argtypes = [C.POINTER(SceneDesc)]
         L.igo_destroy.argtypes = [C.c_void_p]
+        L.igo_set_aovs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.igo_render.argtypes = [C.c_void_p, C.POINTER(Settings), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.igo_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
@@ -128,6 +129,13 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+    def set_aovs(self, normals, albedo):
+        """Normals / Albedo AOVs of the reference's infobuffer wrapper: (H, W, 3) float32 arrays accumulated by render() at iteration 0."""
+        for a in (normals, albedo):
+            assert a is None or (a.dtype == np.float32 and a.flags.c_contiguous)
+        self._aovs = (normals, albedo)
+        lib().igo_set_aovs(self._h, None if normals is None else normals.ctypes.data, None if albedo is None else albedo.ctypes.data)
 
     def render(self, width, height, spi=1, iteration=0, seed=0, frame=0, fb=None, threads=0, use_bvh=True,
                rays=None, partition=(0, 1, 32)):

@@ -326,3 +326,32 @@ def test_spot_lights_match_oracle():
     got, ref, stats, cnt = render_both(t, 200, 200, 2, 2)
     assert rel_l2(got, ref) <= REL_L2_TOL
     assert (stats["CameraRayCount"], stats["ShadowRayCount"], stats["BounceRayCount"]) == tuple(int(x) for x in cnt)
+
+
+def test_standard_aovs_match_oracle():
+    """Normals / Albedo AOVs of the reference's infobuffer wrapper (technique/internal/infobuffer.art): first-hit shading normal and
+    BSDF albedo, written at iteration 0 only, through the C ABI and through the C++ plugin (which finds the wrapper in the script)."""
+    from ignis_b200 import plugin
+    t = load_scene(scene_path("diamond_scene.json"))
+    w, h, spi = 160, 90, 4
+    o = Oracle(t)
+    ref_n, ref_a, ref = (np.zeros((h, w, 3), np.float32) for _ in range(3))
+    o.set_aovs(ref_n, ref_a)
+    for it in range(2):
+        o.render(w, h, spi=spi, iteration=it, fb=ref)
+    assert np.abs(ref_n).sum() > 0 and ref_a.max() <= 1.0 + 1e-6
+    with Runtime(t, w, h, spi=spi) as rt:
+        with pytest.raises(Exception, match="AOV"):
+            rt.device.getFramebufferForHost("Normals")          # off by default
+        rt.device.setOption("std_aovs", 1)
+        rt.step(); rt.step()
+        got = [rt.device.getFramebufferForHost(n).copy() for n in ("Normals", "Albedo", "")]
+    with plugin.PluginRuntime(t, w, h, spi, std_aovs=True) as prt:
+        prt.step(); prt.step()
+        got_p = [prt.getFramebufferForHost(n).copy() for n in ("Normals", "Albedo", "")]
+    for g in (got, got_p):
+        assert rel_l2(g[0], ref_n) <= 1e-5 and rel_l2(g[1], ref_a) <= 1e-5 and rel_l2(g[2], ref) <= REL_L2_TOL
+    with plugin.PluginRuntime(t, w, h, spi, std_aovs=False) as prt:
+        prt.step()
+        with pytest.raises(Exception, match="AOV"):
+            prt.getFramebufferForHost("Albedo")
