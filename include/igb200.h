@@ -179,9 +179,9 @@ int igb200_upload_framebuffer(igb200_ctx* ctx, const char* aov, const float* hos
 int igb200_stats(igb200_ctx* ctx, uint64_t out[5], double* render_ms);
 int igb200_reset_stats(igb200_ctx* ctx);
 
-/* Time spent in the phases of the persistent wavefront kernel since the last reset, measured on the device
- * (%globaltimer at the grid barriers): out_ms = {0, trace phase (closest + any hit), shade + generate phase, 0},
- * out_launches = number of phases. */
+/* Time spent in the two phases of the wavefront turns since the last reset, measured on the device (%globaltimer at the
+ * grid barriers of the persistent kernel and at the start of the split-turn kernels): out_ms = {0, trace phases (closest +
+ * any hit), shade + generate phases, 0}, out_launches = number of phases. */
 int igb200_kernel_times(igb200_ctx* ctx, double out_ms[4], uint64_t out_launches[4]);
 /* With the option "profile_kernels" = 1 every kernel launch of igb200_render is bracketed by CUDA events on the context's
  * stream; this returns, since the last reset, the summed durations and launch counts per kernel (0 k_wavefront, 1 k_turn_trace,
