@@ -505,6 +505,37 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
             tri_prim.push_back(t);
         }
     }
+    // ---- node order: breadth-first across ALL trees (top-level root first, then level by level over every shape's tree), so that
+    // the part of the node array that is staged in shared memory (configure_kernels) holds the top of every tree instead of
+    // the whole first shape: with geometry that does not fit, every bottom-level walk then saves its first L2 round trips
+    if (!nodes.empty()) {
+        const int n = (int)nodes.size();
+        std::vector<int> order; order.reserve(n);
+        std::vector<char> seen(n, 0);
+        std::vector<int> frontier, next;
+        frontier.push_back(0);
+        for (int s = 0; s < d->n_shapes; ++s) if (shape_root[s] > 0) frontier.push_back(shape_root[s] - 1);
+        while (!frontier.empty()) {
+            next.clear();
+            for (const int i : frontier) {
+                if (i < 0 || i >= n || seen[i]) continue;
+                seen[i] = 1; order.push_back(i);
+                for (int k = 0; k < 8; ++k) if (nodes[i].child[k] > 0) next.push_back(nodes[i].child[k] - 1);
+            }
+            frontier.swap(next);
+        }
+        for (int i = 0; i < n; ++i) if (!seen[i]) order.push_back(i);
+        std::vector<int> perm(n);
+        for (int k = 0; k < n; ++k) perm[order[k]] = k;
+        std::vector<Node8> sorted(n);
+        for (int i = 0; i < n; ++i) {
+            Node8 nd = nodes[i];
+            for (int k = 0; k < 8; ++k) if (nd.child[k] > 0) nd.child[k] = perm[nd.child[k] - 1] + 1;
+            sorted[perm[i]] = nd;
+        }
+        nodes.swap(sorted);
+        for (int s = 0; s < d->n_shapes; ++s) if (shape_root[s] > 0) shape_root[s] = perm[shape_root[s] - 1] + 1;
+    }
     // ---- entity records
     auto as_f = [](int32_t v) { float f; std::memcpy(&f, &v, 4); return f; };
     auto as_fu = [](uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; };
