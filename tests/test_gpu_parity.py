@@ -76,15 +76,21 @@ def test_closest_hit_records_match_oracle(scene, w, h):
     o = Oracle(t)
     ref = o.trace_closest(rays, use_bvh=True)
     ref_occ = o.trace_any(rays, flags=np.full(len(rays), 8, np.uint32))
-    # both walks of the device: one lane per ray (large queues) and eight lanes per ray (small queues, traverse.cuh trace_wide)
-    for wide in (0, 1 << 20):
+    # both walks of the device: one lane per ray (large queues) and eight lanes per ray (small queues, traverse.cuh trace_wide);
+    # with the scene copy in shared memory when it fits (the default), with nothing staged, and with a staged prefix (nodes and
+    # triangles partly in shared memory, partly read through L1/L2) -- the closest hit must not depend on any of it
+    for wide, opts in ((0, {}), (1 << 20, {}), (0, {"stage_budget": 0}), (1 << 20, {"stage_budget": 0}),
+                       (0, {"stage_partial": 1, "stage_budget": 6144}), (1 << 20, {"stage_partial": 1, "stage_budget": 6144})):
+        budget = tuple(opts.items())
         with B200Device() as dev:
             dev.assignScene(t)
             dev.setOption("wide_rays_per_group", wide)
+            for k, v in opts.items():
+                dev.setOption(k, v)
             got = dev.traceClosest(rays)
             occ = dev.traceAny(rays)
-        assert (got["ent_id"] == ref["ent_id"]).all(), wide
-        assert (got["prim_id"] == ref["prim_id"]).all(), wide
+        assert (got["ent_id"] == ref["ent_id"]).all(), (wide, budget)
+        assert (got["prim_id"] == ref["prim_id"]).all(), (wide, budget)
         for k in ("t", "u", "v"):
             np.testing.assert_array_equal(got[k].view(np.uint32), ref[k].view(np.uint32))
         np.testing.assert_array_equal(occ, ref_occ)
