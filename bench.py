@@ -260,20 +260,29 @@ def run_b200(args):
                             stream.synchronize()
                     else:
                         host = dev.getFramebufferForHost()   # D2H of the accumulated frame into pinned memory
+            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev_a.record(stream)      # the K iterations are issued (fused launches flush every `fuse` iterations)
             if not e2e:
                 dev.sync()           # finishes the deferred tail of the last steps: all work of the K steps is inside the timed region
-                if world > 1:
-                    reduce_to_root()
+            ev_b.record(stream)
+            if not e2e and world > 1:
+                reduce_to_root()
             ev1.record(stream)
             stream.synchronize()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         dev_ms = ev0.elapsed_time(ev1)
+        parts = [ev0.elapsed_time(ev_a), ev_a.elapsed_time(ev_b), ev_b.elapsed_time(ev1)]   # render launches | flush + drain | reduce
         ms = max(dev_ms, 0.0)
         st = dev.getStatistics()
         vals = torch.tensor([ms, wall_ms, st["CameraRayCount"], st["ShadowRayCount"], st["BounceRayCount"], st["Splats"], st["KernelLaunches"]],
                             dtype=torch.float64, device="cuda")
+        per_rank = [parts + [ms, float(st["CameraRayCount"] + st["ShadowRayCount"] + st["BounceRayCount"])]]
         if world > 1:
+            mine = torch.tensor(per_rank[0], dtype=torch.float64, device="cuda")
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            per_rank = [[round(float(x), 3) for x in t_] for t_ in every]
             mx = vals.clone()
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             sm = vals.clone()
@@ -283,11 +292,13 @@ def run_b200(args):
         else:
             tot = {k: st[k] for k in ("CameraRayCount", "ShadowRayCount", "BounceRayCount", "Splats", "KernelLaunches")}
         tot["TotalRays"] = tot["CameraRayCount"] + tot["ShadowRayCount"] + tot["BounceRayCount"]
+        timed.per_rank = per_rank
         return ms, wall_ms, tot, clk.summary(), host
 
     host_t = torch.empty(w * h * 3, dtype=torch.float32, pin_memory=True) if (world > 1 and rank == 0) else None
 
     ms, wall_ms, tot, clocks, _ = timed(e2e=False)
+    per_rank = timed.per_rank
     ms_e, wall_e, tot_e, _, host = timed(e2e=True)
 
     # ---- per-kernel timing (separate pass, N = 1): every launch bracketed by CUDA events on the render stream
@@ -315,6 +326,7 @@ def run_b200(args):
                 "clocks": clocks, "gpu_launches": tot["KernelLaunches"],
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": w * h * 12,
                         "ms_per_step": wall_e / args.steps, "timed": "host wall clock between barriers, max over ranks"},
+                "per_rank_ms": {"columns": ["issued launches", "flush + drain of the deferred tail", "NCCL reduce", "total", "rays traced"], "ranks": per_rank},
                 "rays": tot, "msamples_per_s": w * h * spi * args.steps / (ms * 1e-3) / 1e6, "wall_ms_per_step": wall_ms / args.steps}
         step_bytes = algorithmic_bytes(tot)
         line["roofline_step"] = {"bound": "hbm", "achieved": step_bytes / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",

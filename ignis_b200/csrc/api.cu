@@ -794,7 +794,7 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
     rp.tiles_x = (W + rp.tile_w - 1) / rp.tile_w;
     const int tiles_y = (H + rp.tile_h - 1) / rp.tile_h;
     const long long tiles_total = (long long)rp.tiles_x * tiles_y;
-    const long long local_tiles = tiles_total > rp.rank ? (tiles_total - rp.rank + rp.world - 1) / rp.world : 0;
+    const long long local_tiles = (tiles_total + rp.world - 1) / rp.world;   // one tile of every group of `world` tiles (wavefront.cuh phase_generate)
     rp.per_iter = local_tiles * rp.tile_w * rp.tile_h * rp.spi;             // padded ray domain of this rank, one iteration
     const long long total = rp.per_iter * n_iter;                          // ... of the launch (n_iter consecutive iterations)
 
