@@ -25,11 +25,19 @@ constexpr int WF_BLOCK = 256;       // threads per CTA of the persistent kernels
 // "vote" picks the scheduling of the traversal visit kinds (traverse.cuh turn / turn_vote); all variants are built.
 using WaveKernel = void (*)(const WaveParams);
 using TraceKernel = void (*)(const DevScene, const PrimaryQueue, int, const ShadowQueue, int, float*, int*, unsigned long long*, int, int, int, int, int);
-static WaveKernel wave_kernel(int min_blocks, int vote) {
-    if (vote) return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 2> : k_wavefront<WF_BLOCK, 2, 2>;
-    return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 0> : k_wavefront<WF_BLOCK, 2, 0>;
+// "full": the shade code with every feature (shade.cuh shade_record<true>) or only what the BASELINE configurations use.
+static WaveKernel wave_kernel(int min_blocks, int vote, bool full) {
+    if (full) {
+        if (vote) return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 2, true> : k_wavefront<WF_BLOCK, 2, 2, true>;
+        return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 0, true> : k_wavefront<WF_BLOCK, 2, 0, true>;
+    }
+    if (vote) return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 2, false> : k_wavefront<WF_BLOCK, 2, 2, false>;
+    return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 0, false> : k_wavefront<WF_BLOCK, 2, 0, false>;
 }
-static WaveKernel turn_shade_kernel(int blocks) { return blocks >= 4 ? k_turn_shade<WF_BLOCK, 4> : blocks == 3 ? k_turn_shade<WF_BLOCK, 3> : k_turn_shade<WF_BLOCK, 2>; }
+static WaveKernel turn_shade_kernel(int blocks, bool full) {
+    if (full) return blocks >= 4 ? k_turn_shade<WF_BLOCK, 4, true> : blocks == 3 ? k_turn_shade<WF_BLOCK, 3, true> : k_turn_shade<WF_BLOCK, 2, true>;
+    return blocks >= 4 ? k_turn_shade<WF_BLOCK, 4, false> : blocks == 3 ? k_turn_shade<WF_BLOCK, 3, false> : k_turn_shade<WF_BLOCK, 2, false>;
+}
 static WaveKernel turn_trace_kernel(int blocks, int vote) {
     if (vote) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2> : k_turn_trace<WF_BLOCK, 2, 2>;
     return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 0> : k_turn_trace<WF_BLOCK, 2, 0>;
@@ -90,12 +98,13 @@ struct igb200_ctx {
     int device = 0, n_sm = 0;
     cudaStream_t stream = nullptr;
     bool has_scene = false;
+    bool scene_full = false;       // the scene uses features only shade_record<true> has (conductors, sphere / spot lights, non-uniform selectors)
     igb200_scene_desc desc{};      // scalar members only are kept
     DevScene dev{};
     DevBuf<float4> nodes, tris, ent_leaf, ent_shade, blob, materials;
     DevBuf<int> tri_prim;
     DevBuf<int4> shape_info;
-    DevBuf<float> inf_lights, fin_lights;
+    DevBuf<float> inf_lights, fin_lights, selector_data;
     // framebuffer
     int width = 0, height = 0;
     DevBuf<float> fb;
@@ -173,10 +182,15 @@ static int configure_kernels(igb200_ctx* c) {
     c->stage_nodes = (int)std::min<int64_t>(s.n_nodes, left / 256); left -= (int64_t)c->stage_nodes * 256;
     c->stage_tris = (int)std::min<int64_t>(s.n_tris, left / 48);
     c->smem_bytes = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)c->stage_ent * 128 + (size_t)c->stage_nodes * 256 + (size_t)c->stage_tris * 48;
-    CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    for (int full = 0; full < 2; ++full) CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote, full != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CU(cudaFuncSetAttribute((const void*)trace_kernel(c->min_blocks, c->vote), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     int nb = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)wave_kernel(c->min_blocks, c->vote), WF_BLOCK, c->smem_bytes));
+    {   // both shade variants must fit the cooperative grid
+        int nb1 = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)wave_kernel(c->min_blocks, c->vote, false), WF_BLOCK, c->smem_bytes));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, (const void*)wave_kernel(c->min_blocks, c->vote, true), WF_BLOCK, c->smem_bytes));
+        nb = std::min(nb, nb1);
+    }
     if (nb < 1) return fail(-2, "k_wavefront does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
     c->blocks_per_sm = nb;
     // split turn kernels
@@ -184,7 +198,12 @@ static int configure_kernels(igb200_ctx* c) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote), WF_BLOCK, c->smem_bytes));
     if (nb < 1) return fail(-2, "k_turn_trace does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
     c->grid_turn_trace = nb * c->n_sm;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)turn_shade_kernel(c->turn_shade_blocks), WF_BLOCK, 0));
+    {
+        int nb1 = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)turn_shade_kernel(c->turn_shade_blocks, false), WF_BLOCK, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, (const void*)turn_shade_kernel(c->turn_shade_blocks, true), WF_BLOCK, 0));
+        nb = std::min(nb, nb1);
+    }
     if (nb < 1) return fail(-2, "k_turn_shade does not fit an SM");
     c->grid_turn_shade = nb * c->n_sm;
     return 0;
@@ -193,6 +212,7 @@ static int configure_kernels(igb200_ctx* c) {
 static WaveParams make_params(igb200_ctx* c, const RenderParams& rp, const DevScene& sc, long long total, const igb200_ray* d_rays, int defer) {
     WaveParams P;
     P.sc = sc; P.rp = rp;
+    P.sc.full = (c->scene_full || rp.aov_normals != nullptr) ? 1 : 0;
     P.q[0] = c->qa.view(); P.q[1] = c->qb.view();
     P.sq = ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p};
     P.fb = c->fb.p; P.ctl = c->control.p;
@@ -233,7 +253,7 @@ static int launch_wave(igb200_ctx* c, const RenderParams& rp, const DevScene& sc
     CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
     void* args[] = {&P};
     { const int r = prof_begin(c, 0); if (r) return r; }
-    CU(cudaLaunchCooperativeKernel((const void*)wave_kernel(c->min_blocks, c->vote), dim3((unsigned)(c->blocks_per_sm * c->n_sm)), dim3(WF_BLOCK), args, c->smem_bytes, c->stream));
+    CU(cudaLaunchCooperativeKernel((const void*)wave_kernel(c->min_blocks, c->vote, P.sc.full != 0), dim3((unsigned)(c->blocks_per_sm * c->n_sm)), dim3(WF_BLOCK), args, c->smem_bytes, c->stream));
     { const int r = prof_end(c); if (r) return r; }
     c->launches += 1;
     c->pending = true;
@@ -261,7 +281,7 @@ static int launch_split_turns(igb200_ctx* c, const WaveParams& P, int turns) {
     CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
     for (int t = 0; t < turns; ++t) {
         { const int r = prof_begin(c, 2); if (r) return r; }
-        turn_shade_kernel(c->turn_shade_blocks)<<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
+        turn_shade_kernel(c->turn_shade_blocks, P.sc.full != 0)<<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
         { const int r = prof_end(c); if (r) return r; }
         { const int r = prof_begin(c, 1); if (r) return r; }
         turn_trace_kernel(c->turn_trace_blocks, c->vote)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
@@ -421,6 +441,23 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     CU(cudaSetDevice(c->device));
     { const int r = sync_control(c); if (r) return r; }
     if (d->technique.max_depth > 254) return fail(-4, "igb200_set_scene: max_depth %d > 254 is not supported (the depth travels in 8 bits of the ray record)", d->technique.max_depth);
+    {   // light selector and the buffer it reads
+        const int sel = d->technique.light_selector, n = d->n_finite;
+        if (sel < IGB200_SELECTOR_UNIFORM || sel > IGB200_SELECTOR_HIERARCHY) return fail(-4, "igb200_set_scene: unsupported light selector %d", sel);
+        if (sel != IGB200_SELECTOR_UNIFORM) {
+            if (n < 1) return fail(-1, "igb200_set_scene: light selector %d needs finite lights (the reference generates the uniform selector then, LoaderLight.cpp:428-437)", sel);
+            const long long need = sel == IGB200_SELECTOR_CDF ? n : (n == 1 ? 0 : (long long)(n + 3) / 4 * 4 + 8LL * (2 * n - 1));
+            if (!d->selector_data || d->n_selector_data < need) return fail(-1, "igb200_set_scene: light selector %d over %d finite lights needs %lld words of selector_data, got %d", sel, n, need, d->n_selector_data);
+            if (sel == IGB200_SELECTOR_HIERARCHY && n > 1) {   // every child index must stay inside the buffer; depth <= 32 (the codes are 32 bits)
+                const int n_nodes = (d->n_selector_data - (n + 3) / 4 * 4) / 8;
+                const float* e = d->selector_data + (n + 3) / 4 * 4;
+                for (int k = 0; k < n_nodes; ++k) {
+                    int32_t idx; std::memcpy(&idx, e + 8 * k + 7, 4);
+                    if (idx >= n || (idx < 0 && (-idx - 1 + 1 >= n_nodes || -idx - 1 <= k))) return fail(-1, "igb200_set_scene: light hierarchy node %d refers to %d (%d nodes, %d lights)", k, idx, n_nodes, n);
+                }
+            }
+        }
+    }
     if (d->n_leaves != d->n_entities) return fail(-1, "igb200_set_scene: %d leaves for %d entities (one EntityLeaf1 per entity expected)", d->n_leaves, d->n_entities);
     if (d->shape_data_bytes % 16) return fail(-1, "igb200_set_scene: shapes dyn-table data must be a multiple of 16 bytes");
     for (int m = 0; m < d->n_materials; ++m)
@@ -594,6 +631,9 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     CU(c->nodes.upload(node_f4)); CU(c->tris.upload(tris)); CU(c->tri_prim.upload(tri_prim)); CU(c->ent_leaf.upload(ent_leaf)); CU(c->ent_shade.upload(ent_shade));
     CU(c->blob.upload(blob)); CU(c->shape_info.upload(shape_info)); CU(c->materials.upload(mats));
     CU(c->inf_lights.upload(infl)); CU(c->fin_lights.upload(finl));
+    std::vector<float> seld;
+    if (d->technique.light_selector != IGB200_SELECTOR_UNIFORM) seld.assign(d->selector_data, d->selector_data + d->n_selector_data);
+    CU(c->selector_data.upload(seld));
 
     DevScene& s = c->dev;
     s.nodes = c->nodes.p; s.tris = c->tris.p; s.tri_prim = c->tri_prim.p; s.ent_leaf = c->ent_leaf.p; s.ent_shade = c->ent_shade.p; s.blob = c->blob.p;
@@ -604,6 +644,11 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
         const float dx = d->bbox_max[0] - d->bbox_min[0], dy = d->bbox_max[1] - d->bbox_min[1], dz = d->bbox_max[2] - d->bbox_min[2];
         s.scene_radius = std::sqrt(std::fmaf(dx, dx, std::fmaf(dy, dy, dz * dz))) / 2 * 1.01f;
     }
+    s.selector = d->technique.light_selector; s.selector_data = c->selector_data.p;
+    c->scene_full = s.selector != IGB200_SELECTOR_UNIFORM;
+    for (int m = 0; m < d->n_materials; ++m) c->scene_full |= d->materials[m].bsdf == IGB200_BSDF_CONDUCTOR;
+    for (int l = 0; l < d->n_finite; ++l) c->scene_full |= d->finite_lights[l].type == IGB200_LIGHT_SPHERE_AREA || d->finite_lights[l].type == IGB200_LIGHT_SPOT;
+    s.full = c->scene_full ? 1 : 0;
     s.max_depth = d->technique.max_depth; s.min_depth = d->technique.min_depth; s.clamp_value = d->technique.clamp; s.nee = d->technique.nee;
     c->desc = *d;
     c->desc.entities = nullptr; c->desc.shape_lookups = nullptr; c->desc.shape_data = nullptr; c->desc.leaves = nullptr;

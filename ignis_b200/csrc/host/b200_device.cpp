@@ -70,6 +70,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     std::vector<igb200_light> inf, fin;
     igb200_camera camera; std::memset(&camera, 0, sizeof(camera));
     igb200_technique technique{};
+    std::vector<float> selector_data;
     try {
         if (set.HitShaders.size() != mScene.entity_per_material->size()) throw RecognizeError{"one hit shader per material expected"};
         const StageDescriptor* light_stage = nullptr; const IG::ParameterSet* light_local = nullptr;
@@ -88,7 +89,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
             mStdAovs = (int)light_stage->std_aovs;
         }
         resolve_lights(*light_stage, Registries{light_local, global}, inf, fin);
-        technique = resolve_technique(*light_stage, Registries{light_local, global});
+        technique = resolve_technique(*light_stage, Registries{light_local, global}, selector_data);
         const StageDescriptor* rg = static_cast<const StageDescriptor*>(set.RayGenerationShader.Exec);
         if (!rg) throw RecognizeError{"null ray generation shader"};
         if (rg->has_camera) camera = resolve_camera(*rg, Registries{set.RayGenerationShader.LocalRegistry.get(), global});
@@ -100,6 +101,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     append(bytes, fin.data(), fin.size() * sizeof(igb200_light));
     append(bytes, &camera, sizeof(camera));
     append(bytes, &technique, sizeof(technique));
+    append(bytes, selector_data.data(), selector_data.size() * sizeof(float));
     if (!mSceneDirty && bytes == mDescriptorBytes) return true;
 
     const IG::SceneDatabase& db = *mScene.database;
@@ -126,6 +128,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     d.infinite_lights = inf.data(); d.n_infinite = (int32_t)inf.size();
     d.finite_lights = fin.data(); d.n_finite = (int32_t)fin.size();
     d.camera = camera; d.technique = technique;
+    d.selector_data = selector_data.empty() ? nullptr : selector_data.data(); d.n_selector_data = (int32_t)selector_data.size();
     for (int k = 0; k < 3; ++k) { d.bbox_min[k] = db.SceneBBox.min.v[k]; d.bbox_max[k] = db.SceneBBox.max.v[k]; }
     if (igb200_set_scene(mCtx, &d) != 0) { error(std::string("scene upload failed: ") + igb200_last_error()); return false; }
     mDescriptorBytes.swap(bytes);

@@ -8,6 +8,8 @@
 
 #include "b200_device.h"
 
+#include <algorithm>
+
 using namespace IG;
 
 namespace {
@@ -74,8 +76,15 @@ int igbh_describe_lights(void* stage, ParameterSet* local, ParameterSet* global,
         return 0;
     } catch (const igbh::RecognizeError& e) { igbh::set_last_error(e.what); return -1; }
 }
-int igbh_describe_technique(void* stage, ParameterSet* local, ParameterSet* global, igb200_technique* out) {
-    try { *out = igbh::resolve_technique(*static_cast<igbh::StageDescriptor*>(stage), igbh::Registries{local, global}); return 0; }
+// selector: receives up to `cap` words of the light selector's buffer; *n = the number of words it holds (may exceed cap)
+int igbh_describe_technique(void* stage, ParameterSet* local, ParameterSet* global, igb200_technique* out, float* selector, int cap, int* n) {
+    try {
+        std::vector<float> data;
+        *out = igbh::resolve_technique(*static_cast<igbh::StageDescriptor*>(stage), igbh::Registries{local, global}, data);
+        if (n) *n = (int)data.size();
+        if (selector) std::copy(data.begin(), data.begin() + std::min<size_t>(data.size(), (size_t)std::max(cap, 0)), selector);
+        return 0;
+    }
     catch (const igbh::RecognizeError& e) { igbh::set_last_error(e.what); return -1; }
 }
 int igbh_describe_camera(void* stage, ParameterSet* local, ParameterSet* global, igb200_camera* out) {

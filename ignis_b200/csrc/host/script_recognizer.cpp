@@ -1,6 +1,8 @@
 // script_recognizer.cpp -- see script_recognizer.h. Host-only C++17, no CUDA.
 #include "script_recognizer.h"
 
+#include <cstdio>
+
 #include <cctype>
 #include <cmath>
 #include <cstdlib>
@@ -538,14 +540,47 @@ void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vect
     for (const std::string& b : stage.finite_lights) finite.push_back(resolve_light(ev, b));
 }
 
-igb200_technique resolve_technique(const StageDescriptor& stage, const Registries& r) {
+igb200_technique resolve_technique(const StageDescriptor& stage, const Registries& r, std::vector<float>& selector_data) {
     if (!stage.has_technique) fail(stage.function + " carries no technique");
     Eval ev{stage, r};
     const Val t = ev.binding("technique");   // PathTechnique.cpp:35-79
     if (t.kind != Val::Ctor || t.name != "make_path_renderer") fail("technique '" + (t.kind == Val::Ctor ? t.name : std::string("?")) + "' is not supported by this device (path only)");
-    const Val& sel = ctor_arg(t, 2);
-    if (sel.kind != Val::Ctor || sel.name != "make_uniform_light_selector") fail("light selector '" + sel.name + "' is not supported by this device (uniform only)");
     igb200_technique out;
+    std::memset(&out, 0, sizeof(out));
+    selector_data.clear();
+    // light selector (LoaderLight.cpp:423-452). The cdf and hierarchy selectors read a buffer the loader wrote into its cache directory and
+    // named in the script -- `device.load_buffer("<dir>/light_cdf.bin" | "<dir>/light_hierarchy.bin")` -- which is read here the way
+    // Device::loadBuffer would (src/device/Device.cpp: a file of raw 32-bit words). With no finite light both degrade to the uniform
+    // selector at specialisation time (light_selector.art:80-81), with no light at all the generator never emits them.
+    const Val& sel = ctor_arg(t, 2);
+    if (sel.kind != Val::Ctor) fail("light selector is not a constructor call");
+    auto buffer_of = [&](const Val& v) -> std::string {
+        if (v.kind != Val::Ctor || v.name != "device.load_buffer" || v.args.size() != 1 || v.args[0].kind != Val::Sym || v.args[0].name.empty() || v.args[0].name[0] != '"')
+            fail("the light selector's buffer is not device.load_buffer(\"file\")");
+        return v.args[0].name.substr(1);
+    };
+    std::string file;
+    if (sel.name == "make_uniform_light_selector") out.light_selector = IGB200_SELECTOR_UNIFORM;
+    else if (sel.name == "make_hierarchy_light_selector") { out.light_selector = IGB200_SELECTOR_HIERARCHY; file = buffer_of(ctor_arg(sel, 2)); }
+    else if (sel.name == "make_cdf_light_selector") {
+        out.light_selector = IGB200_SELECTOR_CDF;
+        const Val& cdf = ctor_arg(sel, 2);
+        if (cdf.kind != Val::Ctor || cdf.name != "cdf::make_cdf_1d_from_buffer") fail("the cdf light selector's sampler is not cdf::make_cdf_1d_from_buffer(...)");
+        file = buffer_of(ctor_arg(cdf, 0));
+        if (as_num(ctor_arg(cdf, 2), "cdf offset") != 0) fail("cdf::make_cdf_1d_from_buffer with a non-zero offset");
+    } else fail("light selector '" + sel.name + "' is not supported by this device (uniform, cdf, hierarchy)");
+    if (out.light_selector != IGB200_SELECTOR_UNIFORM) {
+        if (stage.finite_lights.empty()) out.light_selector = IGB200_SELECTOR_UNIFORM;
+        else {
+            FILE* f = std::fopen(file.c_str(), "rb");
+            if (!f) fail("cannot open the light selector's buffer '" + file + "'");
+            std::fseek(f, 0, SEEK_END); const long bytes = std::ftell(f); std::fseek(f, 0, SEEK_SET);
+            selector_data.resize((size_t)std::max(0L, bytes) / 4);
+            const size_t got = selector_data.empty() ? 0 : std::fread(selector_data.data(), 4, selector_data.size(), f);
+            std::fclose(f);
+            if (got != selector_data.size() || selector_data.empty()) fail("cannot read the light selector's buffer '" + file + "'");
+        }
+    }
     out.max_depth = (int32_t)as_num(ctor_arg(t, 0), "max_depth");
     out.min_depth = (int32_t)as_num(ctor_arg(t, 1), "min_depth");
     out.clamp = as_num(ctor_arg(t, 4), "clamp");

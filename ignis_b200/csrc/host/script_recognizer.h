@@ -54,7 +54,8 @@ struct Registries { const IG::ParameterSet* local; const IG::ParameterSet* globa
 
 igb200_material resolve_material(const StageDescriptor& hit, const Registries& r);     // throws RecognizeError
 void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vector<igb200_light>& infinite, std::vector<igb200_light>& finite);
-igb200_technique resolve_technique(const StageDescriptor& stage, const Registries& r);
+// selector_data: contents of the buffer the cdf / hierarchy light selector reads (igb200_scene_desc::selector_data), empty for uniform
+igb200_technique resolve_technique(const StageDescriptor& stage, const Registries& r, std::vector<float>& selector_data);
 igb200_camera resolve_camera(const StageDescriptor& raygen, const Registries& r);
 
 const std::string& last_error();

@@ -185,6 +185,8 @@ __device__ __forceinline__ void sphere_emitter_sample(const DevScene& sc, const 
     }
 }
 
+// FULL: see shade_record
+template <bool FULL>
 __device__ __forceinline__ LightSample light_sample_direct(const DevScene& sc, const float* L, int type, Rng& rnd, const Surf& from) {
     LightSample o;
     if (type == 0) {          // light/env.art:84-88
@@ -201,7 +203,7 @@ __device__ __forceinline__ LightSample light_sample_direct(const DevScene& sc, c
         o.pos = pos; o.dir = mulf(d_, safe_div(1, dist));
         o.intensity = c3(__ldg(L + 5), __ldg(L + 6), __ldg(L + 7));
         o.pdf.value = 1; o.pdf.measure = 1; o.cos = 1; o.dist = dist;
-    } else if (type == 5) {   // light/spot.art:8-44
+    } else if (FULL && type == 5) {   // light/spot.art:8-44
         const V3 pos = v3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4)), sdir = v3(__ldg(L + 5), __ldg(L + 6), __ldg(L + 7));
         const float cos_cutoff = __ldg(L + 8), cos_falloff = __ldg(L + 9);
         const float blend = cos_falloff - cos_cutoff;
@@ -238,7 +240,7 @@ __device__ __forceinline__ LightSample light_sample_direct(const DevScene& sc, c
             o.pdf.value = safe_div(1, sq.s); o.pdf.measure = 0;
             weight = sq.s;
             radiance = c3(__ldg(L + 23), __ldg(L + 24), __ldg(L + 25));
-        } else if (type == 4) {   // sphere emitter
+        } else if (FULL && type == 4) {   // sphere emitter
             sphere_emitter_sample(sc, L, u, v, from.point, to_point, to_normal);
             const float area = __ldg(L + 9);
             o.pdf.value = safe_div(1, area); o.pdf.measure = 1;
@@ -276,9 +278,106 @@ __device__ __forceinline__ int coalesced_append(int* counter) {
     return g.shfl(base, 0) + (int)g.thread_rank();
 }
 
+// ---- non-uniform light selectors (light/light_selector.art:46-110). Kept out of line: scenes with the uniform selector -- every
+// BASELINE configuration -- never execute them, and the shade kernel is instruction-fetch bound.
+struct LightPick { int id; float pdf; uint32_t counter; };   // id: index into [infinite lights | finite lights]
+
+// light_cdf.bin = [x1 .. x(n-1), 1]; the leading 0 is virtual (core/cdf.art:43-48,70-73)
+__device__ __forceinline__ float sel_cdf_get(const float* data, int i) { return i == 0 ? 0.0f : __ldg(data + i - 1); }
+__device__ __forceinline__ int sel_cdf_sample(const float* data, int n_fin, float u, float& pdf) {
+    const int size = n_fin + 1;
+    int first = 0, len = size;                     // interval::binary_search, core/interval.art:7-23
+    while (len > 0) {
+        const int half = len / 2, middle = first + half;
+        if (sel_cdf_get(data, middle) <= u) { first = middle + 1; len -= half + 1; } else len = half;
+    }
+    const int off = min(min(max(first - 1, 0), size - 1), n_fin - 1);
+    pdf = sel_cdf_get(data, off + 1) - sel_cdf_get(data, off);
+    return off;
+}
+// light_hierarchy.bin = codes[round_up(n, 4)] then 8 words per node {pos, +-flux, dir, id} (light/light_hierarchy.art:13-38)
+struct HEntry { V3 pos, dir; float flux; int id; bool has_dir, is_leaf; };
+__device__ __forceinline__ HEntry sel_h_load(const float* nodes, int id) {
+    const float4 e1 = __ldg(reinterpret_cast<const float4*>(nodes) + id * 2), e2 = __ldg(reinterpret_cast<const float4*>(nodes) + id * 2 + 1);
+    const int index = __float_as_int(e2.w);
+    HEntry h;
+    h.pos = v3(e1.x, e1.y, e1.z); h.dir = v3(e2.x, e2.y, e2.z);
+    h.flux = fabsf(e1.w); h.id = index < 0 ? -index - 1 : index;
+    h.has_dir = (__float_as_uint(e1.w) >> 31) == 0; h.is_leaf = index >= 0;
+    return h;
+}
+__device__ __forceinline__ float sel_h_cost(const HEntry& e, V3 pos) {      // light_hierarchy.art:40-52
+    const V3 cdir = e.pos - pos;
+    const float dist2 = len2(cdir);
+    const float cos_d = e.has_dir ? fabsf(dot(e.dir, normalize(cdir))) : 1.0f;
+    return safe_div(e.flux * cos_d, dist2);
+}
+__device__ __forceinline__ float sel_h_left(const HEntry& l, const HEntry& r, V3 pos) { const float cl = sel_h_cost(l, pos), cr = sel_h_cost(r, pos); return 1 / (1 + cr / cl); }
+
+__device__ __noinline__ LightPick selector_sample(const float* data, int kind, int n_inf, int n_fin, uint32_t seed, uint32_t counter, float px, float py, float pz) {
+    Rng rnd; rnd.seed = seed; rnd.counter = counter;
+    const V3 from = v3(px, py, pz);
+    LightPick r; r.pdf = 1.0f; r.id = 0;
+    bool finite = true; float scale = 1.0f;
+    if (n_inf != 0) {   // half the samples go to the infinite lights (light_selector.art:57-75,92-108)
+        const float q = rnd.next_f32();
+        if (q < 0.5f) { r.id = n_inf <= 1 ? 0 : rnd.next_i32(0, n_inf - 1); r.pdf = 1 / (float)n_inf * 0.5f; finite = false; }
+        else scale = 1 - 0.5f;
+    }
+    if (finite) {
+        int id = 0; float pdf = 1.0f;
+        if (kind == 1) id = sel_cdf_sample(data, n_fin, rnd.next_f32(), pdf);
+        else if (n_fin > 1) {                                               // light_hierarchy.art:63-76
+            const float* nodes = data + (n_fin + 3) / 4 * 4;
+            HEntry entry = sel_h_load(nodes, 0);
+            while (!entry.is_leaf) {
+                const HEntry left = sel_h_load(nodes, entry.id), right = sel_h_load(nodes, entry.id + 1);
+                const float prop = sel_h_left(left, right, from);
+                const bool is_left = rnd.next_f32() < prop;
+                entry = is_left ? left : right;
+                pdf *= is_left ? prop : 1 - prop;
+            }
+            id = entry.id;
+        }
+        r.id = n_inf + id;
+        r.pdf = n_inf != 0 ? pdf * scale : pdf;
+    }
+    r.counter = rnd.counter;
+    return r;
+}
+
+// probability with which the selector picks this light from `from` (light_selector.art:53,71,88,106; light_hierarchy.art:78-95)
+__device__ __noinline__ float selector_pdf(const float* data, int kind, int n_inf, int n_fin, int infinite, int light_id, float px, float py, float pz) {
+    if (infinite) return 1 / (float)n_inf * 0.5f;
+    float pdf = 1.0f;
+    if (kind == 1) pdf = sel_cdf_get(data, light_id + 1) - sel_cdf_get(data, light_id);
+    else if (n_fin > 1) {
+        const V3 from = v3(px, py, pz);
+        const float* nodes = data + (n_fin + 3) / 4 * 4;
+        uint32_t code = __float_as_uint(__ldg(data + light_id));
+        HEntry entry = sel_h_load(nodes, 0);
+        while (!entry.is_leaf) {
+            const HEntry left = sel_h_load(nodes, entry.id), right = sel_h_load(nodes, entry.id + 1);
+            const float prop = sel_h_left(left, right, from);
+            const bool is_left = (code & 1u) == 0;
+            entry = is_left ? left : right;
+            pdf *= is_left ? prop : 1 - prop;
+            code >>= 1;
+        }
+    }
+    return n_inf == 0 ? pdf : pdf * (1 - 0.5f);
+}
+
+
 // Hit and miss shading of primary-queue record i (gpu_hit_shade / gpu_miss_shade, driver/mapping_gpu.art:123-290;
 // technique/pathtracer.art:40-228). Splats emission / environment contributions (returns how many), appends the
 // shadow ray of the next-event estimate and the continuation ray, if any.
+// The shade kernels are built TWICE and one is picked per launch (api.cu: scene_full / std_aovs): FULL = false has only what
+// the BASELINE configurations use -- diffuse and dielectric BSDFs, environment / point / plane / mesh area lights, the uniform
+// light selector -- FULL = true adds smooth conductors, sphere and spot lights, the cdf and hierarchy selectors and the standard
+// AOVs. The shade phase is instruction-fetch bound: code a scene never executes still costs it when it sits between
+// the instructions it does execute. The reference specialises harder -- it JIT-compiles one shader per material.
+template <bool FULL>
 __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderParams& rp, const PrimaryQueue& q, int i, float* __restrict__ fb, const ShadeSink& sink) {
     int n_splat = 0;
     const float4 o = q.org_tmin[i], d = q.dir_tmax[i];
@@ -305,7 +404,8 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
             ++inflights;
             const C3 emit = c3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));           // env.art:96
             const float pdf_s = 1 / (4 * IGB_FLT_PI);                                // env.art:97
-            const float mis = nee ? 1 / (1 + inv_pdf * pdf_lights * pdf_s) : 1.0f;
+            const float sel_pdf = (!FULL || sc.selector == 0) ? pdf_lights : selector_pdf(sc.selector_data, sc.selector, sc.n_inf, sc.n_fin, 1, l, rorg.x, rorg.y, rorg.z);
+            const float mis = nee ? 1 / (1 + inv_pdf * sel_pdf * pdf_s) : 1.0f;
             color = cadd(color, handle_color(sc, cmulf(cmul(contrib, emit), mis)));
         }
         if (inflights > 0) { splat(fb, pixel, color, rp.inv_spi); ++n_splat; }
@@ -336,7 +436,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
         Rng rnd; rnd.seed = random_seed(sample, iter, rp.frame, pixel % rp.width, pixel / rp.width, rp.seed); rnd.counter = st.y;
 
         // ---- wrap_infobuffer_renderer, technique/internal/infobuffer.art:9-24: Normals / Albedo of the first hit, iteration 0 only
-        if (rp.aov_normals && depth == 1 && iter == 0) {
+        if (FULL && rp.aov_normals && depth == 1 && iter == 0) {
             C3 albedo;
             if (bsdf == 0) albedo = c3(m0.z, m0.w, m1.x);                                                       // diffuse.art:10 (kd)
             else if (bsdf == 1) albedo = c3(lerp1(m1.x, m1.w, 0.5f), lerp1(m1.y, m2.x, 0.5f), lerp1(m1.z, m2.y, 0.5f));   // dielectric.art:35 color_lerp(ks, kt, 0.5)
@@ -357,7 +457,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
                     const PlaneEm e = load_plane(L);
                     const SQ sqv = compute_sq(e, rorg);
                     pdf.value = safe_div(1, sqv.s); pdf.measure = 0;
-                } else if (lt == 4) {   // light/area.art:301-303
+                } else if (FULL && lt == 4) {   // light/area.art:301-303
                     intensity = c3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));
                     pdf.value = safe_div(1, __ldg(L + 9)); pdf.measure = 1;
                 } else {
@@ -367,7 +467,8 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
                     pdf.value = pdfv; pdf.measure = 1;
                 }
                 const float pdf_s = pdf_as_solid(pdf, dt, dist * dist);
-                const float mis = nee ? 1 / (1 + inv_pdf * pdf_lights * pdf_s) : 1.0f;
+                const float sel_pdf = (!FULL || sc.selector == 0) ? pdf_lights : selector_pdf(sc.selector_data, sc.selector, sc.n_inf, sc.n_fin, 0, light_id, rorg.x, rorg.y, rorg.z);
+                const float mis = nee ? 1 / (1 + inv_pdf * sel_pdf * pdf_s) : 1.0f;
                 splat(fb, pixel, handle_color(sc, cmulf(cmul(contrib, intensity), mis)), rp.inv_spi); ++n_splat;
             }
         }
@@ -375,14 +476,19 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
         const V3 out_dir = neg(rdir);
         // ---- on_shadow, pathtracer.art:52-117
         if (nee && bsdf == 0 && n_lights != 0 && !(depth + 1 > sc.max_depth)) {
-            const int id = n_lights <= 1 ? 0 : rnd.next_i32(0, n_lights - 1);            // light_selector.art:18-24
+            int id; float light_select_pdf = pdf_lights;
+            if (!FULL || sc.selector == 0) id = n_lights <= 1 ? 0 : rnd.next_i32(0, n_lights - 1);   // light_selector.art:18-24
+            else {
+                const LightPick pk = selector_sample(sc.selector_data, sc.selector, sc.n_inf, sc.n_fin, rnd.seed, rnd.counter, surf.point.x, surf.point.y, surf.point.z);
+                id = pk.id; light_select_pdf = pk.pdf; rnd.counter = pk.counter;
+            }
             const float* L = id < sc.n_inf ? sc.inf_lights + 32 * id : sc.fin_lights + 32 * (id - sc.n_inf);
             const int lt = __float_as_int(__ldg(L));
-            const LightSample ls = light_sample_direct(sc, L, lt, rnd, surf);
-            const float pdf_l_s = pdf_as_solid(ls.pdf, ls.cos, ls.dist * ls.dist) * pdf_lights;
+            const LightSample ls = light_sample_direct<FULL>(sc, L, lt, rnd, surf);
+            const float pdf_l_s = pdf_as_solid(ls.pdf, ls.cos, ls.dist * ls.dist) * light_select_pdf;
             if (!(pdf_l_s <= IGB_FLT_EPS) && ls.cos > IGB_FLT_EPS) {
                 float mis;
-                if (lt == 1 || lt == 5) mis = 1.0f;   // delta lights
+                if (lt == 1 || (FULL && lt == 5)) mis = 1.0f;   // delta lights
                 else { const float pdf_e_s = positive_cos(ls.dir, N) / IGB_FLT_PI; mis = 1 / (1 + pdf_e_s / pdf_l_s); }
                 const float factor = ls.pdf.value / pdf_l_s;
                 const C3 ev = cmulf(kd, positive_cos(ls.dir, N) * IGB_FLT_INV_PI);     // diffuse.art:3
@@ -406,7 +512,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
                 V3 ld;
                 sample_cosine_hemisphere(u, v, ld, s_pdf);
                 in_dir = m33_mul(surf.local, ld); s_color = kd; s_eta = 1; is_delta = false;
-            } else if (bsdf == 2) {   // conductor.art:2-27: mirror / smooth conductor; p = eta rgb, k rgb, ks rgb, mirror flag
+            } else if (FULL && bsdf == 2) {   // conductor.art:2-27: mirror / smooth conductor; p = eta rgb, k rgb, ks rgb, mirror flag
                 const C3 ks = c3(m2.x, m2.y, m2.z);
                 in_dir = mulf(N, 2 * dot(N, out_dir)) - out_dir;                                                                   // vector.art:124
                 if (m2.w != 0.0f) s_color = ks;

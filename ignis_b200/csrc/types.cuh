@@ -28,6 +28,9 @@ struct DevScene {
     int   max_depth, min_depth;
     float clamp_value;
     int   nee;
+    int   full;               // the launch needs the shade kernels with every feature (shade.cuh shade_record<true>): set per launch by api.cu make_params
+    int   selector;           // light selector: 0 uniform, 1 flux cdf ("simple"), 2 light hierarchy (igb200_technique.light_selector)
+    const float* selector_data;   // light_cdf.bin / light_hierarchy.bin words
     float eye[3], view[9];    // view = columns right, up, dir
     float scale_x, scale_y, cam_tmin, cam_tmax;
 };

@@ -33,7 +33,7 @@ class CameraDesc(C.Structure):
 
 
 class TechniqueDesc(C.Structure):
-    _fields_ = [("max_depth", C.c_int32), ("min_depth", C.c_int32), ("clamp", C.c_float), ("nee", C.c_int32)]
+    _fields_ = [("max_depth", C.c_int32), ("min_depth", C.c_int32), ("clamp", C.c_float), ("nee", C.c_int32), ("light_selector", C.c_int32)]
 
 
 class SceneDesc(C.Structure):
@@ -46,7 +46,8 @@ class SceneDesc(C.Structure):
                 ("infinite_lights", C.c_void_p), ("n_infinite", C.c_int32),
                 ("finite_lights", C.c_void_p), ("n_finite", C.c_int32),
                 ("camera", CameraDesc), ("technique", TechniqueDesc),
-                ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3)]
+                ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3),
+                ("selector_data", C.c_void_p), ("n_selector_data", C.c_int32)]
 
 
 class Settings(C.Structure):
@@ -132,6 +133,9 @@ def make_scene_desc(tables: SceneTables):
     C.memmove(C.byref(d.technique), tables.technique.tobytes(), C.sizeof(TechniqueDesc))
     d.bbox_min[:] = [float(x) for x in tables.bbox_min]
     d.bbox_max[:] = [float(x) for x in tables.bbox_max]
+    sel = np.ascontiguousarray(getattr(tables, "selector_data", np.zeros(0, np.float32)), np.float32)
+    keep.append(sel)
+    d.selector_data, d.n_selector_data = (sel.ctypes.data if sel.size else None), int(sel.size)
     return d, keep
 
 

@@ -55,7 +55,7 @@ def lib():
         L.igbh_compile.argtypes = [C.c_char_p, C.c_char_p]
         L.igbh_describe_material.argtypes = [vp, vp, vp, vp]
         L.igbh_describe_lights.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int), vp, C.POINTER(C.c_int), C.c_int]
-        L.igbh_describe_technique.argtypes = [vp, vp, vp, vp]
+        L.igbh_describe_technique.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
         L.igbh_describe_camera.argtypes = [vp, vp, vp, vp]
         L.igbh_set_destroy.argtypes = [vp]
         for f in ("igbh_set_raygen", "igbh_set_miss", "igbh_set_add_hit"):
@@ -125,8 +125,11 @@ class CompiledStage:
 
     def technique(self, global_params: Params) -> np.ndarray:
         out = np.zeros((), TECHNIQUE_DTYPE)
-        if lib().igbh_describe_technique(self.handle, self.local.h, global_params.h, out.ctypes.data):
+        sel = np.zeros(1 << 16, np.float32)
+        n = C.c_int(0)
+        if lib().igbh_describe_technique(self.handle, self.local.h, global_params.h, out.ctypes.data, sel.ctypes.data, sel.size, C.byref(n)):
             raise DeviceError(_err())
+        self.selector_data = sel[:min(n.value, sel.size)].copy()   # the buffer the cdf / hierarchy light selector reads
         return out
 
     def camera(self, global_params: Params) -> np.ndarray:
@@ -143,7 +146,9 @@ class PluginRuntime:
                  specialization: str = "default", tracer: bool = False, std_aovs: bool = True):
         L = lib()
         self.tables, self.width, self.height, self.spi, self.seed = tables, int(width), int(height), int(spi), seed
-        self.stages = refscript.generate(tables, specialization=specialization, tracer=tracer, std_aovs=std_aovs)
+        import tempfile
+        self._cache = tempfile.TemporaryDirectory(prefix="igb200_cache_")   # the loader's cache directory (exported selector buffers)
+        self.stages = refscript.generate(tables, specialization=specialization, tracer=tracer, std_aovs=std_aovs, cache_dir=self._cache.name)
         # compileShaders (Runtime.cpp:596-668)
         self.global_params = Params(self.stages.global_registry)
         self.raygen = CompiledStage(self.stages.raygen)
@@ -204,6 +209,9 @@ class PluginRuntime:
 
     def close(self):
         L = lib()
+        if getattr(self, "_cache", None):
+            self._cache.cleanup()
+            self._cache = None
         if getattr(self, "dev", None):
             L.igbh_device_destroy(self.dev)
             L.igbh_assign_release(self.keep)

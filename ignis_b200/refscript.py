@@ -215,13 +215,29 @@ def _lights(t: SceneTables, tree: _Tree) -> str:
     return s
 
 
-def _technique(t: SceneTables, std_aovs: bool) -> str:
+def _technique(t: SceneTables, std_aovs: bool, cache_dir: str | None = None) -> str:
     tech = t.technique
     s = ('  let tech_max_depth = registry::get_global_parameter_i32("__tech_max_depth", 8);\n' if int(tech["max_depth"]) >= 2 else f"  let tech_max_depth = {int(tech['max_depth'])}:i32;\n")
     s += ('  let tech_min_depth = registry::get_global_parameter_i32("__tech_min_depth", 2);\n' if int(tech["min_depth"]) >= 2 else f"  let tech_min_depth = {int(tech['min_depth'])}:i32;\n")
     s += ('  let tech_clamp = registry::get_global_parameter_f32("__tech_clamp", 0);\n' if float(tech["clamp"]) > 0 else f"  let tech_clamp = {_stream(tech['clamp'])}:f32;\n")
     s += "  let aovs = @|id:i32| -> AOVImage {\n    match(id) {\n      _ => make_empty_aov_image(0, 0)\n    }\n  };\n"
-    s += "  let light_selector = make_uniform_light_selector(infinite_lights, finite_lights);\n"
+    # LoaderLight.cpp:423-452: the cdf ("simple") and hierarchy selectors read a buffer the loader exports into its cache directory
+    sel = int(tech["light_selector"]) if "light_selector" in tech.dtype.names else 0
+    if sel == 0:
+        s += "  let light_selector = make_uniform_light_selector(infinite_lights, finite_lights);\n"
+    else:
+        if cache_dir is None:
+            raise ValueError("the cdf / hierarchy light selectors need a cache directory for their buffer (LoaderLight.cpp:434,441)")
+        import os
+        name = "light_cdf.bin" if sel == 1 else "light_hierarchy.bin"
+        path = os.path.join(cache_dir, name).replace("\\", "/")
+        if not os.path.exists(path):
+            t.selector_data.astype("<f4").tofile(path)
+        if sel == 1:
+            s += f'  let light_cdf = cdf::make_cdf_1d_from_buffer(device.load_buffer("{path}"), finite_lights.count, 0);\n'
+            s += "  let light_selector = make_cdf_light_selector(infinite_lights, finite_lights, light_cdf);\n"
+        else:
+            s += f'  let light_selector = make_hierarchy_light_selector(infinite_lights, finite_lights, device.load_buffer("{path}"));\n'
     s += f"  let technique = make_path_renderer(tech_max_depth, tech_min_depth, light_selector, aovs, tech_clamp,{'true' if int(tech['nee']) else 'false'});\n"
     s += ("  let full_technique = wrap_infobuffer_renderer(device, settings.iter, spi, technique);\n" if std_aovs else "  let full_technique = technique;\n")
     return s
@@ -260,8 +276,9 @@ def _bsdf(t: SceneTables, mat_id: int, tree: _Tree) -> str:
     return s
 
 
-def generate(t: SceneTables, specialization: str = "default", std_aovs: bool = True, tracer: bool = False) -> StageSet:
-    """The stage scripts + registries of one technique variant for `t`."""
+def generate(t: SceneTables, specialization: str = "default", std_aovs: bool = True, tracer: bool = False, cache_dir: str | None = None) -> StageSet:
+    """The stage scripts + registries of one technique variant for `t`. `cache_dir`: where exported buffers go (the loader's cache
+    directory, src/runtime/loader/LoaderContext.h CacheManager); only needed by the cdf / hierarchy light selectors."""
     g = Registry()
     cam = t.camera
     g.vectors["__camera_eye"] = tuple(float(x) for x in cam["eye"])
@@ -299,7 +316,7 @@ def generate(t: SceneTables, specialization: str = "default", std_aovs: bool = T
     local = Registry()
     tree = _Tree(local, specialization)
     s = STD_LIB_STUB + "#[export] fn ig_miss_shader(settings: &Settings, first: i32, last: i32) -> () {\n" + prologue
-    s += _lights(t, tree) + "\n" + _technique(t, std_aovs) + "\n"
+    s += _lights(t, tree) + "\n" + _technique(t, std_aovs, cache_dir) + "\n"
     s += "  let use_framebuffer = true;\n  device.handle_miss_shader(full_technique, payload_info, first, last, use_framebuffer);\n}\n"
     miss = Stage("ig_miss_shader", s, local)
 
@@ -309,7 +326,7 @@ def generate(t: SceneTables, specialization: str = "default", std_aovs: bool = T
         local = Registry()
         tree = _Tree(local, specialization)
         s = STD_LIB_STUB + "#[export] fn ig_hit_shader(settings: &Settings, mat_id: i32, first: i32, last: i32) -> () {\n" + prologue
-        s += _database(has_sphere) + _lights(t, tree) + "\n" + _bsdf(t, mat_id, tree) + _technique(t, std_aovs) + "\n"
+        s += _database(has_sphere) + _lights(t, tree) + "\n" + _bsdf(t, mat_id, tree) + _technique(t, std_aovs, cache_dir) + "\n"
         s += "  let use_framebuffer = true;\n  device.handle_hit_shader(shader, scene, full_technique, payload_info, first, last, use_framebuffer);\n}\n"
         hits.append(Stage("ig_hit_shader", s, local))
     return StageSet(raygen, miss, hits, g)

@@ -56,10 +56,14 @@ MATERIAL_DTYPE = np.dtype([("bsdf", "<i4"), ("light_id", "<i4"), ("p", "<f4", 14
 LIGHT_DTYPE = np.dtype([("type", "<i4"), ("entity_id", "<i4"), ("p", "<f4", 30)])
 CAMERA_DTYPE = np.dtype([("eye", "<f4", 3), ("dir", "<f4", 3), ("up", "<f4", 3), ("fov", "<f4"),
                          ("fov_vertical", "<i4"), ("aspect", "<f4"), ("tmin", "<f4"), ("tmax", "<f4")])
-TECHNIQUE_DTYPE = np.dtype([("max_depth", "<i4"), ("min_depth", "<i4"), ("clamp", "<f4"), ("nee", "<i4")])
+TECHNIQUE_DTYPE = np.dtype([("max_depth", "<i4"), ("min_depth", "<i4"), ("clamp", "<f4"), ("nee", "<i4"), ("light_selector", "<i4")])
+
+SELECTOR_UNIFORM = 0     # make_uniform_light_selector (light/light_selector.art:26-44)
+SELECTOR_CDF = 1         # "simple": make_cdf_light_selector over the lights' flux (light_selector.art:46-77, LoaderLight.cpp:440-476)
+SELECTOR_HIERARCHY = 2   # make_hierarchy_light_selector (light_selector.art:79-110, light/light_hierarchy.art)
 assert LOOKUP_DTYPE.itemsize == 16 and LEAF_DTYPE.itemsize == 96
 assert MATERIAL_DTYPE.itemsize == 64 and LIGHT_DTYPE.itemsize == 128
-assert CAMERA_DTYPE.itemsize == 56 and TECHNIQUE_DTYPE.itemsize == 16
+assert CAMERA_DTYPE.itemsize == 56 and TECHNIQUE_DTYPE.itemsize == 20
 
 
 class SceneError(RuntimeError):
@@ -84,6 +88,7 @@ class SceneTables:
     film_size: tuple[int, int]
     entity_names: list[str] = field(default_factory=list)
     material_names: list[str] = field(default_factory=list)
+    selector_data: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))   # light_cdf.bin / light_hierarchy.bin as f32 words
     spot_angles: dict = field(default_factory=dict)   # finite light index -> (cutoff, falloff) in degrees (the descriptors hold the cosines)
 
     @property
@@ -364,6 +369,104 @@ def _serialize_trimesh(m: TriMesh, lo: np.ndarray, hi: np.ndarray) -> bytes:
 
 
 # ------------------------------------------------------------------ loader
+def light_cdf(flux) -> np.ndarray:
+    """`light_cdf.bin` of the "simple" selector: CDF::computeForArray (src/runtime/CDF.cpp:14-44) over the lights' flux. The leading
+    0 is not stored: [x1, ..., x(n-1), 1] (core/cdf.art:70-73)."""
+    v = np.asarray(flux, F)
+    cdf = np.zeros(len(v), F)
+    acc = F(0)
+    for i, x in enumerate(v):
+        acc = F(acc + x) if i else F(x)
+        cdf[i] = acc
+    total = cdf[-1]
+    if total > F(1e-5):
+        cdf = (cdf * F(F(1) / total)).astype(F)
+    else:
+        n = F(F(1) / F(len(v)))
+        for x in range(1, len(v)):
+            cdf[x - 1] = F(F(x) * n)
+    cdf[-1] = 1
+    return cdf
+
+
+def light_hierarchy(lights) -> np.ndarray:
+    """`light_hierarchy.bin` (src/runtime/light/LightHierarchy.cpp:47-129): a binary tree over the finite lights' positions, built
+    by inserting them one by one (src/runtime/container/PointBvh.inl:23-96), every node carrying a position, a direction and a
+    flux (negative = no direction). Returns the file's f32 words: codes[round_up(n, 4)] (u32: the left/right turns from the root
+    to the light, LSB first) followed by 8 words per node {pos xyz, flux, dir xyz, id} (id >= 0: light; < 0: -(left child + 1)).
+
+    `lights`: (position, direction or None, flux) per finite light, in table order."""
+    inf = float("inf")
+    nodes = []   # dict(index, lo, hi, mid, axis): axis < 0 = leaf holding light `index`
+
+    def leaf(lo, hi):
+        return dict(index=0, lo=np.array(lo, F), hi=np.array(hi, F), mid=F(0), axis=-1)
+
+    for li, (pos, _, _) in enumerate(lights):
+        p = np.asarray(pos, F)
+        if not nodes:
+            nodes.append(leaf(p, p))
+            continue
+        # descend to the leaf the point falls into, growing every box on the way (getForPointExtend)
+        k = 0
+        while True:
+            nd = nodes[k]
+            nd["lo"], nd["hi"] = np.minimum(nd["lo"], p), np.maximum(nd["hi"], p)
+            if nd["axis"] < 0:
+                break
+            ctr = F((nd["hi"][nd["axis"]] + nd["lo"][nd["axis"]]) / F(2))
+            k = nd["index"] if p[nd["axis"]] < ctr else nd["index"] + 1
+        old = nd["index"]
+        diam = (nd["hi"] - nd["lo"]).astype(F)
+        axis = int(np.argmax(diam))                      # Eigen maxCoeff: first maximum
+        mid = F(diam[axis] / F(2))                       # half the extent (the reference compares the coordinate with this value)
+        left_idx = len(nodes)
+        nd["index"], nd["axis"], nd["mid"] = left_idx, axis, mid
+        off = F((nd["hi"][axis] - nd["lo"][axis]) * F(0.5))
+        lhi = nd["hi"].copy(); lhi[axis] = F(lhi[axis] - off)
+        rlo = nd["lo"].copy(); rlo[axis] = F(rlo[axis] + off)
+        left, right = leaf(nd["lo"], lhi), leaf(rlo, nd["hi"])
+        if p[axis] < mid:
+            left["index"], right["index"] = li, old
+        else:
+            left["index"], right["index"] = old, li
+        nodes += [left, right]
+
+    n = len(lights)
+    entries = np.zeros((len(nodes), 8), F)
+    codes = np.zeros((n + 3) // 4 * 4, np.uint32)
+
+    def populate(k, code, depth):   # populateInnerNodes; returns (dir, signed flux)
+        nd = nodes[k]
+        e = entries[k]
+        if nd["axis"] < 0:
+            pos, d, flux = lights[nd["index"]]
+            e[0:3] = pos
+            e[3] = flux if d is not None else -flux
+            e[4:7] = d if d is not None else (0, 0, 1)
+            e[7:8].view(np.int32)[0] = nd["index"]
+            codes[nd["index"]] = code
+        else:
+            ld, lf = populate(nd["index"], code, depth + 1)
+            rd, rf = populate(nd["index"] + 1, code | (1 << depth), depth + 1)
+            e[0:3] = ((nd["hi"] + nd["lo"]) / F(2)).astype(F)
+            e[7:8].view(np.int32)[0] = -(nd["index"] + 1)
+            if lf < 0 and rf < 0:
+                e[4:7], e[3] = (0, 0, 1), F(lf + rf)
+            elif lf < 0:
+                e[4:7], e[3] = (0, 0, 1), F(-(F(-lf) + rf))
+            elif rf < 0:
+                e[4:7], e[3] = (0, 0, 1), F(-(lf - rf))
+            else:
+                sm = (ld + rd).astype(F)
+                nrm = F(np.sqrt(np.sum(sm * sm, dtype=F)))
+                e[4:7], e[3] = (sm / nrm if nrm > 0 else sm), F(lf + rf)
+        return e[4:7].copy(), F(e[3])
+
+    populate(0, 0, 0)
+    return np.concatenate([codes.view(F), entries.reshape(-1)]).astype(F)
+
+
 def load_scene(path, width: int | None = None, height: int | None = None,
                max_depth: int | None = None, base_dir: str | None = None) -> SceneTables:
     """`path` is a scene file name or an already parsed scene dict (the reference's `loadFromString`)."""
@@ -390,8 +493,6 @@ def load_scene(path, width: int | None = None, height: int | None = None,
     if tech.get("aov_mis", False):
         raise SceneError("aov_mis (advanced shadow handling) is outside the supported path")
     sel = str(tech.get("light_selector", "") or "uniform").lower()
-    if sel not in ("uniform", ""):
-        raise SceneError(f"light_selector '{sel}' is outside the supported path (only 'uniform')")
     technique = np.zeros((), TECHNIQUE_DTYPE)
     technique["max_depth"] = int(max_depth if max_depth is not None else tech.get("max_depth", 64))
     technique["min_depth"] = int(tech.get("min_depth", 2))
@@ -498,6 +599,7 @@ def load_scene(path, width: int | None = None, height: int | None = None,
 
     # ---- lights (LoaderLight.cpp:263-300: infinite and finite lights have separate id spaces)
     inf_l, fin_l = [], []
+    fin_sel = []   # per finite light: (position, direction or None, flux) -- Light::position/direction/computeFlux, for the light selectors
     spot_angles: dict = {}
     fin_of_entity: dict[str, int] = {}
     for lj in lights_json:
@@ -517,6 +619,9 @@ def load_scene(path, width: int | None = None, height: int | None = None,
                 rec["p"][3:6] = (_color(lj["power"], (0, 0, 0)) * F(1.0 / (4 * PI))).astype(F)
             else:
                 rec["p"][3:6] = _color(lj.get("intensity"), (1, 1, 1))
+            # PointLight.cpp:18-31: the cached colour is the power (intensity * 4 pi), flux = its mean
+            flux = float(np.mean(_color(lj["power"], (0, 0, 0)) if "power" in lj else _color(lj.get("intensity"), (1, 1, 1)) * F(4 * PI)))
+            fin_sel.append((rec["p"][0:3].copy(), None, flux))
             fin_l.append(rec)
         elif lt == "spot":
             # SpotLight.cpp:11-20,62-90: cutoff / falloff in degrees; rad(x) = x / 180 * pi in f32 (core/common.art:20); the two
@@ -533,6 +638,10 @@ def load_scene(path, width: int | None = None, height: int | None = None,
             else:
                 rec["p"][8:11] = _color(lj.get("intensity"), (1, 1, 1))
             spot_angles[len(fin_l)] = (float(lj.get("cutoff", 30.0)), float(lj.get("falloff", 20.0)), "power" in lj, _color(lj["power"], (0, 0, 0)) if "power" in lj else None)
+            # SpotLight.cpp:17-39: power_factor = 2 pi (1 - (cos cutoff + cos falloff) / 2)
+            pf = 2 * PI * (1 - 0.5 * (math.cos(math.radians(float(lj.get("cutoff", 30.0)))) + math.cos(math.radians(float(lj.get("falloff", 20.0))))))
+            flux = float(np.mean(_color(lj["power"], (0, 0, 0)) if "power" in lj else _color(lj.get("intensity"), (1, 1, 1)) * F(pf)))
+            fin_sel.append((rec["p"][0:3].copy(), rec["p"][3:6].copy(), flux))
             fin_l.append(rec)
         elif lt == "area":
             ename = lj.get("entity", "")
@@ -553,6 +662,8 @@ def load_scene(path, width: int | None = None, height: int | None = None,
                     rec["p"][0:3] = _color(lj.get("radiance"), (1, 1, 1))
                 rec["p"][3:6], rec["p"][6], rec["p"][7] = org, radius, area
                 fin_of_entity[ename] = len(fin_l)
+                col = _color(lj["power"], (0, 0, 0)) if "power" in lj else _color(lj.get("radiance"), (1, 1, 1)) * F(area * PI)   # AreaLight.cpp:100-113
+                fin_sel.append(((t[:3, :3] @ np.asarray(org, np.float64) + t[:3, 3]).astype(F), None, float(np.mean(col))))
                 fin_l.append(rec)
                 continue
             plane = info["plane"] if lj.get("optimize", True) else None
@@ -568,6 +679,7 @@ def load_scene(path, width: int | None = None, height: int | None = None,
                 rec["p"][12] = area
                 rec["p"][13:21] = plane["texcoords"].reshape(-1)
                 rad_off = 21
+                sel_pos, sel_dir = (origin + xa * F(0.5) + ya * F(0.5)).astype(F), (cr / area).astype(F)   # AreaLight.cpp:69-70
             else:
                 mesh = info["mesh"]
                 d = (info["hi"] - info["lo"]).astype(np.float64)
@@ -578,15 +690,32 @@ def load_scene(path, width: int | None = None, height: int | None = None,
                 area = mesh.compute_area() * (w * h + w * dd + h * dd) / half
                 rec["type"] = LIGHT_SHAPE_AREA
                 rad_off = 0
+                ctr = (info["lo"].astype(np.float64) + info["hi"].astype(np.float64)) / 2
+                sel_pos, sel_dir = (t[:3, :3] @ ctr + t[:3, 3]).astype(F), None                              # AreaLight.cpp:89-90
             rec["entity_id"] = ei["id"]
             if "power" in lj:
                 rec["p"][rad_off:rad_off + 3] = (_color(lj["power"], (0, 0, 0)) * F(1.0 / PI / area)).astype(F)
             else:
                 rec["p"][rad_off:rad_off + 3] = _color(lj.get("radiance"), (1, 1, 1))
             fin_of_entity[ename] = len(fin_l)
+            col = _color(lj["power"], (0, 0, 0)) if "power" in lj else _color(lj.get("radiance"), (1, 1, 1)) * F(area * PI)
+            fin_sel.append((sel_pos, sel_dir, float(np.mean(col))))
             fin_l.append(rec)
         else:
             raise SceneError(f"light type '{lt}' is outside the supported path (SURVEY §8f)")
+
+    # ---- light selector (LoaderLight.cpp:423-452): one light or none -> uniform whatever was asked for
+    selector_data = np.zeros(0, F)
+    if sel in ("uniform", "") or len(inf_l) + len(fin_l) <= 1 or not fin_l:
+        technique["light_selector"] = SELECTOR_UNIFORM
+    elif sel == "simple":
+        technique["light_selector"] = SELECTOR_CDF
+        selector_data = light_cdf([f for _, _, f in fin_sel])
+    elif sel == "hierarchy":
+        technique["light_selector"] = SELECTOR_HIERARCHY
+        selector_data = light_hierarchy(fin_sel)
+    else:
+        technique["light_selector"] = SELECTOR_UNIFORM   # LoaderLight.cpp:448-450: anything else is the uniform selector
 
     # ---- materials
     materials = np.zeros(len(groups), MATERIAL_DTYPE)
@@ -688,4 +817,4 @@ def load_scene(path, width: int | None = None, height: int | None = None,
         entity_per_material=np.asarray([len(g) for g in groups], np.int32), materials=materials,
         infinite_lights=_arr(inf_l), finite_lights=_arr(fin_l), camera=cam, technique=technique,
         bbox_min=bb_lo.astype(F), bbox_max=bb_hi.astype(F), film_size=(fw, fh),
-        entity_names=names, material_names=[f"{b}{'@' + e if e else ''}" for b, e in mat_keys], spot_angles=spot_angles)
+        selector_data=selector_data, entity_names=names, material_names=[f"{b}{'@' + e if e else ''}" for b, e in mat_keys], spot_angles=spot_angles)

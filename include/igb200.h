@@ -91,11 +91,17 @@ typedef struct igb200_camera {
     float   tmin, tmax;   /* near / far clip */
 } igb200_camera;
 
-/* make_path_renderer(max_depth, min_depth, light_selector(uniform), aovs(none), clamp, nee): PathTechnique.cpp:35-79 */
+/* Light selectors (src/artic/light/light_selector.art; chosen by technique.light_selector, LoaderLight.cpp:423-452) */
+#define IGB200_SELECTOR_UNIFORM   0  /* make_uniform_light_selector :26-44 */
+#define IGB200_SELECTOR_CDF       1  /* "simple": make_cdf_light_selector :46-77 over light_cdf.bin (flux CDF, CDF.cpp:14-44) */
+#define IGB200_SELECTOR_HIERARCHY 2  /* make_hierarchy_light_selector :79-110 over light_hierarchy.bin (LightHierarchy.cpp:47-129) */
+
+/* make_path_renderer(max_depth, min_depth, light_selector, aovs, clamp, nee): PathTechnique.cpp:35-79 */
 typedef struct igb200_technique {
     int32_t max_depth, min_depth;
     float   clamp;
     int32_t nee;
+    int32_t light_selector;              /* IGB200_SELECTOR_* */
 } igb200_technique;
 
 /* What IRenderDevice::assignScene receives (SceneDatabase + entity_per_material, IRenderDevice.h:22-28,
@@ -119,6 +125,11 @@ typedef struct igb200_scene_desc {
     igb200_camera              camera;
     igb200_technique           technique;
     float                      bbox_min[3], bbox_max[3]; /* __scene_bbox_lower / upper */
+    /* The buffer the selector's constructor receives (`device.load_buffer(".../light_cdf.bin" | ".../light_hierarchy.bin")`), as
+     * 32-bit words, NULL / 0 for the uniform selector. cdf: n_finite floats [x1 .. x(n-1), 1]. hierarchy: u32 codes[round_up(n_finite, 4)],
+     * then 8 words per tree node {pos xyz, flux (negative: no direction), dir xyz, id (>= 0 light, < 0: -(left child + 1))}. */
+    const float*               selector_data;
+    int32_t                    n_selector_data;
 } igb200_scene_desc;
 
 /* `Settings`, src/artic/driver/settings.art:2-11, filled by the device at src/device/Device.cpp:384-397 */

@@ -282,7 +282,7 @@ struct EntityLeaf { float min[3]; int32_t entity_id; float max[3]; int32_t shape
 struct MaterialDesc { int32_t bsdf, light_id; float p[14]; };
 struct LightDesc { int32_t type, entity_id; float p[30]; };
 struct CameraDesc { float eye[3], dir[3], up[3]; float fov; int32_t fov_vertical; float aspect, tmin, tmax; };
-struct TechniqueDesc { int32_t max_depth, min_depth; float clamp; int32_t nee; };
+struct TechniqueDesc { int32_t max_depth, min_depth; float clamp; int32_t nee; int32_t light_selector; };   // selector: 0 uniform, 1 cdf ("simple"), 2 hierarchy
 struct SceneDesc {
     const float* entities; int32_t n_entities;
     const LookupEntry* shape_lookups; int32_t n_shapes;
@@ -295,6 +295,7 @@ struct SceneDesc {
     CameraDesc camera;
     TechniqueDesc technique;
     float bbox_min[3], bbox_max[3];
+    const float* selector_data; int32_t n_selector_data;   // light_cdf.bin / light_hierarchy.bin as 32-bit words (LoaderLight.cpp:423-476, LightHierarchy.cpp)
 };
 struct Settings { int32_t device, thread_count, spi, frame, iter, width, height, seed; };  // driver/settings.art:2-11
 struct StreamRay { float org[3], dir[3], tmin, tmax; };                                       // traversal/ray.art:2-7
@@ -383,6 +384,7 @@ struct Scene {
     std::vector<LightDesc> inf_lights, fin_lights;
     std::vector<uint8_t> shape_blob;
     CameraDesc camera; TechniqueDesc technique;
+    std::vector<float> selector_data;
     BBox bbox;
     Bvh2 top;   // over leaves
     int num_materials;
@@ -442,6 +444,7 @@ struct Scene {
         inf_lights.assign(d.infinite_lights, d.infinite_lights + d.n_infinite);
         fin_lights.assign(d.finite_lights, d.finite_lights + d.n_finite);
         camera = d.camera; technique = d.technique; num_materials = d.n_materials;
+        if (d.selector_data && d.n_selector_data > 0) selector_data.assign(d.selector_data, d.selector_data + d.n_selector_data);
         bbox = BBox{v3(d.bbox_min[0], d.bbox_min[1], d.bbox_min[2]), v3(d.bbox_max[0], d.bbox_max[1], d.bbox_max[2])};
         std::vector<BBox> lb(leaves.size());
         for (size_t i = 0; i < leaves.size(); ++i) lb[i] = BBox{v3(leaves[i].min[0], leaves[i].min[1], leaves[i].min[2]), v3(leaves[i].max[0], leaves[i].max[1], leaves[i].max[2])};
@@ -881,16 +884,102 @@ struct PathTracer {
     const Scene& sc;
     int max_path_len, min_path_len; float clamp_value; bool enable_nee;
     int n_inf, n_fin, num_lights; float pdf_lights;
+    int selector;   // 0 uniform, 1 cdf, 2 hierarchy
     explicit PathTracer(const Scene& s) : sc(s) {
+        selector = s.technique.light_selector;
         max_path_len = s.technique.max_depth; min_path_len = s.technique.min_depth; clamp_value = s.technique.clamp; enable_nee = s.technique.nee != 0;
         n_inf = (int)s.inf_lights.size(); n_fin = (int)s.fin_lights.size(); num_lights = n_inf + n_fin;
         pdf_lights = num_lights == 0 ? 1.0f : 1 / (float)num_lights;   // light/light_selector.art:26-44
     }
     Color handle_color(Color c) const { return clamp_value > 0 ? csaturate(c, clamp_value) : c; }   // :46-50
-    const LightDesc& select_light(Rng& rnd, float& pdf) const {  // light_selector.art:18-24,32-39
-        const int id = num_lights <= 1 ? 0 : rnd.next_i32(0, num_lights - 1);
-        pdf = pdf_lights;
-        return id < n_inf ? sc.inf_lights[id] : sc.fin_lights[id - n_inf];
+    // ---- light selectors (light/light_selector.art). `from` is the point light is gathered at.
+    // cdf ("simple") selector: core/cdf.art:43-48,70-73, core/interval.art:7-23 over light_cdf.bin = [x1 .. x(n-1), 1]
+    float cdf_get(int i) const { return i == 0 ? 0.0f : sc.selector_data[(size_t)i - 1]; }
+    float cdf_pdf_discrete(int x) const { return cdf_get(x + 1) - cdf_get(x); }
+    int cdf_sample_discrete(float u, float& pdf) const {
+        const int size = n_fin + 1;
+        int first = 0, len = size;
+        while (len > 0) {
+            const int half = len / 2, middle = first + half;
+            if (cdf_get(middle) <= u) { first = middle + 1; len -= half + 1; } else len = half;
+        }
+        const int off = std::min(std::min(std::max(first - 1, 0), size - 1), n_fin - 1);
+        pdf = cdf_pdf_discrete(off);
+        return off;
+    }
+    // hierarchy: light/light_hierarchy.art:13-105 over light_hierarchy.bin = codes[round_up(n, 4)] then 8 words per node
+    struct HEntry { Vec3 pos, dir; float flux; int id; bool has_dir, is_leaf; };
+    HEntry h_load(int id) const {
+        const float* e = sc.selector_data.data() + (size_t)((n_fin + 3) / 4 * 4) + (size_t)id * 8;
+        int32_t index; std::memcpy(&index, e + 7, 4);
+        HEntry h;
+        h.pos = v3(e[0], e[1], e[2]); h.dir = v3(e[4], e[5], e[6]);
+        h.flux = std::fabs(e[3]); h.id = index < 0 ? -index - 1 : index;
+        h.has_dir = !std::signbit(e[3]); h.is_leaf = index >= 0;
+        return h;
+    }
+    static float h_cost(const HEntry& e, Vec3 pos) {
+        const Vec3 cdir = e.pos - pos;
+        const float dist2 = len2(cdir);
+        const float cos_d = e.has_dir ? std::fabs(dot(e.dir, normalize(cdir))) : 1.0f;
+        return safe_div(e.flux * cos_d, dist2);
+    }
+    static float h_left_prop(const HEntry& l, const HEntry& r, Vec3 pos) { const float cl = h_cost(l, pos), cr = h_cost(r, pos); return 1 / (1 + cr / cl); }
+    int h_sample(Rng& rnd, Vec3 pos, float& pdf) const {
+        pdf = 1.0f;
+        HEntry entry = h_load(0);
+        while (!entry.is_leaf) {
+            const HEntry left = h_load(entry.id), right = h_load(entry.id + 1);
+            const float prop = h_left_prop(left, right, pos);
+            const bool is_left = rnd.next_f32() < prop;
+            entry = is_left ? left : right;
+            pdf *= is_left ? prop : 1 - prop;
+        }
+        return entry.id;
+    }
+    float h_pdf(int light_id, Vec3 pos) const {
+        uint32_t code; std::memcpy(&code, sc.selector_data.data() + light_id, 4);
+        float pdf = 1.0f;
+        HEntry entry = h_load(0);
+        while (!entry.is_leaf) {
+            const HEntry left = h_load(entry.id), right = h_load(entry.id + 1);
+            const float prop = h_left_prop(left, right, pos);
+            const bool is_left = (code & 1u) == 0;
+            entry = is_left ? left : right;
+            pdf *= is_left ? prop : 1 - prop;
+            code >>= 1;
+        }
+        return pdf;
+    }
+    int pick_light_id(Rng& rnd, int n) const { return n <= 1 ? 0 : rnd.next_i32(0, n - 1); }   // light_selector.art:18-24
+    // finite part of the cdf / hierarchy selectors
+    int select_finite(Rng& rnd, Vec3 from, float& pdf) const {
+        if (selector == 1) return cdf_sample_discrete(rnd.next_f32(), pdf);
+        if (n_fin == 1) { pdf = 1.0f; return 0; }                                               // light_hierarchy.art:109-113
+        return h_sample(rnd, from, pdf);
+    }
+    float pdf_finite(int light_id, Vec3 from) const {
+        if (selector == 1) return cdf_pdf_discrete(light_id);
+        return n_fin == 1 ? 1.0f : h_pdf(light_id, from);
+    }
+    const LightDesc& select_light(Rng& rnd, Vec3 from, float& pdf) const {
+        if (selector == 0) {                                                                     // light_selector.art:26-44
+            const int id = pick_light_id(rnd, num_lights);
+            pdf = pdf_lights;
+            return id < n_inf ? sc.inf_lights[id] : sc.fin_lights[id - n_inf];
+        }
+        if (n_inf == 0) return sc.fin_lights[select_finite(rnd, from, pdf)];                    // :48-55, :82-90
+        const float q = rnd.next_f32();                                                          // :57-75, :92-108: half the samples go to the infinite lights
+        if (q < 0.5f) { const int id = pick_light_id(rnd, n_inf); pdf = 1 / (float)n_inf * 0.5f; return sc.inf_lights[id]; }
+        const int id = select_finite(rnd, from, pdf);
+        pdf = pdf * (1 - 0.5f);
+        return sc.fin_lights[id];
+    }
+    // probability of having picked this light from `from`
+    float select_pdf(bool infinite, int light_id, Vec3 from) const {
+        if (selector == 0) return pdf_lights;
+        if (infinite) return 1 / (float)n_inf * 0.5f;
+        return n_inf == 0 ? pdf_finite(light_id, from) : pdf_finite(light_id, from) * (1 - 0.5f);
     }
     // :52-117
     bool on_shadow(const ShadingContext& ctx, Rng& rnd, const Payload& payload, const Material& mat, Ray& out_ray, Color& out_color) const {
@@ -899,7 +988,7 @@ struct PathTracer {
         const PTRayPayload pt = unwrap(payload);
         if (pt.depth + 1 > max_path_len) return false;
         float light_select_pdf;
-        const LightDesc& light = select_light(rnd, light_select_pdf);
+        const LightDesc& light = select_light(rnd, ctx.surf.point, light_select_pdf);
         const DirectLightSample ls = light_sample_direct(sc, light, rnd, ctx.surf);
         const float pdf_l_s = ls.pdf.as_solid(ls.cos, ls.dist * ls.dist) * light_select_pdf;
         if (pdf_l_s <= flt_eps) return false;
@@ -942,7 +1031,7 @@ struct PathTracer {
                     pdf = Pdf{pdfv, PDF_AREA};
                 }
                 const float pdf_s = pdf.as_solid(dt, ctx.hit.distance * ctx.hit.distance);
-                const float mis = enable_nee ? 1 / (1 + pt.inv_pdf * pdf_lights * pdf_s) : 1.0f;
+                const float mis = enable_nee ? 1 / (1 + pt.inv_pdf * select_pdf(false, (int)(mat.light - sc.fin_lights.data()), ctx.ray.org) * pdf_s) : 1.0f;
                 out = handle_color(cmulf(cmul(pt.contrib, intensity), mis));
                 return true;
             }
@@ -950,7 +1039,7 @@ struct PathTracer {
         return false;
     }
     // :141-168
-    bool on_miss(const Ray&, const Payload& payload, Color& out) const {
+    bool on_miss(const Ray& ray, const Payload& payload, Color& out) const {
         int inflights = 0;
         Color color = col(0, 0, 0);
         for (int i = 0; i < n_inf; ++i) {
@@ -960,7 +1049,7 @@ struct PathTracer {
                 ++inflights;
                 const Color emit = col(l.p[0], l.p[1], l.p[2]);             // light/env.art:96
                 const float pdf_s = 1 / (4 * flt_pi);                        // light/env.art:97, sampling.art:47-51
-                const float mis = enable_nee ? 1 / (1 + pt.inv_pdf * pdf_lights * pdf_s) : 1.0f;
+                const float mis = enable_nee ? 1 / (1 + pt.inv_pdf * select_pdf(true, i, ray.org) * pdf_s) : 1.0f;
                 color = cadd(color, handle_color(cmulf(cmul(pt.contrib, emit), mis)));
             }
         }

@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     from ignis_b200 import scene
     assert C.sizeof(device.LookupEntry) == 16 == scene.LOOKUP_DTYPE.itemsize
     assert C.sizeof(device.CameraDesc) == 56 == scene.CAMERA_DTYPE.itemsize
-    assert C.sizeof(device.TechniqueDesc) == 16 == scene.TECHNIQUE_DTYPE.itemsize
+    assert C.sizeof(device.TechniqueDesc) == 20 == scene.TECHNIQUE_DTYPE.itemsize
     assert C.sizeof(device.Settings) == 32
     assert device.RAY_DTYPE.itemsize == 32 and device.HIT_DTYPE.itemsize == 20
     assert scene.LEAF_DTYPE.itemsize == 96 and scene.MATERIAL_DTYPE.itemsize == 64 and scene.LIGHT_DTYPE.itemsize == 128

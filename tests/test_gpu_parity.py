@@ -116,6 +116,8 @@ def render_both(tables, w, h, spi, iters, seed=0):
     ("primitives.json", 240, 135, 4, 1),                 # C3 at reduced size
     ("evaluation/cbox-d6.json", 128, 128, 2, 2),
     ("evaluation/multilight-uniform.json", 128, 128, 2, 1),
+    ("evaluation/multilight-simple.json", 128, 128, 2, 2),      # flux-CDF light selector (light_selector.art:46-77)
+    ("evaluation/multilight-hierarchy.json", 128, 128, 2, 2),   # light hierarchy (light/light_hierarchy.art)
     ("evaluation/emissive-plane.json", 128, 128, 1, 1),
     ("evaluation/point.json", 64, 64, 1, 1),
     ("evaluation/sphere-light-pure.json", 128, 128, 2, 2),

@@ -13,6 +13,7 @@ from ignis_b200.scene import load_scene
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "evaluation/cbox-d6.json", "evaluation/multilight-uniform.json",
+          "evaluation/multilight-simple.json", "evaluation/multilight-hierarchy.json",
           "evaluation/emissive-plane.json", "evaluation/point.json", "evaluation/plane-d1.json", "evaluation/sphere-light-pure.json",
           "evaluation/two-planes-mirror.json", "<spot>"]
 
@@ -38,9 +39,9 @@ def test_host_library_exports_plugin_entry_points():
 
 @pytest.mark.parametrize("name", SCENES)
 @pytest.mark.parametrize("mode", ["default", "disable", "force"])
-def test_recognised_descriptors_equal_loader_descriptors(name, mode):
+def test_recognised_descriptors_equal_loader_descriptors(name, mode, tmp_path):
     t = scene(name)
-    st = refscript.generate(t, specialization=mode)
+    st = refscript.generate(t, specialization=mode, cache_dir=str(tmp_path))
     g = plugin.Params(st.global_registry)
     exact = mode != "force"   # `force` prints every value with std::to_string's 6 decimals (ShadingTree.cpp:933-981): lossy by design
     hits = [plugin.CompiledStage(s) for s in st.hits]
@@ -67,6 +68,8 @@ def test_recognised_descriptors_equal_loader_descriptors(name, mode):
                 np.testing.assert_allclose(got["p"], ref["p"], rtol=1e-5, atol=1e-6)
         tech = stage.technique(g)
         assert tech.tobytes() == t.technique.tobytes()
+        # the buffer of the cdf / hierarchy light selector, read from the file the script names
+        np.testing.assert_array_equal(stage.selector_data.view(np.uint32), t.selector_data.view(np.uint32))
     cam = plugin.CompiledStage(st.raygen).camera(g)
     assert cam.tobytes() == t.camera.tobytes()
 
@@ -79,9 +82,12 @@ def test_unknown_constructs_fail_loudly():
     bad = refscript.Stage("ig_hit_shader", st.hits[0].script.replace("make_diffuse_bsdf(ctx.surf,", "make_principled_bsdf(ctx.surf,"), st.hits[0].local)
     with pytest.raises(plugin.DeviceError, match="make_principled_bsdf"):
         plugin.CompiledStage(bad).material(g)
-    # another light selector
-    bad = refscript.Stage("ig_miss_shader", st.miss.script.replace("make_uniform_light_selector(infinite_lights, finite_lights)", 'make_hierarchy_light_selector(infinite_lights, finite_lights, device.load_buffer("x"))'), st.miss.local)
-    with pytest.raises(plugin.DeviceError, match="selector"):
+    # a light selector the device does not implement; a selector whose buffer does not exist
+    bad = refscript.Stage("ig_miss_shader", st.miss.script.replace("make_uniform_light_selector(infinite_lights, finite_lights)", "make_power_light_selector(infinite_lights, finite_lights)"), st.miss.local)
+    with pytest.raises(plugin.DeviceError, match="make_power_light_selector"):
+        plugin.CompiledStage(bad).technique(g)
+    bad = refscript.Stage("ig_miss_shader", st.miss.script.replace("make_uniform_light_selector(infinite_lights, finite_lights)", 'make_hierarchy_light_selector(infinite_lights, finite_lights, device.load_buffer("/nonexistent/light_hierarchy.bin"))'), st.miss.local)
+    with pytest.raises(plugin.DeviceError, match="cannot open"):
         plugin.CompiledStage(bad).technique(g)
     # embedded light tables (>= 10 simple lights) are rejected at compile time
     bad = refscript.Stage("ig_miss_shader", st.miss.script.replace("let finite_lights = LightTable {", "let finite_lights = load_simple_point_lights(12, 0, device); let unused_table = LightTable {"), st.miss.local)
@@ -96,7 +102,8 @@ def test_unknown_constructs_fail_loudly():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,w,h,spi", [("diamond_scene.json", 160, 90, 2), ("primitives.json", 160, 90, 2), ("evaluation/multilight-uniform.json", 96, 96, 2)])
+@pytest.mark.parametrize("name,w,h,spi", [("diamond_scene.json", 160, 90, 2), ("primitives.json", 160, 90, 2), ("evaluation/multilight-uniform.json", 96, 96, 2),
+                                           ("evaluation/multilight-hierarchy.json", 96, 96, 2), ("evaluation/multilight-simple.json", 96, 96, 2)])
 def test_render_through_cpp_plugin_matches_oracle(name, w, h, spi):
     from oracle.oracle import Oracle
     t = scene(name)

@@ -22,6 +22,8 @@ IMAGES = {
     "plane-d1": "ref-plane-d1-4096.exr", "plane-d6": "ref-plane-d6-4096.exr", "point": "ref-point-4096.exr",
     "emissive-plane": "ref-emissive-plane-4096.exr", "cbox-d1": "ref-cbox-d1-4096.exr", "cbox-d6": "ref-cbox-d6-4096.exr",
     "multilight-uniform": "ref-multilight-4096.exr",
+    # the same scene with the other two light selectors (flux CDF, light hierarchy): same expectation, same reference image
+    "multilight-simple": "ref-multilight-4096.exr", "multilight-hierarchy": "ref-multilight-4096.exr",
     # analytic sphere area light. (The only reference image with a pure dielectric, ref-three-planes-dielectric-rad.exr, is a
     # Radiance rendering of a single glass interface; Ignis' own dielectric (bsdf/dielectric.art:15-37) applies no 1/eta^2
     # radiance scaling in the non-adjoint direction, so the reference's algorithm itself does not reproduce that image -- it is
@@ -41,7 +43,7 @@ IMAGES = {
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "primitives_data.json", "flipped_prim.json",
           "meshes/Room.obj", "meshes/Bottom.ply", "meshes/Top.ply", "meshes/Left.ply", "meshes/Right.ply", "meshes/Back.ply", "meshes/Diamond.ply"]
 EVAL = ["plane-base.json", "plane-d1.json", "plane-d6.json", "point.json", "emissive-plane.json", "cbox-base.json", "cbox-d1.json",
-        "cbox-d6.json", "multilight.json", "multilight-uniform.json", "flipped-prim-base.json", "flipped-prim-diffuse.json",
+        "cbox-d6.json", "multilight.json", "multilight-uniform.json", "multilight-simple.json", "multilight-hierarchy.json", "flipped-prim-base.json", "flipped-prim-diffuse.json",
         "sphere-light-base.json", "sphere-light-pure.json", "sphere-light-ico.json", "sphere-light-uv.json", "sphere-light-ico-nopt.json",
         "emissive-plane-nopt.json", "emissive-plane-scale.json", "emissive-plane-scale-nopt.json", "two-planes-base.json", "two-planes-mirror.json", "room.json"]
 
