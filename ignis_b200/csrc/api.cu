@@ -38,11 +38,16 @@ static WaveKernel turn_shade_kernel(int blocks, bool full) {
     if (full) return blocks >= 4 ? k_turn_shade<WF_BLOCK, 4, true> : blocks == 3 ? k_turn_shade<WF_BLOCK, 3, true> : k_turn_shade<WF_BLOCK, 2, true>;
     return blocks >= 4 ? k_turn_shade<WF_BLOCK, 4, false> : blocks == 3 ? k_turn_shade<WF_BLOCK, 3, false> : k_turn_shade<WF_BLOCK, 2, false>;
 }
-static WaveKernel turn_trace_kernel(int blocks, int vote) {
-    if (vote) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2> : k_turn_trace<WF_BLOCK, 2, 2>;
-    return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 0> : k_turn_trace<WF_BLOCK, 2, 0>;
+// where: 1 the whole scene is staged in shared memory (shared-memory loads without range checks: -6 % trace time on diamond_scene
+// and cbox), 0 decided per index (traverse.cuh node_ptr). Specialised for the default scheduling (vote 2) only. An "everything in
+// global memory" variant (2) was measured too: +1 to +2.5 % (more spills), so unstaged scenes use the generic kernel.
+static WaveKernel turn_trace_kernel(int blocks, int vote, int where) {
+    if (vote && where == 1) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 1> : k_turn_trace<WF_BLOCK, 2, 2, 1>;
+    if (vote) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 0> : k_turn_trace<WF_BLOCK, 2, 2, 0>;
+    return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 0, 0> : k_turn_trace<WF_BLOCK, 2, 0, 0>;
 }
-static TraceKernel trace_kernel(int min_blocks, int vote) {
+static TraceKernel trace_kernel(int min_blocks, int vote, int where = 0) {
+    if (vote && where == 1 && min_blocks < 4) return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 2, 1> : k_trace<WF_BLOCK, 2, 2, 1>;   // as turn_trace_kernel
     if (min_blocks >= 4) return vote ? k_trace<WF_BLOCK, 4, 2> : k_trace<WF_BLOCK, 4, 0>;   // 64 registers: stand-alone trace phase only
     if (vote) return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 2> : k_trace<WF_BLOCK, 2, 2>;
     return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 0> : k_trace<WF_BLOCK, 2, 0>;
@@ -124,6 +129,8 @@ struct igb200_ctx {
     int stage_nodes = 0, stage_tris = 0, stage_ent = 0;
     size_t smem_bytes = 0;
     int64_t stage_budget = 40 * 1024;  // bytes of shared memory per CTA for the staged scene copy
+    int stage_where = 0;               // 1: the whole scene is staged in shared memory, 0: not (selects the k_turn_trace variant)
+    int specialise_where = 1;          // option: 0 = always use the generic (per index) trace kernel
     int stage_partial = 0;             // 1: stage the prefix that fits even if the scene does not fit as a whole
     int refill = 24, min_blocks = 2, vote = 2;
     int split_turns = -1;               // leading turns of an iteration run as separate shade / trace launches (0: all in the persistent kernel)
@@ -181,6 +188,8 @@ static int configure_kernels(igb200_ctx* c) {
     c->stage_ent = (int)std::min<int64_t>(s.n_ent, left / 128); left -= (int64_t)c->stage_ent * 128;
     c->stage_nodes = (int)std::min<int64_t>(s.n_nodes, left / 256); left -= (int64_t)c->stage_nodes * 256;
     c->stage_tris = (int)std::min<int64_t>(s.n_tris, left / 48);
+    c->stage_where = (c->stage_ent == s.n_ent && c->stage_nodes == s.n_nodes && c->stage_tris == s.n_tris) ? 1 : 0;
+    if (!c->specialise_where) c->stage_where = 0;
     c->smem_bytes = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)c->stage_ent * 128 + (size_t)c->stage_nodes * 256 + (size_t)c->stage_tris * 48;
     for (int full = 0; full < 2; ++full) CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote, full != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CU(cudaFuncSetAttribute((const void*)trace_kernel(c->min_blocks, c->vote), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
@@ -194,8 +203,8 @@ static int configure_kernels(igb200_ctx* c) {
     if (nb < 1) return fail(-2, "k_wavefront does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
     c->blocks_per_sm = nb;
     // split turn kernels
-    CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote), WF_BLOCK, c->smem_bytes));
+    CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where), WF_BLOCK, c->smem_bytes));
     if (nb < 1) return fail(-2, "k_turn_trace does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
     c->grid_turn_trace = nb * c->n_sm;
     {
@@ -284,7 +293,7 @@ static int launch_split_turns(igb200_ctx* c, const WaveParams& P, int turns) {
         turn_shade_kernel(c->turn_shade_blocks, P.sc.full != 0)<<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
         { const int r = prof_end(c); if (r) return r; }
         { const int r = prof_begin(c, 1); if (r) return r; }
-        turn_trace_kernel(c->turn_trace_blocks, c->vote)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
+        turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
         { const int r = prof_end(c); if (r) return r; }
         { const int r = prof_begin(c, 3); if (r) return r; }
         k_turn_end<<<1, 1, 0, c->stream>>>(P);
@@ -418,6 +427,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
         if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); }
         return 0;
     }
+    if (!strcmp(name, "specialise_where")) { c->specialise_where = value ? 1 : 0; if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); } return 0; }
     if (!strcmp(name, "stage_partial")) { c->stage_partial = value ? 1 : 0; if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); } return 0; }
     if (!strcmp(name, "stage_budget")) {
         if (value < 0 || value > 160 * 1024) return fail(-1, "stage_budget must be in [0, 163840] bytes");
@@ -932,7 +942,7 @@ static int run_trace(igb200_ctx* c, const igb200_ray* d_rays, const uint32_t* d_
     { const int r = ensure_queues(c, n); if (r) return r; }
     if (n > c->capacity) return fail(-1, "igb200_trace_*: %zu rays exceed the queue capacity %zu", n, c->capacity);
     const int tb = c->trace_blocks ? c->trace_blocks : c->min_blocks;
-    const TraceKernel tk = trace_kernel(tb, c->vote);
+    const TraceKernel tk = trace_kernel(tb, c->vote, c->stage_where);
     CU(cudaFuncSetAttribute((const void*)tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     int nb = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)tk, WF_BLOCK, c->smem_bytes));

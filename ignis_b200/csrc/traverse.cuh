@@ -118,13 +118,25 @@ struct Staged {
     const float4* tris;     int n_tris;
     const float4* ent_leaf; int n_ent;
 };
+// WHERE: 0 = per index (a staged prefix, the rest in global memory: generic loads), 1 = the whole scene is staged (shared-memory
+// loads, no range checks), 2 = nothing is staged (global loads). The host stages all or nothing (api.cu configure_kernels), so 1 and
+// 2 are what actually runs; 0 remains for the "stage_partial" option and the kernels that are not specialised.
+template <int WHERE = 0>
 __device__ __forceinline__ const float4* node_ptr(const DevScene& sc, const Staged& sg, int node) {
+    if (WHERE == 1) return sg.nodes + node * 16;
+    if (WHERE == 2) return sc.nodes + (size_t)node * 16;
     return node < sg.n_nodes ? sg.nodes + node * 16 : sc.nodes + (size_t)node * 16;
 }
+template <int WHERE = 0>
 __device__ __forceinline__ const float4* tri_ptr(const DevScene& sc, const Staged& sg, int slot) {
+    if (WHERE == 1) return sg.tris + slot * 3;
+    if (WHERE == 2) return sc.tris + (size_t)slot * 3;
     return slot < sg.n_tris ? sg.tris + slot * 3 : sc.tris + (size_t)slot * 3;
 }
+template <int WHERE = 0>
 __device__ __forceinline__ const float4* leaf_ptr(const DevScene& sc, const Staged& sg, int slot) {
+    if (WHERE == 1) return sg.ent_leaf + slot * 8;
+    if (WHERE == 2) return sc.ent_leaf + (size_t)slot * 8;
     return slot < sg.n_ent ? sg.ent_leaf + slot * 8 : sc.ent_leaf + (size_t)slot * 8;
 }
 
@@ -205,11 +217,12 @@ struct Traversal {
     }
 
     // ---- N: inner node. Eight branch-free slab tests; the nearest hit child becomes `cur`, the others stay pushed.
+    template <int WHERE = 0>
     __device__ __forceinline__ void node_step(const DevScene& sc, const Staged& sg, Stack& st) {
 #ifdef IGB_STEP_STATS
         ++n_node;
 #endif
-        const float4* N = node_ptr(sc, sg, cur - 1);
+        const float4* N = node_ptr<WHERE>(sc, sg, cur - 1);
         // rows of the node: lo_x hi_x lo_y hi_y lo_z hi_z, two float4 each; the octant picks near / far by address
         const int ox = (bits & TB_SX) ? 2 : 0, oy = (bits & TB_SY) ? 2 : 0, oz = (bits & TB_SZ) ? 2 : 0;
         int n = 0, best = 0, best_slot = 0;
@@ -249,11 +262,12 @@ struct Traversal {
     }
 
     // ---- E: top-level leaf = one entity (traversal/mapping_cpu.art:470-500)
+    template <int WHERE = 0>
     __device__ __forceinline__ void entity_step(const DevScene& sc, const Staged& sg, Stack& st) {
 #ifdef IGB_STEP_STATS
         ++n_ent;
 #endif
-        const float4* L = leaf_ptr(sc, sg, (-cur - 1) >> 2);
+        const float4* L = leaf_ptr<WHERE>(sc, sg, (-cur - 1) >> 2);
         const float4 l0 = L[0], l1 = L[1];
         cur = 0;
         const uint32_t eflags = __float_as_uint(l0.w);
@@ -283,7 +297,7 @@ struct Traversal {
             if (cur < 0) {
                 // untransformed shape of <= 4 triangles (walls, area lights): test them right here -- no sentinel to push and
                 // pop, no separate leaf visit, and one visit kind less for the warp to diverge over
-                leaf_step(sc, sg);
+                leaf_step<WHERE>(sc, sg);
                 ent = -1;
                 return;
             }
@@ -296,6 +310,7 @@ struct Traversal {
     }
 
     // ---- L: bottom-level leaf = up to four triangles (shapes/trimesh.art:124-144)
+    template <int WHERE = 0>
     __device__ __forceinline__ void leaf_step(const DevScene& sc, const Staged& sg) {
 #ifdef IGB_STEP_STATS
         ++n_leaf;
@@ -303,7 +318,7 @@ struct Traversal {
         const int r = -cur - 1;
         const int first = r >> 2, cnt = (r & 3) + 1;
         cur = 0;
-        if (first + cnt <= sg.n_tris) {   // leaf staged in shared memory
+        if (WHERE == 1 || (WHERE == 0 && first + cnt <= sg.n_tris)) {   // leaf staged in shared memory
             for (int j = 0; j < cnt; ++j) {
                 const float4* T = sg.tris + (first + j) * 3;
                 const float4 a = T[0], b = T[1], c = T[2];
@@ -317,12 +332,12 @@ struct Traversal {
         }
         // geometry read through L2: one triangle of look-ahead, so that the next triangle's three loads are in flight while this
         // one is tested (else a leaf costs up to four dependent round trips; synthetic_room: -6 % trace time)
-        const float4* T = tri_ptr(sc, sg, first);
+        const float4* T = tri_ptr<WHERE>(sc, sg, first);
         float4 a = T[0], b = T[1], c = T[2];
 #pragma unroll 1
         for (int j = 0; j < cnt; ++j) {
             float4 na = a, nb = b, nc = c;
-            if (j + 1 < cnt) { const float4* Tn = tri_ptr(sc, sg, first + j + 1); na = Tn[0]; nb = Tn[1]; nc = Tn[2]; }
+            if (j + 1 < cnt) { const float4* Tn = tri_ptr<WHERE>(sc, sg, first + j + 1); na = Tn[0]; nb = Tn[1]; nc = Tn[2]; }
             float t, u, v;
             if (intersect_tri(org, dir, tmin, tmax, a, b, c, t, u, v)) {
                 const int prim = __ldg(sc.tri_prim + first + j);
@@ -335,11 +350,12 @@ struct Traversal {
     // One turn of the pipeline P -> N -> E -> L: a lane performs every visit its state allows, in that order, so that
     // a fresh ray does root node, entity and triangle leaf in one turn and lanes of a warp stay aligned.
     // Returns true when the traversal is finished (hit holds the result).
+    template <int WHERE = 0>
     __device__ __forceinline__ bool turn(const DevScene& sc, const Staged& sg, Stack& st, const float4* po, const float4* pd) {
         if (cur == 0 && pop_step(st, po, pd)) return true;
-        if (cur > 0) node_step(sc, sg, st);
-        if (cur < 0 && ent < 0) entity_step(sc, sg, st);
-        if (cur < 0 && ent >= 0) leaf_step(sc, sg);
+        if (cur > 0) node_step<WHERE>(sc, sg, st);
+        if (cur < 0 && ent < 0) entity_step<WHERE>(sc, sg, st);
+        if (cur < 0 && ent >= 0) leaf_step<WHERE>(sc, sg);
         return (bits & TB_DONE) != 0;
     }
 
@@ -347,6 +363,7 @@ struct Traversal {
     // kind wanted by at least half as many lanes as the most wanted) runs, lanes waiting for another kind keep their
     // state. The kinds then run 2-3x wider than when all three sections execute back to back for whoever needs them.
     // Must be called by all 32 lanes; `active` false lanes only vote. Returns true when this lane's traversal finished.
+    template <int WHERE = 0>
     __device__ __forceinline__ bool turn_vote(const DevScene& sc, const Staged& sg, Stack& st, const float4* po, const float4* pd, bool active, int vote) {
         bool fin = false;
         if (active && cur == 0) fin = pop_step(st, po, pd);
@@ -355,9 +372,9 @@ struct Traversal {
         const int nN = __popc(__ballot_sync(0xffffffffu, wN)), nE = __popc(__ballot_sync(0xffffffffu, wE)), nL = __popc(__ballot_sync(0xffffffffu, wL));
         const int mx = max(nN, max(nE, nL));
         const int need = vote >= 2 ? max(1, (mx + 1) >> 1) : max(1, mx);
-        if (nN >= need) { if (wN) node_step(sc, sg, st); }
-        if (nE >= need) { if (cur < 0 && ent < 0 && live) entity_step(sc, sg, st); }
-        if (nL >= need) { if (cur < 0 && ent >= 0 && live) leaf_step(sc, sg); }
+        if (nN >= need) { if (wN) node_step<WHERE>(sc, sg, st); }
+        if (nE >= need) { if (cur < 0 && ent < 0 && live) entity_step<WHERE>(sc, sg, st); }
+        if (nL >= need) { if (cur < 0 && ent >= 0 && live) leaf_step<WHERE>(sc, sg); }
         return fin || (live && (bits & TB_DONE) != 0);
     }
 };

@@ -79,7 +79,7 @@ def test_closest_hit_records_match_oracle(scene, w, h):
     # both walks of the device: one lane per ray (large queues) and eight lanes per ray (small queues, traverse.cuh trace_wide);
     # with the scene copy in shared memory when it fits (the default), with nothing staged, and with a staged prefix (nodes and
     # triangles partly in shared memory, partly read through L1/L2) -- the closest hit must not depend on any of it
-    for wide, opts in ((0, {}), (1 << 20, {}), (0, {"stage_budget": 0}), (1 << 20, {"stage_budget": 0}),
+    for wide, opts in ((0, {}), (1 << 20, {}), (0, {"specialise_where": 0}), (0, {"stage_budget": 0}), (1 << 20, {"stage_budget": 0}),
                        (0, {"stage_partial": 1, "stage_budget": 6144}), (1 << 20, {"stage_partial": 1, "stage_budget": 6144})):
         budget = tuple(opts.items())
         with B200Device() as dev:
