@@ -9,7 +9,7 @@ own harness (scripts/Benchmark.py). Mrays/s = (camera + bounce + shadow rays) / 
     python bench.py [--gpus N] [--steps K] [--warmup W]            this repository's CUDA device
     python bench.py --impl reference [...]                         CPU restatement of the reference's CPU device
 
-For N > 1 it is launched by torchrun (one rank per GPU): the framebuffer is split into 32x32 tiles dealt round-robin
+For N > 1 it is launched by torchrun (one rank per GPU): the framebuffer is split into 32x32 tiles dealt in rotating round-robin order
 to the ranks (scene replicated, no data-path collective), and the accumulation buffers are summed onto rank 0 with
 one NCCL reduce at the end of the K steps (inside the timed region). Total work is fixed => "scaling": "strong".
 
@@ -185,7 +185,7 @@ def workload_config(args, world):
     return {"workload": f"{SCENE} {args.width}x{args.height}, path integrator max_depth 64, spi {args.spi}, seed 0; 1 step = 1 render() iteration "
                         f"({args.spi} spp, {args.width * args.height * args.spi} camera rays); 16 steps = 64 spp (BASELINE.json configs[1])",
             "spi": args.spi, "width": args.width, "height": args.height,
-            "parallelism": f"framebuffer tiles 32x32 round-robin over {world} GPU(s), scene replicated, one NCCL reduce of the accumulation buffer",
+            "parallelism": f"framebuffer tiles 32x32 in rotating round-robin order over {world} GPU(s), scene replicated, one NCCL reduce of the accumulation buffer",
             "l2": "no flush needed: every step streams its ray queues through HBM (> 800 MB per step per GPU at N=1, L2 is 126 MB)"}
 
 
@@ -334,7 +334,7 @@ def run_b200(args):
                                  "what": f"whole wavefront step per GPU: {B_PRIMARY} B x primary + {B_SHADOW} B x shadow + {B_SPLAT} B x splat (SURVEY.md 8d), peak {peak_src}"}
         line["roofline"] = dict(line["roofline_step"], kernel="whole step, all kernels (per-kernel figures are measured at N = 1)")
         if kt is not None:
-            # Dominant kernel of the step: k_turn_trace<256,3,2>, the trace phase of the split turns. Algorithmic bytes of a launch
+            # Dominant kernel of the step: k_turn_trace<256,3,2,1>, the trace phase of the split turns. Algorithmic bytes of a launch
             # (trace share): 40 B ray read + 20 B hit write per primary ray, 52 B per shadow ray, 24 B per splat.
             kern = prof["kernels"]
             total_ms = sum(v["ms"] for v in kern.values()) or 1.0
@@ -344,7 +344,7 @@ def run_b200(args):
             kbytes = (B_STAGE["traverse_primary"] * w_["primary"] + B_STAGE["traverse_secondary"] * w_["shadow"] + B_SPLAT * w_["splats"]) / n_l
             ach = kbytes / (avg_ms * 1e-3) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES,
-                                "kernel": "k_turn_trace<256,3,2> (closest-hit + any-hit/splat phase of a split wavefront turn)",
+                                "kernel": "k_turn_trace<256,3,2,1> (scene staged in shared memory; closest-hit + any-hit/splat phase of a split wavefront turn)",
                                 "avg_launch_ms": avg_ms, "launches": n_l, "share_of_step": kern["k_turn_trace"]["ms"] / total_ms,
                                 "algorithmic_bytes_per_launch": kbytes, "rays_per_launch": (w_["primary"] + w_["shadow"]) / n_l,
                                 "peak_source": peak_src, "traffic_source": NCU_TRAFFIC_SOURCE,

@@ -37,12 +37,16 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     global OUT
+    if os.environ.get("IGB200_EXPERIMENT"):   # kernel experiments: -DIGB_EXP_<name>, separate binary (tools/tune.py)
+        OUT = os.path.join(HERE, "libigb200_exp_%s.so" % os.environ["IGB200_EXPERIMENT"])
+        force = force or not os.path.exists(OUT)
     if os.environ.get("IGB200_STEP_STATS"):   # diagnostics build: counts BVH visits per ray (slow), separate binary
         OUT = os.path.join(HERE, "libigb200_stats.so")
         force = force or not os.path.exists(OUT)
     if not force and not needs_build():
         return OUT
-    extra = (["-Xptxas", "-v"] if verbose else []) + (["-DIGB_STEP_STATS"] if os.environ.get("IGB200_STEP_STATS") else [])
+    extra = (["-Xptxas", "-v"] if verbose else []) + (["-DIGB_STEP_STATS"] if os.environ.get("IGB200_STEP_STATS") else []) + \
+            (["-DIGB_EXP_" + x for x in os.environ["IGB200_EXPERIMENT"].split("_")] if os.environ.get("IGB200_EXPERIMENT") else [])
     cmd = [nvcc_path(), *flags(extra), "-shared", "-o", OUT,
            *[os.path.join(SRC, s) for s in SOURCES]]
     r = subprocess.run(cmd, capture_output=True, text=True)
