@@ -205,6 +205,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner would otherwise precede the JSON line on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w, h, spi = args.width, args.height, args.spi

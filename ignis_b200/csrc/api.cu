@@ -473,7 +473,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     for (int m = 0; m < d->n_materials; ++m)
         if (d->materials[m].bsdf < IGB200_BSDF_DIFFUSE || d->materials[m].bsdf > IGB200_BSDF_CONDUCTOR) return fail(-4, "igb200_set_scene: material %d has unsupported bsdf %d", m, d->materials[m].bsdf);
     for (int l = 0; l < d->n_infinite; ++l)
-        if (d->infinite_lights[l].type != IGB200_LIGHT_ENV_CONST) return fail(-4, "igb200_set_scene: infinite light %d has unsupported type %d", l, d->infinite_lights[l].type);
+        if (d->infinite_lights[l].type != IGB200_LIGHT_ENV_CONST && d->infinite_lights[l].type != IGB200_LIGHT_SUN && d->infinite_lights[l].type != IGB200_LIGHT_DIRECTIONAL) return fail(-4, "igb200_set_scene: infinite light %d has unsupported type %d", l, d->infinite_lights[l].type);
     for (int l = 0; l < d->n_finite; ++l) {
         const int t = d->finite_lights[l].type;
         if (t != IGB200_LIGHT_POINT && t != IGB200_LIGHT_PLANE_AREA && t != IGB200_LIGHT_SHAPE_AREA && t != IGB200_LIGHT_SPHERE_AREA && t != IGB200_LIGHT_SPOT) return fail(-4, "igb200_set_scene: finite light %d has unsupported type %d", l, t);
@@ -658,6 +658,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     c->scene_full = s.selector != IGB200_SELECTOR_UNIFORM;
     for (int m = 0; m < d->n_materials; ++m) c->scene_full |= d->materials[m].bsdf == IGB200_BSDF_CONDUCTOR;
     for (int l = 0; l < d->n_finite; ++l) c->scene_full |= d->finite_lights[l].type == IGB200_LIGHT_SPHERE_AREA || d->finite_lights[l].type == IGB200_LIGHT_SPOT;
+    for (int l = 0; l < d->n_infinite; ++l) c->scene_full |= d->infinite_lights[l].type != IGB200_LIGHT_ENV_CONST;
     s.full = c->scene_full ? 1 : 0;
     s.max_depth = d->technique.max_depth; s.min_depth = d->technique.min_depth; s.clamp_value = d->technique.clamp; s.nee = d->technique.nee;
     c->desc = *d;

@@ -382,6 +382,14 @@ struct Eval {
         if (fn == "color_mul") return arith('*', vec_arg(fn, a, 0), vec_arg(fn, a, 1));
         if (fn == "make_constant_texture") return vec_arg(fn, a, 0);   // texture/constant: the colour itself on this path
         if (fn == "maybe_unused") return Val::num(0);
+        if (fn == "vec3_normalize") {   // core/vector.art; the length in double, rounded once, then three f32 divisions (scene.py normalize_f32)
+            Val v = vec_arg(fn, a, 0);
+            const float len = (float)std::sqrt((double)v.f[0] * v.f[0] + (double)v.f[1] * v.f[1] + (double)v.f[2] * v.f[2]);
+            for (int i = 0; i < 3; ++i) v.f[i] = v.f[i] / len;
+            return v;
+        }
+        if (fn == "math_builtins::cos") { Val v = Val::num((float)std::cos((double)num_arg(fn, a, 0))); v.known = a[0].known; return v; }
+        if (fn == "sun_area_from_srad") { const float r = num_arg(fn, a, 0); Val v = Val::num(3.14159265359f * r * r); v.known = a[0].known; return v; }   // light/sun.art:5
         if (fn == "rad") { Val v = Val::num(num_arg(fn, a, 0) / 180 * 3.14159265359f); v.known = a[0].known; return v; }   // core/common.art:20
         if (fn == "spot_from_power") {   // light/spot.art:1-6; the cosines as in resolve_light
             const float cc = (float)std::cos((double)num_arg(fn, a, 1)), cf = (float)std::cos((double)num_arg(fn, a, 2));
@@ -477,6 +485,16 @@ static igb200_light resolve_light(Eval& ev, const std::string& binding) {
         const Val c = Eval::arith('*', as_vec(ctor_arg(l, 2), "environment scale"), as_vec(ctor_arg(l, 3), "environment radiance"));
         out.type = IGB200_LIGHT_ENV_CONST;
         put3(out.p, c);
+    } else if (l.name == "make_sun_light") {        // SunLight.cpp:28-57; light/sun.art:10-48
+        if (as_num(ctor_arg(l, 5), "sun handle_as_delta flag") != 0) fail("a sun light handled as a delta light is not supported");
+        out.type = IGB200_LIGHT_SUN;
+        put3(out.p, as_vec(ctor_arg(l, 1), "sun direction"));
+        out.p[3] = as_num(ctor_arg(l, 3), "cosine of the sun's half angle");
+        put3(out.p + 4, as_vec(ctor_arg(l, 4), "sun radiance"));
+    } else if (l.name == "make_directional_light") { // DirectionalLight.cpp:25-41; light/directional.art:1-17
+        out.type = IGB200_LIGHT_DIRECTIONAL;
+        put3(out.p, as_vec(ctor_arg(l, 1), "light direction"));
+        put3(out.p + 3, as_vec(ctor_arg(l, 3), "irradiance"));
     } else if (l.name == "make_point_light") {      // PointLight.cpp:44-62
         out.type = IGB200_LIGHT_POINT;
         put3(out.p, as_vec(ctor_arg(l, 1), "point light origin"));

@@ -185,6 +185,16 @@ __device__ __forceinline__ void sphere_emitter_sample(const DevScene& sc, const 
     }
 }
 
+// core/warp.art:2-22
+__device__ __forceinline__ void square_to_concentric_disk(float px, float py, float& x, float& y) {
+    const float a = 2 * px - 1, b = 2 * py - 1;
+    if (a == 0 && b == 0) { x = 0; y = 0; return; }
+    float sn, cs;
+    if (a * a > b * b) { const float phi = (IGB_FLT_PI / 4) * safe_div(b, a); dm_sincosf(phi, &sn, &cs); x = cs * a; y = sn * a; }
+    else { const float phi = (IGB_FLT_PI / 2) - (IGB_FLT_PI / 4) * safe_div(a, b); dm_sincosf(phi, &sn, &cs); x = cs * b; y = sn * b; }
+}
+__device__ __forceinline__ float uniform_cone_pdf(float cos_angle) { return safe_div(1, 2 * IGB_FLT_PI * (1 - cos_angle)); }   // core/sampling.art:106
+
 // FULL: see shade_record
 template <bool FULL>
 __device__ __forceinline__ LightSample light_sample_direct(const DevScene& sc, const float* L, int type, Rng& rnd, const Surf& from) {
@@ -203,6 +213,25 @@ __device__ __forceinline__ LightSample light_sample_direct(const DevScene& sc, c
         o.pos = pos; o.dir = mulf(d_, safe_div(1, dist));
         o.intensity = c3(__ldg(L + 5), __ldg(L + 6), __ldg(L + 7));
         o.pdf.value = 1; o.pdf.measure = 1; o.cos = 1; o.dist = dist;
+    } else if (FULL && type == 6) {   // light/sun.art:22-26; p = direction towards the sun, cos(half angle), radiance
+        const float cos_angle = __ldg(L + 5);
+        const M33 frame = make_orthonormal(neg(v3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4))));
+        const float u = rnd.next_f32(); const float v = rnd.next_f32();
+        const float c1 = 1 - cos_angle;                                                    // sample_uniform_cone, core/sampling.art:109-116
+        float px, py; square_to_concentric_disk(u, v, px, py);
+        const float n2 = px * px + py * py;
+        const float z = cos_angle + c1 * (1 - n2);
+        const float f = sqrtf(fmaxf(0.0f, c1 * (2 - c1 * n2)));
+        const V3 ndir = m33_mul(frame, v3(px * f, py * f, z));
+        const float inv_pdf = 2 * IGB_FLT_PI * (1 - cos_angle);
+        o.pos = v3(0, 0, 0); o.dir = neg(ndir);
+        o.intensity = cmulf(c3(__ldg(L + 6), __ldg(L + 7), __ldg(L + 8)), inv_pdf);
+        o.pdf.value = uniform_cone_pdf(cos_angle); o.pdf.measure = 0; o.cos = z; o.dist = __int_as_float(0x7f800000);
+    } else if (FULL && type == 7) {   // light/directional.art:6; p = direction the light travels, irradiance
+        const V3 dir = v3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));
+        o.pos = from.point + mulf(dir, -sc.scene_radius); o.dir = neg(dir);
+        o.intensity = c3(__ldg(L + 5), __ldg(L + 6), __ldg(L + 7));
+        o.pdf.value = 1; o.pdf.measure = 2; o.cos = 1; o.dist = sc.scene_radius;
     } else if (FULL && type == 5) {   // light/spot.art:8-44
         const V3 pos = v3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4)), sdir = v3(__ldg(L + 5), __ldg(L + 6), __ldg(L + 7));
         const float cos_cutoff = __ldg(L + 8), cos_falloff = __ldg(L + 9);
@@ -401,9 +430,17 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
         int inflights = 0; C3 color = c3(0, 0, 0);
         for (int l = 0; l < sc.n_inf; ++l) {
             const float* L = sc.inf_lights + 32 * l;
+            C3 emit; float pdf_s;
+            if (FULL && __float_as_int(__ldg(L)) != 0) {
+                if (__float_as_int(__ldg(L)) == 7) continue;                          // delta lights are not seen by rays (pathtracer.art:149)
+                const bool hit = dot(v3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4)), rdir) >= __ldg(L + 5);   // sun.art:18,33-45
+                emit = hit ? c3(__ldg(L + 6), __ldg(L + 7), __ldg(L + 8)) : c3(0, 0, 0);
+                pdf_s = hit ? uniform_cone_pdf(__ldg(L + 5)) : 0.0f;
+            } else {
+                emit = c3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));                 // env.art:96
+                pdf_s = 1 / (4 * IGB_FLT_PI);                                        // env.art:97
+            }
             ++inflights;
-            const C3 emit = c3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4));           // env.art:96
-            const float pdf_s = 1 / (4 * IGB_FLT_PI);                                // env.art:97
             const float sel_pdf = (!FULL || sc.selector == 0) ? pdf_lights : selector_pdf(sc.selector_data, sc.selector, sc.n_inf, sc.n_fin, 1, l, rorg.x, rorg.y, rorg.z);
             const float mis = nee ? 1 / (1 + inv_pdf * sel_pdf * pdf_s) : 1.0f;
             color = cadd(color, handle_color(sc, cmulf(cmul(contrib, emit), mis)));
@@ -488,14 +525,14 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
             const float pdf_l_s = pdf_as_solid(ls.pdf, ls.cos, ls.dist * ls.dist) * light_select_pdf;
             if (!(pdf_l_s <= IGB_FLT_EPS) && ls.cos > IGB_FLT_EPS) {
                 float mis;
-                if (lt == 1 || (FULL && lt == 5)) mis = 1.0f;   // delta lights
+                if (lt == 1 || (FULL && (lt == 5 || lt == 7))) mis = 1.0f;   // delta lights
                 else { const float pdf_e_s = positive_cos(ls.dir, N) / IGB_FLT_PI; mis = 1 / (1 + pdf_e_s / pdf_l_s); }
                 const float factor = ls.pdf.value / pdf_l_s;
                 const C3 ev = cmulf(kd, positive_cos(ls.dir, N) * IGB_FLT_INV_PI);     // diffuse.art:3
                 const C3 cc = handle_color(sc, cmulf(cmul(ls.intensity, cmul(contrib, ev)), mis * factor));
                 if (!((cc.r + cc.g + cc.b) / 3 <= IGB_FLT_EPS)) {
                     V3 s_dir; float s_tmax;
-                    if (lt == 0) { s_dir = ls.dir; s_tmax = IGB_FLT_MAX; }
+                    if (lt == 0 || (FULL && (lt == 6 || lt == 7))) { s_dir = ls.dir; s_tmax = IGB_FLT_MAX; }   // infinite lights
                     else { s_dir = ls.pos - surf.point; s_tmax = 1 - 0.001f; }
                     const int ss = coalesced_append(sink.shadow_count);
                     sink.sq.org_tmin[ss] = make_float4(surf.point.x, surf.point.y, surf.point.z, 0.001f);

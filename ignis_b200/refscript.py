@@ -148,8 +148,22 @@ def _lights(t: SceneTables, tree: _Tree) -> str:
             'registry::get_global_parameter_vec3("__scene_bbox_upper", vec3_expand(0)))')
     inf_names, fin_names = [], []
     for i, l in enumerate(t.infinite_lights):
-        assert int(l["type"]) == LIGHT_ENV_CONST
         cid = tree.closure(f"__inf_light_{i}")
+        if int(l["type"]) in (6, 7):   # SunLight.cpp:28-57, DirectionalLight.cpp:25-41 (the scene box is the shader's `scene_bbox`, LoaderUtils.cpp:10-19)
+            raw_dir, angle, use_radiance, colour = t.sun_params[i]
+            if int(l["type"]) == 6:
+                col = tree.color(cid, "radiance" if use_radiance else "irradiance", colour)
+                ang = tree.number(cid, "angle", angle)
+                direction = tree.vector(cid, "direction", raw_dir)
+                rad = col if use_radiance else f"color_mulf({col}, 1 / sun_area_from_srad(rad({ang}/2)))"
+                s += tree.pull_header() + f"  let light_{cid} = make_sun_light({i}, vec3_normalize({direction}), scene_bbox, math_builtins::cos(rad({ang}/2)), {rad}, false);\n"
+            else:
+                col = tree.color(cid, "irradiance", colour)
+                direction = tree.vector(cid, "direction", raw_dir)
+                s += tree.pull_header() + f"  let light_{cid} = make_directional_light({i}, vec3_normalize({direction}), scene_bbox, {col});\n"
+            inf_names.append(f"light_{cid}")
+            continue
+        assert int(l["type"]) == LIGHT_ENV_CONST
         scale = tree.color(cid, "scale", (1, 1, 1))
         rad = "make_constant_texture(" + tree.color(cid, "radiance", l["p"][0:3]) + ")"
         ident = "make_mat3x3(make_vec3(1.000000, 0.000000, 0.000000),make_vec3(0.000000, 1.000000, 0.000000),make_vec3(0.000000, 0.000000, 1.000000))"

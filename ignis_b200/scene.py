@@ -48,6 +48,8 @@ LIGHT_PLANE_AREA = 2  # make_area_light + make_plane_area_emitter (light/area.ar
 LIGHT_SHAPE_AREA = 3  # make_area_light + make_shape_area_emitter (light/area.art:62-107)
 LIGHT_SPHERE_AREA = 4  # make_area_light + make_sphere_area_emitter (light/area.art:260-316)
 LIGHT_SPOT = 5         # make_spot_light (light/spot.art:8-44)
+LIGHT_SUN = 6          # make_sun_light (light/sun.art:10-48): infinite, p = direction towards the sun, cos(angle / 2), radiance
+LIGHT_DIRECTIONAL = 7  # make_directional_light (light/directional.art): infinite delta light, p = direction of travel, irradiance
 
 LOOKUP_DTYPE = np.dtype([("type_id", "<u4"), ("flags", "<u4"), ("offset", "<u8")])
 LEAF_DTYPE = np.dtype([("min", "<f4", 3), ("entity_id", "<i4"), ("max", "<f4", 3), ("shape_id", "<i4"),
@@ -89,6 +91,7 @@ class SceneTables:
     entity_names: list[str] = field(default_factory=list)
     material_names: list[str] = field(default_factory=list)
     selector_data: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))   # light_cdf.bin / light_hierarchy.bin as f32 words
+    sun_params: dict = field(default_factory=dict)    # infinite light index -> (direction before vec3_normalize, angle in degrees, radiance given?, colour as given)
     spot_angles: dict = field(default_factory=dict)   # finite light index -> (cutoff, falloff) in degrees (the descriptors hold the cosines)
 
     @property
@@ -369,6 +372,29 @@ def _serialize_trimesh(m: TriMesh, lo: np.ndarray, hi: np.ndarray) -> bytes:
 
 
 # ------------------------------------------------------------------ loader
+def light_direction(lj) -> np.ndarray:
+    """LoaderUtils::getDirection (src/runtime/loader/LoaderUtils.cpp:89-106, skysun/ElevationAzimuth.h:15-30): `direction` (or
+    `sun_direction`) goes through elevation / azimuth and back (y up), else `elevation` / `azimuth` are used as given (radians)."""
+    if "direction" in lj or "sun_direction" in lj:
+        d = np.asarray(lj.get("direction", lj.get("sun_direction")), np.float64)
+        d = (d / np.linalg.norm(d)).astype(F)
+        theta = F(math.acos(float(d[1])))
+        phi = F(math.atan2(-float(d[0]), -float(d[2])))
+        elev, azim = F(F(math.pi / 2) - theta), (F(phi + F(2 * math.pi)) if phi < 0 else phi)
+    elif "elevation" in lj or "azimuth" in lj:
+        elev, azim = F(lj.get("elevation", 0)), F(lj.get("azimuth", 0))
+    else:
+        raise SceneError("sun position from time and location is outside the supported path")
+    se, ce, sa, ca = (F(f(float(x))) for f, x in ((math.sin, elev), (math.cos, elev), (math.sin, azim), (math.cos, azim)))
+    return np.array([-ce * sa, se, -ce * ca], F)
+
+
+def normalize_f32(v) -> np.ndarray:
+    """vec3_normalize as the C++ recogniser evaluates it: the length in double, rounded once, then three f32 divisions."""
+    v = np.asarray(v, F)
+    return (v / F(math.sqrt(float(v[0]) ** 2 + float(v[1]) ** 2 + float(v[2]) ** 2))).astype(F)
+
+
 def light_cdf(flux) -> np.ndarray:
     """`light_cdf.bin` of the "simple" selector: CDF::computeForArray (src/runtime/CDF.cpp:14-44) over the lights' flux. The leading
     0 is not stored: [x1, ..., x(n-1), 1] (core/cdf.art:70-73)."""
@@ -601,6 +627,7 @@ def load_scene(path, width: int | None = None, height: int | None = None,
     inf_l, fin_l = [], []
     fin_sel = []   # per finite light: (position, direction or None, flux) -- Light::position/direction/computeFlux, for the light selectors
     spot_angles: dict = {}
+    sun_params: dict = {}
     fin_of_entity: dict[str, int] = {}
     for lj in lights_json:
         lt = lj.get("type", "").lower()
@@ -611,6 +638,26 @@ def load_scene(path, width: int | None = None, height: int | None = None,
             scale = _color(lj.get("scale"), (1, 1, 1))
             rec["type"] = LIGHT_ENV_CONST
             rec["p"][0:3] = (scale * _color(rad, (1, 1, 1))).astype(F)   # color_mul(scale, tex)
+            inf_l.append(rec)
+        elif lt in ("sun", "directional", "direction", "distant"):
+            # LoaderUtils::getDirection (LoaderUtils.cpp:89-106): direction -> elevation / azimuth -> direction (y up), then
+            # vec3_normalize in the script (SunLight.cpp:44, DirectionalLight.cpp:36)
+            d = light_direction(lj)
+            rec["p"][0:3] = normalize_f32(d)
+            if lt == "sun":
+                rec["type"] = LIGHT_SUN
+                angle = float(lj.get("angle", 0.533))                                    # degrees (light/sun.art:1)
+                half = F(F(angle) / F(2)) / F(180) * F(3.14159265359)                    # rad(angle/2), core/common.art:20
+                rec["p"][3] = F(math.cos(float(half)))
+                sun_params[len(inf_l)] = (d, angle, "radiance" in lj, _color(lj["radiance"] if "radiance" in lj else lj.get("irradiance"), (1, 1, 1)))
+                if "radiance" in lj:
+                    rec["p"][4:7] = _color(lj["radiance"], (1, 1, 1))
+                else:                                                                    # irradiance / sun_area_from_srad(rad(angle/2)), sun.art:5
+                    rec["p"][4:7] = (_color(lj.get("irradiance"), (1, 1, 1)) * (F(1) / (F(3.14159265359) * half * half))).astype(F)
+            else:
+                rec["type"] = LIGHT_DIRECTIONAL
+                rec["p"][3:6] = _color(lj.get("irradiance"), (1, 1, 1))
+                sun_params[len(inf_l)] = (d, 0.0, False, rec["p"][3:6].copy())
             inf_l.append(rec)
         elif lt == "point":
             rec["type"] = LIGHT_POINT
@@ -817,4 +864,4 @@ def load_scene(path, width: int | None = None, height: int | None = None,
         entity_per_material=np.asarray([len(g) for g in groups], np.int32), materials=materials,
         infinite_lights=_arr(inf_l), finite_lights=_arr(fin_l), camera=cam, technique=technique,
         bbox_min=bb_lo.astype(F), bbox_max=bb_hi.astype(F), film_size=(fw, fh),
-        selector_data=selector_data, entity_names=names, material_names=[f"{b}{'@' + e if e else ''}" for b, e in mat_keys], spot_angles=spot_angles)
+        selector_data=selector_data, entity_names=names, material_names=[f"{b}{'@' + e if e else ''}" for b, e in mat_keys], spot_angles=spot_angles, sun_params=sun_params)

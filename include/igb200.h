@@ -69,7 +69,9 @@ enum { IGB200_LIGHT_ENV_CONST = 0,  /* make_environment_light (constant radiance
        IGB200_LIGHT_PLANE_AREA = 2, /* make_area_light(make_plane_area_emitter), light/area.art:10-43,124-258 */
        IGB200_LIGHT_SHAPE_AREA = 3, /* make_area_light(make_shape_area_emitter), light/area.art:62-107 */
        IGB200_LIGHT_SPHERE_AREA = 4, /* make_area_light(make_sphere_area_emitter), light/area.art:260-316 */
-       IGB200_LIGHT_SPOT = 5        /* make_spot_light, light/spot.art:8-44 */ };
+       IGB200_LIGHT_SPOT = 5,       /* make_spot_light, light/spot.art:8-44 */
+       IGB200_LIGHT_SUN = 6,        /* make_sun_light (not handled as delta), light/sun.art:10-48: an INFINITE light */
+       IGB200_LIGHT_DIRECTIONAL = 7 /* make_directional_light, light/directional.art:1-17: an INFINITE delta light */ };
 
 typedef struct igb200_light {
     int32_t type;      /* IGB200_LIGHT_* */
@@ -78,7 +80,9 @@ typedef struct igb200_light {
                           PLANE_AREA: origin, x_axis, y_axis, normal (3 each), area, t0..t3 (2 each), radiance rgb |
                           SHAPE_AREA: radiance rgb |
                           SPOT: position xyz, direction xyz, cos(cutoff), cos(falloff), intensity rgb |
-                          SPHERE_AREA: radiance rgb, sphere origin xyz (local), radius, area (compute_ellipsoid_area, shapes/sphere.art:21-27) */
+                          SPHERE_AREA: radiance rgb, sphere origin xyz (local), radius, area (compute_ellipsoid_area, shapes/sphere.art:21-27) |
+                          SUN: direction towards the sun xyz (unit), cos(angle / 2), radiance rgb |
+                          DIRECTIONAL: direction the light travels xyz (unit), irradiance rgb */
 } igb200_light;
 
 /* make_perspective_camera(eye, dir, up, compute_scale_from_{h,v}fov(fov, aspect), w, h, tmin, tmax):

@@ -304,7 +304,9 @@ static_assert(sizeof(EntityLeaf) == 96 && sizeof(MaterialDesc) == 64 && sizeof(L
 
 enum { SHAPE_TRIMESH = 0, SHAPE_SPHERE = 1 };
 enum { BSDF_DIFFUSE = 0, BSDF_DIELECTRIC = 1, BSDF_CONDUCTOR = 2 };
-enum { LIGHT_ENV_CONST = 0, LIGHT_POINT = 1, LIGHT_PLANE_AREA = 2, LIGHT_SHAPE_AREA = 3, LIGHT_SPHERE_AREA = 4, LIGHT_SPOT = 5 };
+enum { LIGHT_ENV_CONST = 0, LIGHT_POINT = 1, LIGHT_PLANE_AREA = 2, LIGHT_SHAPE_AREA = 3, LIGHT_SPHERE_AREA = 4, LIGHT_SPOT = 5,
+       LIGHT_SUN = 6,            // make_sun_light (light/sun.art:10-48): infinite cone light; p = direction towards the sun, cos(half angle), radiance
+       LIGHT_DIRECTIONAL = 7 };  // make_directional_light (light/directional.art:1-17): infinite delta light; p = direction the light travels, irradiance
 
 // ------------------------------------------------------------------------------------------ own BVH2 (median split)
 struct Bvh2 {
@@ -810,8 +812,27 @@ inline void sphere_emitter_sample(const Scene& sc, const LightDesc& l, Vec2 uv, 
 
 struct LightRef { const LightDesc* d; bool infinite; int id; };
 
-inline bool light_delta(const LightDesc& l) { return l.type == LIGHT_POINT || l.type == LIGHT_SPOT; }
-inline bool light_infinite(const LightDesc& l) { return l.type == LIGHT_ENV_CONST; }
+inline bool light_delta(const LightDesc& l) { return l.type == LIGHT_POINT || l.type == LIGHT_SPOT || l.type == LIGHT_DIRECTIONAL; }
+inline bool light_infinite(const LightDesc& l) { return l.type == LIGHT_ENV_CONST || l.type == LIGHT_SUN || l.type == LIGHT_DIRECTIONAL; }
+// core/warp.art:2-22
+inline void square_to_concentric_disk(float px, float py, float& x, float& y) {
+    const float a = 2 * px - 1, b = 2 * py - 1;
+    if (a == 0 && b == 0) { x = 0; y = 0; return; }
+    float sn, cs;
+    if (a * a > b * b) { const float phi = (flt_pi / 4) * safe_div(b, a); dm_sincosf(phi, &sn, &cs); x = cs * a; y = sn * a; }
+    else { const float phi = (flt_pi / 2) - (flt_pi / 4) * safe_div(a, b); dm_sincosf(phi, &sn, &cs); x = cs * b; y = sn * b; }
+}
+inline float uniform_cone_pdf(float cos_angle) { return safe_div(1, 2 * flt_pi * (1 - cos_angle)); }   // core/sampling.art:106
+// core/sampling.art:109-116
+inline DirSample sample_uniform_cone(float u, float v, float cos_angle) {
+    const float c1 = 1 - cos_angle;
+    float px, py; square_to_concentric_disk(u, v, px, py);
+    const float n2 = px * px + py * py;
+    const float z = cos_angle + c1 * (1 - n2);
+    const float f = safe_sqrt(c1 * (2 - c1 * n2));
+    return DirSample{v3(px * f, py * f, z), uniform_cone_pdf(cos_angle)};
+}
+inline bool sun_hit(const LightDesc& l, Vec3 dir) { return dot(v3(l.p[0], l.p[1], l.p[2]), dir) >= l.p[3]; }   // light/sun.art:18
 
 inline DirectLightSample light_sample_direct(const Scene& sc, const LightDesc& l, Rng& rnd, const SurfaceElement& from) {
     switch (l.type) {
@@ -822,6 +843,20 @@ inline DirectLightSample light_sample_direct(const Scene& sc, const LightDesc& l
         const float pdf = 1 / (4 * flt_pi);
         const Color intensity = cmulf(col(l.p[0], l.p[1], l.p[2]), 1 / pdf);
         return DirectLightSample{from.point + mulf(dir, scene_radius), dir, intensity, Pdf{pdf, PDF_SOLID}, 1.0f, scene_radius};
+    }
+    case LIGHT_SUN: {  // light/sun.art:22-26
+        const float cos_angle = l.p[3];
+        const Mat3x3 frame = make_orthonormal(neg(v3(l.p[0], l.p[1], l.p[2])));
+        const float u = rnd.next_f32(); const float v = rnd.next_f32();
+        const DirSample smp = sample_uniform_cone(u, v, cos_angle);
+        const Vec3 ndir = mat3x3_mul(frame, smp.dir);
+        const float inv_pdf = 2 * flt_pi * (1 - cos_angle);
+        return DirectLightSample{v3(0, 0, 0), neg(ndir), cmulf(col(l.p[4], l.p[5], l.p[6]), inv_pdf), Pdf{smp.pdf, PDF_SOLID}, smp.dir.z, std::numeric_limits<float>::infinity()};
+    }
+    case LIGHT_DIRECTIONAL: {  // light/directional.art:6
+        const float scene_radius = len(sc.bbox.max - sc.bbox.min) / 2 * 1.01f;
+        const Vec3 dir = v3(l.p[0], l.p[1], l.p[2]);
+        return DirectLightSample{from.point + mulf(dir, -scene_radius), neg(dir), col(l.p[3], l.p[4], l.p[5]), Pdf{1, PDF_DELTA}, 1, scene_radius};
     }
     case LIGHT_POINT: {  // light/point.art:3-8
         const Vec3 pos = v3(l.p[0], l.p[1], l.p[2]);
@@ -1047,8 +1082,15 @@ struct PathTracer {
             if (light_infinite(l) && !light_delta(l)) {
                 const PTRayPayload pt = unwrap(payload);
                 ++inflights;
-                const Color emit = col(l.p[0], l.p[1], l.p[2]);             // light/env.art:96
-                const float pdf_s = 1 / (4 * flt_pi);                        // light/env.art:97, sampling.art:47-51
+                Color emit; float pdf_s;
+                if (l.type == LIGHT_SUN) {                                   // light/sun.art:33-45
+                    const bool hit = sun_hit(l, ray.dir);
+                    emit = hit ? col(l.p[4], l.p[5], l.p[6]) : col(0, 0, 0);
+                    pdf_s = hit ? uniform_cone_pdf(l.p[3]) : 0.0f;
+                } else {
+                    emit = col(l.p[0], l.p[1], l.p[2]);                      // light/env.art:96
+                    pdf_s = 1 / (4 * flt_pi);                                // light/env.art:97, sampling.art:47-51
+                }
                 const float mis = enable_nee ? 1 / (1 + pt.inv_pdf * select_pdf(true, i, ray.org) * pdf_s) : 1.0f;
                 color = cadd(color, handle_color(cmulf(cmul(pt.contrib, emit), mis)));
             }

@@ -116,6 +116,7 @@ def render_both(tables, w, h, spi, iters, seed=0):
     ("primitives.json", 240, 135, 4, 1),                 # C3 at reduced size
     ("evaluation/cbox-d6.json", 128, 128, 2, 2),
     ("evaluation/multilight-uniform.json", 128, 128, 2, 1),
+    ("evaluation/sun-on-plane.json", 128, 128, 2, 2),           # sun: infinite cone light (light/sun.art)
     ("evaluation/multilight-simple.json", 128, 128, 2, 2),      # flux-CDF light selector (light_selector.art:46-77)
     ("evaluation/multilight-hierarchy.json", 128, 128, 2, 2),   # light hierarchy (light/light_hierarchy.art)
     ("evaluation/emissive-plane.json", 128, 128, 1, 1),
@@ -334,6 +335,23 @@ def test_spot_lights_match_oracle():
     got, ref, stats, cnt = render_both(t, 200, 200, 2, 2)
     assert rel_l2(got, ref) <= REL_L2_TOL
     assert (stats["CameraRayCount"], stats["ShadowRayCount"], stats["BounceRayCount"]) == tuple(int(x) for x in cnt)
+
+
+def test_distant_lights_match_oracle():
+    """Directional (delta) and sun (cone) lights next to an environment, all three light selectors."""
+    for sel in ("uniform", "simple", "hierarchy"):
+        s = flat_scene()
+        s["technique"]["light_selector"] = sel
+        s["lights"].append({"type": "directional", "name": "d", "direction": [0.2, 0.1, 1], "irradiance": [1, 0.5, 0.25]})
+        s["lights"].append({"type": "sun", "name": "s", "direction": [0.3, 0.2, -1], "irradiance": [3, 2, 1], "angle": 2.5})
+        s["lights"].append({"type": "env", "name": "e", "radiance": [0.1, 0.1, 0.1]})
+        s["lights"].append({"type": "point", "name": "p", "position": [-0.5, 0.3, -1], "intensity": [0.2, 0.2, 0.2]})
+        s["lights"].append({"type": "point", "name": "q", "position": [0.5, -0.3, -1.5], "intensity": [0.1, 0.3, 0.2]})
+        t = load_scene(s)
+        got, ref, stats, cnt = render_both(t, 200, 200, 2, 2)
+        assert ref.sum() > 0
+        assert rel_l2(got, ref) <= REL_L2_TOL, sel
+        assert (stats["CameraRayCount"], stats["ShadowRayCount"], stats["BounceRayCount"]) == tuple(int(x) for x in cnt), sel
 
 
 def test_standard_aovs_match_oracle():

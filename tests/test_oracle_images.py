@@ -19,7 +19,7 @@ from make_golden import IMAGES  # noqa: E402  scene name -> reference file (seve
 # thresholds of scripts/RunEvaluations.py:95-123 (default 1e-3)
 EPS_1024 = {"plane-d1": 1e-3, "plane-d6": 1e-3, "point": 1e-3, "emissive-plane": 1e-3, "cbox-d1": 5e-3, "cbox-d6": 5e-3,
             "multilight-uniform": 3e-4, "multilight-simple": 3e-4, "multilight-hierarchy": 3e-4, "sphere-light-pure": 3e-3, "sphere-light-ico": 2e-3, "sphere-light-uv": 2e-3,
-            "sphere-light-ico-nopt": 2e-3, "emissive-plane-nopt": 1e-3, "emissive-plane-scale": 1e-3, "emissive-plane-scale-nopt": 1e-3, "two-planes-base": 1e-3, "room": 1e-3}
+            "sphere-light-ico-nopt": 2e-3, "emissive-plane-nopt": 1e-3, "emissive-plane-scale": 1e-3, "emissive-plane-scale-nopt": 1e-3, "two-planes-base": 1e-3, "room": 1e-3, "sun-on-plane": 1e-3}
 # a 64 x 32 uv-sphere has ~2 % less area than the sphere the reference image was rendered with
 MEAN_TOL = {"sphere-light-uv": 0.035}
 
@@ -37,7 +37,7 @@ def relmse(img, ref):
                                       ("cbox-d1", 128), ("cbox-d6", 512), ("multilight-uniform", 512), ("multilight-simple", 512), ("multilight-hierarchy", 512), ("sphere-light-pure", 256),
                                       ("sphere-light-ico", 256), ("sphere-light-uv", 256), ("sphere-light-ico-nopt", 256),
                                       ("emissive-plane-nopt", 256), ("emissive-plane-scale", 256), ("emissive-plane-scale-nopt", 256),
-                                      ("two-planes-base", 256), ("room", 256)])
+                                      ("two-planes-base", 256), ("room", 256), ("sun-on-plane", 128)])
 def test_oracle_matches_reference_image(name, spp):
     refs = np.load(os.path.join(ROOT, "tests", "golden", "ref_images.npz"))
     ref = refs[IMAGES[name][:-4]].astype(np.float32)

@@ -126,6 +126,22 @@ def test_spot_light_scene_average():
     assert scene_average(s)[0] == pytest.approx(0.0348280902, abs=2.5e-3)
 
 
+def test_directional_and_sun_light_scene_averages():
+    # a Lambertian plane of albedo 1 facing a distant light of irradiance E shows radiance E / pi (light/directional.art, light/sun.art;
+    # the sun's irradiance is spread over a cone of 0.533 degrees, SunLight.cpp:46-52)
+    s = flat_scene()
+    s["lights"].append({"type": "directional", "name": "_light", "direction": [0, 0, 1], "irradiance": [1, 1, 1]})   # direction the light travels
+    assert scene_average(s, size=256, iters=2)[0] == pytest.approx(1 / np.pi, rel=1e-4)
+    s = flat_scene()
+    s["lights"].append({"type": "sun", "name": "_light", "direction": [0, 0, -1], "irradiance": [1.5, 1.5, 1.5]})    # direction towards the sun
+    # 1 - cos(0.2665 deg) = 1.08e-5 carries only ~7 bits in f32 (the reference evaluates it in f32 too, light/sun.art:15): -0.3 %
+    assert scene_average(s, size=256, iters=4)[0] == pytest.approx(1.5 / np.pi, rel=5e-3)
+    # tilted by 60 degrees: cos = 0.5
+    s = flat_scene()
+    s["lights"].append({"type": "sun", "name": "_light", "direction": [0, np.sin(np.pi / 3), -np.cos(np.pi / 3)], "irradiance": [2, 2, 2]})
+    assert scene_average(s, size=256, iters=4)[0] == pytest.approx(2 * 0.5 / np.pi, rel=6e-3)
+
+
 def test_env_light_scene_average():
     s = flat_scene()
     s["lights"].append({"type": "env", "name": "_light", "radiance": [1, 1, 1]})

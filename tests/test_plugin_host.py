@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "evaluation/cbox-d6.json", "evaluation/multilight-uniform.json",
           "evaluation/multilight-simple.json", "evaluation/multilight-hierarchy.json",
           "evaluation/emissive-plane.json", "evaluation/point.json", "evaluation/plane-d1.json", "evaluation/sphere-light-pure.json",
-          "evaluation/two-planes-mirror.json", "<spot>"]
+          "evaluation/two-planes-mirror.json", "evaluation/sun-on-plane.json", "<spot>", "<distant>"]
 
 
 def scene(name):
@@ -24,6 +24,13 @@ def scene(name):
         s = flat_scene()
         s["lights"].append({"type": "spot", "name": "_light", "cutoff": 45, "falloff": 30, "position": [0, 0, -2], "direction": [0.1, 0, 1], "power": [1, 2, 3]})
         s["lights"].append({"type": "spot", "name": "_light2", "cutoff": 20, "falloff": 20, "position": [0.5, 0, -2], "direction": [0, 0, 1], "intensity": [1, 1, 1]})
+        return load_scene(s)
+    if name == "<distant>":   # a directional light and a sun given by irradiance and elevation / azimuth next to an environment
+        from conftest import flat_scene
+        s = flat_scene()
+        s["lights"].append({"type": "directional", "name": "_d", "direction": [0.2, 0.1, 1], "irradiance": [1, 0.5, 0.25]})
+        s["lights"].append({"type": "sun", "name": "_s", "elevation": 1.1, "azimuth": 0.4, "irradiance": [3, 2, 1], "angle": 2.5})
+        s["lights"].append({"type": "env", "name": "_e", "radiance": [0.1, 0.1, 0.1]})
         return load_scene(s)
     return load_scene(os.path.join(ROOT, "scenes", name))
 

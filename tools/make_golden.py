@@ -39,13 +39,17 @@ IMAGES = {
     # under a uniform environment of radiance 0.8 has radiance 0.64 wherever only the environment lights it; the oracle gives 0.635,
     # that image 0.496 = 0.8 * 0.8^2.2, i.e. it was rendered with the albedo taken as an sRGB value.)
     "room": "ref-room-4096.exr",
+    # Radiance rendering of a diffuse plane under the sun (cone of 0.533 degrees, radiance 1e5): pins make_sun_light. (Not used:
+    # ref-sun-on-plane-and-stick-rad.exr -- the Ignis scene file puts the sun on the horizon, direction (0.707, -0.707, 0) in a z-up
+    # scene, and renders a plane at grazing incidence (mean 0.03); the Radiance image shows a fully lit plane (mean 0.24).)
+    "sun-on-plane": "ref-sun-on-plane-rad.exr",
 }
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "primitives_data.json", "flipped_prim.json",
           "meshes/Room.obj", "meshes/Bottom.ply", "meshes/Top.ply", "meshes/Left.ply", "meshes/Right.ply", "meshes/Back.ply", "meshes/Diamond.ply"]
 EVAL = ["plane-base.json", "plane-d1.json", "plane-d6.json", "point.json", "emissive-plane.json", "cbox-base.json", "cbox-d1.json",
         "cbox-d6.json", "multilight.json", "multilight-uniform.json", "multilight-simple.json", "multilight-hierarchy.json", "flipped-prim-base.json", "flipped-prim-diffuse.json",
         "sphere-light-base.json", "sphere-light-pure.json", "sphere-light-ico.json", "sphere-light-uv.json", "sphere-light-ico-nopt.json",
-        "emissive-plane-nopt.json", "emissive-plane-scale.json", "emissive-plane-scale-nopt.json", "two-planes-base.json", "two-planes-mirror.json", "room.json"]
+        "emissive-plane-nopt.json", "emissive-plane-scale.json", "emissive-plane-scale-nopt.json", "two-planes-base.json", "two-planes-mirror.json", "room.json", "sun-on-plane.json"]
 
 
 def main():
