@@ -64,12 +64,7 @@ __device__ __forceinline__ void sphere_map_uv(V3 dir, float& u, float& v) {
     u = phi / (2 * IGB_FLT_PI); v = theta / IGB_FLT_PI;
 }
 // shapes/sphere.art:108-136
-#ifdef IGB_EXP_A
-__device__ __noinline__ bool intersect_sphere(V3 origin,
-#else
-__device__ __forceinline__ bool intersect_sphere(V3 origin,
-#endif
- float radius, V3 org, V3 dir, float rtmin, float rtmax, float& ot, float& ou, float& ov) {
+__device__ __forceinline__ bool intersect_sphere(V3 origin, float radius, V3 org, V3 dir, float rtmin, float rtmax, float& ot, float& ou, float& ov) {
     const V3 L = org - origin;
     const float S = -dot(L, dir);
     const float D2 = len2(dir);
@@ -162,33 +157,6 @@ constexpr uint32_t TB_ANY = 1u << 8, TB_NEGZERO = 1u << 9, TB_SX = 1u << 10, TB_
         n += hit_ ? 1 : 0;                                                                                               \
     }
 
-#ifdef IGB_EXP_B
-// node_step with a deep stack (entries beyond the shared-memory part): out of line, it runs for a handful of rays per million
-struct DeepOut { int sp, cur; };
-__device__ __noinline__ DeepOut node_step_deep(const float4* N, uint32_t bits, V3 idir, V3 ilo, V3 ihi, float tmin, float tcull, int sp, uint2* ss, int stride, uint2* sl) {
-    Stack st; st.s = ss; st.stride = stride; st.l = sl;
-    const int ox = (bits & TB_SX) ? 2 : 0, oy = (bits & TB_SY) ? 2 : 0, oz = (bits & TB_SZ) ? 2 : 0;
-    int n = 0, best = 0, best_slot = 0;
-    float best_t = __int_as_float(0x7fc00000);
-    const int sp0 = sp;
-#define IGB_STORE(C, T) if (hit_ && sp < STACK_SIZE) st.push(sp, (C), (T));
-#pragma unroll 1
-    for (int g = 0; g < 2; ++g) {
-        const int4 ch = *reinterpret_cast<const int4*>(N + 12 + g);
-        if (g == 1 && ch.x == 0) break;
-        const float4 nx = N[ox + g], fx = N[2 - ox + g], ny = N[4 + oy + g], fy = N[6 - oy + g], nz = N[8 + oz + g], fz = N[10 - oz + g];
-        IGB_CHILD(x) IGB_CHILD(y) IGB_CHILD(z) IGB_CHILD(w)
-    }
-#undef IGB_STORE
-    DeepOut r;
-    if (sp == sp0) { r.sp = sp; r.cur = 0; return r; }
-    const uint2 top = st.pop(sp);
-    if (sp0 + best_slot != sp) st.set(sp0 + best_slot, top);
-    r.sp = sp; r.cur = best;
-    return r;
-}
-#endif
-
 struct Traversal {
     V3 org, dir;              // ray in the current space (world, or local to `ent`)
     float tmin, tmax;         // the ray's own interval (never shrunk: the triangle test uses it, see header)
@@ -275,10 +243,6 @@ struct Traversal {
             if (best_slot != n) base[best_slot * st.stride] = base[n * st.stride];
             sp += n; cur = best;
         } else {
-#ifdef IGB_EXP_B
-            const DeepOut r = node_step_deep(N, bits, idir, ilo, ihi, tmin, tcull, sp, st.s, st.stride, st.l);
-            sp = r.sp; cur = r.cur;
-#else
             // deep stack: same tests, entries go through the overflow-aware push (rare)
             const int sp0 = sp;
 #define IGB_STORE(C, T) if (hit_ && sp < STACK_SIZE) st.push(sp, (C), (T));
@@ -294,7 +258,6 @@ struct Traversal {
             const uint2 top = st.pop(sp);
             if (sp0 + best_slot != sp) st.set(sp0 + best_slot, top);
             cur = best;
-#endif
         }
     }
 
