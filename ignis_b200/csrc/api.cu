@@ -26,7 +26,11 @@ constexpr int WF_BLOCK = 256;       // threads per CTA of the persistent kernels
 using WaveKernel = void (*)(const WaveParams);
 using TraceKernel = void (*)(const DevScene, const PrimaryQueue, int, const ShadowQueue, int, float*, int*, unsigned long long*, int, int, int, int, int);
 // "full": the shade code with every feature (shade.cuh shade_record<true>) or only what the BASELINE configurations use.
-static WaveKernel wave_kernel(int min_blocks, int vote, bool full) {
+static WaveKernel wave_kernel(int min_blocks, int vote, bool full, int where = 0) {
+    if (vote && where == 1) {   // scene staged as a whole (as turn_trace_kernel)
+        if (full) return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 2, true, 1> : k_wavefront<WF_BLOCK, 2, 2, true, 1>;
+        return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 2, false, 1> : k_wavefront<WF_BLOCK, 2, 2, false, 1>;
+    }
     if (full) {
         if (vote) return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 2, true> : k_wavefront<WF_BLOCK, 2, 2, true>;
         return min_blocks >= 3 ? k_wavefront<WF_BLOCK, 3, 0, true> : k_wavefront<WF_BLOCK, 2, 0, true>;
@@ -191,13 +195,13 @@ static int configure_kernels(igb200_ctx* c) {
     c->stage_where = (c->stage_ent == s.n_ent && c->stage_nodes == s.n_nodes && c->stage_tris == s.n_tris) ? 1 : 0;
     if (!c->specialise_where) c->stage_where = 0;
     c->smem_bytes = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)c->stage_ent * 128 + (size_t)c->stage_nodes * 256 + (size_t)c->stage_tris * 48;
-    for (int full = 0; full < 2; ++full) CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote, full != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    for (int full = 0; full < 2; ++full) CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote, full != 0, c->stage_where), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CU(cudaFuncSetAttribute((const void*)trace_kernel(c->min_blocks, c->vote), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     int nb = 0;
     {   // both shade variants must fit the cooperative grid
         int nb1 = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)wave_kernel(c->min_blocks, c->vote, false), WF_BLOCK, c->smem_bytes));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, (const void*)wave_kernel(c->min_blocks, c->vote, true), WF_BLOCK, c->smem_bytes));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)wave_kernel(c->min_blocks, c->vote, false, c->stage_where), WF_BLOCK, c->smem_bytes));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, (const void*)wave_kernel(c->min_blocks, c->vote, true, c->stage_where), WF_BLOCK, c->smem_bytes));
         nb = std::min(nb, nb1);
     }
     if (nb < 1) return fail(-2, "k_wavefront does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
@@ -262,7 +266,7 @@ static int launch_wave(igb200_ctx* c, const RenderParams& rp, const DevScene& sc
     CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
     void* args[] = {&P};
     { const int r = prof_begin(c, 0); if (r) return r; }
-    CU(cudaLaunchCooperativeKernel((const void*)wave_kernel(c->min_blocks, c->vote, P.sc.full != 0), dim3((unsigned)(c->blocks_per_sm * c->n_sm)), dim3(WF_BLOCK), args, c->smem_bytes, c->stream));
+    CU(cudaLaunchCooperativeKernel((const void*)wave_kernel(c->min_blocks, c->vote, P.sc.full != 0, c->stage_where), dim3((unsigned)(c->blocks_per_sm * c->n_sm)), dim3(WF_BLOCK), args, c->smem_bytes, c->stream));
     { const int r = prof_end(c); if (r) return r; }
     c->launches += 1;
     c->pending = true;

@@ -396,6 +396,7 @@ struct WideStack {
 };
 constexpr int WIDE_STACK = SMEM_STACK * 8;
 
+template <int WHERE = 0>
 __device__ __forceinline__ HitR trace_wide(const DevScene& sc, const Staged& sg, const WideStack& ws, unsigned gmask, int j,
                                            const float4* po, const float4* pd, uint32_t ray_flags, bool any_hit) {
     Traversal T;
@@ -418,7 +419,7 @@ __device__ __forceinline__ HitR trace_wide(const DevScene& sc, const Staged& sg,
         }
         if (T.cur > 0) {
             // ---- inner node: lane j tests child j
-            const float* N = reinterpret_cast<const float*>(node_ptr(sc, sg, T.cur - 1));
+            const float* N = reinterpret_cast<const float*>(node_ptr<WHERE>(sc, sg, T.cur - 1));
             const int c = reinterpret_cast<const int*>(N)[48 + j];
             const float lx = N[j], hx = N[8 + j], ly = N[16 + j], hy = N[24 + j], lz = N[32 + j], hz = N[40 + j];
             const bool sx = (T.bits & TB_SX) != 0, sy = (T.bits & TB_SY) != 0, sz = (T.bits & TB_SZ) != 0;
@@ -449,7 +450,7 @@ __device__ __forceinline__ HitR trace_wide(const DevScene& sc, const Staged& sg,
             {
                 // entity_step pushes at most one entry (a sentinel) at index T.sp: redirect it into `lst`
                 const int keep = T.sp; T.sp = 0;
-                T.entity_step(sc, sg, one);
+                T.template entity_step<WHERE>(sc, sg, one);
                 spx = T.sp; T.sp = keep;
             }
             if (spx > 0) { if (j == 0 && sp0 < WIDE_STACK) ws.at(sp0) = lst[0]; T.sp = min(sp0 + 1, WIDE_STACK); __syncwarp(gmask); }
@@ -461,7 +462,7 @@ __device__ __forceinline__ HitR trace_wide(const DevScene& sc, const Staged& sg,
             T.cur = 0;
             float t = __int_as_float(0x7f800000), u = 0, v = 0; int prim = -1;
             if (j < cnt) {
-                const float4* P = tri_ptr(sc, sg, first + j);
+                const float4* P = tri_ptr<WHERE>(sc, sg, first + j);
                 float tt, uu, vv;
                 if (intersect_tri(T.org, T.dir, T.tmin, T.tmax, P[0], P[1], P[2], tt, uu, vv)) {
                     const int pp = __ldg(sc.tri_prim + first + j);
