@@ -141,7 +141,8 @@ __device__ __forceinline__ const float4* leaf_ptr(const DevScene& sc, const Stag
 }
 
 // Ray state bits
-constexpr uint32_t TB_ANY = 1u << 8, TB_NEGZERO = 1u << 9, TB_SX = 1u << 10, TB_SY = 1u << 11, TB_SZ = 1u << 12, TB_DONE = 1u << 13;
+constexpr uint32_t TB_ANY = 1u << 8, TB_NEGZERO = 1u << 9, TB_SX = 1u << 10, TB_SY = 1u << 11, TB_SZ = 1u << 12, TB_DONE = 1u << 13,
+                   TB_STALE = 1u << 14;   // an instance was left: the world-space ray must be restored before the next visit (lazily: often there is none)
 
 // One slab test of child lane K of a group of four; the entry is written to the stack slot above the ones pushed so far
 // and only kept (n advances) if the child is hit, so there is no branch per child. `nearer` uses "not >=" so that the
@@ -210,9 +211,14 @@ struct Traversal {
             if (sp == 0) return true;
             const uint2 e = st.pop(sp);
             cur = (int)e.x;
-            if (cur > SENTINEL_KEEP) { if (__uint_as_float(e.y) <= tcull) return false; continue; }
+            if (cur > SENTINEL_KEEP) {
+                if (!(__uint_as_float(e.y) <= tcull)) continue;
+                // leaving a transformed instance costs three reciprocals: pay only if something is still to be visited in world space
+                if (bits & TB_STALE) { const float4 o = *po, d = *pd; bits &= ~TB_STALE; set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)); }
+                return false;
+            }
             ent = -1;
-            if (cur == SENTINEL_RESTORE) { const float4 o = *po, d = *pd; set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)); }
+            if (cur == SENTINEL_RESTORE) bits |= TB_STALE;
         }
     }
 
@@ -410,9 +416,13 @@ __device__ __forceinline__ HitR trace_wide(const DevScene& sc, const Staged& sg,
                 if (T.sp == 0) { empty = true; break; }
                 const uint2 e = ws.at(--T.sp);
                 T.cur = (int)e.x;
-                if (T.cur > SENTINEL_KEEP) { if (__uint_as_float(e.y) <= T.tcull) break; continue; }
+                if (T.cur > SENTINEL_KEEP) {
+                    if (!(__uint_as_float(e.y) <= T.tcull)) continue;
+                    if (T.bits & TB_STALE) { const float4 o = *po, d = *pd; T.bits &= ~TB_STALE; T.set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)); }
+                    break;
+                }
                 T.ent = -1;
-                if (T.cur == SENTINEL_RESTORE) { const float4 o = *po, d = *pd; T.set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)); }
+                if (T.cur == SENTINEL_RESTORE) T.bits |= TB_STALE;
             }
             if (empty) break;
             __syncwarp(gmask);   // every lane has read the popped entries before any lane pushes over them
