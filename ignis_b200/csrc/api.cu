@@ -609,7 +609,9 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
         // bit 1: the local matrix is bit for bit the identity, so transforming the ray is the exact map x -> x + 0
         static const float ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
         const bool identity = std::memcmp(m, ident, sizeof(ident)) == 0;
-        L[1] = make_float4(lf.max[0], lf.max[1], lf.max[2], as_f((type == IGB200_SHAPE_SPHERE ? 1 : 0) | (identity ? 2 : 0)));
+        // bit 2: only a translation (linear part bit for bit the identity): the direction, hence its reciprocals, stay as they are
+        const bool translation = !identity && std::memcmp(m, ident, 9 * sizeof(float)) == 0;
+        L[1] = make_float4(lf.max[0], lf.max[1], lf.max[2], as_f((type == IGB200_SHAPE_SPHERE ? 1 : 0) | (identity ? 2 : 0) | (translation ? 4 : 0)));
         L[2] = make_float4(m[0], m[3], m[6], m[9]);
         L[3] = make_float4(m[1], m[4], m[7], m[10]);
         L[4] = make_float4(m[2], m[5], m[8], m[11]);

@@ -89,8 +89,9 @@ __device__ __forceinline__ bool intersect_sphere(V3 origin, float radius, V3 org
 constexpr int SMEM_STACK  = 16;                       // entries per thread held in shared memory
 constexpr int LOCAL_STACK = 80;                       // overflow entries per thread (local memory)
 constexpr int STACK_SIZE  = SMEM_STACK + LOCAL_STACK;
-constexpr int   SENTINEL_RESTORE = (int)0x80000000;   // pop: back to world space, reload the ray
-constexpr int   SENTINEL_KEEP    = (int)0x80000001;   // pop: back to the top level, ray unchanged (identity instance)
+constexpr int   SENTINEL_RESTORE   = (int)0x80000000;   // pop: back to world space, reload the ray
+constexpr int   SENTINEL_RESTORE_T = (int)0x80000001;   // pop: back to world space, only the origin changed (translated instance)
+constexpr int   SENTINEL_KEEP      = (int)0x80000002;   // pop: back to the top level, ray unchanged (identity instance); the largest sentinel
 constexpr float CULL_SLACK = 9.5367431640625e-07f;    // 2^-20
 constexpr float CULL_TMAX  = 1.0000152587890625f;     // 1 + 2^-16
 
@@ -142,6 +143,7 @@ __device__ __forceinline__ const float4* leaf_ptr(const DevScene& sc, const Stag
 
 // Ray state bits
 constexpr uint32_t TB_ANY = 1u << 8, TB_NEGZERO = 1u << 9, TB_SX = 1u << 10, TB_SY = 1u << 11, TB_SZ = 1u << 12, TB_DONE = 1u << 13,
+                   TB_STALE_T = 1u << 15,  // ... only its origin (the instance was a pure translation)
                    TB_STALE = 1u << 14;   // an instance was left: the world-space ray must be restored before the next visit (lazily: often there is none)
 
 // One slab test of child lane K of a group of four; the entry is written to the stack slot above the ones pushed so far
@@ -171,15 +173,20 @@ struct Traversal {
 #endif
 
     __device__ __forceinline__ void set_ray(V3 o, V3 d) {
-        org = o; dir = d;
+        dir = d;
         idir = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));                 // traversal/ray.art:27-39
+        bits = (bits & ~(TB_SX | TB_SY | TB_SZ)) | (idir.x < 0 ? TB_SX : 0u) | (idir.y < 0 ? TB_SY : 0u) | (idir.z < 0 ? TB_SZ : 0u);
+        set_origin(o);
+    }
+    // the part of set_ray that depends on the origin: enough when the direction is unchanged (translated instances)
+    __device__ __forceinline__ void set_origin(V3 o) {
+        org = o;
         const V3 iorg = neg(o * idir);
         const float inf = __int_as_float(0x7f800000);
         const float ax = fabsf(iorg.x), ay = fabsf(iorg.y), az = fabsf(iorg.z);
         // |iorg| = inf: org * flt_max overflowed (axis-parallel ray) -> no bound from that axis
         ilo = v3(ax == inf ? -inf : iorg.x - ax * CULL_SLACK, ay == inf ? -inf : iorg.y - ay * CULL_SLACK, az == inf ? -inf : iorg.z - az * CULL_SLACK);
         ihi = v3(ax == inf ? inf : iorg.x + ax * CULL_SLACK, ay == inf ? inf : iorg.y + ay * CULL_SLACK, az == inf ? inf : iorg.z + az * CULL_SLACK);
-        bits = (bits & ~(TB_SX | TB_SY | TB_SZ)) | (idir.x < 0 ? TB_SX : 0u) | (idir.y < 0 ? TB_SY : 0u) | (idir.z < 0 ? TB_SZ : 0u);
     }
 
     // po / pd: the ray record (org.xyz,tmin / dir.xyz,tmax). Returns false if there is nothing to traverse.
@@ -214,11 +221,17 @@ struct Traversal {
             if (cur > SENTINEL_KEEP) {
                 if (!(__uint_as_float(e.y) <= tcull)) continue;
                 // leaving a transformed instance costs three reciprocals: pay only if something is still to be visited in world space
-                if (bits & TB_STALE) { const float4 o = *po, d = *pd; bits &= ~TB_STALE; set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)); }
+                if (bits & (TB_STALE | TB_STALE_T)) {
+                    const float4 o = *po;
+                    if (bits & TB_STALE) { const float4 d = *pd; set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)); }
+                    else set_origin(v3(o.x, o.y, o.z));
+                    bits &= ~(TB_STALE | TB_STALE_T);
+                }
                 return false;
             }
             ent = -1;
             if (cur == SENTINEL_RESTORE) bits |= TB_STALE;
+            else if (cur == SENTINEL_RESTORE_T) bits |= TB_STALE_T;
         }
     }
 
@@ -288,7 +301,7 @@ struct Traversal {
             if (!((en <= ex) & (ex >= 0))) return;
         }
         const float4 l5 = L[5];
-        const int kind = __float_as_int(l1.w);    // bit 0: analytic sphere, bit 1: identity local matrix
+        const int kind = __float_as_int(l1.w);    // bit 0: analytic sphere, bit 1: identity local matrix, bit 2: translation only
         const int e = __float_as_int(l5.x);
         if (kind & 1) {
             const float4 r0 = L[2], r1 = L[3], r2 = L[4], s = L[6];
@@ -311,6 +324,12 @@ struct Traversal {
             return;
         }
         const float4 r0 = L[2], r1 = L[3], r2 = L[4];
+        if ((kind & 4) && !(bits & TB_NEGZERO)) {
+            // pure translation: the transformed direction is the direction (exactly, as no component is -0), so only the origin moves
+            set_origin(xform_point(r0, r1, r2, org));
+            st.push(sp, SENTINEL_RESTORE_T, -1.0f);
+            return;
+        }
         set_ray(xform_point(r0, r1, r2, org), xform_dir(r0, r1, r2, dir));                            // ray.art:53-59
         st.push(sp, SENTINEL_RESTORE, -1.0f);
     }
@@ -418,11 +437,17 @@ __device__ __forceinline__ HitR trace_wide(const DevScene& sc, const Staged& sg,
                 T.cur = (int)e.x;
                 if (T.cur > SENTINEL_KEEP) {
                     if (!(__uint_as_float(e.y) <= T.tcull)) continue;
-                    if (T.bits & TB_STALE) { const float4 o = *po, d = *pd; T.bits &= ~TB_STALE; T.set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)); }
+                    if (T.bits & (TB_STALE | TB_STALE_T)) {
+                        const float4 o = *po;
+                        if (T.bits & TB_STALE) { const float4 d = *pd; T.set_ray(v3(o.x, o.y, o.z), v3(d.x, d.y, d.z)); }
+                        else T.set_origin(v3(o.x, o.y, o.z));
+                        T.bits &= ~(TB_STALE | TB_STALE_T);
+                    }
                     break;
                 }
                 T.ent = -1;
                 if (T.cur == SENTINEL_RESTORE) T.bits |= TB_STALE;
+                else if (T.cur == SENTINEL_RESTORE_T) T.bits |= TB_STALE_T;
             }
             if (empty) break;
             __syncwarp(gmask);   // every lane has read the popped entries before any lane pushes over them
