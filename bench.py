@@ -42,7 +42,7 @@ B_PRIMARY, B_SHADOW, B_SPLAT = 216, 108, 24
 # the same figure split by pipeline stage (DESIGN.md "Algorithmic bytes")
 # dram__bytes_read.sum + dram__bytes_write.sum per k_turn_trace launch of this workload (ncu --set full, profiles/)
 NCU_TRAFFIC_BYTES = 5.385e8
-NCU_TRAFFIC_SOURCE = ("profiles/r3c_k_turn_trace_full.csv: dram read + write of the three k_turn_trace launches of the first iteration "
+NCU_TRAFFIC_SOURCE = ("profiles/r3d_k_turn_trace_full.csv: dram read + write of the three k_turn_trace launches of the first iteration "
                       "(436 + 749 + 430 MB) / 3; later iterations also trace the carried paths, hence the larger algorithmic figure")
 B_STAGE = {"generate": 68, "traverse_primary": 60, "shade_read": 88, "shade_bounce_write": 68, "shade_shadow_write": 56,
            "traverse_secondary": 52}

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from ignis_b200.device import Runtime, RAY_DTYPE
 from ignis_b200.scene import load_scene
-for scene, w, h in (("diamond_scene.json", 96, 54), ("primitives.json", 64, 36)):
+for scene, w, h in (("diamond_scene.json", 96, 54), ("primitives.json", 64, 36), ("evaluation/multilight-hierarchy.json", 48, 48), ("evaluation/sun-on-plane.json", 48, 48)):
     t = load_scene(os.path.join(ROOT, "scenes", scene))
     with Runtime(t, w, h, spi=2) as rt:
         for split in (0, 2):
