@@ -11,12 +11,12 @@ own harness (scripts/Benchmark.py). Mrays/s = (camera + bounce + shadow rays) / 
 
 For N > 1 it is launched by torchrun (one rank per GPU): the framebuffer is split into 32x32 tiles dealt in rotating round-robin order
 to the ranks (scene replicated, no data-path collective), and the accumulation buffers are summed onto rank 0 with
-one NCCL reduce at the end of the K steps (inside the timed region). Total work is fixed => "scaling": "strong".
+one NCCL exchange at the end of the K steps (inside the timed region): every rank sends the pixels of its own tiles to rank 0 (ignis_b200/partition.py TileGather). Total work is fixed => "scaling": "strong".
 
 Timed regions: `value` = K steps issued back to back with the scene resident in HBM, timed with CUDA events on the
 device's render stream between barriers, max over ranks. `e2e` = the same K steps through the public host API
 (B200Device.render + getFramebufferForHost over the C ABI): every step uploads its Settings and reads the whole
-accumulated framebuffer back into pinned host memory (after the NCCL reduce for N > 1).
+accumulated framebuffer back into pinned host memory (after the NCCL gather for N > 1).
 
 The oracle (oracle/) is executed here only for `cpu_baseline` and `--impl reference`.
 """
@@ -185,7 +185,7 @@ def workload_config(args, world):
     return {"workload": f"{SCENE} {args.width}x{args.height}, path integrator max_depth 64, spi {args.spi}, seed 0; 1 step = 1 render() iteration "
                         f"({args.spi} spp, {args.width * args.height * args.spi} camera rays); 16 steps = 64 spp (BASELINE.json configs[1])",
             "spi": args.spi, "width": args.width, "height": args.height,
-            "parallelism": f"framebuffer tiles 32x32 in rotating round-robin order over {world} GPU(s), scene replicated, one NCCL reduce of the accumulation buffer",
+            "parallelism": f"framebuffer tiles 32x32 in rotating round-robin order over {world} GPU(s), scene replicated, one NCCL gather of the ranks' tiles of the accumulation buffer onto rank 0",
             "l2": "no flush needed: every step streams its ray queues through HBM (> 800 MB per step per GPU at N=1, L2 is 126 MB)"}
 
 
@@ -194,7 +194,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from ignis_b200.device import Runtime
-    from ignis_b200.partition import TILE, reduce_framebuffer
+    from ignis_b200.partition import TILE, TileGather
     from ignis_b200.scene import load_scene
 
     rank = int(os.environ.get("RANK", "0"))
@@ -205,7 +205,10 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner would otherwise precede the JSON line on stdout
+        # NCCL prints its version banner on stdout when the first communicator is made: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w, h, spi = args.width, args.height, args.spi
@@ -219,7 +222,8 @@ def run_b200(args):
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
     fb_t = torch.as_tensor(_FB(dev.getFramebufferForDevice(), w * h * 3), device=torch.device("cuda", local_rank))
-    scratch = torch.empty_like(fb_t) if world > 1 else None
+    scratch = torch.empty_like(fb_t) if (world > 1 and rank == 0) else None
+    gather = TileGather(w, h, rank, world, TILE, device=torch.device("cuda", local_rank)) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -227,10 +231,10 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def reduce_to_root():
-        # disjoint tile support: the sum is a gather of the per-rank tiles
+        # disjoint tile support: the sum of the accumulation buffers is a gather of the per-rank tiles; rank 0 ends up
+        # with the complete frame in `scratch` (its own accumulation buffer keeps accumulating only its tiles)
         with torch.cuda.stream(stream):
-            scratch.copy_(fb_t)
-            reduce_framebuffer(scratch, dst=0)
+            gather.run(fb_t, out=scratch)
 
     # ---- warm-up (also sizes the ray queues and warms NCCL)
     for _ in range(max(args.warmup, 0)):
@@ -238,6 +242,10 @@ def run_b200(args):
     if world > 1:
         reduce_to_root()
     barrier()
+    if world > 1:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     def timed(e2e: bool):
         rt.reset()
@@ -327,7 +335,7 @@ def run_b200(args):
                 "clocks": clocks, "gpu_launches": tot["KernelLaunches"],
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": w * h * 12,
                         "ms_per_step": wall_e / args.steps, "timed": "host wall clock between barriers, max over ranks"},
-                "per_rank_ms": {"columns": ["issued launches", "flush + drain of the deferred tail", "NCCL reduce", "total", "rays traced"], "ranks": per_rank},
+                "per_rank_ms": {"columns": ["issued launches", "flush + drain of the deferred tail", "NCCL gather of the tiles", "total", "rays traced"], "ranks": per_rank},
                 "rays": tot, "msamples_per_s": w * h * spi * args.steps / (ms * 1e-3) / 1e6, "wall_ms_per_step": wall_ms / args.steps}
         step_bytes = algorithmic_bytes(tot)
         line["roofline_step"] = {"bound": "hbm", "achieved": step_bytes / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
@@ -376,7 +384,7 @@ def run_b200(args):
     # tear down in dependency order: tensors that alias or were used on the device's stream go first, then the device
     # (which owns that stream), then NCCL; otherwise the allocator records events on a stream that no longer exists at exit
     torch.cuda.synchronize()
-    del fb_t, scratch, host_t, stream
+    del fb_t, scratch, host_t, gather, stream
     torch.cuda.synchronize()
     rt.close()
     if world > 1:

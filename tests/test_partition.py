@@ -25,7 +25,7 @@ def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
-    from ignis_b200.partition import reduce_framebuffer, tile_owner
+    from ignis_b200.partition import TileGather, reduce_framebuffer, tile_owner
     from ignis_b200.scene import load_scene
     from oracle.oracle import Oracle
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -39,8 +39,13 @@ def _worker(rank, world, port, out_dir):
         o.render(w, h, spi=spi, iteration=it, fb=fb, threads=2, partition=(rank, world, 32))
     own = tile_owner(w, h, world, 32) == rank
     assert not fb[~own].any(), "a rank wrote outside its tiles"
+    # the two forms of the exchange: gather of the rank's own tiles, sum of whole frames
+    g = TileGather(w, h, rank, world, 32)
+    full = g.run(torch.from_numpy(fb.copy()).reshape(-1), out=torch.zeros(h * w * 3))
     ft = torch.from_numpy(fb)
     reduce_framebuffer(ft, dst=0)
+    if rank == 0:
+        assert torch.equal(full.reshape(h, w, 3), ft), "gather of tiles != sum of frames"
     if rank == 0:
         np.save(os.path.join(out_dir, "reduced.npy"), ft.numpy())
     dist.barrier()
