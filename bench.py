@@ -9,7 +9,7 @@ own harness (scripts/Benchmark.py). Mrays/s = (camera + bounce + shadow rays) / 
     python bench.py [--gpus N] [--steps K] [--warmup W]            this repository's CUDA device
     python bench.py --impl reference [...]                         CPU restatement of the reference's CPU device
 
-For N > 1 it is launched by torchrun (one rank per GPU): the framebuffer is split into 32x32 tiles dealt in rotating round-robin order
+For N > 1 it is launched by torchrun (one rank per GPU): the framebuffer is split into 32x32 tiles dealt along diagonals ((tx + ty) mod N)
 to the ranks (scene replicated, no data-path collective), and the accumulation buffers are summed onto rank 0 with
 one NCCL exchange at the end of the K steps (inside the timed region): every rank sends the pixels of its own tiles to rank 0 (ignis_b200/partition.py TileGather). Total work is fixed => "scaling": "strong".
 
@@ -185,7 +185,7 @@ def workload_config(args, world):
     return {"workload": f"{SCENE} {args.width}x{args.height}, path integrator max_depth 64, spi {args.spi}, seed 0; 1 step = 1 render() iteration "
                         f"({args.spi} spp, {args.width * args.height * args.spi} camera rays); 16 steps = 64 spp (BASELINE.json configs[1])",
             "spi": args.spi, "width": args.width, "height": args.height,
-            "parallelism": f"framebuffer tiles 32x32 in rotating round-robin order over {world} GPU(s), scene replicated, one NCCL gather of the ranks' tiles of the accumulation buffer onto rank 0",
+            "parallelism": f"framebuffer tiles 32x32 dealt along diagonals over {world} GPU(s), scene replicated, one NCCL gather of the ranks' tiles of the accumulation buffer onto rank 0",
             "l2": "no flush needed: every step streams its ray queues through HBM (> 800 MB per step per GPU at N=1, L2 is 126 MB)"}
 
 

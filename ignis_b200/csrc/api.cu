@@ -158,6 +158,8 @@ struct igb200_ctx {
     RenderParams last_rp{}; DevScene last_sc{};
     // partition
     int rank = 0, world = 1, tile = 32;
+    DevBuf<int> tile_table;            // the rank's tiles (row-major tile indices), rebuilt when size / tile / rank / world change
+    long long n_local_tiles = 0, tile_key[5] = {0, 0, 0, 0, 0};
     // stats
     uint64_t launches = 0;             // kernels launched by igb200_render (and its drains) since the last reset
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -856,7 +858,23 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
     rp.tiles_x = (W + rp.tile_w - 1) / rp.tile_w;
     const int tiles_y = (H + rp.tile_h - 1) / rp.tile_h;
     const long long tiles_total = (long long)rp.tiles_x * tiles_y;
-    const long long local_tiles = (tiles_total + rp.world - 1) / rp.world;   // one tile of every group of `world` tiles (wavefront.cuh phase_generate)
+    // this rank's tiles: tile (tx, ty) belongs to rank (tx + ty) mod world -- diagonals, so that no rank is tied to a set of columns or
+    // rows; the list is kept on the device (phase_generate maps its k-th local tile through it)
+    long long local_tiles = tiles_total;
+    rp.tile_table = nullptr;
+    if (rp.world > 1) {
+        const long long key[5] = {W, H, rp.tile_w, rp.rank, rp.world};
+        if (std::memcmp(key, c->tile_key, sizeof(key)) != 0) {
+            std::vector<int> table;
+            for (long long t = 0; t < tiles_total; ++t) if ((int)((t % rp.tiles_x + t / rp.tiles_x) % rp.world) == rp.rank) table.push_back((int)t);
+            CU(cudaStreamSynchronize(c->stream));
+            CU(c->tile_table.upload(table));
+            c->n_local_tiles = (long long)table.size();
+            std::memcpy(c->tile_key, key, sizeof(key));
+        }
+        local_tiles = c->n_local_tiles;
+        rp.tile_table = c->tile_table.p;
+    }
     rp.per_iter = local_tiles * rp.tile_w * rp.tile_h * rp.spi;             // padded ray domain of this rank, one iteration
     const long long total = rp.per_iter * n_iter;                          // ... of the launch (n_iter consecutive iterations)
 

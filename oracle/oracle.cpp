@@ -1310,9 +1310,8 @@ void igo_destroy(void* o) { delete (Oracle*)o; }
 void igo_set_aovs(void* o, float* normals, float* albedo) { ((Oracle*)o)->aov_normals = normals; ((Oracle*)o)->aov_albedo = albedo; }
 
 // Renders one iteration (driver/mapping_cpu.art cpu_trace) over 16x16 tiles with `n_threads` workers into `fb`
-// (W*H*3, accumulated). When part_world > 1 only the rank's tiles are rendered: tile_index enumerates part_tile x part_tile blocks
-// row-major, every group of part_world consecutive tiles holds one tile of each rank, and the rank's place in the group rotates
-// with the group number (tile g * world + s belongs to rank (s - g) mod world) so that no rank is tied to a set of columns. counters = {camera, shadow, bounce} rays.
+// (W*H*3, accumulated). When part_world > 1 only the rank's tiles are rendered: the part_tile x part_tile block in tile column tx and
+// tile row ty belongs to rank (tx + ty) mod part_world (diagonals: no rank is tied to a set of columns or rows). counters = {camera, shadow, bounce} rays.
 void igo_render(void* o, const Settings* st, const StreamRay* rays, float* fb, int n_threads, int use_bvh,
                 int part_rank, int part_world, int part_tile, uint64_t counters[3]) {
     const Scene& sc = ((Oracle*)o)->scene;
@@ -1328,7 +1327,7 @@ void igo_render(void* o, const Settings* st, const StreamRay* rays, float* fb, i
             if (part_world > 1) {
                 const int ptx = (W + part_tile - 1) / part_tile;
                 const int pidx = (y0 / part_tile) * ptx + (x0 / part_tile);
-                if (((pidx % part_world) - (pidx / part_world) % part_world + part_world) % part_world != part_rank) continue;
+                if (((pidx % ptx) + (pidx / ptx)) % part_world != part_rank) continue;
             }
             trace_tile(sc, *st, rays, x0, y0, std::min(W, x0 + T), std::min(H, y0 + T), fb, use_bvh != 0, cnt[tid].data(), rays ? nullptr : ((Oracle*)o)->aov_normals, rays ? nullptr : ((Oracle*)o)->aov_albedo);
         }
