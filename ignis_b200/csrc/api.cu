@@ -135,6 +135,7 @@ struct igb200_ctx {
     int64_t stage_budget = 40 * 1024;  // bytes of shared memory per CTA for the staged scene copy
     int stage_where = 0;               // 1: the whole scene is staged in shared memory, 0: not (selects the k_turn_trace variant)
     int specialise_where = 1;          // option: 0 = always use the generic (per index) trace kernel
+    int carveout = -1;                 // option: preferred shared-memory carve-out of the trace kernels in percent (-1: the driver's choice)
     int stage_partial = 0;             // 1: stage the prefix that fits even if the scene does not fit as a whole
     int refill = 24, min_blocks = 2, vote = 2;
     int split_turns = -1;               // leading turns of an iteration run as separate shade / trace launches (0: all in the persistent kernel)
@@ -210,6 +211,10 @@ static int configure_kernels(igb200_ctx* c) {
     c->blocks_per_sm = nb;
     // split turn kernels
     CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    if (c->carveout >= 0) {
+        CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where), cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout));
+        for (int full = 0; full < 2; ++full) CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote, full != 0, c->stage_where), cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout));
+    }
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where), WF_BLOCK, c->smem_bytes));
     if (nb < 1) return fail(-2, "k_turn_trace does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
     c->grid_turn_trace = nb * c->n_sm;
@@ -434,6 +439,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "specialise_where")) { c->specialise_where = value ? 1 : 0; if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); } return 0; }
+    if (!strcmp(name, "carveout")) { if (value < -1 || value > 100) return fail(-1, "carveout must be -1 or 0..100"); c->carveout = (int)value; if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); } return 0; }
     if (!strcmp(name, "stage_partial")) { c->stage_partial = value ? 1 : 0; if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); } return 0; }
     if (!strcmp(name, "stage_budget")) {
         if (value < 0 || value > 160 * 1024) return fail(-1, "stage_budget must be in [0, 163840] bytes");

@@ -81,3 +81,23 @@ def test_gloo_world2_reduce_equals_single_device(tmp_path):
         o.render(w, h, spi=spi, iteration=it, fb=ref, threads=2)
     assert ref.sum() > 0
     np.testing.assert_array_equal(got, ref)
+
+
+def test_tile_gather_single_process_and_index_sets():
+    """World 1 needs no process group: the frame comes back unchanged. The index sets of all ranks partition the frame."""
+    import torch
+    from ignis_b200.partition import TileGather, tile_owner
+    w, h = 100, 70
+    fb = torch.arange(w * h * 3, dtype=torch.float32)
+    g = TileGather(w, h, 0, 1, 32)
+    assert torch.equal(g.run(fb.clone(), out=torch.zeros_like(fb)), fb)
+    world = 3
+    own = tile_owner(w, h, world, 32).ravel()
+    seen = np.zeros(w * h, np.int32)
+    for r in range(world):
+        tg = TileGather.__new__(TileGather)   # only the bookkeeping: no collective is run here
+        TileGather.__init__(tg, w, h, r, world, 32, dst=r)
+        idx = tg.idx[r].numpy()
+        assert len(idx) == tg.counts[r] <= tg.n_max and (own[idx] == r).all()
+        seen[idx] += 1
+    assert (seen == 1).all()
