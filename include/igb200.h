@@ -209,7 +209,7 @@ int igb200_turn_log(igb200_ctx* ctx, uint32_t* items, uint32_t* trace_ns, uint32
  * >= 16 (out[8..15]): inner-node visits, triangle-leaf visits, entity visits, max visits of one ray, rays traced. */
 int igb200_step_stats(igb200_ctx* ctx, uint64_t out[16]);
 /* Tunables: "capacity" (records per ray queue), "refill" (lanes), "stage_budget" (bytes of shared memory for the staged
- * scene copy; used only if the whole scene fits, unless "stage_partial" = 1; "specialise_where" = 0 disables the trace kernel built for a fully staged scene), "min_blocks" (2|3 CTAs per SM), "vote" (0|2), "defer_permille" (deferred tail threshold, 0 = off), "split_turns"
+ * scene copy; used only if the whole scene fits, unless "stage_partial" = 1; "specialise_where" = 0 disables the trace kernel built for a fully staged scene; "carveout" = preferred shared-memory carve-out of the trace kernels in percent, -1 = the driver's choice), "min_blocks" (2|3 CTAs per SM), "vote" (0|2), "defer_permille" (deferred tail threshold, 0 = off), "split_turns"
  * (leading turns run as separate shade / trace launches), "turn_trace_blocks" (2|3), "wide_rays_per_group", "fuse" (iterations per launch, 0 = automatic), "profile_kernels", "std_aovs" (1: the "Normals" and
  * "Albedo" AOVs of the reference's infobuffer wrapper, technique/internal/infobuffer.art, exist and are written at iteration 0). */
 int igb200_set_option(igb200_ctx* ctx, const char* name, int64_t value);
