@@ -354,6 +354,17 @@ def test_distant_lights_match_oracle():
         assert (stats["CameraRayCount"], stats["ShadowRayCount"], stats["BounceRayCount"]) == tuple(int(x) for x in cnt), sel
 
 
+@pytest.mark.parametrize("selector", ["simple", "hierarchy"])
+def test_many_lights_selectors_match_oracle(selector):
+    """25 finite lights + an environment: a light tree five levels deep, codes of the pdf walk, the 50 % infinite-light branch."""
+    from test_light_selectors import _many_lights_scene
+    t = load_scene(_many_lights_scene(selector))
+    got, ref, stats, cnt = render_both(t, 160, 120, 2, 2)
+    assert ref.sum() > 0
+    assert rel_l2(got, ref) <= REL_L2_TOL
+    assert (stats["CameraRayCount"], stats["ShadowRayCount"], stats["BounceRayCount"]) == tuple(int(x) for x in cnt)
+
+
 def test_standard_aovs_match_oracle():
     """Normals / Albedo AOVs of the reference's infobuffer wrapper (technique/internal/infobuffer.art): first-hit shading normal and
     BSDF albedo, written at iteration 0 only, through the C ABI and through the C++ plugin (which finds the wrapper in the script)."""
