@@ -324,6 +324,45 @@ def run_b200(args):
         kst = dev.getStatistics()
         dev.setOption("profile_kernels", 0)
 
+    # ---- parity of the frames THIS configuration produces (same size, spi, seed, partition and exchange as the timed runs): P iterations
+    # rendered again from iteration 0, brought to rank 0 exactly as in the timed region, and compared there with the oracle's parity build
+    parity = None
+    if args.parity_iters > 0:
+        P = args.parity_iters
+        rt.reset()
+        dev.resetStatistics()
+        rt.IterationCount = 0
+        for _ in range(P):
+            rt.step()
+        frame = None
+        if world > 1:
+            dev.sync()
+            reduce_to_root()
+            if rank == 0:
+                with torch.cuda.stream(stream):
+                    host_t.copy_(scratch, non_blocking=True)
+                stream.synchronize()
+                frame = host_t.numpy().reshape(h, w, 3).copy()
+        else:
+            frame = dev.getFramebufferForHost().copy()
+        pst = dev.getStatistics()
+        cnt = torch.tensor([pst["CameraRayCount"], pst["ShadowRayCount"], pst["BounceRayCount"]], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            from oracle.oracle import Oracle
+            orc = Oracle(tables)
+            ref = np.zeros((h, w, 3), np.float32)
+            for it in range(P):
+                orc.render(w, h, spi=spi, iteration=it, fb=ref)
+            rel = float(np.linalg.norm((frame - ref).ravel()) / max(float(np.linalg.norm(ref.ravel())), 1e-30))
+            parity = {"rel_l2": rel, "tolerance": 1e-4, "ok": bool(rel <= 1e-4), "iterations": P, "n_gpus": world,
+                      "ray_counts": [int(x) for x in cnt.tolist()], "oracle_ray_counts": [int(x) for x in orc.counters],
+                      "ray_counts_equal": [int(x) for x in cnt.tolist()] == [int(x) for x in orc.counters],
+                      "against": "oracle/oracle.cpp (parity build -O2 -ffp-contract=off), same scene / size / spi / seed / iterations; at N > 1 the frame compared is the one "
+                                 "gathered onto rank 0 from the ranks' tiles. diamond_scene has no reference image: the oracle's dielectric is pinned by physics tests (DESIGN.md 4)"}
+            orc.close()
+
     line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -368,6 +407,7 @@ def run_b200(args):
                                     "algorithmic_GBps": phase_bytes[k] / max(v["ms"], 1e-9) / 1e6} for k, v in kt.items()}
         if host is not None:
             line["image_mean"] = float(np.asarray(host).mean() / args.steps)
+        line["parity"] = parity
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -404,6 +444,7 @@ def main():
     ap.add_argument("--spi", type=int, default=4)
     ap.add_argument("--cpu-iters", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-iters", type=int, default=2, help="iterations of the parity check against the oracle (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -106,6 +106,8 @@ struct QueueMem {
 struct igb200_ctx {
     int device = 0, n_sm = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // device -> host copies of finished frames, overlapping the next iteration's kernels
+    cudaEvent_t ev_frame = nullptr, ev_copied = nullptr;
     bool has_scene = false;
     bool scene_full = false;       // the scene uses features only shade_record<true> has (conductors, sphere / spot lights, non-uniform selectors)
     igb200_scene_desc desc{};      // scalar members only are kept
@@ -379,17 +381,23 @@ int igb200_create(int cuda_device, igb200_ctx** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, cuda_device));
     if (prop.major != 10) return fail(-3, "igb200_create: device %d is sm_%d%d; this library is built for sm_100a only", cuda_device, prop.major, prop.minor);
+    if (!prop.cooperativeLaunch) return fail(-3, "igb200_create: device %d does not support cooperative launches", cuda_device);
     igb200_ctx* c = new igb200_ctx();
     c->device = cuda_device;
     c->n_sm = prop.multiProcessorCount;
-    if (!prop.cooperativeLaunch) return fail(-3, "igb200_create: device %d does not support cooperative launches", cuda_device);
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(c->control.alloc(1));
-    CU(cudaMemset(c->control.p, 0, sizeof(Control)));
-    CU(cudaMemset(&c->control.p->turn_t0, 0xFF, 2 * sizeof(unsigned long long)));
-    CU(cudaMallocHost(&c->host_control, sizeof(Control)));
-    std::memset(c->host_control, 0, sizeof(Control));
-    CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
+    const int rc = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CU(c->control.alloc(1));
+        CU(cudaMemset(c->control.p, 0, sizeof(Control)));
+        CU(cudaMemset(&c->control.p->turn_t0, 0xFF, 2 * sizeof(unsigned long long)));
+        CU(cudaMallocHost(&c->host_control, sizeof(Control)));
+        std::memset(c->host_control, 0, sizeof(Control));
+        CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
+        CU(cudaEventCreateWithFlags(&c->ev_frame, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
+        return 0;
+    }();
+    if (rc) { igb200_destroy(c); return rc; }   // nothing leaks on the error paths
     *out = c;
     return 0;
 }
@@ -397,12 +405,16 @@ int igb200_create(int cuda_device, igb200_ctx** out) {
 int igb200_destroy(igb200_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_frame) cudaEventDestroy(c->ev_frame);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
     if (c->host_fb) cudaFreeHost(c->host_fb);
     for (int k = 0; k < 2; ++k) if (c->host_aov[k]) cudaFreeHost(c->host_aov[k]);
     if (c->host_control) cudaFreeHost(c->host_control);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
 }
@@ -504,6 +516,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     }
     // top-level tree first so that its root is node 1
     Bvh8 top = build_bvh8(ent_boxes, 1);
+    int max_shape_depth = 0;
     nodes.insert(nodes.end(), top.nodes.begin(), top.nodes.end());
     for (int s = 0; s < d->n_shapes; ++s) {
         const igb200_lookup_entry& lk = d->shape_lookups[s];
@@ -517,7 +530,13 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
         }
         if (lk.type_id != IGB200_SHAPE_TRIMESH) return fail(-4, "igb200_set_scene: shape %d has unsupported provider %u", s, lk.type_id);
         const int32_t* h = reinterpret_cast<const int32_t*>(p);   // shapes/trimesh.art:77-96
-        const int nf = h[0], nv = h[1], nn = h[2];
+        if (lk.offset + 48 > d->shape_data_bytes) return fail(-1, "igb200_set_scene: shape %d: trimesh header beyond the end of the shapes table", s);
+        const int nf = h[0], nv = h[1], nn = h[2], nt = h[3];
+        // shapes/trimesh.art:77-96: header 16 B + box 32 B, then 16 B per vertex, normal and face, 8 B per texture coordinate
+        if (nf < 0 || nv < 0 || nn < 0 || nt < 0 || (uint64_t)lk.offset + 48 + 16ull * ((uint64_t)nv + (uint64_t)nn + (uint64_t)nf) + 8ull * (uint64_t)nt > d->shape_data_bytes)
+            return fail(-1, "igb200_set_scene: shape %d: trimesh header (%d faces, %d vertices, %d normals, %d texcoords) does not fit the shapes table", s, nf, nv, nn, nt);
+        // normals and texture coordinates are looked up with the vertex indices (shapes/trimesh.art:20-36)
+        if (nf > 0 && (nn < nv || nt < nv)) return fail(-1, "igb200_set_scene: shape %d has fewer normals (%d) or texture coordinates (%d) than vertices (%d)", s, nn, nt, nv);
         const float* verts = reinterpret_cast<const float*>(p) + 12;
         const int32_t* inds = reinterpret_cast<const int32_t*>(verts + 4 * (size_t)nv + 4 * (size_t)nn);
         const int v_start = off4 + 3, n_start = v_start + nv, i_start = n_start + nn;
@@ -530,6 +549,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
             boxes[t] = b;
         }
         Bvh8 bvh = build_bvh8(boxes, 4);
+        max_shape_depth = std::max(max_shape_depth, nf > 4 ? bvh.max_depth : 0);
         const int node_base = (int)nodes.size(), tri_base = (int)(tris.size() / 3);
         shape_root[s] = node_base + 1;
         if (nf == 0) {   // empty mesh: a root without children
@@ -569,6 +589,12 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
             tris.push_back(make_float4(e2[0], e2[1], e2[2], n[2]));
             tri_prim.push_back(t);
         }
+    }
+    {   // Traversal-stack bound: a visit of an inner node leaves at most 7 entries behind, entering an instance one sentinel. Beyond
+        // the stack the walks would drop entries silently (missed hits, light leaks), so such a scene is refused instead.
+        const int need = 7 * (top.max_depth + max_shape_depth) + 2;
+        const int have = std::min(STACK_SIZE, WIDE_STACK);
+        if (need > have) return fail(-4, "igb200_set_scene: BVH too deep for the traversal stack (top level %d + shape level %d levels need %d entries, %d available)", top.max_depth, max_shape_depth, need, have);
     }
     // ---- node order: breadth-first across ALL trees (top-level root first, then level by level over every shape's tree), so that
     // the part of the node array that is staged in shared memory (configure_kernels) holds the top of every tree instead of
@@ -770,7 +796,10 @@ int igb200_upload_framebuffer(igb200_ctx* c, const char* aov, const float* host_
 
 int igb200_stream(igb200_ctx* c, void** cuda_stream) {
     if (!c || !cuda_stream) return fail(-1, "igb200_stream: null argument");
-    { const int r = flush_queued(c); if (r) return r; }   // whatever the caller enqueues next is ordered after every render() so far
+    // whatever the caller enqueues next is ordered after every render() so far INCLUDING its deferred tail: the drain launches are
+    // asynchronous, so this does not wait for the device (a gather ordered after flush_queued() alone read an incomplete frame)
+    CU(cudaSetDevice(c->device));
+    { const int r = drain(c); if (r) return r; }
     *cuda_stream = (void*)c->stream;
     return 0;
 }
@@ -948,6 +977,7 @@ int igb200_render(igb200_ctx* c, const igb200_settings* st, const igb200_ray* ra
     if (!c->has_scene) return fail(-1, "igb200_render: no scene assigned");
     if (st->spi < 1) return fail(-1, "igb200_render: spi must be >= 1");
     if (rays) {   // igtrace: synchronous, never fused
+        if (n_rays < 1 || (long long)n_rays * st->spi >= ((long long)1 << 31)) return fail(-1, "igb200_render: %zu rays at %d samples per iteration do not fit the 32-bit ray id", n_rays, st->spi);
         { const int r = flush_queued(c); if (r) return r; }
         return launch_iterations(c, st, 1, rays, n_rays);
     }

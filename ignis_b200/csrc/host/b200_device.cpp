@@ -50,7 +50,7 @@ void B200Device::assignScene(const SceneSettings& settings) { mScene = settings;
 void B200Device::resize(size_t width, size_t height) {
     if (!mCtx) return;
     if (igb200_resize(mCtx, (int)width, (int)height) != 0) { error(igb200_last_error()); return; }
-    mWidth = width; mHeight = height; mHostPtr = nullptr;
+    mWidth = width; mHeight = height; mHostPtrs.clear();
 }
 
 // Device.cpp:1684-1690 drops cached uploads; the next render() re-uploads the scene.
@@ -170,7 +170,7 @@ static const char* aov_name(const std::string& name) { return (name.empty() || n
 IG::IRenderDevice::AOVAccessor B200Device::getFramebufferForHost(const std::string& name, bool) {
     float* p = nullptr;
     if (!mCtx || igb200_framebuffer(mCtx, aov_name(name), &p) != 0) { error(igb200_last_error()); return AOVAccessor{nullptr}; }
-    mHostPtr = p;
+    mHostPtrs[aov_name(name) ? name : std::string()] = p;
     return AOVAccessor{p};
 }
 IG::IRenderDevice::AOVAccessor B200Device::getFramebufferForDevice(const std::string& name, bool) {
@@ -182,10 +182,17 @@ void B200Device::clearFramebuffer(const std::string& name) { if (mCtx && igb200_
 void B200Device::clearAllFramebuffer() { if (mCtx && igb200_clear(mCtx, nullptr) != 0) error(igb200_last_error()); }
 // Device.cpp:1724-1736: pushes the host copy the caller may have modified back to the device
 void B200Device::syncFramebufferHostToDevice(const std::string& name) {
-    if (!mCtx || !mHostPtr) return;
-    if (igb200_upload_framebuffer(mCtx, aov_name(name), mHostPtr) != 0) error(igb200_last_error());
+    if (!mCtx) return;
+    const auto it = mHostPtrs.find(aov_name(name) ? name : std::string());   // the host copy of THIS AOV, never another one's
+    if (it == mHostPtrs.end() || !it->second) return;                      // never mapped for the host: nothing the caller could have changed
+    if (igb200_upload_framebuffer(mCtx, aov_name(name), it->second) != 0) error(igb200_last_error());
 }
-void B200Device::syncAllFramebufferHostToDevice() { syncFramebufferHostToDevice(""); }
+// Device.cpp:1724-1736 maps every AOV: here every AOV the host has a copy of
+void B200Device::syncAllFramebufferHostToDevice() {
+    std::vector<std::string> names;
+    for (const auto& kv : mHostPtrs) names.push_back(kv.first);
+    for (const std::string& n : names) syncFramebufferHostToDevice(n);
+}
 
 // Named scratch buffers belong to techniques outside this path (photon mapper, AEPT): none exist here.
 size_t B200Device::getBufferSizeInBytes(const std::string&) { return 0; }

@@ -76,7 +76,7 @@ private:
     int mStdAovs = -1;                       // Normals / Albedo AOVs currently enabled on the device (-1: not set yet)
     std::vector<uint8_t> mDescriptorBytes;   // materials + lights + camera + technique of the scene on the device
     std::vector<float> mHostFramebuffer;     // what getFramebufferForHost handed out, for syncFramebufferHostToDevice
-    float* mHostPtr = nullptr;
+    std::unordered_map<std::string, float*> mHostPtrs;   // per AOV ("" = Color): the context-owned host buffer last handed out
     IG::Statistics mStats;
     std::string mError;
 };

@@ -196,32 +196,36 @@ def test_tile_partition_sums_to_full_frame():
     assert rel_l2(acc, full) <= 1e-6
 
 
-@pytest.mark.parametrize("scene", ["diamond_scene.json", "primitives.json", "synthetic_room.json"])
-def test_full_size_properties(scene):
-    """BASELINE configs C2 / C3 / C4 (stand-in) at full size (1920x1080, spi 4): size-independent properties instead of the
-    slow oracle -- exact camera-ray count, finite non-negative image, same seed => same image, and agreement of the
-    down-sampled frame with the oracle rendered at 1/8 resolution."""
+@pytest.mark.parametrize("scene,world", [("diamond_scene.json", 1), ("primitives.json", 1), ("synthetic_room.json", 4)])
+def test_full_size_configs_match_oracle(scene, world):
+    """BASELINE configs C2 / C3 / C4 (stand-in) at THEIR OWN size -- 1920x1080, spi 4, one iteration -- against the oracle:
+    relative L2 <= 1e-4 (north_star) and exactly the oracle's camera / shadow / bounce ray counts. C4 is specified on 4 GPUs: its
+    frame is rendered as the four tile partitions `setPartition(r, 4)` of a 4-rank run (one after the other on this GPU; the
+    partitions are independent, tests/test_multi_gpu.py runs them on separate devices) and summed as the exchange does.
+    diamond_scene has no reference image: parity on C2 rests on GPU == oracle plus the oracle's physics pins."""
+    w, h, spi = 1920, 1080, 4
     t = load_scene(scene_path(scene))
-    with Runtime(t, 1920, 1080, spi=4) as rt:
-        rt.step()
-        a = rt.getFramebufferForHost().copy()
-        st = rt.device.getStatistics()
-        rt.reset()
-        rt.step()
-        b = rt.getFramebufferForHost().copy()
-    assert st["CameraRayCount"] == 1920 * 1080 * 4
-    assert np.isfinite(a).all() and (a >= 0).all()
-    assert rel_l2(a, b) <= 1e-6                              # same seed, same iteration -> same image (up to atomics order)
     o = Oracle(t)
-    ref = np.zeros((135, 240, 3), np.float32)
-    for it in range(4):
-        o.render(240, 135, spi=4, iteration=it, fb=ref)
-    small = a.reshape(135, 8, 240, 8, 3).mean(axis=(1, 3))
-    assert small.mean() == pytest.approx((ref / 4).mean(), rel=0.05)
-    # rays per camera ray are a property of the scene, not of the resolution
-    per_cam = (st["ShadowRayCount"] + st["BounceRayCount"]) / st["CameraRayCount"]
-    per_cam_ref = float(o.counters[1] + o.counters[2]) / float(o.counters[0])
-    assert per_cam == pytest.approx(per_cam_ref, rel=0.03)
+    ref = o.render(w, h, spi=spi, iteration=0)
+    acc = np.zeros_like(ref)
+    counts = np.zeros(3, np.int64)
+    for r in range(world):
+        with Runtime(t, w, h, spi=spi) as rt:
+            rt.device.setPartition(r, world, 32)
+            rt.step()
+            part = rt.getFramebufferForHost().copy()
+            st = rt.device.getStatistics()
+            if world == 1:   # same seed, same iteration -> same image up to the order of the float atomics
+                rt.reset()
+                rt.step()
+                assert rel_l2(rt.getFramebufferForHost(), part) <= 1e-6
+        assert ((part != 0) & (acc != 0)).sum() == 0          # the ranks' tiles are disjoint
+        acc += part
+        counts += (st["CameraRayCount"], st["ShadowRayCount"], st["BounceRayCount"])
+    assert np.isfinite(acc).all() and (acc >= 0).all()
+    assert counts[0] == w * h * spi
+    assert tuple(int(x) for x in counts) == tuple(int(x) for x in o.counters)
+    assert rel_l2(acc, ref) <= REL_L2_TOL
 
 
 def test_deferred_tail_is_invisible():
