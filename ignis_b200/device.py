@@ -47,7 +47,14 @@ class SceneDesc(C.Structure):
                 ("finite_lights", C.c_void_p), ("n_finite", C.c_int32),
                 ("camera", CameraDesc), ("technique", TechniqueDesc),
                 ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3),
-                ("selector_data", C.c_void_p), ("n_selector_data", C.c_int32)]
+                ("selector_data", C.c_void_p), ("n_selector_data", C.c_int32),
+                ("textures", C.c_void_p), ("n_textures", C.c_int32),
+                ("images", C.c_void_p), ("n_images", C.c_int32),
+                ("aux_data", C.c_void_p), ("n_aux_data", C.c_int32)]
+
+
+class ImageDesc(C.Structure):
+    _fields_ = [("format", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("reserved", C.c_int32), ("pixels", C.c_void_p)]
 
 
 class Settings(C.Structure):
@@ -136,6 +143,16 @@ def make_scene_desc(tables: SceneTables):
     sel = np.ascontiguousarray(getattr(tables, "selector_data", np.zeros(0, np.float32)), np.float32)
     keep.append(sel)
     d.selector_data, d.n_selector_data = (sel.ctypes.data if sel.size else None), int(sel.size)
+    tex = np.ascontiguousarray(getattr(tables, "textures", np.zeros(0, np.uint8)))
+    aux = np.ascontiguousarray(getattr(tables, "aux_data", np.zeros(0, np.float32)), np.float32)
+    imgs = [(int(f), np.ascontiguousarray(a)) for f, a in getattr(tables, "images", [])]
+    img_descs = (ImageDesc * max(len(imgs), 1))()
+    for i, (f, a) in enumerate(imgs):
+        img_descs[i] = ImageDesc(f, a.shape[1], a.shape[0], 0, a.ctypes.data)
+    keep += [tex, aux, imgs, img_descs]
+    d.textures, d.n_textures = (tex.ctypes.data if tex.size else None), int(tex.shape[0]) if tex.size else 0
+    d.images, d.n_images = (C.cast(img_descs, C.c_void_p).value if imgs else None), len(imgs)
+    d.aux_data, d.n_aux_data = (aux.ctypes.data if aux.size else None), int(aux.size)
     return d, keep
 
 

@@ -50,11 +50,24 @@ LIGHT_SPHERE_AREA = 4  # make_area_light + make_sphere_area_emitter (light/area.
 LIGHT_SPOT = 5         # make_spot_light (light/spot.art:8-44)
 LIGHT_SUN = 6          # make_sun_light (light/sun.art:10-48): infinite, p = direction towards the sun, cos(angle / 2), radiance
 LIGHT_DIRECTIONAL = 7  # make_directional_light (light/directional.art): infinite delta light, p = direction of travel, irradiance
+LIGHT_ENV_TEXTURED = 8  # make_environment_light_textured (light/env.art:112-160): env map / sky with a 2-D cdf
+LIGHT_ENV_TEX = 9       # make_environment_light over a texture (light/env.art:161-167), sampled uniformly
+
+MICROFACET_DELTA, MICROFACET_VNDF_GGX = 0, 1      # BSDF::setupRoughness (bsdf/BSDF.cpp:53-98), core/microfacet.art:403-425
+MAP_NONE, MAP_BUMP, MAP_NORMAL = 0, 1, 2           # bsdf/map.art:56-68
+TEX_CHECKERBOARD, TEX_IMAGE = 0, 1                 # texture/checkerboard.art, texture/image.art
+FILTERS = {"nearest": 0, "bilinear": 1}            # anything else is the bicubic filter (ImagePattern.cpp:26-30)
+FILTER_BICUBIC = 2
+BORDERS = {"clamp": 1, "mirror": 2}                # anything else repeats (ImagePattern.cpp:32-39)
+IMAGE_RGBA8, IMAGE_MONO8, IMAGE_RGBA32F = 0, 1, 2
 
 LOOKUP_DTYPE = np.dtype([("type_id", "<u4"), ("flags", "<u4"), ("offset", "<u8")])
 LEAF_DTYPE = np.dtype([("min", "<f4", 3), ("entity_id", "<i4"), ("max", "<f4", 3), ("shape_id", "<i4"),
                        ("local", "<f4", 12), ("flags", "<u4"), ("mat_id", "<i4"), ("user1", "<i4"), ("user2", "<i4")])
-MATERIAL_DTYPE = np.dtype([("bsdf", "<i4"), ("light_id", "<i4"), ("p", "<f4", 14)])
+MATERIAL_DTYPE = np.dtype([("bsdf", "<i4"), ("light_id", "<i4"), ("p", "<f4", 14), ("tex", "<i4", 2), ("distribution", "<i4"),
+                           ("alpha_u", "<f4"), ("alpha_v", "<f4"), ("map_kind", "<i4"), ("map_tex", "<i4"), ("map_strength", "<f4"), ("reserved", "<i4", 8)])
+TEXTURE_DTYPE = np.dtype([("type", "<i4"), ("image", "<i4"), ("filter", "<i4"), ("border_u", "<i4"), ("border_v", "<i4"), ("reserved", "<i4", 3),
+                          ("transform", "<f4", 6), ("p", "<f4", 10)])
 LIGHT_DTYPE = np.dtype([("type", "<i4"), ("entity_id", "<i4"), ("p", "<f4", 30)])
 CAMERA_DTYPE = np.dtype([("eye", "<f4", 3), ("dir", "<f4", 3), ("up", "<f4", 3), ("fov", "<f4"),
                          ("fov_vertical", "<i4"), ("aspect", "<f4"), ("tmin", "<f4"), ("tmax", "<f4")])
@@ -64,7 +77,7 @@ SELECTOR_UNIFORM = 0     # make_uniform_light_selector (light/light_selector.art
 SELECTOR_CDF = 1         # "simple": make_cdf_light_selector over the lights' flux (light_selector.art:46-77, LoaderLight.cpp:440-476)
 SELECTOR_HIERARCHY = 2   # make_hierarchy_light_selector (light_selector.art:79-110, light/light_hierarchy.art)
 assert LOOKUP_DTYPE.itemsize == 16 and LEAF_DTYPE.itemsize == 96
-assert MATERIAL_DTYPE.itemsize == 64 and LIGHT_DTYPE.itemsize == 128
+assert MATERIAL_DTYPE.itemsize == 128 and LIGHT_DTYPE.itemsize == 128 and TEXTURE_DTYPE.itemsize == 96
 assert CAMERA_DTYPE.itemsize == 56 and TECHNIQUE_DTYPE.itemsize == 20
 
 
@@ -91,6 +104,11 @@ class SceneTables:
     entity_names: list[str] = field(default_factory=list)
     material_names: list[str] = field(default_factory=list)
     selector_data: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))   # light_cdf.bin / light_hierarchy.bin as f32 words
+    textures: np.ndarray = field(default_factory=lambda: np.zeros(0, TEXTURE_DTYPE))
+    images: list = field(default_factory=list)       # (format, array): RGBA8 -> (H, W, 4) u8, MONO8 -> (H, W) u8, RGBA32F -> (H, W, 4) f32; rows bottom-up
+    aux_data: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))        # 2-D cdfs of textured environment lights
+    texture_names: list = field(default_factory=list)
+    embedded_lights: bool = False                    # the finite lights come from embedded fix-tables (LoaderLight.h:27)
     sun_params: dict = field(default_factory=dict)    # infinite light index -> (direction before vec3_normalize, angle in degrees, radiance given?, colour as given)
     spot_angles: dict = field(default_factory=dict)   # finite light index -> (cutoff, falloff) in degrees (the descriptors hold the cosines)
 
@@ -371,6 +389,232 @@ def _serialize_trimesh(m: TriMesh, lo: np.ndarray, hi: np.ndarray) -> bytes:
     return head + box + v4.tobytes() + n4.tobytes() + m.indices.astype("<u4").tobytes() + m.texcoords.astype("<f4").tobytes()
 
 
+# ------------------------------------------------------------------ images and textures
+def read_png(path: str) -> np.ndarray:
+    """Minimal PNG decoder (8-bit grey / grey+alpha / RGB / RGBA, non-interlaced) -> (H, W, C) u8, rows top-down as in the file."""
+    import struct
+    import zlib
+    with open(path, "rb") as fh:
+        data = fh.read()
+    if data[:8] != b"\x89PNG\r\n\x1a\n":
+        raise SceneError(f"{path}: not a PNG file")
+    pos, idat, hdr = 8, [], None
+    while pos < len(data):
+        n, kind = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        pos += 12 + n
+        if kind == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", body)
+        elif kind == b"IDAT":
+            idat.append(body)
+        elif kind == b"IEND":
+            break
+    w, h, depth, ctype, _, _, interlace = hdr
+    if depth != 8 or interlace != 0 or ctype not in (0, 2, 4, 6):
+        raise SceneError(f"{path}: only 8-bit non-interlaced grey / RGB / RGBA PNG files are supported")
+    ch = {0: 1, 2: 3, 4: 2, 6: 4}[ctype]
+    raw = np.frombuffer(zlib.decompress(b"".join(idat)), np.uint8).reshape(h, 1 + w * ch)
+    out = np.zeros((h, w * ch), np.uint8)
+    prev = np.zeros(w * ch, np.int32)
+    for y in range(h):
+        ft, line = int(raw[y, 0]), raw[y, 1:].astype(np.int32)
+        if ft == 0:
+            cur = line
+        elif ft == 2:
+            cur = (line + prev) & 255
+        elif ft == 1:      # Sub: prefix sums per channel
+            cur = line.reshape(w, ch).cumsum(axis=0).reshape(-1) & 255
+        else:              # Average / Paeth depend on the reconstructed left neighbour: pixel by pixel
+            cur = np.zeros(w * ch, np.int32)
+            for i in range(w * ch):
+                a = cur[i - ch] if i >= ch else 0
+                b = prev[i]
+                if ft == 3:
+                    cur[i] = (line[i] + ((a + b) >> 1)) & 255
+                else:
+                    c = prev[i - ch] if i >= ch else 0
+                    pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+                    cur[i] = (line[i] + (a if pa <= pb and pa <= pc else (b if pb <= pc else c))) & 255
+        out[y] = cur
+        prev = cur
+    return out.reshape(h, w, ch)
+
+
+def srgb_byte_to_linear_byte() -> np.ndarray:
+    """byte_color_to_linear for all 256 values (src/runtime/Image.cpp:40-51): floor(srgb_invgamma(c / 255) * 255) in f32."""
+    c = (np.arange(256, dtype=F) / F(255)).astype(F)
+    lin = np.where(c <= F(0.04045), c / F(12.92), np.power(((c + F(0.055)) / F(1.055)).astype(F), F(2.4)).astype(F)).astype(F)
+    return np.minimum(255, np.floor(lin * F(255))).astype(np.uint8)
+
+
+def load_image_for_device(path: str, linear_hint: bool = False):
+    """An image as the reference's device holds it (igb200_image): (format, array), rows bottom-up.
+    8-bit files are `packed` (Image::isPacked, Image.cpp:358-365) and mapped to linear bytes unless the texture says `linear`
+    (Image::loadAsPacked, Image.cpp:714-810 -- NB its `linear` argument means "already linear"); .npy / .npz hold float RGB(A)
+    fixtures made from the reference's EXR files by tools/make_golden.py (Image::load, Image.cpp:500-712)."""
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".png":
+        px = read_png(path)[::-1]                               # stbi_set_flip_vertically_on_load(1)
+        lut = np.arange(256, dtype=np.uint8) if linear_hint else srgb_byte_to_linear_byte()
+        h, w, ch = px.shape
+        if ch == 1:
+            return IMAGE_MONO8, np.ascontiguousarray(lut[px[:, :, 0]])
+        if ch == 2:                                             # grey + alpha: stb re-reads it as RGBA (Image.cpp:730-734)
+            px = np.concatenate([px[:, :, :1]] * 3 + [px[:, :, 1:]], axis=2)
+        out = np.full((h, w, 4), 255, np.uint8)
+        out[:, :, :3] = lut[px[:, :, :3]]
+        if px.shape[2] == 4:
+            out[:, :, 3] = px[:, :, 3]
+        return IMAGE_RGBA8, np.ascontiguousarray(out)
+    if ext in (".npy", ".npz"):
+        a = np.load(path)
+        if ext == ".npz":
+            a = a[a.files[0]]
+        a = np.asarray(a, F)
+        if a.ndim != 3 or a.shape[2] not in (3, 4):
+            raise SceneError(f"{path}: expected an (H, W, 3|4) array, rows top-down as in the image file")
+        out = np.ones((a.shape[0], a.shape[1], 4), F)
+        out[:, :, :a.shape[2]] = a
+        return IMAGE_RGBA32F, np.ascontiguousarray(out[::-1])   # Image::flipY
+    raise SceneError(f"image file type '{ext}' is outside the supported path (PNG, or .npy / .npz fixtures of float images)")
+
+
+def transform_2d(v) -> np.ndarray:
+    """LoaderUtils::inlineTransformAs2d (LoaderUtils.cpp:40-46): rows 0 and 1 of [linear 2x2 | translation xy]."""
+    t = parse_transform(v)
+    return np.array([t[0, 0], t[0, 1], t[0, 3], t[1, 0], t[1, 1], t[1, 3]], F)
+
+
+def image_pixels_f32(fmt: int, arr: np.ndarray) -> np.ndarray:
+    """(H, W, 3) f32 pixel values of a device image (driver/image.art:9-34)."""
+    if fmt == IMAGE_RGBA32F:
+        return arr[:, :, :3].astype(F)
+    if fmt == IMAGE_MONO8:
+        g = (arr.astype(F) / F(255)).astype(F)
+        return np.stack([g, g, g], axis=2)
+    return (arr[:, :, :3].astype(F) / F(255)).astype(F)
+
+
+def _border_np(mode: int, x: np.ndarray, w: int) -> np.ndarray:
+    if mode == 1:
+        return np.clip(x, 0, w - 1)
+    if mode == 2:
+        t = np.where(x < 0, -1 - x, x)
+        i = t // w
+        k = t - i * w
+        return np.where((i & 1) == 0, w - 1 - k, k)
+    t = np.fmod(x, w)            # C remainder (sign of the dividend), as Artic's % on i32
+    return np.where(t < 0, t + w, t)
+
+
+def eval_texture_np(tex, images, u: np.ndarray, v: np.ndarray) -> np.ndarray:
+    """Host-side texture evaluation on arrays of uv (f32), for baking (what the reference does with ig_bake_shader,
+    entrypoints/bake.art:1-27). Same formulas as the device (texture/checkerboard.art, texture/image.art). Returns (..., 3) f32."""
+    u, v = np.asarray(u, F), np.asarray(v, F)
+    m = tex["transform"].astype(F)
+    fma = lambda a, b, c: (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(F)   # one rounding, as fmaf
+    u2 = fma(u, m[0], fma(v, m[1], np.full_like(u, m[2] * F(1))))
+    v2 = fma(u, m[3], fma(v, m[4], np.full_like(u, m[5] * F(1))))
+    if int(tex["type"]) == TEX_CHECKERBOARD:
+        p = tex["p"].astype(F)
+        wrap2 = lambda a: (a - F(2) * np.floor(a / F(2))).astype(F)
+        px = (wrap2((u2 * p[0]).astype(F)).astype(np.int32) % 2) == 0
+        py = (wrap2((v2 * p[1]).astype(F)).astype(np.int32) % 2) == 0
+        return np.where((px != py)[..., None], p[2:5], p[5:8]).astype(F)
+    fmt, arr = images[int(tex["image"])]
+    pix = image_pixels_f32(fmt, arr)
+    h, w = pix.shape[:2]
+    flt, bu, bv = int(tex["filter"]), int(tex["border_u"]), int(tex["border_v"])
+    px = lambda x, y: pix[_border_np(bv, y, h), _border_np(bu, x, w)]
+    if flt == 0:
+        return px(np.floor(u2 * F(w)).astype(np.int64), np.floor(v2 * F(h)).astype(np.int64))
+    uu, vv = (u2 * F(w) - F(0.5)).astype(F), (v2 * F(h) - F(0.5)).astype(F)
+    ix, iy = np.floor(uu).astype(np.int64), np.floor(vv).astype(np.int64)
+    fx, fy = (uu - np.floor(uu)).astype(F)[..., None], (vv - np.floor(vv)).astype(F)[..., None]
+    lerp = lambda a, b, t: ((F(1) - t) * a + t * b).astype(F)
+    if flt == 1:
+        return lerp(lerp(px(ix, iy), px(ix + 1, iy), fx), lerp(px(ix, iy + 1), px(ix + 1, iy + 1), fx), fy)
+    w0 = lambda a: (a * (a * (-a + F(3)) - F(3)) + F(1)) / F(6)
+    w1 = lambda a: (a * a * (F(3) * a - F(6)) + F(4)) / F(6)
+    w2 = lambda a: (a * (a * (F(-3) * a + F(3)) + F(3)) + F(1)) / F(6)
+    w3 = lambda a: (a * a * a) / F(6)
+    g0, g1 = (lambda a: w0(a) + w1(a)), (lambda a: w2(a) + w3(a))
+    h0, h1 = (lambda a: (w1(a) / g0(a)) - F(1)), (lambda a: (w3(a) / g1(a)) + F(1))
+    fx1, fy1 = fx[..., 0], fy[..., 0]
+    ix0 = np.floor(ix.astype(F) + h0(fx1) + F(0.5)).astype(np.int64); iy0 = np.floor(iy.astype(F) + h0(fy1) + F(0.5)).astype(np.int64)
+    ix1 = np.floor(ix.astype(F) + h1(fx1) + F(0.5)).astype(np.int64); iy1 = np.floor(iy.astype(F) + h1(fy1) + F(0.5)).astype(np.int64)
+    return ((px(ix0, iy0) * (g0(fx) * g0(fy)) + px(ix1, iy0) * (g1(fx) * g0(fy))) + (px(ix0, iy1) * (g0(fx) * g1(fy)) + px(ix1, iy1) * (g1(fx) * g1(fy)))).astype(F)
+
+
+def bake_texture(tex, images, max_w: int = 1024, max_h: int = 512) -> np.ndarray:
+    """ShadingTree::bakeTexture with TextureBakeOptions{0, 0, 1024, 512} (ShadingTree.cpp:580-630, EnvironmentLight.cpp:52): the texture on a
+    grid uv = (x / (w - 1), y / (h - 1)), resolution = the image's, capped. Returns (h, w, 3) f32."""
+    if int(tex["type"]) == TEX_IMAGE:
+        fmt, arr = images[int(tex["image"])]
+        h, w = arr.shape[:2]
+    else:
+        w = h = 1
+    w, h = max(1, min(max_w, w)), max(1, min(max_h, h))
+    xs = (np.arange(w, dtype=F) / F(max(w - 1, 1))).astype(F) if w > 1 else np.full(1, np.nan, F)
+    ys = (np.arange(h, dtype=F) / F(max(h - 1, 1))).astype(F) if h > 1 else np.full(1, np.nan, F)
+    uu, vv = np.meshgrid(xs, ys)
+    return eval_texture_np(tex, images, uu, vv)
+
+
+SKY_KEYS = ("ground", "turbidity", "direction", "sun_direction", "elevation", "azimuth", "year", "month", "day", "hour", "minute", "seconds",
+            "latitude", "longitude", "timezone")
+SKY_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scenes", "textures", "sky")
+
+
+def sky_key(lj: dict) -> str:
+    import hashlib
+    return hashlib.sha1(json.dumps({k: lj[k] for k in SKY_KEYS if k in lj}, sort_keys=True).encode()).hexdigest()[:12]
+
+
+def sky_image(lj: dict) -> np.ndarray:
+    """The sky model image of a `sky` light as the device holds it: (256, 512, 4) f32, rows bottom-up. The model itself (Hosek-Wilkie
+    coefficient tables, sun position from date and place: src/runtime/skysun/) is loader-side data production outside the hot path;
+    its output for a given parameter set is a fixture under scenes/textures/sky/ made by tools/make_sky.py from the reference's sources."""
+    path = os.path.join(SKY_DIR, f"sky_{sky_key(lj)}.npz")
+    if not os.path.exists(path):
+        raise SceneError(f"no baked sky image for these parameters ({path}); run tools/make_sky.py with the reference tree present")
+    a = np.load(path)["rgb"].astype(F)       # file order: row 0 = zenith (SkyModel.cpp:30-52)
+    out = np.ones((a.shape[0], a.shape[1], 4), F)
+    out[:, :, :3] = a
+    return np.ascontiguousarray(out[::-1])   # Image::load flips (Image.cpp:708)
+
+
+def cdf2d_for_image(rgb: np.ndarray, premultiply_sin: bool = True, compensate: bool = True) -> np.ndarray:
+    """CDF::computeForImage (src/runtime/CDF.cpp:46-150): [marginal (H) | H conditionals (W)], each without the leading 0.
+    `rgb`: (H, W, 3) f32 in memory order (rows as the device sees them)."""
+    rgb = np.asarray(rgb, F)
+    h, w, _ = rgb.shape
+    resp = lambda a: ((np.maximum(a[..., 0], F(0)) + np.maximum(a[..., 1], F(0)) + np.maximum(a[..., 2], F(0))) / F(3)).astype(F)
+    defect = F(0)
+    if compensate:   # computeMISDefect: sequential f32 sum of response / width over all pixels, then / height
+        r = resp(rgb).reshape(-1)
+        d = F(np.cumsum((r / F(w)).astype(F), dtype=F)[-1] / F(h))
+        defect = F(0) if abs(float(r.min()) - float(d)) < 1e-4 else d
+    rr = resp((rgb - defect).astype(F))
+    cond = np.cumsum(rr, axis=1, dtype=F)                      # np.add.accumulate is sequential in the array's dtype
+    total = cond[:, -1].copy()
+    sin_row = np.sin((F(PI) * (np.arange(h, dtype=F) + F(0.5)) / F(h)).astype(F)).astype(F)
+    marg = (total * sin_row).astype(F) if premultiply_sin else total.copy()
+    ok = total > F(1e-5)
+    cond[ok] = (cond[ok] * (F(1) / total[ok])[:, None]).astype(F)
+    if (~ok).any():
+        ramp = (np.arange(1, w + 1, dtype=F) * F(F(1) / F(w))).astype(F)
+        cond[~ok] = ramp
+    cond[:, -1] = 1
+    marg = np.cumsum(marg, dtype=F)
+    if marg[-1] > F(1e-5):
+        marg = (marg * F(F(1) / marg[-1])).astype(F)
+    else:
+        marg = (np.arange(1, h + 1, dtype=F) * F(F(1) / F(h))).astype(F)
+    marg[-1] = 1
+    return np.concatenate([marg, cond.reshape(-1)]).astype(F)
+
+
 # ------------------------------------------------------------------ loader
 def light_direction(lj) -> np.ndarray:
     """LoaderUtils::getDirection (src/runtime/loader/LoaderUtils.cpp:89-106, skysun/ElevationAzimuth.h:15-30): `direction` (or
@@ -526,6 +770,48 @@ def load_scene(path, width: int | None = None, height: int | None = None,
     technique["nee"] = 1 if tech.get("nee", True) else 0
 
     bsdfs = {b["name"]: b for b in doc.get("bsdfs", [])}
+
+    # ---- textures (LoaderTexture.cpp:60-70, pattern/{Image,CheckerBoard}Pattern.cpp): declared lazily, in order of first use
+    tex_json = {t["name"]: t for t in doc.get("textures", [])}
+    tex_ids: dict[str, int] = {}
+    tex_recs, images, image_ids, aux_words = [], [], {}, []
+
+    def texture_id(name: str) -> int:
+        if name in tex_ids:
+            return tex_ids[name]
+        tj = tex_json[name]
+        tt = tj.get("type", "").lower()
+        rec = np.zeros((), TEXTURE_DTYPE)
+        rec["transform"] = transform_2d(tj.get("transform"))
+        if tt in ("image", "bitmap"):
+            fname = tj["filename"]
+            key = (fname, bool(tj.get("linear", False)))
+            if key not in image_ids:
+                image_ids[key] = len(images)
+                images.append(load_image_for_device(fname, key[1]))
+            rec["type"], rec["image"] = TEX_IMAGE, image_ids[key]
+            rec["filter"] = FILTERS.get(str(tj.get("filter_type", "bicubic")), FILTER_BICUBIC)
+            if "wrap_mode_u" in tj:
+                rec["border_u"] = BORDERS.get(str(tj.get("wrap_mode_u", "repeat")), 0)
+                rec["border_v"] = BORDERS.get(str(tj.get("wrap_mode_v", "repeat")), 0)
+            else:
+                rec["border_u"] = rec["border_v"] = BORDERS.get(str(tj.get("wrap_mode", "repeat")), 0)
+        elif tt == "checkerboard":
+            rec["type"] = TEX_CHECKERBOARD
+            rec["p"][0], rec["p"][1] = float(tj.get("scale_x", 2.0)), float(tj.get("scale_y", 2.0))
+            rec["p"][2:5] = _color(tj.get("color0"), (0, 0, 0))
+            rec["p"][5:8] = _color(tj.get("color1"), (1, 1, 1))
+        else:
+            raise SceneError(f"texture type '{tt}' is outside the supported path (image / bitmap, checkerboard)")
+        tex_ids[name] = len(tex_recs)
+        tex_recs.append(rec)
+        return tex_ids[name]
+
+    def color_or_tex(v, default):
+        """A colour property: (rgb, texture id or -1). A string naming a texture is the PExpr `name` = tex_name(uv)."""
+        if isinstance(v, str) and v.strip() in tex_json:
+            return np.zeros(3, F), texture_id(v.strip())
+        return _color(v, default), -1
     shapes_json = {s["name"]: s for s in doc.get("shapes", [])}
     entities_json = doc.get("entities", [])
     lights_json = doc.get("lights", [])
@@ -627,6 +913,7 @@ def load_scene(path, width: int | None = None, height: int | None = None,
     inf_l, fin_l = [], []
     fin_sel = []   # per finite light: (position, direction or None, flux) -- Light::position/direction/computeFlux, for the light selectors
     spot_angles: dict = {}
+    point_raw: dict = {}
     sun_params: dict = {}
     fin_of_entity: dict[str, int] = {}
     for lj in lights_json:
@@ -636,8 +923,50 @@ def load_scene(path, width: int | None = None, height: int | None = None,
         if lt in ("env", "constant", "uniform", "envmap"):
             rad = lj.get("radiance", [1, 1, 1])
             scale = _color(lj.get("scale"), (1, 1, 1))
-            rec["type"] = LIGHT_ENV_CONST
-            rec["p"][0:3] = (scale * _color(rad, (1, 1, 1))).astype(F)   # color_mul(scale, tex)
+            rgb, tid = color_or_tex(rad, (1, 1, 1))
+            if tid < 0:
+                rec["type"] = LIGHT_ENV_CONST
+                rec["p"][0:3] = (scale * rgb).astype(F)   # color_mul(scale, tex)
+            else:
+                # EnvironmentLight.cpp:45-110: a textured environment; with a cdf (default "conditional", MIS compensation on) the
+                # light is make_environment_light_textured over the 2-D cdf of the baked radiance, else make_environment_light
+                if "transform" in lj:
+                    raise SceneError("transformed environment lights are outside the supported path")
+                method = str(lj.get("cdf", "conditional")).lower()
+                if method not in ("none", "conditional", ""):
+                    raise SceneError(f"environment cdf method '{method}' is outside the supported path (conditional, none)")
+                rec["p"][0:3] = scale
+                rec["p"][3:12] = (1, 0, 0, 0, 1, 0, 0, 0, 1)
+                rec["p"][12:13].view(np.int32)[0] = tid
+                baked = bake_texture(tex_recs[tid], images)
+                if method == "none" or baked.shape[0] <= 1 or baked.shape[1] <= 1:
+                    rec["type"] = LIGHT_ENV_TEX
+                else:
+                    rec["type"] = LIGHT_ENV_TEXTURED
+                    cdf = cdf2d_for_image(baked, True, bool(lj.get("compensate", True)))
+                    rec["p"][13:16].view(np.int32)[:] = (sum(len(a) for a in aux_words), baked.shape[1], baked.shape[0])
+                    aux_words.append(cdf)
+            inf_l.append(rec)
+        elif lt == "sky":
+            # SkyLight.cpp:9-80: the Hosek-Wilkie model baked into a 512 x 256 image (skysun/SkyModel.cpp), then
+            # make_environment_light_textured(bilinear, repeat) over its 2-D cdf (premultiplied by sin, no compensation)
+            if "transform" in lj:
+                raise SceneError("transformed sky lights are outside the supported path")
+            sky = sky_image(lj)
+            images.append((IMAGE_RGBA32F, sky))
+            trec = np.zeros((), TEXTURE_DTYPE)
+            trec["type"], trec["image"], trec["filter"] = TEX_IMAGE, len(images) - 1, 1
+            trec["transform"] = (1, 0, 0, 0, 1, 0)
+            tex_recs.append(trec)
+            tid = len(tex_recs) - 1
+            tex_ids["_sky_" + str(lj.get("name", len(inf_l)))] = tid
+            rec["type"] = LIGHT_ENV_TEXTURED
+            rec["p"][0:3] = _color(lj.get("scale"), (1, 1, 1))
+            rec["p"][3:12] = (1, 0, 0, 0, 1, 0, 0, 0, 1)
+            rec["p"][12:13].view(np.int32)[0] = tid
+            cdf = cdf2d_for_image(sky[:, :, :3], True, False)
+            rec["p"][13:16].view(np.int32)[:] = (sum(len(a) for a in aux_words), sky.shape[1], sky.shape[0])
+            aux_words.append(cdf)
             inf_l.append(rec)
         elif lt in ("sun", "directional", "direction", "distant"):
             # LoaderUtils::getDirection (LoaderUtils.cpp:89-106): direction -> elevation / azimuth -> direction (y up), then
@@ -669,6 +998,8 @@ def load_scene(path, width: int | None = None, height: int | None = None,
             # PointLight.cpp:18-31: the cached colour is the power (intensity * 4 pi), flux = its mean
             flux = float(np.mean(_color(lj["power"], (0, 0, 0)) if "power" in lj else _color(lj.get("intensity"), (1, 1, 1)) * F(4 * PI)))
             fin_sel.append((rec["p"][0:3].copy(), None, flux))
+            rec_raw = (_color(lj["power"], (0, 0, 0)), True) if "power" in lj else (_color(lj.get("intensity"), (1, 1, 1)), False)
+            point_raw[id(rec)] = rec_raw
             fin_l.append(rec)
         elif lt == "spot":
             # SpotLight.cpp:11-20,62-90: cutoff / falloff in degrees; rad(x) = x / 180 * pi in f32 (core/common.art:20); the two
@@ -751,6 +1082,33 @@ def load_scene(path, width: int | None = None, height: int | None = None,
         else:
             raise SceneError(f"light type '{lt}' is outside the supported path (SURVEY §8f)")
 
+    # ---- embedded light tables (LoaderLight.h:27, LoaderLight.cpp:316-420): once >= 10 finite lights are "simple" (constant parameters),
+    # they are written into per-class fix-tables and come FIRST in the id space, class by class (the reference iterates an
+    # unordered_map of class names: implementation-defined; here classes in order of first appearance), the other lights after them.
+    # A simple point light's table entry holds power / (4 pi), the power being intensity * 4 pi (PointLight.cpp:18-31,63-70).
+    embed_class = []
+    for rec in fin_l:
+        t_ = int(rec["type"])
+        embed_class.append({LIGHT_POINT: "SimplePointLight", LIGHT_SPOT: "SimpleSpotLight", LIGHT_PLANE_AREA: "SimplePlaneLight",
+                            LIGHT_SHAPE_AREA: "SimpleAreaLight", LIGHT_SPHERE_AREA: "SimpleSphereLight"}.get(t_))
+    embedded = sum(c is not None for c in embed_class) >= 10
+    if embedded:
+        classes = []
+        for c in embed_class:
+            if c is not None and c not in classes:
+                classes.append(c)
+        order = [i for c in classes for i, ec in enumerate(embed_class) if ec == c] + [i for i, ec in enumerate(embed_class) if ec is None]
+        remap = {old: new for new, old in enumerate(order)}
+        fin_l = [fin_l[i] for i in order]
+        fin_sel = [fin_sel[i] for i in order]
+        spot_angles = {remap[k]: v for k, v in spot_angles.items()}
+        fin_of_entity = {k: remap[v] for k, v in fin_of_entity.items()}
+        sr = F(4 * PI)
+        for rec in fin_l:
+            if int(rec["type"]) == LIGHT_POINT:
+                colour, is_power = point_raw[id(rec)]
+                rec["p"][3:6] = ((colour if is_power else (colour * sr).astype(F)) / sr).astype(F)
+
     # ---- light selector (LoaderLight.cpp:423-452): one light or none -> uniform whatever was asked for
     selector_data = np.zeros(0, F)
     if sel in ("uniform", "") or len(inf_l) + len(fin_l) <= 1 or not fin_l:
@@ -771,12 +1129,27 @@ def load_scene(path, width: int | None = None, height: int | None = None,
         bt = bj.get("type", "").lower()
         rec = materials[mid]
         rec["light_id"] = fin_of_entity[emis] if emis is not None else -1
+        rec["tex"] = (-1, -1)
+        rec["map_tex"] = -1
+        if bt in ("bumpmap", "normalmap"):
+            # MapBSDF.cpp:17-55: a wrapper that replaces the shading frame of its inner BSDF (bsdf/map.art:39-68)
+            inner = bj.get("bsdf", "")
+            if inner not in bsdfs or bsdfs[inner].get("type", "").lower() in ("bumpmap", "normalmap"):
+                raise SceneError(f"bsdf '{bname}': missing inner bsdf / nested maps are outside the supported path")
+            mp = bj.get("map")
+            if not (isinstance(mp, str) and mp.strip() in tex_json):
+                raise SceneError(f"bsdf '{bname}': the map must be a texture name")
+            rec["map_kind"] = MAP_BUMP if bt == "bumpmap" else MAP_NORMAL
+            rec["map_tex"] = texture_id(mp.strip())
+            rec["map_strength"] = float(bj.get("strength", 1.0))
+            bj = bsdfs[inner]
+            bt = bj.get("type", "").lower()
         if bt in ("diffuse", "roughdiffuse"):
             alpha = bj.get("alpha", bj.get("roughness", 0.0))
             if isinstance(alpha, str) or float(alpha) > 1.1920928955e-07:
                 raise SceneError("Oren-Nayar (rough) diffuse is outside the supported path")
             rec["bsdf"] = BSDF_DIFFUSE
-            rec["p"][0:3] = _color(bj.get("reflectance"), (0.8, 0.8, 0.8))
+            rec["p"][0:3], rec["tex"][0] = color_or_tex(bj.get("reflectance"), (0.8, 0.8, 0.8))
         elif bt in ("dielectric", "glass", "roughdielectric", "thindielectric"):
             rough = [bj.get(k, 0) or 0 for k in ("roughness", "alpha", "roughness_u", "roughness_v", "alpha_u", "alpha_v")]
             if bj.get("thin", False) or any(isinstance(r, str) or float(r) > 0 for r in rough):
@@ -786,12 +1159,26 @@ def load_scene(path, width: int | None = None, height: int | None = None,
             int_ = bj.get("int_ior", iors.get(str(bj.get("int_ior_material", "")).lower(), 1.5046))
             rec["bsdf"] = BSDF_DIELECTRIC
             rec["p"][0], rec["p"][1] = float(ext), float(int_)
-            rec["p"][2:5] = _color(bj.get("specular_reflectance"), (1, 1, 1))
-            rec["p"][5:8] = _color(bj.get("specular_transmittance"), (1, 1, 1))
+            rec["p"][2:5], rec["tex"][0] = color_or_tex(bj.get("specular_reflectance"), (1, 1, 1))
+            rec["p"][5:8], rec["tex"][1] = color_or_tex(bj.get("specular_transmittance"), (1, 1, 1))
         elif bt in ("mirror", "conductor", "roughconductor"):
-            # ConductorBSDF.cpp:13-35: smooth only (no roughness property -> microfacet::make_delta_distribution)
-            if any(k in bj for k in ("roughness", "alpha", "roughness_u", "roughness_v", "alpha_u", "alpha_v")):
-                raise SceneError("rough conductors are outside the supported path (SURVEY §8f)")
+            # ConductorBSDF.cpp:13-35 + BSDF::setupRoughness (BSDF.cpp:53-98): no roughness property -> make_delta_distribution, else
+            # make_vndf_ggx_distribution over compute_explicit(roughness, anisotropic) or the explicit (roughness_u, roughness_v)
+            old = any(k in bj for k in ("alpha", "alpha_u", "alpha_v"))
+            rp = "alpha" if old else "roughness"
+            if any(k in bj for k in (rp, rp + "_u", rp + "_v")):
+                if str(bj.get("distribution", "vndf_ggx")).lower() in ("ggx", "beckmann"):
+                    raise SceneError("the plain ggx / beckmann distributions are outside the supported path (vndf_ggx is the default)")
+                vals = [bj.get(k) for k in (rp, rp + "_u", rp + "_v", "anisotropic")]
+                if any(isinstance(x, str) for x in vals):
+                    raise SceneError("textured roughness is outside the supported path")
+                if (rp + "_u") in bj or (rp + "_v") in bj:
+                    au, av = F(bj.get(rp + "_u", 0.1)), F(bj.get(rp + "_v", 0.1))
+                else:   # microfacet::compute_explicit, core/microfacet.art:427-432
+                    r, an = F(bj.get(rp, 0.1)), F(bj.get("anisotropic", 0.0))
+                    aspect = F(1) if an == 0 else F(np.sqrt(F(1) - F(min(max(float(an), 0.0), 1.0)) * F(0.99)))
+                    au, av = F(r / aspect), F(r * aspect)
+                rec["distribution"], rec["alpha_u"], rec["alpha_v"] = MICROFACET_VNDF_GGX, au, av
             conductors = {"none": ((0.0, 0.0, 0.0), (1.0, 1.0, 1.0)), "aluminum": ((1.34560, 0.96521, 0.61722), (7.47460, 6.39950, 5.30310)),
                           "brass": ((0.44400, 0.52700, 1.09400), (3.69500, 2.76500, 1.82900)), "copper": ((0.27105, 0.67693, 1.31640), (3.60920, 2.62480, 2.29210)),
                           "gold": ((0.18299, 0.42108, 1.37340), (3.4242, 2.34590, 1.77040)), "iron": ((2.91140, 2.94970, 2.58450), (3.08930, 2.93180, 2.76700)),
@@ -802,7 +1189,7 @@ def load_scene(path, width: int | None = None, height: int | None = None,
             eta, kk = _color(bj.get("eta"), d_eta), _color(bj.get("k"), d_k)
             rec["bsdf"] = BSDF_CONDUCTOR
             rec["p"][0:3], rec["p"][3:6] = eta, kk
-            rec["p"][6:9] = _color(bj.get("specular_reflectance"), (1, 1, 1))
+            rec["p"][6:9], rec["tex"][0] = color_or_tex(bj.get("specular_reflectance"), (1, 1, 1))
             # conductor.art:133-135: the mirror is chosen when eta and k are constants the generator printed into the text, i.e.
             # (default specialisation, ShadingTree.cpp:868-884) eta black and k white
             rec["p"][9] = 1.0 if (np.all(np.abs(eta) <= 1.1920929e-07) and np.all(np.abs(kk - 1) <= 1.1920929e-07)) else 0.0
@@ -864,4 +1251,5 @@ def load_scene(path, width: int | None = None, height: int | None = None,
         entity_per_material=np.asarray([len(g) for g in groups], np.int32), materials=materials,
         infinite_lights=_arr(inf_l), finite_lights=_arr(fin_l), camera=cam, technique=technique,
         bbox_min=bb_lo.astype(F), bbox_max=bb_hi.astype(F), film_size=(fw, fh),
-        selector_data=selector_data, entity_names=names, material_names=[f"{b}{'@' + e if e else ''}" for b, e in mat_keys], spot_angles=spot_angles, sun_params=sun_params)
+        embedded_lights=embedded, selector_data=selector_data, textures=(np.asarray(tex_recs, TEXTURE_DTYPE) if tex_recs else np.zeros(0, TEXTURE_DTYPE)), images=images,
+        aux_data=(np.concatenate(aux_words).astype(F) if aux_words else np.zeros(0, F)), texture_names=list(tex_ids), entity_names=names, material_names=[f"{b}{'@' + e if e else ''}" for b, e in mat_keys], spot_angles=spot_angles, sun_params=sun_params)

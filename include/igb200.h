@@ -57,12 +57,56 @@ enum { IGB200_BSDF_DIFFUSE = 0,    /* make_diffuse_bsdf(surf, 0, kd) -> make_lam
        IGB200_BSDF_DIELECTRIC = 1, /* make_dielectric_bsdf(..., delta, thin=false) -> make_pure_dielectric_bsdf (bsdf/dielectric.art:15-37) */
        IGB200_BSDF_CONDUCTOR = 2   /* make_conductor_bsdf(..., delta) -> make_mirror_bsdf / make_pure_conductor_bsdf (bsdf/conductor.art:2-27,131-141) */ };
 
+/* Microfacet distribution of a CONDUCTOR (BSDF::setupRoughness, src/runtime/bsdf/BSDF.cpp:53-98; src/artic/core/microfacet.art):
+ * no roughness property -> make_delta_distribution; else make_vndf_ggx_distribution(face_normal, local, alpha_u, alpha_v), which is
+ * itself the delta distribution when alpha_u or alpha_v <= 1e-4 (microfacet.art:297,403-425). alpha_u / alpha_v are the results of
+ * microfacet::compute_explicit(roughness, anisotropic) (microfacet.art:427-432), evaluated by the host. */
+enum { IGB200_MICROFACET_DELTA = 0, IGB200_MICROFACET_VNDF_GGX = 1 };
+/* Normal-modifying wrappers around the material's BSDF (src/artic/bsdf/map.art:56-68, generator src/runtime/bsdf/MapBSDF.cpp) */
+enum { IGB200_MAP_NONE = 0,
+       IGB200_MAP_BUMP = 1,    /* make_bumpmap(ctx, inner, texture_dx(map, ctx).r, texture_dy(map, ctx).r, strength) */
+       IGB200_MAP_NORMAL = 2   /* make_normalmap(ctx, inner, map(ctx), strength) */ };
+
 typedef struct igb200_material {
     int32_t bsdf;     /* IGB200_BSDF_* */
     int32_t light_id; /* finite-light index if the entity is an area emitter (make_emissive_material), else -1 */
     float   p[14];    /* DIFFUSE: kd rgb | DIELECTRIC: ext_ior, int_ior, ks rgb, kt rgb |
                          CONDUCTOR: eta rgb, k rgb, ks rgb, mirror flag (eta, k were compile-time constants ~ (0, 1)) */
-} igb200_material;
+    int32_t tex[2];   /* >= 0: index of the texture that replaces a colour parameter (ShadingTree::addColor with a texture name):
+                         [0] DIFFUSE reflectance, CONDUCTOR / DIELECTRIC specular_reflectance; [1] DIELECTRIC specular_transmittance. -1: the constant in p */
+    int32_t distribution;  /* CONDUCTOR: IGB200_MICROFACET_* */
+    float   alpha_u, alpha_v;
+    int32_t map_kind;      /* IGB200_MAP_* */
+    int32_t map_tex;       /* texture of the bump / normal map */
+    float   map_strength;
+    int32_t reserved[8];   /* 0 */
+} igb200_material;     /* 128 bytes */
+
+/* ---- textures: src/artic/texture/{common,checkerboard,image}.art; generators src/runtime/pattern/{CheckerBoard,Image}Pattern.cpp -- */
+enum { IGB200_TEX_CHECKERBOARD = 0, /* make_checkerboard_texture(scale, color0, color1, transform), texture/checkerboard.art:4-13 */
+       IGB200_TEX_IMAGE = 1         /* make_image_texture(border, filter, image, transform), texture/image.art:148-153 */ };
+enum { IGB200_FILTER_NEAREST = 0, IGB200_FILTER_BILINEAR = 1, IGB200_FILTER_BICUBIC = 2 };   /* texture/image.art:78-146 */
+enum { IGB200_BORDER_REPEAT = 0, IGB200_BORDER_CLAMP = 1, IGB200_BORDER_MIRROR = 2 };        /* texture/image.art:9-44 */
+typedef struct igb200_texture {
+    int32_t type;               /* IGB200_TEX_* */
+    int32_t image;              /* IMAGE: index into igb200_scene_desc.images */
+    int32_t filter;             /* IMAGE: IGB200_FILTER_* */
+    int32_t border_u, border_v; /* IMAGE: IGB200_BORDER_* (make_split_border when they differ) */
+    int32_t reserved[3];
+    float   transform[6];       /* rows 0 and 1 of the 3x3 the generator inlines (LoaderUtils::inlineTransformAs2d): uv' = (row0 . (u,v,1), row1 . (u,v,1)) */
+    float   p[10];              /* CHECKERBOARD: scale_x, scale_y, color0 rgb, color1 rgb */
+} igb200_texture;               /* 96 bytes */
+
+/* Pixel data exactly as the reference's device keeps it after loading the file (src/device/Device.cpp:735-799, src/runtime/Image.cpp:500-810):
+ * rows bottom-up (stbi_set_flip_vertically_on_load), 8-bit images packed and -- unless the texture says `linear` -- already mapped from sRGB
+ * to linear BYTES (byte_color_to_linear, Image.cpp:48-51); float images RGBA. Decoding files is the caller's business. */
+enum { IGB200_IMAGE_RGBA8 = 0,    /* device.load_packed_image(.., 4, ..): channel k of a pixel = byte k / 255 (driver/image.art:9-14) */
+       IGB200_IMAGE_MONO8 = 1,    /* device.load_packed_image(.., 1, ..): grey = byte / 255 (driver/image.art:16,27-34) */
+       IGB200_IMAGE_RGBA32F = 2   /* device.load_image(.., 4): four floats per pixel */ };
+typedef struct igb200_image {
+    int32_t     format, width, height, reserved;
+    const void* pixels;
+} igb200_image;
 
 enum { IGB200_LIGHT_ENV_CONST = 0,  /* make_environment_light (constant radiance), light/env.art:75-100,161-164 */
        IGB200_LIGHT_POINT = 1,      /* make_point_light, light/point.art:1-18 */
@@ -71,7 +115,10 @@ enum { IGB200_LIGHT_ENV_CONST = 0,  /* make_environment_light (constant radiance
        IGB200_LIGHT_SPHERE_AREA = 4, /* make_area_light(make_sphere_area_emitter), light/area.art:260-316 */
        IGB200_LIGHT_SPOT = 5,       /* make_spot_light, light/spot.art:8-44 */
        IGB200_LIGHT_SUN = 6,        /* make_sun_light (not handled as delta), light/sun.art:10-48: an INFINITE light */
-       IGB200_LIGHT_DIRECTIONAL = 7 /* make_directional_light, light/directional.art:1-17: an INFINITE delta light */ };
+       IGB200_LIGHT_DIRECTIONAL = 7, /* make_directional_light, light/directional.art:1-17: an INFINITE delta light */
+       IGB200_LIGHT_ENV_TEXTURED = 8, /* make_environment_light_textured(.., scale, tex, cdf::make_cdf_2d_from_buffer(..), transform), light/env.art:112-160:
+                                         environment map (EnvironmentLight.cpp:60-91 with cdf = conditional) and the sky model (SkyLight.cpp:42-80) */
+       IGB200_LIGHT_ENV_TEX = 9       /* make_environment_light(.., scale, tex, transform), light/env.art:161-167: textured, sampled uniformly (cdf = none) */ };
 
 typedef struct igb200_light {
     int32_t type;      /* IGB200_LIGHT_* */
@@ -82,7 +129,11 @@ typedef struct igb200_light {
                           SPOT: position xyz, direction xyz, cos(cutoff), cos(falloff), intensity rgb |
                           SPHERE_AREA: radiance rgb, sphere origin xyz (local), radius, area (compute_ellipsoid_area, shapes/sphere.art:21-27) |
                           SUN: direction towards the sun xyz (unit), cos(angle / 2), radiance rgb |
-                          DIRECTIONAL: direction the light travels xyz (unit), irradiance rgb */
+                          DIRECTIONAL: direction the light travels xyz (unit), irradiance rgb |
+                          ENV_TEXTURED: scale rgb, transform 3x3 column major (9), then as int32 bits: texture, first word of the cdf inside
+                                        aux_data, size_x (conditional), size_y (marginal); the buffer is [marginal size_y | size_y rows of size_x],
+                                        each 1-D cdf without its leading 0 (CDF::computeForImage, src/runtime/CDF.cpp:70-150) |
+                          ENV_TEX: scale rgb, transform 3x3 column major (9), texture (int32 bits) */
 } igb200_light;
 
 /* make_perspective_camera(eye, dir, up, compute_scale_from_{h,v}fov(fov, aspect), w, h, tmin, tmax):
@@ -134,6 +185,13 @@ typedef struct igb200_scene_desc {
      * then 8 words per tree node {pos xyz, flux (negative: no direction), dir xyz, id (>= 0 light, < 0: -(left child + 1))}. */
     const float*               selector_data;
     int32_t                    n_selector_data;
+    /* textures, images and further read-only buffers the descriptors above refer to by index / offset */
+    const igb200_texture*      textures;
+    int32_t                    n_textures;
+    const igb200_image*        images;
+    int32_t                    n_images;
+    const float*               aux_data;      /* 32-bit words: the 2-D cdfs of ENV_TEXTURED lights */
+    int32_t                    n_aux_data;
 } igb200_scene_desc;
 
 /* `Settings`, src/artic/driver/settings.art:2-11, filled by the device at src/device/Device.cpp:384-397 */

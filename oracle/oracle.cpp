@@ -279,7 +279,9 @@ inline bool intersect_sphere(Vec3 origin, float radius, const Ray& ray, float& o
 // Same binary layouts as include/igb200.h (declared independently on purpose).
 struct LookupEntry { uint32_t type_id, flags; uint64_t offset; };
 struct EntityLeaf { float min[3]; int32_t entity_id; float max[3]; int32_t shape_id; float local[12]; uint32_t flags; int32_t mat_id, user1, user2; };
-struct MaterialDesc { int32_t bsdf, light_id; float p[14]; };
+struct MaterialDesc { int32_t bsdf, light_id; float p[14]; int32_t tex[2]; int32_t distribution; float alpha_u, alpha_v; int32_t map_kind, map_tex; float map_strength; int32_t reserved[8]; };
+struct TextureDesc { int32_t type, image, filter, border_u, border_v, reserved[3]; float transform[6]; float p[10]; };
+struct ImageDesc { int32_t format, width, height, reserved; const void* pixels; };
 struct LightDesc { int32_t type, entity_id; float p[30]; };
 struct CameraDesc { float eye[3], dir[3], up[3]; float fov; int32_t fov_vertical; float aspect, tmin, tmax; };
 struct TechniqueDesc { int32_t max_depth, min_depth; float clamp; int32_t nee; int32_t light_selector; };   // selector: 0 uniform, 1 cdf ("simple"), 2 hierarchy
@@ -296,17 +298,28 @@ struct SceneDesc {
     TechniqueDesc technique;
     float bbox_min[3], bbox_max[3];
     const float* selector_data; int32_t n_selector_data;   // light_cdf.bin / light_hierarchy.bin as 32-bit words (LoaderLight.cpp:423-476, LightHierarchy.cpp)
+    const TextureDesc* textures; int32_t n_textures;
+    const ImageDesc* images; int32_t n_images;
+    const float* aux_data; int32_t n_aux_data;             // 2-D cdfs of the textured environment lights (CDF.cpp:70-150)
 };
 struct Settings { int32_t device, thread_count, spi, frame, iter, width, height, seed; };  // driver/settings.art:2-11
 struct StreamRay { float org[3], dir[3], tmin, tmax; };                                       // traversal/ray.art:2-7
 struct HitRecord { int32_t ent_id, prim_id; float t, u, v; };
-static_assert(sizeof(EntityLeaf) == 96 && sizeof(MaterialDesc) == 64 && sizeof(LightDesc) == 128, "layout");
+static_assert(sizeof(EntityLeaf) == 96 && sizeof(MaterialDesc) == 128 && sizeof(LightDesc) == 128 && sizeof(TextureDesc) == 96 && sizeof(ImageDesc) == 24, "layout");
 
 enum { SHAPE_TRIMESH = 0, SHAPE_SPHERE = 1 };
 enum { BSDF_DIFFUSE = 0, BSDF_DIELECTRIC = 1, BSDF_CONDUCTOR = 2 };
 enum { LIGHT_ENV_CONST = 0, LIGHT_POINT = 1, LIGHT_PLANE_AREA = 2, LIGHT_SHAPE_AREA = 3, LIGHT_SPHERE_AREA = 4, LIGHT_SPOT = 5,
        LIGHT_SUN = 6,            // make_sun_light (light/sun.art:10-48): infinite cone light; p = direction towards the sun, cos(half angle), radiance
-       LIGHT_DIRECTIONAL = 7 };  // make_directional_light (light/directional.art:1-17): infinite delta light; p = direction the light travels, irradiance
+       LIGHT_DIRECTIONAL = 7,    // make_directional_light (light/directional.art:1-17): infinite delta light; p = direction the light travels, irradiance
+       LIGHT_ENV_TEXTURED = 8,   // make_environment_light_textured (light/env.art:112-160): p = scale rgb, transform (9, column major), texture, cdf offset, size_x, size_y (int bits)
+       LIGHT_ENV_TEX = 9 };      // make_environment_light with a texture (light/env.art:161-167): p = scale rgb, transform (9), texture (int bits)
+enum { MICROFACET_DELTA = 0, MICROFACET_VNDF_GGX = 1 };
+enum { MAP_NONE = 0, MAP_BUMP = 1, MAP_NORMAL = 2 };
+enum { TEX_CHECKERBOARD = 0, TEX_IMAGE = 1 };
+enum { FILTER_NEAREST = 0, FILTER_BILINEAR = 1, FILTER_BICUBIC = 2 };
+enum { BORDER_REPEAT = 0, BORDER_CLAMP = 1, BORDER_MIRROR = 2 };
+enum { IMAGE_RGBA8 = 0, IMAGE_MONO8 = 1, IMAGE_RGBA32F = 2 };
 
 // ------------------------------------------------------------------------------------------ own BVH2 (median split)
 struct Bvh2 {
@@ -387,6 +400,10 @@ struct Scene {
     std::vector<uint8_t> shape_blob;
     CameraDesc camera; TechniqueDesc technique;
     std::vector<float> selector_data;
+    std::vector<TextureDesc> textures;
+    std::vector<ImageDesc> images;                  // pixels point into image_data
+    std::vector<std::vector<uint8_t>> image_data;
+    std::vector<float> aux_data;
     BBox bbox;
     Bvh2 top;   // over leaves
     int num_materials;
@@ -447,6 +464,16 @@ struct Scene {
         fin_lights.assign(d.finite_lights, d.finite_lights + d.n_finite);
         camera = d.camera; technique = d.technique; num_materials = d.n_materials;
         if (d.selector_data && d.n_selector_data > 0) selector_data.assign(d.selector_data, d.selector_data + d.n_selector_data);
+        if (d.textures && d.n_textures > 0) textures.assign(d.textures, d.textures + d.n_textures);
+        if (d.aux_data && d.n_aux_data > 0) aux_data.assign(d.aux_data, d.aux_data + d.n_aux_data);
+        for (int i = 0; i < d.n_images; ++i) {
+            ImageDesc im = d.images[i];
+            const size_t bpp = im.format == IMAGE_RGBA8 ? 4 : im.format == IMAGE_MONO8 ? 1 : 16;
+            const uint8_t* px = (const uint8_t*)im.pixels;
+            image_data.emplace_back(px, px + bpp * (size_t)im.width * (size_t)im.height);
+            im.pixels = image_data.back().data();
+            images.push_back(im);
+        }
         bbox = BBox{v3(d.bbox_min[0], d.bbox_min[1], d.bbox_min[2]), v3(d.bbox_max[0], d.bbox_max[1], d.bbox_max[2])};
         std::vector<BBox> lb(leaves.size());
         for (size_t i = 0; i < leaves.size(); ++i) lb[i] = BBox{v3(leaves[i].min[0], leaves[i].min[1], leaves[i].min[2]), v3(leaves[i].max[0], leaves[i].max[1], leaves[i].max[2])};
@@ -652,34 +679,230 @@ inline float conductor_factor(float n, float k, float cos_i) {
     return clampf((R_s * R_s + R_p * R_p) * 0.5f, 0, 1);
 }
 
+// ------------------------------------------------------------------------------------------ textures
+// core/math.art:74,88-91
+inline float fractf_(float x) { return x - floorf(x); }
+inline float wrapf_(float v, float mn, float mx) { const float range = mx - mn; return range <= flt_eps ? mn : v - (range * floorf((v - mn) / range)); }
+// core/matrix.art:237-240 on the two rows the generator inlines (LoaderUtils::inlineTransformAs2d)
+inline Vec2 transform_point_affine(const float* m, Vec2 v) { return Vec2{dot(v3(m[0], m[1], m[2]), v3(v.x, v.y, 1)), dot(v3(m[3], m[4], m[5]), v3(v.x, v.y, 1))}; }
+struct Color4 { float r, g, b, a; };
+inline Color4 c4lerp(Color4 a, Color4 b, float t) { return Color4{(1 - t) * a.r + t * b.r, (1 - t) * a.g + t * b.g, (1 - t) * a.b + t * b.b, (1 - t) * a.a + t * b.a}; }   // core/color.art:17-21
+inline Color4 c4mulf(Color4 a, float f) { return Color4{a.r * f, a.g * f, a.b * f, a.a * f}; }
+inline Color4 c4add(Color4 a, Color4 b) { return Color4{a.r + b.r, a.g + b.g, a.b + b.b, a.a + b.a}; }
+// texture/image.art:9-44
+inline int border_index(int mode, int x, int w) {
+    if (mode == BORDER_CLAMP) return x < 0 ? 0 : (x > w - 1 ? w - 1 : x);
+    if (mode == BORDER_MIRROR) { const int t = x < 0 ? -1 - x : x; const int i = t / w; const int k = t - i * w; return (i & 1) == 0 ? w - 1 - k : k; }
+    const int t = x % w; return t < 0 ? t + w : t;
+}
+// driver/image.art:9-34
+inline Color4 image_pixel(const ImageDesc& im, int x, int y) {
+    const size_t i = (size_t)y * (size_t)im.width + (size_t)x;
+    if (im.format == IMAGE_RGBA8) { const uint8_t* p = (const uint8_t*)im.pixels + 4 * i; return Color4{(float)p[0] / 255, (float)p[1] / 255, (float)p[2] / 255, (float)p[3] / 255}; }
+    if (im.format == IMAGE_MONO8) { const float g = (float)((const uint8_t*)im.pixels)[i] / 255; return Color4{g, g, g, 1}; }
+    const float* p = (const float*)im.pixels + 4 * i; return Color4{p[0], p[1], p[2], p[3]};
+}
+// texture/image.art:78-146
+inline Color4 image_filter(const ImageDesc& im, int filter, int bu, int bv, Vec2 uv) {
+    if (filter == FILTER_NEAREST) {
+        const float u = uv.x * (float)im.width, v = uv.y * (float)im.height;
+        return image_pixel(im, border_index(bu, (int)floorf(u), im.width), border_index(bv, (int)floorf(v), im.height));
+    }
+    const float u = uv.x * (float)im.width - 0.5f, v = uv.y * (float)im.height - 0.5f;
+    const int ix = (int)floorf(u), iy = (int)floorf(v);
+    const float fx = fractf_(u), fy = fractf_(v);
+    if (filter == FILTER_BILINEAR) {
+        const int x0 = border_index(bu, ix, im.width), y0 = border_index(bv, iy, im.height), x1 = border_index(bu, ix + 1, im.width), y1 = border_index(bv, iy + 1, im.height);
+        return c4lerp(c4lerp(image_pixel(im, x0, y0), image_pixel(im, x1, y0), fx), c4lerp(image_pixel(im, x0, y1), image_pixel(im, x1, y1), fx), fy);
+    }
+    auto w0 = [](float a) { return (a * (a * (-a + 3) - 3) + 1) / 6; };
+    auto w1 = [](float a) { return (a * a * (3 * a - 6) + 4) / 6; };
+    auto w2 = [](float a) { return (a * (a * (-3 * a + 3) + 3) + 1) / 6; };
+    auto w3 = [](float a) { return (a * a * a) / 6; };
+    auto g0 = [&](float a) { return w0(a) + w1(a); };
+    auto g1 = [&](float a) { return w2(a) + w3(a); };
+    auto h0 = [&](float a) { return (w1(a) / g0(a)) - 1; };
+    auto h1 = [&](float a) { return (w3(a) / g1(a)) + 1; };
+    const float g0x = g0(fx), g0y = g0(fy), g1x = g1(fx), g1y = g1(fy);
+    const int ix0 = (int)floorf((float)ix + h0(fx) + 0.5f), iy0 = (int)floorf((float)iy + h0(fy) + 0.5f);
+    const int ix1 = (int)floorf((float)ix + h1(fx) + 0.5f), iy1 = (int)floorf((float)iy + h1(fy) + 0.5f);
+    const int x0 = border_index(bu, ix0, im.width), y0 = border_index(bv, iy0, im.height), x1 = border_index(bu, ix1, im.width), y1 = border_index(bv, iy1, im.height);
+    const Color4 p00 = c4mulf(image_pixel(im, x0, y0), g0x * g0y), p10 = c4mulf(image_pixel(im, x1, y0), g1x * g0y);
+    const Color4 p01 = c4mulf(image_pixel(im, x0, y1), g0x * g1y), p11 = c4mulf(image_pixel(im, x1, y1), g1x * g1y);
+    return c4add(c4add(p00, p10), c4add(p01, p11));
+}
+struct TextureSet { const TextureDesc* tex; const ImageDesc* img; };
+// texture/checkerboard.art:4-13, texture/image.art:148-153; uv = ctx.uvw.xy
+inline Color eval_texture(const TextureSet& ts, int id, Vec2 uv) {
+    const TextureDesc& t = ts.tex[id];
+    const Vec2 uv2 = transform_point_affine(t.transform, uv);
+    if (t.type == TEX_CHECKERBOARD) {
+        const float sx = uv2.x * t.p[0], sy = uv2.y * t.p[1];
+        const bool px = ((int)wrapf_(sx, 0, 2) % 2) == 0, py = ((int)wrapf_(sy, 0, 2) % 2) == 0;
+        return (px != py) ? col(t.p[2], t.p[3], t.p[4]) : col(t.p[5], t.p[6], t.p[7]);
+    }
+    const Color4 c = image_filter(ts.img[t.image], t.filter, t.border_u, t.border_v, uv2);
+    return col(c.r, c.g, c.b);
+}
+
+// ------------------------------------------------------------------------------------------ microfacets (core/microfacet.art)
+inline float absolute_cos(Vec3 a, Vec3 b) { return fabsf(dot(a, b)); }                                   // core/common.art:270
+inline Vec3 reflect(Vec3 v, Vec3 n) { return mulf(n, 2 * dot(n, v)) - v; }                                // core/vector.art:124
+inline Vec3 to_world(const Mat3x3& l, Vec3 v) { return (mulf(l.c0, v.x) + mulf(l.c1, v.y)) + mulf(l.c2, v.z); }   // core/shading.art:8
+inline Vec3 to_local(const Mat3x3& l, Vec3 v) { return v3(dot(l.c0, v), dot(l.c1, v), dot(l.c2, v)); }           // core/shading.art:9 (= mat3x3_left_mul)
+// :159-178
+inline float g_1_smith(const Mat3x3& local, Vec3 w, float alpha_u, float alpha_v) {
+    const float cosZ = dot(local.c2, w);
+    if (fabsf(cosZ) <= flt_eps) return 0;
+    const float cosX = dot(local.c0, w), cosY = dot(local.c1, w);
+    const float kx = alpha_u * cosX, ky = alpha_v * cosY;
+    const float a2 = kx * kx + ky * ky;
+    if (a2 <= flt_eps) return 1;
+    const float k2 = a2 / (cosZ * cosZ);
+    const float denom = 1 + sqrtf(1 + k2);
+    return 2 / denom;
+}
+// :192-202
+inline float ndf_ggx(const Mat3x3& local, Vec3 m, float alpha_u, float alpha_v) {
+    const float cosZ = dot(local.c2, m), cosX = dot(local.c0, m), cosY = dot(local.c1, m);
+    const float kx = cosX / alpha_u, ky = cosY / alpha_v;
+    const float k = kx * kx + ky * ky + cosZ * cosZ;
+    return safe_div(1, flt_pi * alpha_u * alpha_v * k * k);
+}
+// :370-394 (Dupuy & Benyoub, spherical caps), as written: the UNSTRETCHED view vector is added to the cap sample
+inline Vec3 sample_vndf_ggx(Rng& rnd, const Mat3x3& local, Vec3 vN, float alpha_u, float alpha_v) {
+    const Vec3 vL = to_local(local, vN);
+    const Vec3 sL = normalize(v3(alpha_u * vL.x, alpha_v * vL.y, vL.z));
+    const float u0 = rnd.next_f32(); const float u1 = rnd.next_f32();
+    const float phi = 2 * flt_pi * u0;
+    const float z = (1 - u1) * (1 + sL.z) - sL.z;
+    const float sinTheta = sqrtf(clampf(1 - z * z, 0, 1));
+    float sn, cs; dm_sincosf(phi, &sn, &cs);
+    const float x = sinTheta * cs, y = sinTheta * sn;
+    const Vec3 h = v3(x, y, z) + vL;
+    const Vec3 Nh = normalize(v3(h.x * alpha_u, h.y * alpha_v, h.z));
+    return to_world(local, Nh);
+}
+// :396-399
+inline float pdf_vndf_ggx(const Mat3x3& local, Vec3 w, Vec3 h, float alpha_u, float alpha_v) {
+    const float cosZ = absolute_cos(local.c2, w);
+    return safe_div(g_1_smith(local, w, alpha_u, alpha_v) * absolute_cos(w, h) * ndf_ggx(local, h, alpha_u, alpha_v), cosZ);
+}
+inline bool check_if_delta_distribution(float au, float av) { return au <= 1e-4f || av <= 1e-4f; }       // :297
+
+// ------------------------------------------------------------------------------------------ normal / bump mapping (bsdf/map.art, core/sampling.art:118-165, core/matrix.art:261-284)
+inline Vec3 ensure_valid_reflection(Vec3 Ng, Vec3 I, Vec3 N) {
+    const Vec3 R = reflect(I, N);
+    const float threshold = fminf(0.9f * dot(Ng, I), 0.01f);
+    if (dot(Ng, R) >= threshold) return N;
+    const float NdotNg = dot(N, Ng);
+    const Vec3 X = normalize(N - mulf(Ng, NdotNg));
+    const float Ix = dot(I, X), Iz = dot(I, Ng);
+    const float Ix2 = Ix * Ix, Iz2 = Iz * Iz;
+    const float a = Ix2 + Iz2;
+    const float b = safe_sqrt(Ix2 * (a - threshold * threshold));
+    const float c = Iz * threshold + a;
+    const float fac = 0.5f / a;
+    const float N1_z2 = fac * (b + c), N2_z2 = fac * (-b + c);
+    const bool valid1 = (N1_z2 > 1e-5f) && (N1_z2 <= (1.0f + 1e-5f)), valid2 = (N2_z2 > 1e-5f) && (N2_z2 <= (1.0f + 1e-5f));
+    Vec2 Nn;
+    if (valid1 && valid2) {
+        const Vec2 N1{safe_sqrt(1 - N1_z2), safe_sqrt(N1_z2)}, N2{safe_sqrt(1 - N2_z2), safe_sqrt(N2_z2)};
+        const float R1 = 2 * (N1.x * Ix + N1.y * Iz) * N1.y - Iz, R2 = 2 * (N2.x * Ix + N2.y * Iz) * N2.y - Iz;
+        const bool valid3 = R1 >= 1e-5f, valid4 = R2 >= 1e-5f;
+        if (valid3 && valid4) Nn = R1 < R2 ? N1 : N2; else Nn = R1 > R2 ? N1 : N2;
+    } else if (valid1 || valid2) {
+        const float Nz2 = valid1 ? N1_z2 : N2_z2;
+        Nn = Vec2{safe_sqrt(1 - Nz2), safe_sqrt(Nz2)};
+    } else Nn = Vec2{0, 1};
+    return mulf(X, Nn.x) + mulf(Ng, Nn.y);
+}
+inline Mat3x3 mat3x3_align_vectors(Vec3 a, Vec3 b) {
+    const Vec3 axis = cross(b, a);
+    const float cosA = dot(a, b);
+    if (cosA <= -1) return Mat3x3{v3(-1, 0, 0), v3(0, -1, 0), v3(0, 0, -1)};
+    const float k = 1 / (1 + cosA);
+    return Mat3x3{v3((axis.x * axis.x * k) + cosA, (axis.y * axis.x * k) - axis.z, (axis.z * axis.x * k) + axis.y),
+                  v3((axis.x * axis.y * k) + axis.z, (axis.y * axis.y * k) + cosA, (axis.z * axis.y * k) - axis.x),
+                  v3((axis.x * axis.z * k) - axis.y, (axis.y * axis.z * k) + axis.x, (axis.z * axis.z * k) + cosA)};
+}
+inline Mat3x3 mat3x3_matmul(const Mat3x3& a, const Mat3x3& b) { return Mat3x3{mat3x3_mul(a, b.c0), mat3x3_mul(a, b.c1), mat3x3_mul(a, b.c2)}; }   // core/matrix.art:124-127
+// make_normal_set, bsdf/map.art:39-45: the frame the inner BSDF is built on
+inline Mat3x3 normal_set_frame(const SurfaceElement& surf, Vec3 ray_dir, Vec3 normal) {
+    const Vec3 n = ensure_valid_reflection(surf.face_normal, neg(ray_dir), normalize(normal));
+    return mat3x3_matmul(mat3x3_align_vectors(surf.local.c2, n), surf.local);
+}
+
 // ------------------------------------------------------------------------------------------ BSDFs
 struct BsdfSample { Vec3 in_dir; float pdf; Color color; float eta; bool is_delta; };
 struct Bsdf {
-    int type; const SurfaceElement* surf; Color kd; float n1, n2; Color ks, kt; Color c_eta, c_k; bool mirror;
-    bool is_all_delta() const { return type != BSDF_DIFFUSE; }
-    // bsdf/diffuse.art:2-12 ; bsdf/dielectric.art:15-37
-    Color eval(Vec3 in_dir, Vec3) const { return type == BSDF_DIFFUSE ? cmulf(kd, positive_cos(in_dir, surf->local.c2) * flt_inv_pi) : col(0, 0, 0); }
-    float pdf(Vec3 in_dir, Vec3) const { return type == BSDF_DIFFUSE ? positive_cos(in_dir, surf->local.c2) / flt_pi : 0.0f; }
+    int type; Mat3x3 local; bool is_entering; Color kd; float n1, n2; Color ks, kt; Color c_eta, c_k; bool mirror;
+    bool rough; float alpha_u, alpha_v;   // CONDUCTOR with make_vndf_ggx_distribution (bsdf/conductor.art:45-141)
+    bool is_all_delta() const { return type == BSDF_DIELECTRIC || (type == BSDF_CONDUCTOR && !rough); }
+    Color fresnel_term(float c) const { return col(conductor_factor(c_eta.r, c_k.r, c), conductor_factor(c_eta.g, c_k.g, c), conductor_factor(c_eta.b, c_k.b, c)); }
+    // bsdf/diffuse.art:2-12 ; bsdf/dielectric.art:15-37 ; bsdf/conductor.art:78-91
+    Color eval(Vec3 in_dir, Vec3 out_dir) const {
+        if (type == BSDF_DIFFUSE) return cmulf(kd, positive_cos(in_dir, local.c2) * flt_inv_pi);
+        if (type == BSDF_CONDUCTOR && rough) {
+            const Vec3 N = local.c2;
+            const float cos_o = absolute_cos(out_dir, N), cos_i = absolute_cos(in_dir, N);
+            if (cos_o <= flt_eps || cos_i <= flt_eps) return col(0, 0, 0);
+            const Vec3 H = normalize(in_dir + out_dir);
+            const float D = ndf_ggx(local, H, alpha_u, alpha_v);
+            const float G = g_1_smith(local, in_dir, alpha_u, alpha_v) * g_1_smith(local, out_dir, alpha_u, alpha_v);
+            const Color F = fresnel_term(absolute_cos(out_dir, H));
+            const Color IF = col(1 - F.r, 1 - F.g, 1 - F.b);
+            return cmulf(cadd(cmul(col(0, 0, 0), IF), cmul(ks, F)), D * G / (4 * cos_o));   // kd = black (make_rough_conductor_bsdf)
+        }
+        return col(0, 0, 0);
+    }
+    float pdf(Vec3 in_dir, Vec3 out_dir) const {
+        if (type == BSDF_DIFFUSE) return positive_cos(in_dir, local.c2) / flt_pi;
+        if (type == BSDF_CONDUCTOR && rough) {   // conductor.art:95-100
+            const Vec3 H = normalize(in_dir + out_dir);
+            const float cos_h_o = absolute_cos(out_dir, H);
+            const float jacob = safe_div(1, 4 * cos_h_o);
+            return pdf_vndf_ggx(local, out_dir, H, alpha_u, alpha_v) * jacob;
+        }
+        return 0.0f;
+    }
     bool sample(Rng& rnd, Vec3 out_dir, bool adjoint, BsdfSample& s) const {
         if (type == BSDF_DIFFUSE) {
             const float u = rnd.next_f32(); const float v = rnd.next_f32();
             const DirSample ds = sample_cosine_hemisphere(u, v);
-            s = BsdfSample{mat3x3_mul(surf->local, ds.dir), ds.pdf, kd, 1, false};
+            s = BsdfSample{mat3x3_mul(local, ds.dir), ds.pdf, kd, 1, false};
+            return true;
+        }
+        if (type == BSDF_CONDUCTOR && rough) {   // conductor.art:101-122
+            const Vec3 N = local.c2;
+            const float cos_o = absolute_cos(out_dir, N);
+            if (cos_o <= flt_eps) return false;
+            const Vec3 m = sample_vndf_ggx(rnd, local, out_dir, alpha_u, alpha_v);
+            const float m_pdf = pdf_vndf_ggx(local, out_dir, m, alpha_u, alpha_v);
+            if (len2(m) <= flt_eps) return false;
+            const Vec3 oH = normalize(m);
+            const Vec3 H = std::signbit(dot(oH, out_dir)) ? neg(oH) : oH;
+            const Vec3 in_dir = reflect(out_dir, H);
+            const float cos_i = absolute_cos(in_dir, N);
+            if (cos_i <= flt_eps) return false;
+            const float cos_h_o = absolute_cos(out_dir, H);
+            const float jacob = 1 / (4 * cos_h_o);
+            const float pdf = m_pdf * jacob;
+            s = BsdfSample{in_dir, pdf, cmulf(eval(in_dir, out_dir), safe_div(1, pdf)), 1, false};
             return true;
         }
         if (type == BSDF_CONDUCTOR) {
             // bsdf/conductor.art:2-10 (make_mirror_bsdf) and :14-27 (make_pure_conductor_bsdf); which one is the generator's
             // partial-evaluation decision (conductor.art:131-141: eta, k known constants ~ (0, 1))
-            const Vec3 nn = surf->local.c2;
+            const Vec3 nn = local.c2;
             const Vec3 r = mulf(nn, 2 * dot(nn, out_dir)) - out_dir;   // core/vector.art:124
             if (mirror) { s = BsdfSample{r, 1, ks, 1, true}; return true; }
             const float cos_i = dot(out_dir, nn);
-            const Color f = col(conductor_factor(c_eta.r, c_k.r, cos_i), conductor_factor(c_eta.g, c_k.g, cos_i), conductor_factor(c_eta.b, c_k.b, cos_i));
-            s = BsdfSample{r, 1, cmul(ks, f), 1, true};
+            s = BsdfSample{r, 1, cmul(ks, fresnel_term(cos_i)), 1, true};
             return true;
         }
-        const float k = surf->is_entering ? n1 / n2 : n2 / n1;
-        const Vec3 n = surf->local.c2;
+        const float k = is_entering ? n1 / n2 : n2 / n1;
+        const Vec3 n = local.c2;
         const float cos_o = dot(out_dir, n);
         FresnelTerm ft{0, 1};
         if (!fresnel(k, cos_o, ft)) ft = FresnelTerm{0, 1};
@@ -693,6 +916,14 @@ struct Bsdf {
             s = BsdfSample{mulf(n, 2 * dot(n, out_dir)) - out_dir, 1, ks, 1, true};
         }
         return true;
+    }
+    // Bsdf.albedo, for the Albedo AOV (technique/internal/infobuffer.art): diffuse.art:10, dielectric.art:35, conductor.art:9,28-38,50-56
+    Color albedo(Vec3 out_dir) const {
+        if (type == BSDF_DIFFUSE) return kd;
+        if (type == BSDF_DIELECTRIC) return col(lerp(ks.r, kt.r, 0.5f), lerp(ks.g, kt.g, 0.5f), lerp(ks.b, kt.b, 0.5f));
+        if (rough) { const Color F = fresnel_term(absolute_cos(out_dir, local.c2)); return cadd(cmul(col(0, 0, 0), col(1 - F.r, 1 - F.g, 1 - F.b)), cmul(ks, F)); }
+        if (mirror) return ks;
+        return cmul(ks, fresnel_term(dot(out_dir, local.c2)));
     }
 };
 
@@ -813,7 +1044,81 @@ inline void sphere_emitter_sample(const Scene& sc, const LightDesc& l, Vec2 uv, 
 struct LightRef { const LightDesc* d; bool infinite; int id; };
 
 inline bool light_delta(const LightDesc& l) { return l.type == LIGHT_POINT || l.type == LIGHT_SPOT || l.type == LIGHT_DIRECTIONAL; }
-inline bool light_infinite(const LightDesc& l) { return l.type == LIGHT_ENV_CONST || l.type == LIGHT_SUN || l.type == LIGHT_DIRECTIONAL; }
+inline bool light_infinite(const LightDesc& l) { return l.type == LIGHT_ENV_CONST || l.type == LIGHT_SUN || l.type == LIGHT_DIRECTIONAL || l.type == LIGHT_ENV_TEXTURED || l.type == LIGHT_ENV_TEX; }
+
+// ---- 1-D / 2-D cdfs over a buffer without the leading 0 (core/cdf.art:34-75,105-155, core/interval.art:7-23)
+struct Cdf1D {
+    const float* data; int func_size;
+    float get(int i) const { return i == 0 ? 0.0f : data[i - 1]; }
+    float pdf_discrete(int x) const { return get(x + 1) - get(x); }
+    int sample_discrete(float u, float& pdf) const {
+        const int size = func_size + 1;
+        int first = 0, len = size;
+        while (len > 0) {
+            const int half = len / 2, middle = first + half;
+            if (get(middle) <= u) { first = middle + 1; len -= half + 1; } else len = half;
+        }
+        const int off = std::min(std::min(std::max(first - 1, 0), size - 1), func_size - 1);
+        pdf = pdf_discrete(off);
+        return off;
+    }
+    // returns the offset; pos in [0, 1], pdf with respect to pos
+    int sample_continuous(float u, float& pos, float& pdf) const {
+        float dpdf;
+        const int off = sample_discrete(u, dpdf);
+        const float rem = safe_div(u - get(off), dpdf);
+        pos = clampf(((float)off + rem) / (float)func_size, 0, 1);
+        pdf = dpdf * (float)func_size;
+        return off;
+    }
+    int pdf_continuous(float x, float& pdf) const {
+        const int off = std::min(std::max((int)(x * (float)func_size), 0), func_size - 1);
+        pdf = pdf_discrete(off) * (float)func_size;
+        return off;
+    }
+};
+struct Cdf2D {   // make_cdf_2d_from_buffer: the marginal (over y) first, then size_y conditionals of size_x
+    const float* data; int size_x, size_y;
+    Cdf1D marginal() const { return Cdf1D{data, size_y}; }
+    Cdf1D conditional(int i) const { return Cdf1D{data + size_y + (size_t)i * size_x, size_x}; }
+    void sample_continuous(float ux, float uy, Vec2& pos, float& pdf) const {
+        float p1, pdf1, p2, pdf2;
+        const int off1 = marginal().sample_continuous(uy, p1, pdf1);
+        conditional(off1).sample_continuous(ux, p2, pdf2);
+        pos = Vec2{p2, p1}; pdf = pdf1 * pdf2;
+    }
+    float pdf_continuous(Vec2 pos) const {
+        float pdf1, pdf2;
+        const int off1 = marginal().pdf_continuous(pos.y, pdf1);
+        conditional(off1).pdf_continuous(pos.x, pdf2);
+        return pdf1 * pdf2;
+    }
+};
+inline int32_t fbits(float f) { int32_t i; std::memcpy(&i, &f, 4); return i; }
+inline Vec3 switch_env_up(Vec3 v) { return v3(v.x, v.z, v.y); }                     // light/env.art:13
+inline Vec2 map_env_uv(Vec3 dir) {                                                 // light/env.art:16-21, core/warp.art:44-48
+    const float theta = dm_acosf(dir.z);
+    float phi = dm_atan2f(dir.y, dir.x);
+    if (phi < 0) phi = phi + 2 * flt_pi;
+    const float v = theta / flt_pi, u = phi / (2 * flt_pi);
+    return Vec2{fractf_(u + 0.25f), 1 - v};
+}
+inline Mat3x3 env_transform(const LightDesc& l) { return Mat3x3{v3(l.p[3], l.p[4], l.p[5]), v3(l.p[6], l.p[7], l.p[8]), v3(l.p[9], l.p[10], l.p[11])}; }
+// make_environment_light_textured (light/env.art:112-160): direction pdf of `dir` and emitted radiance towards -dir
+inline float env_textured_pdf(const LightDesc& l, const float* aux, Vec3 dir) {
+    const Vec3 ldir = switch_env_up(mat3x3_mul(env_transform(l), dir));
+    const float sinTheta = safe_sqrt(1 - ldir.z * ldir.z);                         // core/shading.art:16-17
+    const Cdf2D cdf{aux + fbits(l.p[13]), fbits(l.p[14]), fbits(l.p[15])};
+    return safe_div(cdf.pdf_continuous(map_env_uv(ldir)), sinTheta * flt_pi * flt_pi * 2);
+}
+inline Color env_textured_emission(const LightDesc& l, const TextureSet& ts, Vec3 dir) {
+    const Vec3 ldir = switch_env_up(mat3x3_mul(env_transform(l), dir));
+    return cmul(col(l.p[0], l.p[1], l.p[2]), eval_texture(ts, fbits(l.p[12]), map_env_uv(ldir)));
+}
+// make_environment_light over a texture (light/env.art:161-167): func(dir) = scale * tex(map_env_uv(switch_env_up(dir))), applied to transform * dir
+inline Color env_tex_radiance(const LightDesc& l, const TextureSet& ts, Vec3 dir) {
+    return cmul(col(l.p[0], l.p[1], l.p[2]), eval_texture(ts, fbits(l.p[12]), map_env_uv(switch_env_up(mat3x3_mul(env_transform(l), dir)))));
+}
 // core/warp.art:2-22
 inline void square_to_concentric_disk(float px, float py, float& x, float& y) {
     const float a = 2 * px - 1, b = 2 * py - 1;
@@ -843,6 +1148,29 @@ inline DirectLightSample light_sample_direct(const Scene& sc, const LightDesc& l
         const float pdf = 1 / (4 * flt_pi);
         const Color intensity = cmulf(col(l.p[0], l.p[1], l.p[2]), 1 / pdf);
         return DirectLightSample{from.point + mulf(dir, scene_radius), dir, intensity, Pdf{pdf, PDF_SOLID}, 1.0f, scene_radius};
+    }
+    case LIGHT_ENV_TEX: {  // light/env.art:84-88 with func = scale * tex
+        const float scene_radius = len(sc.bbox.max - sc.bbox.min) / 2 * 1.01f;
+        const float u = rnd.next_f32(); const float v = rnd.next_f32();
+        const Vec3 dir = equal_area_square_to_sphere(u, v);
+        const float pdf = 1 / (4 * flt_pi);
+        const Color intensity = cmulf(env_tex_radiance(l, TextureSet{sc.textures.data(), sc.images.data()}, dir), 1 / pdf);
+        return DirectLightSample{from.point + mulf(dir, scene_radius), dir, intensity, Pdf{pdf, PDF_SOLID}, 1.0f, scene_radius};
+    }
+    case LIGHT_ENV_TEXTURED: {  // light/env.art:115-126,136-139 (the sampled intensity is NOT multiplied by `scale`, as in the reference)
+        const float scene_radius = len(sc.bbox.max - sc.bbox.min) / 2 * 1.01f;
+        const Cdf2D cdf{sc.aux_data.data() + fbits(l.p[13]), fbits(l.p[14]), fbits(l.p[15])};
+        const float u = rnd.next_f32(); const float v = rnd.next_f32();
+        Vec2 pos; float spdf;
+        cdf.sample_continuous(u, v, pos, spdf);
+        const Color intensity = eval_texture(TextureSet{sc.textures.data(), sc.images.data()}, fbits(l.p[12]), pos);
+        const float theta = (1 - pos.y) * flt_pi, phi = (pos.x - 0.25f) * 2 * flt_pi;
+        float st, ct, sp, cp; dm_sincosf(theta, &st, &ct); dm_sincosf(phi, &sp, &cp);   // dir_from_spherical, core/warp.art:50-57
+        const Vec3 d = v3(st * cp, st * sp, ct);
+        const float sinTheta = safe_sqrt(1 - d.z * d.z);
+        const float pdf_dir = safe_div(spdf, sinTheta * flt_pi * flt_pi * 2);
+        const Vec3 dir = to_local(env_transform(l), switch_env_up(d));                  // mat3x3_left_mul(transform, .)
+        return DirectLightSample{from.point + mulf(dir, scene_radius), dir, cmulf(intensity, 1 / pdf_dir), Pdf{pdf_dir, PDF_SOLID}, 1.0f, scene_radius};
     }
     case LIGHT_SUN: {  // light/sun.art:22-26
         const float cos_angle = l.p[3];
@@ -906,14 +1234,48 @@ inline DirectLightSample light_sample_direct(const Scene& sc, const LightDesc& l
 
 // ------------------------------------------------------------------------------------------ material
 struct Material { int id; Bsdf bsdf; const LightDesc* light; bool is_emissive; };
+struct ShadingContext { int pixel; Ray ray; Hit hit; SurfaceElement surf; };
+
+// The BSDF shader of one material at one hit: what the generated `bsdf_<id> : BSDFShader = @|ctx| ...` evaluates (HitShader.cpp:16-53,
+// DiffuseBSDF.cpp:13-27, DielectricBSDF.cpp:13-41, ConductorBSDF.cpp:13-35, MapBSDF.cpp:17-55): colour parameters that are textures are
+// looked up at ctx.uvw = (surf.tex_coords, 0); a bump / normal map replaces the frame the inner BSDF is built on (bsdf/map.art:39-68).
+inline Bsdf make_bsdf(const Scene& sc, const MaterialDesc& md, const ShadingContext& ctx) {
+    const TextureSet ts{sc.textures.data(), sc.images.data()};
+    const Vec2 uv = ctx.surf.tex_coords;
+    Bsdf b{};
+    b.type = md.bsdf; b.local = ctx.surf.local; b.is_entering = ctx.surf.is_entering;
+    if (md.map_kind == MAP_BUMP) {          // texture_dx / texture_dy, texture/common.art:28-38: forward differences with delta = 0.001
+        const float delta = 0.001f;
+        const Color c = eval_texture(ts, md.map_tex, uv);
+        const float dx = ((eval_texture(ts, md.map_tex, Vec2{uv.x + delta, uv.y}).r - c.r) * (1 / delta));
+        const float dy = ((eval_texture(ts, md.map_tex, Vec2{uv.x, uv.y + delta}).r - c.r) * (1 / delta));
+        const Mat3x3& l = ctx.surf.local;
+        const Vec3 N = normalize(l.c2 - mulf(mulf(l.c0, dx) + mulf(l.c1, dy), md.map_strength));
+        b.local = normal_set_frame(ctx.surf, ctx.ray.dir, N);
+    } else if (md.map_kind == MAP_NORMAL) { // bsdf/map.art:56-60
+        const Color c = eval_texture(ts, md.map_tex, uv);
+        const Mat3x3& l = ctx.surf.local;
+        const Vec3 oN = to_local(l, normalize(v3(2 * c.r - 1, 2 * c.g - 1, 2 * c.b - 1)));   // mat3x3_left_mul, as the reference writes it
+        const Vec3 N = md.map_strength != 1 ? normalize(l.c2 + mulf(oN - l.c2, md.map_strength)) : oN;
+        b.local = normal_set_frame(ctx.surf, ctx.ray.dir, N);
+    }
+    auto colour = [&](int slot, const float* c) { return md.tex[slot] >= 0 ? eval_texture(ts, md.tex[slot], uv) : col(c[0], c[1], c[2]); };
+    if (md.bsdf == BSDF_DIFFUSE) b.kd = colour(0, md.p);
+    else if (md.bsdf == BSDF_DIELECTRIC) { b.n1 = md.p[0]; b.n2 = md.p[1]; b.ks = colour(0, md.p + 2); b.kt = colour(1, md.p + 5); }
+    else {                                   // p = eta rgb, k rgb, ks rgb, mirror flag
+        b.c_eta = col(md.p[0], md.p[1], md.p[2]); b.c_k = col(md.p[3], md.p[4], md.p[5]);
+        b.ks = colour(0, md.p + 6); b.mirror = md.p[9] != 0.0f;
+        b.alpha_u = md.alpha_u; b.alpha_v = md.alpha_v;
+        b.rough = md.distribution == MICROFACET_VNDF_GGX && !check_if_delta_distribution(md.alpha_u, md.alpha_v);
+    }
+    return b;
+}
 
 // ------------------------------------------------------------------------------------------ path technique (technique/pathtracer.art)
 struct PTRayPayload { float inv_pdf; Color contrib; int depth; float eta; };
 struct Payload { float v[6]; };
 inline PTRayPayload unwrap(const Payload& p) { return PTRayPayload{p.v[0], col(p.v[1], p.v[2], p.v[3]), (int)p.v[4], p.v[5]}; }   // :24-29
 inline void wrap(Payload& p, const PTRayPayload& pt) { p.v[0] = pt.inv_pdf; p.v[1] = pt.contrib.r; p.v[2] = pt.contrib.g; p.v[3] = pt.contrib.b; p.v[4] = (float)pt.depth; p.v[5] = pt.eta; }  // :15-22
-
-struct ShadingContext { int pixel; Ray ray; Hit hit; SurfaceElement surf; };
 
 struct PathTracer {
     const Scene& sc;
@@ -1087,6 +1449,12 @@ struct PathTracer {
                     const bool hit = sun_hit(l, ray.dir);
                     emit = hit ? col(l.p[4], l.p[5], l.p[6]) : col(0, 0, 0);
                     pdf_s = hit ? uniform_cone_pdf(l.p[3]) : 0.0f;
+                } else if (l.type == LIGHT_ENV_TEXTURED) {                   // light/env.art:145-152
+                    emit = env_textured_emission(l, TextureSet{sc.textures.data(), sc.images.data()}, ray.dir);
+                    pdf_s = env_textured_pdf(l, sc.aux_data.data(), ray.dir);
+                } else if (l.type == LIGHT_ENV_TEX) {
+                    emit = env_tex_radiance(l, TextureSet{sc.textures.data(), sc.images.data()}, ray.dir);
+                    pdf_s = 1 / (4 * flt_pi);
                 } else {
                     emit = col(l.p[0], l.p[1], l.p[2]);                      // light/env.art:96
                     pdf_s = 1 / (4 * flt_pi);                                // light/env.art:97, sampling.art:47-51
@@ -1246,25 +1614,14 @@ void trace_tile(const Scene& sc, const Settings& st, const StreamRay* list_rays,
                     const MaterialDesc& md = sc.materials[mat_id];
                     Material mat;
                     mat.id = mat_id;
-                    mat.bsdf.type = md.bsdf; mat.bsdf.surf = &ctx.surf;
-                    mat.bsdf.kd = col(md.p[0], md.p[1], md.p[2]);
-                    mat.bsdf.n1 = md.p[0]; mat.bsdf.n2 = md.p[1];
-                    mat.bsdf.ks = col(md.p[2], md.p[3], md.p[4]); mat.bsdf.kt = col(md.p[5], md.p[6], md.p[7]);
-                    if (md.bsdf == BSDF_CONDUCTOR) {   // p = eta rgb, k rgb, ks rgb, mirror flag
-                        mat.bsdf.c_eta = col(md.p[0], md.p[1], md.p[2]); mat.bsdf.c_k = col(md.p[3], md.p[4], md.p[5]);
-                        mat.bsdf.ks = col(md.p[6], md.p[7], md.p[8]); mat.bsdf.mirror = md.p[9] != 0.0f;
-                    }
+                    mat.bsdf = make_bsdf(sc, md, ctx);
                     mat.is_emissive = md.light_id >= 0;
                     mat.light = mat.is_emissive ? &sc.fin_lights[md.light_id] : nullptr;
                     Color hc;
                     // wrap_infobuffer_renderer, technique/internal/infobuffer.art:9-24
                     if (aov_normals && st.iter == 0 && (ray.flags & ray_flag_camera) == ray_flag_camera) {
                         const Vec3 n = ctx.surf.local.c2;
-                        Color alb;
-                        if (mat.bsdf.type == BSDF_DIFFUSE) alb = mat.bsdf.kd;                                                         // diffuse.art:10
-                        else if (mat.bsdf.type == BSDF_DIELECTRIC) alb = col(lerp(mat.bsdf.ks.r, mat.bsdf.kt.r, 0.5f), lerp(mat.bsdf.ks.g, mat.bsdf.kt.g, 0.5f), lerp(mat.bsdf.ks.b, mat.bsdf.kt.b, 0.5f));   // dielectric.art:35
-                        else if (mat.bsdf.mirror) alb = mat.bsdf.ks;                                                                  // conductor.art:9
-                        else { const float ci = dot(neg(ray.dir), n); alb = cmul(mat.bsdf.ks, col(conductor_factor(mat.bsdf.c_eta.r, mat.bsdf.c_k.r, ci), conductor_factor(mat.bsdf.c_eta.g, mat.bsdf.c_k.g, ci), conductor_factor(mat.bsdf.c_eta.b, mat.bsdf.c_k.b, ci))); }   // conductor.art:28-38
+                        const Color alb = mat.bsdf.albedo(neg(ray.dir));
                         const int px = ray_id / spi;
                         aov_normals[px * 3 + 0] += n.x * inv_spi; aov_normals[px * 3 + 1] += n.y * inv_spi; aov_normals[px * 3 + 2] += n.z * inv_spi;
                         aov_albedo[px * 3 + 0] += fminf(alb.r, 1.0f) * inv_spi; aov_albedo[px * 3 + 1] += fminf(alb.g, 1.0f) * inv_spi; aov_albedo[px * 3 + 2] += fminf(alb.b, 1.0f) * inv_spi;
@@ -1388,7 +1745,7 @@ void igo_dielectric_sample(float n1, float n2, const float n[3], const float out
     SurfaceElement surf{};
     surf.is_entering = entering != 0;
     surf.local = make_orthonormal(v3(n[0], n[1], n[2]));
-    Bsdf b{}; b.type = BSDF_DIELECTRIC; b.surf = &surf; b.n1 = n1; b.n2 = n2; b.ks = col(0.25f, 0.25f, 0.25f); b.kt = col(0.5f, 0.5f, 0.5f);
+    Bsdf b{}; b.type = BSDF_DIELECTRIC; b.local = surf.local; b.is_entering = surf.is_entering; b.n1 = n1; b.n2 = n2; b.ks = col(0.25f, 0.25f, 0.25f); b.kt = col(0.5f, 0.5f, 0.5f);
     Rng rnd{seed, counter};
     BsdfSample sm{};
     b.sample(rnd, v3(out_dir[0], out_dir[1], out_dir[2]), false, sm);
@@ -1399,6 +1756,60 @@ void igo_dielectric_sample(float n1, float n2, const float n[3], const float out
 }
 void igo_cosine_hemisphere(float u, float v, float out[4]) { const DirSample d = sample_cosine_hemisphere(u, v); out[0] = d.dir.x; out[1] = d.dir.y; out[2] = d.dir.z; out[3] = d.pdf; }
 void igo_equal_area_sphere(float u, float v, float out[3]) { const Vec3 d = equal_area_square_to_sphere(u, v); out[0] = d.x; out[1] = d.y; out[2] = d.z; }
+// ---- known-answer hooks for the round-2 additions (tests/test_oracle_kat.py)
+// 1-D cdf over `data` = [x1 .. xn] (leading 0 virtual), src/tests/artic/test_cdf.art: out = {discrete off, discrete pdf, continuous off, pos, pdf, pdf_continuous(pos) off, pdf}
+void igo_cdf1d(const float* data, int func_size, float u, float out[7]) {
+    const Cdf1D c{data, func_size};
+    float dpdf, pos, cpdf, ppdf;
+    const int doff = c.sample_discrete(u, dpdf);
+    const int coff = c.sample_continuous(u, pos, cpdf);
+    const int poff = c.pdf_continuous(pos, ppdf);
+    out[0] = (float)doff; out[1] = dpdf; out[2] = (float)coff; out[3] = pos; out[4] = cpdf; out[5] = (float)poff; out[6] = ppdf;
+}
+// 2-D cdf (make_cdf_2d_from_buffer): out = {pos x, pos y, pdf, pdf_continuous(pos)}
+void igo_cdf2d(const float* data, int size_x, int size_y, float ux, float uy, float out[4]) {
+    const Cdf2D c{data, size_x, size_y};
+    Vec2 pos; float pdf;
+    c.sample_continuous(ux, uy, pos, pdf);
+    out[0] = pos.x; out[1] = pos.y; out[2] = pdf; out[3] = c.pdf_continuous(pos);
+}
+// GGX microfacet functions on the identity frame (src/tests/artic/test_microfacet.art): fn 0 ndf_ggx(m), 1 g_1_smith(w), 2 pdf_vndf_ggx(w, m),
+// 3 sample_vndf_ggx(seed, counter; w) -> out = normal xyz, pdf
+void igo_microfacet(int fn, float alpha_u, float alpha_v, const float w[3], const float m[3], uint32_t seed, uint32_t counter, float out[4]) {
+    const Mat3x3 id{v3(1, 0, 0), v3(0, 1, 0), v3(0, 0, 1)};
+    const Vec3 W = v3(w[0], w[1], w[2]), M = v3(m[0], m[1], m[2]);
+    if (fn == 0) out[0] = ndf_ggx(id, M, alpha_u, alpha_v);
+    else if (fn == 1) out[0] = g_1_smith(id, W, alpha_u, alpha_v);
+    else if (fn == 2) out[0] = pdf_vndf_ggx(id, W, M, alpha_u, alpha_v);
+    else { Rng rnd{seed, counter}; const Vec3 n = sample_vndf_ggx(rnd, id, W, alpha_u, alpha_v); out[0] = n.x; out[1] = n.y; out[2] = n.z; out[3] = pdf_vndf_ggx(id, W, n, alpha_u, alpha_v); }
+}
+// One sample of the rough conductor (bsdf/conductor.art:45-141, eta = 0, k = 1, ks = 1) on the frame with normal n: out = valid, in_dir xyz, pdf, colour rgb, pdf(in, out), eval(in, out) rgb
+void igo_rough_conductor_sample(float alpha_u, float alpha_v, const float n[3], const float out_dir[3], uint32_t seed, uint32_t counter, float out[12]) {
+    Bsdf b{}; b.type = BSDF_CONDUCTOR; b.local = make_orthonormal(v3(n[0], n[1], n[2])); b.is_entering = true;
+    b.c_eta = col(0, 0, 0); b.c_k = col(1, 1, 1); b.ks = col(1, 1, 1); b.rough = true; b.alpha_u = alpha_u; b.alpha_v = alpha_v;
+    Rng rnd{seed, counter};
+    BsdfSample sm{};
+    const Vec3 o = v3(out_dir[0], out_dir[1], out_dir[2]);
+    const bool ok = b.sample(rnd, o, false, sm);
+    out[0] = ok ? 1.0f : 0.0f;
+    if (!ok) return;
+    out[1] = sm.in_dir.x; out[2] = sm.in_dir.y; out[3] = sm.in_dir.z; out[4] = sm.pdf; out[5] = sm.color.r; out[6] = sm.color.g; out[7] = sm.color.b;
+    out[8] = b.pdf(sm.in_dir, o);
+    const Color e = b.eval(sm.in_dir, o); out[9] = e.r; out[10] = e.g; out[11] = e.b;
+}
+// texture lookup through the scene's tables (checkerboard / image filters / borders)
+void igo_eval_texture(void* o, int tex, const float* uv, int64_t n, float* out_rgb) {
+    const Scene& sc = ((Oracle*)o)->scene;
+    const TextureSet ts{sc.textures.data(), sc.images.data()};
+    for (int64_t i = 0; i < n; ++i) { const Color c = eval_texture(ts, tex, Vec2{uv[2 * i], uv[2 * i + 1]}); out_rgb[3 * i] = c.r; out_rgb[3 * i + 1] = c.g; out_rgb[3 * i + 2] = c.b; }
+}
+// ensure_valid_reflection + mat3x3_align_vectors (bsdf/map.art:39-45): the frame after make_normal_set; out = 9 floats, columns
+void igo_normal_set_frame(const float face_n[3], const float shading_n[3], const float ray_dir[3], const float new_n[3], float out[9]) {
+    SurfaceElement s{}; s.face_normal = v3(face_n[0], face_n[1], face_n[2]); s.local = make_orthonormal(v3(shading_n[0], shading_n[1], shading_n[2]));
+    const Mat3x3 m = normal_set_frame(s, v3(ray_dir[0], ray_dir[1], ray_dir[2]), v3(new_n[0], new_n[1], new_n[2]));
+    const Vec3 c[3] = {m.c0, m.c1, m.c2};
+    for (int k = 0; k < 3; ++k) { out[3 * k] = c[k].x; out[3 * k + 1] = c[k].y; out[3 * k + 2] = c[k].z; }
+}
 int igo_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

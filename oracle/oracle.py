@@ -39,7 +39,14 @@ class SceneDesc(C.Structure):
                 ("finite_lights", C.c_void_p), ("n_finite", C.c_int32),
                 ("camera", CameraDesc), ("technique", TechniqueDesc),
                 ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3),
-                ("selector_data", C.c_void_p), ("n_selector_data", C.c_int32)]
+                ("selector_data", C.c_void_p), ("n_selector_data", C.c_int32),
+                ("textures", C.c_void_p), ("n_textures", C.c_int32),
+                ("images", C.c_void_p), ("n_images", C.c_int32),
+                ("aux_data", C.c_void_p), ("n_aux_data", C.c_int32)]
+
+
+class ImageDesc(C.Structure):
+    _fields_ = [("format", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("reserved", C.c_int32), ("pixels", C.c_void_p)]
 
 
 class Settings(C.Structure):
@@ -73,6 +80,16 @@ def make_scene_desc(tables):
     sel = np.ascontiguousarray(getattr(tables, "selector_data", np.zeros(0, np.float32)), np.float32)
     keep.append(sel)
     d.selector_data, d.n_selector_data = (sel.ctypes.data if sel.size else None), int(sel.size)
+    tex = np.ascontiguousarray(getattr(tables, "textures", np.zeros(0, np.uint8)))
+    aux = np.ascontiguousarray(getattr(tables, "aux_data", np.zeros(0, np.float32)), np.float32)
+    imgs = [(int(f), np.ascontiguousarray(a)) for f, a in getattr(tables, "images", [])]
+    img_descs = (ImageDesc * max(len(imgs), 1))()
+    for i, (f, a) in enumerate(imgs):
+        img_descs[i] = ImageDesc(f, a.shape[1], a.shape[0], 0, a.ctypes.data)
+    keep += [tex, aux, imgs, img_descs]
+    d.textures, d.n_textures = (tex.ctypes.data if tex.size else None), int(tex.shape[0]) if tex.size else 0
+    d.images, d.n_images = (C.cast(img_descs, C.c_void_p).value if imgs else None), len(imgs)
+    d.aux_data, d.n_aux_data = (aux.ctypes.data if aux.size else None), int(aux.size)
     return d, keep
 
 
@@ -110,6 +127,12 @@ def lib():
         L.igo_dielectric_sample.argtypes = [C.c_float, C.c_float, f3, f3, C.c_int, C.c_uint32, C.c_uint32, f3]
         L.igo_equal_area_sphere.argtypes = [C.c_float, C.c_float, f3]
         L.igo_hardware_threads.restype = C.c_int
+        L.igo_cdf1d.argtypes = [C.c_void_p, C.c_int, C.c_float, f3]
+        L.igo_cdf2d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, f3]
+        L.igo_microfacet.argtypes = [C.c_int, C.c_float, C.c_float, f3, f3, C.c_uint32, C.c_uint32, f3]
+        L.igo_rough_conductor_sample.argtypes = [C.c_float, C.c_float, f3, f3, C.c_uint32, C.c_uint32, f3]
+        L.igo_eval_texture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+        L.igo_normal_set_frame.argtypes = [f3, f3, f3, f3, f3]
         _LIB = L
     return _LIB
 
@@ -159,6 +182,12 @@ class Oracle:
                          partition[0], partition[1], partition[2], cnt)
         self.counters += np.asarray(list(cnt), np.uint64)
         return fb
+
+    def eval_texture(self, tex: int, uv) -> np.ndarray:
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.zeros((uv.shape[0], 3), np.float32)
+        lib().igo_eval_texture(self._h, tex, uv.ctypes.data, uv.shape[0], out.ctypes.data)
+        return out
 
     def trace_closest(self, rays, flags=None, use_bvh=True):
         rays = np.ascontiguousarray(rays, RAY_DTYPE)

@@ -43,13 +43,19 @@ IMAGES = {
     # ref-sun-on-plane-and-stick-rad.exr -- the Ignis scene file puts the sun on the horizon, direction (0.707, -0.707, 0) in a z-up
     # scene, and renders a plane at grazing incidence (mean 0.03); the Radiance image shows a fully lit plane (mean 0.24).)
     "sun-on-plane": "ref-sun-on-plane-rad.exr",
+    # textured environment lights (light/env.art:112-167): a diffuse floor under an environment map, sampled through the 2-D cdf
+    # ("conditional", the default) and uniformly ("none"); `env` is a 100 x 50 map with one bright pixel, nearest filter, scale 100.
+    # The 4k map (93 MB) is stored box-filtered to 1024 x 512 -- the resolution the reference bakes it to for its cdf anyway.
+    "env4k-conditional": "ref-env4k-4096.exr", "env4k-none": "ref-env4k-4096.exr", "env": "ref-env-4096.exr",
 }
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "primitives_data.json", "flipped_prim.json",
+          "many_point_lights.json", "meshes/Pillar.ply", "textures/bumpmap.png", "textures/environment/single_bright_pixel.png",
           "meshes/Room.obj", "meshes/Bottom.ply", "meshes/Top.ply", "meshes/Left.ply", "meshes/Right.ply", "meshes/Back.ply", "meshes/Diamond.ply"]
 EVAL = ["plane-base.json", "plane-d1.json", "plane-d6.json", "point.json", "emissive-plane.json", "cbox-base.json", "cbox-d1.json",
         "cbox-d6.json", "multilight.json", "multilight-uniform.json", "multilight-simple.json", "multilight-hierarchy.json", "flipped-prim-base.json", "flipped-prim-diffuse.json",
         "sphere-light-base.json", "sphere-light-pure.json", "sphere-light-ico.json", "sphere-light-uv.json", "sphere-light-ico-nopt.json",
-        "emissive-plane-nopt.json", "emissive-plane-scale.json", "emissive-plane-scale-nopt.json", "two-planes-base.json", "two-planes-mirror.json", "room.json", "sun-on-plane.json"]
+        "emissive-plane-nopt.json", "emissive-plane-scale.json", "emissive-plane-scale-nopt.json", "two-planes-base.json", "two-planes-mirror.json", "room.json", "sun-on-plane.json",
+        "env4k-base.json", "env4k-conditional.json", "env4k-none.json", "env.json"]
 
 
 def main():
@@ -77,6 +83,18 @@ def main():
         if True:
             os.makedirs(os.path.join(ROOT, "scenes", "evaluation", "meshes"), exist_ok=True)
             shutil.copyfile(os.path.join(mdir, f), os.path.join(ROOT, "scenes", "evaluation", "meshes", f))
+    # the 4k environment map, box-filtered 4 x 4 -> 1024 x 512 float16 (rows top-down as in the file); the scene file is pointed at it
+    env = cv2.imread(os.path.join(REF, "textures", "environment", "phalzer_forest_01_4k.exr"), cv2.IMREAD_UNCHANGED)
+    if env is not None:
+        rgb = env[..., 2::-1].astype(np.float64)
+        k = rgb.shape[1] // 1024
+        small = rgb.reshape(rgb.shape[0] // k, k, rgb.shape[1] // k, k, 3).mean(axis=(1, 3))
+        assert small.max() < 60000
+        os.makedirs(os.path.join(ROOT, "scenes", "textures", "environment"), exist_ok=True)
+        np.savez_compressed(os.path.join(ROOT, "scenes", "textures", "environment", "phalzer_forest_01_1k.npz"), rgb=small.astype(np.float16))
+        base = os.path.join(ROOT, "scenes", "evaluation", "env4k-base.json")
+        txt = open(base).read().replace("phalzer_forest_01_4k.exr", "phalzer_forest_01_1k.npz")
+        open(base, "w").write(txt)
     print({k: v.shape for k, v in out.items()})
 
 
