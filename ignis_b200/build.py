@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libigb200.so")
 SOURCES = ["api.cu"]
-DEPS = ["api.cu", "wavefront.cuh", "traverse.cuh", "shade.cuh", "types.cuh", "device_math.cuh", "bvh8.h", "../../include/igb200.h", "../build.py"]
+DEPS = ["api.cu", "wavefront.cuh", "traverse.cuh", "shade.cuh", "material.cuh", "types.cuh", "device_math.cuh", "bvh8.h", "../../include/igb200.h", "../build.py"]
 
 
 def nvcc_path() -> str:

@@ -115,7 +115,9 @@ struct igb200_ctx {
     DevBuf<float4> nodes, tris, ent_leaf, ent_shade, blob, materials;
     DevBuf<int> tri_prim;
     DevBuf<int4> shape_info;
-    DevBuf<float> inf_lights, fin_lights, selector_data;
+    DevBuf<float> inf_lights, fin_lights, selector_data, textures, aux_data;
+    DevBuf<int4> images;
+    DevBuf<uint32_t> image_data;
     // framebuffer
     int width = 0, height = 0;
     DevBuf<float> fb;
@@ -494,10 +496,39 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     }
     if (d->n_leaves != d->n_entities) return fail(-1, "igb200_set_scene: %d leaves for %d entities (one EntityLeaf1 per entity expected)", d->n_leaves, d->n_entities);
     if (d->shape_data_bytes % 16) return fail(-1, "igb200_set_scene: shapes dyn-table data must be a multiple of 16 bytes");
-    for (int m = 0; m < d->n_materials; ++m)
-        if (d->materials[m].bsdf < IGB200_BSDF_DIFFUSE || d->materials[m].bsdf > IGB200_BSDF_CONDUCTOR) return fail(-4, "igb200_set_scene: material %d has unsupported bsdf %d", m, d->materials[m].bsdf);
-    for (int l = 0; l < d->n_infinite; ++l)
-        if (d->infinite_lights[l].type != IGB200_LIGHT_ENV_CONST && d->infinite_lights[l].type != IGB200_LIGHT_SUN && d->infinite_lights[l].type != IGB200_LIGHT_DIRECTIONAL) return fail(-4, "igb200_set_scene: infinite light %d has unsupported type %d", l, d->infinite_lights[l].type);
+    if (d->n_textures < 0 || d->n_images < 0 || d->n_aux_data < 0 || (d->n_textures && !d->textures) || (d->n_images && !d->images) || (d->n_aux_data && !d->aux_data))
+        return fail(-1, "igb200_set_scene: bad texture / image / aux_data tables");
+    for (int i = 0; i < d->n_images; ++i) {
+        const igb200_image& im = d->images[i];
+        if (im.format < IGB200_IMAGE_RGBA8 || im.format > IGB200_IMAGE_RGBA32F || im.width < 1 || im.height < 1 || !im.pixels || (long long)im.width * im.height > (1ll << 28))
+            return fail(-1, "igb200_set_scene: image %d is invalid (format %d, %d x %d)", i, im.format, im.width, im.height);
+    }
+    for (int t = 0; t < d->n_textures; ++t) {
+        const igb200_texture& tx = d->textures[t];
+        if (tx.type != IGB200_TEX_CHECKERBOARD && tx.type != IGB200_TEX_IMAGE) return fail(-4, "igb200_set_scene: texture %d has unsupported type %d", t, tx.type);
+        if (tx.type == IGB200_TEX_IMAGE && (tx.image < 0 || tx.image >= d->n_images || tx.filter < 0 || tx.filter > 2 || tx.border_u < 0 || tx.border_u > 2 || tx.border_v < 0 || tx.border_v > 2))
+            return fail(-1, "igb200_set_scene: texture %d refers to a bad image / filter / border", t);
+    }
+    auto tex_ok = [&](int id) { return id < d->n_textures; };   // negative: no texture
+    for (int m = 0; m < d->n_materials; ++m) {
+        const igb200_material& mt = d->materials[m];
+        if (mt.bsdf < IGB200_BSDF_DIFFUSE || mt.bsdf > IGB200_BSDF_CONDUCTOR) return fail(-4, "igb200_set_scene: material %d has unsupported bsdf %d", m, mt.bsdf);
+        if (!tex_ok(mt.tex[0]) || !tex_ok(mt.tex[1])) return fail(-1, "igb200_set_scene: material %d refers to a texture that does not exist", m);
+        if (mt.map_kind < IGB200_MAP_NONE || mt.map_kind > IGB200_MAP_NORMAL || (mt.map_kind != IGB200_MAP_NONE && (mt.map_tex < 0 || !tex_ok(mt.map_tex))))
+            return fail(-1, "igb200_set_scene: material %d has a bad bump / normal map", m);
+        if (mt.distribution != IGB200_MICROFACET_DELTA && mt.distribution != IGB200_MICROFACET_VNDF_GGX) return fail(-4, "igb200_set_scene: material %d has unsupported microfacet distribution %d", m, mt.distribution);
+    }
+    for (int l = 0; l < d->n_infinite; ++l) {
+        const igb200_light& li = d->infinite_lights[l];
+        const int t = li.type;
+        if (t != IGB200_LIGHT_ENV_CONST && t != IGB200_LIGHT_SUN && t != IGB200_LIGHT_DIRECTIONAL && t != IGB200_LIGHT_ENV_TEXTURED && t != IGB200_LIGHT_ENV_TEX) return fail(-4, "igb200_set_scene: infinite light %d has unsupported type %d", l, t);
+        if (t == IGB200_LIGHT_ENV_TEXTURED || t == IGB200_LIGHT_ENV_TEX) {
+            int32_t w[4]; std::memcpy(w, li.p + 12, sizeof(w));
+            if (w[0] < 0 || w[0] >= d->n_textures) return fail(-1, "igb200_set_scene: environment light %d refers to texture %d (%d textures)", l, w[0], d->n_textures);
+            if (t == IGB200_LIGHT_ENV_TEXTURED && (w[1] < 0 || w[2] < 1 || w[3] < 1 || (long long)w[1] + (long long)w[3] * (w[2] + 1) > d->n_aux_data))
+                return fail(-1, "igb200_set_scene: environment light %d: its cdf (%d x %d at word %d) does not fit aux_data (%d words)", l, w[2], w[3], w[1], d->n_aux_data);
+        }
+    }
     for (int l = 0; l < d->n_finite; ++l) {
         const int t = d->finite_lights[l].type;
         if (t != IGB200_LIGHT_POINT && t != IGB200_LIGHT_PLANE_AREA && t != IGB200_LIGHT_SHAPE_AREA && t != IGB200_LIGHT_SPHERE_AREA && t != IGB200_LIGHT_SPOT) return fail(-4, "igb200_set_scene: finite light %d has unsupported type %d", l, t);
@@ -671,7 +702,23 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     if (!nodes.empty()) std::memcpy(node_f4.data(), nodes.data(), nodes.size() * sizeof(Node8));
     std::vector<float4> blob(d->shape_data_bytes / 16);
     if (!blob.empty()) std::memcpy(blob.data(), d->shape_data, d->shape_data_bytes);
-    std::vector<float4> mats(4 * (size_t)d->n_materials);
+    std::vector<float4> mats(8 * (size_t)d->n_materials);
+    static_assert(sizeof(igb200_material) == 128 && sizeof(igb200_texture) == 96, "descriptor layout");
+    std::vector<float> texs(24 * (size_t)d->n_textures);
+    if (d->n_textures) std::memcpy(texs.data(), d->textures, sizeof(igb200_texture) * (size_t)d->n_textures);
+    std::vector<int4> img_table((size_t)d->n_images);
+    std::vector<uint32_t> img_words;
+    for (int i = 0; i < d->n_images; ++i) {
+        const igb200_image& im = d->images[i];
+        const size_t bytes = (size_t)im.width * im.height * (im.format == IGB200_IMAGE_RGBA8 ? 4 : im.format == IGB200_IMAGE_MONO8 ? 1 : 16);
+        const size_t first = img_words.size();                      // a multiple of 4 words: float4 pixels stay 16-byte aligned
+        img_words.resize(first + (bytes + 15) / 16 * 4, 0u);
+        std::memcpy(img_words.data() + first, im.pixels, bytes);
+        if (first > 0x7fffffffull) return fail(-1, "igb200_set_scene: more than 8 GB of image data");
+        img_table[i] = make_int4(im.format, im.width, im.height, (int)first);
+    }
+    std::vector<float> aux;
+    if (d->n_aux_data) aux.assign(d->aux_data, d->aux_data + d->n_aux_data);
     if (d->n_materials) std::memcpy(mats.data(), d->materials, sizeof(igb200_material) * (size_t)d->n_materials);
     std::vector<float> infl(32 * (size_t)d->n_infinite), finl(32 * (size_t)d->n_finite);
     if (d->n_infinite) std::memcpy(infl.data(), d->infinite_lights, sizeof(igb200_light) * (size_t)d->n_infinite);
@@ -681,6 +728,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     CU(c->nodes.upload(node_f4)); CU(c->tris.upload(tris)); CU(c->tri_prim.upload(tri_prim)); CU(c->ent_leaf.upload(ent_leaf)); CU(c->ent_shade.upload(ent_shade));
     CU(c->blob.upload(blob)); CU(c->shape_info.upload(shape_info)); CU(c->materials.upload(mats));
     CU(c->inf_lights.upload(infl)); CU(c->fin_lights.upload(finl));
+    CU(c->textures.upload(texs)); CU(c->images.upload(img_table)); CU(c->image_data.upload(img_words)); CU(c->aux_data.upload(aux));
     std::vector<float> seld;
     if (d->technique.light_selector != IGB200_SELECTOR_UNIFORM) seld.assign(d->selector_data, d->selector_data + d->n_selector_data);
     CU(c->selector_data.upload(seld));
@@ -688,6 +736,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     DevScene& s = c->dev;
     s.nodes = c->nodes.p; s.tris = c->tris.p; s.tri_prim = c->tri_prim.p; s.ent_leaf = c->ent_leaf.p; s.ent_shade = c->ent_shade.p; s.blob = c->blob.p;
     s.shape_info = c->shape_info.p; s.materials = c->materials.p; s.inf_lights = c->inf_lights.p; s.fin_lights = c->fin_lights.p;
+    s.textures = c->textures.p; s.images = c->images.p; s.image_data = c->image_data.p; s.aux_data = c->aux_data.p;
     s.n_ent = d->n_entities; s.n_mat = d->n_materials; s.n_inf = d->n_infinite; s.n_fin = d->n_finite;
     s.n_nodes = (int)nodes.size(); s.n_tris = (int)tri_prim.size();
     {   // bbox_radius(scene_bbox) * 1.01: light/env.art:76, core/bbox.art:24 (fma dot as on the device)
@@ -696,7 +745,10 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     }
     s.selector = d->technique.light_selector; s.selector_data = c->selector_data.p;
     c->scene_full = s.selector != IGB200_SELECTOR_UNIFORM;
-    for (int m = 0; m < d->n_materials; ++m) c->scene_full |= d->materials[m].bsdf == IGB200_BSDF_CONDUCTOR;
+    for (int m = 0; m < d->n_materials; ++m) {
+        const igb200_material& mt = d->materials[m];
+        c->scene_full |= mt.bsdf == IGB200_BSDF_CONDUCTOR || mt.tex[0] >= 0 || mt.tex[1] >= 0 || mt.map_kind != IGB200_MAP_NONE;
+    }
     for (int l = 0; l < d->n_finite; ++l) c->scene_full |= d->finite_lights[l].type == IGB200_LIGHT_SPHERE_AREA || d->finite_lights[l].type == IGB200_LIGHT_SPOT;
     for (int l = 0; l < d->n_infinite; ++l) c->scene_full |= d->infinite_lights[l].type != IGB200_LIGHT_ENV_CONST;
     s.full = c->scene_full ? 1 : 0;
@@ -704,6 +756,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     c->desc = *d;
     c->desc.entities = nullptr; c->desc.shape_lookups = nullptr; c->desc.shape_data = nullptr; c->desc.leaves = nullptr;
     c->desc.entity_per_material = nullptr; c->desc.materials = nullptr; c->desc.infinite_lights = nullptr; c->desc.finite_lights = nullptr;
+    c->desc.selector_data = nullptr; c->desc.textures = nullptr; c->desc.images = nullptr; c->desc.aux_data = nullptr;
     c->has_scene = true;
     return configure_kernels(c);
 }

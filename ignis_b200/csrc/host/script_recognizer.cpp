@@ -440,6 +440,7 @@ igb200_material resolve_material(const StageDescriptor& hit, const Registries& r
     igb200_material m;
     std::memset(&m, 0, sizeof(m));
     m.light_id = -1;
+    m.tex[0] = m.tex[1] = -1; m.map_tex = -1;   // no textured parameters, no bump / normal map
     if (hit.emissive) {   // ShaderUtils.cpp:127-136: the light id lives in the stage's LocalRegistry
         if (!r.local || !r.local->IntParameters.count("_light_id")) fail("emissive material without '_light_id' in its local registry");
         m.light_id = r.local->IntParameters.at("_light_id");

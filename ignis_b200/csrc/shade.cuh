@@ -4,10 +4,21 @@
 #include <cooperative_groups.h>
 
 #include "types.cuh"
+#include "material.cuh"
 
 namespace igb {
 
 struct Surf { bool is_entering; V3 point, face_normal; float area, inv_area; float pu, pv; M33 local; };
+
+// tex_coords of a triangle-mesh hit: vec2_lerp2 of the three vertices' uv (shapes/trimesh.art:27-36, core/vector.art:148-151)
+__device__ __forceinline__ void trimesh_texcoords(const DevScene& sc, int shape, int prim, float u, float v, float& tu, float& tv) {
+    const int4 si = __ldg(sc.shape_info + 2 * shape);
+    const int tex_start = __ldg(sc.shape_info + 2 * shape + 1).x;
+    const int4 idx = __ldg(reinterpret_cast<const int4*>(sc.blob + si.w + prim));
+    const float2* T = reinterpret_cast<const float2*>(sc.blob) + tex_start;
+    const float2 t0 = __ldg(T + idx.x), t1 = __ldg(T + idx.y), t2 = __ldg(T + idx.z);
+    tu = lerp2(t0.x, t1.x, t2.x, u, v); tv = lerp2(t0.y, t1.y, t2.y, u, v);
+}
 struct Pdf { float value; int measure; };   // 0 solid, 1 area, 2 delta  (driver/pdf.art:16-46)
 __device__ __forceinline__ float pdf_as_solid(Pdf p, float cos, float dist2) { return p.measure == 1 ? p.value * dist2 / cos : (p.measure == 2 ? 1.0f : p.value); }
 
@@ -213,6 +224,31 @@ __device__ __forceinline__ LightSample light_sample_direct(const DevScene& sc, c
         o.pos = pos; o.dir = mulf(d_, safe_div(1, dist));
         o.intensity = c3(__ldg(L + 5), __ldg(L + 6), __ldg(L + 7));
         o.pdf.value = 1; o.pdf.measure = 1; o.cos = 1; o.dist = dist;
+    } else if (FULL && type == 9) {   // make_environment_light over a texture: light/env.art:84-88,161-167
+        const float u = rnd.next_f32(); const float v = rnd.next_f32();
+        const V3 dir = equal_area_square_to_sphere(u, v);
+        const float pdf = 1 / (4 * IGB_FLT_PI);
+        const float4 e = env_textured_eval(sc, L, 9, dir.x, dir.y, dir.z);
+        o.pos = from.point + mulf(dir, sc.scene_radius); o.dir = dir;
+        o.intensity = cmulf(c3(e.x, e.y, e.z), 1 / pdf);
+        o.pdf.value = pdf; o.pdf.measure = 0; o.cos = 1.0f; o.dist = sc.scene_radius;
+    } else if (FULL && type == 8) {   // make_environment_light_textured: light/env.art:115-126,136-139 (the sampled intensity is not scaled, as in the reference)
+        const float* cdf = sc.aux_data + __float_as_int(__ldg(L + 15));
+        const int sx = __float_as_int(__ldg(L + 16)), sy = __float_as_int(__ldg(L + 17));
+        const float u = rnd.next_f32(); const float v = rnd.next_f32();
+        float p1, pdf1, p2, pdf2;
+        const int off1 = cdf_sample_continuous(cdf, sy, v, p1, pdf1);
+        cdf_sample_continuous(cdf + sy + (size_t)off1 * sx, sx, u, p2, pdf2);
+        const C3 intensity = eval_texture(sc, __float_as_int(__ldg(L + 14)), p2, p1);
+        const float theta = (1 - p1) * IGB_FLT_PI, phi = (p2 - 0.25f) * 2 * IGB_FLT_PI;
+        float st, ct, sp, cp; dm_sincosf(theta, &st, &ct); dm_sincosf(phi, &sp, &cp);
+        const V3 d = v3(st * cp, st * sp, ct);
+        const float sinTheta = safe_sqrt(1 - d.z * d.z);
+        const float pdf_dir = safe_div(pdf1 * pdf2, sinTheta * IGB_FLT_PI * IGB_FLT_PI * 2);
+        const V3 dir = to_local(env_transform(L), switch_env_up(d));
+        o.pos = from.point + mulf(dir, sc.scene_radius); o.dir = dir;
+        o.intensity = cmulf(intensity, 1 / pdf_dir);
+        o.pdf.value = pdf_dir; o.pdf.measure = 0; o.cos = 1.0f; o.dist = sc.scene_radius;
     } else if (FULL && type == 6) {   // light/sun.art:22-26; p = direction towards the sun, cos(half angle), radiance
         const float cos_angle = __ldg(L + 5);
         const M33 frame = make_orthonormal(neg(v3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4))));
@@ -431,7 +467,10 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
         for (int l = 0; l < sc.n_inf; ++l) {
             const float* L = sc.inf_lights + 32 * l;
             C3 emit; float pdf_s;
-            if (FULL && __float_as_int(__ldg(L)) != 0) {
+            if (FULL && __float_as_int(__ldg(L)) >= 8) {                              // textured environment: light/env.art:145-152,161-167
+                const float4 e = env_textured_eval(sc, L, __float_as_int(__ldg(L)), rdir.x, rdir.y, rdir.z);
+                emit = c3(e.x, e.y, e.z); pdf_s = e.w;
+            } else if (FULL && __float_as_int(__ldg(L)) != 0) {
                 if (__float_as_int(__ldg(L)) == 7) continue;                          // delta lights are not seen by rays (pathtracer.art:149)
                 const bool hit = dot(v3(__ldg(L + 2), __ldg(L + 3), __ldg(L + 4)), rdir) >= __ldg(L + 5);   // sun.art:18,33-45
                 emit = hit ? c3(__ldg(L + 6), __ldg(L + 7), __ldg(L + 8)) : c3(0, 0, 0);
@@ -466,19 +505,59 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
             surf.is_entering = true; surf.point = point; surf.face_normal = normal; surf.area = 0; surf.inv_area = 0;
             surf.pu = hh.y; surf.pv = hh.z; surf.local = make_orthonormal(normal);
         }
-        const float4 m0 = ldg4(sc.materials + 4 * mat_id), m1 = ldg4(sc.materials + 4 * mat_id + 1), m2 = ldg4(sc.materials + 4 * mat_id + 2);
+        const float4* M = sc.materials + 8 * mat_id;
+        const float4 m0 = ldg4(M), m1 = ldg4(M + 1), m2 = ldg4(M + 2);
         const int bsdf = __float_as_int(m0.x);
         const int light_id = __float_as_int(m0.y);
         const V3 N = surf.local.c2;
+        // The BSDF shader of the material (HitShader.cpp:16-53): colour parameters that are textures are looked up at ctx.uvw = tex_coords,
+        // a bump / normal map replaces the frame the BSDF is built on (bsdf/map.art:39-68); emission keeps the surface's own frame.
+        C3 kd = c3(m0.z, m0.w, m1.x);                                                   // DIFFUSE reflectance
+        C3 d_ks = c3(m1.x, m1.y, m1.z), d_kt = c3(m1.w, m2.x, m2.y);                    // DIELECTRIC
+        C3 c_ks = c3(m2.x, m2.y, m2.z);                                                 // CONDUCTOR
+        M33 bl = surf.local;
+        bool rough = false; float au = 0, av = 0;
+        if (FULL) {
+            const float4 m4 = ldg4(M + 4), m5 = ldg4(M + 5);
+            const int tex0 = __float_as_int(m4.x), tex1 = __float_as_int(m4.y), map_kind = __float_as_int(m5.y);
+            if (tex0 >= 0 || tex1 >= 0 || map_kind != 0) {
+                float tu = surf.pu, tv = surf.pv;                                       // sphere: tex_coords = prim_coords (shapes/sphere.art:70)
+                if (si.x == 0) trimesh_texcoords(sc, shape, prim, hh.y, hh.z, tu, tv);
+                if (map_kind == 1) {          // make_bumpmap, texture_dx / texture_dy (texture/common.art:28-38): forward differences, delta = 0.001
+                    const int mt = __float_as_int(m5.z);
+                    const float delta = 0.001f;
+                    const float c0 = eval_texture(sc, mt, tu, tv).r;
+                    const float dx = (eval_texture(sc, mt, tu + delta, tv).r - c0) * (1 / delta);
+                    const float dy = (eval_texture(sc, mt, tu, tv + delta).r - c0) * (1 / delta);
+                    const V3 nn = normalize(surf.local.c2 - mulf(mulf(surf.local.c0, dx) + mulf(surf.local.c1, dy), m5.w));
+                    bl = normal_set_frame(surf.local, surf.face_normal, rdir, nn);
+                } else if (map_kind == 2) {   // make_normalmap, bsdf/map.art:56-60
+                    const C3 c = eval_texture(sc, __float_as_int(m5.z), tu, tv);
+                    const V3 oN = to_local(surf.local, normalize(v3(2 * c.r - 1, 2 * c.g - 1, 2 * c.b - 1)));
+                    const V3 nn = m5.w != 1 ? normalize(surf.local.c2 + mulf(oN - surf.local.c2, m5.w)) : oN;
+                    bl = normal_set_frame(surf.local, surf.face_normal, rdir, nn);
+                }
+                if (tex0 >= 0) { const C3 t = eval_texture(sc, tex0, tu, tv); kd = t; d_ks = t; c_ks = t; }
+                if (tex1 >= 0) d_kt = eval_texture(sc, tex1, tu, tv);
+            }
+            au = m4.w; av = m5.x;
+            rough = bsdf == 2 && __float_as_int(m4.z) == 1 && !(au <= 1e-4f || av <= 1e-4f);   // core/microfacet.art:297,403-425
+        }
+        const V3 bN = bl.c2;
         Rng rnd; rnd.seed = random_seed(sample, iter, rp.frame, pixel % rp.width, pixel / rp.width, rp.seed); rnd.counter = st.y;
 
         // ---- wrap_infobuffer_renderer, technique/internal/infobuffer.art:9-24: Normals / Albedo of the first hit, iteration 0 only
         if (FULL && rp.aov_normals && depth == 1 && iter == 0) {
             C3 albedo;
-            if (bsdf == 0) albedo = c3(m0.z, m0.w, m1.x);                                                       // diffuse.art:10 (kd)
-            else if (bsdf == 1) albedo = c3(lerp1(m1.x, m1.w, 0.5f), lerp1(m1.y, m2.x, 0.5f), lerp1(m1.z, m2.y, 0.5f));   // dielectric.art:35 color_lerp(ks, kt, 0.5)
-            else if (m2.w != 0.0f) albedo = c3(m2.x, m2.y, m2.z);                                               // conductor.art:9 (ks)
-            else { const float ci = dot(neg(rdir), N); albedo = cmul(c3(m2.x, m2.y, m2.z), c3(conductor_factor(m0.z, m1.y, ci), conductor_factor(m0.w, m1.z, ci), conductor_factor(m1.x, m1.w, ci))); }   // conductor.art:28-38
+            if (bsdf == 0) albedo = kd;                                                                         // diffuse.art:10 (kd)
+            else if (bsdf == 1) albedo = c3(lerp1(d_ks.r, d_kt.r, 0.5f), lerp1(d_ks.g, d_kt.g, 0.5f), lerp1(d_ks.b, d_kt.b, 0.5f));   // dielectric.art:35 color_lerp(ks, kt, 0.5)
+            else if (rough) {                                                                                   // conductor.art:50-56 (kd = black)
+                const float ci = absolute_cos(neg(rdir), bN);
+                const C3 F = c3(conductor_factor(m0.z, m1.y, ci), conductor_factor(m0.w, m1.z, ci), conductor_factor(m1.x, m1.w, ci));
+                albedo = c3(0.0f * (1 - F.r) + c_ks.r * F.r, 0.0f * (1 - F.g) + c_ks.g * F.g, 0.0f * (1 - F.b) + c_ks.b * F.b);
+            }
+            else if (m2.w != 0.0f) albedo = c_ks;                                                               // conductor.art:9 (ks)
+            else { const float ci = dot(neg(rdir), bN); albedo = cmul(c_ks, c3(conductor_factor(m0.z, m1.y, ci), conductor_factor(m0.w, m1.z, ci), conductor_factor(m1.x, m1.w, ci))); }   // conductor.art:28-38
             splat(rp.aov_normals, pixel, c3(N.x, N.y, N.z), rp.inv_spi);
             splat(rp.aov_albedo, pixel, c3(fminf(albedo.r, 1.0f), fminf(albedo.g, 1.0f), fminf(albedo.b, 1.0f)), rp.inv_spi);   // color_saturate(albedo, 1)
         }
@@ -509,10 +588,14 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
                 splat(fb, pixel, handle_color(sc, cmulf(cmul(contrib, intensity), mis)), rp.inv_spi); ++n_splat;
             }
         }
-        const C3 kd = c3(m0.z, m0.w, m1.x);
         const V3 out_dir = neg(rdir);
+        BsdfD rb;                                    // the rough conductor (the other BSDFs are written out below)
+        if (FULL && rough) {
+            rb.type = 2; rb.rough = true; rb.mirror = false; rb.entering = surf.is_entering; rb.local = bl; rb.kd = c_ks;
+            rb.kt = c3(m0.z, m0.w, m1.x); rb.ck = c3(m1.y, m1.z, m1.w); rb.n1 = au; rb.n2 = av;
+        }
         // ---- on_shadow, pathtracer.art:52-117
-        if (nee && bsdf == 0 && n_lights != 0 && !(depth + 1 > sc.max_depth)) {
+        if (nee && (bsdf == 0 || (FULL && rough)) && n_lights != 0 && !(depth + 1 > sc.max_depth)) {
             int id; float light_select_pdf = pdf_lights;
             if (!FULL || sc.selector == 0) id = n_lights <= 1 ? 0 : rnd.next_i32(0, n_lights - 1);   // light_selector.art:18-24
             else {
@@ -526,13 +609,13 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
             if (!(pdf_l_s <= IGB_FLT_EPS) && ls.cos > IGB_FLT_EPS) {
                 float mis;
                 if (lt == 1 || (FULL && (lt == 5 || lt == 7))) mis = 1.0f;   // delta lights
-                else { const float pdf_e_s = positive_cos(ls.dir, N) / IGB_FLT_PI; mis = 1 / (1 + pdf_e_s / pdf_l_s); }
+                else { const float pdf_e_s = (FULL && rough) ? rb.pdf(ls.dir, out_dir) : positive_cos(ls.dir, bN) / IGB_FLT_PI; mis = 1 / (1 + pdf_e_s / pdf_l_s); }
                 const float factor = ls.pdf.value / pdf_l_s;
-                const C3 ev = cmulf(kd, positive_cos(ls.dir, N) * IGB_FLT_INV_PI);     // diffuse.art:3
+                const C3 ev = (FULL && rough) ? rb.eval(ls.dir, out_dir) : cmulf(kd, positive_cos(ls.dir, bN) * IGB_FLT_INV_PI);     // diffuse.art:3
                 const C3 cc = handle_color(sc, cmulf(cmul(ls.intensity, cmul(contrib, ev)), mis * factor));
                 if (!((cc.r + cc.g + cc.b) / 3 <= IGB_FLT_EPS)) {
                     V3 s_dir; float s_tmax;
-                    if (lt == 0 || (FULL && (lt == 6 || lt == 7))) { s_dir = ls.dir; s_tmax = IGB_FLT_MAX; }   // infinite lights
+                    if (lt == 0 || (FULL && (lt >= 6))) { s_dir = ls.dir; s_tmax = IGB_FLT_MAX; }   // infinite lights (env, sun, directional, textured env)
                     else { s_dir = ls.pos - surf.point; s_tmax = 1 - 0.001f; }
                     const int ss = coalesced_append(sink.shadow_count);
                     sink.sq.org_tmin[ss] = make_float4(surf.point.x, surf.point.y, surf.point.z, 0.001f);
@@ -548,25 +631,39 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
                 const float u = rnd.next_f32(); const float v = rnd.next_f32();
                 V3 ld;
                 sample_cosine_hemisphere(u, v, ld, s_pdf);
-                in_dir = m33_mul(surf.local, ld); s_color = kd; s_eta = 1; is_delta = false;
+                in_dir = m33_mul(bl, ld); s_color = kd; s_eta = 1; is_delta = false;
+            } else if (FULL && rough) {       // conductor.art:101-122: VNDF sample, mirror about the visible normal; a rejected sample ends the path
+                s_pdf = 0; s_eta = 1; is_delta = false; in_dir = v3(0, 0, 1); s_color = c3(0, 0, 0);
+                if (!(absolute_cos(out_dir, bN) <= IGB_FLT_EPS)) {
+                    const V3 m = sample_vndf_ggx(rnd, bl, out_dir, au, av);
+                    const float m_pdf = pdf_vndf_ggx(bl, out_dir, m, au, av);
+                    if (!(len2(m) <= IGB_FLT_EPS)) {
+                        const V3 oH = normalize(m);
+                        const V3 H = signbit(dot(oH, out_dir)) ? neg(oH) : oH;
+                        in_dir = reflect_(out_dir, H);
+                        if (!(absolute_cos(in_dir, bN) <= IGB_FLT_EPS)) {
+                            const float jacob = 1 / (4 * absolute_cos(out_dir, H));
+                            s_pdf = m_pdf * jacob;
+                            s_color = cmulf(rb.eval(in_dir, out_dir), safe_div(1, s_pdf));
+                        }
+                    }
+                }
             } else if (FULL && bsdf == 2) {   // conductor.art:2-27: mirror / smooth conductor; p = eta rgb, k rgb, ks rgb, mirror flag
-                const C3 ks = c3(m2.x, m2.y, m2.z);
-                in_dir = mulf(N, 2 * dot(N, out_dir)) - out_dir;                                                                   // vector.art:124
-                if (m2.w != 0.0f) s_color = ks;
+                in_dir = mulf(bN, 2 * dot(bN, out_dir)) - out_dir;                                                                 // vector.art:124
+                if (m2.w != 0.0f) s_color = c_ks;
                 else {
-                    const float cos_i = dot(out_dir, N);
-                    s_color = cmul(ks, c3(conductor_factor(m0.z, m1.y, cos_i), conductor_factor(m0.w, m1.z, cos_i), conductor_factor(m1.x, m1.w, cos_i)));
+                    const float cos_i = dot(out_dir, bN);
+                    s_color = cmul(c_ks, c3(conductor_factor(m0.z, m1.y, cos_i), conductor_factor(m0.w, m1.z, cos_i), conductor_factor(m1.x, m1.w, cos_i)));
                 }
                 s_eta = 1; s_pdf = 1; is_delta = true;
             } else {          // dielectric.art:18-34
                 const float n1 = m0.z, n2 = m0.w;
-                const C3 ks = c3(m1.x, m1.y, m1.z), kt = c3(m1.w, m2.x, m2.y);
                 const float k = surf.is_entering ? n1 / n2 : n2 / n1;
-                const float cos_o = dot(out_dir, N);
+                const float cos_o = dot(out_dir, bN);
                 float cos_t = 0, factor = 1;
                 if (!fresnel(k, cos_o, cos_t, factor)) { cos_t = 0; factor = 1; }
-                if (rnd.next_f32() > factor) { in_dir = mulf(N, k * cos_o - cos_t) - mulf(out_dir, k); s_color = kt; s_eta = k; }   // vector.art:127
-                else { in_dir = mulf(N, 2 * dot(N, out_dir)) - out_dir; s_color = ks; s_eta = 1; }                                 // vector.art:124
+                if (rnd.next_f32() > factor) { in_dir = mulf(bN, k * cos_o - cos_t) - mulf(out_dir, k); s_color = d_kt; s_eta = k; }   // vector.art:127
+                else { in_dir = mulf(bN, 2 * dot(bN, out_dir)) - out_dir; s_color = d_ks; s_eta = 1; }                               // vector.art:124
                 s_pdf = 1; is_delta = true;
             }
             if (!(s_pdf <= IGB_FLT_EPS)) {

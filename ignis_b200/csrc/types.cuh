@@ -19,7 +19,11 @@ struct DevScene {
     const float4* ent_shade;  // 6 float4 per entity: global rows 0-2, normal rows 0-2 (.w = shape_id, mat_id, 0)
     const float4* blob;       // `shapes` dyn-table data
     const int4*   shape_info; // 2 int4 per shape: (type, v_start, n_start, i_start) (tex_start_f2, n_face, 0, 0)
-    const float4* materials;  // 4 float4 per material (igb200_material)
+    const float4* materials;  // 8 float4 per material (igb200_material, 128 bytes)
+    const float*  textures;   // 24 words per texture (igb200_texture)
+    const int4*   images;     // per image: format, width, height, first 32-bit word of its pixels inside image_data (16-byte aligned)
+    const uint32_t* image_data;
+    const float*  aux_data;   // 2-D cdfs of the textured environment lights
     const float*  inf_lights; // 32 words per light (igb200_light)
     const float*  fin_lights;
     int   n_ent, n_mat, n_inf, n_fin;

@@ -555,8 +555,8 @@ def bake_texture(tex, images, max_w: int = 1024, max_h: int = 512) -> np.ndarray
     else:
         w = h = 1
     w, h = max(1, min(max_w, w)), max(1, min(max_h, h))
-    xs = (np.arange(w, dtype=F) / F(max(w - 1, 1))).astype(F) if w > 1 else np.full(1, np.nan, F)
-    ys = (np.arange(h, dtype=F) / F(max(h - 1, 1))).astype(F) if h > 1 else np.full(1, np.nan, F)
+    xs = (np.arange(w, dtype=F) / F(max(w - 1, 1))).astype(F) if w > 1 else np.zeros(1, F)
+    ys = (np.arange(h, dtype=F) / F(max(h - 1, 1))).astype(F) if h > 1 else np.zeros(1, F)
     uu, vv = np.meshgrid(xs, ys)
     return eval_texture_np(tex, images, uu, vv)
 
