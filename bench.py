@@ -37,6 +37,15 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 SCENE = "scenes/diamond_scene.json"
+# BASELINE.json configs; the default (headline, what the driver runs) is c2. The others are parity-test cases that can be timed the same way.
+WORKLOADS = {
+    "c2": dict(scene="scenes/diamond_scene.json", width=1920, height=1080, spi=4, name="diamond_scene", note="BASELINE.json configs[1]; 16 steps = 64 spp"),
+    "c3": dict(scene="scenes/primitives.json", width=1920, height=1080, spi=4, name="primitives", note="BASELINE.json configs[2]; 64 steps = 256 spp"),
+    "c4": dict(scene="scenes/synthetic_room.json", width=1920, height=1080, spi=4, name="synthetic_room",
+               note="BASELINE.json configs[3] (4 GPUs): the Bitterli bedroom is not obtainable offline; stand-in with 1.8 M instanced triangles (tools/make_room_scene.py); 32 steps = 128 spp"),
+    "c5": dict(scene="scenes/many_point_lights.json", width=3840, height=2160, spi=1, name="many_point_lights",
+               note="BASELINE.json configs[4] (8 GPUs): hierarchy selector over 10 embedded point lights + sky, checkerboard, bump-mapped rough conductor; spi 1 = the reference's GPU policy at this size (Runtime.cpp:71-79); 512 steps = 512 spp"),
+}
 # algorithmic bytes per unit of work of the wavefront hand-off
 B_PRIMARY, B_SHADOW, B_SPLAT = 216, 108, 24
 # the same figure split by pipeline stage (DESIGN.md "Algorithmic bytes")
@@ -162,13 +171,13 @@ def run_reference(args):
     from oracle import oracle as o
     flags = build_timing_oracle()
     cores = int(o.lib().igo_hardware_threads())
-    tables = load_scene(os.path.join(ROOT, SCENE), args.width, args.height)
+    tables = load_scene(os.path.join(ROOT, args.scene), args.width, args.height)
     w, h, spi = args.width, args.height, args.spi
     if args.warmup > 0:
         cpu_render_steps(tables, w, h, spi, args.warmup)
     dt, rays = cpu_render_steps(tables, w, h, spi, args.steps, first_iter=args.warmup)
     value = rays / dt / 1e6
-    line = {"impl": "reference", "metric": "Mrays/s (camera+bounce+shadow) @1920x1080 diamond_scene path", "value": value, "unit": "Mrays/s",
+    line = {"impl": "reference", "metric": metric_name(args), "value": value, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1),
@@ -181,11 +190,16 @@ def run_reference(args):
     return 0
 
 
+def metric_name(args):
+    return f"Mrays/s (camera+bounce+shadow) @{args.width}x{args.height} {WORKLOADS[args.workload]['name']} path"
+
+
 def workload_config(args, world):
-    return {"workload": f"{SCENE} {args.width}x{args.height}, path integrator max_depth 64, spi {args.spi}, seed 0; 1 step = 1 render() iteration "
-                        f"({args.spi} spp, {args.width * args.height * args.spi} camera rays); 16 steps = 64 spp (BASELINE.json configs[1])",
+    return {"workload": f"{args.scene} {args.width}x{args.height}, path integrator, spi {args.spi}, seed 0; 1 step = 1 render() iteration "
+                        f"({args.spi} spp, {args.width * args.height * args.spi} camera rays); {WORKLOADS[args.workload]['note']}",
+            "config_id": args.workload,
             "spi": args.spi, "width": args.width, "height": args.height,
-            "parallelism": f"framebuffer tiles 32x32 dealt along diagonals over {world} GPU(s), scene replicated, one NCCL gather of the ranks' tiles of the accumulation buffer onto rank 0",
+            "parallelism": f"framebuffer tiles 32x32 dealt along diagonals over {world} GPU(s), scene replicated, one NCCL gather (send / recv inside the device library, igb200_comm_gather_framebuffer) of the ranks' tiles of the accumulation buffer onto rank 0",
             "l2": "no flush needed: every step streams its ray queues through HBM (> 800 MB per step per GPU at N=1, L2 is 126 MB)"}
 
 
@@ -193,8 +207,8 @@ def workload_config(args, world):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from ignis_b200.device import Runtime
-    from ignis_b200.partition import TILE, TileGather
+    from ignis_b200.device import B200Device, Runtime
+    from ignis_b200.partition import TILE
     from ignis_b200.scene import load_scene
 
     rank = int(os.environ.get("RANK", "0"))
@@ -212,29 +226,26 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w, h, spi = args.width, args.height, args.spi
-    tables = load_scene(os.path.join(ROOT, SCENE), w, h)
+    tables = load_scene(os.path.join(ROOT, args.scene), w, h)
     rt = Runtime(tables, w, h, spi=spi, seed=0, cuda_device=local_rank)
     dev = rt.device
-    dev.setPartition(rank, world, TILE)
+    if world > 1:
+        # the exchange lives behind the C ABI (igb200_comm_*: NCCL send / recv of the ranks' tiles inside the device library);
+        # torch.distributed only carries the 128-byte NCCL id to the ranks, the barriers and the statistics of this script
+        ids = [B200Device.commUniqueId() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        dev.commInit(rank, world, ids[0], TILE)
     stream = torch.cuda.ExternalStream(dev.stream(), device=torch.device("cuda", local_rank))
-
-    class _FB:  # device framebuffer as a torch tensor (no copy)
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-    fb_t = torch.as_tensor(_FB(dev.getFramebufferForDevice(), w * h * 3), device=torch.device("cuda", local_rank))
-    scratch = torch.empty_like(fb_t) if (world > 1 and rank == 0) else None
-    gather = TileGather(w, h, rank, world, TILE, device=torch.device("cuda", local_rank)) if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def reduce_to_root():
+    def reduce_to_root(to_host=False):
         # disjoint tile support: the sum of the accumulation buffers is a gather of the per-rank tiles; rank 0 ends up
-        # with the complete frame in `scratch` (its own accumulation buffer keeps accumulating only its tiles)
-        with torch.cuda.stream(stream):
-            gather.run(fb_t, out=scratch)
+        # with the complete frame in a buffer of its own (its accumulation buffer keeps accumulating only its tiles)
+        return dev.commGatherFramebuffer("", to_host=to_host)[1]
 
     # ---- warm-up (also sizes the ray queues and warms NCCL)
     for _ in range(max(args.warmup, 0)):
@@ -261,12 +272,7 @@ def run_b200(args):
                 rt.step()
                 if e2e:
                     if world > 1:
-                        dev.sync()
-                        reduce_to_root()
-                        if rank == 0:
-                            with torch.cuda.stream(stream):
-                                host_t.copy_(scratch, non_blocking=True)
-                            stream.synchronize()
+                        host = reduce_to_root(to_host=True)   # gather onto rank 0 + D2H of the complete frame there
                     else:
                         host = dev.getFramebufferForHost()   # D2H of the accumulated frame into pinned memory
             ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -304,8 +310,6 @@ def run_b200(args):
         timed.per_rank = per_rank
         return ms, wall_ms, tot, clk.summary(), host
 
-    host_t = torch.empty(w * h * 3, dtype=torch.float32, pin_memory=True) if (world > 1 and rank == 0) else None
-
     ms, wall_ms, tot, clocks, _ = timed(e2e=False)
     per_rank = timed.per_rank
     ms_e, wall_e, tot_e, _, host = timed(e2e=True)
@@ -336,13 +340,8 @@ def run_b200(args):
             rt.step()
         frame = None
         if world > 1:
-            dev.sync()
-            reduce_to_root()
-            if rank == 0:
-                with torch.cuda.stream(stream):
-                    host_t.copy_(scratch, non_blocking=True)
-                stream.synchronize()
-                frame = host_t.numpy().reshape(h, w, 3).copy()
+            frame = reduce_to_root(to_host=True)
+            frame = None if frame is None else frame.copy()
         else:
             frame = dev.getFramebufferForHost().copy()
         pst = dev.getStatistics()
@@ -368,7 +367,7 @@ def run_b200(args):
         peak, peak_src = measured_peaks()
         value = tot["TotalRays"] / (ms * 1e-3) / 1e6
         e2e_value = tot_e["TotalRays"] / (wall_e * 1e-3) / 1e6
-        line = {"metric": "Mrays/s (camera+bounce+shadow) @1920x1080 diamond_scene path", "value": value, "unit": "Mrays/s", "n_gpus": world,
+        line = {"metric": metric_name(args), "value": value, "unit": "Mrays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
                 "clocks": clocks, "gpu_launches": tot["KernelLaunches"],
@@ -424,7 +423,7 @@ def run_b200(args):
     # tear down in dependency order: tensors that alias or were used on the device's stream go first, then the device
     # (which owns that stream), then NCCL; otherwise the allocator records events on a stream that no longer exists at exit
     torch.cuda.synchronize()
-    del fb_t, scratch, host_t, gather, stream
+    del stream
     torch.cuda.synchronize()
     rt.close()
     if world > 1:
@@ -439,13 +438,17 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--spi", type=int, default=4)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config (default: the headline one, c2)")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--spi", type=int, default=0)
     ap.add_argument("--cpu-iters", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-iters", type=int, default=2, help="iterations of the parity check against the oracle (0: skip)")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    args.scene = wl["scene"]
+    args.width, args.height, args.spi = args.width or wl["width"], args.height or wl["height"], args.spi or wl["spi"]
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -1,5 +1,7 @@
 // C ABI (include/igb200.h) + global kernels + host-side wavefront loop of the B200 render device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is loaded at run time (igb200_comm_*)
 
 #include <algorithm>
 #include <cfloat>
@@ -55,6 +57,32 @@ static TraceKernel trace_kernel(int min_blocks, int vote, int where = 0) {
     if (min_blocks >= 4) return vote ? k_trace<WF_BLOCK, 4, 2> : k_trace<WF_BLOCK, 4, 0>;   // 64 registers: stand-alone trace phase only
     if (vote) return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 2> : k_trace<WF_BLOCK, 2, 2>;
     return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 0> : k_trace<WF_BLOCK, 2, 0>;
+}
+
+// ---- the exchange step: pixels of one rank's tiles <-> a contiguous buffer [local tile][tile x tile][rgb]
+// pack: this rank's k-th tile (tile_table[k] = row-major tile index) out of its accumulation buffer
+__global__ void k_pack_tiles(const float* __restrict__ fb, float* __restrict__ out, const int* __restrict__ tile_table, int n_tiles, int tile, int tiles_x, int width, int height) {
+    const long long n = (long long)n_tiles * tile * tile;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / (tile * tile)), r = (int)(i - (long long)k * tile * tile);
+        const int t = tile_table[k];
+        const int x = (t % tiles_x) * tile + r % tile, y = (t / tiles_x) * tile + r / tile;
+        float3 v = make_float3(0, 0, 0);
+        if (x < width && y < height) { const float* p = fb + ((size_t)y * width + x) * 3; v = make_float3(p[0], p[1], p[2]); }
+        out[i * 3] = v.x; out[i * 3 + 1] = v.y; out[i * 3 + 2] = v.z;
+    }
+}
+// unpack (rank 0): every pixel of the frame from the region of the rank that owns its tile; local_index[t] = position of tile t in its owner's list
+__global__ void k_unpack_tiles(float* __restrict__ frame, const float* __restrict__ in, const int* __restrict__ local_index, const long long* __restrict__ rank_offset,
+                               int world, int tile, int tiles_x, int width, int height) {
+    const long long n = (long long)width * height;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(p % width), y = (int)(p / width);
+        const int tx = x / tile, ty = y / tile, t = ty * tiles_x + tx;
+        const int r = (tx + ty) % world;
+        const float* src = in + rank_offset[r] + ((long long)local_index[t] * tile * tile + (long long)(y % tile) * tile + x % tile) * 3;
+        frame[p * 3] = src[0]; frame[p * 3 + 1] = src[1]; frame[p * 3 + 2] = src[2];
+    }
 }
 
 __global__ void k_detmath(int fn, const float* a, const float* b, float* out, int n) {
@@ -175,6 +203,14 @@ struct igb200_ctx {
     std::vector<Timed> timed;
     double prof_ms[4] = {0, 0, 0, 0}; uint64_t prof_n[4] = {0, 0, 0, 0};
     DevBuf<igb200_ray> list_rays;
+    // multi-GPU exchange (igb200_comm_*)
+    ncclComm_t comm = nullptr;
+    DevBuf<float> comm_send, comm_recv, comm_frame;
+    DevBuf<int> comm_local_index;
+    DevBuf<long long> comm_rank_offset;
+    float* comm_host = nullptr; size_t comm_host_n = 0;
+    long long comm_key[4] = {0, 0, 0, 0};
+    std::vector<long long> comm_counts;   // floats each rank sends
 };
 
 static int ensure_queues(igb200_ctx* c, size_t need) {
@@ -320,6 +356,21 @@ static int launch_split_turns(igb200_ctx* c, const WaveParams& P, int turns) {
     return 0;
 }
 
+// This rank's tiles (row-major tile indices) on the device: tile (tx, ty) belongs to rank (tx + ty) mod world
+static int ensure_tile_table(igb200_ctx* c, int W, int H) {
+    const int tiles_x = (W + c->tile - 1) / c->tile, tiles_y = (H + c->tile - 1) / c->tile;
+    const long long tiles_total = (long long)tiles_x * tiles_y;
+    const long long key[5] = {W, H, c->tile, c->rank, c->world};
+    if (std::memcmp(key, c->tile_key, sizeof(key)) == 0) return 0;
+    std::vector<int> table;
+    for (long long t = 0; t < tiles_total; ++t) if ((int)((t % tiles_x + t / tiles_x) % c->world) == c->rank) table.push_back((int)t);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(c->tile_table.upload(table));
+    c->n_local_tiles = (long long)table.size();
+    std::memcpy(c->tile_key, key, sizeof(key));
+    return 0;
+}
+
 // iterations per launch: enough to generate ~8 M camera rays, at most 8 (option "fuse" overrides)
 static int fuse_factor(const igb200_ctx* c, const igb200_settings* st) {
     if (c->fuse > 0) return c->fuse;
@@ -408,6 +459,7 @@ int igb200_destroy(igb200_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    igb200_comm_destroy(c);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_frame) cudaEventDestroy(c->ev_frame);
     if (c->ev_copied) cudaEventDestroy(c->ev_copied);
@@ -768,6 +820,7 @@ int igb200_resize(igb200_ctx* c, int width, int height) {
     if (width == c->width && height == c->height) return 0;
     { const int r = sync_control(c); if (r) return r; }
     c->width = width; c->height = height;
+    std::memset(c->comm_key, 0, sizeof(c->comm_key));
     const size_t n = (size_t)width * height * 3;
     CU(c->fb.alloc(n));
     CU(cudaMemset(c->fb.p, 0, n * sizeof(float)));
@@ -951,15 +1004,7 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
     long long local_tiles = tiles_total;
     rp.tile_table = nullptr;
     if (rp.world > 1) {
-        const long long key[5] = {W, H, rp.tile_w, rp.rank, rp.world};
-        if (std::memcmp(key, c->tile_key, sizeof(key)) != 0) {
-            std::vector<int> table;
-            for (long long t = 0; t < tiles_total; ++t) if ((int)((t % rp.tiles_x + t / rp.tiles_x) % rp.world) == rp.rank) table.push_back((int)t);
-            CU(cudaStreamSynchronize(c->stream));
-            CU(c->tile_table.upload(table));
-            c->n_local_tiles = (long long)table.size();
-            std::memcpy(c->tile_key, key, sizeof(key));
-        }
+        { const int r = ensure_tile_table(c, W, H); if (r) return r; }
         local_tiles = c->n_local_tiles;
         rp.tile_table = c->tile_table.p;
     }
@@ -1117,6 +1162,138 @@ int igb200_trace_any(igb200_ctx* c, const igb200_ray* rays, size_t n, int32_t* o
 int igb200_bench_trace(igb200_ctx* c, const igb200_ray* rays, size_t n, int any_hit, int repeat, double* ms_per_pass) {
     if (!ms_per_pass || repeat < 1) return fail(-1, "igb200_bench_trace: bad argument");
     return trace_list(c, rays, nullptr, n, any_hit, nullptr, nullptr, repeat, ms_per_pass);
+}
+
+// ---- multi-GPU exchange: NCCL point-to-point over NVLink, loaded at run time -------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr; decltype(&ncclCommInitRank) CommInitRank = nullptr; decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr; decltype(&ncclRecv) Recv = nullptr; decltype(&ncclGroupStart) GroupStart = nullptr; decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr; decltype(&ncclGetVersion) GetVersion = nullptr;
+    std::string where;
+};
+NcclApi g_nccl;
+int load_nccl() {
+    if (g_nccl.handle) return 0;
+    // the copy the process already has (PyTorch brings its own) wins: two NCCL builds in one process must not be mixed
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    std::string where = "libnccl.so.2 (already loaded in the process)";
+    if (!h) { const char* env = getenv("IGB200_NCCL_LIB"); if (env && *env) { h = dlopen(env, RTLD_NOW | RTLD_GLOBAL); where = env; } }
+    if (!h) { h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL); where = "libnccl.so.2 (system)"; }
+    if (!h) return fail(-3, "igb200_comm: cannot load libnccl.so.2 (%s); set IGB200_NCCL_LIB", dlerror());
+    NcclApi a; a.handle = h; a.where = where;
+#define IGB_SYM(N) a.N = reinterpret_cast<decltype(a.N)>(dlsym(h, "nccl" #N)); if (!a.N) return fail(-3, "igb200_comm: nccl" #N " not found in %s", where.c_str());
+    IGB_SYM(GetUniqueId) IGB_SYM(CommInitRank) IGB_SYM(CommDestroy) IGB_SYM(Send) IGB_SYM(Recv) IGB_SYM(GroupStart) IGB_SYM(GroupEnd) IGB_SYM(GetErrorString) IGB_SYM(GetVersion)
+#undef IGB_SYM
+    g_nccl = a;
+    return 0;
+}
+}  // namespace
+#define NC(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(-2, "%s failed: %s (%s:%d)", #x, g_nccl.GetErrorString(r_), __FILE__, __LINE__); } while (0)
+
+int igb200_comm_unique_id(uint8_t id[128]) {
+    if (!id) return fail(-1, "igb200_comm_unique_id: null argument");
+    { const int r = load_nccl(); if (r) return r; }
+    ncclUniqueId u;
+    static_assert(sizeof(u) == 128, "ncclUniqueId");
+    NC(g_nccl.GetUniqueId(&u));
+    std::memcpy(id, &u, 128);
+    return 0;
+}
+
+int igb200_comm_init(igb200_ctx* c, int rank, int world, int tile_size, const uint8_t id[128]) {
+    if (!c || !id) return fail(-1, "igb200_comm_init: null argument");
+    if (world < 1 || rank < 0 || rank >= world || tile_size < 1) return fail(-1, "igb200_comm_init: invalid rank %d / world %d / tile %d", rank, world, tile_size);
+    if (c->comm) return fail(-1, "igb200_comm_init: this context already has a communicator");
+    { const int r = load_nccl(); if (r) return r; }
+    { const int r = igb200_set_partition(c, rank, world, tile_size); if (r) return r; }
+    CU(cudaSetDevice(c->device));
+    ncclUniqueId u; std::memcpy(&u, id, 128);
+    NC(g_nccl.CommInitRank(&c->comm, world, u, rank));
+    return 0;
+}
+
+int igb200_comm_destroy(igb200_ctx* c) {
+    if (!c) return fail(-1, "null context");
+    if (c->comm) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        g_nccl.CommDestroy(c->comm);
+        c->comm = nullptr;
+    }
+    if (c->comm_host) { cudaFreeHost(c->comm_host); c->comm_host = nullptr; c->comm_host_n = 0; }
+    return 0;
+}
+
+int igb200_comm_gather_framebuffer(igb200_ctx* c, const char* aov, float** device_frame, float** host_frame) {
+    if (!c) return fail(-1, "null context");
+    if (!c->comm) return fail(-1, "igb200_comm_gather_framebuffer: no communicator (igb200_comm_init)");
+    const int which = aov_index(c, aov);
+    if (which < 0) return fail(-4, "igb200_comm_gather_framebuffer: AOV '%s' does not exist", aov);
+    { const int r = flush_queued(c); if (r) return r; }
+    if (!c->fb.p) return fail(-1, "igb200_comm_gather_framebuffer: no framebuffer");
+    CU(cudaSetDevice(c->device));
+    { const int r = drain(c); if (r) return r; }   // asynchronous: the exchange below is ordered behind it on the stream
+    const int W = c->width, H = c->height, tile = c->tile, world = c->world, rank = c->rank;
+    const int tiles_x = (W + tile - 1) / tile, tiles_y = (H + tile - 1) / tile;
+    const long long per_tile = (long long)tile * tile * 3;
+    {   // per-rank tile counts, and on rank 0 the tables the unpack kernel needs
+        const long long key[4] = {W, H, tile, world};
+        if (std::memcmp(key, c->comm_key, sizeof(key)) != 0) {
+            std::vector<long long> n_tiles(world, 0), offs(world, 0);
+            std::vector<int> local_index((size_t)tiles_x * tiles_y);
+            for (int t = 0; t < tiles_x * tiles_y; ++t) { const int r = (t % tiles_x + t / tiles_x) % world; local_index[t] = (int)n_tiles[r]++; }
+            long long total = 0;
+            for (int r = 0; r < world; ++r) { offs[r] = total; total += n_tiles[r] * per_tile; }
+            c->comm_counts.assign(world, 0);
+            for (int r = 0; r < world; ++r) c->comm_counts[r] = n_tiles[r] * per_tile;
+            CU(cudaStreamSynchronize(c->stream));
+            CU(c->comm_send.alloc((size_t)c->comm_counts[rank]));
+            if (rank == 0) {
+                CU(c->comm_recv.alloc((size_t)total));
+                CU(c->comm_frame.alloc((size_t)W * H * 3));
+                CU(c->comm_local_index.upload(local_index));
+                CU(c->comm_rank_offset.upload(offs));
+            }
+            std::memcpy(c->comm_key, key, sizeof(key));
+        }
+        { const int r = ensure_tile_table(c, W, H); if (r) return r; }
+    }
+    const float* src = which == 0 ? c->fb.p : c->aov[which - 1].p;
+    if (!src) return fail(-1, "igb200_comm_gather_framebuffer: AOV '%s' is not allocated", aov);
+    const int grid = c->n_sm * 8;
+    std::vector<long long> offs(world, 0);
+    { long long t = 0; for (int r = 0; r < world; ++r) { offs[r] = t; t += c->comm_counts[r]; } }
+    // rank 0 packs straight into its region of the receive buffer; the others into their send buffer
+    float* pack_to = rank == 0 ? c->comm_recv.p + offs[0] : c->comm_send.p;
+    if (world > 1) k_pack_tiles<<<grid, 256, 0, c->stream>>>(src, pack_to, c->tile_table.p, (int)c->n_local_tiles, tile, tiles_x, W, H);
+    if (world > 1) {
+        NC(g_nccl.GroupStart());
+        if (rank == 0) { for (int r = 1; r < world; ++r) NC(g_nccl.Recv(c->comm_recv.p + offs[r], (size_t)c->comm_counts[r], ncclFloat32, r, c->comm, c->stream)); }
+        else NC(g_nccl.Send(c->comm_send.p, (size_t)c->comm_counts[rank], ncclFloat32, 0, c->comm, c->stream));
+        NC(g_nccl.GroupEnd());
+    }
+    c->pending = true;
+    if (device_frame) *device_frame = nullptr;
+    if (host_frame && rank != 0) *host_frame = nullptr;
+    if (rank != 0) { CU(cudaGetLastError()); return 0; }
+    if (world > 1) k_unpack_tiles<<<grid, 256, 0, c->stream>>>(c->comm_frame.p, c->comm_recv.p, c->comm_local_index.p, c->comm_rank_offset.p, world, tile, tiles_x, W, H);
+    else CU(cudaMemcpyAsync(c->comm_frame.p, src, (size_t)W * H * 3 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaGetLastError());
+    if (device_frame) *device_frame = c->comm_frame.p;
+    if (host_frame) {
+        const size_t n = (size_t)W * H * 3;
+        if (c->comm_host_n != n) {
+            if (c->comm_host) { cudaFreeHost(c->comm_host); c->comm_host = nullptr; }
+            CU(cudaMallocHost(&c->comm_host, n * sizeof(float)));
+            c->comm_host_n = n;
+        }
+        CU(cudaMemcpyAsync(c->comm_host, c->comm_frame.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        *host_frame = c->comm_host;
+    }
+    return 0;
 }
 
 int igb200_test_detmath(igb200_ctx* c, int fn, const float* a, const float* b, float* out, size_t n) {

@@ -69,7 +69,8 @@ HIT_DTYPE = np.dtype([("ent_id", "<i4"), ("prim_id", "<i4"), ("t", "<f4"), ("u",
 SYMBOLS = ["igb200_last_error", "igb200_version", "igb200_create", "igb200_destroy", "igb200_set_scene", "igb200_resize",
            "igb200_set_partition", "igb200_render", "igb200_sync", "igb200_framebuffer", "igb200_framebuffer_device", "igb200_clear",
            "igb200_upload_framebuffer", "igb200_stats", "igb200_reset_stats", "igb200_kernel_times", "igb200_launch_profile", "igb200_turn_log", "igb200_step_stats", "igb200_set_option",
-           "igb200_stream", "igb200_trace_closest", "igb200_trace_any", "igb200_bench_trace", "igb200_test_detmath"]
+           "igb200_stream", "igb200_trace_closest", "igb200_trace_any", "igb200_bench_trace", "igb200_test_detmath",
+           "igb200_comm_unique_id", "igb200_comm_init", "igb200_comm_gather_framebuffer", "igb200_comm_destroy"]
 
 
 def library_path() -> str:
@@ -113,6 +114,10 @@ def lib():
         L.igb200_trace_any.argtypes = [vp, vp, C.c_size_t, vp]
         L.igb200_bench_trace.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.igb200_test_detmath.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t]
+        L.igb200_comm_unique_id.argtypes = [vp]
+        L.igb200_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+        L.igb200_comm_gather_framebuffer.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.POINTER(C.c_float))]
+        L.igb200_comm_destroy.argtypes = [vp]
         _LIB = L
     return _LIB
 
@@ -247,6 +252,28 @@ class B200Device:
     # -- device-specific
     def setPartition(self, rank: int, world: int, tile: int = 32):
         _check(lib().igb200_set_partition(self._h, rank, world, tile))
+
+    # -- multi-GPU exchange inside the device (include/igb200.h igb200_comm_*)
+    @staticmethod
+    def commUniqueId() -> bytes:
+        """ncclGetUniqueId: made by rank 0, carried to every rank by the caller."""
+        buf = (C.c_uint8 * 128)()
+        _check(lib().igb200_comm_unique_id(buf))
+        return bytes(buf)
+
+    def commInit(self, rank: int, world: int, unique_id: bytes, tile: int = 32):
+        assert len(unique_id) == 128
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().igb200_comm_init(self._h, rank, world, tile, buf))
+        self._rank, self._world = rank, world
+
+    def commGatherFramebuffer(self, name: str = "", to_host: bool = True):
+        """The path's one exchange: every rank's tiles -> rank 0. Collective. Rank 0 gets (device pointer, host array or None)."""
+        dp, hp = C.c_void_p(), C.POINTER(C.c_float)()
+        _check(lib().igb200_comm_gather_framebuffer(self._h, name.encode(), C.byref(dp), C.byref(hp) if to_host else None))
+        if not dp.value:
+            return None, None
+        return int(dp.value), (np.ctypeslib.as_array(hp, shape=(self._h_, self._w, 3)) if to_host else None)
 
     def setOption(self, name: str, value: int):
         _check(lib().igb200_set_option(self._h, name.encode(), int(value)))

@@ -224,6 +224,21 @@ int igb200_resize(igb200_ctx* ctx, int width, int height);        /* IRenderDevi
  * tile row ty belongs to rank (tx + ty) mod world. No reference counterpart (the reference is single-device, Device.cpp:1632). */
 int igb200_set_partition(igb200_ctx* ctx, int rank, int world, int tile_size);
 
+/* ---- multi-GPU exchange inside the device (the reference is single-device, Device.cpp:1632) --------------------------------
+ * One context per GPU, one process (or thread) per context. The ranks' contexts form an NCCL communicator: rank 0 makes a unique id
+ * (ncclGetUniqueId), the caller carries the 128 bytes to every rank by whatever means it has (file, socket, MPI, torch.distributed),
+ * every rank calls igb200_comm_init, which also sets the tile partition (as igb200_set_partition). igb200_comm_gather_framebuffer is the
+ * path's ONE exchange step: every rank packs the pixels of its own tiles (a kernel on the context's stream), sends them to rank 0
+ * (ncclSend / ncclRecv over NVLink, enqueued on the same stream right behind the render kernels and the drain of their deferred tail), and
+ * rank 0 unpacks them into a complete frame that it owns separately from its own accumulation buffer. Collective: every rank must call it.
+ * NCCL is loaded at run time (libnccl.so.2: the copy already in the process if there is one, else $IGB200_NCCL_LIB, else the system's). */
+int igb200_comm_unique_id(uint8_t id[128]);
+int igb200_comm_init(igb200_ctx* ctx, int rank, int world, int tile_size, const uint8_t id[128]);
+/* Asynchronous on the context's stream. Rank 0: *device_frame = the gathered frame (W*H*3 floats, valid until the next gather or resize);
+ * if host_frame is non-NULL the frame is also copied to context-owned pinned memory and the call waits for it. Other ranks: both NULL. */
+int igb200_comm_gather_framebuffer(igb200_ctx* ctx, const char* aov, float** device_frame, float** host_frame);
+int igb200_comm_destroy(igb200_ctx* ctx);
+
 /* One iteration: IRenderDevice::render, Device.cpp:1672-1682. `rays` non-null selects the list emitter of igtrace
  * (Runtime::trace, Runtime.cpp:389-446): width = n_rays, height = 1. Accumulates into the device framebuffer.
  * The call is ASYNCHRONOUS on the context's stream (the reference's GPU device ends every iteration with acc.sync(),
