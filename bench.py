@@ -219,7 +219,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on stdout when the first communicator is made: keep stdout for the one JSON line
+        # NCCL prints on stdout (version banner, everything NCCL_DEBUG asks for): keep the real stdout for the one JSON line (see the end)
         sys.stdout.flush()
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
@@ -253,10 +253,6 @@ def run_b200(args):
     if world > 1:
         reduce_to_root()
     barrier()
-    if world > 1:
-        sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
-        os.close(saved_stdout)
 
     def timed(e2e: bool):
         rt.reset()
@@ -265,10 +261,24 @@ def run_b200(args):
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
+        frames = 0
         with ClockSampler(local_rank) as clk:
             ev0.record(stream)
             host = None
-            for _ in range(args.steps):
+            if e2e and args.e2e_mode == "stream":
+                # every step's frame travels to pinned host memory (after the tile gather at N > 1) while later steps render; the timed
+                # region ends when the LAST step's frame has arrived (igb200_frame_stream_*). All K frames are received inside it.
+                for _ in range(args.steps):
+                    rt.step()
+                    while (f := dev.frameStreamNext(0)) is not None:
+                        frames += 1
+                        host = f[1]
+                while (f := dev.frameStreamNext(2)) is not None:
+                    frames += 1
+                    host = f[1]
+                if rank == 0:
+                    assert frames == args.steps, (frames, args.steps)
+            for _ in range(args.steps if not (e2e and args.e2e_mode == "stream") else 0):
                 rt.step()
                 if e2e:
                     if world > 1:
@@ -312,7 +322,16 @@ def run_b200(args):
 
     ms, wall_ms, tot, clocks, _ = timed(e2e=False)
     per_rank = timed.per_rank
+    if args.e2e_mode == "stream":
+        dev.frameStreamBegin(32 if world > 1 else 16)
+        for _ in range(2):                 # warm the streaming path: pinned frame buffers are allocated on first use
+            rt.step()
+        while dev.frameStreamNext(2) is not None:
+            pass
     ms_e, wall_e, tot_e, _, host = timed(e2e=True)
+    image_mean = float(np.asarray(host).mean() / args.steps) if host is not None else None
+    if args.e2e_mode == "stream":
+        dev.frameStreamEnd()
 
     # ---- per-kernel timing (separate pass, N = 1): every launch bracketed by CUDA events on the render stream
     kt = None
@@ -372,7 +391,9 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
                 "clocks": clocks, "gpu_launches": tot["KernelLaunches"],
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": w * h * 12,
-                        "ms_per_step": wall_e / args.steps, "timed": "host wall clock between barriers, max over ranks"},
+                        "ms_per_step": wall_e / args.steps, "timed": "host wall clock between barriers, max over ranks",
+                        "mode": ("every step's accumulated frame streamed to pinned host memory while later steps render (igb200_frame_stream_*), all K frames received inside the timed region"
+                                 if args.e2e_mode == "stream" else "render() + synchronous getFramebufferForHost every step")},
                 "per_rank_ms": {"columns": ["issued launches", "flush + drain of the deferred tail", "NCCL gather of the tiles", "total", "rays traced"], "ranks": per_rank},
                 "rays": tot, "msamples_per_s": w * h * spi * args.steps / (ms * 1e-3) / 1e6, "wall_ms_per_step": wall_ms / args.steps}
         step_bytes = algorithmic_bytes(tot)
@@ -404,8 +425,8 @@ def run_b200(args):
             total_k = sum(v["ms"] for v in kt.values()) or 1.0
             line["phase_ms"] = {k: {"ms_per_step": v["ms"] / args.steps, "share": v["ms"] / total_k,
                                     "algorithmic_GBps": phase_bytes[k] / max(v["ms"], 1e-9) / 1e6} for k, v in kt.items()}
-        if host is not None:
-            line["image_mean"] = float(np.asarray(host).mean() / args.steps)
+        if image_mean is not None:
+            line["image_mean"] = image_mean
         line["parity"] = parity
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
@@ -419,7 +440,12 @@ def run_b200(args):
                                 "sample": f"{n_it} full-frame iteration(s) of the same workload ({w}x{h}, spi {spi}; {rays} rays, {dt:.1f} s) on {cores} threads, "
                                           f"CPU restatement of the reference's CPU device built {flags}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        if world > 1:
+            # NCCL (with NCCL_DEBUG set) writes to fd 1 whenever it likes, also at exit: fd 1 stays pointed at stderr for the whole run
+            # and the ONE JSON line goes to the real stdout
+            os.write(saved_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     # tear down in dependency order: tensors that alias or were used on the device's stream go first, then the device
     # (which owns that stream), then NCCL; otherwise the allocator records events on a stream that no longer exists at exit
     torch.cuda.synchronize()
@@ -444,6 +470,7 @@ def main():
     ap.add_argument("--spi", type=int, default=0)
     ap.add_argument("--cpu-iters", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-mode", default="stream", choices=["stream", "sync"], help="end-to-end leg: streamed frames (default) or a synchronous read-back every step")
     ap.add_argument("--parity-iters", type=int, default=2, help="iterations of the parity check against the oracle (0: skip)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

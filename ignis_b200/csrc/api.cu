@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -82,6 +83,16 @@ __global__ void k_unpack_tiles(float* __restrict__ frame, const float* __restric
         const int r = (tx + ty) % world;
         const float* src = in + rank_offset[r] + ((long long)local_index[t] * tile * tile + (long long)(y % tile) * tile + x % tile) * 3;
         frame[p * 3] = src[0]; frame[p * 3 + 1] = src[1]; frame[p * 3 + 2] = src[2];
+    }
+}
+
+// Frame streaming: folds the finished iteration's slot into the accumulated frame, clears the slot for its next user and leaves a
+// snapshot of the frame for the copy engine (the accumulated frame itself is folded into again while that copy runs)
+__global__ void k_publish(float* __restrict__ acc, float* __restrict__ slot, float* __restrict__ snap, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float r = acc[i] + slot[i];
+        acc[i] = r; slot[i] = 0.0f;
+        if (snap) snap[i] = r;
     }
 }
 
@@ -203,6 +214,22 @@ struct igb200_ctx {
     std::vector<Timed> timed;
     double prof_ms[4] = {0, 0, 0, 0}; uint64_t prof_n[4] = {0, 0, 0, 0};
     DevBuf<igb200_ray> list_rays;
+    // frame streaming (igb200_frame_stream_*): per-iteration framebuffer slots + in-order publication of finished frames
+    bool fs_on = false;
+    int fs_slots = 0;                               // ring size (power of two)
+    DevBuf<float> fs_ring, fs_snap[2];
+    size_t fs_n4 = 0;                               // float4 per (padded) frame
+    struct FsIter { int iter; long long shades_left; };
+    std::deque<FsIter> fs_inflight;                 // iterations generated but not yet known to be finished, oldest first
+    struct FsFrame { int iter; int host; cudaEvent_t copied; };
+    std::deque<FsFrame> fs_ready;                   // published frames the caller has not taken yet, oldest first
+    std::vector<float*> fs_host;                    // pinned frames
+    std::vector<int> fs_host_free;
+    std::vector<cudaEvent_t> fs_events;             // pool of "copied" events
+    cudaEvent_t fs_ev_pub[2] = {nullptr, nullptr}, fs_ev_snapfree[2] = {nullptr, nullptr};
+    bool fs_snap_used[2] = {false, false};
+    long long fs_published = 0;
+    int fs_last_taken_host = -1;
     // multi-GPU exchange (igb200_comm_*)
     ncclComm_t comm = nullptr;
     DevBuf<float> comm_send, comm_recv, comm_frame;
@@ -272,10 +299,12 @@ static int configure_kernels(igb200_ctx* c) {
 static WaveParams make_params(igb200_ctx* c, const RenderParams& rp, const DevScene& sc, long long total, const igb200_ray* d_rays, int defer) {
     WaveParams P;
     P.sc = sc; P.rp = rp;
+    P.rp.ring_mask = 0; P.rp.ring_stride = 0;
+    if (c->fs_on && !d_rays) { P.rp.ring_mask = c->fs_slots - 1; P.rp.ring_stride = (long long)c->fb.n; }
     P.sc.full = (c->scene_full || rp.aov_normals != nullptr) ? 1 : 0;
     P.q[0] = c->qa.view(); P.q[1] = c->qb.view();
     P.sq = ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p};
-    P.fb = c->fb.p; P.ctl = c->control.p;
+    P.fb = P.rp.ring_stride ? c->fs_ring.p : c->fb.p; P.ctl = c->control.p;
     P.total = total; P.capacity = (int)c->capacity; P.list_rays = d_rays;
     P.stage_nodes = c->stage_nodes; P.stage_tris = c->stage_tris; P.stage_ent = c->stage_ent;
     P.refill = c->refill; P.defer = defer;
@@ -386,6 +415,7 @@ static int flush_queued(igb200_ctx* c) {
     return launch_iterations(c, &first, n, nullptr, 0);
 }
 
+extern "C" { static int fs_publish(igb200_ctx* c, bool all); }
 static int drain(igb200_ctx* c) {
     { const int r = flush_queued(c); if (r) return r; }
     if (c->maybe_carry) {
@@ -397,6 +427,8 @@ static int drain(igb200_ctx* c) {
         if (r) return r;
         c->maybe_carry = false;
     }
+    // frame streaming: with every path finished, every iteration still in flight is complete -> fold them all into the frame
+    if (c->fs_on && !c->fs_inflight.empty()) { CU(cudaSetDevice(c->device)); const int r = fs_publish(c, true); if (r) return r; }
     return 0;
 }
 
@@ -459,6 +491,9 @@ int igb200_destroy(igb200_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->fs_on) igb200_frame_stream_end(c);
+    for (cudaEvent_t e : c->fs_events) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k) { if (c->fs_ev_pub[k]) cudaEventDestroy(c->fs_ev_pub[k]); if (c->fs_ev_snapfree[k]) cudaEventDestroy(c->fs_ev_snapfree[k]); }
     igb200_comm_destroy(c);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_frame) cudaEventDestroy(c->ev_frame);
@@ -519,6 +554,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
 int igb200_set_partition(igb200_ctx* c, int rank, int world, int tile_size) {
     if (!c) return fail(-1, "null context");
     if (world < 1 || rank < 0 || rank >= world || tile_size < 1) return fail(-1, "igb200_set_partition: invalid rank %d / world %d / tile %d", rank, world, tile_size);
+    if (c->fs_on) return fail(-1, "igb200_set_partition: end the frame stream first (igb200_frame_stream_end)");
     { const int r = sync_control(c); if (r) return r; }
     c->rank = rank; c->world = world; c->tile = tile_size;
     return 0;
@@ -818,6 +854,7 @@ int igb200_resize(igb200_ctx* c, int width, int height) {
     if (width < 1 || height < 1) return fail(-1, "igb200_resize: invalid size %dx%d", width, height);
     CU(cudaSetDevice(c->device));
     if (width == c->width && height == c->height) return 0;
+    if (c->fs_on) return fail(-1, "igb200_resize: end the frame stream first (igb200_frame_stream_end)");
     { const int r = sync_control(c); if (r) return r; }
     c->width = width; c->height = height;
     std::memset(c->comm_key, 0, sizeof(c->comm_key));
@@ -1057,6 +1094,8 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
     // The iteration (asynchronously: nothing comes back to the host): its first, big turns as split launches, then one
     // cooperative launch of the persistent kernel that generates whatever camera rays did not fit yet and runs until at
     // most `defer` paths are alive.
+    // frame streaming: every iteration in flight owns a framebuffer slot; when the ring would overflow, everything is finished first
+    if (c->fs_on && !rays && (int)c->fs_inflight.size() + n_iter > c->fs_slots) { const int r = drain(c); if (r) return r; }
     CU(cudaMemsetAsync(&c->control.p->next_cam, 0, sizeof(long long), c->stream));
     // split turns pay three launches each: worth it while a turn holds millions of rays (4 at 8 M camera rays, 2 at 1 M)
     const int split_turns = c->split_turns >= 0 ? c->split_turns : (int)std::min<long long>(4, std::max<long long>(1, cam_rays >> 19));
@@ -1066,6 +1105,17 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
     c->carry_settings = *st; c->carry_settings.width = W; c->carry_settings.height = H; c->carry_settings.iter = st->iter + n_iter - 1;
     c->carry_rank = rp.rank; c->carry_world = rp.world; c->carry_tile = rp.tile_w;
     c->last_rp = rp; c->last_sc = sc;
+    if (c->fs_on && !rays) {
+        // Which iterations are finished now? Every launch shades the WHOLE primary queue at least (split turns + 1) times, a path is
+        // dead after max_depth shades (technique/pathtracer.art:68,177), and shadow rays never outlive the turn that made them: an
+        // iteration generated by an earlier launch is complete once the launches after it add up to max_depth shade passes. Exact, and
+        // known to the host without a read-back; the same on every rank.
+        const long long shades = (long long)split_turns + 1;
+        for (igb200_ctx::FsIter& f : c->fs_inflight) f.shades_left -= shades;
+        for (int k = 0; k < n_iter; ++k) c->fs_inflight.push_back(igb200_ctx::FsIter{st->iter + k, (long long)std::max(c->dev.max_depth, 1)});
+        if (defer == 0) for (igb200_ctx::FsIter& f : c->fs_inflight) f.shades_left = 0;   // the launch ran every path to its end
+        { const int r = fs_publish(c, false); if (r) return r; }
+    }
     if (rays) { const int r = sync_control(c); if (r) return r; }   // the caller may free `rays` after the call
     return 0;
 }
@@ -1226,6 +1276,54 @@ int igb200_comm_destroy(igb200_ctx* c) {
     return 0;
 }
 
+// Tables and buffers of the exchange for the current frame size
+static int comm_prepare(igb200_ctx* c) {
+    const int W = c->width, H = c->height, tile = c->tile, world = c->world, rank = c->rank;
+    const int tiles_x = (W + tile - 1) / tile, tiles_y = (H + tile - 1) / tile;
+    const long long per_tile = (long long)tile * tile * 3;
+    const long long key[4] = {W, H, tile, world};
+    if (std::memcmp(key, c->comm_key, sizeof(key)) != 0) {
+        std::vector<long long> n_tiles(world, 0), offs(world, 0);
+        std::vector<int> local_index((size_t)tiles_x * tiles_y);
+        for (int t = 0; t < tiles_x * tiles_y; ++t) { const int r = (t % tiles_x + t / tiles_x) % world; local_index[t] = (int)n_tiles[r]++; }
+        long long total = 0;
+        for (int r = 0; r < world; ++r) { offs[r] = total; total += n_tiles[r] * per_tile; }
+        c->comm_counts.assign(world, 0);
+        for (int r = 0; r < world; ++r) c->comm_counts[r] = n_tiles[r] * per_tile;
+        CU(cudaStreamSynchronize(c->stream));
+        CU(c->comm_send.alloc((size_t)c->comm_counts[rank]));
+        if (rank == 0) {
+            CU(c->comm_recv.alloc((size_t)total));
+            CU(c->comm_frame.alloc((size_t)W * H * 3));
+            CU(c->comm_local_index.upload(local_index));
+            CU(c->comm_rank_offset.upload(offs));
+        }
+        std::memcpy(c->comm_key, key, sizeof(key));
+    }
+    return ensure_tile_table(c, W, H);
+}
+// The exchange itself, asynchronous on the context's stream: the tiles this rank owns out of `src` -> rank 0, which assembles `frame`
+static int comm_gather_async(igb200_ctx* c, const float* src, float* frame) {
+    { const int r = comm_prepare(c); if (r) return r; }
+    const int W = c->width, H = c->height, tile = c->tile, world = c->world, rank = c->rank;
+    const int tiles_x = (W + tile - 1) / tile;
+    const int grid = c->n_sm * 8;
+    std::vector<long long> offs(world, 0);
+    { long long t = 0; for (int r = 0; r < world; ++r) { offs[r] = t; t += c->comm_counts[r]; } }
+    if (world == 1) { CU(cudaMemcpyAsync(frame, src, (size_t)W * H * 3 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream)); return 0; }
+    // rank 0 packs straight into its region of the receive buffer; the others into their send buffer
+    float* pack_to = rank == 0 ? c->comm_recv.p + offs[0] : c->comm_send.p;
+    k_pack_tiles<<<grid, 256, 0, c->stream>>>(src, pack_to, c->tile_table.p, (int)c->n_local_tiles, tile, tiles_x, W, H);
+    NC(g_nccl.GroupStart());
+    if (rank == 0) { for (int r = 1; r < world; ++r) NC(g_nccl.Recv(c->comm_recv.p + offs[r], (size_t)c->comm_counts[r], ncclFloat32, r, c->comm, c->stream)); }
+    else NC(g_nccl.Send(c->comm_send.p, (size_t)c->comm_counts[rank], ncclFloat32, 0, c->comm, c->stream));
+    NC(g_nccl.GroupEnd());
+    if (rank == 0) k_unpack_tiles<<<grid, 256, 0, c->stream>>>(frame, c->comm_recv.p, c->comm_local_index.p, c->comm_rank_offset.p, world, tile, tiles_x, W, H);
+    CU(cudaGetLastError());
+    c->pending = true;
+    return 0;
+}
+
 int igb200_comm_gather_framebuffer(igb200_ctx* c, const char* aov, float** device_frame, float** host_frame) {
     if (!c) return fail(-1, "null context");
     if (!c->comm) return fail(-1, "igb200_comm_gather_framebuffer: no communicator (igb200_comm_init)");
@@ -1235,55 +1333,16 @@ int igb200_comm_gather_framebuffer(igb200_ctx* c, const char* aov, float** devic
     if (!c->fb.p) return fail(-1, "igb200_comm_gather_framebuffer: no framebuffer");
     CU(cudaSetDevice(c->device));
     { const int r = drain(c); if (r) return r; }   // asynchronous: the exchange below is ordered behind it on the stream
-    const int W = c->width, H = c->height, tile = c->tile, world = c->world, rank = c->rank;
-    const int tiles_x = (W + tile - 1) / tile, tiles_y = (H + tile - 1) / tile;
-    const long long per_tile = (long long)tile * tile * 3;
-    {   // per-rank tile counts, and on rank 0 the tables the unpack kernel needs
-        const long long key[4] = {W, H, tile, world};
-        if (std::memcmp(key, c->comm_key, sizeof(key)) != 0) {
-            std::vector<long long> n_tiles(world, 0), offs(world, 0);
-            std::vector<int> local_index((size_t)tiles_x * tiles_y);
-            for (int t = 0; t < tiles_x * tiles_y; ++t) { const int r = (t % tiles_x + t / tiles_x) % world; local_index[t] = (int)n_tiles[r]++; }
-            long long total = 0;
-            for (int r = 0; r < world; ++r) { offs[r] = total; total += n_tiles[r] * per_tile; }
-            c->comm_counts.assign(world, 0);
-            for (int r = 0; r < world; ++r) c->comm_counts[r] = n_tiles[r] * per_tile;
-            CU(cudaStreamSynchronize(c->stream));
-            CU(c->comm_send.alloc((size_t)c->comm_counts[rank]));
-            if (rank == 0) {
-                CU(c->comm_recv.alloc((size_t)total));
-                CU(c->comm_frame.alloc((size_t)W * H * 3));
-                CU(c->comm_local_index.upload(local_index));
-                CU(c->comm_rank_offset.upload(offs));
-            }
-            std::memcpy(c->comm_key, key, sizeof(key));
-        }
-        { const int r = ensure_tile_table(c, W, H); if (r) return r; }
-    }
     const float* src = which == 0 ? c->fb.p : c->aov[which - 1].p;
     if (!src) return fail(-1, "igb200_comm_gather_framebuffer: AOV '%s' is not allocated", aov);
-    const int grid = c->n_sm * 8;
-    std::vector<long long> offs(world, 0);
-    { long long t = 0; for (int r = 0; r < world; ++r) { offs[r] = t; t += c->comm_counts[r]; } }
-    // rank 0 packs straight into its region of the receive buffer; the others into their send buffer
-    float* pack_to = rank == 0 ? c->comm_recv.p + offs[0] : c->comm_send.p;
-    if (world > 1) k_pack_tiles<<<grid, 256, 0, c->stream>>>(src, pack_to, c->tile_table.p, (int)c->n_local_tiles, tile, tiles_x, W, H);
-    if (world > 1) {
-        NC(g_nccl.GroupStart());
-        if (rank == 0) { for (int r = 1; r < world; ++r) NC(g_nccl.Recv(c->comm_recv.p + offs[r], (size_t)c->comm_counts[r], ncclFloat32, r, c->comm, c->stream)); }
-        else NC(g_nccl.Send(c->comm_send.p, (size_t)c->comm_counts[rank], ncclFloat32, 0, c->comm, c->stream));
-        NC(g_nccl.GroupEnd());
-    }
-    c->pending = true;
+    { const int r = comm_prepare(c); if (r) return r; }
+    { const int r = comm_gather_async(c, src, c->comm_frame.p); if (r) return r; }
     if (device_frame) *device_frame = nullptr;
-    if (host_frame && rank != 0) *host_frame = nullptr;
-    if (rank != 0) { CU(cudaGetLastError()); return 0; }
-    if (world > 1) k_unpack_tiles<<<grid, 256, 0, c->stream>>>(c->comm_frame.p, c->comm_recv.p, c->comm_local_index.p, c->comm_rank_offset.p, world, tile, tiles_x, W, H);
-    else CU(cudaMemcpyAsync(c->comm_frame.p, src, (size_t)W * H * 3 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaGetLastError());
+    if (host_frame) *host_frame = nullptr;
+    if (c->rank != 0) return 0;
     if (device_frame) *device_frame = c->comm_frame.p;
     if (host_frame) {
-        const size_t n = (size_t)W * H * 3;
+        const size_t n = (size_t)c->width * c->height * 3;
         if (c->comm_host_n != n) {
             if (c->comm_host) { cudaFreeHost(c->comm_host); c->comm_host = nullptr; }
             CU(cudaMallocHost(&c->comm_host, n * sizeof(float)));
@@ -1294,6 +1353,112 @@ int igb200_comm_gather_framebuffer(igb200_ctx* c, const char* aov, float** devic
         *host_frame = c->comm_host;
     }
     return 0;
+}
+
+// ---- frame streaming -----------------------------------------------------------------------------------------------------------
+static int fs_host_buffer(igb200_ctx* c, int* out) {
+    if (!c->fs_host_free.empty()) { *out = c->fs_host_free.back(); c->fs_host_free.pop_back(); return 0; }
+    float* p = nullptr;
+    CU(cudaMallocHost(&p, c->fb.n * sizeof(float)));
+    c->fs_host.push_back(p);
+    *out = (int)c->fs_host.size() - 1;
+    return 0;
+}
+// Publishes finished iterations in order (all of them when `all`: the caller has just finished every path). Asynchronous.
+static int fs_publish(igb200_ctx* c, bool all) {
+    const size_t n = c->fb.n;
+    const bool root = c->rank == 0;
+    while (!c->fs_inflight.empty() && (all || c->fs_inflight.front().shades_left <= 0)) {
+        const igb200_ctx::FsIter f = c->fs_inflight.front();
+        c->fs_inflight.pop_front();
+        const int p = (int)(c->fs_published & 1);
+        float* slot = c->fs_ring.p + (size_t)(f.iter & (c->fs_slots - 1)) * n;
+        float* snap = nullptr;
+        if (root) {
+            // the snapshot the copy engine reads must not be overwritten before its previous copy is through
+            if (c->fs_snap_used[p]) CU(cudaStreamWaitEvent(c->stream, c->fs_ev_snapfree[p], 0));
+            snap = c->fs_snap[p].p;
+        }
+        const bool gather = c->comm != nullptr && c->world > 1;
+        k_publish<<<c->n_sm * 4, 256, 0, c->stream>>>(c->fb.p, slot, gather ? nullptr : snap, (long long)n);
+        if (gather) { const int r = comm_gather_async(c, c->fb.p, snap); if (r) return r; }   // every rank's tiles of the frame -> rank 0's snapshot
+        CU(cudaGetLastError());
+        c->fs_published++;
+        c->pending = true;
+        if (!root) continue;
+        CU(cudaEventRecord(c->fs_ev_pub[p], c->stream));
+        int h = -1;
+        { const int r = fs_host_buffer(c, &h); if (r) return r; }
+        CU(cudaStreamWaitEvent(c->copy_stream, c->fs_ev_pub[p], 0));
+        CU(cudaMemcpyAsync(c->fs_host[h], snap, n * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(cudaEventRecord(c->fs_ev_snapfree[p], c->copy_stream));
+        c->fs_snap_used[p] = true;
+        cudaEvent_t e;
+        if (!c->fs_events.empty()) { e = c->fs_events.back(); c->fs_events.pop_back(); } else CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaEventRecord(e, c->copy_stream));
+        c->fs_ready.push_back(igb200_ctx::FsFrame{f.iter, h, e});
+    }
+    return 0;
+}
+
+int igb200_frame_stream_begin(igb200_ctx* c, int slots) {
+    if (!c) return fail(-1, "null context");
+    if (c->fs_on) return fail(-1, "igb200_frame_stream_begin: already streaming");
+    if (!c->fb.p) return fail(-1, "igb200_frame_stream_begin: no framebuffer (call igb200_resize first)");
+    if ((long long)c->width * c->height >= (1ll << 24)) return fail(-4, "igb200_frame_stream_begin: frames of 2^24 pixels and more are not supported (the slot rides in the shadow ray's pixel word)");
+    if (slots <= 0) slots = 16;
+    int R = 2; while (R < slots) R <<= 1;
+    if (R > 128) return fail(-1, "igb200_frame_stream_begin: at most 128 slots");
+    { const int r = sync_control(c); if (r) return r; }   // nothing in flight when the framebuffer layout changes
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->fb.n;
+    CU(c->fs_ring.alloc((size_t)R * n));
+    CU(cudaMemset(c->fs_ring.p, 0, (size_t)R * n * sizeof(float)));
+    if (c->rank == 0) for (int k = 0; k < 2; ++k) {
+        CU(c->fs_snap[k].alloc(n));
+        if (!c->fs_ev_pub[k]) { CU(cudaEventCreateWithFlags(&c->fs_ev_pub[k], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->fs_ev_snapfree[k], cudaEventDisableTiming)); }
+        c->fs_snap_used[k] = false;
+    }
+    c->fs_slots = R; c->fs_on = true; c->fs_published = 0; c->fs_last_taken_host = -1;
+    return 0;
+}
+
+// Releases the ring; frames not taken yet are dropped. The accumulated framebuffer keeps everything that was rendered.
+int igb200_frame_stream_end(igb200_ctx* c) {
+    if (!c) return fail(-1, "null context");
+    if (!c->fs_on) return 0;
+    { const int r = sync_control(c); if (r) return r; }
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    for (const igb200_ctx::FsFrame& f : c->fs_ready) c->fs_events.push_back(f.copied);
+    c->fs_ready.clear(); c->fs_inflight.clear();
+    for (float* p : c->fs_host) cudaFreeHost(p);
+    c->fs_host.clear(); c->fs_host_free.clear();
+    c->fs_ring.release(); c->fs_snap[0].release(); c->fs_snap[1].release();
+    c->fs_on = false; c->fs_slots = 0;
+    return 0;
+}
+
+int igb200_frame_stream_next(igb200_ctx* c, int wait, int* iteration, float** host_rgb) {
+    if (!c || !iteration || !host_rgb) return fail(-1, "igb200_frame_stream_next: null argument");
+    if (!c->fs_on) return fail(-1, "igb200_frame_stream_next: not streaming (igb200_frame_stream_begin)");
+    *host_rgb = nullptr; *iteration = -1;
+    CU(cudaSetDevice(c->device));
+    if (c->fs_last_taken_host >= 0) { c->fs_host_free.push_back(c->fs_last_taken_host); c->fs_last_taken_host = -1; }   // the previous frame's buffer is the caller's no longer
+    if (wait >= 2) { const int r = drain(c); if (r) return r; }   // finish everything that was rendered: every frame becomes ready
+    else { const int r = flush_queued(c); if (r) return r; }
+    if (c->rank != 0 || c->fs_ready.empty()) return 0;
+    const igb200_ctx::FsFrame f = c->fs_ready.front();
+    if (wait == 0) {
+        const cudaError_t q = cudaEventQuery(f.copied);
+        if (q == cudaErrorNotReady) return 0;
+        CU(q);
+    } else CU(cudaEventSynchronize(f.copied));
+    c->fs_ready.pop_front();
+    c->fs_events.push_back(f.copied);
+    c->fs_last_taken_host = f.host;
+    *iteration = f.iter; *host_rgb = c->fs_host[f.host];
+    return 1;
 }
 
 int igb200_test_detmath(igb200_ctx* c, int fn, const float* a, const float* b, float* out, size_t n) {

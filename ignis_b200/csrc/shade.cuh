@@ -458,6 +458,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
     const float eta = __uint_as_float(st.w);
     const C3 contrib = c3(pc.x, pc.y, pc.z);
     const float inv_pdf = pc.w;
+    fb += (size_t)(iter & rp.ring_mask) * (size_t)rp.ring_stride;   // frame streaming: the slot of the iteration that generated the path
     const int n_lights = sc.n_inf + sc.n_fin;
     const float pdf_lights = n_lights == 0 ? 1.0f : 1 / (float)n_lights;          // light_selector.art:26-29
     const bool nee = sc.nee != 0;
@@ -620,7 +621,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
                     const int ss = coalesced_append(sink.shadow_count);
                     sink.sq.org_tmin[ss] = make_float4(surf.point.x, surf.point.y, surf.point.z, 0.001f);
                     sink.sq.dir_tmax[ss] = make_float4(s_dir.x, s_dir.y, s_dir.z, s_tmax);
-                    sink.sq.color_pix[ss] = make_float4(cc.r, cc.g, cc.b, __int_as_float(pixel));
+                    sink.sq.color_pix[ss] = make_float4(cc.r, cc.g, cc.b, __int_as_float(pixel | ((iter & rp.ring_mask) << 24)));   // ring_mask != 0 only if W * H < 2^24
                 }
             }
         }

@@ -46,6 +46,9 @@ struct RenderParams {
     const int* tile_table;   // multi-GPU: row-major index of the rank's k-th tile (api.cu launch_iterations); null = all tiles
     float* aov_normals; float* aov_albedo;   // standard AOVs (technique/internal/infobuffer.art): written by camera-ray hits of iteration 0; null = off
     long long per_iter;   // camera-ray domain of ONE iteration; a launch may generate several consecutive iterations (api.cu: fused iterations)
+    // Frame streaming (api.cu igb200_frame_stream_*): every iteration splats into its own slot `iter & ring_mask` of a ring of framebuffers
+    // (ring_stride floats apart), so that a frame can be handed out while later iterations are already in flight. 0 / 0: one framebuffer.
+    int ring_mask; long long ring_stride;
 };
 
 struct PrimaryQueue {

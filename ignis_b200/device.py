@@ -70,7 +70,8 @@ SYMBOLS = ["igb200_last_error", "igb200_version", "igb200_create", "igb200_destr
            "igb200_set_partition", "igb200_render", "igb200_sync", "igb200_framebuffer", "igb200_framebuffer_device", "igb200_clear",
            "igb200_upload_framebuffer", "igb200_stats", "igb200_reset_stats", "igb200_kernel_times", "igb200_launch_profile", "igb200_turn_log", "igb200_step_stats", "igb200_set_option",
            "igb200_stream", "igb200_trace_closest", "igb200_trace_any", "igb200_bench_trace", "igb200_test_detmath",
-           "igb200_comm_unique_id", "igb200_comm_init", "igb200_comm_gather_framebuffer", "igb200_comm_destroy"]
+           "igb200_comm_unique_id", "igb200_comm_init", "igb200_comm_gather_framebuffer", "igb200_comm_destroy",
+           "igb200_frame_stream_begin", "igb200_frame_stream_next", "igb200_frame_stream_end"]
 
 
 def library_path() -> str:
@@ -118,6 +119,9 @@ def lib():
         L.igb200_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
         L.igb200_comm_gather_framebuffer.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.POINTER(C.c_float))]
         L.igb200_comm_destroy.argtypes = [vp]
+        L.igb200_frame_stream_begin.argtypes = [vp, C.c_int]
+        L.igb200_frame_stream_next.argtypes = [vp, C.c_int, ip, C.POINTER(C.POINTER(C.c_float))]
+        L.igb200_frame_stream_end.argtypes = [vp]
         _LIB = L
     return _LIB
 
@@ -274,6 +278,23 @@ class B200Device:
         if not dp.value:
             return None, None
         return int(dp.value), (np.ctypeslib.as_array(hp, shape=(self._h_, self._w, 3)) if to_host else None)
+
+    # -- frame streaming (include/igb200.h igb200_frame_stream_*)
+    def frameStreamBegin(self, slots: int = 0):
+        _check(lib().igb200_frame_stream_begin(self._h, slots))
+
+    def frameStreamNext(self, wait: int = 0):
+        """(iteration, frame) of the next finished iteration -- a borrowed (H, W, 3) view valid until the next call -- or None."""
+        it, p = C.c_int(), C.POINTER(C.c_float)()
+        rc = lib().igb200_frame_stream_next(self._h, wait, C.byref(it), C.byref(p))
+        if rc < 0:
+            _check(rc)
+        if rc == 0:
+            return None
+        return it.value, np.ctypeslib.as_array(p, shape=(self._h_, self._w, 3))
+
+    def frameStreamEnd(self):
+        _check(lib().igb200_frame_stream_end(self._h))
 
     def setOption(self, name: str, value: int):
         _check(lib().igb200_set_option(self._h, name.encode(), int(value)))

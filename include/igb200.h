@@ -239,6 +239,21 @@ int igb200_comm_init(igb200_ctx* ctx, int rank, int world, int tile_size, const 
 int igb200_comm_gather_framebuffer(igb200_ctx* ctx, const char* aov, float** device_frame, float** host_frame);
 int igb200_comm_destroy(igb200_ctx* ctx);
 
+/* ---- frame streaming: every iteration's accumulated frame delivered to the host while later iterations render ---------------------------
+ * igb200_framebuffer is synchronous, as IRenderDevice::getFramebufferForHost is: it finishes the deepest paths of the last iteration (a
+ * latency-bound tail of ~50 tiny wavefront turns) and copies 12 bytes per pixel while the GPU idles. A caller that wants EVERY iteration's
+ * frame (a progressive viewer, a denoiser feeding on intermediate frames, bench.py's end-to-end leg) streams them instead:
+ * after igb200_frame_stream_begin each iteration accumulates into its own slot of a ring of framebuffers; once an iteration is known to be
+ * finished (from the launches issued since -- no read-back) its slot is folded into the accumulated frame, in order, and a snapshot of the
+ * frame travels to pinned host memory on a copy stream (with a communicator: after the tile gather, on rank 0) while the next iterations
+ * render. igb200_frame_stream_next hands the frames out in iteration order: frame k = the sum of iterations 0..k, exactly what
+ * igb200_framebuffer would have returned after render(k). wait: 0 = only if one is ready, 1 = block until the oldest outstanding frame
+ * arrives (returns 0 if none is outstanding), 2 = first finish everything rendered so far, then as 1. Returns 1 with a frame (valid until the
+ * next call), 0 without. Frames exist on rank 0 only; the other ranks call it all the same (the gather is collective) and get 0. */
+int igb200_frame_stream_begin(igb200_ctx* ctx, int slots /* iterations in flight, rounded up to a power of two; 0 = 16 */);
+int igb200_frame_stream_next(igb200_ctx* ctx, int wait, int* iteration, float** host_rgb);
+int igb200_frame_stream_end(igb200_ctx* ctx);
+
 /* One iteration: IRenderDevice::render, Device.cpp:1672-1682. `rays` non-null selects the list emitter of igtrace
  * (Runtime::trace, Runtime.cpp:389-446): width = n_rays, height = 1. Accumulates into the device framebuffer.
  * The call is ASYNCHRONOUS on the context's stream (the reference's GPU device ends every iteration with acc.sync(),

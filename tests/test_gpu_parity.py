@@ -355,6 +355,52 @@ def test_deferred_tail_is_invisible():
     assert rel_l2(out[4000][0], ref) <= REL_L2_TOL
 
 
+@pytest.mark.parametrize("scene,w,h,spi,iters,opts", [
+    ("diamond_scene.json", 320, 180, 4, 24, {}),                                  # max_depth 64: a frame is finished ~13 launches after its render
+    ("diamond_scene.json", 200, 120, 2, 20, {"split_turns": 0, "defer_permille": 50}),
+    ("diamond_scene.json", 200, 120, 2, 20, {"fuse": 4}),                         # several iterations per launch (a rank's share at N GPUs)
+    ("many_point_lights.json", 160, 160, 1, 10, {}),
+    ("evaluation/cbox-d6.json", 128, 128, 2, 12, {}),                              # max_depth 6: finished after two launches
+])
+def test_streamed_frames_are_the_synchronous_frames(scene, w, h, spi, iters, opts):
+    """igb200_frame_stream_*: frame k handed out while later iterations render == the oracle's sum of iterations 0..k == what the
+    synchronous igb200_framebuffer returns after render(k); frames arrive in order, each exactly once, none before it is complete."""
+    t = load_scene(scene_path(scene))
+    o = Oracle(t)
+    ref = np.zeros((h, w, 3), np.float32)
+    refs = []
+    for it in range(iters):
+        o.render(w, h, spi=spi, iteration=it, fb=ref)
+        refs.append(ref.copy())
+    got = {}
+    with Runtime(t, w, h, spi=spi) as rt:
+        for k, v in opts.items():
+            rt.device.setOption(k, v)
+        rt.device.frameStreamBegin()
+        early = 0
+        for it in range(iters):
+            rt.step()
+            while (f := rt.device.frameStreamNext(0)) is not None:
+                got[f[0]] = f[1].copy()
+                early += 1
+        while (f := rt.device.frameStreamNext(2)) is not None:
+            got[f[0]] = f[1].copy()
+        final = rt.device.getFramebufferForHost().copy()          # the synchronous call still works and sees everything
+        st = rt.device.getStatistics()
+        rt.device.frameStreamEnd()
+        rt.step()                                                  # ... and the device renders normally afterwards
+        after = rt.device.getFramebufferForHost().copy()
+    assert sorted(got) == list(range(iters))
+    for it in range(iters):
+        assert rel_l2(got[it], refs[it]) <= REL_L2_TOL, it
+    assert rel_l2(final, refs[-1]) <= REL_L2_TOL
+    assert (st["CameraRayCount"], st["ShadowRayCount"], st["BounceRayCount"]) == tuple(int(x) for x in o.counters)
+    o.render(w, h, spi=spi, iteration=iters, fb=ref)
+    assert rel_l2(after, ref) <= REL_L2_TOL
+    if t.technique["max_depth"] <= 8 and iters >= 8:
+        assert early >= iters // 2                                 # shallow paths: frames really do arrive while rendering goes on
+
+
 def test_white_furnace_through_glass_on_gpu():
     """Energy conservation of the whole device pipeline on delta paths (tests/test_oracle_kat.py has the oracle's)."""
     t = load_scene(furnace_scene())
