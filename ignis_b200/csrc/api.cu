@@ -1420,6 +1420,13 @@ int igb200_frame_stream_begin(igb200_ctx* c, int slots) {
         c->fs_snap_used[k] = false;
     }
     c->fs_slots = R; c->fs_on = true; c->fs_published = 0; c->fs_last_taken_host = -1;
+    // pinned frames for everything that can be outstanding at once (a drain publishes every iteration in flight in one go); pinning
+    // memory costs milliseconds per frame, so it happens here and not inside a render
+    if (c->rank == 0) {
+        std::vector<int> hs((size_t)R + 2);
+        for (int& h : hs) { const int r = fs_host_buffer(c, &h); if (r) return r; }
+        for (int h : hs) c->fs_host_free.push_back(h);
+    }
     return 0;
 }
 
