@@ -20,6 +20,32 @@ def _n_gpus():
         return 0
 
 
+def _rank_stream(rank, world, conn, scene, w, h, spi, iters, fuse):
+    """Frame streaming across ranks: every iteration's gathered frame arrives on rank 0, in order, while later iterations render."""
+    sys.path.insert(0, ROOT)
+    from ignis_b200.device import Runtime
+    from ignis_b200.scene import load_scene
+    try:
+        uid = conn.recv()
+        t = load_scene(os.path.join(ROOT, "scenes", scene))
+        with Runtime(t, w, h, spi=spi, cuda_device=rank) as rt:
+            rt.device.commInit(rank, world, uid, 32)
+            rt.device.setOption("fuse", fuse)
+            rt.device.frameStreamBegin(32)
+            out = {}
+            for it in range(iters):
+                rt.step()
+                while (f := rt.device.frameStreamNext(0)) is not None:
+                    out[f[0]] = f[1].copy()
+            while (f := rt.device.frameStreamNext(2)) is not None:
+                out[f[0]] = f[1].copy()
+            st = rt.device.getStatistics()
+            rt.device.frameStreamEnd()
+        conn.send(("ok", [out[k] for k in sorted(out)] if rank == 0 else [], (st["CameraRayCount"], st["ShadowRayCount"], st["BounceRayCount"])))
+    except Exception as e:   # noqa: BLE001
+        conn.send(("error", repr(e), None))
+
+
 def _rank_main(rank, world, conn, scene, w, h, spi, iters, gather_without_sync):
     sys.path.insert(0, ROOT)
     from ignis_b200.device import B200Device, Runtime
@@ -43,13 +69,13 @@ def _rank_main(rank, world, conn, scene, w, h, spi, iters, gather_without_sync):
         conn.send(("error", repr(e), None))
 
 
-def _run(world, scene, w, h, spi, iters, gather_without_sync=True):
+def _run(world, scene, w, h, spi, iters, gather_without_sync=True, target=None, extra=None):
     from ignis_b200.device import B200Device
     ctx = mp.get_context("spawn")
     pipes, procs = [], []
     for r in range(world):
         a, b = ctx.Pipe()
-        p = ctx.Process(target=_rank_main, args=(r, world, b, scene, w, h, spi, iters, gather_without_sync))
+        p = ctx.Process(target=target or _rank_main, args=(r, world, b, scene, w, h, spi, iters, gather_without_sync if extra is None else extra))
         p.start()
         pipes.append(a)
         procs.append(p)
@@ -83,5 +109,25 @@ def test_gathered_frame_equals_oracle(world, scene, w, h, spi):
         o.render(w, h, spi=spi, iteration=it, fb=ref)
         err = float(np.linalg.norm((frames[it] - ref).ravel()) / np.linalg.norm(ref.ravel()))
         assert err <= 1e-4, (it, err)            # every gathered frame, taken right behind an asynchronous render
+    counts = np.sum([r[2] for r in res], axis=0)
+    assert tuple(int(x) for x in counts) == tuple(int(x) for x in o.counters)
+
+
+@pytest.mark.parametrize("world,fuse", [(2, 1), (2, 4), (8, 8)])
+def test_streamed_gathered_frames_equal_oracle(world, fuse):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from ignis_b200.scene import load_scene
+    from oracle.oracle import Oracle
+    scene, w, h, spi, iters = "diamond_scene.json", 480, 270, 4, 18
+    res = _run(world, scene, w, h, spi, iters, target=_rank_stream, extra=fuse)
+    frames = res[0][1]
+    assert len(frames) == iters
+    o = Oracle(load_scene(os.path.join(ROOT, "scenes", scene)))
+    ref = np.zeros((h, w, 3), np.float32)
+    for it in range(iters):
+        o.render(w, h, spi=spi, iteration=it, fb=ref)
+        err = float(np.linalg.norm((frames[it] - ref).ravel()) / np.linalg.norm(ref.ravel()))
+        assert err <= 1e-4, (it, err)
     counts = np.sum([r[2] for r in res], axis=0)
     assert tuple(int(x) for x in counts) == tuple(int(x) for x in o.counters)
