@@ -169,6 +169,9 @@ struct igb200_ctx {
     size_t capacity = 0, want_capacity = (size_t)1 << 25;   // upper bound of records per queue (84 B each, two queues + 48 B shadow)
     QueueMem qa, qb;
     DevBuf<float4> sq_org, sq_dir, sq_col;
+    DevBuf<int> bin_order;             // material binning: SHADE_BINS index lists of `capacity` entries
+    int bin_materials = -1;            // option: 1 on, 0 off, -1 = on when the scene has a heavy material class (textures, maps, rough conductors)
+    bool scene_heavy = false;
     DevBuf<Control> control;
     Control* host_control = nullptr;   // pinned
     // persistent-kernel configuration
@@ -246,6 +249,7 @@ static int ensure_queues(igb200_ctx* c, size_t need) {
     if (cap <= c->capacity) return 0;
     CU(c->qa.alloc(cap)); CU(c->qb.alloc(cap));
     CU(c->sq_org.alloc(cap)); CU(c->sq_dir.alloc(cap)); CU(c->sq_col.alloc(cap));
+    c->bin_order.release();
     c->capacity = cap;
     return 0;
 }
@@ -308,6 +312,7 @@ static WaveParams make_params(igb200_ctx* c, const RenderParams& rp, const DevSc
     P.total = total; P.capacity = (int)c->capacity; P.list_rays = d_rays;
     P.stage_nodes = c->stage_nodes; P.stage_tris = c->stage_tris; P.stage_ent = c->stage_ent;
     P.refill = c->refill; P.defer = defer;
+    P.order = c->bin_order.p;
     P.wide_limit = (int)std::min<int64_t>(c->wide_rays_per_group * c->blocks_per_sm * c->n_sm * (WF_BLOCK / 8), (int64_t)1 << 30);
     return P;
 }
@@ -518,6 +523,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "profile_kernels")) { c->profile = value != 0; return 0; }
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
     if (!strcmp(name, "std_aovs")) { c->std_aovs = value != 0; CU(cudaSetDevice(c->device)); return ensure_aovs(c); }
+    if (!strcmp(name, "bin_materials")) { if (value < -1 || value > 2) return fail(-1, "bin_materials must be -1 (automatic), 0, 1 or 2"); c->bin_materials = (int)value; return 0; }
     if (!strcmp(name, "fuse")) { if (value < 0 || value > 64) return fail(-1, "fuse must be in [0, 64]"); c->fuse = (int)value; return 0; }
     if (!strcmp(name, "split_turns")) { if (value < -1 || value > 64) return fail(-1, "split_turns must be in [-1, 64] (-1: chosen from the number of camera rays)"); c->split_turns = (int)value; return 0; }
     if (!strcmp(name, "turn_shade_blocks")) {
@@ -784,7 +790,12 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
         E[2] = make_float4(g[2], g[5], g[8], g[11]);
         E[3] = make_float4(nm[0], nm[3], nm[6], as_f(shape_id));
         E[4] = make_float4(nm[1], nm[4], nm[7], as_f(mat_id));
-        E[5] = make_float4(nm[2], nm[5], nm[8], 0);
+        // shade bin of the entity's material (wavefront.cuh bin_append): 0 plain, 1 heavy (textured parameters, bump / normal map, rough conductor)
+        const igb200_material& mt = d->materials[mat_id];
+        const bool heavy = mt.tex[0] >= 0 || mt.tex[1] >= 0 || mt.map_kind != IGB200_MAP_NONE ||
+                           (mt.bsdf == IGB200_BSDF_CONDUCTOR && mt.distribution == IGB200_MICROFACET_VNDF_GGX && mt.alpha_u > 1e-4f && mt.alpha_v > 1e-4f);
+        // (experiment "bin_materials" = 2: when no material is heavy, split delta BSDFs -- no next-event estimation -- from the others)
+        E[5] = make_float4(nm[2], nm[5], nm[8], as_f((heavy || (c->bin_materials == 2 && mt.bsdf != IGB200_BSDF_DIFFUSE)) ? 1 : 0));
     }
     std::vector<float4> node_f4(nodes.size() * 16);
     if (!nodes.empty()) std::memcpy(node_f4.data(), nodes.data(), nodes.size() * sizeof(Node8));
@@ -840,6 +851,8 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     for (int l = 0; l < d->n_finite; ++l) c->scene_full |= d->finite_lights[l].type == IGB200_LIGHT_SPHERE_AREA || d->finite_lights[l].type == IGB200_LIGHT_SPOT;
     for (int l = 0; l < d->n_infinite; ++l) c->scene_full |= d->infinite_lights[l].type != IGB200_LIGHT_ENV_CONST;
     s.full = c->scene_full ? 1 : 0;
+    c->scene_heavy = false;
+    for (int e = 0; e < d->n_entities; ++e) c->scene_heavy |= __builtin_bit_cast(int, ent_shade[6 * (size_t)e + 5].w) != 0;
     s.max_depth = d->technique.max_depth; s.min_depth = d->technique.min_depth; s.clamp_value = d->technique.clamp; s.nee = d->technique.nee;
     c->desc = *d;
     c->desc.entities = nullptr; c->desc.shape_lookups = nullptr; c->desc.shape_data = nullptr; c->desc.leaves = nullptr;
@@ -1090,6 +1103,11 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
         { const int r = ensure_queues(c, need); if (r) return r; }
     }
     const int defer = (int)std::min<long long>(want_defer, (long long)c->capacity - 1024);
+    {   // material binning (a9): on by default when shading cost differs between material classes
+        const bool want_bins = !rays && (c->bin_materials >= 1 || (c->bin_materials < 0 && c->scene_heavy));
+        if (want_bins && !c->bin_order.p) { { const int r = sync_control(c); if (r) return r; } CU(c->bin_order.alloc((size_t)SHADE_BINS * c->capacity)); }
+        if (!want_bins && c->bin_order.p) { { const int r = sync_control(c); if (r) return r; } c->bin_order.release(); }
+    }
 
     // The iteration (asynchronously: nothing comes back to the host): its first, big turns as split launches, then one
     // cooperative launch of the persistent kernel that generates whatever camera rays did not fit yet and runs until at

@@ -399,6 +399,34 @@ def test_streamed_frames_are_the_synchronous_frames(scene, w, h, spi, iters, opt
     assert rel_l2(after, ref) <= REL_L2_TOL
 
 
+@pytest.mark.parametrize("scene,w,h,spi", [("many_point_lights.json", 640, 640, 1), ("diamond_scene.json", 480, 270, 4)])
+def test_material_binning_is_invisible(scene, w, h, spi):
+    """a9: shading through the per-class index lists the trace phase writes (split turns) gives the image and the exact ray counts of
+    shading in queue order -- only the order of the float additions into a pixel can differ. Also with a deferred tail and fused iterations."""
+    t = load_scene(scene_path(scene))
+    out = {}
+    for mode, extra in ((0, {}), (1, {}), (1, {"split_turns": 6, "defer_permille": 300}), (1, {"fuse": 2})):
+        with Runtime(t, w, h, spi=spi) as rt:
+            rt.device.setOption("bin_materials", mode)
+            for k, v in extra.items():
+                rt.device.setOption(k, v)
+            for _ in range(3):
+                rt.step()
+            img = rt.getFramebufferForHost().copy()
+            st = rt.device.getStatistics()
+        out[(mode, tuple(extra))] = (img, st)
+    ref_img, ref_st = out[(0, ())]
+    for key, (img, st) in out.items():
+        assert rel_l2(img, ref_img) <= 1e-6, key
+        for k in ("CameraRayCount", "ShadowRayCount", "BounceRayCount", "Splats"):
+            assert st[k] == ref_st[k], (key, k)
+    o = Oracle(t)
+    ref = np.zeros((h, w, 3), np.float32)
+    for it in range(3):
+        o.render(w, h, spi=spi, iteration=it, fb=ref)
+    assert rel_l2(out[(1, ())][0], ref) <= REL_L2_TOL
+
+
 def test_white_furnace_through_glass_on_gpu():
     """Energy conservation of the whole device pipeline on delta paths (tests/test_oracle_kat.py has the oracle's)."""
     t = load_scene(furnace_scene())
