@@ -156,7 +156,7 @@ def cpu_render_steps(tables, w, h, spi, steps, first_iter=0):
     fb = np.zeros((h, w, 3), np.float32)
     t0 = time.perf_counter()
     for it in range(steps):
-        o.render(w, h, spi=spi, iteration=first_iter + it, fb=fb)
+        o.render(w, h, spi=spi, iteration=first_iter + it, fb=fb, use_bvh=2)   # SAH BVH4 + 4-triangle leaves, near child first: the reference's CPU tree
     dt = time.perf_counter() - t0
     rays = int(o.counters.sum())
     o.close()
@@ -183,7 +183,7 @@ def run_reference(args):
             "config": workload_config(args, 1),
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} full-frame iterations ({w}x{h}, spi {spi}) of the CPU restatement of the reference's CPU device "
-                                       f"(oracle/oracle.cpp, scalar, 16x16 tiles, {cores} threads, built {flags}); the reference itself needs the AnyDSL JIT and cannot be built"},
+                                       f"(oracle/oracle.cpp, scalar, 16x16 tiles, SAH BVH4 + 4-triangle leaves walked near child first as the reference's CPU device does, {cores} threads, built {flags}); the reference itself needs the AnyDSL JIT and cannot be built"},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "msamples_per_s": w * h * spi * args.steps / dt / 1e6}
     print(json.dumps(line))
@@ -438,7 +438,7 @@ def run_b200(args):
         dt, rays = cpu_render_steps(tables, w, h, spi, n_it)
         line["cpu_baseline"] = {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                                 "sample": f"{n_it} full-frame iteration(s) of the same workload ({w}x{h}, spi {spi}; {rays} rays, {dt:.1f} s) on {cores} threads, "
-                                          f"CPU restatement of the reference's CPU device built {flags}"}
+                                          f"CPU restatement of the reference's CPU device (BVH4+Tri4 ordered: SAH BVH4, 4-triangle leaves, near child first) built {flags}"}
     if rank == 0:
         if world > 1:
             # NCCL (with NCCL_DEBUG set) writes to fd 1 whenever it likes, also at exit: fd 1 stays pointed at stderr for the whole run

@@ -43,6 +43,8 @@
 #include <vector>
 
 #include "detmath.h"
+// The timing arm's tree is built with the product's binned-SAH builder (a header-only host function; results do not depend on the tree)
+#include "../ignis_b200/csrc/bvh8.h"
 
 namespace {
 
@@ -360,6 +362,90 @@ struct Bvh2 {
     }
 };
 
+// ------------------------------------------------------------------------------------------ BVH4 + 4-primitive leaves, near child first
+// What the reference's CPU device walks at vector width < 8: a SAH-built tree collapsed to arity 4 with Tri4 leaves
+// (src/runtime/shape/TriMeshProvider.cpp:549-557, src/runtime/bvh/NArityBvh.h:94-143, TriBVHAdapter.h:94-141), children tested unordered and
+// pushed so that the nearest ends up on top of the stack (traversal/mapping_cpu.art:353-381, stack.art push / push_after). Used by the
+// TIMING arm (use_bvh = 2: bench.py cpu_baseline / --impl reference); culling stays the conservative one, so hit records are identical to
+// the other two walks (tests/test_oracle_kat.py).
+struct Bvh4 {
+    struct Node { BBox box[4]; int child[4]; };   // child > 0: node index + 1; < 0: ~leaf index; 0: empty
+    struct Leaf { int first, count; };
+    std::vector<Node> nodes; std::vector<Leaf> leaves; std::vector<int> order;
+    void build(const std::vector<BBox>& boxes) {
+        nodes.clear(); leaves.clear(); order.clear();
+        if (boxes.empty()) return;
+        std::vector<igb::Box3> b3(boxes.size());
+        for (size_t i = 0; i < boxes.size(); ++i) b3[i] = igb::Box3{{boxes[i].min.x, boxes[i].min.y, boxes[i].min.z}, {boxes[i].max.x, boxes[i].max.y, boxes[i].max.z}};
+        igb::detail::Builder2 b2(b3, 4);
+        order = b2.order;
+        const auto& n2 = b2.nodes;
+        auto to_box = [](const igb::Box3& b) { return BBox{v3(b.lo[0], b.lo[1], b.lo[2]), v3(b.hi[0], b.hi[1], b.hi[2])}; };
+        struct Work { int n2, n4; };
+        std::vector<Work> st;
+        nodes.push_back(Node{});
+        st.push_back(Work{0, 0});
+        while (!st.empty()) {
+            const Work w = st.back(); st.pop_back();
+            int kids[4]; int nk = 0;
+            if (n2[w.n2].count > 0) kids[nk++] = w.n2;
+            else {
+                kids[nk++] = n2[w.n2].left; kids[nk++] = n2[w.n2].right;
+                while (nk < 4) {   // open the inner child with the largest surface area (NArityBvh.h:94-143)
+                    int best = -1; float best_area = -1;
+                    for (int i = 0; i < nk; ++i) if (n2[kids[i]].count == 0) { const float a = n2[kids[i]].box.half_area(); if (a > best_area) { best_area = a; best = i; } }
+                    if (best < 0) break;
+                    const int k = kids[best];
+                    kids[best] = n2[k].left; kids[nk++] = n2[k].right;
+                }
+            }
+            Node nd{};
+            for (int i = 0; i < 4; ++i) { nd.child[i] = 0; nd.box[i] = BBox{v3(INFINITY, INFINITY, INFINITY), v3(-INFINITY, -INFINITY, -INFINITY)}; }
+            for (int i = 0; i < nk; ++i) {
+                nd.box[i] = to_box(n2[kids[i]].box);
+                if (n2[kids[i]].count > 0) { leaves.push_back(Leaf{n2[kids[i]].first, n2[kids[i]].count}); nd.child[i] = ~((int)leaves.size() - 1); }
+                else { nodes.push_back(Node{}); nd.child[i] = (int)nodes.size(); st.push_back(Work{kids[i], (int)nodes.size() - 1}); }
+            }
+            nodes[w.n4] = nd;
+        }
+    }
+    // Generic ordered walk: visit(leaf) is called for leaves whose (conservatively widened) box the ray enters before `closest()`.
+    template <class Visit, class Closest, class Done>
+    void walk(const Ray& ray, Visit visit, Closest closest, Done done) const {
+        if (nodes.empty()) return;
+        struct E { int node; float t; };
+        E stack[128]; int sp = 0;
+        stack[sp++] = E{1, ray.tmin};
+        const float k = 9.5367431640625e-07f;
+        while (sp && !done()) {
+            const E top = stack[--sp];
+            if (top.t > closest() * 1.0000152587890625f) continue;                                  // mapping_cpu.art:332 (conservative form)
+            if (top.node < 0) { visit(leaves[~top.node]); continue; }
+            const Node& n = nodes[top.node - 1];
+            for (int i = 0; i < 4; ++i) {
+                if (n.child[i] == 0) break;
+                // slab test widened by its rounding error (cull_box), entry distance kept for the ordering
+                float entry = ray.tmin, exit = closest() * 1.0000152587890625f;
+                auto axis = [&](float inv_dir, float inv_org, float lo, float hi) {
+                    const float a = fabsf(inv_org);
+                    if (a == INFINITY) return;
+                    const float t0 = fmaf_(inv_dir, lo, inv_org), t1 = fmaf_(inv_dir, hi, inv_org);
+                    const float tn = fmin_sel(t0, t1) - a * k, tf = fmax_sel(t0, t1) + a * k;
+                    if (tn > entry) entry = tn;
+                    if (tf < exit) exit = tf;
+                };
+                axis(ray.inv_dir.x, ray.inv_org.x, n.box[i].min.x, n.box[i].max.x);
+                axis(ray.inv_dir.y, ray.inv_org.y, n.box[i].min.y, n.box[i].max.y);
+                axis(ray.inv_dir.z, ray.inv_org.z, n.box[i].min.z, n.box[i].max.z);
+                if (exit < entry || sp >= 127) continue;
+                // nearest on top: push, or slip under the current top (stack.art push_after; mapping_cpu.art:371-376)
+                if (sp == 0 || stack[sp - 1].t > entry) stack[sp++] = E{n.child[i], entry};
+                else { stack[sp] = stack[sp - 1]; stack[sp - 1] = E{n.child[i], entry}; ++sp; }
+            }
+        }
+    }
+};
+
 struct MeshView {
     int num_face, num_verts, num_norms, num_tex;
     const float* verts;   // xyz + pad
@@ -376,6 +462,7 @@ struct Shape {
     MeshView mesh;            // trimesh
     std::vector<Tri> tris;    // per primitive, runtime/bvh/TriBVHAdapter.h:40-61 (p0, e1=p2-p0, e2=p0-p1, stable n)
     Bvh2 bvh;
+    Bvh4 bvh4;                // timing arm
     Vec3 sph_origin; float sph_radius;
 };
 
@@ -406,6 +493,7 @@ struct Scene {
     std::vector<float> aux_data;
     BBox bbox;
     Bvh2 top;   // over leaves
+    Bvh4 top4;  // timing arm
     int num_materials;
 
     explicit Scene(const SceneDesc& d) {
@@ -450,6 +538,7 @@ struct Scene {
                     boxes[t].max = v3(std::max({p0.x, p1.x, p2.x}), std::max({p0.y, p1.y, p2.y}), std::max({p0.z, p1.z, p2.z}));
                 }
                 sh.bvh.build(boxes, 4);
+                sh.bvh4.build(boxes);
             } else {
                 const float* f = (const float*)p;  // shapes/sphere.art:74-81
                 sh.sph_origin = v3(f[0], f[1], f[2]);
@@ -478,6 +567,7 @@ struct Scene {
         std::vector<BBox> lb(leaves.size());
         for (size_t i = 0; i < leaves.size(); ++i) lb[i] = BBox{v3(leaves[i].min[0], leaves[i].min[1], leaves[i].min[2]), v3(leaves[i].max[0], leaves[i].max[1], leaves[i].max[2])};
         top.build(lb, 1);
+        top4.build(lb);
     }
 };
 
@@ -491,7 +581,7 @@ inline bool better(float t, int ent, int prim, const Hit& h) {
 }
 
 // One entity: traversal/mapping_cpu.art:282-412 (bottom level) + shapes/trimesh.art:124-144 / sphere.art:138-147
-inline void intersect_entity(const Scene& sc, const EntityLeaf& leaf, const Ray& ray, bool any_hit, bool use_bvh, Hit& hit, bool& done) {
+inline void intersect_entity(const Scene& sc, const EntityLeaf& leaf, const Ray& ray, bool any_hit, int use_bvh, Hit& hit, bool& done) {
     const int ent = leaf.entity_id & 0x7FFFFFFF;
     const Mat3x4 local{v3(leaf.local[0], leaf.local[1], leaf.local[2]), v3(leaf.local[3], leaf.local[4], leaf.local[5]),
                        v3(leaf.local[6], leaf.local[7], leaf.local[8]), v3(leaf.local[9], leaf.local[10], leaf.local[11])};
@@ -516,6 +606,11 @@ inline void intersect_entity(const Scene& sc, const EntityLeaf& leaf, const Ray&
         for (int p = 0; p < sh.mesh.num_face && !done; ++p) test_tri(p);
         return;
     }
+    if (use_bvh == 2) {
+        sh.bvh4.walk(lray, [&](const Bvh4::Leaf& l) { for (int i = 0; i < l.count && !done; ++i) test_tri(sh.bvh4.order[l.first + i]); },
+                     [&]() { return hit.distance; }, [&]() { return done; });
+        return;
+    }
     int stack[128]; int sp = 0;
     if (sh.bvh.nodes.empty()) return;
     stack[sp++] = 0;
@@ -528,7 +623,7 @@ inline void intersect_entity(const Scene& sc, const EntityLeaf& leaf, const Ray&
 }
 
 // Top level: traversal/mapping_cpu.art:421-518
-inline Hit traverse(const Scene& sc, const Ray& ray, bool any_hit, bool use_bvh) {
+inline Hit traverse(const Scene& sc, const Ray& ray, bool any_hit, int use_bvh) {
     Hit hit = invalid_hit(ray.tmax);
     bool done = false;
     auto visit_leaf = [&](const EntityLeaf& leaf) {
@@ -542,6 +637,11 @@ inline Hit traverse(const Scene& sc, const Ray& ray, bool any_hit, bool use_bvh)
     };
     if (!use_bvh) {
         for (size_t i = 0; i < sc.leaves.size() && !done; ++i) visit_leaf(sc.leaves[i]);
+        return hit;
+    }
+    if (use_bvh == 2) {
+        sc.top4.walk(ray, [&](const Bvh4::Leaf& l) { for (int i = 0; i < l.count && !done; ++i) visit_leaf(sc.leaves[sc.top4.order[l.first + i]]); },
+                     [&]() { return hit.distance; }, [&]() { return done; });
         return hit;
     }
     if (sc.top.nodes.empty()) return hit;
@@ -1522,7 +1622,7 @@ struct Oracle {
 
 // One tile: driver/mapping_cpu.art:719-861
 void trace_tile(const Scene& sc, const Settings& st, const StreamRay* list_rays, int xmin, int ymin, int xmax, int ymax,
-                float* fb, bool use_bvh, uint64_t counters[3], float* aov_normals = nullptr, float* aov_albedo = nullptr) {
+                float* fb, int use_bvh, uint64_t counters[3], float* aov_normals = nullptr, float* aov_albedo = nullptr) {
     const int spi = st.spi;
     const int capacity = spi * 16 * 16;                         // :717
     const int W = st.width, H = st.height;
@@ -1686,7 +1786,7 @@ void igo_render(void* o, const Settings* st, const StreamRay* rays, float* fb, i
                 const int pidx = (y0 / part_tile) * ptx + (x0 / part_tile);
                 if (((pidx % ptx) + (pidx / ptx)) % part_world != part_rank) continue;
             }
-            trace_tile(sc, *st, rays, x0, y0, std::min(W, x0 + T), std::min(H, y0 + T), fb, use_bvh != 0, cnt[tid].data(), rays ? nullptr : ((Oracle*)o)->aov_normals, rays ? nullptr : ((Oracle*)o)->aov_albedo);
+            trace_tile(sc, *st, rays, x0, y0, std::min(W, x0 + T), std::min(H, y0 + T), fb, use_bvh, cnt[tid].data(), rays ? nullptr : ((Oracle*)o)->aov_normals, rays ? nullptr : ((Oracle*)o)->aov_albedo);
         }
     };
     if (n_threads <= 1) worker(0);
@@ -1699,7 +1799,7 @@ void igo_trace_closest(void* o, const StreamRay* rays, const uint32_t* flags, in
     for (int64_t i = 0; i < n; ++i) {
         const StreamRay& r = rays[i];
         const Ray ray = make_ray(v3(r.org[0], r.org[1], r.org[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax, flags ? flags[i] : ray_flag_camera);
-        const Hit h = traverse(sc, ray, false, use_bvh != 0);
+        const Hit h = traverse(sc, ray, false, use_bvh);
         out[i] = HitRecord{h.ent_id, h.prim_id, h.distance, h.prim_coords.x, h.prim_coords.y};
     }
 }
@@ -1708,7 +1808,7 @@ void igo_trace_any(void* o, const StreamRay* rays, const uint32_t* flags, int64_
     for (int64_t i = 0; i < n; ++i) {
         const StreamRay& r = rays[i];
         const Ray ray = make_ray(v3(r.org[0], r.org[1], r.org[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax, flags ? flags[i] : ray_flag_shadow);
-        occluded[i] = traverse(sc, ray, true, use_bvh != 0).prim_id >= 0;
+        occluded[i] = traverse(sc, ray, true, use_bvh).prim_id >= 0;
     }
 }
 

@@ -166,7 +166,8 @@ class Oracle:
 
     def render(self, width, height, spi=1, iteration=0, seed=0, frame=0, fb=None, threads=0, use_bvh=True,
                rays=None, partition=(0, 1, 32)):
-        """One `render()` iteration accumulated into fb (H, W, 3) float32."""
+        """One `render()` iteration accumulated into fb (H, W, 3) float32. use_bvh: 0 / False = brute force, 1 / True = median-split BVH2 (the
+        parity walks), 2 = SAH BVH4 with 4-primitive leaves, near child first (what the reference's CPU device walks; the timing arm)."""
         if fb is None:
             fb = np.zeros((height, width, 3), np.float32)
         assert fb.dtype == np.float32 and fb.flags.c_contiguous and fb.size == width * height * 3
@@ -178,7 +179,7 @@ class Oracle:
         if rays is not None:
             rays = np.ascontiguousarray(rays, RAY_DTYPE)
             rp = rays.ctypes.data
-        lib().igo_render(self._h, C.byref(st), rp, fb.ctypes.data, threads, 1 if use_bvh else 0,
+        lib().igo_render(self._h, C.byref(st), rp, fb.ctypes.data, threads, int(use_bvh),
                          partition[0], partition[1], partition[2], cnt)
         self.counters += np.asarray(list(cnt), np.uint64)
         return fb
@@ -194,7 +195,7 @@ class Oracle:
         out = np.zeros(rays.shape[0], HIT_DTYPE)
         fl = None if flags is None else np.ascontiguousarray(flags, np.uint32)
         lib().igo_trace_closest(self._h, rays.ctypes.data, None if fl is None else fl.ctypes.data, rays.shape[0],
-                                out.ctypes.data, 1 if use_bvh else 0)
+                                out.ctypes.data, int(use_bvh))
         return out
 
     def trace_any(self, rays, flags=None, use_bvh=True):
@@ -202,7 +203,7 @@ class Oracle:
         out = np.zeros(rays.shape[0], np.int32)
         fl = None if flags is None else np.ascontiguousarray(flags, np.uint32)
         lib().igo_trace_any(self._h, rays.ctypes.data, None if fl is None else fl.ctypes.data, rays.shape[0],
-                            out.ctypes.data, 1 if use_bvh else 0)
+                            out.ctypes.data, int(use_bvh))
         return out
 
 

@@ -173,6 +173,9 @@ def test_bvh_and_brute_force_agree_on_hits(scenes_dir):
     np.testing.assert_array_equal(a, b)
     assert (a["prim_id"] >= 0).mean() > 0.8    # five-sided box
     np.testing.assert_array_equal(o.trace_any(rays, use_bvh=True), o.trace_any(rays, use_bvh=False))
+    # the timing arm's tree (SAH BVH4, 4-primitive leaves, nearest child first -- what the reference's CPU device walks) gives the same records
+    np.testing.assert_array_equal(o.trace_closest(rays, use_bvh=2), b)
+    np.testing.assert_array_equal(o.trace_any(rays, use_bvh=2), o.trace_any(rays, use_bvh=False))
 
 
 def test_oracle_bvh_equals_brute_force_on_coplanar_geometry():
@@ -194,6 +197,9 @@ def test_oracle_bvh_equals_brute_force_on_coplanar_geometry():
         o = Oracle(t)
         a, b = o.trace_closest(rays, use_bvh=True), o.trace_closest(rays, use_bvh=False)
         assert a.tobytes() == b.tobytes()
+        assert o.trace_closest(rays, use_bvh=2).tobytes() == b.tobytes()
+        img = [o.render(96, 64, spi=2, use_bvh=m) for m in (1, 2)]
+        np.testing.assert_array_equal(img[0], img[1])
         fl = np.full(len(rays), 8, np.uint32)
         np.testing.assert_array_equal(o.trace_any(rays, flags=fl, use_bvh=True), o.trace_any(rays, flags=fl, use_bvh=False))
 
