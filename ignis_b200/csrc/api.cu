@@ -48,12 +48,14 @@ static WaveKernel turn_shade_kernel(int blocks, bool full) {
 // where: 1 the whole scene is staged in shared memory (shared-memory loads without range checks: -6 % trace time on diamond_scene
 // and cbox), 0 decided per index (traverse.cuh node_ptr). Specialised for the default scheduling (vote 2) only. An "everything in
 // global memory" variant (2) was measured too: +1 to +2.5 % (more spills), so unstaged scenes use the generic kernel.
-static WaveKernel turn_trace_kernel(int blocks, int vote, int where) {
+static WaveKernel turn_trace_kernel(int blocks, int vote, int where, bool flat = false) {
+    if (flat) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 1, true> : k_turn_trace<WF_BLOCK, 2, 2, 1, true>;   // merged tree (small scenes, staged)
     if (vote && where == 1) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 1> : k_turn_trace<WF_BLOCK, 2, 2, 1>;
     if (vote) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 0> : k_turn_trace<WF_BLOCK, 2, 2, 0>;
     return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 0, 0> : k_turn_trace<WF_BLOCK, 2, 0, 0>;
 }
-static TraceKernel trace_kernel(int min_blocks, int vote, int where = 0) {
+static TraceKernel trace_kernel(int min_blocks, int vote, int where = 0, bool flat = false) {
+    if (flat) return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 2, 1, true> : k_trace<WF_BLOCK, 2, 2, 1, true>;
     if (vote && where == 1 && min_blocks < 4) return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 2, 1> : k_trace<WF_BLOCK, 2, 2, 1>;   // as turn_trace_kernel
     if (min_blocks >= 4) return vote ? k_trace<WF_BLOCK, 4, 2> : k_trace<WF_BLOCK, 4, 0>;   // 64 registers: stand-alone trace phase only
     if (vote) return min_blocks >= 3 ? k_trace<WF_BLOCK, 3, 2> : k_trace<WF_BLOCK, 2, 2>;
@@ -153,6 +155,10 @@ struct igb200_ctx {
     DevScene dev{};
     DevBuf<float4> nodes, tris, ent_leaf, ent_shade, blob, materials;
     DevBuf<int> tri_prim;
+    DevBuf<float4> flat_nodes;         // merged tree of small scenes (build_flat_tree)
+    int flat_option = 1;               // option "flat": 0 = always walk the two-level tree
+    bool flat_on = false;              // the split-turn trace kernel and the trace hooks walk the merged tree
+    size_t smem_flat = 0;
     DevBuf<int4> shape_info;
     DevBuf<float> inf_lights, fin_lights, selector_data, textures, aux_data;
     DevBuf<int4> images;
@@ -187,7 +193,7 @@ struct igb200_ctx {
     int split_turns = -1;               // leading turns of an iteration run as separate shade / trace launches (0: all in the persistent kernel)
     int turn_trace_blocks = 3;         // CTAs per SM the trace kernel of a split turn is compiled for
     int turn_shade_blocks = 3;         // ... and the shade + generate kernel
-    int grid_turn_shade = 0, grid_turn_trace = 0;
+    int grid_turn_shade = 0, grid_turn_trace = 0, grid_turn_trace_flat = 0;
     int trace_blocks = 0;              // stand-alone trace hooks: CTAs per SM the kernel is compiled for (0: as min_blocks)
     // deferred tail: a launch ends once at most defer_permille/1000 of the iteration's camera rays are still alive as paths;
     // they are carried into the next launch (render) or finished by a drain launch before anything is observed
@@ -269,6 +275,10 @@ static int configure_kernels(igb200_ctx* c) {
     c->stage_where = (c->stage_ent == s.n_ent && c->stage_nodes == s.n_nodes && c->stage_tris == s.n_tris) ? 1 : 0;
     if (!c->specialise_where) c->stage_where = 0;
     c->smem_bytes = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)c->stage_ent * 128 + (size_t)c->stage_nodes * 256 + (size_t)c->stage_tris * 48;
+    // the merged tree (small scenes): walked by the split-turn trace kernel and the trace hooks when the two-level scene is staged as a whole
+    c->flat_on = c->flat_option != 0 && s.n_flat_nodes > 0 && c->stage_where == 1 && c->vote != 0 &&
+                 (int64_t)s.n_flat_nodes * 256 + (int64_t)s.n_tris * 48 + (int64_t)s.n_ent * 128 <= c->stage_budget;
+    c->smem_flat = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)s.n_ent * 128 + (size_t)s.n_flat_nodes * 256 + (size_t)s.n_tris * 48;
     for (int full = 0; full < 2; ++full) CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote, full != 0, c->stage_where), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CU(cudaFuncSetAttribute((const void*)trace_kernel(c->min_blocks, c->vote), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     int nb = 0;
@@ -282,6 +292,13 @@ static int configure_kernels(igb200_ctx* c) {
     c->blocks_per_sm = nb;
     // split turn kernels
     CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    if (c->flat_on) {
+        CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, 1, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_flat));
+        int nbf = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbf, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, 1, true), WF_BLOCK, c->smem_flat));
+        if (nbf < c->turn_trace_blocks) c->flat_on = false;   // would cost occupancy: keep the two-level walk
+        else c->grid_turn_trace_flat = nbf * c->n_sm;
+    }
     if (c->carveout >= 0) {
         CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where), cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout));
         for (int full = 0; full < 2; ++full) CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote, full != 0, c->stage_where), cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout));
@@ -314,6 +331,7 @@ static WaveParams make_params(igb200_ctx* c, const RenderParams& rp, const DevSc
     P.refill = c->refill; P.defer = defer;
     P.order = c->bin_order.p;
     P.wide_limit = (int)std::min<int64_t>(c->wide_rays_per_group * c->blocks_per_sm * c->n_sm * (WF_BLOCK / 8), (int64_t)1 << 30);
+    P.stage_flat = c->flat_on ? sc.n_flat_nodes : 0;
     return P;
 }
 
@@ -378,7 +396,8 @@ static int launch_split_turns(igb200_ctx* c, const WaveParams& P, int turns) {
         turn_shade_kernel(c->turn_shade_blocks, P.sc.full != 0)<<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
         { const int r = prof_end(c); if (r) return r; }
         { const int r = prof_begin(c, 1); if (r) return r; }
-        turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
+        if (c->flat_on) turn_trace_kernel(c->turn_trace_blocks, c->vote, 1, true)<<<c->grid_turn_trace_flat, WF_BLOCK, c->smem_flat, c->stream>>>(P);
+        else turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
         { const int r = prof_end(c); if (r) return r; }
         { const int r = prof_begin(c, 3); if (r) return r; }
         k_turn_end<<<1, 1, 0, c->stream>>>(P);
@@ -523,6 +542,11 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "profile_kernels")) { c->profile = value != 0; return 0; }
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
     if (!strcmp(name, "std_aovs")) { c->std_aovs = value != 0; CU(cudaSetDevice(c->device)); return ensure_aovs(c); }
+    if (!strcmp(name, "flat")) {   // 0: never walk the merged tree. Takes effect at the next igb200_set_scene (the tree is built there) or at once when switching off
+        c->flat_option = value ? 1 : 0;
+        if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); }
+        return 0;
+    }
     if (!strcmp(name, "bin_materials")) { if (value < -1 || value > 2) return fail(-1, "bin_materials must be -1 (automatic), 0, 1 or 2"); c->bin_materials = (int)value; return 0; }
     if (!strcmp(name, "fuse")) { if (value < 0 || value > 64) return fail(-1, "fuse must be in [0, 64]"); c->fuse = (int)value; return 0; }
     if (!strcmp(name, "split_turns")) { if (value < -1 || value > 64) return fail(-1, "split_turns must be in [-1, 64] (-1: chosen from the number of camera rays)"); c->split_turns = (int)value; return 0; }
@@ -634,6 +658,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     std::vector<int> tri_prim;
     std::vector<int4> shape_info(2 * (size_t)d->n_shapes);
     std::vector<int> shape_root(d->n_shapes, 0);
+    std::vector<int> shape_node_base(d->n_shapes, 0), shape_node_count(d->n_shapes, 0);   // the shape's tree inside `nodes`, before the reordering below
     std::vector<Box3> ent_boxes(d->n_entities);
     for (int i = 0; i < d->n_entities; ++i) {
         const igb200_entity_leaf& lf = d->leaves[i];
@@ -689,6 +714,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
             for (int t = 0; t < nf; ++t) bvh.order[t] = t;
             shape_root[s] = -(((tri_base << 2) | (nf - 1)) + 1);
         }
+        shape_node_base[s] = node_base; shape_node_count[s] = (int)bvh.nodes.size();
         for (Node8 n : bvh.nodes) {
             for (int k = 0; k < 8; ++k) {
                 if (n.child[k] > 0) n.child[k] += node_base;
@@ -720,6 +746,79 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
         const int need = 7 * (top.max_depth + max_shape_depth) + 2;
         const int have = std::min(STACK_SIZE, WIDE_STACK);
         if (need > have) return fail(-4, "igb200_set_scene: BVH too deep for the traversal stack (top level %d + shape level %d levels need %d entries, %d available)", top.max_depth, max_shape_depth, need, have);
+    }
+    // ---- merged tree for small scenes (traverse.cuh "merged-tree walk"): the top-level tree whose leaves are replaced by the instances'
+    // own trees, each instance's node boxes refitted in WORLD space from its transformed triangles. Triangles stay per shape (local space).
+    std::vector<Node8> flat;
+    {
+        bool ok = c->flat_option != 0 && d->n_entities >= 1 && d->n_entities <= 510 && tri_prim.size() < ((size_t)1 << 20);
+        for (int s = 0; s < d->n_shapes && ok; ++s) ok = d->shape_lookups[s].type_id == IGB200_SHAPE_TRIMESH;
+        size_t flat_nodes_n = top.nodes.size();
+        for (int i = 0; i < d->n_entities && ok; ++i) flat_nodes_n += shape_root[d->leaves[i].shape_id] > 0 ? shape_node_count[d->leaves[i].shape_id] : 0;
+        ok = ok && (int64_t)flat_nodes_n * 256 + (int64_t)tri_prim.size() * 48 + (int64_t)d->n_entities * 128 <= c->stage_budget;   // only when all of it is staged
+        if (ok) {
+            flat.assign(top.nodes.begin(), top.nodes.end());
+            const float inf = std::numeric_limits<float>::max();
+            for (size_t tn = 0; tn < top.nodes.size(); ++tn) {
+                for (int k = 0; k < 8; ++k) {
+                    const int code = flat[tn].child[k];
+                    if (code >= 0) continue;                              // inner child of the top-level tree (indices are already those of `flat`)
+                    const int slot = (-code - 1) >> 2;                    // top-level leaves hold one entity each
+                    const igb200_entity_leaf& lf = d->leaves[top.order[slot]];
+                    const int sh = lf.shape_id, ent = lf.entity_id & 0x7FFFFFFF;
+                    const float* G = d->entities + 36 * (size_t)ent + 12;   // local -> world, column major 3x4 (LoaderEntity.cpp:150-162)
+                    const uint8_t* sp = d->shape_data + d->shape_lookups[sh].offset;
+                    const int32_t* hdr = reinterpret_cast<const int32_t*>(sp);
+                    const float* verts = reinterpret_cast<const float*>(sp) + 12;
+                    const int32_t* inds = reinterpret_cast<const int32_t*>(verts + 4 * (size_t)hdr[1] + 4 * (size_t)hdr[2]);
+                    // world-space box of the triangle in primitive slot `ts`, padded well beyond the rounding of transform + triangle test
+                    auto tri_box = [&](int ts) {
+                        Box3 b = Box3::empty();
+                        const int t = tri_prim[ts];
+                        for (int v = 0; v < 3; ++v) {
+                            const float* p = verts + 4 * (size_t)inds[4 * t + v];
+                            float w[3];
+                            for (int a = 0; a < 3; ++a) w[a] = (float)((double)G[a] * p[0] + (double)G[3 + a] * p[1] + (double)G[6 + a] * p[2] + (double)G[9 + a]);
+                            b.extend(w);
+                        }
+                        for (int a = 0; a < 3; ++a) {
+                            const float pad = 3.0517578125e-05f * std::max(std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])), b.hi[a] - b.lo[a]) + 1e-30f;   // 2^-15 relative
+                            b.lo[a] -= pad; b.hi[a] += pad;
+                        }
+                        return b;
+                    };
+                    auto leaf_code = [&](int shape_leaf_code, Box3& box) {   // the shape's leaf code -> the merged tree's, + the leaf's world box
+                        const int r = -shape_leaf_code - 1, first = r >> 2, cnt = (r & 3) + 1;
+                        box = Box3::empty();
+                        for (int j = 0; j < cnt; ++j) box.extend(tri_box(first + j));
+                        return -((((slot << 20) | first) << 2 | (cnt - 1)) + 1);
+                    };
+                    auto set_box = [&](Node8& n, int lane, const Box3& b) {
+                        n.bounds[0][lane] = b.lo[0]; n.bounds[1][lane] = b.hi[0]; n.bounds[2][lane] = b.lo[1]; n.bounds[3][lane] = b.hi[1]; n.bounds[4][lane] = b.lo[2]; n.bounds[5][lane] = b.hi[2];
+                    };
+                    Box3 root_box;
+                    if (shape_root[sh] < 0) { flat[tn].child[k] = leaf_code(shape_root[sh], root_box); set_box(flat[tn], k, root_box); continue; }
+                    // copy the shape's tree, children rebased, boxes refitted bottom-up (children follow their parents in the array)
+                    const int base = (int)flat.size(), sb = shape_node_base[sh], sn = shape_node_count[sh];
+                    for (int i = 0; i < sn; ++i) flat.push_back(nodes[sb + i]);
+                    std::vector<Box3> node_box(sn, Box3::empty());
+                    for (int i = sn - 1; i >= 0; --i) {
+                        Node8& n = flat[base + i];
+                        Box3 nb = Box3::empty();
+                        for (int ch = 0; ch < 8; ++ch) {
+                            Box3 cb;
+                            if (n.child[ch] > 0) { const int ci = n.child[ch] - 1 - sb; cb = node_box[ci]; n.child[ch] = base + ci + 1; }
+                            else if (n.child[ch] < 0) n.child[ch] = leaf_code(n.child[ch], cb);
+                            else { for (int q = 0; q < 6; ++q) n.bounds[q][ch] = (q & 1) ? -inf : inf; continue; }
+                            set_box(n, ch, cb); nb.extend(cb);
+                        }
+                        node_box[i] = nb;
+                    }
+                    flat[tn].child[k] = base + 1;
+                    set_box(flat[tn], k, node_box[0]);
+                }
+            }
+        }
     }
     // ---- node order: breadth-first across ALL trees (top-level root first, then level by level over every shape's tree), so that
     // the part of the node array that is staged in shared memory (configure_kernels) holds the top of every tree instead of
@@ -797,6 +896,8 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
         // (experiment "bin_materials" = 2: when no material is heavy, split delta BSDFs -- no next-event estimation -- from the others)
         E[5] = make_float4(nm[2], nm[5], nm[8], as_f((heavy || (c->bin_materials == 2 && mt.bsdf != IGB200_BSDF_DIFFUSE)) ? 1 : 0));
     }
+    std::vector<float4> flat_f4(flat.size() * 16);
+    if (!flat.empty()) std::memcpy(flat_f4.data(), flat.data(), flat.size() * sizeof(Node8));
     std::vector<float4> node_f4(nodes.size() * 16);
     if (!nodes.empty()) std::memcpy(node_f4.data(), nodes.data(), nodes.size() * sizeof(Node8));
     std::vector<float4> blob(d->shape_data_bytes / 16);
@@ -824,6 +925,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     if (d->n_finite) std::memcpy(finl.data(), d->finite_lights, sizeof(igb200_light) * (size_t)d->n_finite);
 
     CU(cudaStreamSynchronize(c->stream));
+    CU(c->flat_nodes.upload(flat_f4));
     CU(c->nodes.upload(node_f4)); CU(c->tris.upload(tris)); CU(c->tri_prim.upload(tri_prim)); CU(c->ent_leaf.upload(ent_leaf)); CU(c->ent_shade.upload(ent_shade));
     CU(c->blob.upload(blob)); CU(c->shape_info.upload(shape_info)); CU(c->materials.upload(mats));
     CU(c->inf_lights.upload(infl)); CU(c->fin_lights.upload(finl));
@@ -838,6 +940,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     s.textures = c->textures.p; s.images = c->images.p; s.image_data = c->image_data.p; s.aux_data = c->aux_data.p;
     s.n_ent = d->n_entities; s.n_mat = d->n_materials; s.n_inf = d->n_infinite; s.n_fin = d->n_finite;
     s.n_nodes = (int)nodes.size(); s.n_tris = (int)tri_prim.size();
+    s.flat_nodes = c->flat_nodes.p; s.n_flat_nodes = (int)flat.size();
     {   // bbox_radius(scene_bbox) * 1.01: light/env.art:76, core/bbox.art:24 (fma dot as on the device)
         const float dx = d->bbox_max[0] - d->bbox_min[0], dy = d->bbox_max[1] - d->bbox_min[1], dz = d->bbox_max[2] - d->bbox_min[2];
         s.scene_radius = std::sqrt(std::fmaf(dx, dx, std::fmaf(dy, dy, dz * dz))) / 2 * 1.01f;
@@ -1169,10 +1272,12 @@ static int run_trace(igb200_ctx* c, const igb200_ray* d_rays, const uint32_t* d_
     { const int r = ensure_queues(c, n); if (r) return r; }
     if (n > c->capacity) return fail(-1, "igb200_trace_*: %zu rays exceed the queue capacity %zu", n, c->capacity);
     const int tb = c->trace_blocks ? c->trace_blocks : c->min_blocks;
-    const TraceKernel tk = trace_kernel(tb, c->vote, c->stage_where);
-    CU(cudaFuncSetAttribute((const void*)tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    const bool flat = c->flat_on && tb < 4;
+    const TraceKernel tk = trace_kernel(tb, c->vote, c->stage_where, flat);
+    const size_t smem = flat ? c->smem_flat : c->smem_bytes;
+    CU(cudaFuncSetAttribute((const void*)tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)tk, WF_BLOCK, c->smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)tk, WF_BLOCK, smem));
     if (nb < 1) return fail(-2, "k_trace does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
     const int grid = nb * c->n_sm;
     k_import_rays<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(d_rays, d_flags, any_hit ? RAY_SHADOW : RAY_CAMERA, (int)n, c->qa.view(), ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, any_hit);
@@ -1180,8 +1285,8 @@ static int run_trace(igb200_ctx* c, const igb200_ray* d_rays, const uint32_t* d_
         if (ms_per_pass && r == 3) CU(cudaEventRecord(c->ev0, c->stream));
         CU(cudaMemsetAsync(c->control.p, 0, CONTROL_SCRATCH, c->stream));
         if (!any_hit && r > 0) k_import_rays<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(d_rays, d_flags, RAY_CAMERA, (int)n, c->qa.view(), ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, 0);
-        tk<<<grid, WF_BLOCK, c->smem_bytes, c->stream>>>(c->dev, c->qa.view(), any_hit ? 0 : (int)n, ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, any_hit ? (int)n : 0, d_fb,
-                                                                                     &c->control.p->fetch_trace, &c->control.p->cam_launch, c->stage_nodes, c->stage_tris, c->stage_ent, c->refill,
+        tk<<<grid, WF_BLOCK, smem, c->stream>>>(c->dev, c->qa.view(), any_hit ? 0 : (int)n, ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p}, any_hit ? (int)n : 0, d_fb,
+                                                                                     &c->control.p->fetch_trace, &c->control.p->cam_launch, flat ? c->dev.n_flat_nodes : c->stage_nodes, c->stage_tris, c->stage_ent, c->refill,
                                                                                      (int)std::min<int64_t>(c->wide_rays_per_group * grid * (WF_BLOCK / 8), (int64_t)1 << 30));
     }
     if (ms_per_pass) {

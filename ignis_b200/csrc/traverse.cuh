@@ -167,6 +167,8 @@ struct Traversal {
     float tcull;              // hit.t * CULL_TMAX
     HitR hit;
     int cur, ent, sp;         // node code (0: pop next); entity whose bottom-level tree is walked (-1: top level)
+                              // (merged-tree walk: `ent` = the entity-leaf slot whose local ray is cached in lorg / ldir, -1: none)
+    V3 lorg, ldir;            // merged-tree walk only: the ray in the local space of entity slot `ent`
     uint32_t bits;            // ray type flags (ray.art:51) | TB_*
 #ifdef IGB_STEP_STATS
     int n_node, n_leaf, n_ent;   // diagnostics build only: visits of each kind
@@ -370,6 +372,72 @@ struct Traversal {
             }
             a = na; b = nb; c = nc;
         }
+    }
+
+    // ================= merged-tree walk (small scenes; DevScene::flat_nodes) =====================================================
+    // The instances' trees hang directly off the top-level tree and their node boxes are refitted in world space, so the walk never
+    // leaves world space: no entity visit, no sentinel, no ray set-up (three reciprocals) on entering or leaving an instance -- two visit
+    // kinds instead of three for the warp to diverge over. What the reference does per entity (traversal/mapping_cpu.art:479-494) is
+    // kept to the letter, only moved: the ray is transformed into the entity's space when a leaf of that entity is reached (cached
+    // while consecutive leaves belong to the same entity) and the triangle test runs on that local ray exactly as before, so t / u / v
+    // are the same bits; the entity's visibility and box tests are properties of (ray, entity) and are evaluated when a candidate hit
+    // in that entity turns up. A leaf code carries the entity: r = -code - 1 = (entity-leaf slot << 22) | (first slot << 2) | (count - 1).
+    __device__ __forceinline__ bool pop_flat(Stack& st) {
+        for (;;) {
+            if (sp == 0) return true;
+            const uint2 e = st.pop(sp);
+            if (__uint_as_float(e.y) <= tcull) { cur = (int)e.x; return false; }
+        }
+    }
+    template <int WHERE>
+    __device__ __forceinline__ bool entity_admits(const DevScene& sc, const Staged& sg, int slot) {
+        const float4* L = leaf_ptr<WHERE>(sc, sg, slot);
+        const float4 l0 = L[0], l1 = L[1];
+        const uint32_t eflags = __float_as_uint(l0.w);
+        if ((bits & RAY_TYPE_MASK) != ((bits & eflags) & RAY_TYPE_MASK)) return false;                       // ray.art:51
+        const V3 iorg = neg(org * idir);                                                                       // intersection.art:247-256, exact reference form
+        const float t0x = fma_(idir.x, l0.x, iorg.x), t1x = fma_(idir.x, l1.x, iorg.x);
+        const float t0y = fma_(idir.y, l0.y, iorg.y), t1y = fma_(idir.y, l1.y, iorg.y);
+        const float t0z = fma_(idir.z, l0.z, iorg.z), t1z = fma_(idir.z, l1.z, iorg.z);
+        const float en = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+        const float ex = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
+        return (en <= ex) & (ex >= 0);
+    }
+    template <int WHERE>
+    __device__ __forceinline__ void flat_leaf_step(const DevScene& sc, const Staged& sg) {
+        const int r = -cur - 1;
+        const int cnt = (r & 3) + 1, first = (r >> 2) & 0xFFFFF, slot = r >> 22;
+        cur = 0;
+        const float4* L = leaf_ptr<WHERE>(sc, sg, slot);
+        if (slot != ent) {
+            const int kind = __float_as_int(L[1].w);
+            if ((kind & 2) && !(bits & TB_NEGZERO)) { lorg = org; ldir = dir; }                              // bit-exact identity: x -> x + 0
+            else { const float4 r0 = L[2], r1 = L[3], r2 = L[4]; lorg = xform_point(r0, r1, r2, org); ldir = xform_dir(r0, r1, r2, dir); }   // ray.art:53-59
+            ent = slot;
+        }
+        for (int j = 0; j < cnt; ++j) {
+            const float4* T = tri_ptr<WHERE>(sc, sg, first + j);
+            const float4 a = T[0], b = T[1], c = T[2];
+            float t, u, v;
+            if (intersect_tri(lorg, ldir, tmin, tmax, a, b, c, t, u, v)) {
+                const int prim = __ldg(sc.tri_prim + first + j);
+                const int e = __float_as_int(L[5].x);
+                if (better(t, e, prim, hit) && entity_admits<WHERE>(sc, sg, slot)) accept(t, u, v, prim, e);
+            }
+        }
+    }
+    template <int WHERE>
+    __device__ __forceinline__ bool turn_vote_flat(const DevScene& sc, const Staged& sg, Stack& st, bool active, int vote) {
+        bool fin = false;
+        if (active && cur == 0) fin = pop_flat(st);
+        const bool live = active && !fin;
+        const bool wN = live && cur > 0, wL = live && cur < 0;
+        const int nN = __popc(__ballot_sync(0xffffffffu, wN)), nL = __popc(__ballot_sync(0xffffffffu, wL));
+        const int mx = max(nN, nL);
+        const int need = vote >= 2 ? max(1, (mx + 1) >> 1) : max(1, mx);
+        if (nN >= need) { if (wN) node_step<WHERE>(sc, sg, st); }
+        if (nL >= need) { if (cur < 0 && live) flat_leaf_step<WHERE>(sc, sg); }
+        return fin || (live && (bits & TB_DONE) != 0);
     }
 
     // One turn of the pipeline P -> N -> E -> L: a lane performs every visit its state allows, in that order, so that

@@ -28,6 +28,9 @@ struct DevScene {
     const float*  fin_lights;
     int   n_ent, n_mat, n_inf, n_fin;
     int   n_nodes, n_tris;    // array sizes (for staging into shared memory)
+    // Small scenes: ONE merged tree (api.cu build_flat_tree) -- the top-level tree with every instance's tree hanging off it, the
+    // instances' node boxes refitted in WORLD space. Leaves carry the entity (traverse.cuh flat_leaf_step); triangles stay per shape.
+    const float4* flat_nodes; int n_flat_nodes;
     float scene_radius;
     int   max_depth, min_depth;
     float clamp_value;

@@ -79,7 +79,8 @@ def test_closest_hit_records_match_oracle(scene, w, h):
     # both walks of the device: one lane per ray (large queues) and eight lanes per ray (small queues, traverse.cuh trace_wide);
     # with the scene copy in shared memory when it fits (the default), with nothing staged, and with a staged prefix (nodes and
     # triangles partly in shared memory, partly read through L1/L2) -- the closest hit must not depend on any of it
-    for wide, opts in ((0, {}), (1 << 20, {}), (0, {"specialise_where": 0}), (0, {"stage_budget": 0}), (1 << 20, {"stage_budget": 0}),
+    # ... nor on the merged single-level tree small scenes are walked with by default ("flat": 0 = the two-level walk)
+    for wide, opts in ((0, {}), (0, {"flat": 0}), (1 << 20, {}), (1 << 20, {"flat": 0}), (0, {"specialise_where": 0}), (0, {"stage_budget": 0}), (1 << 20, {"stage_budget": 0}),
                        (0, {"stage_partial": 1, "stage_budget": 6144}), (1 << 20, {"stage_partial": 1, "stage_budget": 6144})):
         budget = tuple(opts.items())
         with B200Device() as dev:
@@ -425,6 +426,30 @@ def test_material_binning_is_invisible(scene, w, h, spi):
     for it in range(3):
         o.render(w, h, spi=spi, iteration=it, fb=ref)
     assert rel_l2(out[(1, ())][0], ref) <= REL_L2_TOL
+
+
+@pytest.mark.parametrize("scene", ["diamond_scene.json", "evaluation/cbox-d6.json", "many_point_lights.json", "evaluation/multilight-uniform.json"])
+def test_merged_tree_walk_is_invisible(scene):
+    """Small scenes are traced through one merged tree (instances refitted in world space, traverse.cuh): same image, exactly the same
+    ray counts as the two-level walk, and both equal to the oracle."""
+    t = load_scene(scene_path(scene))
+    w, h, spi = 320, 200, 2
+    out = {}
+    for flat in (1, 0):
+        with Runtime(t, w, h, spi=spi) as rt:
+            rt.device.setOption("flat", flat)
+            for _ in range(3):
+                rt.step()
+            out[flat] = (rt.getFramebufferForHost().copy(), rt.device.getStatistics())
+    assert rel_l2(out[1][0], out[0][0]) <= 1e-6
+    for k in ("CameraRayCount", "ShadowRayCount", "BounceRayCount", "Splats"):
+        assert out[1][1][k] == out[0][1][k], k
+    o = Oracle(t)
+    ref = np.zeros((h, w, 3), np.float32)
+    for it in range(3):
+        o.render(w, h, spi=spi, iteration=it, fb=ref)
+    assert rel_l2(out[1][0], ref) <= REL_L2_TOL
+    assert (out[1][1]["CameraRayCount"], out[1][1]["ShadowRayCount"], out[1][1]["BounceRayCount"]) == tuple(int(x) for x in o.counters)
 
 
 def test_white_furnace_through_glass_on_gpu():
