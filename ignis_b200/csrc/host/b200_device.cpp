@@ -129,7 +129,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     d.finite_lights = fin.data(); d.n_finite = (int32_t)fin.size();
     d.camera = camera; d.technique = technique;
     d.selector_data = selector_data.empty() ? nullptr : selector_data.data(); d.n_selector_data = (int32_t)selector_data.size();
-    for (int k = 0; k < 3; ++k) { d.bbox_min[k] = db.SceneBBox.min.v[k]; d.bbox_max[k] = db.SceneBBox.max.v[k]; }
+    for (int k = 0; k < 3; ++k) { d.bbox_min[k] = db.SceneBBox.min(k); d.bbox_max[k] = db.SceneBBox.max(k); }
     if (igb200_set_scene(mCtx, &d) != 0) { error(std::string("scene upload failed: ") + igb200_last_error()); return false; }
     mDescriptorBytes.swap(bytes);
     mSceneDirty = false;
@@ -148,12 +148,12 @@ void B200Device::render(const IG::TechniqueVariantShaderSet& shader_set, const R
         std::vector<igb200_ray> rays(settings.width);
         for (size_t i = 0; i < settings.width; ++i) {
             const IG::Ray& r = settings.rays[i];
-            const float dx = r.Direction.v[0], dy = r.Direction.v[1], dz = r.Direction.v[2];
+            const float dx = r.Direction(0), dy = r.Direction(1), dz = r.Direction(2);
             const float n = std::sqrt(dx * dx + dy * dy + dz * dz);
             igb200_ray& o = rays[i];
-            o.org[0] = r.Origin.v[0]; o.org[1] = r.Origin.v[1]; o.org[2] = r.Origin.v[2];
+            o.org[0] = r.Origin(0); o.org[1] = r.Origin(1); o.org[2] = r.Origin(2);
             o.dir[0] = dx / n; o.dir[1] = dy / n; o.dir[2] = dz / n;
-            o.tmin = r.Range.v[0]; o.tmax = r.Range.v[1];
+            o.tmin = r.Range(0); o.tmax = r.Range(1);
         }
         rc = igb200_render(mCtx, &st, rays.data(), rays.size());
         mWidth = settings.width; mHeight = 1;
@@ -199,11 +199,21 @@ size_t B200Device::getBufferSizeInBytes(const std::string&) { return 0; }
 bool B200Device::copyBufferToHost(const std::string& name, void*, size_t) { error("buffer '" + name + "' does not exist on this device"); return false; }
 IG::IRenderDevice::BufferAccessor B200Device::getBufferForDevice(const std::string&) { return BufferAccessor{nullptr, 0}; }
 
+// Device.cpp:1762-1771. The reference's Statistics keeps its counters private (the runtime merges and prints them), so the device
+// refills the object from the device-side totals; rayCounters() is the same figures for callers without the class.
 const IG::Statistics* B200Device::getStatistics() {
-    uint64_t s[5]; double ms = 0;
-    if (!mCtx || igb200_stats(mCtx, s, &ms) != 0) return nullptr;
-    mStats.CameraRayCount = s[0]; mStats.ShadowRayCount = s[1]; mStats.BounceRayCount = s[2]; mStats.RenderMilliseconds = ms;
+    uint64_t s[3]; double ms = 0;
+    if (!rayCounters(s, &ms)) return nullptr;
+    mStats.reset();
+    mStats.increase(IG::Quantity::CameraRayCount, s[0]); mStats.increase(IG::Quantity::ShadowRayCount, s[1]); mStats.increase(IG::Quantity::BounceRayCount, s[2]);
     return &mStats;
+}
+bool B200Device::rayCounters(uint64_t out[3], double* render_ms) {
+    uint64_t s[5]; double ms = 0;
+    if (!mCtx || igb200_stats(mCtx, s, &ms) != 0) return false;
+    out[0] = s[0]; out[1] = s[1]; out[2] = s[2];
+    if (render_ms) *render_ms = ms;
+    return true;
 }
 
 // Post kernels are outside the hot path: reported, never silently emulated.

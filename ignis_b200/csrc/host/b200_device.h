@@ -61,6 +61,7 @@ public:
 
     // device-specific (no reference counterpart): multi-GPU tile partition, see include/igb200.h
     bool setPartition(int rank, int world, int tile);
+    bool rayCounters(uint64_t out[3], double* render_ms = nullptr);   // camera, shadow, bounce rays since the last reset
     igb200_ctx* context() { return mCtx; }
     const std::string& lastError() const { return mError; }
 
@@ -84,7 +85,7 @@ private:
 class B200DeviceInterface : public IG::IDeviceInterface {
 public:
     IG::Build::Version getVersion() const override { return IG::Build::Version{IGB200_VERSION_MAJOR, IGB200_VERSION_MINOR}; }
-    IG::GPUArchitecture getArchitecture() const override { return IG::GPUArchitecture::Nvidia; }
+    IG::TargetArchitecture getArchitecture() const override { return IG::TargetArchitecture{IG::GPUArchitecture::Nvidia}; }   // it replaces ig_device_cuda (Target.h:7-21)
     IG::IRenderDevice* createRenderDevice(const IG::IRenderDevice::SetupSettings& settings) const override;
     IG::ICompilerDevice* createCompilerDevice() const override { return new B200CompilerDevice(); }
 };

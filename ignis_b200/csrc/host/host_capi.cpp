@@ -21,7 +21,7 @@ ICompilerDevice* compiler() { static std::unique_ptr<ICompilerDevice> c(ig_get_i
 extern "C" {
 
 const char* igbh_last_error() { return igbh::last_error().c_str(); }
-int igbh_interface_version(int* major, int* minor) { const Build::Version v = ig_get_interface()->getVersion(); *major = (int)v.Major; *minor = (int)v.Minor; return ig_get_interface()->getArchitecture() == GPUArchitecture::Nvidia ? 0 : -1; }
+int igbh_interface_version(int* major, int* minor) { const Build::Version v = ig_get_interface()->getVersion(); *major = (int)v.Major; *minor = (int)v.Minor; return ig_get_interface()->getArchitecture() == TargetArchitecture{GPUArchitecture::Nvidia} ? 0 : -1; }
 
 // ---- SceneDatabase
 SceneDatabase* igbh_db_create() { return new SceneDatabase(); }
@@ -46,7 +46,7 @@ void igbh_db_set_bvh(SceneDatabase* db, int provider, const uint8_t* leaves, siz
     db->SceneBVHs[std::string_view(names[provider ? 1 : 0])] = std::move(b);
 }
 void igbh_db_set_bbox(SceneDatabase* db, const float mn[3], const float mx[3], size_t materials) {
-    for (int k = 0; k < 3; ++k) { db->SceneBBox.min.v[k] = mn[k]; db->SceneBBox.max.v[k] = mx[k]; }
+    for (int k = 0; k < 3; ++k) { db->SceneBBox.min(k) = mn[k]; db->SceneBBox.max(k) = mx[k]; }
     db->MaterialCount = materials;
 }
 
@@ -55,8 +55,8 @@ ParameterSet* igbh_params_create() { return new ParameterSet(); }
 void igbh_params_destroy(ParameterSet* p) { delete p; }
 void igbh_params_set_int(ParameterSet* p, const char* k, int v) { p->IntParameters[k] = v; }
 void igbh_params_set_float(ParameterSet* p, const char* k, float v) { p->FloatParameters[k] = v; }
-void igbh_params_set_vec3(ParameterSet* p, const char* k, const float v[3]) { p->VectorParameters[k] = Vector3f{{v[0], v[1], v[2]}}; }
-void igbh_params_set_color(ParameterSet* p, const char* k, const float v[4]) { p->ColorParameters[k] = Vector4f{{v[0], v[1], v[2], v[3]}}; }
+void igbh_params_set_vec3(ParameterSet* p, const char* k, const float v[3]) { p->VectorParameters[k] = Vector3f(v[0], v[1], v[2]); }
+void igbh_params_set_color(ParameterSet* p, const char* k, const float v[4]) { p->ColorParameters[k] = Vector4f(v[0], v[1], v[2], v[3]); }
 
 // ---- ICompilerDevice
 void* igbh_compile(const char* script, const char* function) { return compiler()->compileAndGet(ICompilerDevice::Settings{}, script, function); }
@@ -101,7 +101,7 @@ void igbh_set_add_hit(ShaderSet* s, void* stage, ParameterSet* local) { s->set.H
 
 // ---- IRenderDevice
 IRenderDevice* igbh_device_create(int cuda_device) {
-    IRenderDevice::SetupSettings st; st.target.dev = (size_t)cuda_device;
+    IRenderDevice::SetupSettings st; st.target = Target::makeGPU(GPUArchitecture::Nvidia, (size_t)cuda_device);
     IRenderDevice* d = ig_get_interface()->createRenderDevice(st);
     if (!d) igbh::set_last_error(igb200_last_error());
     return d;
@@ -120,7 +120,7 @@ int igbh_device_render(IRenderDevice* d, ShaderSet* s, ParameterSet* global, int
     rs.spi = (size_t)spi; rs.width = (size_t)width; rs.height = (size_t)height; rs.iteration = (size_t)iteration; rs.frame = (size_t)frame; rs.user_seed = (size_t)seed;
     std::vector<Ray> r(n_rays);
     if (rays) {
-        for (size_t i = 0; i < n_rays; ++i) { const float* p = rays + 8 * i; r[i] = Ray{{{p[0], p[1], p[2]}}, {{p[3], p[4], p[5]}}, {{p[6], p[7]}}}; }
+        for (size_t i = 0; i < n_rays; ++i) { const float* p = rays + 8 * i; r[i] = Ray{Vector3f(p[0], p[1], p[2]), Vector3f(p[3], p[4], p[5]), Vector2f(p[6], p[7])}; }
         rs.rays = r.data(); rs.width = n_rays; rs.height = 1;
     }
     igbh::B200Device* bd = static_cast<igbh::B200Device*>(d);
@@ -137,10 +137,8 @@ float* igbh_device_framebuffer(IRenderDevice* d, const char* name) {
 }
 void igbh_device_clear(IRenderDevice* d) { d->clearAllFramebuffer(); }
 int igbh_device_stats(IRenderDevice* d, uint64_t out[3]) {
-    const Statistics* s = d->getStatistics();
-    if (!s) return -1;
-    out[0] = s->CameraRayCount; out[1] = s->ShadowRayCount; out[2] = s->BounceRayCount;
-    return 0;
+    if (!d->getStatistics()) return -1;   // the interface call (its counters are private, as in the reference) ...
+    return static_cast<igbh::B200Device*>(d)->rayCounters(out) ? 0 : -1;   // ... and the figures it was filled from
 }
 
 }  // extern "C"

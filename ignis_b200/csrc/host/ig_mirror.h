@@ -6,12 +6,16 @@
 // generated `generated_interface.h`, none of which exist in this container, so this file restates ONLY the types that
 // cross the boundary on the `path` hot path, with the reference's names, member names and meaning. Inside the reference's
 // build tree, define IGB200_WITH_IGNIS and the real headers are used instead; `namespace IG` is the
-// same in both cases, so b200_device.cpp compiles unchanged.
+// same in both cases and the restated types offer the members of the real ones that the host layer touches (Eigen's
+// `v(i)` / `x()` accessors, `Statistics::reset / increase`, `TargetArchitecture`), so b200_device.cpp and
+// script_recognizer.cpp compile unchanged against either -- tests/test_plugin_real_headers.py type-checks them against the
+// reference's own headers (g++ -std=c++20 -fsyntax-only -DIGB200_WITH_IGNIS -I<reference>/src/runtime).
 #pragma once
 
 #ifdef IGB200_WITH_IGNIS
 #include "device/IDeviceInterface.h"
 #include "table/SceneDatabase.h"
+#include "Statistics.h"
 #else
 
 #include <array>
@@ -21,6 +25,7 @@
 #include <string>
 #include <string_view>
 #include <unordered_map>
+#include <variant>
 #include <vector>
 
 namespace IG {
@@ -30,10 +35,21 @@ using int32 = int32_t;
 using uint32 = uint32_t;
 using uint64 = uint64_t;
 
-// Stand-ins for the Eigen vectors of the reference (same storage: packed floats)
-struct Vector2f { float v[2]; float x() const { return v[0]; } float y() const { return v[1]; } };
-struct Vector3f { float v[3]; float x() const { return v[0]; } float y() const { return v[1]; } float z() const { return v[2]; } };
-struct Vector4f { float v[4]; float x() const { return v[0]; } float y() const { return v[1]; } float z() const { return v[2]; } float w() const { return v[3]; } };
+// Stand-ins for the Eigen vectors of the reference (same storage: packed floats; the accessors are Eigen's: v(i), v[i], x() ...)
+template <int N> struct VecNf {
+    float m[N] = {};
+    VecNf() = default;
+    VecNf(float a, float b) : m{a, b} { static_assert(N == 2, "size"); }
+    VecNf(float a, float b, float c) : m{a, b, c} { static_assert(N == 3, "size"); }
+    VecNf(float a, float b, float c, float d) : m{a, b, c, d} { static_assert(N == 4, "size"); }
+    static VecNf Zero() { return VecNf(); }
+    float& operator()(std::ptrdiff_t i) { return m[i]; }
+    float operator()(std::ptrdiff_t i) const { return m[i]; }
+    float& operator[](std::ptrdiff_t i) { return m[i]; }
+    float operator[](std::ptrdiff_t i) const { return m[i]; }
+    float x() const { return m[0]; } float y() const { return m[1]; } float z() const { return m[2]; } float w() const { return m[3]; }
+};
+using Vector2f = VecNf<2>; using Vector3f = VecNf<3>; using Vector4f = VecNf<4>;
 
 // src/runtime/RuntimeStructs.h:39-43
 struct Ray { Vector3f Origin; Vector3f Direction; Vector2f Range; };
@@ -86,11 +102,15 @@ struct SceneDatabase {
 
 // src/runtime/device/Target.h:7-21 (only what a plugin answers with)
 enum class GPUArchitecture { AMD_HSA, Intel, Nvidia, Unknown };
+enum class CPUArchitecture { ARM, X86, Unknown };
+using TargetArchitecture = std::variant<CPUArchitecture, GPUArchitecture>;
 struct Target {
     bool gpu = true; GPUArchitecture arch = GPUArchitecture::Nvidia; size_t dev = 0;
     bool isGPU() const { return gpu; }
     GPUArchitecture gpuArchitecture() const { return arch; }
     size_t device() const { return dev; }
+    void setDevice(size_t d) { dev = d; }
+    static Target makeGPU(GPUArchitecture a, size_t device) { Target t; t.gpu = true; t.arch = a; t.dev = device; return t; }
 };
 
 // src/runtime/technique/TechniqueVariant.h:5-35
@@ -105,19 +125,25 @@ template <typename T> struct TechniqueVariantBase {
 using TechniqueVariantShaderSet = TechniqueVariantBase<void*>;
 struct TechniqueVariantInfo { bool UsesLights = true; size_t PrimaryPayloadCount = 6, SecondaryPayloadCount = 0; };   // technique/TechniqueInfo.h (fields used here)
 
-// src/runtime/Statistics.h:57-64 (the ray counters; the rest of the class is host-side bookkeeping)
+// src/runtime/Statistics.h:57-64,69-105 (the ray counters; the rest of the class is host-side bookkeeping). As in the reference the
+// counters are private: the runtime only ever merges (`add`) and prints (`dump`) them.
+enum class Quantity { CameraRayCount = 0, ShadowRayCount, BounceRayCount, _COUNT };
 class Statistics {
 public:
-    uint64 CameraRayCount = 0, ShadowRayCount = 0, BounceRayCount = 0;
-    double RenderMilliseconds = 0;
-    uint64 primaryRays() const { return CameraRayCount + BounceRayCount; }               // Statistics.cpp:286-290
-    uint64 totalRays() const { return CameraRayCount + BounceRayCount + ShadowRayCount; }
+    void reset() { *this = Statistics(); }
+    void increase(Quantity quantity, uint64 value) { mQuantities[(size_t)quantity] += value; }
+    void add(const Statistics& other) { for (size_t i = 0; i < mQuantities.size(); ++i) mQuantities[i] += other.mQuantities[i]; }
+private:
+    std::array<uint64, (size_t)Quantity::_COUNT> mQuantities{};
 };
 
 struct TonemapSettings; struct ImageInfoSettings;
-struct ImageInfoOutput { float Min = 0, Max = 0, Average = 0; };
+struct ImageInfoOutput { float Min, Max, Average, SoftMin, SoftMax, Median; int InfCount, NaNCount, NegCount; };   // RuntimeStructs.h:27-37
 
-namespace Build { struct Version { uint32 Major, Minor; uint32 asNumber() const { return (Major << 16) | Minor; } }; }
+namespace Build {   // src/runtime/config/Build.h:6-13
+struct Version { uint32 Major, Minor; uint32 asNumber() const { return (Major << 8) | Minor; } };
+inline bool operator==(const Version& a, const Version& b) { return a.asNumber() == b.asNumber(); }
+}
 
 // src/runtime/device/IRenderDevice.h:14-81
 class IRenderDevice {
@@ -176,7 +202,7 @@ class IDeviceInterface {
 public:
     virtual ~IDeviceInterface() = default;
     virtual Build::Version getVersion() const = 0;
-    virtual GPUArchitecture getArchitecture() const = 0;   // the reference returns std::variant<CPU, GPU>; a GPU plugin always holds the GPU alternative
+    virtual TargetArchitecture getArchitecture() const = 0;
     virtual IRenderDevice* createRenderDevice(const IRenderDevice::SetupSettings& settings) const = 0;
     virtual ICompilerDevice* createCompilerDevice() const = 0;
 };

@@ -364,8 +364,8 @@ struct Eval {
                 auto dyn = [](Val v) { v.known = false; return v; };
                 if (ty == "i32") { const auto it = ps->IntParameters.find(key); if (it != ps->IntParameters.end()) return dyn(Val::num((float)it->second)); }
                 else if (ty == "f32") { const auto it = ps->FloatParameters.find(key); if (it != ps->FloatParameters.end()) return dyn(Val::num(it->second)); }
-                else if (ty == "vec3") { const auto it = ps->VectorParameters.find(key); if (it != ps->VectorParameters.end()) return dyn(Val::vec(it->second.v[0], it->second.v[1], it->second.v[2])); }
-                else if (ty == "color") { const auto it = ps->ColorParameters.find(key); if (it != ps->ColorParameters.end()) return dyn(Val::vec(it->second.v[0], it->second.v[1], it->second.v[2])); }
+                else if (ty == "vec3") { const auto it = ps->VectorParameters.find(key); if (it != ps->VectorParameters.end()) return dyn(Val::vec(it->second(0), it->second(1), it->second(2))); }
+                else if (ty == "color") { const auto it = ps->ColorParameters.find(key); if (it != ps->ColorParameters.end()) return dyn(Val::vec(it->second(0), it->second(1), it->second(2))); }
                 else fail("unsupported registry type in " + fn);
             }
             if (a.size() < 2) fail(fn + ": default value expected");
@@ -461,8 +461,8 @@ igb200_material resolve_material(const StageDescriptor& hit, const Registries& r
     } else if (b.name == "make_conductor_bsdf") {   // ConductorBSDF.cpp:13-35; bsdf/conductor.art:2-27,131-141
         const Val& md = ctor_arg(b, 4);
         if (md.kind != Val::Ctor || md.name != "microfacet::make_delta_distribution") fail("rough conductor BSDFs are not supported by this device");
-        const Val& eta = as_vec(ctor_arg(b, 1), "conductor eta");
-        const Val& kk = as_vec(ctor_arg(b, 2), "conductor k");
+        const Val eta = as_vec(ctor_arg(b, 1), "conductor eta");
+        const Val kk = as_vec(ctor_arg(b, 2), "conductor k");
         m.bsdf = IGB200_BSDF_CONDUCTOR;
         put3(m.p, eta); put3(m.p + 3, kk);
         put3(m.p + 6, as_vec(ctor_arg(b, 3), "specular_reflectance"));
