@@ -98,6 +98,18 @@ __global__ void k_publish(float* __restrict__ acc, float* __restrict__ slot, flo
     }
 }
 
+// Deterministic accumulation: folds the per-sample slots of one iteration into the frame in sample order and clears them. One thread per
+// word of the frame; the additions of a pixel happen in one thread in a fixed order, so the frame is a pure function of the inputs.
+__global__ void k_resolve(float* __restrict__ frame, float* __restrict__ slots, long long n_pixels, int spi) {
+    const long long n = n_pixels * 3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / 3; const int ch = (int)(i - p * 3);
+        float acc = frame[i];
+        for (int s = 0; s < spi; ++s) { float* w = slots + (p * spi + s) * 3 + ch; acc += *w; *w = 0.0f; }
+        frame[i] = acc;
+    }
+}
+
 __global__ void k_detmath(int fn, const float* a, const float* b, float* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -223,6 +235,9 @@ struct igb200_ctx {
     std::vector<Timed> timed;
     double prof_ms[4] = {0, 0, 0, 0}; uint64_t prof_n[4] = {0, 0, 0, 0};
     DevBuf<igb200_ray> list_rays;
+    // deterministic accumulation (option "deterministic"): per-sample slots for the colour buffer and the two standard AOVs
+    bool deterministic = false;
+    DevBuf<float> det_slots, det_aov[2];
     // frame streaming (igb200_frame_stream_*): per-iteration framebuffer slots + in-order publication of finished frames
     bool fs_on = false;
     int fs_slots = 0;                               // ring size (power of two)
@@ -325,7 +340,7 @@ static WaveParams make_params(igb200_ctx* c, const RenderParams& rp, const DevSc
     P.sc.full = (c->scene_full || rp.aov_normals != nullptr) ? 1 : 0;
     P.q[0] = c->qa.view(); P.q[1] = c->qb.view();
     P.sq = ShadowQueue{c->sq_org.p, c->sq_dir.p, c->sq_col.p};
-    P.fb = P.rp.ring_stride ? c->fs_ring.p : c->fb.p; P.ctl = c->control.p;
+    P.fb = P.rp.det ? c->det_slots.p : P.rp.ring_stride ? c->fs_ring.p : c->fb.p; P.ctl = c->control.p;
     P.total = total; P.capacity = (int)c->capacity; P.list_rays = d_rays;
     P.stage_nodes = c->stage_nodes; P.stage_tris = c->stage_tris; P.stage_ent = c->stage_ent;
     P.refill = c->refill; P.defer = defer;
@@ -426,6 +441,7 @@ static int ensure_tile_table(igb200_ctx* c, int W, int H) {
 
 // iterations per launch: enough to generate ~8 M camera rays, at most 8 (option "fuse" overrides)
 static int fuse_factor(const igb200_ctx* c, const igb200_settings* st) {
+    if (c->deterministic) return 1;   // every iteration is resolved on its own
     if (c->fuse > 0) return c->fuse;
     const long long cam_rays = std::max<long long>((long long)st->width * st->height * st->spi / std::max(c->world, 1), 1);
     return (int)std::min<long long>(8, std::max<long long>(1, ((long long)1 << 23) / cam_rays));
@@ -548,6 +564,14 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "bin_materials")) { if (value < -1 || value > 2) return fail(-1, "bin_materials must be -1 (automatic), 0, 1 or 2"); c->bin_materials = (int)value; return 0; }
+    if (!strcmp(name, "deterministic")) {
+        // Same inputs => bit-identical frame, whatever the spi (src/tests/integrator/test_reproducibility.py:5-11; the reference's CPU device adds
+        // without atomics, driver/accumulator.art:4-21). Costs one slot per sample (12 B x W x H x spi) and the deferred tail / fused iterations.
+        if (c->fs_on && value) return fail(-1, "deterministic accumulation and frame streaming exclude each other (end the frame stream first)");
+        c->deterministic = value != 0;
+        if (!c->deterministic) { c->det_slots.release(); c->det_aov[0].release(); c->det_aov[1].release(); }
+        return 0;
+    }
     if (!strcmp(name, "fuse")) { if (value < 0 || value > 64) return fail(-1, "fuse must be in [0, 64]"); c->fuse = (int)value; return 0; }
     if (!strcmp(name, "split_turns")) { if (value < -1 || value > 64) return fail(-1, "split_turns must be in [-1, 64] (-1: chosen from the number of camera rays)"); c->split_turns = (int)value; return 0; }
     if (!strcmp(name, "turn_shade_blocks")) {
@@ -1147,6 +1171,14 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
     rp.inv_spi = 1 / (float)st->spi;
     { const int r = ensure_aovs(c); if (r) return r; }
     rp.aov_normals = (c->std_aovs && !rays) ? c->aov[0].p : nullptr; rp.aov_albedo = (c->std_aovs && !rays) ? c->aov[1].p : nullptr;
+    rp.det = c->deterministic ? 1 : 0;
+    if (rp.det) {   // one slot per sample; allocated zeroed, k_resolve leaves them zeroed
+        if (n_iter != 1) return fail(-1, "igb200_render: deterministic accumulation renders one iteration per launch");
+        const size_t n_slots = (size_t)W * H * st->spi * 3;
+        auto want = [&](DevBuf<float>& b) -> int { if (b.n == n_slots) return 0; { const int r = sync_control(c); if (r) return r; } CU(b.alloc(n_slots)); CU(cudaMemset(b.p, 0, n_slots * sizeof(float))); return 0; };
+        { const int r = want(c->det_slots); if (r) return r; }
+        if (rp.aov_normals) { for (int k = 0; k < 2; ++k) { const int r = want(c->det_aov[k]); if (r) return r; } rp.aov_normals = c->det_aov[0].p; rp.aov_albedo = c->det_aov[1].p; }
+    }
     if (rays) { rp.tile_w = W; rp.tile_h = 1; rp.rank = 0; rp.world = 1; }
     else { rp.tile_w = c->tile; rp.tile_h = c->tile; rp.rank = c->rank; rp.world = c->world; }
     rp.tiles_x = (W + rp.tile_w - 1) / rp.tile_w;
@@ -1197,7 +1229,7 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
     // With a deferred tail the launch returns once at most `defer` paths are alive; they continue in the next launch or in
     // a drain launch. The queues are sized so that the carried records and all new camera rays fit the first turn.
     const long long cam_rays = (long long)W * H * st->spi / std::max(rp.world, 1) * n_iter;
-    const long long want_defer = rays ? 0 : cam_rays * c->defer_permille / 1000;
+    const long long want_defer = (rays || rp.det) ? 0 : cam_rays * c->defer_permille / 1000;   // deterministic: every path ends inside its own launch
     // queues sized for a full batch of fused iterations from the start (a reallocation costs tens of milliseconds)
     const int f_full = rays ? 1 : std::max(n_iter, fuse_factor(c, st));
     const size_t need = (size_t)std::max<long long>((total / n_iter + want_defer / n_iter) * f_full, 1);
@@ -1222,6 +1254,12 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
     const int split_turns = c->split_turns >= 0 ? c->split_turns : (int)std::min<long long>(4, std::max<long long>(1, cam_rays >> 19));
     if (!rays) { const int r = launch_split_turns(c, make_params(c, rp, sc, total, nullptr, defer), split_turns); if (r) return r; }
     { const int r = launch_wave(c, rp, sc, total, d_rays, defer); if (r) return r; }
+    if (rp.det) {
+        k_resolve<<<c->n_sm * 8, 256, 0, c->stream>>>(c->fb.p, c->det_slots.p, (long long)W * H, st->spi);
+        if (rp.aov_normals && st->iter == 0) for (int k = 0; k < 2; ++k) k_resolve<<<c->n_sm * 8, 256, 0, c->stream>>>(c->aov[k].p, c->det_aov[k].p, (long long)W * H, st->spi);
+        CU(cudaGetLastError());
+        c->launches += 1;
+    }
     c->maybe_carry = defer > 0; c->last_defer = defer;
     c->carry_settings = *st; c->carry_settings.width = W; c->carry_settings.height = H; c->carry_settings.iter = st->iter + n_iter - 1;
     c->carry_rank = rp.rank; c->carry_world = rp.world; c->carry_tile = rp.tile_w;
@@ -1527,6 +1565,7 @@ static int fs_publish(igb200_ctx* c, bool all) {
 int igb200_frame_stream_begin(igb200_ctx* c, int slots) {
     if (!c) return fail(-1, "null context");
     if (c->fs_on) return fail(-1, "igb200_frame_stream_begin: already streaming");
+    if (c->deterministic) return fail(-1, "igb200_frame_stream_begin: frame streaming and deterministic accumulation exclude each other");
     if (!c->fb.p) return fail(-1, "igb200_frame_stream_begin: no framebuffer (call igb200_resize first)");
     if ((long long)c->width * c->height >= (1ll << 24)) return fail(-4, "igb200_frame_stream_begin: frames of 2^24 pixels and more are not supported (the slot rides in the shadow ray's pixel word)");
     if (slots <= 0) slots = 16;

@@ -453,6 +453,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
     const int ray_id = (int)st.x;
     const int sample = ray_id % rp.spi;
     const int pixel = ray_id / rp.spi;
+    const int target = rp.det ? ray_id : pixel;   // where this path's radiance goes: its pixel, or its own slot (deterministic accumulation)
     const int depth = (int)(st.z & 0xFFu);
     const int iter = (int)(st.z >> 8);   // the iteration that generated the path: it may be shaded by a later launch (deferred tail)
     const float eta = __uint_as_float(st.w);
@@ -485,7 +486,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
             const float mis = nee ? 1 / (1 + inv_pdf * sel_pdf * pdf_s) : 1.0f;
             color = cadd(color, handle_color(sc, cmulf(cmul(contrib, emit), mis)));
         }
-        if (inflights > 0) { splat(fb, pixel, color, rp.inv_spi); ++n_splat; }
+        if (inflights > 0) { splat(fb, target, color, rp.inv_spi); ++n_splat; }
     } else {
         const float4 hh = q.hit[i];
         const int prim = __float_as_int(hh.w);
@@ -559,8 +560,8 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
             }
             else if (m2.w != 0.0f) albedo = c_ks;                                                               // conductor.art:9 (ks)
             else { const float ci = dot(neg(rdir), bN); albedo = cmul(c_ks, c3(conductor_factor(m0.z, m1.y, ci), conductor_factor(m0.w, m1.z, ci), conductor_factor(m1.x, m1.w, ci))); }   // conductor.art:28-38
-            splat(rp.aov_normals, pixel, c3(N.x, N.y, N.z), rp.inv_spi);
-            splat(rp.aov_albedo, pixel, c3(fminf(albedo.r, 1.0f), fminf(albedo.g, 1.0f), fminf(albedo.b, 1.0f)), rp.inv_spi);   // color_saturate(albedo, 1)
+            splat(rp.aov_normals, target, c3(N.x, N.y, N.z), rp.inv_spi);
+            splat(rp.aov_albedo, target, c3(fminf(albedo.r, 1.0f), fminf(albedo.g, 1.0f), fminf(albedo.b, 1.0f)), rp.inv_spi);   // color_saturate(albedo, 1)
         }
         // ---- on_hit, pathtracer.art:119-139
         if (light_id >= 0 && surf.is_entering) {
@@ -586,7 +587,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
                 const float pdf_s = pdf_as_solid(pdf, dt, dist * dist);
                 const float sel_pdf = (!FULL || sc.selector == 0) ? pdf_lights : selector_pdf(sc.selector_data, sc.selector, sc.n_inf, sc.n_fin, 0, light_id, rorg.x, rorg.y, rorg.z);
                 const float mis = nee ? 1 / (1 + inv_pdf * sel_pdf * pdf_s) : 1.0f;
-                splat(fb, pixel, handle_color(sc, cmulf(cmul(contrib, intensity), mis)), rp.inv_spi); ++n_splat;
+                splat(fb, target, handle_color(sc, cmulf(cmul(contrib, intensity), mis)), rp.inv_spi); ++n_splat;
             }
         }
         const V3 out_dir = neg(rdir);
@@ -621,7 +622,7 @@ __device__ __forceinline__ int shade_record(const DevScene& sc, const RenderPara
                     const int ss = coalesced_append(sink.shadow_count);
                     sink.sq.org_tmin[ss] = make_float4(surf.point.x, surf.point.y, surf.point.z, 0.001f);
                     sink.sq.dir_tmax[ss] = make_float4(s_dir.x, s_dir.y, s_dir.z, s_tmax);
-                    sink.sq.color_pix[ss] = make_float4(cc.r, cc.g, cc.b, __int_as_float(pixel | ((iter & rp.ring_mask) << 24)));   // ring_mask != 0 only if W * H < 2^24
+                    sink.sq.color_pix[ss] = make_float4(cc.r, cc.g, cc.b, __int_as_float(target | ((iter & rp.ring_mask) << 24)));   // ring_mask != 0 only if W * H < 2^24
                 }
             }
         }

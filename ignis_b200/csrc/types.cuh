@@ -52,6 +52,9 @@ struct RenderParams {
     // Frame streaming (api.cu igb200_frame_stream_*): every iteration splats into its own slot `iter & ring_mask` of a ring of framebuffers
     // (ring_stride floats apart), so that a frame can be handed out while later iterations are already in flight. 0 / 0: one framebuffer.
     int ring_mask; long long ring_stride;
+    // Deterministic accumulation (api.cu option "deterministic"): contributions go to a slot per SAMPLE (index = ray id) instead of the
+    // pixel, so no two threads ever add to the same word; k_resolve then folds the slots into the frame in sample order.
+    int det;
 };
 
 struct PrimaryQueue {
