@@ -50,9 +50,10 @@ WORKLOADS = {
 B_PRIMARY, B_SHADOW, B_SPLAT = 216, 108, 24
 # the same figure split by pipeline stage (DESIGN.md "Algorithmic bytes")
 # dram__bytes_read.sum + dram__bytes_write.sum per k_turn_trace launch of this workload (ncu --set full, profiles/)
-NCU_TRAFFIC_BYTES = 5.385e8
-NCU_TRAFFIC_SOURCE = ("profiles/r3d_k_turn_trace_full.csv: dram read + write of the three k_turn_trace launches of the first iteration "
-                      "(436 + 749 + 430 MB) / 3; later iterations also trace the carried paths, hence the larger algorithmic figure")
+NCU_TRAFFIC_BYTES = 5.383e8
+NCU_TRAFFIC_SOURCE = ("profiles/r5a_k_turn_trace_full.csv (re-measured this round on the merged-tree kernel k_turn_trace<256,3,2,1,1>): dram read + write "
+                      "of the three k_turn_trace launches of the first iteration (437 + 749 + 428 MB) / 3; later iterations also trace the carried "
+                      "paths, hence the larger algorithmic figure")
 B_STAGE = {"generate": 68, "traverse_primary": 60, "shade_read": 88, "shade_bounce_write": 68, "shade_shadow_write": 56,
            "traverse_secondary": 52}
 
@@ -412,7 +413,7 @@ def run_b200(args):
             kbytes = (B_STAGE["traverse_primary"] * w_["primary"] + B_STAGE["traverse_secondary"] * w_["shadow"] + B_SPLAT * w_["splats"]) / n_l
             ach = kbytes / (avg_ms * 1e-3) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES,
-                                "kernel": "k_turn_trace<256,3,2,1> (scene staged in shared memory; closest-hit + any-hit/splat phase of a split wavefront turn)",
+                                "kernel": "k_turn_trace<256,3,2,1,1> (merged single-level tree staged in shared memory; closest-hit + any-hit/splat phase of a split wavefront turn)",
                                 "avg_launch_ms": avg_ms, "launches": n_l, "share_of_step": kern["k_turn_trace"]["ms"] / total_ms,
                                 "algorithmic_bytes_per_launch": kbytes, "rays_per_launch": (w_["primary"] + w_["shadow"]) / n_l,
                                 "peak_source": peak_src, "traffic_source": NCU_TRAFFIC_SOURCE,

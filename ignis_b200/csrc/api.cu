@@ -48,6 +48,9 @@ static WaveKernel turn_shade_kernel(int blocks, bool full) {
 // where: 1 the whole scene is staged in shared memory (shared-memory loads without range checks: -6 % trace time on diamond_scene
 // and cbox), 0 decided per index (traverse.cuh node_ptr). Specialised for the default scheduling (vote 2) only. An "everything in
 // global memory" variant (2) was measured too: +1 to +2.5 % (more spills), so unstaged scenes use the generic kernel.
+// The merged-tree kernel of small scenes with its ray records staged through shared memory (wavefront.cuh phase_trace_staged): CTAs of
+// 384 threads x 2 per SM or 768 x 1 (option "flat_block"), 256 = the unstaged kernel
+static WaveKernel flat_staged_kernel(int block) { return block == 768 ? k_turn_trace<768, 1, 2, 1, true, true> : k_turn_trace<384, 2, 2, 1, true, true>; }
 static WaveKernel turn_trace_kernel(int blocks, int vote, int where, bool flat = false) {
     if (flat) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 1, true> : k_turn_trace<WF_BLOCK, 2, 2, 1, true>;   // merged tree (small scenes, staged)
     if (vote && where == 1) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 1> : k_turn_trace<WF_BLOCK, 2, 2, 1>;
@@ -171,6 +174,13 @@ struct igb200_ctx {
     int flat_option = 1;               // option "flat": 0 = always walk the two-level tree
     bool flat_on = false;              // the split-turn trace kernel and the trace hooks walk the merged tree
     size_t smem_flat = 0;
+    // option "flat_block": 384 | 768 = the merged-tree trace kernel with its ray records staged through shared memory by TMA (CTAs of that size),
+    // 256 = records read from global memory. Measured (profiles/r5b_staged_rays.txt): the staged kernel is SLOWER (diamond_scene trace 3.56 ->
+    // 4.12 / 3.84 ms per step, cbox 2.44 -> 2.79) although it removes the long-scoreboard stalls of the refill (a quarter of the stall samples):
+    // the other warps were covering them, and a swap every 32 rays costs more issue slots than the stalls did. Kept as an option, off.
+    int flat_block_option = WF_BLOCK;
+    int flat_block = WF_BLOCK;         // what runs: WF_BLOCK = the unstaged kernel
+    size_t smem_flat_staged = 0;
     DevBuf<int4> shape_info;
     DevBuf<float> inf_lights, fin_lights, selector_data, textures, aux_data;
     DevBuf<int4> images;
@@ -313,6 +323,17 @@ static int configure_kernels(igb200_ctx* c) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbf, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, 1, true), WF_BLOCK, c->smem_flat));
         if (nbf < c->turn_trace_blocks) c->flat_on = false;   // would cost occupancy: keep the two-level walk
         else c->grid_turn_trace_flat = nbf * c->n_sm;
+        c->flat_block = WF_BLOCK;
+        if (c->flat_on && c->flat_block_option != WF_BLOCK) {   // ray records staged through shared memory, if the larger CTA fits as often as it must
+            const int blk = c->flat_block_option, want = blk == 768 ? 1 : 2;
+            const size_t scene = ((size_t)s.n_ent * 128 + (size_t)s.n_flat_nodes * 256 + (size_t)s.n_tris * 48 + 127) & ~(size_t)127;
+            const size_t smem = (size_t)SMEM_STACK * blk * sizeof(uint2) + scene + (size_t)(blk / 32) * STAGE_WARP_BYTES;
+            int nbs = 0;
+            if (cudaFuncSetAttribute((const void*)flat_staged_kernel(blk), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbs, (const void*)flat_staged_kernel(blk), blk, smem) == cudaSuccess && nbs >= want) {
+                c->flat_block = blk; c->smem_flat_staged = smem; c->grid_turn_trace_flat = want * c->n_sm;
+            } else cudaGetLastError();   // does not fit: the unstaged kernel stays
+        }
     }
     if (c->carveout >= 0) {
         CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where), cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout));
@@ -411,7 +432,8 @@ static int launch_split_turns(igb200_ctx* c, const WaveParams& P, int turns) {
         turn_shade_kernel(c->turn_shade_blocks, P.sc.full != 0)<<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
         { const int r = prof_end(c); if (r) return r; }
         { const int r = prof_begin(c, 1); if (r) return r; }
-        if (c->flat_on) turn_trace_kernel(c->turn_trace_blocks, c->vote, 1, true)<<<c->grid_turn_trace_flat, WF_BLOCK, c->smem_flat, c->stream>>>(P);
+        if (c->flat_on && c->flat_block != WF_BLOCK) flat_staged_kernel(c->flat_block)<<<c->grid_turn_trace_flat, c->flat_block, c->smem_flat_staged, c->stream>>>(P);
+        else if (c->flat_on) turn_trace_kernel(c->turn_trace_blocks, c->vote, 1, true)<<<c->grid_turn_trace_flat, WF_BLOCK, c->smem_flat, c->stream>>>(P);
         else turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
         { const int r = prof_end(c); if (r) return r; }
         { const int r = prof_begin(c, 3); if (r) return r; }
@@ -560,6 +582,12 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "std_aovs")) { c->std_aovs = value != 0; CU(cudaSetDevice(c->device)); return ensure_aovs(c); }
     if (!strcmp(name, "flat")) {   // 0: never walk the merged tree. Takes effect at the next igb200_set_scene (the tree is built there) or at once when switching off
         c->flat_option = value ? 1 : 0;
+        if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); }
+        return 0;
+    }
+    if (!strcmp(name, "flat_block")) {
+        if (value != 256 && value != 384 && value != 768) return fail(-1, "flat_block must be 256 (ray records read from global memory), 384 or 768 (staged through shared memory)");
+        c->flat_block_option = (int)value;
         if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); }
         return 0;
     }

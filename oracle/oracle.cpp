@@ -1617,12 +1617,13 @@ struct Camera {  // camera/perspective.art:2-6,29-42
 struct Oracle {
     Scene scene;
     float* aov_normals = nullptr; float* aov_albedo = nullptr;   // standard AOVs (technique/internal/infobuffer.art), set by igo_set_aovs
+    bool deterministic = false;   // igo_set_deterministic: per-sample accumulation (the device's option "deterministic")
     explicit Oracle(const SceneDesc& d) : scene(d) {}
 };
 
 // One tile: driver/mapping_cpu.art:719-861
 void trace_tile(const Scene& sc, const Settings& st, const StreamRay* list_rays, int xmin, int ymin, int xmax, int ymax,
-                float* fb, int use_bvh, uint64_t counters[3], float* aov_normals = nullptr, float* aov_albedo = nullptr) {
+                float* fb, int use_bvh, uint64_t counters[3], float* aov_normals = nullptr, float* aov_albedo = nullptr, bool deterministic = false) {
     const int spi = st.spi;
     const int capacity = spi * 16 * 16;                         // :717
     const int W = st.width, H = st.height;
@@ -1631,14 +1632,24 @@ void trace_tile(const Scene& sc, const Settings& st, const StreamRay* list_rays,
     const PathTracer tech(sc);
     const Camera camera(sc.camera, W, H);
     const float inv_spi = 1 / (float)spi;                        // driver/accumulator.art:23-31
+    const int tile_w = xmax - xmin, tile_h = ymax - ymin;
+    const int num_rays = spi * tile_w * tile_h;
+    // Deterministic accumulation (the device's option "deterministic"): the order in which the contributions of ONE pixel are added is
+    // what makes the frame depend on scheduling -- in the reference it is the order of the tile's wavefront, here and on the device it
+    // is fixed: every sample (ray id) sums its own contributions in path order, then the samples are added to the pixel in sample order.
+    std::vector<float> slots, nslots, aslots;   // colour, Normals, Albedo: one rgb slot per sample of the tile
+    if (deterministic) { slots.assign((size_t)num_rays * 3, 0.0f); if (aov_normals) { nslots.assign((size_t)num_rays * 3, 0.0f); aslots.assign((size_t)num_rays * 3, 0.0f); } }
+    auto slot_of = [&](int ray_id) {
+        const int pixel = ray_id / spi, sample = ray_id - pixel * spi;
+        const int px = pixel % W - xmin, py = pixel / W - ymin;
+        return ((size_t)(py * tile_w + px) * spi + sample) * 3;
+    };
     auto splat = [&](int ray_id, Color c) {                      // :437-451
-        const int pixel = ray_id / spi;
-        fb[pixel * 3 + 0] += c.r * inv_spi; fb[pixel * 3 + 1] += c.g * inv_spi; fb[pixel * 3 + 2] += c.b * inv_spi;
+        float* p = deterministic ? slots.data() + slot_of(ray_id) : fb + (size_t)(ray_id / spi) * 3;
+        p[0] += c.r * inv_spi; p[1] += c.g * inv_spi; p[2] += c.b * inv_spi;
     };
     const int n_ent = (int)sc.entities.size();
     std::vector<int> ray_begins(n_ent + 2), ray_ends(n_ent + 2);
-    const int tile_w = xmax - xmin, tile_h = ymax - ymin;
-    const int num_rays = spi * tile_w * tile_h;
     int id = 0, current_size = 0;
     while (id < num_rays || current_size > 0) {
         // ---- (re-)generate: cpu_generate_rays :313-360, make_camera_emitter driver/emitter.art:6-16
@@ -1722,9 +1733,10 @@ void trace_tile(const Scene& sc, const Settings& st, const StreamRay* list_rays,
                     if (aov_normals && st.iter == 0 && (ray.flags & ray_flag_camera) == ray_flag_camera) {
                         const Vec3 n = ctx.surf.local.c2;
                         const Color alb = mat.bsdf.albedo(neg(ray.dir));
-                        const int px = ray_id / spi;
-                        aov_normals[px * 3 + 0] += n.x * inv_spi; aov_normals[px * 3 + 1] += n.y * inv_spi; aov_normals[px * 3 + 2] += n.z * inv_spi;
-                        aov_albedo[px * 3 + 0] += fminf(alb.r, 1.0f) * inv_spi; aov_albedo[px * 3 + 1] += fminf(alb.g, 1.0f) * inv_spi; aov_albedo[px * 3 + 2] += fminf(alb.b, 1.0f) * inv_spi;
+                        float* pn = deterministic ? nslots.data() + slot_of(ray_id) : aov_normals + (size_t)(ray_id / spi) * 3;
+                        float* pa = deterministic ? aslots.data() + slot_of(ray_id) : aov_albedo + (size_t)(ray_id / spi) * 3;
+                        pn[0] += n.x * inv_spi; pn[1] += n.y * inv_spi; pn[2] += n.z * inv_spi;
+                        pa[0] += fminf(alb.r, 1.0f) * inv_spi; pa[1] += fminf(alb.g, 1.0f) * inv_spi; pa[2] += fminf(alb.b, 1.0f) * inv_spi;
                     }
                     if (tech.on_hit(ctx, primary.payload[i], mat, hc)) splat(ray_id, hc);
                     Ray sray; Color scol;
@@ -1754,6 +1766,17 @@ void trace_tile(const Scene& sc, const Settings& st, const StreamRay* list_rays,
             }
         }
     }
+    if (deterministic) {   // fold the samples into their pixels, sample 0 first (api.cu k_resolve)
+        auto resolve = [&](float* dst, const std::vector<float>& src) {
+            for (int py = 0; py < tile_h; ++py) for (int px = 0; px < tile_w; ++px) for (int ch = 0; ch < 3; ++ch) {
+                float acc = dst[((size_t)(ymin + py) * W + xmin + px) * 3 + ch];
+                for (int smp = 0; smp < spi; ++smp) acc += src[((size_t)(py * tile_w + px) * spi + smp) * 3 + ch];
+                dst[((size_t)(ymin + py) * W + xmin + px) * 3 + ch] = acc;
+            }
+        };
+        resolve(fb, slots);
+        if (aov_normals && st.iter == 0) { resolve(aov_normals, nslots); resolve(aov_albedo, aslots); }
+    }
 }
 
 }  // namespace
@@ -1765,6 +1788,8 @@ void* igo_create(const SceneDesc* d) { return new Oracle(*d); }
 void igo_destroy(void* o) { delete (Oracle*)o; }
 // Enables the Normals / Albedo AOVs for subsequent igo_render calls (W*H*3 floats each, accumulated; null disables)
 void igo_set_aovs(void* o, float* normals, float* albedo) { ((Oracle*)o)->aov_normals = normals; ((Oracle*)o)->aov_albedo = albedo; }
+// Per-sample accumulation for subsequent igo_render calls (trace_tile): the counterpart of the device's option "deterministic"
+void igo_set_deterministic(void* o, int on) { ((Oracle*)o)->deterministic = on != 0; }
 
 // Renders one iteration (driver/mapping_cpu.art cpu_trace) over 16x16 tiles with `n_threads` workers into `fb`
 // (W*H*3, accumulated). When part_world > 1 only the rank's tiles are rendered: the part_tile x part_tile block in tile column tx and
@@ -1786,7 +1811,7 @@ void igo_render(void* o, const Settings* st, const StreamRay* rays, float* fb, i
                 const int pidx = (y0 / part_tile) * ptx + (x0 / part_tile);
                 if (((pidx % ptx) + (pidx / ptx)) % part_world != part_rank) continue;
             }
-            trace_tile(sc, *st, rays, x0, y0, std::min(W, x0 + T), std::min(H, y0 + T), fb, use_bvh, cnt[tid].data(), rays ? nullptr : ((Oracle*)o)->aov_normals, rays ? nullptr : ((Oracle*)o)->aov_albedo);
+            trace_tile(sc, *st, rays, x0, y0, std::min(W, x0 + T), std::min(H, y0 + T), fb, use_bvh, cnt[tid].data(), rays ? nullptr : ((Oracle*)o)->aov_normals, rays ? nullptr : ((Oracle*)o)->aov_albedo, ((Oracle*)o)->deterministic);
         }
     };
     if (n_threads <= 1) worker(0);

@@ -109,6 +109,7 @@ def lib():
         L.igo_create.argtypes = [C.POINTER(SceneDesc)]
         L.igo_destroy.argtypes = [C.c_void_p]
         L.igo_set_aovs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.igo_set_deterministic.argtypes = [C.c_void_p, C.c_int]
         L.igo_render.argtypes = [C.c_void_p, C.POINTER(Settings), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.igo_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
@@ -163,6 +164,11 @@ class Oracle:
             assert a is None or (a.dtype == np.float32 and a.flags.c_contiguous)
         self._aovs = (normals, albedo)
         lib().igo_set_aovs(self._h, None if normals is None else normals.ctypes.data, None if albedo is None else albedo.ctypes.data)
+
+    def set_deterministic(self, on: bool):
+        """Per-sample accumulation (every sample sums its contributions in path order, samples are added to the pixel in sample order):
+        what the device's option "deterministic" computes, bit for bit."""
+        lib().igo_set_deterministic(self._h, 1 if on else 0)
 
     def render(self, width, height, spi=1, iteration=0, seed=0, frame=0, fb=None, threads=0, use_bvh=True,
                rays=None, partition=(0, 1, 32)):

@@ -596,3 +596,87 @@ def test_standard_aovs_match_oracle():
         prt.step()
         with pytest.raises(Exception, match="AOV"):
             prt.getFramebufferForHost("Albedo")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,w,h,spi,iters,world", [
+    ("diamond_scene.json", 240, 135, 4, 3, 1),               # C2 at reduced size, the reference GPU default spi
+    ("primitives.json", 200, 120, 3, 2, 1),
+    ("many_point_lights.json", 160, 160, 2, 2, 1),           # textures, rough conductor, sky: the full shade kernels
+    ("evaluation/cbox-d6.json", 128, 128, 8, 2, 3),           # three partitions summed
+])
+def test_deterministic_accumulation_is_bit_exact(scene, w, h, spi, iters, world):
+    """Option "deterministic": every sample sums its own contributions in path order, the samples are folded into the pixel in sample
+    order. Same inputs => the SAME BITS, run to run (src/tests/integrator/test_reproducibility.py:5-11 at any spi) -- and the same bits as
+    the oracle accumulating the same way, so the 1e-7 that float atomics leave in the other tests is gone."""
+    t = load_scene(scene_path(scene))
+    o = Oracle(t)
+    o.set_deterministic(True)
+    ref = np.zeros((h, w, 3), np.float32)
+    for it in range(iters):
+        o.render(w, h, spi=spi, iteration=it, fb=ref)
+    frames = []
+    for run in range(2):
+        acc = np.zeros((h, w, 3), np.float32)
+        for rank in range(world):
+            with Runtime(t, w, h, spi=spi) as rt:
+                rt.device.setOption("deterministic", 1)
+                if world > 1:
+                    rt.device.setPartition(rank, world, 32)
+                for _ in range(iters):
+                    rt.step()
+                acc += rt.getFramebufferForHost()            # disjoint supports: x + 0 is exact
+        frames.append(acc)
+    np.testing.assert_array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32))
+    np.testing.assert_array_equal(frames[0].view(np.uint32), ref.view(np.uint32))
+    # and it is the same image as the default accumulation up to the reordering of float additions
+    with Runtime(t, w, h, spi=spi) as rt:
+        for _ in range(iters):
+            rt.step()
+        plain = rt.getFramebufferForHost().copy()
+    assert rel_l2(plain, ref) <= 1e-5
+    if spi > 1 and scene == "diamond_scene.json":
+        assert not np.array_equal(plain.view(np.uint32), ref.view(np.uint32))   # ... which is what the option is for
+
+
+@pytest.mark.gpu
+def test_deterministic_aovs_and_exclusions():
+    t = load_scene(scene_path("diamond_scene.json"))
+    w, h, spi = 160, 90, 4
+    o = Oracle(t)
+    o.set_deterministic(True)
+    ref_n, ref_a, ref = (np.zeros((h, w, 3), np.float32) for _ in range(3))
+    o.set_aovs(ref_n, ref_a)
+    for it in range(2):
+        o.render(w, h, spi=spi, iteration=it, fb=ref)
+    with Runtime(t, w, h, spi=spi) as rt:
+        rt.device.setOption("std_aovs", 1)
+        rt.device.setOption("deterministic", 1)
+        rt.step(); rt.step()
+        got = [rt.device.getFramebufferForHost(n).copy() for n in ("Normals", "Albedo", "")]
+        with pytest.raises(Exception, match="exclude"):
+            rt.device.frameStreamBegin(4)
+    for g, r in zip(got, (ref_n, ref_a, ref)):
+        np.testing.assert_array_equal(g.view(np.uint32), r.view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene", ["diamond_scene.json", "evaluation/cbox-d6.json", "many_point_lights.json"])
+def test_staged_ray_records_are_invisible(scene):
+    """The merged-tree trace kernel fed through shared memory (TMA bulk copies of the ray records one batch ahead, wavefront.cuh
+    phase_trace_staged; CTAs of 384 or 768 threads) against the one that reads the records from global memory: same hits, hence
+    bit-identical frames in deterministic mode and identical ray counts."""
+    t = load_scene(scene_path(scene))
+    w, h, spi = 333, 187, 3     # odd sizes: the last batch is partial and one batch straddles the primary / shadow boundary
+    out = {}
+    for blk in (256, 384, 768):
+        with Runtime(t, w, h, spi=spi) as rt:
+            rt.device.setOption("flat_block", blk)
+            rt.device.setOption("deterministic", 1)
+            for _ in range(3):
+                rt.step()
+            out[blk] = (rt.getFramebufferForHost().copy(), rt.device.getStatistics())
+    for blk in (384, 768):
+        np.testing.assert_array_equal(out[blk][0].view(np.uint32), out[256][0].view(np.uint32))
+        for k in ("CameraRayCount", "ShadowRayCount", "BounceRayCount", "Splats"):
+            assert out[blk][1][k] == out[256][1][k], (blk, k)

@@ -387,3 +387,23 @@ def test_sky_fixture_and_c5_scene_loads():
     assert np.isfinite(img).all() and 0.05 < float(img.mean()) < 1.0
     # reproducible, and NEE through the hierarchy agrees with the uniform selector in the mean
     np.testing.assert_array_equal(img, Oracle(t).render(96, 96, spi=4))
+
+
+# ------------------------------------------------------------------------------------------------ deterministic accumulation
+def test_oracle_deterministic_accumulation():
+    """The oracle's per-sample accumulation (counterpart of the device option "deterministic"): independent of the number of threads
+    (tiles are independent anyway) and the same image as the reference-order accumulation up to float reordering; at spi 1 the two orders
+    coincide in the first iteration (one chain per pixel, added to an empty frame). src/tests/integrator/test_reproducibility.py:5-11."""
+    t = load_scene(os.path.join(ROOT, "scenes", "diamond_scene.json"))
+    w, h = 96, 54
+    def run(det, spi, threads, iters=2):
+        o = Oracle(t); o.set_deterministic(det)
+        fb = np.zeros((h, w, 3), np.float32)
+        for it in range(iters):
+            o.render(w, h, spi=spi, iteration=it, fb=fb, threads=threads)
+        return fb
+    a, b = run(True, 4, 1), run(True, 4, 5)
+    np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    plain = run(False, 4, 3)
+    assert np.linalg.norm((a - plain).ravel()) / np.linalg.norm(plain.ravel()) < 1e-6
+    np.testing.assert_array_equal(run(True, 1, 2, 1).view(np.uint32), run(False, 1, 2, 1).view(np.uint32))   # first iteration: 0 + x is exact
