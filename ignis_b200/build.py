@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libigb200.so")
-SOURCES = ["api.cu"]
-DEPS = ["api.cu", "wavefront.cuh", "traverse.cuh", "shade.cuh", "material.cuh", "types.cuh", "device_math.cuh", "bvh8.h", "../../include/igb200.h", "../build.py"]
+SOURCES = ["api.cu", "bvh_build.cu"]
+DEPS = ["api.cu", "bvh_build.cu", "bvh_build.h", "wavefront.cuh", "traverse.cuh", "shade.cuh", "material.cuh", "types.cuh", "device_math.cuh", "bvh8.h", "../../include/igb200.h", "../build.py"]
 
 
 def nvcc_path() -> str:
@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     extra = (["-Xptxas", "-v"] if verbose else []) + (["-DIGB_STEP_STATS"] if os.environ.get("IGB200_STEP_STATS") else []) + \
             (["-DIGB_EXP_" + x for x in os.environ["IGB200_EXPERIMENT"].split("_")] if os.environ.get("IGB200_EXPERIMENT") else [])
-    cmd = [nvcc_path(), *flags(extra), "-shared", "-o", OUT,
+    cmd = [nvcc_path(), *flags(extra), "--threads", "2", "-shared", "-o", OUT,
            *[os.path.join(SRC, s) for s in SOURCES]]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

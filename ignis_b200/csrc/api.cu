@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -15,6 +16,7 @@
 
 #include "../../include/igb200.h"
 #include "bvh8.h"
+#include "bvh_build.h"
 #include "wavefront.cuh"
 
 using namespace igb;
@@ -245,6 +247,12 @@ struct igb200_ctx {
     std::vector<Timed> timed;
     double prof_ms[4] = {0, 0, 0, 0}; uint64_t prof_n[4] = {0, 0, 0, 0};
     DevBuf<igb200_ray> list_rays;
+    // BVH construction: which builder makes a shape's tree, and the on-disk cache (bvh_build.cu)
+    int gpu_bvh = -1;                          // option "gpu_bvh": 1 = every shape of more than 4 faces is built on the GPU, 0 = never, -1 = from gpu_bvh_min_faces faces on
+    int64_t gpu_bvh_min_faces = 1 << 20;       // option
+    int64_t bvh_cache_min_faces = 500000;      // option: meshes with more faces go through the cache (the reference: MinFaceCountForCache, TriMeshProvider.cpp:328)
+    std::string cache_dir;                     // igb200_set_cache_dir; empty = no cache
+    int64_t build_info[6] = {0, 0, 0, 0, 0, 0};   // last igb200_set_scene: shapes built on the host / on the GPU / loaded from the cache / stored, microseconds spent, nodes
     // deterministic accumulation (option "deterministic"): per-sample slots for the colour buffer and the two standard AOVs
     bool deterministic = false;
     DevBuf<float> det_slots, det_aov[2];
@@ -585,6 +593,9 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
         if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); }
         return 0;
     }
+    if (!strcmp(name, "gpu_bvh")) { if (value < -1 || value > 1) return fail(-1, "gpu_bvh must be -1 (from gpu_bvh_min_faces faces on), 0 (never) or 1 (every shape of more than 4 faces)"); c->gpu_bvh = (int)value; return 0; }
+    if (!strcmp(name, "gpu_bvh_min_faces")) { if (value < 5) return fail(-1, "gpu_bvh_min_faces must be >= 5"); c->gpu_bvh_min_faces = value; return 0; }
+    if (!strcmp(name, "bvh_cache_min_faces")) { if (value < 0) return fail(-1, "bvh_cache_min_faces must be >= 0"); c->bvh_cache_min_faces = value; return 0; }
     if (!strcmp(name, "flat_block")) {
         if (value != 256 && value != 384 && value != 768) return fail(-1, "flat_block must be 256 (ray records read from global memory), 384 or 768 (staged through shared memory)");
         c->flat_block_option = (int)value;
@@ -705,6 +716,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     }
 
     // ---- per-shape geometry: triangles in BVH leaf order + BVH8 (replaces the reference's pre-baked trimesh_primbvh table)
+    for (int64_t& v : c->build_info) v = 0;
     std::vector<Node8> nodes;
     std::vector<float4> tris;
     std::vector<int> tri_prim;
@@ -750,7 +762,28 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
             for (int k = 0; k < 3; ++k) { const int vi = inds[4 * t + k]; if (vi < 0 || vi >= nv) return fail(-1, "igb200_set_scene: shape %d triangle %d has a bad index", s, t); b.extend(verts + 4 * (size_t)vi); }
             boxes[t] = b;
         }
-        Bvh8 bvh = build_bvh8(boxes, 4);
+        Bvh8 bvh;
+        {   // the shape's tree: from the cache, from the GPU builder or from the host builder (bvh_build.cu)
+            const auto t0 = std::chrono::steady_clock::now();
+            const bool on_gpu = nf > 4 && (c->gpu_bvh == 1 || (c->gpu_bvh < 0 && nf >= c->gpu_bvh_min_faces));
+            const int builder = on_gpu ? BVH_BUILDER_GPU_LBVH : BVH_BUILDER_HOST_SAH;
+            const bool cached = !c->cache_dir.empty() && nf > c->bvh_cache_min_faces;
+            const uint64_t hash = cached ? bvh_cache_hash(boxes, 4, builder) : 0;
+            bool have = cached && bvh_cache_load(c->cache_dir, hash, (size_t)nf, builder, bvh);
+            const bool loaded = have;
+            if (loaded) c->build_info[2]++;
+            if (!have && on_gpu) {
+                std::string err;
+                have = build_bvh8_gpu(boxes, bvh, c->stream, err);
+                if (have) c->build_info[1]++;
+                else { cudaGetLastError(); fprintf(stderr, "[igb200] shape %d: %s -- building on the host\n", s, err.c_str()); bvh = Bvh8(); }
+            }
+            if (!have) { bvh = build_bvh8(boxes, 4); c->build_info[0]++; }
+            // a tree the GPU builder could not make is stored under the GPU builder's key all the same: the key names the request, and any valid tree answers it
+            if (cached && !loaded && bvh_cache_store(c->cache_dir, hash, builder, bvh)) c->build_info[3]++;
+            c->build_info[4] += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+            c->build_info[5] += (int64_t)bvh.nodes.size();
+        }
         max_shape_depth = std::max(max_shape_depth, nf > 4 ? bvh.max_depth : 0);
         const int node_base = (int)nodes.size(), tri_base = (int)(tris.size() / 3);
         shape_root[s] = node_base + 1;
@@ -1015,6 +1048,19 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
     c->desc.selector_data = nullptr; c->desc.textures = nullptr; c->desc.images = nullptr; c->desc.aux_data = nullptr;
     c->has_scene = true;
     return configure_kernels(c);
+}
+
+int igb200_set_cache_dir(igb200_ctx* c, const char* dir) {
+    if (!c) return fail(-1, "null context");
+    c->cache_dir = dir ? dir : "";
+    while (c->cache_dir.size() > 1 && c->cache_dir.back() == '/') c->cache_dir.pop_back();
+    return 0;
+}
+
+int igb200_scene_build_info(igb200_ctx* c, int64_t out[6]) {
+    if (!c || !out) return fail(-1, "igb200_scene_build_info: null argument");
+    for (int k = 0; k < 6; ++k) out[k] = c->build_info[k];
+    return 0;
 }
 
 int igb200_resize(igb200_ctx* c, int width, int height) {
@@ -1656,6 +1702,71 @@ int igb200_frame_stream_next(igb200_ctx* c, int wait, int* iteration, float** ho
     c->fs_last_taken_host = f.host;
     *iteration = f.iter; *host_rgb = c->fs_host[f.host];
     return 1;
+}
+
+// Test hook: builds a BVH8 over n boxes (6 floats each) with the host builder (builder 0, needs no GPU and no context) or the GPU builder
+// (builder 1), optionally through the cache in `dir` (store, then load and compare), validates it -- every primitive in exactly one leaf,
+// every child box contains what hangs below it -- and reports {nodes, depth, leaves, SAH cost x 1000 relative to the root's area}.
+int igb200_test_bvh_build(igb200_ctx* c, const float* boxes6, size_t n, int builder, const char* dir, int64_t out[4]) {
+    if (!boxes6 || !out || n < 1) return fail(-1, "igb200_test_bvh_build: bad argument");
+    std::vector<Box3> boxes(n);
+    std::memcpy(boxes.data(), boxes6, n * sizeof(Box3));
+    Bvh8 bvh;
+    if (builder == BVH_BUILDER_GPU_LBVH) {
+        if (!c) return fail(-1, "igb200_test_bvh_build: the GPU builder needs a context");
+        CU(cudaSetDevice(c->device));
+        std::string err;
+        if (!build_bvh8_gpu(boxes, bvh, c->stream, err)) return fail(-2, "%s", err.c_str());
+    } else bvh = build_bvh8(boxes, 4);
+    if (dir && *dir) {
+        const uint64_t h = bvh_cache_hash(boxes, 4, builder);
+        if (!bvh_cache_store(dir, h, builder, bvh)) return fail(-2, "igb200_test_bvh_build: cannot store into '%s'", dir);
+        Bvh8 back;
+        if (!bvh_cache_load(dir, h, n, builder, back)) return fail(-2, "igb200_test_bvh_build: cannot load what was stored");
+        if (back.nodes.size() != bvh.nodes.size() || back.order != bvh.order || back.max_depth != bvh.max_depth ||
+            std::memcmp(back.nodes.data(), bvh.nodes.data(), bvh.nodes.size() * sizeof(Node8)) != 0) return fail(-2, "igb200_test_bvh_build: the cached tree differs from the stored one");
+        if (bvh_cache_load(dir, h ^ 1, n, builder, back)) return fail(-2, "igb200_test_bvh_build: a tree was loaded under a hash it was not stored under");
+    }
+    // validation: depth-first from the root with the box each subtree must stay inside
+    std::vector<int> seen(n, 0);
+    struct Item { int node; Box3 box; int depth; };
+    std::vector<Item> stack;
+    Box3 root = Box3::empty();
+    for (const Box3& b : boxes) root.extend(b);
+    stack.push_back(Item{0, root, 1});
+    auto inside = [](const Box3& a, const Box3& b) { for (int k = 0; k < 3; ++k) if (a.lo[k] < b.lo[k] || a.hi[k] > b.hi[k]) return false; return true; };
+    double cost = 0; int64_t leaves = 0; int depth = 0;
+    if (bvh.nodes.empty()) return fail(-2, "igb200_test_bvh_build: empty tree");
+    while (!stack.empty()) {
+        const Item it = stack.back(); stack.pop_back();
+        depth = std::max(depth, it.depth);
+        if (it.node < 0 || (size_t)it.node >= bvh.nodes.size()) return fail(-2, "igb200_test_bvh_build: child index %d out of range", it.node);
+        const Node8& nd = bvh.nodes[it.node];
+        bool ended = false;
+        for (int k = 0; k < 8; ++k) {
+            const int ch = nd.child[k];
+            if (ch == 0) { ended = true; continue; }
+            if (ended) return fail(-2, "igb200_test_bvh_build: node %d: children are not packed to the front", it.node);
+            Box3 cb; for (int a = 0; a < 3; ++a) { cb.lo[a] = nd.bounds[2 * a][k]; cb.hi[a] = nd.bounds[2 * a + 1][k]; }
+            if (!inside(cb, it.box)) return fail(-2, "igb200_test_bvh_build: node %d child %d sticks out of its parent's box", it.node, k);
+            cost += cb.half_area();
+            if (ch > 0) stack.push_back(Item{ch - 1, cb, it.depth + 1});
+            else {
+                const int r = -ch - 1, first = r >> 2, cnt = (r & 3) + 1;
+                ++leaves;
+                for (int j = 0; j < cnt; ++j) {
+                    if ((size_t)(first + j) >= n) return fail(-2, "igb200_test_bvh_build: leaf slot %d out of range", first + j);
+                    const int p = bvh.order[first + j];
+                    if (p < 0 || (size_t)p >= n || seen[p]++) return fail(-2, "igb200_test_bvh_build: primitive %d is referenced twice or out of range", p);
+                    if (!inside(boxes[p], cb)) return fail(-2, "igb200_test_bvh_build: primitive %d sticks out of its leaf's box", p);
+                }
+            }
+        }
+    }
+    for (size_t p = 0; p < n; ++p) if (!seen[p]) return fail(-2, "igb200_test_bvh_build: primitive %zu is in no leaf", p);
+    if (depth != bvh.max_depth && n > 4) return fail(-2, "igb200_test_bvh_build: max_depth says %d, the tree has %d levels", bvh.max_depth, depth);
+    out[0] = (int64_t)bvh.nodes.size(); out[1] = depth; out[2] = leaves; out[3] = (int64_t)(1000.0 * cost / std::max((double)root.half_area(), 1e-30));
+    return 0;
 }
 
 int igb200_test_detmath(igb200_ctx* c, int fn, const float* a, const float* b, float* out, size_t n) {

@@ -71,7 +71,16 @@ SYMBOLS = ["igb200_last_error", "igb200_version", "igb200_create", "igb200_destr
            "igb200_upload_framebuffer", "igb200_stats", "igb200_reset_stats", "igb200_kernel_times", "igb200_launch_profile", "igb200_turn_log", "igb200_step_stats", "igb200_set_option",
            "igb200_stream", "igb200_trace_closest", "igb200_trace_any", "igb200_bench_trace", "igb200_test_detmath",
            "igb200_comm_unique_id", "igb200_comm_init", "igb200_comm_gather_framebuffer", "igb200_comm_destroy",
-           "igb200_frame_stream_begin", "igb200_frame_stream_next", "igb200_frame_stream_end"]
+           "igb200_frame_stream_begin", "igb200_frame_stream_next", "igb200_frame_stream_end", "igb200_set_cache_dir", "igb200_scene_build_info", "igb200_test_bvh_build"]
+
+
+def test_bvh_build(boxes, builder=0, cache_dir=None, device=None):
+    """igb200_test_bvh_build: builds + validates a BVH8 over (n, 6) float32 boxes; builder 0 = host (no GPU needed), 1 = GPU (needs a B200Device)."""
+    boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+    out = (C.c_int64 * 4)()
+    _check(lib().igb200_test_bvh_build(device._h if device is not None else None, boxes.ctypes.data, boxes.shape[0], int(builder),
+                                       None if cache_dir is None else str(cache_dir).encode(), out))
+    return dict(zip(("nodes", "levels", "leaves", "sah_x1000"), (int(x) for x in out)))
 
 
 def library_path() -> str:
@@ -111,6 +120,9 @@ def lib():
         L.igb200_step_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.igb200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
         L.igb200_stream.argtypes = [vp, C.POINTER(vp)]
+        L.igb200_set_cache_dir.argtypes = [vp, C.c_char_p]
+        L.igb200_scene_build_info.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.igb200_test_bvh_build.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_char_p, C.POINTER(C.c_int64)]
         L.igb200_trace_closest.argtypes = [vp, vp, vp, C.c_size_t, vp]
         L.igb200_trace_any.argtypes = [vp, vp, C.c_size_t, vp]
         L.igb200_bench_trace.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
@@ -298,6 +310,16 @@ class B200Device:
 
     def setOption(self, name: str, value: int):
         _check(lib().igb200_set_option(self._h, name.encode(), int(value)))
+
+    def setCacheDir(self, path):
+        """Directory of the on-disk BVH cache (None: no cache); the reference: LoaderContext.CacheManager, TriMeshProvider.cpp:326-351."""
+        _check(lib().igb200_set_cache_dir(self._h, None if path is None else str(path).encode()))
+
+    def sceneBuildInfo(self):
+        """What the last assignScene did with the shapes' BVHs."""
+        out = (C.c_int64 * 6)()
+        _check(lib().igb200_scene_build_info(self._h, out))
+        return dict(zip(("host_built", "gpu_built", "cache_loaded", "cache_stored", "build_us", "nodes"), (int(x) for x in out)))
 
     def turnLog(self):
         """Per loop turn of the last render(): (rays traced, trace-phase ns, shade-phase ns)."""

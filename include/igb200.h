@@ -299,8 +299,26 @@ int igb200_step_stats(igb200_ctx* ctx, uint64_t out[16]);
 /* Tunables: "capacity" (records per ray queue), "refill" (lanes), "stage_budget" (bytes of shared memory for the staged
  * scene copy; used only if the whole scene fits, unless "stage_partial" = 1; "specialise_where" = 0 disables the trace kernel built for a fully staged scene; "carveout" = preferred shared-memory carve-out of the trace kernels in percent, -1 = the driver's choice), "min_blocks" (2|3 CTAs per SM), "vote" (0|2), "defer_permille" (deferred tail threshold, 0 = off), "split_turns"
  * (leading turns run as separate shade / trace launches), "turn_trace_blocks" (2|3), "wide_rays_per_group", "fuse" (iterations per launch, 0 = automatic), "profile_kernels", "std_aovs" (1: the "Normals" and
- * "Albedo" AOVs of the reference's infobuffer wrapper, technique/internal/infobuffer.art, exist and are written at iteration 0). */
+ * "Albedo" AOVs of the reference's infobuffer wrapper, technique/internal/infobuffer.art, exist and are written at iteration 0),
+ * "deterministic" (1: radiance is accumulated per SAMPLE and folded into the pixel in sample order, so the same inputs give the same bits
+ * whatever the spi and the scheduling -- the reference's CPU device adds without atomics, driver/accumulator.art:4-21, and its
+ * src/tests/integrator/test_reproducibility.py:5-11 expects identical arrays; costs 12 B x W x H x spi of slots, the deferred tail and
+ * fused iterations; excludes frame streaming), "flat" (0: never walk the merged single-level tree of small scenes), "flat_block"
+ * (256 | 384 | 768: merged-tree trace kernel without / with its ray records staged through shared memory by TMA), "bin_materials"
+ * (-1 automatic | 0 | 1: shade through per-material-class index lists). */
 int igb200_set_option(igb200_ctx* ctx, const char* name, int64_t value);
+/* BVH construction. Every trimesh shape gets a BVH8 inside igb200_set_scene: by the host builder (binned SAH,
+ * csrc/bvh8.h) or ON THE GPU (Morton codes -> sort -> Karras radix tree -> bottom-up boxes -> collapse to BVH8, csrc/bvh_build.cu)
+ * -- option "gpu_bvh": 1 = every shape of more than 4 faces, 0 = never, -1 (default) = shapes of at least "gpu_bvh_min_faces" faces
+ * (default 2^20); replaces the reference's CPU build through madmann91/bvh, src/runtime/shape/TriMeshProvider.cpp:255-298,
+ * src/runtime/bvh/NArityBvh.h:94-143. Renders do not depend on which builder made a tree (the closest hit is a pure function of the ray).
+ * igb200_set_cache_dir names a directory in which the trees of shapes with more than "bvh_cache_min_faces" faces (default 500 000, the
+ * reference's MinFaceCountForCache, TriMeshProvider.cpp:326-351) are kept as bvh8_<hash of the builder's input>.bin and loaded instead of
+ * being rebuilt; NULL / "" = no cache (the default). The directory must exist. Corrupt or foreign files are ignored and rebuilt. */
+int igb200_set_cache_dir(igb200_ctx* ctx, const char* dir);
+/* What the LAST igb200_set_scene did: out = {shapes built on the host, built on the GPU, loaded from the cache, stored into the cache,
+ * microseconds spent on the shapes' trees, BVH8 nodes of all shapes}. */
+int igb200_scene_build_info(igb200_ctx* ctx, int64_t out[6]);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a caller can record
  * its own events on it or order a collective after a render (the reference has one implicit device queue). */
 int igb200_stream(igb200_ctx* ctx, void** cuda_stream);
@@ -312,6 +330,10 @@ int igb200_trace_any(igb200_ctx* ctx, const igb200_ray* rays, size_t n, int32_t*
 /* Same, device-resident rays (n repeated `repeat` times), returns average milliseconds per pass. */
 int igb200_bench_trace(igb200_ctx* ctx, const igb200_ray* rays, size_t n, int any_hit, int repeat, double* ms_per_pass);
 
+/* Test hook: builds a BVH8 over n boxes (lo xyz, hi xyz) with the host builder (builder 0; ctx may be NULL, no GPU needed) or the GPU
+ * builder (1), round-trips it through the cache directory when dir is given, validates the tree (every primitive in exactly one leaf,
+ * every box contains its subtree) and returns out = {nodes, levels, leaves, 1000 x sum of child half-areas / root half-area}. */
+int igb200_test_bvh_build(igb200_ctx* ctx, const float* boxes6, size_t n, int builder, const char* dir, int64_t out[4]);
 /* Test hook: evaluates the device's deterministic transcendental (0 sin, 1 cos, 2 acos, 3 atan2(a,b)) on the GPU. */
 int igb200_test_detmath(igb200_ctx* ctx, int fn, const float* a, const float* b, float* out, size_t n);
 

@@ -680,3 +680,71 @@ def test_staged_ray_records_are_invisible(scene):
         np.testing.assert_array_equal(out[blk][0].view(np.uint32), out[256][0].view(np.uint32))
         for k in ("CameraRayCount", "ShadowRayCount", "BounceRayCount", "Splats"):
             assert out[blk][1][k] == out[256][1][k], (blk, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,w,h", [("diamond_scene.json", 240, 135), ("primitives.json", 240, 135), ("synthetic_room.json", 192, 108), ("evaluation/room.json", 128, 128)])
+def test_gpu_built_bvh_is_invisible(scene, w, h):
+    """the shapes' BVH8s built ON THE GPU (Morton codes, radix tree, bottom-up boxes, collapse; csrc/bvh_build.cu) instead of by the
+    host's binned-SAH builder. The closest hit is a pure function of the ray, so hit records are the same bits and deterministic renders are
+    bit-identical, whatever the tree looks like -- and both equal the oracle's brute-force answer."""
+    t = load_scene(scene_path(scene))
+    rays = camera_rays(t, 96, 54)
+    out = {}
+    for gpu in (0, 1):
+        with Runtime(t, w, h, spi=2) as rt:
+            rt.device.setOption("gpu_bvh", gpu)
+            rt.device.setOption("deterministic", 1)
+            rt.device.assignScene(t)
+            info = rt.device.sceneBuildInfo()
+            for _ in range(2):
+                rt.step()
+            out[gpu] = (rt.getFramebufferForHost().copy(), rt.device.traceClosest(rays), rt.device.traceAny(rays), rt.device.getStatistics(), info)
+    assert out[0][4]["gpu_built"] == 0 and out[1][4]["gpu_built"] >= 1 and out[1][4]["nodes"] > 0
+    np.testing.assert_array_equal(out[1][0].view(np.uint32), out[0][0].view(np.uint32))
+    for k in ("ent_id", "prim_id"):
+        np.testing.assert_array_equal(out[1][1][k], out[0][1][k])
+    for k in ("t", "u", "v"):
+        np.testing.assert_array_equal(out[1][1][k].view(np.uint32), out[0][1][k].view(np.uint32))
+    np.testing.assert_array_equal(out[1][2], out[0][2])
+    for k in ("CameraRayCount", "ShadowRayCount", "BounceRayCount", "Splats"):
+        assert out[1][3][k] == out[0][3][k], k
+    ref = Oracle(t).trace_closest(rays, use_bvh=False)    # brute force
+    np.testing.assert_array_equal(out[1][1]["prim_id"], ref["prim_id"])
+    np.testing.assert_array_equal(out[1][1]["t"].view(np.uint32), ref["t"].view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpu", [0, 1])
+def test_bvh_cache_round_trip(tmp_path, gpu):
+    """The on-disk BVH cache (the reference: TriMeshProvider.cpp:326-351): first load builds and stores, second load reads the files,
+    a corrupted file is ignored and rebuilt; the image never changes."""
+    t = load_scene(scene_path("synthetic_room.json"))
+    w, h = 160, 90
+    def run(expect):
+        with Runtime(t, w, h, spi=1) as rt:
+            rt.device.setOption("gpu_bvh", gpu)
+            rt.device.setOption("bvh_cache_min_faces", 1000)     # the room's icospheres have 20 480 / 81 920 faces
+            rt.device.setOption("deterministic", 1)
+            rt.device.setCacheDir(tmp_path)
+            rt.device.assignScene(t)
+            info = rt.device.sceneBuildInfo()
+            rt.step()
+            img = rt.getFramebufferForHost().copy()
+        for k, v in expect.items():
+            assert info[k] == v, (k, info)
+        return img, info
+    a, info = run({"cache_loaded": 0})
+    n = info["cache_stored"]
+    assert n >= 2 and len(list(tmp_path.glob("bvh8_*.bin"))) == n
+    b, _ = run({"cache_loaded": n, "cache_stored": 0, "gpu_built": 0, "host_built": 2})   # the two rectangles (<= 4 faces) are never cached
+    np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    victim = sorted(tmp_path.glob("bvh8_*.bin"))[0]
+    raw = bytearray(victim.read_bytes()); raw[200] ^= 0xFF; raw[-3] ^= 0xFF            # a child code and an order entry
+    victim.write_bytes(bytes(raw[: len(raw) - 8]))                                       # ... and truncated
+    c, info = run({"cache_loaded": n - 1, "cache_stored": 1})
+    np.testing.assert_array_equal(a.view(np.uint32), c.view(np.uint32))
+    with Runtime(t, w, h, spi=1) as rt:                                                  # no cache directory: nothing is read or written
+        rt.device.setOption("bvh_cache_min_faces", 1000)
+        rt.device.assignScene(t)
+        assert rt.device.sceneBuildInfo()["cache_loaded"] == 0 and rt.device.sceneBuildInfo()["cache_stored"] == 0
