@@ -54,6 +54,11 @@ NCU_TRAFFIC_BYTES = 5.383e8
 NCU_TRAFFIC_SOURCE = ("profiles/r5a_k_turn_trace_full.csv (re-measured this round on the merged-tree kernel k_turn_trace<256,3,2,1,1>): dram read + write "
                       "of the three k_turn_trace launches of the first iteration (437 + 749 + 428 MB) / 3; later iterations also trace the carried "
                       "paths, hence the larger algorithmic figure")
+# Thread instructions per traced ray of k_turn_trace on the headline workload (c2), from ncu: smsp__thread_inst_executed.sum of the four
+# split-turn trace launches of one iteration (7.806 + 13.458 + 8.652 + 5.455 = 35.37 G) / the rays they traced (22.85 M primary + 10.83 M
+# shadow; igb200_launch_profile) -- profiles/r5g_issue_roofline.csv. Warp instructions: 1914.9 M for the same launches.
+NCU_THREAD_INST_PER_RAY = 1050.2
+NCU_WARP_INST_PER_RAY = 56.85
 B_STAGE = {"generate": 68, "traverse_primary": 60, "shade_read": 88, "shade_bounce_write": 68, "shade_shadow_write": 56,
            "traverse_secondary": 52}
 
@@ -418,6 +423,19 @@ def run_b200(args):
                                 "algorithmic_bytes_per_launch": kbytes, "rays_per_launch": (w_["primary"] + w_["shadow"]) / n_l,
                                 "peak_source": peak_src, "traffic_source": NCU_TRAFFIC_SOURCE,
                                 "timing": "CUDA events around every launch on the render stream, separate pass of the same K steps"}
+            if args.workload == "c2" and w * h * spi == 1920 * 1080 * 4:
+                # The ceiling this kernel actually runs against (DESIGN.md 3 "Roofline"): the scene sits in shared memory, so the trace phase is bound
+                # by instruction issue, not by HBM. Peak = SMs x 4 schedulers x 32 lanes x clock (thread instructions / s); achieved = the ncu-measured
+                # thread instructions per ray x the rays this run traced per second in this kernel. simt = lanes active per issued instruction.
+                clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+                n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+                rays_s = (w_["primary"] + w_["shadow"]) / (kern["k_turn_trace"]["ms"] * 1e-3)
+                peak_t = n_sm * 4 * 32 * clk
+                line["issue_roofline"] = {"bound": "issue", "kernel": "k_turn_trace", "unit": "T thread-inst/s", "achieved": NCU_THREAD_INST_PER_RAY * rays_s / 1e12, "peak": peak_t / 1e12,
+                                          "frac": NCU_THREAD_INST_PER_RAY * rays_s / peak_t, "thread_inst_per_ray": NCU_THREAD_INST_PER_RAY, "warp_inst_per_ray": NCU_WARP_INST_PER_RAY,
+                                          "simt_lanes_per_inst": NCU_THREAD_INST_PER_RAY / NCU_WARP_INST_PER_RAY, "warp_issue_frac": NCU_WARP_INST_PER_RAY * rays_s / (n_sm * 4 * clk),
+                                          "grays_per_s": rays_s / 1e9, "grays_per_s_at_full_simt_and_issue": peak_t / NCU_THREAD_INST_PER_RAY / 1e9,
+                                          "source": "profiles/r5g_issue_roofline.csv (ncu smsp__thread_inst_executed.sum / smsp__inst_executed.sum of the split-turn trace launches of one iteration) x live ray rate"}
             line["kernels"] = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps, "share": v["ms"] / total_ms} for k, v in kern.items()}
             prim = kst["CameraRayCount"] + kst["BounceRayCount"]
             phase_bytes = {"trace": B_STAGE["traverse_primary"] * prim + B_STAGE["traverse_secondary"] * kst["ShadowRayCount"] + B_SPLAT * kst["Splats"],

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>   // types and prototypes only: the library is loaded at run time (igb200_comm_*)
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: named ranges on the host timeline for nsys / ncu --nvtx (the reference's own section timers, Statistics.h:25-55)
 
 #include <algorithm>
 #include <cfloat>
@@ -54,6 +55,7 @@ static WaveKernel turn_shade_kernel(int blocks, bool full) {
 // 384 threads x 2 per SM or 768 x 1 (option "flat_block"), 256 = the unstaged kernel
 static WaveKernel flat_staged_kernel(int block) { return block == 768 ? k_turn_trace<768, 1, 2, 1, true, true> : k_turn_trace<384, 2, 2, 1, true, true>; }
 static WaveKernel turn_trace_kernel(int blocks, int vote, int where, bool flat = false) {
+    if (flat && where == 2) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 2, true> : k_turn_trace<WF_BLOCK, 2, 2, 2, true>;   // merged tree read from global memory (large scenes)
     if (flat) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 1, true> : k_turn_trace<WF_BLOCK, 2, 2, 1, true>;   // merged tree (small scenes, staged)
     if (vote && where == 1) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 1> : k_turn_trace<WF_BLOCK, 2, 2, 1>;
     if (vote) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 0> : k_turn_trace<WF_BLOCK, 2, 2, 0>;
@@ -130,6 +132,8 @@ __global__ void k_detmath(int fn, const float* a, const float* b, float* out, in
 }  // namespace
 
 // ================================================================================================ host side
+// NVTX range over a host-side step of the pipeline (no-ops unless a profiler is attached)
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } NvtxRange(const NvtxRange&) = delete; NvtxRange& operator=(const NvtxRange&) = delete; };
 static thread_local std::string g_error;
 static int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -173,8 +177,10 @@ struct igb200_ctx {
     DevBuf<float4> nodes, tris, ent_leaf, ent_shade, blob, materials;
     DevBuf<int> tri_prim;
     DevBuf<float4> flat_nodes;         // merged tree of small scenes (build_flat_tree)
-    int flat_option = 1;               // option "flat": 0 = always walk the two-level tree
+    int flat_option = 1;               // option "flat": 0 = always walk the two-level tree, 1 = the merged tree when it fits shared memory, 2 = also when it does not (read from global memory)
     bool flat_on = false;              // the split-turn trace kernel and the trace hooks walk the merged tree
+    bool flat_global = false;          // ... the split-turn trace kernel only, and the tree stays in global memory (large scenes, option "flat" = 2)
+    int64_t flat_max_bytes = 1ll << 30;   // option "flat_max_mb": a merged tree larger than this is not built (instances multiply the nodes)
     size_t smem_flat = 0;
     // option "flat_block": 384 | 768 = the merged-tree trace kernel with its ray records staged through shared memory by TMA (CTAs of that size),
     // 256 = records read from global memory. Measured (profiles/r5b_staged_rays.txt): the staged kernel is SLOWER (diamond_scene trace 3.56 ->
@@ -311,6 +317,14 @@ static int configure_kernels(igb200_ctx* c) {
     // the merged tree (small scenes): walked by the split-turn trace kernel and the trace hooks when the two-level scene is staged as a whole
     c->flat_on = c->flat_option != 0 && s.n_flat_nodes > 0 && c->stage_where == 1 && c->vote != 0 &&
                  (int64_t)s.n_flat_nodes * 256 + (int64_t)s.n_tris * 48 + (int64_t)s.n_ent * 128 <= c->stage_budget;
+    c->flat_global = !c->flat_on && c->flat_option >= 2 && s.n_flat_nodes > 0 && c->vote != 0 && c->stage_nodes == 0 && c->stage_tris == 0 && c->stage_ent == 0;
+    if (c->flat_global) {
+        const size_t smem = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2);
+        CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, 2, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nbg = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbg, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, 2, true), WF_BLOCK, smem));
+        if (nbg < 1) c->flat_global = false; else c->grid_turn_trace_flat = nbg * c->n_sm;
+    }
     c->smem_flat = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)s.n_ent * 128 + (size_t)s.n_flat_nodes * 256 + (size_t)s.n_tris * 48;
     for (int full = 0; full < 2; ++full) CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote, full != 0, c->stage_where), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CU(cudaFuncSetAttribute((const void*)trace_kernel(c->min_blocks, c->vote), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
@@ -440,7 +454,11 @@ static int launch_split_turns(igb200_ctx* c, const WaveParams& P, int turns) {
         turn_shade_kernel(c->turn_shade_blocks, P.sc.full != 0)<<<c->grid_turn_shade, WF_BLOCK, 0, c->stream>>>(P);
         { const int r = prof_end(c); if (r) return r; }
         { const int r = prof_begin(c, 1); if (r) return r; }
-        if (c->flat_on && c->flat_block != WF_BLOCK) flat_staged_kernel(c->flat_block)<<<c->grid_turn_trace_flat, c->flat_block, c->smem_flat_staged, c->stream>>>(P);
+        if (c->flat_global) {   // the merged tree in global memory: the kernel's node array IS the merged tree, nothing is staged
+            WaveParams G = P; G.sc.nodes = G.sc.flat_nodes; G.stage_flat = 0; G.stage_nodes = 0; G.stage_tris = 0; G.stage_ent = 0;
+            turn_trace_kernel(c->turn_trace_blocks, c->vote, 2, true)<<<c->grid_turn_trace_flat, WF_BLOCK, (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2), c->stream>>>(G);
+        }
+        else if (c->flat_on && c->flat_block != WF_BLOCK) flat_staged_kernel(c->flat_block)<<<c->grid_turn_trace_flat, c->flat_block, c->smem_flat_staged, c->stream>>>(P);
         else if (c->flat_on) turn_trace_kernel(c->turn_trace_blocks, c->vote, 1, true)<<<c->grid_turn_trace_flat, WF_BLOCK, c->smem_flat, c->stream>>>(P);
         else turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
         { const int r = prof_end(c); if (r) return r; }
@@ -487,6 +505,7 @@ static int flush_queued(igb200_ctx* c) {
 
 extern "C" { static int fs_publish(igb200_ctx* c, bool all); }
 static int drain(igb200_ctx* c) {
+    NvtxRange nvtx_("igb200: drain (deferred tail)");
     { const int r = flush_queued(c); if (r) return r; }
     if (c->maybe_carry) {
         CU(cudaSetDevice(c->device));
@@ -589,13 +608,15 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
     if (!strcmp(name, "std_aovs")) { c->std_aovs = value != 0; CU(cudaSetDevice(c->device)); return ensure_aovs(c); }
     if (!strcmp(name, "flat")) {   // 0: never walk the merged tree. Takes effect at the next igb200_set_scene (the tree is built there) or at once when switching off
-        c->flat_option = value ? 1 : 0;
+        if (value < 0 || value > 2) return fail(-1, "flat must be 0 (never), 1 (when the merged tree fits shared memory) or 2 (also from global memory)");
+        c->flat_option = (int)value;
         if (c->has_scene) { CU(cudaSetDevice(c->device)); return configure_kernels(c); }
         return 0;
     }
     if (!strcmp(name, "gpu_bvh")) { if (value < -1 || value > 1) return fail(-1, "gpu_bvh must be -1 (from gpu_bvh_min_faces faces on), 0 (never) or 1 (every shape of more than 4 faces)"); c->gpu_bvh = (int)value; return 0; }
     if (!strcmp(name, "gpu_bvh_min_faces")) { if (value < 5) return fail(-1, "gpu_bvh_min_faces must be >= 5"); c->gpu_bvh_min_faces = value; return 0; }
     if (!strcmp(name, "bvh_cache_min_faces")) { if (value < 0) return fail(-1, "bvh_cache_min_faces must be >= 0"); c->bvh_cache_min_faces = value; return 0; }
+    if (!strcmp(name, "flat_max_mb")) { if (value < 0 || value > (1 << 16)) return fail(-1, "flat_max_mb must be in [0, 65536]"); c->flat_max_bytes = value << 20; return 0; }
     if (!strcmp(name, "flat_block")) {
         if (value != 256 && value != 384 && value != 768) return fail(-1, "flat_block must be 256 (ray records read from global memory), 384 or 768 (staged through shared memory)");
         c->flat_block_option = (int)value;
@@ -654,6 +675,7 @@ int igb200_set_partition(igb200_ctx* c, int rank, int world, int tile_size) {
 }
 
 int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
+    NvtxRange nvtx_("igb200_set_scene (BVH build + upload)");
     if (!c || !d) return fail(-1, "igb200_set_scene: null argument");
     CU(cudaSetDevice(c->device));
     { const int r = sync_control(c); if (r) return r; }
@@ -840,7 +862,8 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
         for (int s = 0; s < d->n_shapes && ok; ++s) ok = d->shape_lookups[s].type_id == IGB200_SHAPE_TRIMESH;
         size_t flat_nodes_n = top.nodes.size();
         for (int i = 0; i < d->n_entities && ok; ++i) flat_nodes_n += shape_root[d->leaves[i].shape_id] > 0 ? shape_node_count[d->leaves[i].shape_id] : 0;
-        ok = ok && (int64_t)flat_nodes_n * 256 + (int64_t)tri_prim.size() * 48 + (int64_t)d->n_entities * 128 <= c->stage_budget;   // only when all of it is staged
+        ok = ok && ((int64_t)flat_nodes_n * 256 + (int64_t)tri_prim.size() * 48 + (int64_t)d->n_entities * 128 <= c->stage_budget ||   // all of it staged in shared memory ...
+                    (c->flat_option >= 2 && (int64_t)flat_nodes_n * 256 <= c->flat_max_bytes));                                                 // ... or walked in global memory
         if (ok) {
             flat.assign(top.nodes.begin(), top.nodes.end());
             const float inf = std::numeric_limits<float>::max();
@@ -1109,6 +1132,7 @@ int igb200_clear(igb200_ctx* c, const char* aov) {
 }
 
 int igb200_framebuffer(igb200_ctx* c, const char* aov, float** host_ptr) {
+    NvtxRange nvtx_("igb200_framebuffer (drain + D2H)");
     if (!c || !host_ptr) return fail(-1, "igb200_framebuffer: null argument");
     const int which = aov_index(c, aov);
     if (which < 0) return fail(-4, "igb200_framebuffer: AOV '%s' does not exist", aov);
@@ -1232,6 +1256,7 @@ int igb200_kernel_times(igb200_ctx* c, double out_ms[4], uint64_t out_launches[4
 }
 
 static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_iter, const igb200_ray* rays, size_t n_rays) {
+    NvtxRange nvtx_("igb200_render: launch iterations");
     if (!c || !st) return fail(-1, "igb200_render: null argument");
     if (!c->has_scene) return fail(-1, "igb200_render: no scene assigned");
     if (st->spi < 1) return fail(-1, "igb200_render: spi must be >= 1");
@@ -1539,6 +1564,7 @@ static int comm_prepare(igb200_ctx* c) {
 }
 // The exchange itself, asynchronous on the context's stream: the tiles this rank owns out of `src` -> rank 0, which assembles `frame`
 static int comm_gather_async(igb200_ctx* c, const float* src, float* frame) {
+    NvtxRange nvtx_("igb200_comm: gather tiles (NCCL)");
     { const int r = comm_prepare(c); if (r) return r; }
     const int W = c->width, H = c->height, tile = c->tile, world = c->world, rank = c->rank;
     const int tiles_x = (W + tile - 1) / tile;
@@ -1601,6 +1627,7 @@ static int fs_host_buffer(igb200_ctx* c, int* out) {
 }
 // Publishes finished iterations in order (all of them when `all`: the caller has just finished every path). Asynchronous.
 static int fs_publish(igb200_ctx* c, bool all) {
+    NvtxRange nvtx_("igb200: publish frames");
     const size_t n = c->fb.n;
     const bool root = c->rank == 0;
     while (!c->fs_inflight.empty() && (all || c->fs_inflight.front().shades_left <= 0)) {

@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace igbh {
@@ -38,7 +39,10 @@ void B200Device::error(const std::string& what) {
 }
 
 B200Device::B200Device(const SetupSettings& settings) : mSetup(settings) {
-    if (igb200_create((int)settings.target.device(), &mCtx) != 0) { error(std::string("cannot create the device: ") + igb200_last_error()); mCtx = nullptr; }
+    if (igb200_create((int)settings.target.device(), &mCtx) != 0) { error(std::string("cannot create the device: ") + igb200_last_error()); mCtx = nullptr; return; }
+    // BVH cache: the reference's CacheManager lives in the loader (LoaderContext, TriMeshProvider.cpp:326-351) and does not reach the device;
+    // this device builds its own trees, so it takes the directory from the environment
+    if (const char* dir = std::getenv("IGB200_CACHE_DIR")) { if (*dir && igb200_set_cache_dir(mCtx, dir) != 0) error(igb200_last_error()); }
 }
 
 B200Device::~B200Device() { if (mCtx) igb200_destroy(mCtx); }

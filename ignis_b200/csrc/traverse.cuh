@@ -415,15 +415,33 @@ struct Traversal {
             else { const float4 r0 = L[2], r1 = L[3], r2 = L[4]; lorg = xform_point(r0, r1, r2, org); ldir = xform_dir(r0, r1, r2, dir); }   // ray.art:53-59
             ent = slot;
         }
+        if (WHERE == 1) {
+            for (int j = 0; j < cnt; ++j) {
+                const float4* T = tri_ptr<WHERE>(sc, sg, first + j);
+                const float4 a = T[0], b = T[1], c = T[2];
+                float t, u, v;
+                if (intersect_tri(lorg, ldir, tmin, tmax, a, b, c, t, u, v)) {
+                    const int prim = __ldg(sc.tri_prim + first + j);
+                    const int e = __float_as_int(L[5].x);
+                    if (better(t, e, prim, hit) && entity_admits<WHERE>(sc, sg, slot)) accept(t, u, v, prim, e);
+                }
+            }
+            return;
+        }
+        // geometry read through L2: one triangle of look-ahead, as in leaf_step
+        const float4* T = tri_ptr<WHERE>(sc, sg, first);
+        float4 a = T[0], b = T[1], c = T[2];
+#pragma unroll 1
         for (int j = 0; j < cnt; ++j) {
-            const float4* T = tri_ptr<WHERE>(sc, sg, first + j);
-            const float4 a = T[0], b = T[1], c = T[2];
+            float4 na = a, nb = b, nc = c;
+            if (j + 1 < cnt) { const float4* Tn = tri_ptr<WHERE>(sc, sg, first + j + 1); na = Tn[0]; nb = Tn[1]; nc = Tn[2]; }
             float t, u, v;
             if (intersect_tri(lorg, ldir, tmin, tmax, a, b, c, t, u, v)) {
                 const int prim = __ldg(sc.tri_prim + first + j);
                 const int e = __float_as_int(L[5].x);
                 if (better(t, e, prim, hit) && entity_admits<WHERE>(sc, sg, slot)) accept(t, u, v, prim, e);
             }
+            a = na; b = nb; c = nc;
         }
     }
     template <int WHERE>

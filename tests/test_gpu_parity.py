@@ -715,6 +715,27 @@ def test_gpu_built_bvh_is_invisible(scene, w, h):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("scene", ["synthetic_room.json", "primitives.json"])
+def test_merged_tree_in_global_memory_is_invisible(scene):
+    """Option "flat" = 2: scenes too large for shared memory are traced through the merged single-level tree as well (every instance's
+    nodes refitted in world space, read through L1 / L2): bit-identical frames and ray counts against the two-level walk."""
+    t = load_scene(scene_path(scene))
+    w, h, spi = 320, 180, 2
+    out = {}
+    for flat in (2, 0):
+        with Runtime(t, w, h, spi=spi) as rt:
+            rt.device.setOption("flat", flat)
+            rt.device.setOption("deterministic", 1)
+            rt.device.assignScene(t)
+            for _ in range(2):
+                rt.step()
+            out[flat] = (rt.getFramebufferForHost().copy(), rt.device.getStatistics())
+    np.testing.assert_array_equal(out[2][0].view(np.uint32), out[0][0].view(np.uint32))
+    for k in ("CameraRayCount", "ShadowRayCount", "BounceRayCount", "Splats"):
+        assert out[2][1][k] == out[0][1][k], k
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("gpu", [0, 1])
 def test_bvh_cache_round_trip(tmp_path, gpu):
     """The on-disk BVH cache (the reference: TriMeshProvider.cpp:326-351): first load builds and stores, second load reads the files,
