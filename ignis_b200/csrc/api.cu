@@ -220,6 +220,8 @@ struct igb200_ctx {
     int carveout = -1;                 // option: preferred shared-memory carve-out of the trace kernels in percent (-1: the driver's choice)
     int stage_partial = 0;             // 1: stage the prefix that fits even if the scene does not fit as a whole
     int refill = 24, min_blocks = 2, vote = 2;
+    int shade_sync = 1;                 // k_turn_shade keeps the warps of a CTA in step with block barriers (wavefront.cuh phase_shade_cta): 0 off, 1 on
+    int wave_skip = 1;                  // a step ends with its split turns when nothing forces the persistent kernel to run (wavefront.cuh k_wavefront)
     int split_turns = -1;               // leading turns of an iteration run as separate shade / trace launches (0: all in the persistent kernel)
     int turn_trace_blocks = 3;         // CTAs per SM the trace kernel of a split turn is compiled for
     int turn_shade_blocks = 3;         // ... and the shade + generate kernel
@@ -387,6 +389,7 @@ static WaveParams make_params(igb200_ctx* c, const RenderParams& rp, const DevSc
     P.total = total; P.capacity = (int)c->capacity; P.list_rays = d_rays;
     P.stage_nodes = c->stage_nodes; P.stage_tris = c->stage_tris; P.stage_ent = c->stage_ent;
     P.refill = c->refill; P.defer = defer;
+    P.shade_sync = c->shade_sync; P.wave_skip = c->wave_skip;
     P.order = c->bin_order.p;
     P.wide_limit = (int)std::min<int64_t>(c->wide_rays_per_group * c->blocks_per_sm * c->n_sm * (WF_BLOCK / 8), (int64_t)1 << 30);
     P.stage_flat = c->flat_on ? sc.n_flat_nodes : 0;
@@ -605,6 +608,8 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "wide_rays_per_group")) { if (value < 0) return fail(-1, "wide_rays_per_group must be >= 0"); c->wide_rays_per_group = value; return 0; }
     if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 8000) return fail(-1, "defer_permille must be in [0, 8000]"); c->defer_permille = (int)value; return 0; }
     if (!strcmp(name, "profile_kernels")) { c->profile = value != 0; return 0; }
+    if (!strcmp(name, "shade_sync")) { if (value < 0 || value > 1) return fail(-1, "shade_sync must be 0 or 1"); c->shade_sync = (int)value; return 0; }
+    if (!strcmp(name, "wave_skip")) { if (value < 0 || value > 1) return fail(-1, "wave_skip must be 0 or 1"); { const int r = drain(c); if (r) return r; } c->wave_skip = (int)value; return 0; }
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
     if (!strcmp(name, "std_aovs")) { c->std_aovs = value != 0; CU(cudaSetDevice(c->device)); return ensure_aovs(c); }
     if (!strcmp(name, "flat")) {   // 0: never walk the merged tree. Takes effect at the next igb200_set_scene (the tree is built there) or at once when switching off
@@ -1368,7 +1373,7 @@ static int launch_iterations(igb200_ctx* c, const igb200_settings* st, int n_ite
         // dead after max_depth shades (technique/pathtracer.art:68,177), and shadow rays never outlive the turn that made them: an
         // iteration generated by an earlier launch is complete once the launches after it add up to max_depth shade passes. Exact, and
         // known to the host without a read-back; the same on every rank.
-        const long long shades = (long long)split_turns + 1;
+        const long long shades = (long long)split_turns + (c->wave_skip ? 0 : 1);   // wave_skip: the persistent kernel may not have shaded anything
         for (igb200_ctx::FsIter& f : c->fs_inflight) f.shades_left -= shades;
         for (int k = 0; k < n_iter; ++k) c->fs_inflight.push_back(igb200_ctx::FsIter{st->iter + k, (long long)std::max(c->dev.max_depth, 1)});
         if (defer == 0) for (igb200_ctx::FsIter& f : c->fs_inflight) f.shades_left = 0;   // the launch ran every path to its end

@@ -305,7 +305,10 @@ int igb200_step_stats(igb200_ctx* ctx, uint64_t out[16]);
  * src/tests/integrator/test_reproducibility.py:5-11 expects identical arrays; costs 12 B x W x H x spi of slots, the deferred tail and
  * fused iterations; excludes frame streaming), "flat" (0: never walk the merged single-level tree of small scenes), "flat_block"
  * (256 | 384 | 768: merged-tree trace kernel without / with its ray records staged through shared memory by TMA), "bin_materials"
- * (-1 automatic | 0 | 1: shade through per-material-class index lists). */
+ * (-1 automatic | 0 | 1: shade through per-material-class index lists), "shade_sync" (1: the split-turn shade kernel walks
+ * the queue CTA by CTA with a block barrier per record, so that the warps of a CTA share the instruction lines they fetch), "wave_skip"
+ * (1: a render() whose split turns generated every camera ray and left at most the deferred-tail threshold of paths alive does not run
+ * a turn of the persistent kernel; the paths ride along with the next render() or are finished by whatever observes results). */
 int igb200_set_option(igb200_ctx* ctx, const char* name, int64_t value);
 /* BVH construction. Every trimesh shape gets a BVH8 inside igb200_set_scene: by the host builder (binned SAH,
  * csrc/bvh8.h) or ON THE GPU (Morton codes -> sort -> Karras radix tree -> bottom-up boxes -> collapse to BVH8, csrc/bvh_build.cu)
