@@ -95,6 +95,7 @@ class ClockSampler:
         names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
                  nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
                  nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake", nv.nvmlClocksEventReasonApplicationsClocksSetting: "applications_clocks"}
+        self._stop.wait(0.003)   # the first NVML query not on top of the first launches of the timed region
         while not self._stop.is_set():
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
@@ -264,11 +265,20 @@ def run_b200(args):
         rt.reset()
         dev.resetStatistics()
         rt.IterationCount = 0
-        barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
         frames = 0
-        with ClockSampler(local_rank) as clk:
+        clk = ClockSampler(local_rank)   # NVML is initialised BEFORE the barrier: eight ranks doing it at once take milliseconds each, and a rank
+        barrier()                        # that starts late keeps rank 0 waiting in the gather (r6f: 6.5 ms of "gather" at N = 8 were start skew)
+        if world > 1:
+            # ranks leave the barrier up to 2 ms apart (8 processes + their NCCL / NVML threads on 16 host cores, r6g); the exchange at the end makes
+            # every rank wait for the last one, so the ranks agree on a start instant (CLOCK_MONOTONIC is shared on one box) and spin until it comes
+            tt = torch.tensor([time.perf_counter()], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            go = float(tt[0]) + 0.002
+            while time.perf_counter() < go:
+                pass
+        t0 = time.perf_counter()
+        with clk:
             ev0.record(stream)
             host = None
             if e2e and args.e2e_mode == "stream":
@@ -308,12 +318,17 @@ def run_b200(args):
         st = dev.getStatistics()
         vals = torch.tensor([ms, wall_ms, st["CameraRayCount"], st["ShadowRayCount"], st["BounceRayCount"], st["Splats"], st["KernelLaunches"]],
                             dtype=torch.float64, device="cuda")
-        per_rank = [parts + [ms, float(st["CameraRayCount"] + st["ShadowRayCount"] + st["BounceRayCount"])]]
+        per_rank = [parts + [ms, float(st["CameraRayCount"] + st["ShadowRayCount"] + st["BounceRayCount"]), t0 * 1e3]]   # t0: CLOCK_MONOTONIC, comparable across the ranks of one box
         if world > 1:
             mine = torch.tensor(per_rank[0], dtype=torch.float64, device="cuda")
             every = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(every, mine)
             per_rank = [[round(float(x), 3) for x in t_] for t_ in every]
+            first = min(r[5] for r in per_rank)
+            for r in per_rank: r[5] = round(r[5] - first, 3)
+        else:
+            per_rank[0][5] = 0.0
+        if world > 1:
             mx = vals.clone()
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             sm = vals.clone()
@@ -400,7 +415,7 @@ def run_b200(args):
                         "ms_per_step": wall_e / args.steps, "timed": "host wall clock between barriers, max over ranks",
                         "mode": ("every step's accumulated frame streamed to pinned host memory while later steps render (igb200_frame_stream_*), all K frames received inside the timed region"
                                  if args.e2e_mode == "stream" else "render() + synchronous getFramebufferForHost every step")},
-                "per_rank_ms": {"columns": ["issued launches", "flush + drain of the deferred tail", "NCCL gather of the tiles", "total", "rays traced"], "ranks": per_rank},
+                "per_rank_ms": {"columns": ["issued launches", "flush + drain of the deferred tail", "NCCL gather of the tiles (on rank 0 incl. waiting for the last rank)", "total", "rays traced", "host start after the first rank (ms)"], "ranks": per_rank},
                 "rays": tot, "msamples_per_s": w * h * spi * args.steps / (ms * 1e-3) / 1e6, "wall_ms_per_step": wall_ms / args.steps}
         step_bytes = algorithmic_bytes(tot)
         line["roofline_step"] = {"bound": "hbm", "achieved": step_bytes / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
