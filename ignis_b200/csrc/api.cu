@@ -548,6 +548,16 @@ int igb200_version(int* major, int* minor) {
     return 0;
 }
 
+int igb200_device_count(int* count) {
+    if (!count) return fail(-1, "igb200_device_count: count is null");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    int usable = 0;
+    for (int d = 0; d < n; ++d) { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) usable = d + 1; }   // a prefix: contexts are addressed by CUDA ordinal
+    *count = usable;
+    return 0;
+}
+
 int igb200_create(int cuda_device, igb200_ctx** out) {
     if (!out) return fail(-1, "igb200_create: out is null");
     int n = 0;

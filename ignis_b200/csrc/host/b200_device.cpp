@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace igbh {
 
@@ -38,14 +39,55 @@ void B200Device::error(const std::string& what) {
     std::fprintf(stderr, "[igb200] %s\n", what.c_str());   // the reference logs with IG_LOG(L_ERROR) and carries on
 }
 
+// One context per GPU. The reference is one Device per process on one GPU (Device.cpp:1632); this device spreads the frame over the GPUs
+// named by the environment -- IGB200_GPUS = a count or "all" (default 1: exactly the reference's behaviour) -- starting at the target's device
+// index: every context renders its own 32x32 tiles (igb200_comm_init), the frame is assembled on the first GPU when the host or the device
+// side asks for it (igb200_comm_gather_framebuffer). Nothing else of the IRenderDevice surface changes, so igcli / igtrace use the GPUs unchanged.
 B200Device::B200Device(const SetupSettings& settings) : mSetup(settings) {
-    if (igb200_create((int)settings.target.device(), &mCtx) != 0) { error(std::string("cannot create the device: ") + igb200_last_error()); mCtx = nullptr; return; }
+    int visible = 0;
+    if (igb200_device_count(&visible) != 0) visible = 0;
+    int want = 1;
+    if (const char* g = std::getenv("IGB200_GPUS")) want = !std::strcmp(g, "all") ? visible : std::atoi(g);
+    const int first = (int)settings.target.device();
+    if (want < 1 || (want > 1 && first + want > visible)) { error("IGB200_GPUS asks for " + std::to_string(want) + " GPUs from device " + std::to_string(first) + ", " + std::to_string(visible) + " visible"); return; }
+    for (int k = 0; k < want; ++k) {
+        igb200_ctx* c = nullptr;
+        if (igb200_create(first + k, &c) != 0) { error(std::string("cannot create the device: ") + igb200_last_error()); destroyAll(); return; }
+        mCtxs.push_back(c);
+    }
+    mCtx = mCtxs[0];
+    if (want > 1) {
+        uint8_t id[128];
+        if (igb200_comm_unique_id(id) != 0) { error(std::string("NCCL: ") + igb200_last_error()); destroyAll(); return; }
+        if (!forAll([&](igb200_ctx* c, int rank) { return igb200_comm_init(c, rank, want, 32, id); }, "igb200_comm_init")) { destroyAll(); return; }
+    }
     // BVH cache: the reference's CacheManager lives in the loader (LoaderContext, TriMeshProvider.cpp:326-351) and does not reach the device;
     // this device builds its own trees, so it takes the directory from the environment
-    if (const char* dir = std::getenv("IGB200_CACHE_DIR")) { if (*dir && igb200_set_cache_dir(mCtx, dir) != 0) error(igb200_last_error()); }
+    if (const char* dir = std::getenv("IGB200_CACHE_DIR")) { if (*dir) forAll([&](igb200_ctx* c, int) { return igb200_set_cache_dir(c, dir); }, "igb200_set_cache_dir"); }
 }
 
-B200Device::~B200Device() { if (mCtx) igb200_destroy(mCtx); }
+void B200Device::destroyAll() {
+    forAll([](igb200_ctx* c, int) { igb200_comm_destroy(c); return 0; }, "igb200_comm_destroy");
+    for (igb200_ctx* c : mCtxs) igb200_destroy(c);
+    mCtxs.clear(); mCtx = nullptr;
+}
+
+B200Device::~B200Device() { destroyAll(); }
+
+bool B200Device::forAll(const std::function<int(igb200_ctx*, int)>& f, const char* what) {
+    const int n = (int)mCtxs.size();
+    std::vector<int> rc(n, 0);
+    std::vector<std::string> msg(n);
+    auto one = [&](int k) { rc[k] = f(mCtxs[k], k); if (rc[k] != 0) msg[k] = igb200_last_error(); };   // the C ABI's last error is per thread
+    if (n == 1) one(0);
+    else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < n; ++k) th.emplace_back(one, k);
+        for (std::thread& t : th) t.join();
+    }
+    for (int k = 0; k < n; ++k) if (rc[k] != 0) { error(std::string(what) + " (GPU " + std::to_string(k) + "): " + msg[k]); return false; }
+    return true;
+}
 
 // Device.cpp:1667-1670: borrowed pointers, valid for the device's lifetime (Runtime.cpp:532-541). The upload itself waits
 // for the first render(): the material / light / camera descriptors only arrive with the shader set.
@@ -53,7 +95,7 @@ void B200Device::assignScene(const SceneSettings& settings) { mScene = settings;
 
 void B200Device::resize(size_t width, size_t height) {
     if (!mCtx) return;
-    if (igb200_resize(mCtx, (int)width, (int)height) != 0) { error(igb200_last_error()); return; }
+    if (!forAll([&](igb200_ctx* c, int) { return igb200_resize(c, (int)width, (int)height); }, "resize")) return;
     mWidth = width; mHeight = height; mHostPtrs.clear();
 }
 
@@ -61,6 +103,7 @@ void B200Device::resize(size_t width, size_t height) {
 void B200Device::releaseAll() { mSceneDirty = true; }
 
 bool B200Device::setPartition(int rank, int world, int tile) {
+    if (mCtxs.size() > 1) { error("setPartition: this device already spreads the frame over its own GPUs (IGB200_GPUS)"); return false; }
     if (!mCtx || igb200_set_partition(mCtx, rank, world, tile) != 0) { error(igb200_last_error()); return false; }
     return true;
 }
@@ -89,7 +132,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
         if (!light_stage) throw RecognizeError{"no stage carries the light tables"};
         // Normals / Albedo AOVs requested by the wrapped technique (runtime flag --no-std-aovs removes the wrapper)
         if ((int)light_stage->std_aovs != mStdAovs) {   // only on a change: setting an option synchronises the device
-            if (igb200_set_option(mCtx, "std_aovs", light_stage->std_aovs ? 1 : 0) != 0) throw RecognizeError{igb200_last_error()};
+            if (!forAll([&](igb200_ctx* c, int) { return igb200_set_option(c, "std_aovs", light_stage->std_aovs ? 1 : 0); }, "std_aovs")) throw RecognizeError{mError};
             mStdAovs = (int)light_stage->std_aovs;
         }
         resolve_lights(*light_stage, Registries{light_local, global}, inf, fin);
@@ -134,7 +177,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     d.camera = camera; d.technique = technique;
     d.selector_data = selector_data.empty() ? nullptr : selector_data.data(); d.n_selector_data = (int32_t)selector_data.size();
     for (int k = 0; k < 3; ++k) { d.bbox_min[k] = db.SceneBBox.min(k); d.bbox_max[k] = db.SceneBBox.max(k); }
-    if (igb200_set_scene(mCtx, &d) != 0) { error(std::string("scene upload failed: ") + igb200_last_error()); return false; }
+    if (!forAll([&](igb200_ctx* c, int) { return igb200_set_scene(c, &d); }, "scene upload")) return false;   // the scene is replicated
     mDescriptorBytes.swap(bytes);
     mSceneDirty = false;
     return true;
@@ -159,13 +202,15 @@ void B200Device::render(const IG::TechniqueVariantShaderSet& shader_set, const R
             o.dir[0] = dx / n; o.dir[1] = dy / n; o.dir[2] = dz / n;
             o.tmin = r.Range(0); o.tmax = r.Range(1);
         }
-        rc = igb200_render(mCtx, &st, rays.data(), rays.size());
+        rc = forAll([&](igb200_ctx* c, int) { return igb200_render(c, &st, rays.data(), rays.size()); }, "render") ? 0 : -1;
         mWidth = settings.width; mHeight = 1;
     } else {
-        rc = igb200_render(mCtx, &st, nullptr, 0);
+        // asynchronous: every GPU is left working on its tiles when this returns
+        rc = 0;
+        for (igb200_ctx* c : mCtxs) if (igb200_render(c, &st, nullptr, 0) != 0) { rc = -1; error(std::string("render failed: ") + igb200_last_error()); break; }
         mWidth = settings.width; mHeight = settings.height;
     }
-    if (rc != 0) error(std::string("render failed: ") + igb200_last_error());
+    (void)rc;
 }
 
 static const char* aov_name(const std::string& name) { return (name.empty() || name == "Color") ? nullptr : name.c_str(); }
@@ -173,23 +218,34 @@ static const char* aov_name(const std::string& name) { return (name.empty() || n
 // Device.cpp:1419-1451: RGB f32, W*H*3, owned by the device, valid until resize.
 IG::IRenderDevice::AOVAccessor B200Device::getFramebufferForHost(const std::string& name, bool) {
     float* p = nullptr;
-    if (!mCtx || igb200_framebuffer(mCtx, aov_name(name), &p) != 0) { error(igb200_last_error()); return AOVAccessor{nullptr}; }
+    if (!mCtx) { error("no device"); return AOVAccessor{nullptr}; }
+    if (mCtxs.size() > 1) {   // every GPU sends its tiles to the first one, which assembles the frame and copies it to pinned host memory
+        const char* aov = aov_name(name) ? name.c_str() : "";
+        if (!forAll([&](igb200_ctx* c, int rank) { return igb200_comm_gather_framebuffer(c, aov, nullptr, rank == 0 ? &p : nullptr); }, "framebuffer gather")) return AOVAccessor{nullptr};
+    } else if (igb200_framebuffer(mCtx, aov_name(name), &p) != 0) { error(igb200_last_error()); return AOVAccessor{nullptr}; }
     mHostPtrs[aov_name(name) ? name : std::string()] = p;
     return AOVAccessor{p};
 }
 IG::IRenderDevice::AOVAccessor B200Device::getFramebufferForDevice(const std::string& name, bool) {
     float* p = nullptr;
-    if (!mCtx || igb200_framebuffer_device(mCtx, aov_name(name), &p) != 0) { error(igb200_last_error()); return AOVAccessor{nullptr}; }
+    if (!mCtx) { error("no device"); return AOVAccessor{nullptr}; }
+    if (mCtxs.size() > 1) {
+        const char* aov = aov_name(name) ? name.c_str() : "";
+        if (!forAll([&](igb200_ctx* c, int rank) { return igb200_comm_gather_framebuffer(c, aov, rank == 0 ? &p : nullptr, nullptr); }, "framebuffer gather")) return AOVAccessor{nullptr};
+        if (igb200_sync(mCtx) != 0) { error(igb200_last_error()); return AOVAccessor{nullptr}; }   // the assembled frame is complete when the pointer is handed out
+    } else if (igb200_framebuffer_device(mCtx, aov_name(name), &p) != 0) { error(igb200_last_error()); return AOVAccessor{nullptr}; }
     return AOVAccessor{p};
 }
-void B200Device::clearFramebuffer(const std::string& name) { if (mCtx && igb200_clear(mCtx, aov_name(name)) != 0) error(igb200_last_error()); }
-void B200Device::clearAllFramebuffer() { if (mCtx && igb200_clear(mCtx, nullptr) != 0) error(igb200_last_error()); }
+void B200Device::clearFramebuffer(const std::string& name) { if (mCtx) forAll([&](igb200_ctx* c, int) { return igb200_clear(c, aov_name(name)); }, "clear"); }
+void B200Device::clearAllFramebuffer() { if (mCtx) forAll([](igb200_ctx* c, int) { return igb200_clear(c, nullptr); }, "clear"); }
 // Device.cpp:1724-1736: pushes the host copy the caller may have modified back to the device
 void B200Device::syncFramebufferHostToDevice(const std::string& name) {
     if (!mCtx) return;
     const auto it = mHostPtrs.find(aov_name(name) ? name : std::string());   // the host copy of THIS AOV, never another one's
     if (it == mHostPtrs.end() || !it->second) return;                      // never mapped for the host: nothing the caller could have changed
-    if (igb200_upload_framebuffer(mCtx, aov_name(name), it->second) != 0) error(igb200_last_error());
+    // several GPUs: each keeps the whole frame but only its own tiles are ever gathered, so all of them take the upload
+    float* host = it->second;
+    forAll([&](igb200_ctx* c, int) { return igb200_upload_framebuffer(c, aov_name(name), host); }, "framebuffer upload");
 }
 // Device.cpp:1724-1736 maps every AOV: here every AOV the host has a copy of
 void B200Device::syncAllFramebufferHostToDevice() {
@@ -213,10 +269,16 @@ const IG::Statistics* B200Device::getStatistics() {
     return &mStats;
 }
 bool B200Device::rayCounters(uint64_t out[3], double* render_ms) {
-    uint64_t s[5]; double ms = 0;
-    if (!mCtx || igb200_stats(mCtx, s, &ms) != 0) return false;
-    out[0] = s[0]; out[1] = s[1]; out[2] = s[2];
-    if (render_ms) *render_ms = ms;
+    if (!mCtx) return false;
+    out[0] = out[1] = out[2] = 0;
+    double ms_max = 0;
+    for (igb200_ctx* c : mCtxs) {   // rays add up over the GPUs, time is the slowest GPU's
+        uint64_t s[5]; double ms = 0;
+        if (igb200_stats(c, s, &ms) != 0) return false;
+        out[0] += s[0]; out[1] += s[1]; out[2] += s[2];
+        if (ms > ms_max) ms_max = ms;
+    }
+    if (render_ms) *render_ms = ms_max;
     return true;
 }
 

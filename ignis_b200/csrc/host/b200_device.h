@@ -8,6 +8,7 @@
 // Method for method the behaviour is the reference's; what differs is documented at each member in b200_device.cpp.
 #pragma once
 
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -35,6 +36,7 @@ public:
     explicit B200Device(const SetupSettings& settings);
     ~B200Device() override;
     bool valid() const { return mCtx != nullptr; }
+    int gpuCount() const { return (int)mCtxs.size(); }
 
     void assignScene(const SceneSettings& settings) override;
     void render(const IG::TechniqueVariantShaderSet& shader_set, const RenderSettings& settings, IG::ParameterSet* parameter_set) override;
@@ -68,10 +70,16 @@ public:
 private:
     bool uploadScene(const IG::TechniqueVariantShaderSet& shader_set, const IG::ParameterSet* global);
     void error(const std::string& what);
+    // Runs f(context, rank) on every GPU of the device -- on one thread per GPU when there are several (NCCL calls of the ranks of one
+    // process must not be serialised: a rank's send completes only once the root's receive is posted, and connections are made lazily by
+    // both sides). Returns false and reports the first failure otherwise.
+    bool forAll(const std::function<int(igb200_ctx*, int)>& f, const char* what);
+    void destroyAll();
 
     SetupSettings mSetup;
     SceneSettings mScene{};
-    igb200_ctx* mCtx = nullptr;
+    igb200_ctx* mCtx = nullptr;              // rank 0: the GPU the frame is assembled on
+    std::vector<igb200_ctx*> mCtxs;          // one context per GPU (IGB200_GPUS), mCtxs[0] == mCtx
     size_t mWidth = 0, mHeight = 0;
     bool mSceneDirty = true;
     int mStdAovs = -1;                       // Normals / Albedo AOVs currently enabled on the device (-1: not set yet)

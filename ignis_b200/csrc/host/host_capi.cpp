@@ -136,6 +136,7 @@ float* igbh_device_framebuffer(IRenderDevice* d, const char* name) {
     return p;
 }
 void igbh_device_clear(IRenderDevice* d) { d->clearAllFramebuffer(); }
+int igbh_device_gpu_count(IRenderDevice* d) { return static_cast<igbh::B200Device*>(d)->gpuCount(); }
 int igbh_device_stats(IRenderDevice* d, uint64_t out[3]) {
     if (!d->getStatistics()) return -1;   // the interface call (its counters are private, as in the reference) ...
     return static_cast<igbh::B200Device*>(d)->rayCounters(out) ? 0 : -1;   // ... and the figures it was filled from

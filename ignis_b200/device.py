@@ -66,7 +66,7 @@ RAY_DTYPE = np.dtype([("org", "<f4", 3), ("dir", "<f4", 3), ("tmin", "<f4"), ("t
 HIT_DTYPE = np.dtype([("ent_id", "<i4"), ("prim_id", "<i4"), ("t", "<f4"), ("u", "<f4"), ("v", "<f4")])
 
 # every symbol include/igb200.h declares (checked by tests/test_abi.py)
-SYMBOLS = ["igb200_last_error", "igb200_version", "igb200_create", "igb200_destroy", "igb200_set_scene", "igb200_resize",
+SYMBOLS = ["igb200_last_error", "igb200_version", "igb200_device_count", "igb200_create", "igb200_destroy", "igb200_set_scene", "igb200_resize",
            "igb200_set_partition", "igb200_render", "igb200_sync", "igb200_framebuffer", "igb200_framebuffer_device", "igb200_clear",
            "igb200_upload_framebuffer", "igb200_stats", "igb200_reset_stats", "igb200_kernel_times", "igb200_launch_profile", "igb200_turn_log", "igb200_step_stats", "igb200_set_option",
            "igb200_stream", "igb200_trace_closest", "igb200_trace_any", "igb200_bench_trace", "igb200_test_detmath",

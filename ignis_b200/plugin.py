@@ -23,7 +23,7 @@ SYMBOLS = ["ig_get_interface", "igbh_last_error", "igbh_interface_version", "igb
            "igbh_params_set_vec3", "igbh_params_set_color", "igbh_compile", "igbh_describe_material", "igbh_describe_lights", "igbh_describe_technique",
            "igbh_describe_camera", "igbh_set_create", "igbh_set_destroy", "igbh_set_raygen", "igbh_set_miss", "igbh_set_add_hit", "igbh_device_create",
            "igbh_device_destroy", "igbh_device_assign", "igbh_assign_release", "igbh_device_render", "igbh_device_resize", "igbh_device_framebuffer",
-           "igbh_device_clear", "igbh_device_stats"]
+           "igbh_device_clear", "igbh_device_stats", "igbh_device_gpu_count"]
 
 
 def lib():
@@ -72,6 +72,7 @@ def lib():
         L.igbh_device_framebuffer.argtypes = [vp, C.c_char_p]
         L.igbh_device_clear.argtypes = [vp]
         L.igbh_device_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.igbh_device_gpu_count.argtypes = [vp]
         _LIB = L
     return _LIB
 
@@ -200,6 +201,10 @@ class PluginRuntime:
         if not p:
             raise DeviceError(_err())
         return np.ctypeslib.as_array(p, shape=(self.height, self.width, 3))
+
+    def gpuCount(self) -> int:
+        """GPUs behind this one device (environment IGB200_GPUS, b200_device.cpp)."""
+        return int(lib().igbh_device_gpu_count(self.dev))
 
     def getStatistics(self):
         out = (C.c_uint64 * 3)()

@@ -214,6 +214,7 @@ typedef struct igb200_hit {
 const char* igb200_last_error(void);
 int igb200_version(int* major, int* minor);                       /* IDeviceInterface::getVersion, Interface.cpp:24-27 */
 
+int igb200_device_count(int* count);                                  /* sm_100 devices visible to this process (0 is not an error); Device.cpp:1632 knows exactly one */
 int igb200_create(int cuda_device, igb200_ctx** out);             /* IDeviceInterface::createRenderDevice, Interface.cpp:34-57 */
 int igb200_destroy(igb200_ctx* ctx);                              /* IRenderDevice::~IRenderDevice */
 

@@ -147,3 +147,62 @@ def test_trace_through_cpp_plugin_matches_direct_abi():
         ref = rt2.trace(n)
     assert np.isfinite(got).all() and ref.sum() > 0
     np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5)
+
+
+def _visible_gpus():
+    n = C.c_int(0)
+    from ignis_b200 import device
+    try:
+        device.lib().igb200_device_count(C.byref(n))
+    except Exception:
+        return 0
+    return n.value
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,w,h,spi", [("diamond_scene.json", 200, 120, 2), ("evaluation/multilight-hierarchy.json", 96, 96, 2)])
+def test_plugin_device_spreads_the_frame_over_its_gpus(name, w, h, spi, monkeypatch):
+    """IGB200_GPUS: one B200Device, several GPUs behind it (tiles + NCCL gather inside the plugin) -- same frame, same counters, AOVs included;
+    igtrace's list emitter as well."""
+    if _visible_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle.oracle import Oracle
+    from ignis_b200.device import RAY_DTYPE
+    monkeypatch.setenv("IGB200_GPUS", "2")
+    t = scene(name)
+    o = Oracle(t)
+    ref = np.zeros((h, w, 3), np.float32)
+    for it in range(3):
+        o.render(w, h, spi=spi, iteration=it, fb=ref)
+    with plugin.PluginRuntime(t, w, h, spi) as rt:
+        assert rt.gpuCount() == 2
+        rt.step()
+        rt.step()
+        first = rt.getFramebufferForHost().copy()      # a gather in the middle of the run must not disturb it
+        rt.step()
+        got = rt.getFramebufferForHost().copy()
+        normals = rt.getFramebufferForHost("Normals").copy()
+        stats = rt.getStatistics()
+    assert np.isfinite(first).all() and first.sum() > 0
+    err = float(np.linalg.norm((got - ref).ravel()) / np.linalg.norm(ref.ravel()))
+    assert err <= 1e-4, err
+    assert (stats["CameraRayCount"], stats["ShadowRayCount"], stats["BounceRayCount"]) == tuple(int(x) for x in o.counters)
+    monkeypatch.setenv("IGB200_GPUS", "1")
+    with plugin.PluginRuntime(t, w, h, spi) as rt1:
+        assert rt1.gpuCount() == 1
+        rt1.step()
+        n1 = rt1.getFramebufferForHost("Normals").copy()
+    np.testing.assert_allclose(normals, n1, rtol=1e-5, atol=1e-6)   # written at iteration 0 only
+    # igtrace through two GPUs
+    monkeypatch.setenv("IGB200_GPUS", "2")
+    rng = np.random.default_rng(7)
+    rays = np.zeros(4096, RAY_DTYPE)
+    rays["org"] = rng.uniform(t.bbox_min, t.bbox_max, (4096, 3))
+    rays["dir"] = rng.normal(size=(4096, 3))
+    rays["tmin"], rays["tmax"] = 1e-3, 1e30
+    with plugin.PluginRuntime(t, 4096, 1, 1, tracer=True) as rt2:
+        two = rt2.trace(rays)
+    monkeypatch.setenv("IGB200_GPUS", "1")
+    with plugin.PluginRuntime(t, 4096, 1, 1, tracer=True) as rt3:
+        one = rt3.trace(rays)
+    np.testing.assert_allclose(two, one, rtol=1e-4, atol=1e-5)
