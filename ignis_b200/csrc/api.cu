@@ -220,6 +220,7 @@ struct igb200_ctx {
     int carveout = -1;                 // option: preferred shared-memory carve-out of the trace kernels in percent (-1: the driver's choice)
     int stage_partial = 0;             // 1: stage the prefix that fits even if the scene does not fit as a whole
     int refill = 24, min_blocks = 2, vote = 2;
+    int drain_turns = -1;               // split turns at the start of a drain (-1: from the number of paths that may be waiting)
     int shade_sync = 1;                 // k_turn_shade keeps the warps of a CTA in step with block barriers (wavefront.cuh phase_shade_cta): 0 off, 1 on
     int wave_skip = 1;                  // a step ends with its split turns when nothing forces the persistent kernel to run (wavefront.cuh k_wavefront)
     int split_turns = -1;               // leading turns of an iteration run as separate shade / trace launches (0: all in the persistent kernel)
@@ -308,17 +309,17 @@ static int configure_kernels(igb200_ctx* c) {
     // All or nothing: a partial copy costs more than it saves -- the shared memory it takes is L1 cache the rest of the scene then
     // misses (1920x1080x4: synthetic_room 10.34 -> 9.84 ms, primitives 2.98 -> 2.81 ms with nothing staged). "stage_partial" = 1
     // brings the greedy prefix back.
-    if (!c->stage_partial && (int64_t)s.n_ent * 128 + (int64_t)s.n_nodes * 256 + (int64_t)s.n_tris * 48 > left) left = 0;
+    if (!c->stage_partial && (int64_t)s.n_ent * STAGED_LEAF_BYTES + (int64_t)s.n_nodes * STAGED_NODE_BYTES + (int64_t)s.n_tris * 48 > left) left = 0;
     // entity leaves first (every ray reads them), then nodes (top of every tree first in memory order), then triangles
-    c->stage_ent = (int)std::min<int64_t>(s.n_ent, left / 128); left -= (int64_t)c->stage_ent * 128;
-    c->stage_nodes = (int)std::min<int64_t>(s.n_nodes, left / 256); left -= (int64_t)c->stage_nodes * 256;
+    c->stage_ent = (int)std::min<int64_t>(s.n_ent, left / STAGED_LEAF_BYTES); left -= (int64_t)c->stage_ent * STAGED_LEAF_BYTES;
+    c->stage_nodes = (int)std::min<int64_t>(s.n_nodes, left / STAGED_NODE_BYTES); left -= (int64_t)c->stage_nodes * STAGED_NODE_BYTES;
     c->stage_tris = (int)std::min<int64_t>(s.n_tris, left / 48);
     c->stage_where = (c->stage_ent == s.n_ent && c->stage_nodes == s.n_nodes && c->stage_tris == s.n_tris) ? 1 : 0;
     if (!c->specialise_where) c->stage_where = 0;
-    c->smem_bytes = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)c->stage_ent * 128 + (size_t)c->stage_nodes * 256 + (size_t)c->stage_tris * 48;
+    c->smem_bytes = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)c->stage_ent * STAGED_LEAF_BYTES + (size_t)c->stage_nodes * STAGED_NODE_BYTES + (size_t)c->stage_tris * 48;
     // the merged tree (small scenes): walked by the split-turn trace kernel and the trace hooks when the two-level scene is staged as a whole
     c->flat_on = c->flat_option != 0 && s.n_flat_nodes > 0 && c->stage_where == 1 && c->vote != 0 &&
-                 (int64_t)s.n_flat_nodes * 256 + (int64_t)s.n_tris * 48 + (int64_t)s.n_ent * 128 <= c->stage_budget;
+                 (int64_t)s.n_flat_nodes * STAGED_NODE_BYTES + (int64_t)s.n_tris * 48 + (int64_t)s.n_ent * STAGED_LEAF_BYTES <= c->stage_budget;
     c->flat_global = !c->flat_on && c->flat_option >= 2 && s.n_flat_nodes > 0 && c->vote != 0 && c->stage_nodes == 0 && c->stage_tris == 0 && c->stage_ent == 0;
     if (c->flat_global) {
         const size_t smem = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2);
@@ -327,7 +328,7 @@ static int configure_kernels(igb200_ctx* c) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbg, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, 2, true), WF_BLOCK, smem));
         if (nbg < 1) c->flat_global = false; else c->grid_turn_trace_flat = nbg * c->n_sm;
     }
-    c->smem_flat = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)s.n_ent * 128 + (size_t)s.n_flat_nodes * 256 + (size_t)s.n_tris * 48;
+    c->smem_flat = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)s.n_ent * STAGED_LEAF_BYTES + (size_t)s.n_flat_nodes * STAGED_NODE_BYTES + (size_t)s.n_tris * 48;
     for (int full = 0; full < 2; ++full) CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote, full != 0, c->stage_where), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CU(cudaFuncSetAttribute((const void*)trace_kernel(c->min_blocks, c->vote), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     int nb = 0;
@@ -350,7 +351,7 @@ static int configure_kernels(igb200_ctx* c) {
         c->flat_block = WF_BLOCK;
         if (c->flat_on && c->flat_block_option != WF_BLOCK) {   // ray records staged through shared memory, if the larger CTA fits as often as it must
             const int blk = c->flat_block_option, want = blk == 768 ? 1 : 2;
-            const size_t scene = ((size_t)s.n_ent * 128 + (size_t)s.n_flat_nodes * 256 + (size_t)s.n_tris * 48 + 127) & ~(size_t)127;
+            const size_t scene = ((size_t)s.n_ent * STAGED_LEAF_BYTES + (size_t)s.n_flat_nodes * STAGED_NODE_BYTES + (size_t)s.n_tris * 48 + 127) & ~(size_t)127;
             const size_t smem = (size_t)SMEM_STACK * blk * sizeof(uint2) + scene + (size_t)(blk / 32) * STAGE_WARP_BYTES;
             int nbs = 0;
             if (cudaFuncSetAttribute((const void*)flat_staged_kernel(blk), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
@@ -513,7 +514,7 @@ static int drain(igb200_ctx* c) {
     if (c->maybe_carry) {
         CU(cudaSetDevice(c->device));
         // up to `last_defer` paths may be waiting: their first turns are still big enough for the split kernels
-        const int turns = c->split_turns >= 0 ? c->split_turns : (int)std::min<long long>(8, c->last_defer >> 19);   // measured: 9.90 -> 9.51 ms per drained step with 4 -> 12
+        const int turns = c->drain_turns >= 0 ? c->drain_turns : c->split_turns >= 0 ? c->split_turns : (int)std::min<long long>(8, c->last_defer >> 19);   // measured: 9.90 -> 9.51 ms per drained step with 4 -> 12
         { const int r = launch_split_turns(c, make_params(c, c->last_rp, c->last_sc, 0, nullptr, 0), turns); if (r) return r; }
         const int r = launch_wave(c, c->last_rp, c->last_sc, 0, nullptr, 0);
         if (r) return r;
@@ -618,6 +619,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "wide_rays_per_group")) { if (value < 0) return fail(-1, "wide_rays_per_group must be >= 0"); c->wide_rays_per_group = value; return 0; }
     if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 8000) return fail(-1, "defer_permille must be in [0, 8000]"); c->defer_permille = (int)value; return 0; }
     if (!strcmp(name, "profile_kernels")) { c->profile = value != 0; return 0; }
+    if (!strcmp(name, "drain_turns")) { if (value < -1 || value > 64) return fail(-1, "drain_turns must be in [-1, 64]"); c->drain_turns = (int)value; return 0; }
     if (!strcmp(name, "shade_sync")) { if (value < 0 || value > 1) return fail(-1, "shade_sync must be 0 or 1"); c->shade_sync = (int)value; return 0; }
     if (!strcmp(name, "wave_skip")) { if (value < 0 || value > 1) return fail(-1, "wave_skip must be 0 or 1"); { const int r = drain(c); if (r) return r; } c->wave_skip = (int)value; return 0; }
     if (!strcmp(name, "refill")) { if (value < 1 || value > 32) return fail(-1, "refill must be in [1, 32]"); c->refill = (int)value; return 0; }
@@ -877,7 +879,7 @@ int igb200_set_scene(igb200_ctx* c, const igb200_scene_desc* d) {
         for (int s = 0; s < d->n_shapes && ok; ++s) ok = d->shape_lookups[s].type_id == IGB200_SHAPE_TRIMESH;
         size_t flat_nodes_n = top.nodes.size();
         for (int i = 0; i < d->n_entities && ok; ++i) flat_nodes_n += shape_root[d->leaves[i].shape_id] > 0 ? shape_node_count[d->leaves[i].shape_id] : 0;
-        ok = ok && ((int64_t)flat_nodes_n * 256 + (int64_t)tri_prim.size() * 48 + (int64_t)d->n_entities * 128 <= c->stage_budget ||   // all of it staged in shared memory ...
+        ok = ok && ((int64_t)flat_nodes_n * STAGED_NODE_BYTES + (int64_t)tri_prim.size() * 48 + (int64_t)d->n_entities * STAGED_LEAF_BYTES <= c->stage_budget ||   // all of it staged in shared memory ...
                     (c->flat_option >= 2 && (int64_t)flat_nodes_n * 256 <= c->flat_max_bytes));                                                 // ... or walked in global memory
         if (ok) {
             flat.assign(top.nodes.begin(), top.nodes.end());

@@ -114,6 +114,13 @@ struct Stack {
 };
 
 // Scene arrays (or their first part) staged in shared memory; indices beyond the staged count read global memory.
+// The staged copies are PADDED: a node (256 B) every 272 bytes, an entity leaf (128 B) every 144 bytes. Lanes of a warp read the same row of
+// DIFFERENT nodes (e.g. the near x planes, a float4 each); with a stride that is a multiple of 128 bytes all of those land in the same four
+// banks and the load is replayed once per lane (ncu, unpadded: 55 M bank conflicts and 116 M shared-load wavefronts per launch, the LSU shared
+// pipe 59 % busy; padded: 19 M / 80 M / 44 % -- profiles/r6_trace_experiments.txt). One extra float4 per element rotates the bank group with
+// the index. Triangles (48 B) are spread already. The kernel's time did not move: it is not bound by the shared-memory pipe.
+constexpr int STAGED_NODE_F4 = 17, STAGED_LEAF_F4 = 9;
+constexpr int STAGED_NODE_BYTES = STAGED_NODE_F4 * 16, STAGED_LEAF_BYTES = STAGED_LEAF_F4 * 16;
 struct Staged {
     const float4* nodes;    int n_nodes;
     const float4* tris;     int n_tris;
@@ -124,9 +131,9 @@ struct Staged {
 // 2 are what actually runs; 0 remains for the "stage_partial" option and the kernels that are not specialised.
 template <int WHERE = 0>
 __device__ __forceinline__ const float4* node_ptr(const DevScene& sc, const Staged& sg, int node) {
-    if (WHERE == 1) return sg.nodes + node * 16;
+    if (WHERE == 1) return sg.nodes + node * STAGED_NODE_F4;
     if (WHERE == 2) return sc.nodes + (size_t)node * 16;
-    return node < sg.n_nodes ? sg.nodes + node * 16 : sc.nodes + (size_t)node * 16;
+    return node < sg.n_nodes ? sg.nodes + node * STAGED_NODE_F4 : sc.nodes + (size_t)node * 16;
 }
 template <int WHERE = 0>
 __device__ __forceinline__ const float4* tri_ptr(const DevScene& sc, const Staged& sg, int slot) {
@@ -136,9 +143,9 @@ __device__ __forceinline__ const float4* tri_ptr(const DevScene& sc, const Stage
 }
 template <int WHERE = 0>
 __device__ __forceinline__ const float4* leaf_ptr(const DevScene& sc, const Staged& sg, int slot) {
-    if (WHERE == 1) return sg.ent_leaf + slot * 8;
+    if (WHERE == 1) return sg.ent_leaf + slot * STAGED_LEAF_F4;
     if (WHERE == 2) return sc.ent_leaf + (size_t)slot * 8;
-    return slot < sg.n_ent ? sg.ent_leaf + slot * 8 : sc.ent_leaf + (size_t)slot * 8;
+    return slot < sg.n_ent ? sg.ent_leaf + slot * STAGED_LEAF_F4 : sc.ent_leaf + (size_t)slot * 8;
 }
 
 // Ray state bits
