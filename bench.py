@@ -344,6 +344,12 @@ def run_b200(args):
     ms, wall_ms, tot, clocks, _ = timed(e2e=False)
     per_rank = timed.per_rank
     if args.e2e_mode == "stream":
+        if world > 1 and not args.no_shared_frames:
+            # the ranks of one box hand their tiles of every frame to rank 0 through shared pinned host memory (each GPU over its own PCIe link)
+            # instead of gathering them on rank 0's GPU and copying K whole frames through ONE link (igb200_frame_stream_share)
+            keys = [int.from_bytes(os.urandom(3), "little") + 0x1000000 if rank == 0 else None]
+            dist.broadcast_object_list(keys, src=0)
+            dev.frameStreamShare(keys[0])
         dev.frameStreamBegin(32 if world > 1 else 16)
         for _ in range(2):                 # warm the streaming path: pinned frame buffers are allocated on first use
             rt.step()
@@ -413,7 +419,9 @@ def run_b200(args):
                 "clocks": clocks, "gpu_launches": tot["KernelLaunches"],
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": w * h * 12,
                         "ms_per_step": wall_e / args.steps, "timed": "host wall clock between barriers, max over ranks",
-                        "mode": ("every step's accumulated frame streamed to pinned host memory while later steps render (igb200_frame_stream_*), all K frames received inside the timed region"
+                        "mode": (("every step's accumulated frame streamed to pinned host memory while later steps render (igb200_frame_stream_*), all K frames received inside the timed region"
+                                  + ("; the frames live in shared pinned host memory that every rank writes its own tiles into (igb200_frame_stream_share), rank 0 takes each "
+                                     "frame once all ranks have flagged it" if world > 1 and not args.no_shared_frames else ("; every frame gathered onto rank 0's GPU (NCCL) and copied from there" if world > 1 else "")))
                                  if args.e2e_mode == "stream" else "render() + synchronous getFramebufferForHost every step")},
                 "per_rank_ms": {"columns": ["issued launches", "flush + drain of the deferred tail", "NCCL gather of the tiles (on rank 0 incl. waiting for the last rank)", "total", "rays traced", "host start after the first rank (ms)"], "ranks": per_rank},
                 "rays": tot, "msamples_per_s": w * h * spi * args.steps / (ms * 1e-3) / 1e6, "wall_ms_per_step": wall_ms / args.steps}
@@ -498,6 +506,7 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-shared-frames", action="store_true", help="e2e at N > 1: gather every frame on rank 0's GPU and copy it from there (the round-2 default before r6)")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config (default: the headline one, c2)")
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)

@@ -11,6 +11,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cerrno>
+#include <thread>
+#include <sys/ipc.h>
+#include <sys/shm.h>
 #include <deque>
 #include <string>
 #include <vector>
@@ -58,6 +62,7 @@ static WaveKernel turn_trace_kernel(int blocks, int vote, int where, bool flat =
     if (flat && where == 2) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 2, true> : k_turn_trace<WF_BLOCK, 2, 2, 2, true>;   // merged tree read from global memory (large scenes)
     if (flat) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 1, true> : k_turn_trace<WF_BLOCK, 2, 2, 1, true>;   // merged tree (small scenes, staged)
     if (vote && where == 1) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 1> : k_turn_trace<WF_BLOCK, 2, 2, 1>;
+    if (vote && where == 2) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 2> : k_turn_trace<WF_BLOCK, 2, 2, 2>;   // nothing staged: nodes through 256-bit global loads
     if (vote) return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 2, 0> : k_turn_trace<WF_BLOCK, 2, 2, 0>;
     return blocks >= 3 ? k_turn_trace<WF_BLOCK, 3, 0, 0> : k_turn_trace<WF_BLOCK, 2, 0, 0>;
 }
@@ -103,6 +108,27 @@ __global__ void k_publish(float* __restrict__ acc, float* __restrict__ slot, flo
         acc[i] = r; slot[i] = 0.0f;
         if (snap) snap[i] = r;
     }
+}
+
+// Frame streaming over several ranks with the frames in SHARED host memory (igb200_frame_stream_share): every rank writes the pixels of its own
+// tiles of the snapshot straight into the host frame (zero-copy stores into the mapped segment, each GPU over its own PCIe link), then raises
+// its flag for that frame. Rank 0's host sees a frame complete when every rank's flag carries the frame's sequence number.
+__global__ void k_tiles_to_host(const float* __restrict__ snap, float* __restrict__ host_frame, const int* __restrict__ tile_table, int n_tiles, int tile, int tiles_x, int width, int height) {
+    const int row_words = tile * 3;                                   // one tile row = tile pixels x rgb, contiguous in the frame
+    const long long n = (long long)n_tiles * tile * row_words;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / ((long long)tile * row_words));
+        const int r = (int)(i - (long long)k * tile * row_words);
+        const int ty = r / row_words, w = r - ty * row_words;
+        const int t = tile_table ? tile_table[k] : k;
+        const int x0 = (t % tiles_x) * tile, y = (t / tiles_x) * tile + ty;
+        if (y < height && x0 * 3 + w < width * 3) { const size_t o = ((size_t)y * width + x0) * 3 + w; host_frame[o] = snap[o]; }
+    }
+}
+__global__ void k_raise_flag(volatile unsigned int* flag, unsigned int seq) {
+    __threadfence_system();   // the frame's words (written by the kernel before this one on the same stream) before the flag
+    *flag = seq;
+    __threadfence_system();
 }
 
 // Deterministic accumulation: folds the per-sample slots of one iteration into the frame in sample order and clears them. One thread per
@@ -215,6 +241,8 @@ struct igb200_ctx {
     int stage_nodes = 0, stage_tris = 0, stage_ent = 0;
     size_t smem_bytes = 0;
     int64_t stage_budget = 40 * 1024;  // bytes of shared memory per CTA for the staged scene copy
+    int turn_where = 0;                // ... of the split-turn trace kernel: as stage_where, or 2 = nothing staged (option "wide_loads")
+    int wide_loads = 0;                // measured slower (+9 % trace on synthetic_room, profiles/r6_trace_experiments.txt): off
     int stage_where = 0;               // 1: the whole scene is staged in shared memory, 0: not (selects the k_turn_trace variant)
     int specialise_where = 1;          // option: 0 = always use the generic (per index) trace kernel
     int carveout = -1;                 // option: preferred shared-memory carve-out of the trace kernels in percent (-1: the driver's choice)
@@ -272,7 +300,7 @@ struct igb200_ctx {
     size_t fs_n4 = 0;                               // float4 per (padded) frame
     struct FsIter { int iter; long long shades_left; };
     std::deque<FsIter> fs_inflight;                 // iterations generated but not yet known to be finished, oldest first
-    struct FsFrame { int iter; int host; cudaEvent_t copied; };
+    struct FsFrame { int iter; int host; cudaEvent_t copied; unsigned int seq; };
     std::deque<FsFrame> fs_ready;                   // published frames the caller has not taken yet, oldest first
     std::vector<float*> fs_host;                    // pinned frames
     std::vector<int> fs_host_free;
@@ -281,6 +309,15 @@ struct igb200_ctx {
     bool fs_snap_used[2] = {false, false};
     long long fs_published = 0;
     int fs_last_taken_host = -1;
+    // frames in shared host memory (igb200_frame_stream_share): a System V segment every rank attaches and pins
+    int fs_share_key = 0;                           // 0: off
+    int fs_shm_id = -1;
+    unsigned char* fs_shm = nullptr;                // [header: consumed (64 B), flags[frame][64] u32] [frames]
+    unsigned char* fs_shm_dev = nullptr;            // the same bytes as the GPU sees them
+    size_t fs_shm_bytes = 0, fs_shm_frame_bytes = 0, fs_shm_header = 0;
+    int fs_shm_frames = 0;                          // host frames in the segment
+    bool fs_shm_retry = false;
+    bool fs_taken_shared = false;                   // the caller holds a frame of the segment (released at the next call)
     // multi-GPU exchange (igb200_comm_*)
     ncclComm_t comm = nullptr;
     DevBuf<float> comm_send, comm_recv, comm_frame;
@@ -316,6 +353,8 @@ static int configure_kernels(igb200_ctx* c) {
     c->stage_tris = (int)std::min<int64_t>(s.n_tris, left / 48);
     c->stage_where = (c->stage_ent == s.n_ent && c->stage_nodes == s.n_nodes && c->stage_tris == s.n_tris) ? 1 : 0;
     if (!c->specialise_where) c->stage_where = 0;
+    // the split-turn trace kernel also exists for "nothing staged" (large scenes): nodes come through 256-bit global loads (traverse.cuh node_step_global8)
+    c->turn_where = (c->wide_loads && c->vote && c->stage_ent == 0 && c->stage_nodes == 0 && c->stage_tris == 0) ? 2 : c->stage_where;
     c->smem_bytes = (size_t)SMEM_STACK * WF_BLOCK * sizeof(uint2) + (size_t)c->stage_ent * STAGED_LEAF_BYTES + (size_t)c->stage_nodes * STAGED_NODE_BYTES + (size_t)c->stage_tris * 48;
     // the merged tree (small scenes): walked by the split-turn trace kernel and the trace hooks when the two-level scene is staged as a whole
     c->flat_on = c->flat_option != 0 && s.n_flat_nodes > 0 && c->stage_where == 1 && c->vote != 0 &&
@@ -341,7 +380,7 @@ static int configure_kernels(igb200_ctx* c) {
     if (nb < 1) return fail(-2, "k_wavefront does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
     c->blocks_per_sm = nb;
     // split turn kernels
-    CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->turn_where), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     if (c->flat_on) {
         CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, 1, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_flat));
         int nbf = 0;
@@ -361,10 +400,10 @@ static int configure_kernels(igb200_ctx* c) {
         }
     }
     if (c->carveout >= 0) {
-        CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where), cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout));
+        CU(cudaFuncSetAttribute((const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->turn_where), cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout));
         for (int full = 0; full < 2; ++full) CU(cudaFuncSetAttribute((const void*)wave_kernel(c->min_blocks, c->vote, full != 0, c->stage_where), cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout));
     }
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where), WF_BLOCK, c->smem_bytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)turn_trace_kernel(c->turn_trace_blocks, c->vote, c->turn_where), WF_BLOCK, c->smem_bytes));
     if (nb < 1) return fail(-2, "k_turn_trace does not fit an SM with %zu bytes of shared memory", c->smem_bytes);
     c->grid_turn_trace = nb * c->n_sm;
     {
@@ -464,7 +503,7 @@ static int launch_split_turns(igb200_ctx* c, const WaveParams& P, int turns) {
         }
         else if (c->flat_on && c->flat_block != WF_BLOCK) flat_staged_kernel(c->flat_block)<<<c->grid_turn_trace_flat, c->flat_block, c->smem_flat_staged, c->stream>>>(P);
         else if (c->flat_on) turn_trace_kernel(c->turn_trace_blocks, c->vote, 1, true)<<<c->grid_turn_trace_flat, WF_BLOCK, c->smem_flat, c->stream>>>(P);
-        else turn_trace_kernel(c->turn_trace_blocks, c->vote, c->stage_where)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
+        else turn_trace_kernel(c->turn_trace_blocks, c->vote, c->turn_where)<<<c->grid_turn_trace, WF_BLOCK, c->smem_bytes, c->stream>>>(P);
         { const int r = prof_end(c); if (r) return r; }
         { const int r = prof_begin(c, 3); if (r) return r; }
         k_turn_end<<<1, 1, 0, c->stream>>>(P);
@@ -619,6 +658,7 @@ int igb200_set_option(igb200_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "wide_rays_per_group")) { if (value < 0) return fail(-1, "wide_rays_per_group must be >= 0"); c->wide_rays_per_group = value; return 0; }
     if (!strcmp(name, "defer_permille")) { if (value < 0 || value > 8000) return fail(-1, "defer_permille must be in [0, 8000]"); c->defer_permille = (int)value; return 0; }
     if (!strcmp(name, "profile_kernels")) { c->profile = value != 0; return 0; }
+    if (!strcmp(name, "wide_loads")) { if (value < 0 || value > 1) return fail(-1, "wide_loads must be 0 or 1"); { const int r = sync_control(c); if (r) return r; } c->wide_loads = (int)value; return c->has_scene ? configure_kernels(c) : 0; }
     if (!strcmp(name, "drain_turns")) { if (value < -1 || value > 64) return fail(-1, "drain_turns must be in [-1, 64]"); c->drain_turns = (int)value; return 0; }
     if (!strcmp(name, "shade_sync")) { if (value < 0 || value > 1) return fail(-1, "shade_sync must be 0 or 1"); c->shade_sync = (int)value; return 0; }
     if (!strcmp(name, "wave_skip")) { if (value < 0 || value > 1) return fail(-1, "wave_skip must be 0 or 1"); { const int r = drain(c); if (r) return r; } c->wave_skip = (int)value; return 0; }
@@ -1653,6 +1693,36 @@ static int fs_publish(igb200_ctx* c, bool all) {
         const int p = (int)(c->fs_published & 1);
         float* slot = c->fs_ring.p + (size_t)(f.iter & (c->fs_slots - 1)) * n;
         float* snap = nullptr;
+        if (c->fs_shm) {
+            // ---- frames in shared host memory: no exchange between the GPUs at all. Every rank snapshots its accumulated frame and writes its own
+            // tiles into host frame h of the segment on its copy stream, then raises flags[h][rank] = sequence number of the frame.
+            const unsigned int seq = (unsigned int)(c->fs_published + 1);
+            const int h = (int)(c->fs_published % c->fs_shm_frames);
+            volatile unsigned long long* consumed = reinterpret_cast<volatile unsigned long long*>(c->fs_shm);
+            if ((unsigned long long)c->fs_published - *consumed >= (unsigned long long)c->fs_shm_frames) {
+                // host frame h still belongs to a frame rank 0's caller has not taken (and released) yet
+                if (root) return fail(-5, "frame stream: %d published frames are waiting to be taken (igb200_frame_stream_next); none can be overwritten", c->fs_shm_frames);
+                const auto t0 = std::chrono::steady_clock::now();
+                while ((unsigned long long)c->fs_published - *consumed >= (unsigned long long)c->fs_shm_frames)
+                    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 60.0) return fail(-5, "frame stream: rank 0 has not taken a frame for 60 s");
+            }
+            if (c->fs_snap_used[p]) CU(cudaStreamWaitEvent(c->stream, c->fs_ev_snapfree[p], 0));
+            snap = c->fs_snap[p].p;
+            k_publish<<<c->n_sm * 4, 256, 0, c->stream>>>(c->fb.p, slot, snap, (long long)n);
+            CU(cudaEventRecord(c->fs_ev_pub[p], c->stream));
+            CU(cudaStreamWaitEvent(c->copy_stream, c->fs_ev_pub[p], 0));
+            float* host_frame = reinterpret_cast<float*>(c->fs_shm_dev + c->fs_shm_header + (size_t)h * c->fs_shm_frame_bytes);
+            const int tiles_x = (c->width + c->tile - 1) / c->tile;
+            k_tiles_to_host<<<c->n_sm, 256, 0, c->copy_stream>>>(snap, host_frame, c->tile_table.p, (int)c->n_local_tiles, c->tile, tiles_x, c->width, c->height);
+            k_raise_flag<<<1, 1, 0, c->copy_stream>>>(reinterpret_cast<volatile unsigned int*>(c->fs_shm_dev + 64) + (size_t)h * 64 + c->rank, seq);
+            CU(cudaEventRecord(c->fs_ev_snapfree[p], c->copy_stream));
+            CU(cudaGetLastError());
+            c->fs_snap_used[p] = true;
+            c->fs_published++;
+            c->pending = true;
+            if (root) c->fs_ready.push_back(igb200_ctx::FsFrame{f.iter, h, nullptr, seq});
+            continue;
+        }
         if (root) {
             // the snapshot the copy engine reads must not be overwritten before its previous copy is through
             if (c->fs_snap_used[p]) CU(cudaStreamWaitEvent(c->stream, c->fs_ev_snapfree[p], 0));
@@ -1675,7 +1745,7 @@ static int fs_publish(igb200_ctx* c, bool all) {
         cudaEvent_t e;
         if (!c->fs_events.empty()) { e = c->fs_events.back(); c->fs_events.pop_back(); } else CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU(cudaEventRecord(e, c->copy_stream));
-        c->fs_ready.push_back(igb200_ctx::FsFrame{f.iter, h, e});
+        c->fs_ready.push_back(igb200_ctx::FsFrame{f.iter, h, e, 0u});
     }
     return 0;
 }
@@ -1694,7 +1764,40 @@ int igb200_frame_stream_begin(igb200_ctx* c, int slots) {
     const size_t n = c->fb.n;
     CU(c->fs_ring.alloc((size_t)R * n));
     CU(cudaMemset(c->fs_ring.p, 0, (size_t)R * n * sizeof(float)));
-    if (c->rank == 0) for (int k = 0; k < 2; ++k) {
+    const bool shared = c->fs_share_key != 0 && c->world > 1;
+    if (shared) {
+        { const int r = ensure_tile_table(c, c->width, c->height); if (r) return r; }
+        if (c->world > 64) return fail(-1, "igb200_frame_stream_share: at most 64 ranks");
+        c->fs_shm_frames = 2 * R;
+        c->fs_shm_frame_bytes = (n * sizeof(float) + 4095) & ~(size_t)4095;
+        c->fs_shm_header = (64 + (size_t)c->fs_shm_frames * 64 * sizeof(unsigned int) + 4095) & ~(size_t)4095;
+        c->fs_shm_bytes = c->fs_shm_header + (size_t)c->fs_shm_frames * c->fs_shm_frame_bytes;
+        // rank 0 creates the segment, the others attach once it exists with the right size
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            c->fs_shm_id = c->rank == 0 ? shmget((key_t)c->fs_share_key, c->fs_shm_bytes, IPC_CREAT | IPC_EXCL | 0600) : shmget((key_t)c->fs_share_key, c->fs_shm_bytes, 0600);
+            if (c->fs_shm_id >= 0) break;
+            if (c->rank == 0 && errno == EEXIST && !c->fs_shm_retry) {   // left behind by a run that died: remove it and try once more
+                const int old_id = shmget((key_t)c->fs_share_key, 0, 0600);
+                if (old_id >= 0) shmctl(old_id, IPC_RMID, nullptr);
+                c->fs_shm_retry = true;
+                continue;
+            }
+            if (c->rank == 0) return fail(-5, "igb200_frame_stream_begin: cannot create the shared segment (key %d, %zu bytes): %s", c->fs_share_key, c->fs_shm_bytes, strerror(errno));
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0) return fail(-5, "igb200_frame_stream_begin: the shared segment (key %d) did not appear: %s", c->fs_share_key, strerror(errno));
+            std::this_thread::sleep_for(std::chrono::milliseconds(2));
+        }
+        void* m = shmat(c->fs_shm_id, nullptr, 0);
+        if (m == (void*)-1) { c->fs_shm_id = -1; return fail(-5, "igb200_frame_stream_begin: shmat: %s", strerror(errno)); }
+        c->fs_shm = static_cast<unsigned char*>(m);
+        // (a new System V segment is zero-filled by the kernel: consumed = 0, no flag raised)
+        CU(cudaHostRegister(c->fs_shm, c->fs_shm_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+        void* dp = nullptr;
+        CU(cudaHostGetDevicePointer(&dp, c->fs_shm, 0));
+        c->fs_shm_dev = static_cast<unsigned char*>(dp);
+        c->fs_taken_shared = false;
+    }
+    if (c->rank == 0 || shared) for (int k = 0; k < 2; ++k) {
         CU(c->fs_snap[k].alloc(n));
         if (!c->fs_ev_pub[k]) { CU(cudaEventCreateWithFlags(&c->fs_ev_pub[k], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->fs_ev_snapfree[k], cudaEventDisableTiming)); }
         c->fs_snap_used[k] = false;
@@ -1702,11 +1805,19 @@ int igb200_frame_stream_begin(igb200_ctx* c, int slots) {
     c->fs_slots = R; c->fs_on = true; c->fs_published = 0; c->fs_last_taken_host = -1;
     // pinned frames for everything that can be outstanding at once (a drain publishes every iteration in flight in one go); pinning
     // memory costs milliseconds per frame, so it happens here and not inside a render
-    if (c->rank == 0) {
+    if (c->rank == 0 && !shared) {
         std::vector<int> hs((size_t)R + 2);
         for (int& h : hs) { const int r = fs_host_buffer(c, &h); if (r) return r; }
         for (int h : hs) c->fs_host_free.push_back(h);
     }
+    return 0;
+}
+
+int igb200_frame_stream_share(igb200_ctx* c, int key) {
+    if (!c) return fail(-1, "null context");
+    if (c->fs_on) return fail(-1, "igb200_frame_stream_share: call before igb200_frame_stream_begin");
+    if (key < 0) return fail(-1, "igb200_frame_stream_share: the key must be positive (0 = off)");
+    c->fs_share_key = key;
     return 0;
 }
 
@@ -1717,11 +1828,17 @@ int igb200_frame_stream_end(igb200_ctx* c) {
     { const int r = sync_control(c); if (r) return r; }
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->copy_stream));
-    for (const igb200_ctx::FsFrame& f : c->fs_ready) c->fs_events.push_back(f.copied);
+    for (const igb200_ctx::FsFrame& f : c->fs_ready) if (f.copied) c->fs_events.push_back(f.copied);
     c->fs_ready.clear(); c->fs_inflight.clear();
     for (float* p : c->fs_host) cudaFreeHost(p);
     c->fs_host.clear(); c->fs_host_free.clear();
     c->fs_ring.release(); c->fs_snap[0].release(); c->fs_snap[1].release();
+    if (c->fs_shm) {
+        cudaHostUnregister(c->fs_shm);
+        shmdt(c->fs_shm);
+        if (c->rank == 0) shmctl(c->fs_shm_id, IPC_RMID, nullptr);   // gone once the last rank has detached
+        c->fs_shm = nullptr; c->fs_shm_dev = nullptr; c->fs_shm_id = -1; c->fs_shm_frames = 0;
+    }
     c->fs_on = false; c->fs_slots = 0;
     return 0;
 }
@@ -1732,10 +1849,28 @@ int igb200_frame_stream_next(igb200_ctx* c, int wait, int* iteration, float** ho
     *host_rgb = nullptr; *iteration = -1;
     CU(cudaSetDevice(c->device));
     if (c->fs_last_taken_host >= 0) { c->fs_host_free.push_back(c->fs_last_taken_host); c->fs_last_taken_host = -1; }   // the previous frame's buffer is the caller's no longer
+    if (c->fs_taken_shared) { volatile unsigned long long* consumed = reinterpret_cast<volatile unsigned long long*>(c->fs_shm); *consumed = *consumed + 1; c->fs_taken_shared = false; }
     if (wait >= 2) { const int r = drain(c); if (r) return r; }   // finish everything that was rendered: every frame becomes ready
     else { const int r = flush_queued(c); if (r) return r; }
     if (c->rank != 0 || c->fs_ready.empty()) return 0;
     const igb200_ctx::FsFrame f = c->fs_ready.front();
+    if (c->fs_shm) {
+        // complete when every rank has raised its flag for this frame (each rank's tiles are in the segment by then)
+        volatile unsigned int* flags = reinterpret_cast<volatile unsigned int*>(c->fs_shm + 64) + (size_t)f.host * 64;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            bool all = true;
+            for (int r = 0; r < c->world; ++r) all = all && flags[r] == f.seq;
+            if (all) break;
+            if (wait == 0) return 0;
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0) return fail(-5, "igb200_frame_stream_next: frame of iteration %d did not arrive from every rank within 120 s", f.iter);
+        }
+        __sync_synchronize();
+        c->fs_ready.pop_front();
+        c->fs_taken_shared = true;
+        *iteration = f.iter; *host_rgb = reinterpret_cast<float*>(c->fs_shm + c->fs_shm_header + (size_t)f.host * c->fs_shm_frame_bytes);
+        return 1;
+    }
     if (wait == 0) {
         const cudaError_t q = cudaEventQuery(f.copied);
         if (q == cudaErrorNotReady) return 0;

@@ -244,12 +244,69 @@ struct Traversal {
         }
     }
 
+    // ---- N for nodes in GLOBAL memory (WHERE = 2, large scenes): the same eight slab tests, fed by 256-bit loads. A row of the node (one
+    // plane of all eight children) is 32 bytes = one sector; the float4 walk below reads it with two instructions, i.e. two passes through the
+    // L1 data pipe for the same sector -- and that pipe is what ncu shows saturated on unstaged scenes (l1tex data-pipe wavefronts 75 % of peak,
+    // long scoreboard the top stall, profiles/r5h_room_k_turn_trace_full.csv). sm_100 has ld.global.v8.f32 (LDG.E.256): seven loads per node
+    // instead of fourteen. Evaluated plane by plane (near / far of one axis at a time) so that 16 loaded values are live, not 48.
+    __device__ __forceinline__ static void ldg8(const float4* p, float (&v)[8]) {
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+    }
+    __device__ __forceinline__ void node_step_global8(const DevScene& sc, Stack& st) {
+        const float4* N = sc.nodes + (size_t)(cur - 1) * 16;
+        const int ox = (bits & TB_SX) ? 2 : 0, oy = (bits & TB_SY) ? 2 : 0, oz = (bits & TB_SZ) ? 2 : 0;
+        float tn[8], tf[8], a[8], b[8], chf[8];
+        ldg8(N + ox, a); ldg8(N + 2 - ox, b); ldg8(N + 12, chf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { tn[k] = fma_(idir.x, a[k], ilo.x); tf[k] = fma_(idir.x, b[k], ihi.x); }
+        ldg8(N + 4 + oy, a); ldg8(N + 6 - oy, b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { tn[k] = fmaxf(tn[k], fma_(idir.y, a[k], ilo.y)); tf[k] = fminf(tf[k], fma_(idir.y, b[k], ihi.y)); }
+        ldg8(N + 8 + oz, a); ldg8(N + 10 - oz, b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { tn[k] = fmaxf(tn[k], fmaxf(fma_(idir.z, a[k], ilo.z), tmin)); tf[k] = fminf(tf[k], fminf(fma_(idir.z, b[k], ihi.z), tcull)); }
+        int n = 0, best = 0, best_slot = 0;
+        float best_t = __int_as_float(0x7fc00000);
+        if (sp + 8 <= SMEM_STACK) {
+            uint2* base = st.s + sp * st.stride;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = __float_as_int(chf[k]);
+                const bool hit_ = tn[k] <= tf[k];
+                base[n * st.stride] = make_uint2((uint32_t)c, __float_as_uint(tn[k]));
+                const bool nearer = hit_ && !(tn[k] >= best_t);
+                best_t = nearer ? tn[k] : best_t; best = nearer ? c : best; best_slot = nearer ? n : best_slot;
+                n += hit_ ? 1 : 0;
+            }
+            if (n == 0) { cur = 0; return; }
+            --n;
+            if (best_slot != n) base[best_slot * st.stride] = base[n * st.stride];
+            sp += n; cur = best;
+        } else {
+            const int sp0 = sp;
+#pragma unroll 1
+            for (int k = 0; k < 8; ++k) {
+                const int c = __float_as_int(chf[k]);
+                const bool hit_ = tn[k] <= tf[k];
+                if (hit_ && sp < STACK_SIZE) st.push(sp, c, tn[k]);
+                const bool nearer = hit_ && !(tn[k] >= best_t);
+                best_t = nearer ? tn[k] : best_t; best = nearer ? c : best; best_slot = nearer ? n : best_slot;
+                n += hit_ ? 1 : 0;
+            }
+            if (sp == sp0) { cur = 0; return; }
+            const uint2 top = st.pop(sp);
+            if (sp0 + best_slot != sp) st.set(sp0 + best_slot, top);
+            cur = best;
+        }
+    }
+
     // ---- N: inner node. Eight branch-free slab tests; the nearest hit child becomes `cur`, the others stay pushed.
     template <int WHERE = 0>
     __device__ __forceinline__ void node_step(const DevScene& sc, const Staged& sg, Stack& st) {
 #ifdef IGB_STEP_STATS
         ++n_node;
 #endif
+        if (WHERE == 2) { node_step_global8(sc, st); return; }
         const float4* N = node_ptr<WHERE>(sc, sg, cur - 1);
         // rows of the node: lo_x hi_x lo_y hi_y lo_z hi_z, two float4 each; the octant picks near / far by address
         const int ox = (bits & TB_SX) ? 2 : 0, oy = (bits & TB_SY) ? 2 : 0, oz = (bits & TB_SZ) ? 2 : 0;

@@ -71,7 +71,7 @@ SYMBOLS = ["igb200_last_error", "igb200_version", "igb200_device_count", "igb200
            "igb200_upload_framebuffer", "igb200_stats", "igb200_reset_stats", "igb200_kernel_times", "igb200_launch_profile", "igb200_turn_log", "igb200_step_stats", "igb200_set_option",
            "igb200_stream", "igb200_trace_closest", "igb200_trace_any", "igb200_bench_trace", "igb200_test_detmath",
            "igb200_comm_unique_id", "igb200_comm_init", "igb200_comm_gather_framebuffer", "igb200_comm_destroy",
-           "igb200_frame_stream_begin", "igb200_frame_stream_next", "igb200_frame_stream_end", "igb200_set_cache_dir", "igb200_scene_build_info", "igb200_test_bvh_build"]
+           "igb200_frame_stream_begin", "igb200_frame_stream_share", "igb200_frame_stream_next", "igb200_frame_stream_end", "igb200_set_cache_dir", "igb200_scene_build_info", "igb200_test_bvh_build"]
 
 
 def test_bvh_build(boxes, builder=0, cache_dir=None, device=None):
@@ -294,6 +294,10 @@ class B200Device:
     # -- frame streaming (include/igb200.h igb200_frame_stream_*)
     def frameStreamBegin(self, slots: int = 0):
         _check(lib().igb200_frame_stream_begin(self._h, slots))
+
+    def frameStreamShare(self, key: int):
+        """Frames of a multi-rank stream in shared host memory (System V key, the same on every rank; before frameStreamBegin)."""
+        _check(lib().igb200_frame_stream_share(self._h, int(key)))
 
     def frameStreamNext(self, wait: int = 0):
         """(iteration, frame) of the next finished iteration -- a borrowed (H, W, 3) view valid until the next call -- or None."""

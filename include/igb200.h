@@ -252,6 +252,12 @@ int igb200_comm_destroy(igb200_ctx* ctx);
  * arrives (returns 0 if none is outstanding), 2 = first finish everything rendered so far, then as 1. Returns 1 with a frame (valid until the
  * next call), 0 without. Frames exist on rank 0 only; the other ranks call it all the same (the gather is collective) and get 0. */
 int igb200_frame_stream_begin(igb200_ctx* ctx, int slots /* iterations in flight, rounded up to a power of two; 0 = 16 */);
+/* Several ranks on ONE host: the streamed frames live in a System V shared-memory segment (key > 0, the same on every rank; rank 0 creates it in
+ * igb200_frame_stream_begin, the others attach) that every rank pins and maps. Each rank then writes the pixels of its own tiles straight into
+ * the host frame over its own PCIe link -- no exchange between the GPUs, no full frame through one link -- and rank 0's
+ * igb200_frame_stream_next hands out a frame once every rank has flagged it. Call on every rank before igb200_frame_stream_begin; 0 = off
+ * (the frames are gathered onto rank 0's GPU and copied from there). */
+int igb200_frame_stream_share(igb200_ctx* ctx, int key);
 int igb200_frame_stream_next(igb200_ctx* ctx, int wait, int* iteration, float** host_rgb);
 int igb200_frame_stream_end(igb200_ctx* ctx);
 

@@ -30,7 +30,12 @@ def _rank_stream(rank, world, conn, scene, w, h, spi, iters, fuse):
         t = load_scene(os.path.join(ROOT, "scenes", scene))
         with Runtime(t, w, h, spi=spi, cuda_device=rank) as rt:
             rt.device.commInit(rank, world, uid, 32)
+            share = 0
+            if isinstance(fuse, tuple):
+                fuse, share = fuse
             rt.device.setOption("fuse", fuse)
+            if share:
+                rt.device.frameStreamShare(share)   # frames in shared host memory: every rank writes its own tiles, no exchange between the GPUs
             rt.device.frameStreamBegin(32)
             out = {}
             for it in range(iters):
@@ -113,10 +118,12 @@ def test_gathered_frame_equals_oracle(world, scene, w, h, spi):
     assert tuple(int(x) for x in counts) == tuple(int(x) for x in o.counters)
 
 
-@pytest.mark.parametrize("world,fuse", [(2, 1), (2, 4), (8, 8)])
+@pytest.mark.parametrize("world,fuse", [(2, 1), (2, 4), (8, 8), (2, (1, 0x1b200)), (2, (4, 0x1b201)), (8, (8, 0x1b202))])
 def test_streamed_gathered_frames_equal_oracle(world, fuse):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
+    if isinstance(fuse, tuple):
+        fuse = (fuse[0], fuse[1] + (os.getpid() & 0xFFF) * 16)   # a key of this test run
     from ignis_b200.scene import load_scene
     from oracle.oracle import Oracle
     scene, w, h, spi, iters = "diamond_scene.json", 480, 270, 4, 18
