@@ -113,16 +113,23 @@ __global__ void k_publish(float* __restrict__ acc, float* __restrict__ slot, flo
 // Frame streaming over several ranks with the frames in SHARED host memory (igb200_frame_stream_share): every rank writes the pixels of its own
 // tiles of the snapshot straight into the host frame (zero-copy stores into the mapped segment, each GPU over its own PCIe link), then raises
 // its flag for that frame. Rank 0's host sees a frame complete when every rank's flag carries the frame's sequence number.
+// VEC: 16-byte stores (tile x 3 and width x 3 floats are multiples of four, so every tile row starts on a 16-byte boundary): a warp store is 512
+// contiguous bytes on the link instead of 128.
+template <bool VEC>
 __global__ void k_tiles_to_host(const float* __restrict__ snap, float* __restrict__ host_frame, const int* __restrict__ tile_table, int n_tiles, int tile, int tiles_x, int width, int height) {
-    const int row_words = tile * 3;                                   // one tile row = tile pixels x rgb, contiguous in the frame
+    constexpr int V = VEC ? 4 : 1;
+    const int row_words = tile * 3 / V;                               // one tile row = tile pixels x rgb, contiguous in the frame
     const long long n = (long long)n_tiles * tile * row_words;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(i / ((long long)tile * row_words));
         const int r = (int)(i - (long long)k * tile * row_words);
-        const int ty = r / row_words, w = r - ty * row_words;
+        const int ty = r / row_words, w = (r - ty * row_words) * V;
         const int t = tile_table ? tile_table[k] : k;
         const int x0 = (t % tiles_x) * tile, y = (t / tiles_x) * tile + ty;
-        if (y < height && x0 * 3 + w < width * 3) { const size_t o = ((size_t)y * width + x0) * 3 + w; host_frame[o] = snap[o]; }
+        if (y >= height || x0 * 3 + w >= width * 3) continue;
+        const size_t o = ((size_t)y * width + x0) * 3 + w;
+        if (VEC) *reinterpret_cast<float4*>(host_frame + o) = *reinterpret_cast<const float4*>(snap + o);
+        else host_frame[o] = snap[o];
     }
 }
 __global__ void k_raise_flag(volatile unsigned int* flag, unsigned int seq) {
@@ -1713,7 +1720,8 @@ static int fs_publish(igb200_ctx* c, bool all) {
             CU(cudaStreamWaitEvent(c->copy_stream, c->fs_ev_pub[p], 0));
             float* host_frame = reinterpret_cast<float*>(c->fs_shm_dev + c->fs_shm_header + (size_t)h * c->fs_shm_frame_bytes);
             const int tiles_x = (c->width + c->tile - 1) / c->tile;
-            k_tiles_to_host<<<c->n_sm, 256, 0, c->copy_stream>>>(snap, host_frame, c->tile_table.p, (int)c->n_local_tiles, c->tile, tiles_x, c->width, c->height);
+            if ((c->tile * 3) % 4 == 0 && (c->width * 3) % 4 == 0) k_tiles_to_host<true><<<c->n_sm * 4, 256, 0, c->copy_stream>>>(snap, host_frame, c->tile_table.p, (int)c->n_local_tiles, c->tile, tiles_x, c->width, c->height);
+            else k_tiles_to_host<false><<<c->n_sm * 4, 256, 0, c->copy_stream>>>(snap, host_frame, c->tile_table.p, (int)c->n_local_tiles, c->tile, tiles_x, c->width, c->height);
             k_raise_flag<<<1, 1, 0, c->copy_stream>>>(reinterpret_cast<volatile unsigned int*>(c->fs_shm_dev + 64) + (size_t)h * 64 + c->rank, seq);
             CU(cudaEventRecord(c->fs_ev_snapfree[p], c->copy_stream));
             CU(cudaGetLastError());
@@ -1851,7 +1859,10 @@ int igb200_frame_stream_next(igb200_ctx* c, int wait, int* iteration, float** ho
     if (c->fs_last_taken_host >= 0) { c->fs_host_free.push_back(c->fs_last_taken_host); c->fs_last_taken_host = -1; }   // the previous frame's buffer is the caller's no longer
     if (c->fs_taken_shared) { volatile unsigned long long* consumed = reinterpret_cast<volatile unsigned long long*>(c->fs_shm); *consumed = *consumed + 1; c->fs_taken_shared = false; }
     if (wait >= 2) { const int r = drain(c); if (r) return r; }   // finish everything that was rendered: every frame becomes ready
-    else { const int r = flush_queued(c); if (r) return r; }
+    else if (wait == 1 || c->fs_inflight.empty()) { const int r = flush_queued(c); if (r) return r; }   // the same decision on every rank
+    // (a poll -- wait 0 -- leaves queued iterations alone while the device still has frames in the works: launching them one by one would
+    // undo the fusing of small iterations, which is what a rank's share of a frame at N = 8 lives on: r6q, e2e 29 Grays/s with every step's
+    // poll flushing the queue)
     if (c->rank != 0 || c->fs_ready.empty()) return 0;
     const igb200_ctx::FsFrame f = c->fs_ready.front();
     if (c->fs_shm) {

@@ -248,7 +248,8 @@ int igb200_comm_destroy(igb200_ctx* ctx);
  * finished (from the launches issued since -- no read-back) its slot is folded into the accumulated frame, in order, and a snapshot of the
  * frame travels to pinned host memory on a copy stream (with a communicator: after the tile gather, on rank 0) while the next iterations
  * render. igb200_frame_stream_next hands the frames out in iteration order: frame k = the sum of iterations 0..k, exactly what
- * igb200_framebuffer would have returned after render(k). wait: 0 = only if one is ready, 1 = block until the oldest outstanding frame
+ * igb200_framebuffer would have returned after render(k). wait: 0 = only if one is ready (a poll: render() calls still queued for a fused
+ * launch stay queued unless the device has nothing else in the works), 1 = block until the oldest outstanding frame
  * arrives (returns 0 if none is outstanding), 2 = first finish everything rendered so far, then as 1. Returns 1 with a frame (valid until the
  * next call), 0 without. Frames exist on rank 0 only; the other ranks call it all the same (the gather is collective) and get 0. */
 int igb200_frame_stream_begin(igb200_ctx* ctx, int slots /* iterations in flight, rounded up to a power of two; 0 = 16 */);

@@ -17,6 +17,8 @@ except Exception as e:
 P
 }
 if [ "$2" = "quick" ]; then run 8 c2 20 5; run 8 c5 16 3; exit 0; fi
+if [ "$2" = "c2" ]; then run 8 c2 20 5; run 4 c2 20 5; exit 0; fi
+if [ "$2" = "c2n8" ]; then run 8 c2 20 5; exit 0; fi
 NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,GRAPH,P2P run 8 c2 20 5
 grep -E "via P2P|via SHM|NVLS|Connected|channels" gpurun_out/multi_${TAG}_c2_n8.err | sort | uniq -c | sort -rn | head -30 > gpurun_out/multi_${TAG}_nccl_transport_n8.txt
 run 8 c5 16 3
