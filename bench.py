@@ -343,6 +343,7 @@ def run_b200(args):
 
     ms, wall_ms, tot, clocks, _ = timed(e2e=False)
     per_rank = timed.per_rank
+    shared_frames = False
     if args.e2e_mode == "stream":
         if world > 1 and not args.no_shared_frames:
             # the ranks of one box hand their tiles of every frame to rank 0 through shared pinned host memory (each GPU over its own PCIe link)
@@ -350,7 +351,28 @@ def run_b200(args):
             keys = [int.from_bytes(os.urandom(3), "little") + 0x1000000 if rank == 0 else None]
             dist.broadcast_object_list(keys, src=0)
             dev.frameStreamShare(keys[0])
-        dev.frameStreamBegin(32 if world > 1 else 16)
+        shared_frames = world > 1 and not args.no_shared_frames
+        try:
+            dev.frameStreamBegin(32 if world > 1 else 16)
+            began = 1.0
+        except Exception as e:   # noqa: BLE001 -- e.g. a box that refuses System V segments of this size
+            began = 0.0
+            print(f"[bench] rank {rank}: frame stream could not start ({e})", file=sys.stderr)
+        if world > 1:
+            ok = torch.tensor([began], dtype=torch.float64, device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            began_all = float(ok[0]) > 0
+        else:
+            began_all = began > 0
+        if not began_all:
+            if not shared_frames:
+                raise RuntimeError("frame stream could not start")
+            # every rank falls back together: frames gathered on rank 0's GPU and copied from there
+            if began:
+                dev.frameStreamEnd()
+            dev.frameStreamShare(0)
+            shared_frames = False
+            dev.frameStreamBegin(32)
         for _ in range(2):                 # warm the streaming path: pinned frame buffers are allocated on first use
             rt.step()
         while dev.frameStreamNext(2) is not None:
@@ -421,7 +443,7 @@ def run_b200(args):
                         "ms_per_step": wall_e / args.steps, "timed": "host wall clock between barriers, max over ranks",
                         "mode": (("every step's accumulated frame streamed to pinned host memory while later steps render (igb200_frame_stream_*), all K frames received inside the timed region"
                                   + ("; the frames live in shared pinned host memory that every rank writes its own tiles into (igb200_frame_stream_share), rank 0 takes each "
-                                     "frame once all ranks have flagged it" if world > 1 and not args.no_shared_frames else ("; every frame gathered onto rank 0's GPU (NCCL) and copied from there" if world > 1 else "")))
+                                     "frame once all ranks have flagged it" if shared_frames else ("; every frame gathered onto rank 0's GPU (NCCL) and copied from there" if world > 1 else "")))
                                  if args.e2e_mode == "stream" else "render() + synchronous getFramebufferForHost every step")},
                 "per_rank_ms": {"columns": ["issued launches", "flush + drain of the deferred tail", "NCCL gather of the tiles (on rank 0 incl. waiting for the last rank)", "total", "rays traced", "host start after the first rank (ms)"], "ranks": per_rank},
                 "rays": tot, "msamples_per_s": w * h * spi * args.steps / (ms * 1e-3) / 1e6, "wall_ms_per_step": wall_ms / args.steps}

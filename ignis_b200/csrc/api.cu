@@ -1797,13 +1797,20 @@ int igb200_frame_stream_begin(igb200_ctx* c, int slots) {
         }
         void* m = shmat(c->fs_shm_id, nullptr, 0);
         if (m == (void*)-1) { c->fs_shm_id = -1; return fail(-5, "igb200_frame_stream_begin: shmat: %s", strerror(errno)); }
-        c->fs_shm = static_cast<unsigned char*>(m);
         // (a new System V segment is zero-filled by the kernel: consumed = 0, no flag raised)
-        CU(cudaHostRegister(c->fs_shm, c->fs_shm_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
         void* dp = nullptr;
-        CU(cudaHostGetDevicePointer(&dp, c->fs_shm, 0));
+        cudaError_t e = cudaHostRegister(m, c->fs_shm_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+        if (e == cudaSuccess) { e = cudaHostGetDevicePointer(&dp, m, 0); if (e != cudaSuccess) cudaHostUnregister(m); }
+        if (e != cudaSuccess) {   // leave nothing half set up: the caller may fall back to the gathered stream
+            cudaGetLastError();
+            shmdt(m);
+            if (c->rank == 0) shmctl(c->fs_shm_id, IPC_RMID, nullptr);
+            c->fs_shm_id = -1;
+            return fail(-2, "igb200_frame_stream_begin: cannot pin the shared segment (%zu bytes): %s", c->fs_shm_bytes, cudaGetErrorString(e));
+        }
+        c->fs_shm = static_cast<unsigned char*>(m);
         c->fs_shm_dev = static_cast<unsigned char*>(dp);
-        c->fs_taken_shared = false;
+        c->fs_taken_shared = false; c->fs_shm_retry = false;
     }
     if (c->rank == 0 || shared) for (int k = 0; k < 2; ++k) {
         CU(c->fs_snap[k].alloc(n));
