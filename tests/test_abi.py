@@ -92,3 +92,14 @@ def test_spi_policy():
     assert device.recommend_spi(1920, 1080, gpu=True) == 4
     assert device.recommend_spi(1920, 1080, gpu=False) == 1
     assert device.recommend_spi(256, 256, gpu=True) == 64
+
+
+def test_device_count_without_a_gpu_is_zero_not_an_error():
+    """igb200_device_count is how the plugin device sizes IGB200_GPUS = all: no device is an answer (0), not a failure."""
+    import torch
+    n = C.c_int(-1)
+    assert device.lib().igb200_device_count(C.byref(n)) == 0
+    if not torch.cuda.is_available():
+        assert n.value == 0
+    else:
+        assert 0 <= n.value <= torch.cuda.device_count()
