@@ -50,9 +50,9 @@ WORKLOADS = {
 B_PRIMARY, B_SHADOW, B_SPLAT = 216, 108, 24
 # the same figure split by pipeline stage (DESIGN.md "Algorithmic bytes")
 # dram__bytes_read.sum + dram__bytes_write.sum per k_turn_trace launch of this workload (ncu --set full, profiles/)
-NCU_TRAFFIC_BYTES = 5.383e8
-NCU_TRAFFIC_SOURCE = ("profiles/r5a_k_turn_trace_full.csv (re-measured this round on the merged-tree kernel k_turn_trace<256,3,2,1,1>): dram read + write "
-                      "of the three k_turn_trace launches of the first iteration (437 + 749 + 428 MB) / 3; later iterations also trace the carried "
+NCU_TRAFFIC_BYTES = 5.387e8
+NCU_TRAFFIC_SOURCE = ("profiles/r6x_k_turn_trace_full.csv (ncu --set full of the final merged-tree kernel k_turn_trace<256,3,2,1,1>): dram read + write "
+                      "of the three k_turn_trace launches of the first iteration (437 + 751 + 428 MB) / 3; later iterations also trace the carried "
                       "paths, hence the larger algorithmic figure")
 # Thread instructions per traced ray of k_turn_trace on the headline workload (c2), from ncu: smsp__thread_inst_executed.sum of the four
 # split-turn trace launches of one iteration (7.806 + 13.458 + 8.652 + 5.455 = 35.37 G) / the rays they traced (22.85 M primary + 10.83 M
