@@ -118,13 +118,14 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     igb200_camera camera; std::memset(&camera, 0, sizeof(camera));
     igb200_technique technique{};
     std::vector<float> selector_data;
+    TextureTable textures;   // filled by the materials in order of first use (script_recognizer.h)
     try {
         if (set.HitShaders.size() != mScene.entity_per_material->size()) throw RecognizeError{"one hit shader per material expected"};
         const StageDescriptor* light_stage = nullptr; const IG::ParameterSet* light_local = nullptr;
         for (const auto& hs : set.HitShaders) {
             const StageDescriptor* d = static_cast<const StageDescriptor*>(hs.Exec);
             if (!d) throw RecognizeError{"null hit shader"};
-            materials.push_back(resolve_material(*d, Registries{hs.LocalRegistry.get(), global}));
+            materials.push_back(resolve_material(*d, Registries{hs.LocalRegistry.get(), global}, &textures));
             if (!light_stage && d->has_lights) { light_stage = d; light_local = hs.LocalRegistry.get(); }
         }
         const StageDescriptor* miss = static_cast<const StageDescriptor*>(set.MissShader.Exec);
@@ -135,7 +136,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
             if (!forAll([&](igb200_ctx* c, int) { return igb200_set_option(c, "std_aovs", light_stage->std_aovs ? 1 : 0); }, "std_aovs")) throw RecognizeError{mError};
             mStdAovs = (int)light_stage->std_aovs;
         }
-        resolve_lights(*light_stage, Registries{light_local, global}, inf, fin);
+        resolve_lights(*light_stage, Registries{light_local, global}, inf, fin, mScene.database);
         technique = resolve_technique(*light_stage, Registries{light_local, global}, selector_data);
         const StageDescriptor* rg = static_cast<const StageDescriptor*>(set.RayGenerationShader.Exec);
         if (!rg) throw RecognizeError{"null ray generation shader"};
@@ -149,6 +150,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     append(bytes, &camera, sizeof(camera));
     append(bytes, &technique, sizeof(technique));
     append(bytes, selector_data.data(), selector_data.size() * sizeof(float));
+    append(bytes, textures.records.data(), textures.records.size() * sizeof(igb200_texture));
     if (!mSceneDirty && bytes == mDescriptorBytes) return true;
 
     const IG::SceneDatabase& db = *mScene.database;
@@ -176,6 +178,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     d.finite_lights = fin.data(); d.n_finite = (int32_t)fin.size();
     d.camera = camera; d.technique = technique;
     d.selector_data = selector_data.empty() ? nullptr : selector_data.data(); d.n_selector_data = (int32_t)selector_data.size();
+    d.textures = textures.records.empty() ? nullptr : textures.records.data(); d.n_textures = (int32_t)textures.records.size();   // procedural textures only: no images on this path
     for (int k = 0; k < 3; ++k) { d.bbox_min[k] = db.SceneBBox.min(k); d.bbox_max[k] = db.SceneBBox.max(k); }
     if (!forAll([&](igb200_ctx* c, int) { return igb200_set_scene(c, &d); }, "scene upload")) return false;   // the scene is replicated
     mDescriptorBytes.swap(bytes);

@@ -66,10 +66,23 @@ int igbh_describe_material(void* stage, ParameterSet* local, ParameterSet* globa
     try { *out = igbh::resolve_material(*static_cast<igbh::StageDescriptor*>(stage), igbh::Registries{local, global}); return 0; }
     catch (const igbh::RecognizeError& e) { igbh::set_last_error(e.what); return -1; }
 }
+// ... with a texture table that persists over the hit stages of a scene (created / destroyed by the caller)
+igbh::TextureTable* igbh_textures_create() { return new igbh::TextureTable(); }
+void igbh_textures_destroy(igbh::TextureTable* t) { delete t; }
+int igbh_textures_count(const igbh::TextureTable* t) { return (int)t->records.size(); }
+void igbh_textures_get(const igbh::TextureTable* t, int i, igb200_texture* out) { *out = t->records[(size_t)i]; }
+int igbh_describe_material_tex(void* stage, ParameterSet* local, ParameterSet* global, igbh::TextureTable* textures, igb200_material* out) {
+    try { *out = igbh::resolve_material(*static_cast<igbh::StageDescriptor*>(stage), igbh::Registries{local, global}, textures); return 0; }
+    catch (const igbh::RecognizeError& e) { igbh::set_last_error(e.what); return -1; }
+}
+int igbh_describe_lights_db(void* stage, ParameterSet* local, ParameterSet* global, const SceneDatabase* db, igb200_light* inf, int* n_inf, igb200_light* fin, int* n_fin, int cap);
 int igbh_describe_lights(void* stage, ParameterSet* local, ParameterSet* global, igb200_light* inf, int* n_inf, igb200_light* fin, int* n_fin, int cap) {
+    return igbh_describe_lights_db(stage, local, global, nullptr, inf, n_inf, fin, n_fin, cap);
+}
+int igbh_describe_lights_db(void* stage, ParameterSet* local, ParameterSet* global, const SceneDatabase* db, igb200_light* inf, int* n_inf, igb200_light* fin, int* n_fin, int cap) {
     try {
         std::vector<igb200_light> a, b;
-        igbh::resolve_lights(*static_cast<igbh::StageDescriptor*>(stage), igbh::Registries{local, global}, a, b);
+        igbh::resolve_lights(*static_cast<igbh::StageDescriptor*>(stage), igbh::Registries{local, global}, a, b, db);
         if ((int)a.size() > cap || (int)b.size() > cap) { igbh::set_last_error("too many lights for the output arrays"); return -1; }
         std::memcpy(inf, a.data(), a.size() * sizeof(igb200_light)); std::memcpy(fin, b.data(), b.size() * sizeof(igb200_light));
         *n_inf = (int)a.size(); *n_fin = (int)b.size();

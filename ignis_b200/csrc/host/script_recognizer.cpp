@@ -78,20 +78,51 @@ static StageKind kind_of(const std::string& function) {
     fail("unknown stage entry point '" + function + "'");
 }
 
-// `LightTable { count = N, get = @|id:i32| { match(id) { 0 => light_a, ... _ => make_null_light(id) } }}` (LoaderLight.cpp:131-148,199-246)
-static std::vector<std::string> light_table(const std::string& expr, const std::string& which) {
+// `load_simple_<kind>_lights(count, offset, device[, shapes])` bound to `e_<class>` (LoaderLight.cpp:171-186): appends the table's entries
+static void embedded_entries(const StageDescriptor& d, const std::string& var, const std::string& which, std::vector<std::string>& names) {
+    const auto it = d.index.find(var);
+    if (it == d.index.end()) fail(which + ": embedded light table '" + var + "' is not bound");
+    const std::string& e = d.lets[it->second].expr;
+    static const struct { const char* fn; const char* cls; } kinds[] = {{"load_simple_point_lights", "SimplePointLight"}, {"load_simple_spot_lights", "SimpleSpotLight"},
+                                                                        {"load_simple_plane_lights", "SimplePlaneLight"}, {"load_simple_area_lights", "SimpleAreaLight"}};
+    for (const auto& k : kinds) {
+        if (e.rfind(k.fn, 0) != 0) continue;
+        const size_t p = e.find('(');
+        char* end = nullptr;
+        const long count = std::strtol(e.c_str() + p + 1, &end, 10);
+        const long offset = std::strtol(end + 1, nullptr, 10);
+        if (offset != (long)names.size()) fail(which + ": embedded table '" + var + "' starts at id " + std::to_string(offset) + ", expected " + std::to_string(names.size()));
+        for (long i = 0; i < count; ++i) names.push_back(std::string("@") + k.cls + ":" + std::to_string(i));
+        return;
+    }
+    fail(which + ": '" + e.substr(0, 60) + "' is not an embedded light table this device knows");
+}
+
+// `LightTable { count = N, get = @|id:i32| { match(id) { 0 => light_a, ... _ => make_null_light(id) } }}` (LoaderLight.cpp:131-148,199-246), with
+// embedded fix-table lights in front: `if id < K { e_<class>.get(id - off) } else if ... else { match(id) { K => light_x, ... } }`, or the whole
+// table being one embedded class: `let finite_lights = e_<class>;` (LoaderLight.cpp:188-193)
+static std::vector<std::string> light_table(const StageDescriptor& d, const std::string& expr, const std::string& which) {
     std::vector<std::string> names;
     const std::string e = trim(expr);
     if (e.rfind("LightTable", 0) != 0) {
-        // embedded fix-table lights (>= 10 simple lights, LoaderLight.h:27) and proxies are not on the supported path
-        fail(which + " is not a LightTable literal ('" + e.substr(0, 60) + "...'): embedded / proxy light tables are not supported by this device");
+        bool ident = !e.empty();
+        for (char ch : e) ident = ident && ident_char(ch);
+        if (!ident) fail(which + " is neither a LightTable literal nor an embedded table ('" + e.substr(0, 60) + "...')");
+        embedded_entries(d, e, which, names);
+        return names;
     }
     const size_t cnt = e.find("count");
     if (cnt == std::string::npos) fail(which + ": LightTable without count");
     size_t p = e.find('=', cnt);
     const long count = std::strtol(e.c_str() + p + 1, nullptr, 10);
     const size_t m = e.find("match");
-    if (m == std::string::npos) { if (count == 0) return names; fail(which + ": LightTable without match"); }
+    // embedded classes: every `<var>.get(id - <off>)` in front of the match
+    for (size_t g = e.find(".get("); g != std::string::npos && (m == std::string::npos || g < m); g = e.find(".get(", g + 1)) {
+        size_t v0 = g;
+        while (v0 > 0 && ident_char(e[v0 - 1])) --v0;
+        embedded_entries(d, e.substr(v0, g - v0), which, names);
+    }
+    if (m == std::string::npos) { if (count == (long)names.size()) return names; fail(which + ": LightTable without match"); }
     p = e.find('{', m);
     while (p != std::string::npos) {
         const size_t arrow = e.find("=>", p);
@@ -137,8 +168,8 @@ StageDescriptor* parse_stage(const std::string& script, const std::string& funct
     }
     auto has = [&](const char* n) { return d->index.count(n) != 0; };
     auto expr = [&](const char* n) -> const std::string& { return d->lets[d->index.at(n)].expr; };
-    if (has("infinite_lights")) { d->infinite_lights = light_table(expr("infinite_lights"), "infinite_lights"); d->has_lights = true; }
-    if (has("finite_lights")) d->finite_lights = light_table(expr("finite_lights"), "finite_lights");
+    if (has("infinite_lights")) { d->infinite_lights = light_table(*d, expr("infinite_lights"), "infinite_lights"); d->has_lights = true; }
+    if (has("finite_lights")) d->finite_lights = light_table(*d, expr("finite_lights"), "finite_lights");
     d->has_technique = has("technique");
     d->std_aovs = has("full_technique") && expr("full_technique").find("wrap_infobuffer_renderer") != std::string::npos;
     d->has_camera = has("camera");
@@ -183,6 +214,7 @@ struct Eval {
     const StageDescriptor& st;
     const Registries& reg;
     int depth = 0;
+    std::vector<std::map<std::string, Val>> scopes;   // bindings made inside the blocks being evaluated (`{ let (ru, rv) = ...; f(ru, rv) }`)
 
     // ---- lexer over one expression string
     struct Cursor { const std::string* s; size_t p; };
@@ -239,9 +271,20 @@ struct Eval {
     Val unary(Cursor& c) {
         if (peek(c, "-") && !peek(c, "->")) { eat(c, "-"); return arith('*', Val::num(-1.0f), unary(c)); }
         Val v = primary(c);
-        for (;;) {   // `x as f32`
+        for (;;) {   // `x as f32`, `ctx.{surf=surf2}` (a record update: the record stays what it was to this evaluator), `texture_dx(..).r`
             ws(c);
             if (c.s->compare(c.p, 3, "as ") == 0) { c.p += 3; skip_type(c); continue; }
+            if (c.s->compare(c.p, 2, ".{") == 0) {
+                int d = 0;
+                ++c.p;
+                do { const char ch = (*c.s)[c.p]; if (ch == '{') ++d; else if (ch == '}') --d; ++c.p; } while (c.p < c.s->size() && d > 0);
+                continue;
+            }
+            if (c.p + 1 < c.s->size() && (*c.s)[c.p] == '.' && std::isalpha((unsigned char)(*c.s)[c.p + 1])) {   // component of a run-time value: r | g | b | x ...
+                ++c.p;
+                while (c.p < c.s->size() && ident_char((*c.s)[c.p])) ++c.p;
+                continue;
+            }
             break;
         }
         return v;
@@ -282,7 +325,31 @@ struct Eval {
         if (last.rfind("let ", 0) == 0) fail("block ends in a binding: '" + last + "'");
         // bodies that are real code (the `match` of a light table or of the AOV selector) stay opaque: they are only an
         // error if a descriptor needs their value, which as_num / as_vec then report
-        try { return eval_text(last); } catch (const RecognizeError&) { return Val::sym("<code>"); }
+        scopes.emplace_back();
+        Val out;
+        try {
+            for (size_t i = 0; i + 1 < sts.size(); ++i) {   // `let x = e;` / `let (a, b) = e;` in front of the value: visible to what follows
+                const std::string& stt = sts[i];
+                if (stt.rfind("let ", 0) != 0) continue;
+                const size_t eq = stt.find('=');
+                if (eq == std::string::npos) continue;
+                std::string pat = trim(stt.substr(4, eq - 4));
+                const Val v = eval_text(trim(stt.substr(eq + 1)));
+                if (!pat.empty() && pat[0] == '(') {   // tuple pattern: component k of a vector-valued right-hand side
+                    std::vector<std::string> names; std::string cur;
+                    for (char ch : pat) { if (ident_char(ch)) cur += ch; else { if (!cur.empty()) names.push_back(cur); cur.clear(); } }
+                    if (!cur.empty()) names.push_back(cur);
+                    if (v.kind == Val::Vec) for (size_t k = 0; k < names.size() && (int)k < v.n; ++k) { Val c = Val::num(v.f[k]); c.known = v.known; scopes.back()[names[k]] = c; }
+                } else {
+                    const size_t colon = pat.find(':');
+                    if (colon != std::string::npos) pat = trim(pat.substr(0, colon));
+                    scopes.back()[pat] = v;
+                }
+            }
+            out = eval_text(last);
+        } catch (const RecognizeError&) { out = Val::sym("<code>"); }
+        scopes.pop_back();
+        return out;
     }
 
     Val primary(Cursor& c) {
@@ -330,6 +397,7 @@ struct Eval {
         if (name == "flt_max") return Val::num(3.4028234664e+38f);
         if (name == "color_builtins::black") return Val::vec(0, 0, 0);
         if (name == "color_builtins::white") return Val::vec(1, 1, 1);
+        for (size_t k = scopes.size(); k-- > 0;) { const auto f = scopes[k].find(name); if (f != scopes[k].end()) return f->second; }
         const auto it = st.index.find(name);
         if (it != st.index.end()) {
             if (++depth > 64) fail("binding '" + name + "' is recursive");
@@ -381,6 +449,13 @@ struct Eval {
         if (fn == "color_mulf" || fn == "vec3_mulf") return arith('*', vec_arg(fn, a, 0), Val::num(num_arg(fn, a, 1)));
         if (fn == "color_mul") return arith('*', vec_arg(fn, a, 0), vec_arg(fn, a, 1));
         if (fn == "make_constant_texture") return vec_arg(fn, a, 0);   // texture/constant: the colour itself on this path
+        if ((fn == "vec4_to_color" || fn == "color_to_vec4") && a.size() == 1) return a[0];   // the transpiler's wrapping of a texture look-up (Transpiler.cpp:991,1301)
+        if (fn == "microfacet::compute_explicit") {   // core/microfacet.art:427-432
+            const float r = num_arg(fn, a, 0), an = num_arg(fn, a, 1);
+            const float aspect = (a[1].known && an == 0) ? 1.0f : std::sqrt(1 - std::fmin(std::fmax(an, 0.0f), 1.0f) * 0.99f);
+            Val v = Val::vec(r / aspect, r * aspect, 0); v.n = 2; v.known = a[0].known && a[1].known;
+            return v;
+        }
         if (fn == "maybe_unused") return Val::num(0);
         if (fn == "vec3_normalize") {   // core/vector.art; the length in double, rounded once, then three f32 divisions (scene.py normalize_f32)
             Val v = vec_arg(fn, a, 0);
@@ -432,15 +507,72 @@ void put3(float* dst, const Val& v) { dst[0] = v.f[0]; dst[1] = v.f[1]; dst[2] =
 }  // namespace
 
 // ============================================================================================== descriptors
-igb200_material resolve_material(const StageDescriptor& hit, const Registries& r) {
+int TextureTable::add(const igb200_texture& t) {
+    for (size_t i = 0; i < records.size(); ++i) if (std::memcmp(&records[i], &t, sizeof(t)) == 0) return (int)i;
+    records.push_back(t);
+    return (int)records.size() - 1;
+}
+
+// A texture value: `make_checkerboard_texture(make_vec2(sx, sy), color0, color1, transform)` (pattern/CheckerBoardPattern.cpp:13-33). Image
+// textures name a FILE (`device.load_image(...)`): decoding it is the runtime's business (IG::Image, stb / tinyexr), which this layer does not
+// link -- they are reported, not guessed.
+static int texture_of(const Val& t, TextureTable* textures, const std::string& what) {
+    if (t.kind != Val::Ctor) fail(what + " is neither a constant nor a texture");
+    if (!textures) fail(what + " is textured but no texture table was given");
+    igb200_texture rec;
+    std::memset(&rec, 0, sizeof(rec));
+    if (t.name == "make_checkerboard_texture") {
+        rec.type = IGB200_TEX_CHECKERBOARD;
+        const Val sc = as_vec(ctor_arg(t, 0), what + ": checkerboard scale");
+        rec.p[0] = sc.f[0]; rec.p[1] = sc.f[1];
+        put3(rec.p + 2, as_vec(ctor_arg(t, 1), what + ": checkerboard color0"));
+        put3(rec.p + 5, as_vec(ctor_arg(t, 2), what + ": checkerboard color1"));
+        const Val& tr = ctor_arg(t, 3);   // LoaderUtils::inlineTransformAs2d: mat3x3_identity() | make_mat3x3(col0, col1, col2)
+        if (tr.kind != Val::Ctor) fail(what + ": texture transform is not a matrix");
+        if (tr.name == "mat3x3_identity") { rec.transform[0] = 1; rec.transform[4] = 1; }
+        else if (tr.name == "make_mat3x3") {
+            for (int c = 0; c < 3; ++c) { const Val col = as_vec(ctor_arg(tr, c), what + ": texture transform column"); rec.transform[c] = col.f[0]; rec.transform[3 + c] = col.f[1]; }
+        } else fail(what + ": texture transform '" + tr.name + "' is not understood");
+    } else if (t.name == "make_image_texture" || t.name == "make_bitmap_texture") {
+        fail(what + ": image textures are not available through the script path (the file is decoded by the runtime's image loader, which this layer does not link); use the C ABI's igb200_scene_desc::images");
+    } else fail(what + ": texture constructor '" + t.name + "' is not supported by this device");
+    return textures->add(rec);
+}
+// A colour parameter that may be a texture look-up (ShadingTree::addColor with a texture name -> `tex_<id>(ctx)`)
+static void colour_or_texture(const Val& v, float* dst, int32_t* tex, TextureTable* textures, const std::string& what) {
+    if (v.kind == Val::Vec) { put3(dst, v); return; }
+    if (!tex) fail(what + " is not a compile-time colour");
+    *tex = texture_of(v, textures, what);
+    dst[0] = dst[1] = dst[2] = 0;
+}
+
+igb200_material resolve_material(const StageDescriptor& hit, const Registries& r, TextureTable* textures) {
     if (hit.kind != StageKind::Hit) fail("resolve_material: not a hit stage");
     Eval ev{hit, r};
-    const Val b = ev.binding(hit.bsdf_binding);
+    Val b = ev.binding(hit.bsdf_binding);
     if (b.kind != Val::Ctor) fail(hit.bsdf_binding + " is not a BSDF constructor");
     igb200_material m;
     std::memset(&m, 0, sizeof(m));
     m.light_id = -1;
     m.tex[0] = m.tex[1] = -1; m.map_tex = -1;   // no textured parameters, no bump / normal map
+    // MapBSDF.cpp:17-55: a wrapper around the material's BSDF that replaces its shading frame (bsdf/map.art:56-68). The map's texture is met
+    // before the inner BSDF's, as in the generator.
+    if (b.name == "make_bumpmap" || b.name == "make_normalmap") {
+        const bool bump = b.name == "make_bumpmap";
+        m.map_kind = bump ? IGB200_MAP_BUMP : IGB200_MAP_NORMAL;
+        const Val* map = &ctor_arg(b, 2);
+        if (bump) {   // texture_dx(<map>, ctx).r, texture_dy(<map>, ctx).r
+            if (map->kind != Val::Ctor || map->name != "texture_dx") fail("make_bumpmap: texture_dx(map, ctx).r expected as the x derivative");
+            const Val& dy = ctor_arg(b, 3);
+            if (dy.kind != Val::Ctor || dy.name != "texture_dy") fail("make_bumpmap: texture_dy(map, ctx).r expected as the y derivative");
+            map = &ctor_arg(*map, 0);
+        }
+        m.map_tex = texture_of(*map, textures, bump ? "bump map" : "normal map");
+        m.map_strength = as_num(ctor_arg(b, bump ? 4 : 3), "map strength");
+        const Val inner = ctor_arg(b, 1);
+        if (inner.kind != Val::Ctor || inner.name == "make_bumpmap" || inner.name == "make_normalmap") fail("bump / normal map without a plain inner BSDF");
+        b = inner;
+    }
     if (hit.emissive) {   // ShaderUtils.cpp:127-136: the light id lives in the stage's LocalRegistry
         if (!r.local || !r.local->IntParameters.count("_light_id")) fail("emissive material without '_light_id' in its local registry");
         m.light_id = r.local->IntParameters.at("_light_id");
@@ -449,23 +581,30 @@ igb200_material resolve_material(const StageDescriptor& hit, const Registries& r
         const float rough = as_num(ctor_arg(b, 1), "diffuse roughness");
         if (rough > 1.1920928955e-07f) fail("rough (Oren-Nayar) diffuse BSDFs are not supported by this device");
         m.bsdf = IGB200_BSDF_DIFFUSE;
-        put3(m.p, as_vec(ctor_arg(b, 2), "diffuse reflectance"));
+        colour_or_texture(ctor_arg(b, 2), m.p, &m.tex[0], textures, "diffuse reflectance");
     } else if (b.name == "make_dielectric_bsdf") {  // DielectricBSDF.cpp:13-41; bsdf/dielectric.art:15-37,195
         const Val& md = ctor_arg(b, 5);
         if (md.kind != Val::Ctor || md.name != "microfacet::make_delta_distribution") fail("rough dielectric BSDFs are not supported by this device");
         if (as_num(ctor_arg(b, 6), "dielectric thin flag") != 0) fail("thin dielectric BSDFs are not supported by this device");
         m.bsdf = IGB200_BSDF_DIELECTRIC;
         m.p[0] = as_num(ctor_arg(b, 1), "ext_ior"); m.p[1] = as_num(ctor_arg(b, 2), "int_ior");
-        put3(m.p + 2, as_vec(ctor_arg(b, 3), "specular_reflectance"));
-        put3(m.p + 5, as_vec(ctor_arg(b, 4), "specular_transmittance"));
+        colour_or_texture(ctor_arg(b, 3), m.p + 2, &m.tex[0], textures, "specular_reflectance");
+        colour_or_texture(ctor_arg(b, 4), m.p + 5, &m.tex[1], textures, "specular_transmittance");
     } else if (b.name == "make_conductor_bsdf") {   // ConductorBSDF.cpp:13-35; bsdf/conductor.art:2-27,131-141
+        // BSDF::setupRoughness (BSDF.cpp:53-98): no roughness property -> make_delta_distribution; else make_vndf_ggx_distribution(face_normal, local,
+        // alpha_u, alpha_v) over the explicit pair or over compute_explicit(roughness, anisotropic) (evaluated inside the md block)
         const Val& md = ctor_arg(b, 4);
-        if (md.kind != Val::Ctor || md.name != "microfacet::make_delta_distribution") fail("rough conductor BSDFs are not supported by this device");
+        if (md.kind != Val::Ctor) fail("conductor: microfacet distribution expected");
+        if (md.name == "microfacet::make_vndf_ggx_distribution") {
+            m.distribution = IGB200_MICROFACET_VNDF_GGX;
+            m.alpha_u = as_num(ctor_arg(md, 2), "conductor alpha_u"); m.alpha_v = as_num(ctor_arg(md, 3), "conductor alpha_v");
+        } else if (md.name != "microfacet::make_delta_distribution")
+            fail("microfacet distribution '" + md.name + "' is not supported by this device (delta, vndf_ggx)");
         const Val eta = as_vec(ctor_arg(b, 1), "conductor eta");
         const Val kk = as_vec(ctor_arg(b, 2), "conductor k");
         m.bsdf = IGB200_BSDF_CONDUCTOR;
         put3(m.p, eta); put3(m.p + 3, kk);
-        put3(m.p + 6, as_vec(ctor_arg(b, 3), "specular_reflectance"));
+        colour_or_texture(ctor_arg(b, 3), m.p + 6, &m.tex[0], textures, "specular_reflectance");
         // conductor.art:133-135: `?eta && ?k && is_black_eps(eta, 1e-4) && is_white_eps(k, 1e-4)` -> make_mirror_bsdf
         bool mirror = eta.known && kk.known;
         for (int i = 0; i < 3; ++i) mirror = mirror && std::fabs(eta.f[i]) <= 1e-4f && std::fabs(kk.f[i] - 1) <= 1e-4f;
@@ -551,12 +690,35 @@ static igb200_light resolve_light(Eval& ev, const std::string& binding) {
     return out;
 }
 
-void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vector<igb200_light>& infinite, std::vector<igb200_light>& finite) {
+// Entry k of an embedded fix-table (`@<class>:<k>`): what load_simple_*_lights builds from it
+static igb200_light embedded_light(const std::string& name, const IG::SceneDatabase* db) {
+    const size_t colon = name.find(':');
+    const std::string cls = name.substr(1, colon - 1);
+    const size_t k = (size_t)std::strtoul(name.c_str() + colon + 1, nullptr, 10);
+    if (!db) fail("embedded light table '" + cls + "' but no scene database to read it from");
+    const auto it = db->FixTables.find(cls);
+    if (it == db->FixTables.end()) fail("the scene database has no fix-table '" + cls + "'");
+    const std::vector<IG::uint8>& bytes = it->second.data();
+    igb200_light out;
+    std::memset(&out, 0, sizeof(out));
+    out.entity_id = -1;
+    if (cls == "SimplePointLight") {   // light/point.art:20-36, PointLight.cpp:70-78: position xyz, pad, intensity rgb, pad
+        if ((k + 1) * 32 > bytes.size()) fail("fix-table 'SimplePointLight' has no entry " + std::to_string(k));
+        float f[8];
+        std::memcpy(f, bytes.data() + k * 32, 32);
+        out.type = IGB200_LIGHT_POINT;
+        out.p[0] = f[0]; out.p[1] = f[1]; out.p[2] = f[2];
+        out.p[3] = f[4]; out.p[4] = f[5]; out.p[5] = f[6];
+    } else fail("embedded lights of class '" + cls + "' are not supported by this device (SimplePointLight)");
+    return out;
+}
+
+void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vector<igb200_light>& infinite, std::vector<igb200_light>& finite, const IG::SceneDatabase* db) {
     if (!stage.has_lights) fail(stage.function + " carries no light tables");
     Eval ev{stage, r};
     infinite.clear(); finite.clear();
     for (const std::string& b : stage.infinite_lights) infinite.push_back(resolve_light(ev, b));
-    for (const std::string& b : stage.finite_lights) finite.push_back(resolve_light(ev, b));
+    for (const std::string& b : stage.finite_lights) finite.push_back(!b.empty() && b[0] == '@' ? embedded_light(b, db) : resolve_light(ev, b));
 }
 
 igb200_technique resolve_technique(const StageDescriptor& stage, const Registries& r, std::vector<float>& selector_data) {

@@ -37,7 +37,7 @@ struct StageDescriptor {
     std::string bsdf_binding;                  // hit: `bsdf_<id>` used by the material shader
     bool emissive = false;                     // hit: make_emissive_material(..., @finite_lights.get(light_id))
     std::vector<std::string> infinite_lights;  // hit / miss: `light_<id>` bindings in table order
-    std::vector<std::string> finite_lights;
+    std::vector<std::string> finite_lights;    // ... or "@<EmbedClass>:<k>": entry k of the embedded fix-table of that class (LoaderLight.cpp:171-236)
     bool has_lights = false, has_technique = false, has_camera = false, list_emitter = false;
     bool std_aovs = false;                     // the technique is wrapped: wrap_infobuffer_renderer (Normals / Albedo AOVs, InfoBufferTechnique.cpp:13-17)
 };
@@ -52,8 +52,18 @@ StageDescriptor* parse_stage(const std::string& script, const std::string& funct
 // ---- resolve against registries ------------------------------------------------------------------------------------
 struct Registries { const IG::ParameterSet* local; const IG::ParameterSet* global; };
 
-igb200_material resolve_material(const StageDescriptor& hit, const Registries& r);     // throws RecognizeError
-void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vector<igb200_light>& infinite, std::vector<igb200_light>& finite);
+// The scene's texture table as it builds up while the materials are resolved (hit stages in material order): a texture gets the index of
+// its first use, as in the loader (ignis_b200/scene.py texture_id); the same texture met again in another stage (its `tex_<id>` binding may
+// carry another closure id there) is found by its contents.
+struct TextureTable {
+    std::vector<igb200_texture> records;
+    int add(const igb200_texture& t);
+};
+// textures: null = the stage must not use any (an error otherwise)
+igb200_material resolve_material(const StageDescriptor& hit, const Registries& r, TextureTable* textures = nullptr);     // throws RecognizeError
+// db: the scene database, needed when the finite lights come from embedded fix-tables (load_simple_point_lights reads FixTables["SimplePointLight"],
+// LoaderLight.cpp:171-236,397-422; light/point.art:20-36); null = such tables are an error
+void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vector<igb200_light>& infinite, std::vector<igb200_light>& finite, const IG::SceneDatabase* db = nullptr);
 // selector_data: contents of the buffer the cdf / hierarchy light selector reads (igb200_scene_desc::selector_data), empty for uniform
 igb200_technique resolve_technique(const StageDescriptor& stage, const Registries& r, std::vector<float>& selector_data);
 igb200_camera resolve_camera(const StageDescriptor& raygen, const Registries& r);

@@ -23,7 +23,8 @@ SYMBOLS = ["ig_get_interface", "igbh_last_error", "igbh_interface_version", "igb
            "igbh_params_set_vec3", "igbh_params_set_color", "igbh_compile", "igbh_describe_material", "igbh_describe_lights", "igbh_describe_technique",
            "igbh_describe_camera", "igbh_set_create", "igbh_set_destroy", "igbh_set_raygen", "igbh_set_miss", "igbh_set_add_hit", "igbh_device_create",
            "igbh_device_destroy", "igbh_device_assign", "igbh_assign_release", "igbh_device_render", "igbh_device_resize", "igbh_device_framebuffer",
-           "igbh_device_clear", "igbh_device_stats", "igbh_device_gpu_count"]
+           "igbh_device_clear", "igbh_device_stats", "igbh_device_gpu_count", "igbh_textures_create", "igbh_textures_destroy", "igbh_textures_count",
+           "igbh_textures_get", "igbh_describe_material_tex", "igbh_describe_lights_db"]
 
 
 def lib():
@@ -73,6 +74,12 @@ def lib():
         L.igbh_device_clear.argtypes = [vp]
         L.igbh_device_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.igbh_device_gpu_count.argtypes = [vp]
+        L.igbh_textures_create.restype = vp
+        L.igbh_textures_destroy.argtypes = [vp]
+        L.igbh_textures_count.argtypes = [vp]
+        L.igbh_textures_get.argtypes = [vp, C.c_int, vp]
+        L.igbh_describe_material_tex.argtypes = [vp, vp, vp, vp, vp]
+        L.igbh_describe_lights_db.argtypes = [vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp, C.POINTER(C.c_int), C.c_int]
         _LIB = L
     return _LIB
 
@@ -102,6 +109,42 @@ class Params:
             self.h = None
 
 
+class FixTableDB:
+    """A SceneDatabase holding only fix-tables (the embedded light tables of a StageSet): enough for CompiledStage.lights."""
+
+    def __init__(self, fix_tables: dict):
+        L = lib()
+        self.h = L.igbh_db_create()
+        for name, tab in fix_tables.items():
+            tab = np.ascontiguousarray(tab, np.float32)
+            L.igbh_db_set_fix(self.h, name.encode(), tab.ctypes.data, tab.nbytes, tab.shape[0])
+
+    def close(self):
+        if self.h:
+            lib().igbh_db_destroy(self.h)
+            self.h = None
+
+
+class TextureTable:
+    """The texture table the recogniser builds while the hit stages of a scene are resolved in material order."""
+
+    def __init__(self):
+        self.h = lib().igbh_textures_create()
+
+    def records(self) -> np.ndarray:
+        from .scene import TEXTURE_DTYPE
+        n = lib().igbh_textures_count(self.h)
+        out = np.zeros(n, TEXTURE_DTYPE)
+        for i in range(n):
+            lib().igbh_textures_get(self.h, i, out[i:i + 1].ctypes.data)
+        return out
+
+    def close(self):
+        if self.h:
+            lib().igbh_textures_destroy(self.h)
+            self.h = None
+
+
 class CompiledStage:
     """ICompilerDevice::compileAndGet(script, function) + the stage's LocalRegistry (ShaderOutput<void*>)."""
 
@@ -117,10 +160,18 @@ class CompiledStage:
             raise DeviceError(_err())
         return out
 
-    def lights(self, global_params: Params):
+    def material_tex(self, global_params: Params, textures) -> np.ndarray:
+        """As material(), with the scene's texture table (igbh_textures_create) that the stage's textures are entered into."""
+        out = np.zeros((), MATERIAL_DTYPE)
+        if lib().igbh_describe_material_tex(self.handle, self.local.h, global_params.h, textures.h, out.ctypes.data):
+            raise DeviceError(_err())
+        return out
+
+    def lights(self, global_params: Params, db=None):
+        """db: an igbh_db handle holding the embedded light fix-tables, when the stage's finite lights come from them."""
         inf, fin = np.zeros(64, LIGHT_DTYPE), np.zeros(64, LIGHT_DTYPE)
         ni, nf = C.c_int(), C.c_int()
-        if lib().igbh_describe_lights(self.handle, self.local.h, global_params.h, inf.ctypes.data, C.byref(ni), fin.ctypes.data, C.byref(nf), 64):
+        if lib().igbh_describe_lights_db(self.handle, self.local.h, global_params.h, db.h if db is not None else None, inf.ctypes.data, C.byref(ni), fin.ctypes.data, C.byref(nf), 64):
             raise DeviceError(_err())
         return inf[:ni.value].copy(), fin[:nf.value].copy()
 
@@ -174,6 +225,9 @@ class PluginRuntime:
             if len(sel):
                 L.igbh_db_set_bvh(self.db, prov, sel.ctypes.data, sel.nbytes)
         L.igbh_db_set_bbox(self.db, (C.c_float * 3)(*[float(x) for x in tables.bbox_min]), (C.c_float * 3)(*[float(x) for x in tables.bbox_max]), len(self.hits))
+        for name, tab in self.stages.fix_tables.items():   # LoaderLight::embedLights (LoaderLight.cpp:397-422)
+            tab = np.ascontiguousarray(tab, np.float32)
+            L.igbh_db_set_fix(self.db, name.encode(), tab.ctypes.data, tab.nbytes, tab.shape[0])
         self.dev = L.igbh_device_create(cuda_device)
         if not self.dev:
             raise DeviceError(f"createRenderDevice failed: {_err()}")

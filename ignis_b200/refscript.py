@@ -10,9 +10,14 @@ after the generators:
   stage prologue / database / scene     src/runtime/shader/ShaderUtils.cpp:13-53,55-62,101-141,174-204,206-216
   ig_ray_generation_shader              src/runtime/shader/RayGenerationShader.cpp:12-70, camera/PerspectiveCamera.cpp:26-67
   ig_hit_shader / ig_miss_shader        src/runtime/shader/HitShader.cpp:16-53, MissShader.cpp:15-47
-  BSDFs                                 src/runtime/bsdf/DiffuseBSDF.cpp:13-27, DielectricBSDF.cpp:13-41, BSDF.cpp:53-63
+  BSDFs                                 src/runtime/bsdf/DiffuseBSDF.cpp:13-27, DielectricBSDF.cpp:13-41, ConductorBSDF.cpp:13-35, BSDF.cpp:53-98
+                                        (setupRoughness), MapBSDF.cpp:17-55 (bumpmap / normalmap)
+  textures                              src/runtime/pattern/CheckerBoardPattern.cpp:13-33, loader/ShadingTree.cpp:375-405,795-840 and
+                                        Transpiler.cpp:991,1301 (a texture name inside a colour -> `vec4_to_color(color_to_vec4(tex_<id>(ctx)))`);
+                                        image textures name a file the runtime's image loader decodes: not reconstructed
   lights + tables                       src/runtime/light/{AreaLight.cpp:115-220, PointLight.cpp:44-62, EnvironmentLight.cpp:103-110},
-                                        src/runtime/loader/LoaderLight.cpp:106-247,423-453
+                                        src/runtime/loader/LoaderLight.cpp:106-247,423-453; embedded simple point lights
+                                        (>= 10 simple lights, LoaderLight.h:27): LoaderLight.cpp:171-236,397-422, PointLight.cpp:64-78
   technique                             src/runtime/technique/PathTechnique.cpp:35-79
   value inlining rules                  src/runtime/loader/ShadingTree.cpp:868-981 (default specialisation: only all-zero / all-one
                                         values are printed into the text, with std::to_string's 6 decimals; everything else goes
@@ -27,7 +32,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from .scene import (BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_DIFFUSE, LIGHT_ENV_CONST, LIGHT_PLANE_AREA, LIGHT_POINT, LIGHT_SHAPE_AREA, LIGHT_SPHERE_AREA, LIGHT_SPOT,
-                    SHAPE_SPHERE, SceneTables)
+                    MAP_BUMP, MAP_NONE, MICROFACET_VNDF_GGX, SHAPE_SPHERE, TEX_CHECKERBOARD, SceneTables)
 
 STD_LIB_STUB = "// <the Artic standard library (ig_api[], ScriptCompiler.cpp:36-51) precedes every stage>\nfn @make_dummy() = 0;\n\n"
 
@@ -54,6 +59,7 @@ class StageSet:
     miss: Stage
     hits: list
     global_registry: Registry
+    fix_tables: dict = field(default_factory=dict)   # what LoaderLight::embedLights adds to the scene database: class name -> (n, words) float32
 
 
 def _ts(x: float) -> str:
@@ -68,7 +74,7 @@ class _Tree:
     """ShadingTree: closure ids + the inline-or-registry decision."""
 
     def __init__(self, local: Registry, specialization: str):
-        self.local, self.mode, self.ids, self.header = local, specialization, {}, []
+        self.local, self.mode, self.ids, self.header, self.textures = local, specialization, {}, [], set()
 
     def closure(self, name: str) -> str:
         return str(self.ids.setdefault(name, len(self.ids)))
@@ -81,8 +87,8 @@ class _Tree:
         v = np.asarray(vals, np.float32).ravel()
         return bool((zero and np.all(np.abs(v) <= 1.1920929e-07)) or (one and np.all(np.abs(v - 1) <= 1.1920929e-07)))
 
-    def number(self, cid, prop, val, dynamic=False) -> str:
-        if not dynamic and self._embed([val]):
+    def number(self, cid, prop, val, dynamic=False, zero=True, one=True) -> str:
+        if not dynamic and self._embed([val], zero, one):
             return _ts(val)
         key = f"{cid}_{prop}"
         self.local.floats[key] = float(np.float32(val))
@@ -110,6 +116,26 @@ class _Tree:
         self.local.vectors[key] = tuple(float(np.float32(c)) for c in xyz)
         self.header.append(f'  let var_vec_{key} = registry::get_local_parameter_vec3("{key}", vec3_expand(0));\n')
         return f"var_vec_{key}"
+
+    def texture(self, t: SceneTables, tex: int) -> str:
+        """The look-up a texture name turns into inside a colour expression; the texture's own `let` goes to the header once per stage
+        (ShadingTree::registerTextureUsage, ShadingTree.cpp:795-804)."""
+        cid = self.closure(f"__tex_{tex}")
+        if tex not in self.textures:
+            self.textures.add(tex)
+            rec = t.textures[tex]
+            if int(rec["type"]) != TEX_CHECKERBOARD:
+                raise ValueError("image textures are outside the script path: the runtime's image loader decodes the file (refscript.py header)")
+            p = rec["p"]
+            c0, c1 = self.color(cid, "color0", p[2:5]), self.color(cid, "color1", p[5:8])
+            sx, sy = self.number(cid, "scale_x", p[0]), self.number(cid, "scale_y", p[1])
+            a, b, c, d, e, f = (float(x) for x in rec["transform"])
+            if (a, b, c, d, e, f) == (1, 0, 0, 0, 1, 0):
+                tr = "mat3x3_identity()"
+            else:   # LoaderUtils::inlineMatrix: columns, streamed with the default precision
+                tr = "make_mat3x3(" + ", ".join("make_vec3(%s, %s, %s)" % tuple(_stream(x) for x in col) for col in ((a, d, 0), (b, e, 0), (c, f, 1))) + ")"
+            self.header.append(f"  let tex_{cid} : Texture = make_checkerboard_texture(make_vec2({sx}, {sy}), {c0}, {c1}, {tr});\n")
+        return f"vec4_to_color(color_to_vec4(tex_{cid}(ctx)))"
 
     def pull_header(self) -> str:
         h, self.header = "".join(self.header), []
@@ -173,7 +199,26 @@ def _lights(t: SceneTables, tree: _Tree) -> str:
     for i, n in enumerate(inf_names):
         s += f"      {i} => {n},\n"
     s += "      _ => make_null_light(id)\n    }\n  }};\n  maybe_unused(infinite_lights);\n"
+    # LoaderLight.cpp:152-236: with >= 10 simple lights (LoaderLight.h:27) those come from per-class fix-tables and lead the id space, class by
+    # class (ignis_b200/scene.py orders the records that way); only the others are written into the text
+    embedded = []   # (class, count, offset)
+    if t.embedded_lights:
+        cls_of = {LIGHT_POINT: "SimplePointLight", LIGHT_SPOT: "SimpleSpotLight", LIGHT_PLANE_AREA: "SimplePlaneLight", LIGHT_SHAPE_AREA: "SimpleAreaLight",
+                  LIGHT_SPHERE_AREA: "SimpleSphereLight"}
+        for i, l in enumerate(t.finite_lights):
+            c = cls_of.get(int(l["type"]))
+            if c is None:
+                break
+            if c != "SimplePointLight":
+                raise ValueError(f"embedded lights of class {c} are outside the script path (SimplePointLight only)")
+            if embedded and embedded[-1][0] == c:
+                embedded[-1] = (c, embedded[-1][1] + 1, embedded[-1][2])
+            else:
+                embedded.append((c, 1, i))
+    n_embedded = sum(e[1] for e in embedded)
     for i, l in enumerate(t.finite_lights):
+        if i < n_embedded:
+            continue
         cid = tree.closure(f"__fin_light_{i}")
         ty, p = int(l["type"]), l["p"]
         if ty == LIGHT_POINT:
@@ -221,11 +266,23 @@ def _lights(t: SceneTables, tree: _Tree) -> str:
         else:
             raise ValueError(ty)
         fin_names.append(f"light_{cid}")
-    s += "\n" if fin_names else ""
-    s += f"  let finite_lights = LightTable {{\n    count = {len(fin_names)},\n    get   = @|id:i32| {{\n    match(id) {{\n"
+    s += "\n" if (fin_names or n_embedded) else ""
+    for c, count, offset in embedded:
+        s += f"  let e_{c.lower()} = load_simple_point_lights({count}, {offset}, device);\n"
+        if count == len(t.finite_lights):   # nothing except one embedded class (LoaderLight.cpp:188-193)
+            return s + f"  let finite_lights = e_{c.lower()};\n  maybe_unused(finite_lights);\n"
+    s += f"  let finite_lights = LightTable {{\n    count = {len(fin_names) + n_embedded},\n    get   = @|id:i32| {{\n"
+    for k, (c, count, offset) in enumerate(embedded):
+        s += ("    else if " if k else "    if ") + f"id < {offset + count} {{\n      e_{c.lower()}.get(id - {offset})\n    }}\n"
+    if embedded:
+        s += "    else {\n"
+    s += "    match(id) {\n"
     for i, n in enumerate(fin_names):
-        s += f"      {i} => {n},\n"
-    s += "      _ => make_null_light(id)\n    }\n  }};\n  maybe_unused(finite_lights);\n"
+        s += f"      {i + n_embedded} => {n},\n"
+    s += "      _ => make_null_light(id)\n"
+    if embedded:
+        s += "    }\n"
+    s += "    }\n  }};\n  maybe_unused(finite_lights);\n"
     return s
 
 
@@ -261,25 +318,48 @@ def _bsdf(t: SceneTables, mat_id: int, tree: _Tree) -> str:
     m = t.materials[mat_id]
     cid = tree.closure(f"__bsdf_{mat_id}")
     p = m["p"]
+    s = ""
+    outer = None
+    if int(m["map_kind"]) != MAP_NONE:   # MapBSDF.cpp:17-55: the wrapper's closure comes first (map texture, strength), then the inner BSDF's statements
+        outer = cid
+        tex = tree.texture(t, int(m["map_tex"]))
+        strength = tree.number(outer, "strength", m["map_strength"])
+        cid = tree.closure(f"__bsdf_{mat_id}_inner")
+
+    def colour(prop, rgb, k, **kw):
+        return tree.texture(t, int(m["tex"][k])) if int(m["tex"][k]) >= 0 else tree.color(cid, prop, rgb, **kw)
+
     if int(m["bsdf"]) == BSDF_DIFFUSE:
-        refl = tree.color(cid, "reflectance", p[0:3])
+        refl = colour("reflectance", p[0:3], 0)
         rough = tree.number(cid, "roughness", 0.0)
-        s = tree.pull_header() + f"  let bsdf_{cid} : BSDFShader = @|ctx| make_diffuse_bsdf(ctx.surf, {rough}, {refl});\n"
+        s += tree.pull_header() + f"  let bsdf_{cid} : BSDFShader = @|ctx| make_diffuse_bsdf(ctx.surf, {rough}, {refl});\n"
     elif int(m["bsdf"]) == BSDF_DIELECTRIC:
-        ks = tree.color(cid, "specular_reflectance", p[2:5])
-        kt = tree.color(cid, "specular_transmittance", p[5:8])
+        ks = colour("specular_reflectance", p[2:5], 0)
+        kt = colour("specular_transmittance", p[5:8], 1)
         ext = tree.number(cid, "ext_ior", p[0])
         int_ = tree.number(cid, "int_ior", p[1])
-        s = f"  let md_{cid} = @|ctx : ShadingContext| microfacet::make_delta_distribution(ctx.surf.local);\n"
+        s += f"  let md_{cid} = @|ctx : ShadingContext| microfacet::make_delta_distribution(ctx.surf.local);\n"
         s += tree.pull_header() + (f"  let bsdf_{cid} : BSDFShader = @|ctx| make_dielectric_bsdf(ctx.surf, {ext}, {int_}, {ks}, {kt}, md_{cid}(ctx), false);\n")
     elif int(m["bsdf"]) == BSDF_CONDUCTOR:   # ConductorBSDF.cpp:13-35 (eta: ColorOptions::Black, k: ColorOptions::White)
-        ks = tree.color(cid, "specular_reflectance", p[6:9])
+        ks = colour("specular_reflectance", p[6:9], 0)
         eta = tree.color(cid, "eta", p[0:3], one=False)    # ColorOptions::Black(): only black is printed into the text
         kk = tree.color(cid, "k", p[3:6], zero=False)       # ColorOptions::White()
-        s = f"  let md_{cid} = @|ctx : ShadingContext| microfacet::make_delta_distribution(ctx.surf.local);\n"
+        if int(m["distribution"]) == MICROFACET_VNDF_GGX:   # BSDF::setupRoughness, the explicit form (roughness_u / roughness_v; NumberOptions::Zero)
+            au, av = tree.number(cid, "roughness_u", m["alpha_u"], one=False), tree.number(cid, "roughness_v", m["alpha_v"], one=False)
+            s += tree.pull_header() + (f"  let md_{cid} = @|ctx : ShadingContext| microfacet::make_vndf_ggx_distribution(ctx.surf.face_normal, ctx.surf.local, {au}, {av});\n")
+        else:
+            s += f"  let md_{cid} = @|ctx : ShadingContext| microfacet::make_delta_distribution(ctx.surf.local);\n"
         s += tree.pull_header() + f"  let bsdf_{cid} : BSDFShader = @|ctx| make_conductor_bsdf(ctx.surf, {eta}, {kk}, {ks}, md_{cid}(ctx));\n"
     else:
         raise ValueError(int(m["bsdf"]))
+    if outer is not None:
+        if int(m["map_kind"]) == MAP_BUMP:
+            tf = f"@|ctx:ShadingContext|->Color{{maybe_unused(ctx); {tex}}}"   # ShadingTree::addTexture, the string case
+            s += tree.pull_header() + (f"  let bsdf_{outer} : BSDFShader = @|ctx| make_bumpmap(ctx, @|surf2| -> Bsdf {{  bsdf_{cid}(ctx.{{surf=surf2}}) }}, "
+                                       f"texture_dx({tf}, ctx).r, texture_dy({tf}, ctx).r, {strength});\n")
+        else:
+            s += tree.pull_header() + f"  let bsdf_{outer} : BSDFShader = @|ctx| make_normalmap(ctx, @|surf2| bsdf_{cid}(ctx.{{surf=surf2}}), {tex},{strength});\n"
+        cid = outer
     s += "  let medium_interface = no_medium_interface();\n"
     if int(m["light_id"]) >= 0:
         tree.local.ints["_light_id"] = int(m["light_id"])
@@ -343,4 +423,11 @@ def generate(t: SceneTables, specialization: str = "default", std_aovs: bool = T
         s += _database(has_sphere) + _lights(t, tree) + "\n" + _bsdf(t, mat_id, tree) + _technique(t, std_aovs, cache_dir) + "\n"
         s += "  let use_framebuffer = true;\n  device.handle_hit_shader(shader, scene, full_technique, payload_info, first, last, use_framebuffer);\n}\n"
         hits.append(Stage("ig_hit_shader", s, local))
-    return StageSet(raygen, miss, hits, g)
+    fix = {}
+    if t.embedded_lights:   # PointLight::embed (PointLight.cpp:70-78): position xyz, pad, intensity rgb, pad
+        pts = [l for l in t.finite_lights if int(l["type"]) == LIGHT_POINT]
+        tab = np.zeros((len(pts), 8), np.float32)
+        for k, l in enumerate(pts):
+            tab[k, 0:3], tab[k, 4:7] = l["p"][0:3], l["p"][3:6]
+        fix["SimplePointLight"] = tab
+    return StageSet(raygen, miss, hits, g, fix)

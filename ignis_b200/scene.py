@@ -482,7 +482,9 @@ def load_image_for_device(path: str, linear_hint: bool = False):
 def transform_2d(v) -> np.ndarray:
     """LoaderUtils::inlineTransformAs2d (LoaderUtils.cpp:40-46): rows 0 and 1 of [linear 2x2 | translation xy]."""
     t = parse_transform(v)
-    return np.array([t[0, 0], t[0, 1], t[0, 3], t[1, 0], t[1, 1], t[1, 3]], F)
+    # the generator streams the matrix into shader text (LoaderUtils::inlineMatrix / inlineVector: operator<< with the default precision), so
+    # the device only ever sees six significant digits of every element
+    return np.array([float("%g" % float(F(x))) for x in (t[0, 0], t[0, 1], t[0, 3], t[1, 0], t[1, 1], t[1, 3])], F)
 
 
 def image_pixels_f32(fmt: int, arr: np.ndarray) -> np.ndarray:

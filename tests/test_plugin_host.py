@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "evaluation/cbox-d6.json", "evaluation/multilight-uniform.json",
           "evaluation/multilight-simple.json", "evaluation/multilight-hierarchy.json",
           "evaluation/emissive-plane.json", "evaluation/point.json", "evaluation/plane-d1.json", "evaluation/sphere-light-pure.json",
-          "evaluation/two-planes-mirror.json", "evaluation/sun-on-plane.json", "<spot>", "<distant>"]
+          "evaluation/two-planes-mirror.json", "evaluation/sun-on-plane.json", "<spot>", "<distant>", "<procedural>", "<points-only>"]
 
 
 def scene(name):
@@ -31,6 +31,37 @@ def scene(name):
         s["lights"].append({"type": "directional", "name": "_d", "direction": [0.2, 0.1, 1], "irradiance": [1, 0.5, 0.25]})
         s["lights"].append({"type": "sun", "name": "_s", "elevation": 1.1, "azimuth": 0.4, "irradiance": [3, 2, 1], "angle": 2.5})
         s["lights"].append({"type": "env", "name": "_e", "radiance": [0.1, 0.1, 0.1]})
+        return load_scene(s)
+    if name == "<procedural>":
+        # everything of SURVEY 8f-1 / f-2 that needs no image file: checkerboard textures (one with a transform) as colours and as bump / normal
+        # maps, rough conductors (explicit and roughness + anisotropic), and 12 simple point lights -> an embedded fix-table
+        from conftest import furnace_scene
+        s = furnace_scene()
+        s["technique"]["max_depth"] = 6
+        s["textures"] = [{"type": "checkerboard", "name": "check", "scale_x": 6, "scale_y": 3, "color0": [0.2, 0.3, 0.4], "color1": [0.9, 0.8, 0.7], "transform": {"rotate": [0, 0, 30]}},
+                         {"type": "checkerboard", "name": "grid", "scale_x": 11, "scale_y": 11, "color0": [0, 0, 0], "color1": [1, 1, 1]}]
+        s["bsdfs"] = [{"type": "diffuse", "name": "d_check", "reflectance": "check"},
+                      {"type": "conductor", "name": "rc", "roughness": 0.2, "anisotropic": 0.4, "material": "copper"},
+                      {"type": "conductor", "name": "rc2", "roughness_u": 0.15, "roughness_v": 0.3, "specular_reflectance": "grid"},
+                      {"type": "dielectric", "name": "g_tex", "specular_reflectance": "check", "specular_transmittance": "grid"},
+                      {"type": "bumpmap", "name": "b_rc", "bsdf": "rc", "map": "grid", "strength": 0.35},
+                      {"type": "normalmap", "name": "n_d", "bsdf": "d_check", "map": "check", "strength": 0.8},
+                      {"type": "diffuse", "name": "white", "reflectance": [1, 1, 1]}]
+        s["shapes"] = [{"type": "cube", "name": "Box", "width": 1.0, "height": 1.0, "depth": 1.0, "origin": [-0.5, -0.5, -0.5]},
+                       {"type": "rectangle", "name": "Floor", "width": 12, "height": 12, "origin": [-6, -6, -0.9]},
+                       {"type": "rectangle", "name": "Lamp", "width": 1, "height": 1, "flip_normals": True}, {"type": "uvsphere", "name": "UV", "radius": 0.45}]
+        s["entities"] = [{"name": "Floor", "shape": "Floor", "bsdf": "d_check"},
+                         {"name": "Lamp", "shape": "Lamp", "bsdf": "white", "transform": {"translate": [0, 0, 3]}}]
+        for k, b in enumerate(["rc", "rc2", "g_tex", "b_rc", "n_d"]):
+            s["entities"].append({"name": f"e{k}", "shape": "UV" if k % 2 else "Box", "bsdf": b, "transform": [{"translate": [-2.0 + k, 0.3 * k, 0]}, {"rotate": [10 * k, 20, 5 * k]}]})
+        s["camera"]["transform"] = {"lookat": {"origin": [0.5, -6.5, 3.0], "target": [0, 0, 0], "up": [0, 0, 1]}}
+        s["lights"] = [{"type": "env", "name": "env", "radiance": [0.3, 0.35, 0.4]}]
+        s["lights"] += [{"type": "point", "name": f"p{k}", "position": [np.cos(k) * 3, np.sin(k) * 3, 2 + 0.1 * k], "intensity": [1 + k, 2, 3]} for k in range(12)]
+        return load_scene(s)
+    if name == "<points-only>":   # nothing but embedded simple point lights: `let finite_lights = e_simplepointlight;` (LoaderLight.cpp:188-193)
+        from conftest import flat_scene
+        s = flat_scene()
+        s["lights"] = [{"type": "point", "name": f"p{k}", "position": [0.1 * k - 0.5, 0.05 * k, -2], "power" if k % 2 else "intensity": [1, 1 + k, 1]} for k in range(11)]
         return load_scene(s)
     return load_scene(os.path.join(ROOT, "scenes", name))
 
@@ -52,9 +83,18 @@ def test_recognised_descriptors_equal_loader_descriptors(name, mode, tmp_path):
     g = plugin.Params(st.global_registry)
     exact = mode != "force"   # `force` prints every value with std::to_string's 6 decimals (ShadingTree.cpp:933-981): lossy by design
     hits = [plugin.CompiledStage(s) for s in st.hits]
+    textures = plugin.TextureTable()
+    db = plugin.FixTableDB(st.fix_tables)
     for i, h in enumerate(hits):
-        m = h.material(g)
+        m = h.material_tex(g, textures)
         assert int(m["bsdf"]) == int(t.materials[i]["bsdf"]) and int(m["light_id"]) == int(t.materials[i]["light_id"])
+        for f in ("tex", "distribution", "map_kind", "map_tex"):   # textures by index of first use, the microfacet distribution, the map wrapper
+            np.testing.assert_array_equal(m[f], t.materials[i][f], err_msg=f"material {i}: {f}")
+        for f in ("alpha_u", "alpha_v", "map_strength"):
+            if exact:
+                assert np.float32(m[f]).view(np.uint32) == np.float32(t.materials[i][f]).view(np.uint32), (i, f, m[f], t.materials[i][f])
+            else:
+                np.testing.assert_allclose(m[f], t.materials[i][f], atol=1e-6)
         ref_p = t.materials[i]["p"].copy()
         if int(m["bsdf"]) == 2 and mode == "disable":
             ref_p[9] = 0   # eta / k come from the registry, Artic's `?eta` is false: the reference itself takes make_pure_conductor_bsdf then
@@ -62,8 +102,18 @@ def test_recognised_descriptors_equal_loader_descriptors(name, mode, tmp_path):
             np.testing.assert_array_equal(m["p"].view(np.uint32), ref_p.view(np.uint32))
         else:
             np.testing.assert_allclose(m["p"], ref_p, atol=1e-6)
+    got_tex = textures.records()
+    assert len(got_tex) == len(t.textures)
+    for k in range(len(got_tex)):
+        for f in ("type", "image", "filter", "border_u", "border_v"):
+            assert int(got_tex[k][f]) == int(t.textures[k][f]), (k, f)
+        for f in ("transform", "p"):
+            if exact:
+                np.testing.assert_array_equal(got_tex[k][f].view(np.uint32), t.textures[k][f].view(np.uint32), err_msg=f"texture {k}: {f}")
+            else:
+                np.testing.assert_allclose(got_tex[k][f], t.textures[k][f], atol=1e-6)
     for stage in [plugin.CompiledStage(st.miss)] + hits[:1]:
-        inf, fin = stage.lights(g)
+        inf, fin = stage.lights(g, db)
         assert len(inf) == len(t.infinite_lights) and len(fin) == len(t.finite_lights)
         for got, ref in list(zip(inf, t.infinite_lights)) + list(zip(fin, t.finite_lights)):
             assert int(got["type"]) == int(ref["type"])
@@ -110,7 +160,8 @@ def test_unknown_constructs_fail_loudly():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,w,h,spi", [("diamond_scene.json", 160, 90, 2), ("primitives.json", 160, 90, 2), ("evaluation/multilight-uniform.json", 96, 96, 2),
-                                           ("evaluation/multilight-hierarchy.json", 96, 96, 2), ("evaluation/multilight-simple.json", 96, 96, 2)])
+                                           ("evaluation/multilight-hierarchy.json", 96, 96, 2), ("evaluation/multilight-simple.json", 96, 96, 2),
+                                           ("<procedural>", 160, 120, 2), ("<points-only>", 96, 96, 2)])
 def test_render_through_cpp_plugin_matches_oracle(name, w, h, spi):
     from oracle.oracle import Oracle
     t = scene(name)
@@ -206,3 +257,54 @@ def test_plugin_device_spreads_the_frame_over_its_gpus(name, w, h, spi, monkeypa
     with plugin.PluginRuntime(t, 4096, 1, 1, tracer=True) as rt3:
         one = rt3.trace(rays)
     np.testing.assert_allclose(two, one, rtol=1e-4, atol=1e-5)
+
+
+def test_recogniser_reads_the_other_forms_the_generators_emit(tmp_path):
+    """Forms the reference's generators produce that refscript does not (it only has the loader's final values to go by): the roughness +
+    anisotropic distribution block of BSDF::setupRoughness (BSDF.cpp:88-96) and a light table that mixes an embedded class with lights
+    written into the text (LoaderLight.cpp:199-246)."""
+    import re
+    t = scene("<procedural>")
+    st = refscript.generate(t, cache_dir=str(tmp_path))
+    g = plugin.Params(st.global_registry)
+    # ---- material 1 is the conductor with roughness 0.2, anisotropic 0.4
+    i = next(k for k in range(len(t.materials)) if int(t.materials[k]["distribution"]) == 1 and int(t.materials[k]["map_kind"]) == 0 and int(t.materials[k]["tex"][0]) < 0)
+    hit = st.hits[i]
+    md = re.search(r"let md_(\w+) = @\|ctx : ShadingContext\| microfacet::make_vndf_ggx_distribution\(ctx\.surf\.face_normal, ctx\.surf\.local, [^;]*\);", hit.script)
+    assert md, hit.script
+    block = (f"let md_{md.group(1)} = @|ctx : ShadingContext| {{ let (ru, rv) = microfacet::compute_explicit(var_num_x_roughness, var_num_x_anisotropic);"
+             "microfacet::make_vndf_ggx_distribution(ctx.surf.face_normal, ctx.surf.local, ru, rv) };")
+    script = hit.script.replace(md.group(0), '  let var_num_x_roughness = registry::get_local_parameter_f32("x_roughness", 0);\n'
+                                             '  let var_num_x_anisotropic = registry::get_local_parameter_f32("x_anisotropic", 0);\n  ' + block)
+    local = refscript.Registry(ints=dict(hit.local.ints), floats=dict(hit.local.floats, x_roughness=0.2, x_anisotropic=0.4), vectors=dict(hit.local.vectors), colors=dict(hit.local.colors))
+    m = plugin.CompiledStage(refscript.Stage(hit.function, script, local)).material_tex(g, plugin.TextureTable())
+    for f in ("alpha_u", "alpha_v"):
+        assert np.float32(m[f]).view(np.uint32) == np.float32(t.materials[i][f]).view(np.uint32), (f, m[f], t.materials[i][f])
+    assert int(m["distribution"]) == 1
+    # an isotropic literal: `?anisotropic && anisotropic == 0` -> aspect 1 exactly
+    m0 = plugin.CompiledStage(refscript.Stage(hit.function, hit.script.replace(md.group(0), "  " + block.replace("var_num_x_roughness", "0.250000").replace("var_num_x_anisotropic", "0.000000")), hit.local)).material_tex(g, plugin.TextureTable())
+    assert float(m0["alpha_u"]) == float(m0["alpha_v"]) == 0.25
+    # the plain ggx / beckmann distributions are not what this device implements
+    with pytest.raises(plugin.DeviceError, match="not supported"):
+        plugin.CompiledStage(refscript.Stage(hit.function, hit.script.replace("microfacet::make_vndf_ggx_distribution(ctx.surf.face_normal, ", "microfacet::make_ggx_distribution("), hit.local)).material_tex(g, plugin.TextureTable())
+    # ---- a table of 12 embedded point lights followed by one written-out point light
+    miss = st.miss
+    assert "let finite_lights = e_simplepointlight;" in miss.script
+    mixed = miss.script.replace("  let finite_lights = e_simplepointlight;\n",
+                                "  let light_99 = make_point_light(12, make_vec3(1.000000, 0.000000, 1.000000), make_color(0.000000, 1.000000, 0.000000, 1));\n"
+                                "  let finite_lights = LightTable {\n    count = 13,\n    get   = @|id:i32| {\n    if id < 12 {\n      e_simplepointlight.get(id - 0)\n    }\n"
+                                "    else {\n    match(id) {\n      12 => light_99,\n      _ => make_null_light(id)\n    }\n    }\n  }};\n")
+    db = plugin.FixTableDB(st.fix_tables)
+    inf, fin = plugin.CompiledStage(refscript.Stage(miss.function, mixed, miss.local)).lights(g, db)
+    assert len(fin) == 13 and [int(x["type"]) for x in fin] == [1] * 13
+    for k in range(12):
+        np.testing.assert_array_equal(fin[k]["p"].view(np.uint32), t.finite_lights[k]["p"].view(np.uint32))
+    np.testing.assert_array_equal(fin[12]["p"][:6], [1, 0, 1, 0, 1, 0])
+    # without the scene database the embedded entries cannot be resolved, and that is an error, not a guess
+    with pytest.raises(plugin.DeviceError, match="scene database"):
+        plugin.CompiledStage(miss).lights(g)
+    # image textures name a file: reported
+    tex_hit = next(h for h in st.hits if "make_checkerboard_texture" in h.script)
+    bad = re.sub(r"make_checkerboard_texture\([^;]*\);", 'make_image_texture(make_repeat_border(), make_bilinear_filter(), device.load_image("a.png", 4), mat3x3_identity());', tex_hit.script, count=1)
+    with pytest.raises(plugin.DeviceError, match="image textures"):
+        plugin.CompiledStage(refscript.Stage(tex_hit.function, bad, tex_hit.local)).material_tex(g, plugin.TextureTable())
