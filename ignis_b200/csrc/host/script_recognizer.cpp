@@ -30,11 +30,22 @@ static std::string trim(const std::string& s) {
 // Body of the LAST definition of `fn <function>(` in the script (the generated stage follows the standard library,
 // src/runtime/shader/ScriptCompiler.cpp:36-51).
 static std::string function_body(const std::string& script, const std::string& function) {
-    const std::string key = "fn " + function + "(";
-    const size_t at = script.rfind(key);
+    // `fn`, blanks, the name as a whole identifier, blanks, `(` -- whatever the layout (an attribute such as #[export] may precede it)
+    size_t at = std::string::npos, after = 0;
+    for (size_t q = script.rfind(function); q != std::string::npos; q = q == 0 ? std::string::npos : script.rfind(function, q - 1)) {
+        size_t e = q + function.size();
+        if (e < script.size() && ident_char(script[e])) continue;
+        while (e < script.size() && std::isspace((unsigned char)script[e])) ++e;
+        if (e >= script.size() || script[e] != '(') continue;
+        size_t b = q;
+        while (b > 0 && std::isspace((unsigned char)script[b - 1])) --b;
+        if (b == q || b < 2 || script.compare(b - 2, 2, "fn") != 0 || (b >= 3 && ident_char(script[b - 3]))) continue;
+        at = q; after = e + 1;
+        break;
+    }
     if (at == std::string::npos) fail("function '" + function + "' not found in the script");
     // skip the parameter list, then the return type up to the opening brace of the body
-    size_t p = at + key.size();
+    size_t p = after;
     int depth = 1;
     while (p < script.size() && depth > 0) { if (script[p] == '(') ++depth; else if (script[p] == ')') --depth; ++p; }
     while (p < script.size() && script[p] != '{') ++p;
@@ -43,6 +54,7 @@ static std::string function_body(const std::string& script, const std::string& f
     depth = 0;
     for (; p < script.size(); ++p) {
         const char c = script[p];
+        if (c == '/' && p + 1 < script.size() && script[p + 1] == '/') { while (p < script.size() && script[p] != '\n') ++p; continue; }   // comments may hold anything
         if (c == '"') { ++p; while (p < script.size() && script[p] != '"') ++p; continue; }
         if (c == '{') ++depth;
         else if (c == '}') { if (--depth == 0) return script.substr(open + 1, p - open - 1); }

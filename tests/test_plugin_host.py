@@ -308,3 +308,73 @@ def test_recogniser_reads_the_other_forms_the_generators_emit(tmp_path):
     bad = re.sub(r"make_checkerboard_texture\([^;]*\);", 'make_image_texture(make_repeat_border(), make_bilinear_filter(), device.load_image("a.png", 4), mat3x3_identity());', tex_hit.script, count=1)
     with pytest.raises(plugin.DeviceError, match="image textures"):
         plugin.CompiledStage(refscript.Stage(tex_hit.function, bad, tex_hit.local)).material_tex(g, plugin.TextureTable())
+
+
+def _perturb(script: str, rng) -> str:
+    """The same program with different trivia: blank lines, comments, extra statements that bind nothing, spaces around punctuation outside
+    string literals, and the independent registry look-ups (`let var_* = registry::get_*(...)`) of each run of them in another order."""
+    lines = script.split("\n")
+    out, run = [], []
+
+    def flush():
+        if run:
+            rng.shuffle(run)
+            out.extend(run)
+            run.clear()
+    for ln in lines:
+        if ln.lstrip().startswith("let var_") and "registry::get_" in ln and ln.rstrip().endswith(";"):
+            run.append(ln)
+            continue
+        flush()
+        out.append(ln)
+    flush()
+    res = []
+    for ln in out:
+        r = rng.random()
+        if r < 0.15:
+            res.append('  // a comment; with a semicolon, let x = make_point_light(0, a, b); a brace } and a quote " inside')
+        elif r < 0.25:
+            res.append("")
+        elif r < 0.32 and ln.rstrip().endswith(";") and ln.startswith("  let "):
+            res.append("  maybe_unused(settings);")
+        new, in_str = "", False
+        for ch in ln:
+            if ch == '"':
+                in_str = not in_str
+            if not in_str and ch in ",(" and rng.random() < 0.3:
+                new += ch + " " * int(rng.integers(1, 3))
+            elif not in_str and ch == ")" and rng.random() < 0.2:
+                new += " )"
+            elif not in_str and ch == " " and rng.random() < 0.1:
+                new += "  "
+            else:
+                new += ch
+        res.append(new + (" " * int(rng.integers(0, 3))))
+    return "\n".join(res)
+
+
+@pytest.mark.parametrize("name", ["diamond_scene.json", "evaluation/multilight-hierarchy.json", "<spot>", "<distant>", "<procedural>", "evaluation/sphere-light-pure.json"])
+def test_recogniser_does_not_depend_on_trivia(name, tmp_path):
+    """the stage text has only ever come from this repository's reconstruction of the generators, so at least the
+    recogniser must not depend on how that text is laid out: whitespace, comments, no-op statements and the order of independent bindings."""
+    t = scene(name)
+    st = refscript.generate(t, cache_dir=str(tmp_path))
+    g = plugin.Params(st.global_registry)
+    db = plugin.FixTableDB(st.fix_tables)
+    rng = np.random.default_rng(11)
+
+    def describe(stages):
+        tex = plugin.TextureTable()
+        hits = [plugin.CompiledStage(s) for s in stages.hits]
+        mats = [h.material_tex(g, tex).tobytes() for h in hits]
+        miss = plugin.CompiledStage(stages.miss)
+        inf, fin = miss.lights(g, db)
+        tech = miss.technique(g)
+        cam = plugin.CompiledStage(stages.raygen).camera(g)
+        return mats, tex.records().tobytes(), inf.tobytes(), fin.tobytes(), tech.tobytes(), miss.selector_data.tobytes(), cam.tobytes()
+    ref = describe(st)
+    for _ in range(4):
+        pert = refscript.StageSet(refscript.Stage(st.raygen.function, _perturb(st.raygen.script, rng), st.raygen.local),
+                                  refscript.Stage(st.miss.function, _perturb(st.miss.script, rng), st.miss.local),
+                                  [refscript.Stage(h.function, _perturb(h.script, rng), h.local) for h in st.hits], st.global_registry, st.fix_tables)
+        assert describe(pert) == ref
