@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 HOST_OUT = os.path.join(HERE, "libigb200_host.so")
-HOST_SOURCES = ["host/script_recognizer.cpp", "host/b200_device.cpp", "host/host_capi.cpp"]
+HOST_SOURCES = ["host/script_recognizer.cpp", "host/image_io.cpp", "host/b200_device.cpp", "host/host_capi.cpp"]
 HOST_DEPS = HOST_SOURCES + ["host/script_recognizer.h", "host/b200_device.h", "host/ig_mirror.h", "../../include/igb200.h"]
 
 

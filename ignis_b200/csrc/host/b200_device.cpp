@@ -119,6 +119,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     igb200_technique technique{};
     std::vector<float> selector_data;
     TextureTable textures;   // filled by the materials in order of first use (script_recognizer.h)
+    textures.resource_map = mScene.resource_map;
     try {
         if (set.HitShaders.size() != mScene.entity_per_material->size()) throw RecognizeError{"one hit shader per material expected"};
         const StageDescriptor* light_stage = nullptr; const IG::ParameterSet* light_local = nullptr;
@@ -151,6 +152,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     append(bytes, &technique, sizeof(technique));
     append(bytes, selector_data.data(), selector_data.size() * sizeof(float));
     append(bytes, textures.records.data(), textures.records.size() * sizeof(igb200_texture));
+    for (const DeviceImage& im : textures.images) append(bytes, im.bytes.data(), im.bytes.size());
     if (!mSceneDirty && bytes == mDescriptorBytes) return true;
 
     const IG::SceneDatabase& db = *mScene.database;
@@ -178,7 +180,10 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     d.finite_lights = fin.data(); d.n_finite = (int32_t)fin.size();
     d.camera = camera; d.technique = technique;
     d.selector_data = selector_data.empty() ? nullptr : selector_data.data(); d.n_selector_data = (int32_t)selector_data.size();
-    d.textures = textures.records.empty() ? nullptr : textures.records.data(); d.n_textures = (int32_t)textures.records.size();   // procedural textures only: no images on this path
+    d.textures = textures.records.empty() ? nullptr : textures.records.data(); d.n_textures = (int32_t)textures.records.size();
+    std::vector<igb200_image> images;   // 8-bit files decoded by image_io as the reference's device keeps them
+    for (const DeviceImage& im : textures.images) { igb200_image ii; ii.format = im.format; ii.width = im.width; ii.height = im.height; ii.reserved = 0; ii.pixels = im.bytes.data(); images.push_back(ii); }
+    d.images = images.empty() ? nullptr : images.data(); d.n_images = (int32_t)images.size();
     for (int k = 0; k < 3; ++k) { d.bbox_min[k] = db.SceneBBox.min(k); d.bbox_max[k] = db.SceneBBox.max(k); }
     if (!forAll([&](igb200_ctx* c, int) { return igb200_set_scene(c, &d); }, "scene upload")) return false;   // the scene is replicated
     mDescriptorBytes.swap(bytes);

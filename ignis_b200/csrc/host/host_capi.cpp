@@ -67,8 +67,21 @@ int igbh_describe_material(void* stage, ParameterSet* local, ParameterSet* globa
     catch (const igbh::RecognizeError& e) { igbh::set_last_error(e.what); return -1; }
 }
 // ... with a texture table that persists over the hit stages of a scene (created / destroyed by the caller)
-igbh::TextureTable* igbh_textures_create() { return new igbh::TextureTable(); }
-void igbh_textures_destroy(igbh::TextureTable* t) { delete t; }
+struct TexHandle : igbh::TextureTable { std::vector<std::string> res; };
+igbh::TextureTable* igbh_textures_create() { return new TexHandle(); }
+void igbh_textures_destroy(igbh::TextureTable* t) { delete static_cast<TexHandle*>(t); }
+void igbh_textures_set_resources(igbh::TextureTable* t, const char* const* paths, int n) {   // SceneSettings::resource_map for the recogniser tests
+    TexHandle* h = static_cast<TexHandle*>(t);
+    h->res.assign(paths, paths + n);
+    h->resource_map = &h->res;
+}
+int igbh_textures_image_count(const igbh::TextureTable* t) { return (int)t->images.size(); }
+const uint8_t* igbh_textures_image(const igbh::TextureTable* t, int i, int* format, int* width, int* height, size_t* bytes) {
+    const igbh::DeviceImage& im = t->images[(size_t)i];
+    *format = im.format; *width = im.width; *height = im.height; *bytes = im.bytes.size();
+    return im.bytes.data();
+}
+const uint8_t* igbh_srgb_lut() { return igbh::srgb_byte_to_linear_byte(); }
 int igbh_textures_count(const igbh::TextureTable* t) { return (int)t->records.size(); }
 void igbh_textures_get(const igbh::TextureTable* t, int i, igb200_texture* out) { *out = t->records[(size_t)i]; }
 int igbh_describe_material_tex(void* stage, ParameterSet* local, ParameterSet* global, igbh::TextureTable* textures, igb200_material* out) {
@@ -120,13 +133,15 @@ IRenderDevice* igbh_device_create(int cuda_device) {
     return d;
 }
 void igbh_device_destroy(IRenderDevice* d) { delete d; }
-struct AssignKeep { std::vector<int32> epm; };
-void* igbh_device_assign(IRenderDevice* d, SceneDatabase* db, const int32_t* entity_per_material, size_t n) {
-    AssignKeep* k = new AssignKeep{std::vector<int32>(entity_per_material, entity_per_material + n)};   // borrowed by the device (Runtime.cpp:532-541)
-    IRenderDevice::SceneSettings s; s.database = db; s.entity_per_material = &k->epm;
+struct AssignKeep { std::vector<int32> epm; std::vector<std::string> resources; };
+void* igbh_device_assign_res(IRenderDevice* d, SceneDatabase* db, const int32_t* entity_per_material, size_t n, const char* const* resources, int n_resources) {
+    AssignKeep* k = new AssignKeep{std::vector<int32>(entity_per_material, entity_per_material + n), {}};   // borrowed by the device (Runtime.cpp:532-541)
+    if (resources) k->resources.assign(resources, resources + n_resources);
+    IRenderDevice::SceneSettings s; s.database = db; s.entity_per_material = &k->epm; s.resource_map = &k->resources;
     d->assignScene(s);
     return k;
 }
+void* igbh_device_assign(IRenderDevice* d, SceneDatabase* db, const int32_t* entity_per_material, size_t n) { return igbh_device_assign_res(d, db, entity_per_material, n, nullptr, 0); }
 void igbh_assign_release(void* keep) { delete static_cast<AssignKeep*>(keep); }
 int igbh_device_render(IRenderDevice* d, ShaderSet* s, ParameterSet* global, int spi, int width, int height, int iteration, int frame, int seed, const float* rays, size_t n_rays) {
     IRenderDevice::RenderSettings rs;

@@ -1,0 +1,31 @@
+// image_io.h -- 8-bit image files as the reference's device keeps them after loading (the part of IG::Image this layer needs).
+//
+// The generated stage text does not hold pixels, it names FILES: `device.load_packed_image_by_id(<resource id>, <channels>, <linear>)`
+// (src/runtime/pattern/ImagePattern.cpp:57-66; the id indexes IRenderDevice::SceneSettings::resource_map). The reference's device decodes the
+// file with stb_image through IG::Image::loadAsPacked (src/runtime/Image.cpp:714-810; src/device/Device.cpp:735-799): rows flipped bottom-up,
+// grey files kept as one byte per pixel, everything else as RGBA bytes, and -- unless the texture says `linear` -- every colour byte mapped from
+// sRGB to linear with byte_color_to_linear (Image.cpp:40-51). A plugin built inside the reference tree would call IG::Image itself; this
+// repository's build has no ig_runtime to link, so the one 8-bit format the reference's scenes use -- PNG -- is decoded here (own inflate,
+// filters 0-4, grey / grey+alpha / RGB / RGBA / palette, 8 bits, non-interlaced). Float images (EXR / HDR: `device.load_image_by_id`) are not
+// decoded here and are reported by the recogniser.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace igbh {
+
+struct DeviceImage {
+    int format = 0;            // IGB200_IMAGE_RGBA8 | IGB200_IMAGE_MONO8
+    int width = 0, height = 0;
+    std::vector<uint8_t> bytes;   // rows bottom-up
+};
+
+// Throws RecognizeError (script_recognizer.h) with the reason when the file cannot be read or is not a PNG this reader knows.
+DeviceImage load_packed_image(const std::string& path, bool already_linear);
+
+// byte_color_to_linear (Image.cpp:40-51) for all 256 values
+const uint8_t* srgb_byte_to_linear_byte();
+
+}  // namespace igbh

@@ -525,9 +525,32 @@ int TextureTable::add(const igb200_texture& t) {
     return (int)records.size() - 1;
 }
 
-// A texture value: `make_checkerboard_texture(make_vec2(sx, sy), color0, color1, transform)` (pattern/CheckerBoardPattern.cpp:13-33). Image
-// textures name a FILE (`device.load_image(...)`): decoding it is the runtime's business (IG::Image, stb / tinyexr), which this layer does not
-// link -- they are reported, not guessed.
+int TextureTable::image(const std::string& path, bool linear) {
+    for (size_t i = 0; i < image_keys.size(); ++i) if (image_keys[i].first == path && image_keys[i].second == linear) return (int)i;
+    images.push_back(load_packed_image(path, linear));
+    image_keys.emplace_back(path, linear);
+    return (int)images.size() - 1;
+}
+
+// LoaderUtils::inlineTransformAs2d: mat3x3_identity() | make_mat3x3(col0, col1, col2) -> rows 0 and 1
+static void texture_transform(const Val& tr, float* out6, const std::string& what) {
+    if (tr.kind != Val::Ctor) fail(what + ": texture transform is not a matrix");
+    if (tr.name == "mat3x3_identity") { out6[0] = 1; out6[4] = 1; }
+    else if (tr.name == "make_mat3x3") {
+        for (int c = 0; c < 3; ++c) { const Val col = as_vec(ctor_arg(tr, c), what + ": texture transform column"); out6[c] = col.f[0]; out6[3 + c] = col.f[1]; }
+    } else fail(what + ": texture transform '" + tr.name + "' is not understood");
+}
+static int border_of(const Val& b, const std::string& what) {   // pattern/ImagePattern.cpp:33-51, texture/image.art:9-44
+    if (b.kind == Val::Ctor && b.name == "make_repeat_border") return IGB200_BORDER_REPEAT;
+    if (b.kind == Val::Ctor && b.name == "make_clamp_border") return IGB200_BORDER_CLAMP;
+    if (b.kind == Val::Ctor && b.name == "make_mirror_border") return IGB200_BORDER_MIRROR;
+    fail(what + ": image border '" + (b.kind == Val::Ctor ? b.name : std::string("?")) + "' is not understood");
+}
+
+// A texture value: `make_checkerboard_texture(make_vec2(sx, sy), color0, color1, transform)` (pattern/CheckerBoardPattern.cpp:13-33) or
+// `make_image_texture(border, filter, device.load_packed_image_by_id(id, channels, linear), transform)` (pattern/ImagePattern.cpp:15-73): an
+// 8-bit file named through the resource map, decoded by image_io. Float images (`device.load_image_by_id`: EXR / HDR) are the runtime's
+// business (IG::Image, tinyexr), which this layer does not link -- they are reported, not guessed.
 static int texture_of(const Val& t, TextureTable* textures, const std::string& what) {
     if (t.kind != Val::Ctor) fail(what + " is neither a constant nor a texture");
     if (!textures) fail(what + " is textured but no texture table was given");
@@ -539,14 +562,28 @@ static int texture_of(const Val& t, TextureTable* textures, const std::string& w
         rec.p[0] = sc.f[0]; rec.p[1] = sc.f[1];
         put3(rec.p + 2, as_vec(ctor_arg(t, 1), what + ": checkerboard color0"));
         put3(rec.p + 5, as_vec(ctor_arg(t, 2), what + ": checkerboard color1"));
-        const Val& tr = ctor_arg(t, 3);   // LoaderUtils::inlineTransformAs2d: mat3x3_identity() | make_mat3x3(col0, col1, col2)
-        if (tr.kind != Val::Ctor) fail(what + ": texture transform is not a matrix");
-        if (tr.name == "mat3x3_identity") { rec.transform[0] = 1; rec.transform[4] = 1; }
-        else if (tr.name == "make_mat3x3") {
-            for (int c = 0; c < 3; ++c) { const Val col = as_vec(ctor_arg(tr, c), what + ": texture transform column"); rec.transform[c] = col.f[0]; rec.transform[3 + c] = col.f[1]; }
-        } else fail(what + ": texture transform '" + tr.name + "' is not understood");
-    } else if (t.name == "make_image_texture" || t.name == "make_bitmap_texture") {
-        fail(what + ": image textures are not available through the script path (the file is decoded by the runtime's image loader, which this layer does not link); use the C ABI's igb200_scene_desc::images");
+        texture_transform(ctor_arg(t, 3), rec.transform, what);
+    } else if (t.name == "make_image_texture") {
+        rec.type = IGB200_TEX_IMAGE;
+        const Val& border = ctor_arg(t, 0);
+        if (border.kind == Val::Ctor && border.name == "make_split_border") { rec.border_u = border_of(ctor_arg(border, 0), what); rec.border_v = border_of(ctor_arg(border, 1), what); }
+        else rec.border_u = rec.border_v = border_of(border, what);
+        const Val& filter = ctor_arg(t, 1);
+        if (filter.kind != Val::Ctor) fail(what + ": image filter is not a constructor");
+        if (filter.name == "make_nearest_filter") rec.filter = IGB200_FILTER_NEAREST;
+        else if (filter.name == "make_bilinear_filter") rec.filter = IGB200_FILTER_BILINEAR;
+        else if (filter.name == "make_bicubic_filter") rec.filter = IGB200_FILTER_BICUBIC;
+        else fail(what + ": image filter '" + filter.name + "' is not understood");
+        const Val& img = ctor_arg(t, 2);
+        if (img.kind != Val::Ctor) fail(what + ": image is not a load call");
+        if (img.name == "device.load_image_by_id" || img.name == "device.load_image")
+            fail(what + ": float image textures (EXR / HDR through device.load_image) need the runtime's image loader (IG::Image, tinyexr), which this layer does not link; the C ABI takes decoded pixels in igb200_scene_desc::images");
+        if (img.name != "device.load_packed_image_by_id") fail(what + ": image source '" + img.name + "' is not understood");
+        const int id = (int)as_num(ctor_arg(img, 0), what + ": resource id");
+        const bool linear = as_num(ctor_arg(img, 2), what + ": linear flag") != 0;
+        if (!textures->resource_map || id < 0 || (size_t)id >= textures->resource_map->size()) fail(what + ": resource id " + std::to_string(id) + " is not in the scene's resource map");
+        rec.image = textures->image((*textures->resource_map)[(size_t)id], linear);
+        texture_transform(ctor_arg(t, 3), rec.transform, what);
     } else fail(what + ": texture constructor '" + t.name + "' is not supported by this device");
     return textures->add(rec);
 }

@@ -19,6 +19,7 @@
 
 #include "../../../include/igb200.h"
 #include "ig_mirror.h"
+#include "image_io.h"
 
 namespace igbh {
 
@@ -58,6 +59,12 @@ struct Registries { const IG::ParameterSet* local; const IG::ParameterSet* globa
 struct TextureTable {
     std::vector<igb200_texture> records;
     int add(const igb200_texture& t);
+    // image textures: the files named by the stage text through resource ids (IRenderDevice::SceneSettings::resource_map), decoded as the
+    // reference's device keeps them (image_io.h); one entry per (file, linear flag), numbered by first use
+    const std::vector<std::string>* resource_map = nullptr;
+    std::vector<DeviceImage> images;
+    std::vector<std::pair<std::string, bool>> image_keys;
+    int image(const std::string& path, bool linear);   // throws RecognizeError
 };
 // textures: null = the stage must not use any (an error otherwise)
 igb200_material resolve_material(const StageDescriptor& hit, const Registries& r, TextureTable* textures = nullptr);     // throws RecognizeError

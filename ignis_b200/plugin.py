@@ -24,7 +24,8 @@ SYMBOLS = ["ig_get_interface", "igbh_last_error", "igbh_interface_version", "igb
            "igbh_describe_camera", "igbh_set_create", "igbh_set_destroy", "igbh_set_raygen", "igbh_set_miss", "igbh_set_add_hit", "igbh_device_create",
            "igbh_device_destroy", "igbh_device_assign", "igbh_assign_release", "igbh_device_render", "igbh_device_resize", "igbh_device_framebuffer",
            "igbh_device_clear", "igbh_device_stats", "igbh_device_gpu_count", "igbh_textures_create", "igbh_textures_destroy", "igbh_textures_count",
-           "igbh_textures_get", "igbh_describe_material_tex", "igbh_describe_lights_db"]
+           "igbh_textures_get", "igbh_describe_material_tex", "igbh_describe_lights_db", "igbh_textures_set_resources", "igbh_textures_image_count",
+           "igbh_textures_image", "igbh_srgb_lut", "igbh_device_assign_res"]
 
 
 def lib():
@@ -79,6 +80,13 @@ def lib():
         L.igbh_textures_count.argtypes = [vp]
         L.igbh_textures_get.argtypes = [vp, C.c_int, vp]
         L.igbh_describe_material_tex.argtypes = [vp, vp, vp, vp, vp]
+        L.igbh_textures_set_resources.argtypes = [vp, C.POINTER(C.c_char_p), C.c_int]
+        L.igbh_textures_image_count.argtypes = [vp]
+        L.igbh_textures_image.restype = C.POINTER(C.c_uint8)
+        L.igbh_textures_image.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+        L.igbh_srgb_lut.restype = C.POINTER(C.c_uint8)
+        L.igbh_device_assign_res.restype = vp
+        L.igbh_device_assign_res.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_char_p), C.c_int]
         L.igbh_describe_lights_db.argtypes = [vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp, C.POINTER(C.c_int), C.c_int]
         _LIB = L
     return _LIB
@@ -128,8 +136,21 @@ class FixTableDB:
 class TextureTable:
     """The texture table the recogniser builds while the hit stages of a scene are resolved in material order."""
 
-    def __init__(self):
+    def __init__(self, resource_map=()):
         self.h = lib().igbh_textures_create()
+        if resource_map:   # the files behind the resource ids of the stage text (IRenderDevice::SceneSettings::resource_map)
+            arr = (C.c_char_p * len(resource_map))(*[p.encode() for p in resource_map])
+            lib().igbh_textures_set_resources(self.h, arr, len(resource_map))
+
+    def images(self):
+        """The decoded images, as (format, array) pairs shaped like SceneTables.images."""
+        out = []
+        for i in range(lib().igbh_textures_image_count(self.h)):
+            fmt, w, h, n = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+            p = lib().igbh_textures_image(self.h, i, C.byref(fmt), C.byref(w), C.byref(h), C.byref(n))
+            a = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+            out.append((fmt.value, a.reshape(h.value, w.value) if n.value == w.value * h.value else a.reshape(h.value, w.value, 4)))
+        return out
 
     def records(self) -> np.ndarray:
         from .scene import TEXTURE_DTYPE
@@ -232,7 +253,9 @@ class PluginRuntime:
         if not self.dev:
             raise DeviceError(f"createRenderDevice failed: {_err()}")
         epm = np.ascontiguousarray(tables.entity_per_material, np.int32)
-        self.keep = L.igbh_device_assign(self.dev, self.db, epm.ctypes.data, epm.shape[0])
+        res = self.stages.resource_map
+        arr = (C.c_char_p * max(len(res), 1))(*[p.encode() for p in res]) if res else None
+        self.keep = L.igbh_device_assign_res(self.dev, self.db, epm.ctypes.data, epm.shape[0], arr, len(res))
         L.igbh_device_resize(self.dev, self.width, self.height)
         self.IterationCount = 0
 

@@ -12,9 +12,10 @@ after the generators:
   ig_hit_shader / ig_miss_shader        src/runtime/shader/HitShader.cpp:16-53, MissShader.cpp:15-47
   BSDFs                                 src/runtime/bsdf/DiffuseBSDF.cpp:13-27, DielectricBSDF.cpp:13-41, ConductorBSDF.cpp:13-35, BSDF.cpp:53-98
                                         (setupRoughness), MapBSDF.cpp:17-55 (bumpmap / normalmap)
-  textures                              src/runtime/pattern/CheckerBoardPattern.cpp:13-33, loader/ShadingTree.cpp:375-405,795-840 and
+  textures                              src/runtime/pattern/CheckerBoardPattern.cpp:13-33, ImagePattern.cpp:15-73 (8-bit files: resource id in the
+                                        LocalRegistry + device.load_packed_image_by_id), loader/ShadingTree.cpp:375-405,795-840 and
                                         Transpiler.cpp:991,1301 (a texture name inside a colour -> `vec4_to_color(color_to_vec4(tex_<id>(ctx)))`);
-                                        image textures name a file the runtime's image loader decodes: not reconstructed
+                                        float images (EXR / HDR) are decoded by the runtime's image loader: not reconstructed
   lights + tables                       src/runtime/light/{AreaLight.cpp:115-220, PointLight.cpp:44-62, EnvironmentLight.cpp:103-110},
                                         src/runtime/loader/LoaderLight.cpp:106-247,423-453; embedded simple point lights
                                         (>= 10 simple lights, LoaderLight.h:27): LoaderLight.cpp:171-236,397-422, PointLight.cpp:64-78
@@ -32,7 +33,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from .scene import (BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_DIFFUSE, LIGHT_ENV_CONST, LIGHT_PLANE_AREA, LIGHT_POINT, LIGHT_SHAPE_AREA, LIGHT_SPHERE_AREA, LIGHT_SPOT,
-                    MAP_BUMP, MAP_NONE, MICROFACET_VNDF_GGX, SHAPE_SPHERE, TEX_CHECKERBOARD, SceneTables)
+                    IMAGE_RGBA32F, MAP_BUMP, MAP_NONE, MICROFACET_VNDF_GGX, SHAPE_SPHERE, TEX_CHECKERBOARD, SceneTables)
 
 STD_LIB_STUB = "// <the Artic standard library (ig_api[], ScriptCompiler.cpp:36-51) precedes every stage>\nfn @make_dummy() = 0;\n\n"
 
@@ -60,6 +61,7 @@ class StageSet:
     hits: list
     global_registry: Registry
     fix_tables: dict = field(default_factory=dict)   # what LoaderLight::embedLights adds to the scene database: class name -> (n, words) float32
+    resource_map: list = field(default_factory=list)  # IRenderDevice::SceneSettings::resource_map: file of resource id k
 
 
 def _ts(x: float) -> str:
@@ -75,6 +77,12 @@ class _Tree:
 
     def __init__(self, local: Registry, specialization: str):
         self.local, self.mode, self.ids, self.header, self.textures = local, specialization, {}, [], set()
+        self.resources: list = []   # LoaderContext::registerExternalResource: shared by all stages of a scene (set by generate())
+
+    def resource(self, path: str) -> int:
+        if path not in self.resources:
+            self.resources.append(path)
+        return self.resources.index(path)
 
     def closure(self, name: str) -> str:
         return str(self.ids.setdefault(name, len(self.ids)))
@@ -124,17 +132,30 @@ class _Tree:
         if tex not in self.textures:
             self.textures.add(tex)
             rec = t.textures[tex]
-            if int(rec["type"]) != TEX_CHECKERBOARD:
-                raise ValueError("image textures are outside the script path: the runtime's image loader decodes the file (refscript.py header)")
-            p = rec["p"]
-            c0, c1 = self.color(cid, "color0", p[2:5]), self.color(cid, "color1", p[5:8])
-            sx, sy = self.number(cid, "scale_x", p[0]), self.number(cid, "scale_y", p[1])
             a, b, c, d, e, f = (float(x) for x in rec["transform"])
             if (a, b, c, d, e, f) == (1, 0, 0, 0, 1, 0):
                 tr = "mat3x3_identity()"
             else:   # LoaderUtils::inlineMatrix: columns, streamed with the default precision
                 tr = "make_mat3x3(" + ", ".join("make_vec3(%s, %s, %s)" % tuple(_stream(x) for x in col) for col in ((a, d, 0), (b, e, 0), (c, f, 1))) + ")"
-            self.header.append(f"  let tex_{cid} : Texture = make_checkerboard_texture(make_vec2({sx}, {sy}), {c0}, {c1}, {tr});\n")
+            if int(rec["type"]) == TEX_CHECKERBOARD:
+                p = rec["p"]
+                c0, c1 = self.color(cid, "color0", p[2:5]), self.color(cid, "color1", p[5:8])
+                sx, sy = self.number(cid, "scale_x", p[0]), self.number(cid, "scale_y", p[1])
+                self.header.append(f"  let tex_{cid} : Texture = make_checkerboard_texture(make_vec2({sx}, {sy}), {c0}, {c1}, {tr});\n")
+            else:   # ImagePattern.cpp:15-73: the file travels as a resource id in the stage's LocalRegistry, the device loads it
+                fmt, arr = t.images[int(rec["image"])]
+                ref = t.image_files[int(rec["image"])]
+                if fmt == IMAGE_RGBA32F or ref is None or not ref[0].lower().endswith(".png"):
+                    raise ValueError("float images (EXR / HDR fixtures) are outside the script path: the runtime's image loader decodes them (refscript.py header)")
+                self.local.ints[f"img_{cid}"] = self.resource(ref[0])
+                wraps = ["make_repeat_border()", "make_clamp_border()", "make_mirror_border()"]
+                wu, wv = wraps[int(rec["border_u"])], wraps[int(rec["border_v"])]
+                wrap = wu if wu == wv else f"make_split_border({wu}, {wv})"
+                filt = ["make_nearest_filter()", "make_bilinear_filter()", "make_bicubic_filter()"][int(rec["filter"])]
+                channels = 1 if arr.ndim == 2 else 4   # Image::loadResolution(filename).Channels == 1 ? 1 : 4
+                self.header.append(f'  let img_{cid}_res_id = registry::get_local_parameter_i32("img_{cid}", 0);\n'
+                                   f"  let img_{cid} = device.load_packed_image_by_id(img_{cid}_res_id, {channels}, {'true' if ref[1] else 'false'});\n"
+                                   f"  let tex_{cid} : Texture = make_image_texture({wrap}, {filt}, img_{cid}, {tr});\n")
         return f"vec4_to_color(color_to_vec4(tex_{cid}(ctx)))"
 
     def pull_header(self) -> str:
@@ -407,8 +428,10 @@ def generate(t: SceneTables, specialization: str = "default", std_aovs: bool = T
     raygen = Stage("ig_ray_generation_shader", s, local)
 
     # ---- miss
+    resources: list = []
     local = Registry()
     tree = _Tree(local, specialization)
+    tree.resources = resources
     s = STD_LIB_STUB + "#[export] fn ig_miss_shader(settings: &Settings, first: i32, last: i32) -> () {\n" + prologue
     s += _lights(t, tree) + "\n" + _technique(t, std_aovs, cache_dir) + "\n"
     s += "  let use_framebuffer = true;\n  device.handle_miss_shader(full_technique, payload_info, first, last, use_framebuffer);\n}\n"
@@ -419,6 +442,7 @@ def generate(t: SceneTables, specialization: str = "default", std_aovs: bool = T
     for mat_id in range(int(t.materials.shape[0])):
         local = Registry()
         tree = _Tree(local, specialization)
+        tree.resources = resources
         s = STD_LIB_STUB + "#[export] fn ig_hit_shader(settings: &Settings, mat_id: i32, first: i32, last: i32) -> () {\n" + prologue
         s += _database(has_sphere) + _lights(t, tree) + "\n" + _bsdf(t, mat_id, tree) + _technique(t, std_aovs, cache_dir) + "\n"
         s += "  let use_framebuffer = true;\n  device.handle_hit_shader(shader, scene, full_technique, payload_info, first, last, use_framebuffer);\n}\n"
@@ -430,4 +454,4 @@ def generate(t: SceneTables, specialization: str = "default", std_aovs: bool = T
         for k, l in enumerate(pts):
             tab[k, 0:3], tab[k, 4:7] = l["p"][0:3], l["p"][3:6]
         fix["SimplePointLight"] = tab
-    return StageSet(raygen, miss, hits, g, fix)
+    return StageSet(raygen, miss, hits, g, fix, resources)

@@ -106,6 +106,7 @@ class SceneTables:
     selector_data: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))   # light_cdf.bin / light_hierarchy.bin as f32 words
     textures: np.ndarray = field(default_factory=lambda: np.zeros(0, TEXTURE_DTYPE))
     images: list = field(default_factory=list)       # (format, array): RGBA8 -> (H, W, 4) u8, MONO8 -> (H, W) u8, RGBA32F -> (H, W, 4) f32; rows bottom-up
+    image_files: list = field(default_factory=list)  # per image: (file name, linear flag) -- None for images that are no file (the baked sky)
     aux_data: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))        # 2-D cdfs of textured environment lights
     texture_names: list = field(default_factory=list)
     embedded_lights: bool = False                    # the finite lights come from embedded fix-tables (LoaderLight.h:27)
@@ -777,6 +778,7 @@ def load_scene(path, width: int | None = None, height: int | None = None,
     tex_json = {t["name"]: t for t in doc.get("textures", [])}
     tex_ids: dict[str, int] = {}
     tex_recs, images, image_ids, aux_words = [], [], {}, []
+    image_files: list = []
 
     def texture_id(name: str) -> int:
         if name in tex_ids:
@@ -791,6 +793,7 @@ def load_scene(path, width: int | None = None, height: int | None = None,
             if key not in image_ids:
                 image_ids[key] = len(images)
                 images.append(load_image_for_device(fname, key[1]))
+                image_files.append((os.path.abspath(fname), key[1]))
             rec["type"], rec["image"] = TEX_IMAGE, image_ids[key]
             rec["filter"] = FILTERS.get(str(tj.get("filter_type", "bicubic")), FILTER_BICUBIC)
             if "wrap_mode_u" in tj:
@@ -956,6 +959,7 @@ def load_scene(path, width: int | None = None, height: int | None = None,
                 raise SceneError("transformed sky lights are outside the supported path")
             sky = sky_image(lj)
             images.append((IMAGE_RGBA32F, sky))
+            image_files.append(None)
             trec = np.zeros((), TEXTURE_DTYPE)
             trec["type"], trec["image"], trec["filter"] = TEX_IMAGE, len(images) - 1, 1
             trec["transform"] = (1, 0, 0, 0, 1, 0)
@@ -1254,4 +1258,5 @@ def load_scene(path, width: int | None = None, height: int | None = None,
         infinite_lights=_arr(inf_l), finite_lights=_arr(fin_l), camera=cam, technique=technique,
         bbox_min=bb_lo.astype(F), bbox_max=bb_hi.astype(F), film_size=(fw, fh),
         embedded_lights=embedded, selector_data=selector_data, textures=(np.asarray(tex_recs, TEXTURE_DTYPE) if tex_recs else np.zeros(0, TEXTURE_DTYPE)), images=images,
+        image_files=image_files,
         aux_data=(np.concatenate(aux_words).astype(F) if aux_words else np.zeros(0, F)), texture_names=list(tex_ids), entity_names=names, material_names=[f"{b}{'@' + e if e else ''}" for b, e in mat_keys], spot_angles=spot_angles, sun_params=sun_params)

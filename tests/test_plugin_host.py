@@ -15,7 +15,37 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCENES = ["single_triangle.json", "diamond_scene.json", "primitives.json", "evaluation/cbox-d6.json", "evaluation/multilight-uniform.json",
           "evaluation/multilight-simple.json", "evaluation/multilight-hierarchy.json",
           "evaluation/emissive-plane.json", "evaluation/point.json", "evaluation/plane-d1.json", "evaluation/sphere-light-pure.json",
-          "evaluation/two-planes-mirror.json", "evaluation/sun-on-plane.json", "<spot>", "<distant>", "<procedural>", "<points-only>"]
+          "evaluation/two-planes-mirror.json", "evaluation/sun-on-plane.json", "<spot>", "<distant>", "<procedural>", "<points-only>", "<bitmaps>"]
+
+
+def _write_png(path, px):
+    """(H, W, C) u8 -> an 8-bit PNG whose scanlines use filters 0..4 in rotation (so a reader is tested on every one of them)."""
+    import struct, zlib
+    h, w, ch = px.shape
+    ctype = {1: 0, 2: 4, 3: 2, 4: 6}[ch]
+    raw = bytearray()
+    prev = np.zeros(w * ch, np.int32)
+    for y in range(h):
+        cur = px[y].reshape(-1).astype(np.int32)
+        ft = y % 5
+        a = np.concatenate([np.zeros(ch, np.int32), cur[:-ch]])
+        c = np.concatenate([np.zeros(ch, np.int32), prev[:-ch]])
+        if ft == 0: line = cur
+        elif ft == 1: line = cur - a
+        elif ft == 2: line = cur - prev
+        elif ft == 3: line = cur - ((a + prev) >> 1)
+        else:
+            pa, pb, pc = np.abs(prev - c), np.abs(a - c), np.abs(a + prev - 2 * c)
+            line = cur - np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, c))
+        raw += bytes([ft]) + (line & 255).astype(np.uint8).tobytes()
+        prev = cur
+
+    def chunk(kind, body):
+        return struct.pack(">I", len(body)) + kind + body + struct.pack(">I", zlib.crc32(kind + body) & 0xFFFFFFFF)
+    comp = zlib.compress(bytes(raw), 9)
+    with open(path, "wb") as fh:
+        fh.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0)) + chunk(b"IDAT", comp[:len(comp) // 2])
+                 + chunk(b"IDAT", comp[len(comp) // 2:]) + chunk(b"IEND", b""))
 
 
 def scene(name):
@@ -58,6 +88,36 @@ def scene(name):
         s["lights"] = [{"type": "env", "name": "env", "radiance": [0.3, 0.35, 0.4]}]
         s["lights"] += [{"type": "point", "name": f"p{k}", "position": [np.cos(k) * 3, np.sin(k) * 3, 2 + 0.1 * k], "intensity": [1 + k, 2, 3]} for k in range(12)]
         return load_scene(s)
+    if name == "<bitmaps>":
+        # 8-bit image files through the script path: the reference's own bump map (a grey PNG) under a rough conductor -- the material of BASELINE
+        # config C5 -- and colour PNGs written here (RGB, RGBA, grey + alpha; every scanline filter) with each filter / border / linear variant
+        import tempfile
+        from conftest import furnace_scene
+        tmp = tempfile.mkdtemp(prefix="igb200_png_")
+        rng = np.random.default_rng(3)
+        files = {}
+        for tag, ch in (("rgb", 3), ("rgba", 4), ("ga", 2)):
+            files[tag] = os.path.join(tmp, tag + ".png")
+            _write_png(files[tag], rng.integers(0, 256, (13, 17, ch), dtype=np.uint8))
+        s = furnace_scene()
+        s["technique"]["max_depth"] = 5
+        s["textures"] = [{"type": "bitmap", "name": "bump", "filename": os.path.join(ROOT, "scenes", "textures/bumpmap.png"), "filter_type": "trilinear"},
+                         {"type": "image", "name": "rgb", "filename": files["rgb"], "filter_type": "nearest", "wrap_mode": "mirror"},
+                         {"type": "image", "name": "rgba", "filename": files["rgba"], "filter_type": "bilinear", "wrap_mode_u": "clamp", "wrap_mode_v": "repeat", "transform": {"scale": [2.5, 1.5, 1]}},
+                         {"type": "image", "name": "ga", "filename": files["ga"], "linear": True},
+                         {"type": "image", "name": "rgb_lin", "filename": files["rgb"], "linear": True, "filter_type": "bilinear"}]
+        s["bsdfs"] = [{"type": "conductor", "name": "rc", "roughness": 0.2, "material": "gold"},
+                      {"type": "bumpmap", "name": "b_rc", "bsdf": "rc", "map": "bump", "strength": 0.5},
+                      {"type": "diffuse", "name": "d_rgb", "reflectance": "rgb"}, {"type": "diffuse", "name": "d_rgba", "reflectance": "rgba"},
+                      {"type": "dielectric", "name": "g", "specular_reflectance": "ga", "specular_transmittance": "rgb_lin"}]
+        s["shapes"] = [{"type": "cube", "name": "Box", "width": 1.0, "height": 1.0, "depth": 1.0, "origin": [-0.5, -0.5, -0.5]},
+                       {"type": "rectangle", "name": "Floor", "width": 12, "height": 12, "origin": [-6, -6, -0.9]}, {"type": "uvsphere", "name": "UV", "radius": 0.45}]
+        s["entities"] = [{"name": "Floor", "shape": "Floor", "bsdf": "b_rc"}]
+        for k, b in enumerate(["d_rgb", "d_rgba", "g"]):
+            s["entities"].append({"name": f"e{k}", "shape": "UV" if k % 2 else "Box", "bsdf": b, "transform": [{"translate": [-1.2 + 1.2 * k, 0.2 * k, 0]}, {"rotate": [10 * k, 20, 5 * k]}]})
+        s["camera"]["transform"] = {"lookat": {"origin": [0.5, -5.5, 2.5], "target": [0, 0, 0], "up": [0, 0, 1]}}
+        s["lights"] = [{"type": "env", "name": "env", "radiance": [0.6, 0.7, 0.8]}, {"type": "point", "name": "p", "position": [1, -2, 3], "intensity": [15, 14, 13]}]
+        return load_scene(s)
     if name == "<points-only>":   # nothing but embedded simple point lights: `let finite_lights = e_simplepointlight;` (LoaderLight.cpp:188-193)
         from conftest import flat_scene
         s = flat_scene()
@@ -83,7 +143,7 @@ def test_recognised_descriptors_equal_loader_descriptors(name, mode, tmp_path):
     g = plugin.Params(st.global_registry)
     exact = mode != "force"   # `force` prints every value with std::to_string's 6 decimals (ShadingTree.cpp:933-981): lossy by design
     hits = [plugin.CompiledStage(s) for s in st.hits]
-    textures = plugin.TextureTable()
+    textures = plugin.TextureTable(st.resource_map)
     db = plugin.FixTableDB(st.fix_tables)
     for i, h in enumerate(hits):
         m = h.material_tex(g, textures)
@@ -112,6 +172,11 @@ def test_recognised_descriptors_equal_loader_descriptors(name, mode, tmp_path):
                 np.testing.assert_array_equal(got_tex[k][f].view(np.uint32), t.textures[k][f].view(np.uint32), err_msg=f"texture {k}: {f}")
             else:
                 np.testing.assert_allclose(got_tex[k][f], t.textures[k][f], atol=1e-6)
+    got_img = textures.images()   # decoded by the host layer's own PNG reader == what the loader's reader produced
+    assert len(got_img) == len(t.images)
+    for (gf, ga), (rf, ra) in zip(got_img, t.images):
+        assert gf == rf and ga.shape == ra.shape
+        np.testing.assert_array_equal(ga, ra)
     for stage in [plugin.CompiledStage(st.miss)] + hits[:1]:
         inf, fin = stage.lights(g, db)
         assert len(inf) == len(t.infinite_lights) and len(fin) == len(t.finite_lights)
@@ -161,7 +226,7 @@ def test_unknown_constructs_fail_loudly():
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,w,h,spi", [("diamond_scene.json", 160, 90, 2), ("primitives.json", 160, 90, 2), ("evaluation/multilight-uniform.json", 96, 96, 2),
                                            ("evaluation/multilight-hierarchy.json", 96, 96, 2), ("evaluation/multilight-simple.json", 96, 96, 2),
-                                           ("<procedural>", 160, 120, 2), ("<points-only>", 96, 96, 2)])
+                                           ("<procedural>", 160, 120, 2), ("<points-only>", 96, 96, 2), ("<bitmaps>", 160, 120, 2)])
 def test_render_through_cpp_plugin_matches_oracle(name, w, h, spi):
     from oracle.oracle import Oracle
     t = scene(name)
@@ -305,8 +370,8 @@ def test_recogniser_reads_the_other_forms_the_generators_emit(tmp_path):
         plugin.CompiledStage(miss).lights(g)
     # image textures name a file: reported
     tex_hit = next(h for h in st.hits if "make_checkerboard_texture" in h.script)
-    bad = re.sub(r"make_checkerboard_texture\([^;]*\);", 'make_image_texture(make_repeat_border(), make_bilinear_filter(), device.load_image("a.png", 4), mat3x3_identity());', tex_hit.script, count=1)
-    with pytest.raises(plugin.DeviceError, match="image textures"):
+    bad = re.sub(r"make_checkerboard_texture\([^;]*\);", 'make_image_texture(make_repeat_border(), make_bilinear_filter(), device.load_image_by_id(0, 4), mat3x3_identity());', tex_hit.script, count=1)
+    with pytest.raises(plugin.DeviceError, match="float image textures"):
         plugin.CompiledStage(refscript.Stage(tex_hit.function, bad, tex_hit.local)).material_tex(g, plugin.TextureTable())
 
 
@@ -353,7 +418,7 @@ def _perturb(script: str, rng) -> str:
     return "\n".join(res)
 
 
-@pytest.mark.parametrize("name", ["diamond_scene.json", "evaluation/multilight-hierarchy.json", "<spot>", "<distant>", "<procedural>", "evaluation/sphere-light-pure.json"])
+@pytest.mark.parametrize("name", ["diamond_scene.json", "evaluation/multilight-hierarchy.json", "<spot>", "<distant>", "<procedural>", "<bitmaps>", "evaluation/sphere-light-pure.json"])
 def test_recogniser_does_not_depend_on_trivia(name, tmp_path):
     """the stage text has only ever come from this repository's reconstruction of the generators, so at least the
     recogniser must not depend on how that text is laid out: whitespace, comments, no-op statements and the order of independent bindings."""
@@ -364,7 +429,7 @@ def test_recogniser_does_not_depend_on_trivia(name, tmp_path):
     rng = np.random.default_rng(11)
 
     def describe(stages):
-        tex = plugin.TextureTable()
+        tex = plugin.TextureTable(stages.resource_map)
         hits = [plugin.CompiledStage(s) for s in stages.hits]
         mats = [h.material_tex(g, tex).tobytes() for h in hits]
         miss = plugin.CompiledStage(stages.miss)
@@ -376,5 +441,28 @@ def test_recogniser_does_not_depend_on_trivia(name, tmp_path):
     for _ in range(4):
         pert = refscript.StageSet(refscript.Stage(st.raygen.function, _perturb(st.raygen.script, rng), st.raygen.local),
                                   refscript.Stage(st.miss.function, _perturb(st.miss.script, rng), st.miss.local),
-                                  [refscript.Stage(h.function, _perturb(h.script, rng), h.local) for h in st.hits], st.global_registry, st.fix_tables)
+                                  [refscript.Stage(h.function, _perturb(h.script, rng), h.local) for h in st.hits], st.global_registry, st.fix_tables, st.resource_map)
         assert describe(pert) == ref
+
+
+def test_host_png_reader_and_srgb_table():
+    """The host layer's image reader against the loader's (ignis_b200/scene.py read_png, itself checked against zlib): byte_color_to_linear for all
+    256 values (Image.cpp:40-51) and files that exercise every scanline filter, stored / fixed / dynamic deflate blocks and split IDAT chunks."""
+    from ignis_b200.scene import srgb_byte_to_linear_byte
+    lut = np.ctypeslib.as_array(plugin.lib().igbh_srgb_lut(), shape=(256,))
+    np.testing.assert_array_equal(lut, srgb_byte_to_linear_byte())
+    t = scene("<bitmaps>")
+    tab = plugin.TextureTable([f[0] for f in t.image_files])
+    st = refscript.generate(t)
+    g = plugin.Params(st.global_registry)
+    for h in st.hits:
+        plugin.CompiledStage(h).material_tex(g, tab)
+    assert [f for f, _ in tab.images()] == [f for f, _ in t.images]
+    # a file that is not a PNG, and one that does not exist: reported
+    bad = os.path.join(os.path.dirname(t.image_files[1][0]), "not_a.png")
+    open(bad, "wb").write(b"JFIF....")
+    for path, msg in ((bad, "not a PNG"), (bad + ".missing", "cannot open")):
+        tab2 = plugin.TextureTable([path] * 8)
+        with pytest.raises(plugin.DeviceError, match=msg):
+            for h in st.hits:
+                plugin.CompiledStage(h).material_tex(g, tab2)

@@ -27,7 +27,7 @@ def syntax_check(source, extra=()):
     return subprocess.run(cmd, capture_output=True, text=True)
 
 
-@pytest.mark.parametrize("source", ["b200_device.cpp", "script_recognizer.cpp", "host_capi.cpp"])
+@pytest.mark.parametrize("source", ["b200_device.cpp", "script_recognizer.cpp", "image_io.cpp", "host_capi.cpp"])
 def test_host_layer_compiles_against_the_reference_headers(source):
     r = syntax_check(os.path.join(HOST, source))
     assert r.returncode == 0, r.stderr[-4000:]
