@@ -1,6 +1,6 @@
 """Debug helper (GPU box): prints the closest-hit records where the CUDA path and the oracle disagree."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from ignis_b200.device import B200Device, RAY_DTYPE

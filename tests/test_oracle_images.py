@@ -2,7 +2,7 @@
 copied to tests/golden/ref_images.npz by tools/make_golden.py) with the RelMSE rule of the reference's
 scripts/RunEvaluations.py:83-92. The reference thresholds (default 1e-3, cbox 5e-3, multilight 3e-4; :95-123) are
 stated for 1024 spp; CI runs fewer samples, so thresholds are scaled by the sample ratio (variance ~ 1/spp).
-tools/eval_oracle.py runs the full 1024 spp version (results recorded in DESIGN.md)."""
+tests/aids/eval_oracle.py runs the full 1024 spp version (results recorded in DESIGN.md)."""
 import os
 import sys
 

@@ -1,7 +1,7 @@
 """GPU box: material binning (a9) on / off on the C5 scene and on the textures-and-maps test scene: per-kernel times (CUDA events)."""
 import os, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "aids")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from ignis_b200.device import Runtime
 from ignis_b200.scene import load_scene
 from debug_maps import build
