@@ -353,6 +353,8 @@ def run_b200(args):
             dev.frameStreamShare(keys[0])
         shared_frames = world > 1 and not args.no_shared_frames
         try:
+            if shared_frames and rank == world - 1 and os.environ.get("IGB200_BENCH_FAIL_SHARED"):   # test hook: exercises the collective fall-back below
+                raise RuntimeError("simulated failure to attach the shared segment")
             dev.frameStreamBegin(32 if world > 1 else 16)
             began = 1.0
         except Exception as e:   # noqa: BLE001 -- e.g. a box that refuses System V segments of this size
