@@ -1880,6 +1880,14 @@ void igo_dielectric_sample(float n1, float n2, const float n[3], const float out
     out[0] = sm.in_dir.x; out[1] = sm.in_dir.y; out[2] = sm.in_dir.z; out[3] = sm.eta; out[4] = sm.color.r; out[5] = ft.factor;
 }
 void igo_cosine_hemisphere(float u, float v, float out[4]) { const DirSample d = sample_cosine_hemisphere(u, v); out[0] = d.dir.x; out[1] = d.dir.y; out[2] = d.dir.z; out[3] = d.pdf; }
+// core/warp.art: 0 = square_to_concentric_disk (:2-22), 1 = dir_from_spherical (:50-57), 2 = spherical_from_dir (:44-48) -- the forward maps the path uses,
+// for the bijection tests of src/tests/artic/test_warp.art (tests/test_oracle_kat.py restates the inverse maps)
+void igo_warp(int fn, const float in[3], float out[3]) {
+    out[0] = out[1] = out[2] = 0;
+    if (fn == 0) square_to_concentric_disk(in[0], in[1], out[0], out[1]);
+    else if (fn == 1) { float st, ct, sp, cp; dm_sincosf(in[0], &st, &ct); dm_sincosf(in[1], &sp, &cp); out[0] = st * cp; out[1] = st * sp; out[2] = ct; }
+    else { const float theta = dm_acosf(in[2]); float phi = dm_atan2f(in[1], in[0]); if (phi < 0) phi = phi + 2 * flt_pi; out[0] = theta; out[1] = phi; }
+}
 void igo_equal_area_sphere(float u, float v, float out[3]) { const Vec3 d = equal_area_square_to_sphere(u, v); out[0] = d.x; out[1] = d.y; out[2] = d.z; }
 // ---- known-answer hooks for the round-2 additions (tests/test_oracle_kat.py)
 // 1-D cdf over `data` = [x1 .. xn] (leading 0 virtual), src/tests/artic/test_cdf.art: out = {discrete off, discrete pdf, continuous off, pos, pdf, pdf_continuous(pos) off, pdf}

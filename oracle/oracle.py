@@ -127,6 +127,7 @@ def lib():
         L.igo_cosine_hemisphere.argtypes = [C.c_float, C.c_float, f3]
         L.igo_dielectric_sample.argtypes = [C.c_float, C.c_float, f3, f3, C.c_int, C.c_uint32, C.c_uint32, f3]
         L.igo_equal_area_sphere.argtypes = [C.c_float, C.c_float, f3]
+        L.igo_warp.argtypes = [C.c_int, f3, f3]
         L.igo_hardware_threads.restype = C.c_int
         L.igo_cdf1d.argtypes = [C.c_void_p, C.c_int, C.c_float, f3]
         L.igo_cdf2d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, f3]

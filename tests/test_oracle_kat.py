@@ -314,3 +314,58 @@ def test_white_furnace_through_glass():
     assert int(o.counters[2]) > 5 * int(o.counters[0]) * 0.05       # the cube is actually hit and paths bounce inside it
     assert img.mean() == pytest.approx(1.0, abs=3e-3)
     assert np.abs(img.reshape(12, 8, 12, 8, 3).mean(axis=(1, 3, 4)) - 1).max() < 0.05   # ... everywhere, not only on average
+
+
+def test_warp_bijections_of_the_reference():
+    """src/tests/artic/test_warp.art:1-60: square -> sphere -> square, square -> disk -> square and (theta, phi) -> direction -> (theta, phi) are the
+    identity at the reference's own test points. The forward maps are the oracle's (what the path uses: environment and sphere-light sampling,
+    cone sampling, the environment map look-up); the inverse maps are restated here from core/warp.art:24-41,93-125. The reference compares with
+    |a - b| <= 1.5 (src/tests/artic/interface.cpp:22-32); the bar here is 1e-5, and a grid of 4000 points goes through the same round trip."""
+    import ctypes as C
+    from oracle import oracle as O
+    L = O.lib()
+    F = np.float32
+
+    def fwd(fn, a, b, c=0.0):
+        i, o = (C.c_float * 3)(a, b, c), (C.c_float * 3)()
+        L.igo_warp(fn, i, o)
+        return np.array(list(o), F)
+
+    def sphere_to_square(d):   # core/warp.art:93-125
+        ad = np.abs(d).astype(F)
+        r = F(np.sqrt(max(F(1) - ad[2], F(0))))
+        a, b_ = max(ad[0], ad[1]), min(ad[0], ad[1])
+        b = F(0) if a == 0 else F(b_ / a)
+        phi_ = F(np.arctan(b) * 2 * F(0.31830988618379067154))
+        phi = F(1) - phi_ if ad[0] < ad[1] else phi_
+        v_ = F(phi * r); u_ = F(r - v_)
+        u, v = (F(1) - v_, F(1) - u_) if d[2] < 0 else (u_, v_)
+        return np.array([0.5 * (np.copysign(u, d[0]) + 1), 0.5 * (np.copysign(v, d[1]) + 1)], F)
+
+    def disk_to_square(p):     # core/warp.art:24-41
+        quadrant = abs(p[0]) > abs(p[1])
+        r_sign = p[0] if quadrant else p[1]
+        r = F(np.copysign(np.hypot(p[0], p[1]), r_sign))
+        sgn = lambda x, s: -x if np.signbit(s) else x   # prodsign
+        phi = F(np.arctan2(sgn(p[1], r_sign), sgn(p[0], r_sign)))
+        c = F(4 * phi / F(np.pi))
+        t = F((c if quadrant else 2 - c) * r)
+        a, b = (r, t) if quadrant else (t, r)
+        return np.array([(a + 1) * 0.5, (b + 1) * 0.5], F)
+
+    pts = [(0.2, 0.8), (0, 0.2), (0.9, 0.4), (1, 0), (0.2, 1)]   # test_warp.art:43-53
+    rng = np.random.default_rng(2)
+    grid = [tuple(x) for x in rng.random((2000, 2))]
+    for u, v in pts + grid:
+        o = (C.c_float * 3)()
+        L.igo_equal_area_sphere(u, v, o)
+        d = np.array(list(o), F)
+        assert abs(float(np.linalg.norm(d)) - 1) < 1e-5
+        np.testing.assert_allclose(sphere_to_square(d), (u, v), atol=2e-5)
+        np.testing.assert_allclose(disk_to_square(fwd(0, u, v)[:2]), (u, v), atol=2e-5)
+    pi = float(np.float32(np.pi))
+    for theta, phi in [(0, pi), (pi / 2, pi), (pi / 2, 0), (0, 0), (0, pi / 4)] + [(float(a), float(b)) for a, b in rng.random((500, 2)) * (pi * 0.98, 2 * pi * 0.98) + (0.03, 0.03)]:   # test_warp.art:55-59
+        t2, p2, _ = fwd(2, *fwd(1, theta, phi))
+        assert abs(t2 - theta) < 2e-4
+        if theta > 1e-3:   # at the pole the azimuth is not defined (the reference's 1.5 tolerance hides that)
+            assert abs(p2 - phi) < 2e-4 or abs(abs(p2 - phi) - 2 * pi) < 2e-4
