@@ -82,6 +82,15 @@ const uint8_t* igbh_textures_image(const igbh::TextureTable* t, int i, int* form
     return im.bytes.data();
 }
 const uint8_t* igbh_srgb_lut() { return igbh::srgb_byte_to_linear_byte(); }
+// test hook: an OpenEXR file as the device keeps it (image_io.h load_float_image); returns the pixel count * 4 or -1; out may be null (size query)
+long igbh_load_float_image(const char* path, int* width, int* height, float* out, long cap) {
+    try {
+        const igbh::FloatImage im = igbh::load_float_image(path);
+        *width = im.width; *height = im.height;
+        if (out && (long)im.rgba.size() <= cap) std::memcpy(out, im.rgba.data(), im.rgba.size() * sizeof(float));
+        return (long)im.rgba.size();
+    } catch (const igbh::RecognizeError& e) { igbh::set_last_error(e.what); return -1; }
+}
 int igbh_textures_count(const igbh::TextureTable* t) { return (int)t->records.size(); }
 void igbh_textures_get(const igbh::TextureTable* t, int i, igb200_texture* out) { *out = t->records[(size_t)i]; }
 int igbh_describe_material_tex(void* stage, ParameterSet* local, ParameterSet* global, igbh::TextureTable* textures, igb200_material* out) {

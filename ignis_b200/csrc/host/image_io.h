@@ -25,6 +25,17 @@ struct DeviceImage {
 // Throws RecognizeError (script_recognizer.h) with the reason when the file cannot be read or is not a PNG this reader knows.
 DeviceImage load_packed_image(const std::string& path, bool already_linear);
 
+// Float images -- OpenEXR files (`device.load_image_by_id`: environment maps, the sky texture SkyLight.cpp writes into the cache). What the
+// reference's device keeps (IG::Image::load, Image.cpp:500-712; Device.cpp:735-799): RGBA float, rows bottom-up, alpha 1 where the file has
+// none, a single grey channel spread over R, G and B. Decoded here: single-part scanline files with HALF / FLOAT / UINT channels, compression
+// NONE, RLE, ZIPS, ZIP and PIZ (own Huffman + wavelet decoder) -- what OpenEXR writers produce by default; tiled, deep, multi-part files and the
+// lossy B44 / DWA / PXR24 compressions are reported.
+struct FloatImage {
+    int width = 0, height = 0;
+    std::vector<float> rgba;   // 4 floats per pixel, rows bottom-up
+};
+FloatImage load_float_image(const std::string& path);   // throws RecognizeError
+
 // byte_color_to_linear (Image.cpp:40-51) for all 256 values
 const uint8_t* srgb_byte_to_linear_byte();
 

@@ -25,7 +25,7 @@ SYMBOLS = ["ig_get_interface", "igbh_last_error", "igbh_interface_version", "igb
            "igbh_device_destroy", "igbh_device_assign", "igbh_assign_release", "igbh_device_render", "igbh_device_resize", "igbh_device_framebuffer",
            "igbh_device_clear", "igbh_device_stats", "igbh_device_gpu_count", "igbh_textures_create", "igbh_textures_destroy", "igbh_textures_count",
            "igbh_textures_get", "igbh_describe_material_tex", "igbh_describe_lights_db", "igbh_textures_set_resources", "igbh_textures_image_count",
-           "igbh_textures_image", "igbh_srgb_lut", "igbh_device_assign_res"]
+           "igbh_textures_image", "igbh_srgb_lut", "igbh_device_assign_res", "igbh_load_float_image"]
 
 
 def lib():
@@ -85,6 +85,8 @@ def lib():
         L.igbh_textures_image.restype = C.POINTER(C.c_uint8)
         L.igbh_textures_image.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
         L.igbh_srgb_lut.restype = C.POINTER(C.c_uint8)
+        L.igbh_load_float_image.restype = C.c_long
+        L.igbh_load_float_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.c_long]
         L.igbh_device_assign_res.restype = vp
         L.igbh_device_assign_res.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_char_p), C.c_int]
         L.igbh_describe_lights_db.argtypes = [vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp, C.POINTER(C.c_int), C.c_int]
@@ -115,6 +117,17 @@ class Params:
         if self.h:
             lib().igbh_params_destroy(self.h)
             self.h = None
+
+
+def load_float_image(path: str) -> np.ndarray:
+    """An OpenEXR file decoded by the host layer (csrc/host/image_io.cpp): (H, W, 4) float32, rows bottom-up, as the reference's device keeps it."""
+    w, h = C.c_int(), C.c_int()
+    n = lib().igbh_load_float_image(path.encode(), C.byref(w), C.byref(h), None, 0)
+    if n < 0:
+        raise DeviceError(_err())
+    out = np.zeros(n, np.float32)
+    lib().igbh_load_float_image(path.encode(), C.byref(w), C.byref(h), out.ctypes.data, n)
+    return out.reshape(h.value, w.value, 4)
 
 
 class FixTableDB:
