@@ -122,11 +122,11 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     textures.resource_map = mScene.resource_map;
     try {
         if (set.HitShaders.size() != mScene.entity_per_material->size()) throw RecognizeError{"one hit shader per material expected"};
+        // the stage that carries the light tables: the miss shader, else the first hit shader that has them
         const StageDescriptor* light_stage = nullptr; const IG::ParameterSet* light_local = nullptr;
         for (const auto& hs : set.HitShaders) {
             const StageDescriptor* d = static_cast<const StageDescriptor*>(hs.Exec);
             if (!d) throw RecognizeError{"null hit shader"};
-            materials.push_back(resolve_material(*d, Registries{hs.LocalRegistry.get(), global}, &textures));
             if (!light_stage && d->has_lights) { light_stage = d; light_local = hs.LocalRegistry.get(); }
         }
         const StageDescriptor* miss = static_cast<const StageDescriptor*>(set.MissShader.Exec);
@@ -137,7 +137,10 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
             if (!forAll([&](igb200_ctx* c, int) { return igb200_set_option(c, "std_aovs", light_stage->std_aovs ? 1 : 0); }, "std_aovs")) throw RecognizeError{mError};
             mStdAovs = (int)light_stage->std_aovs;
         }
-        resolve_lights(*light_stage, Registries{light_local, global}, inf, fin, mScene.database);
+        // lights before materials: the textures of environment lights come first in the table, as the loader numbers them
+        resolve_lights(*light_stage, Registries{light_local, global}, inf, fin, mScene.database, &textures);
+        for (const auto& hs : set.HitShaders)
+            materials.push_back(resolve_material(*static_cast<const StageDescriptor*>(hs.Exec), Registries{hs.LocalRegistry.get(), global}, &textures));
         technique = resolve_technique(*light_stage, Registries{light_local, global}, selector_data);
         const StageDescriptor* rg = static_cast<const StageDescriptor*>(set.RayGenerationShader.Exec);
         if (!rg) throw RecognizeError{"null ray generation shader"};
@@ -152,7 +155,8 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     append(bytes, &technique, sizeof(technique));
     append(bytes, selector_data.data(), selector_data.size() * sizeof(float));
     append(bytes, textures.records.data(), textures.records.size() * sizeof(igb200_texture));
-    for (const DeviceImage& im : textures.images) append(bytes, im.bytes.data(), im.bytes.size());
+    for (const DeviceImage& im : textures.images) append(bytes, im.pixels(), im.pixel_bytes());
+    append(bytes, textures.aux.data(), textures.aux.size() * sizeof(float));
     if (!mSceneDirty && bytes == mDescriptorBytes) return true;
 
     const IG::SceneDatabase& db = *mScene.database;
@@ -182,8 +186,9 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     d.selector_data = selector_data.empty() ? nullptr : selector_data.data(); d.n_selector_data = (int32_t)selector_data.size();
     d.textures = textures.records.empty() ? nullptr : textures.records.data(); d.n_textures = (int32_t)textures.records.size();
     std::vector<igb200_image> images;   // 8-bit files decoded by image_io as the reference's device keeps them
-    for (const DeviceImage& im : textures.images) { igb200_image ii; ii.format = im.format; ii.width = im.width; ii.height = im.height; ii.reserved = 0; ii.pixels = im.bytes.data(); images.push_back(ii); }
+    for (const DeviceImage& im : textures.images) { igb200_image ii; ii.format = im.format; ii.width = im.width; ii.height = im.height; ii.reserved = 0; ii.pixels = im.pixels(); images.push_back(ii); }
     d.images = images.empty() ? nullptr : images.data(); d.n_images = (int32_t)images.size();
+    d.aux_data = textures.aux.empty() ? nullptr : textures.aux.data(); d.n_aux_data = (int32_t)textures.aux.size();   // 2-D cdfs of textured environment lights
     for (int k = 0; k < 3; ++k) { d.bbox_min[k] = db.SceneBBox.min(k); d.bbox_max[k] = db.SceneBBox.max(k); }
     if (!forAll([&](igb200_ctx* c, int) { return igb200_set_scene(c, &d); }, "scene upload")) return false;   // the scene is replicated
     mDescriptorBytes.swap(bytes);

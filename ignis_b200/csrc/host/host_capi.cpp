@@ -78,9 +78,10 @@ void igbh_textures_set_resources(igbh::TextureTable* t, const char* const* paths
 int igbh_textures_image_count(const igbh::TextureTable* t) { return (int)t->images.size(); }
 const uint8_t* igbh_textures_image(const igbh::TextureTable* t, int i, int* format, int* width, int* height, size_t* bytes) {
     const igbh::DeviceImage& im = t->images[(size_t)i];
-    *format = im.format; *width = im.width; *height = im.height; *bytes = im.bytes.size();
-    return im.bytes.data();
+    *format = im.format; *width = im.width; *height = im.height; *bytes = im.pixel_bytes();
+    return static_cast<const uint8_t*>(im.pixels());
 }
+const float* igbh_textures_aux(const igbh::TextureTable* t, size_t* words) { *words = t->aux.size(); return t->aux.data(); }
 const uint8_t* igbh_srgb_lut() { return igbh::srgb_byte_to_linear_byte(); }
 // test hook: an OpenEXR file as the device keeps it (image_io.h load_float_image); returns the pixel count * 4 or -1; out may be null (size query)
 long igbh_load_float_image(const char* path, int* width, int* height, float* out, long cap) {
@@ -101,10 +102,14 @@ int igbh_describe_lights_db(void* stage, ParameterSet* local, ParameterSet* glob
 int igbh_describe_lights(void* stage, ParameterSet* local, ParameterSet* global, igb200_light* inf, int* n_inf, igb200_light* fin, int* n_fin, int cap) {
     return igbh_describe_lights_db(stage, local, global, nullptr, inf, n_inf, fin, n_fin, cap);
 }
+int igbh_describe_lights_tex(void* stage, ParameterSet* local, ParameterSet* global, const SceneDatabase* db, igbh::TextureTable* textures, igb200_light* inf, int* n_inf, igb200_light* fin, int* n_fin, int cap);
 int igbh_describe_lights_db(void* stage, ParameterSet* local, ParameterSet* global, const SceneDatabase* db, igb200_light* inf, int* n_inf, igb200_light* fin, int* n_fin, int cap) {
+    return igbh_describe_lights_tex(stage, local, global, db, nullptr, inf, n_inf, fin, n_fin, cap);
+}
+int igbh_describe_lights_tex(void* stage, ParameterSet* local, ParameterSet* global, const SceneDatabase* db, igbh::TextureTable* textures, igb200_light* inf, int* n_inf, igb200_light* fin, int* n_fin, int cap) {
     try {
         std::vector<igb200_light> a, b;
-        igbh::resolve_lights(*static_cast<igbh::StageDescriptor*>(stage), igbh::Registries{local, global}, a, b, db);
+        igbh::resolve_lights(*static_cast<igbh::StageDescriptor*>(stage), igbh::Registries{local, global}, a, b, db, textures);
         if ((int)a.size() > cap || (int)b.size() > cap) { igbh::set_last_error("too many lights for the output arrays"); return -1; }
         std::memcpy(inf, a.data(), a.size() * sizeof(igb200_light)); std::memcpy(fin, b.data(), b.size() * sizeof(igb200_light));
         *n_inf = (int)a.size(); *n_fin = (int)b.size();

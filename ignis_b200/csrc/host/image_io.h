@@ -17,9 +17,12 @@
 namespace igbh {
 
 struct DeviceImage {
-    int format = 0;            // IGB200_IMAGE_RGBA8 | IGB200_IMAGE_MONO8
+    int format = 0;            // IGB200_IMAGE_RGBA8 | IGB200_IMAGE_MONO8 | IGB200_IMAGE_RGBA32F
     int width = 0, height = 0;
-    std::vector<uint8_t> bytes;   // rows bottom-up
+    std::vector<uint8_t> bytes;   // 8-bit formats, rows bottom-up
+    std::vector<float> floats;    // RGBA32F (load_float_image), rows bottom-up
+    const void* pixels() const { return floats.empty() ? static_cast<const void*>(bytes.data()) : static_cast<const void*>(floats.data()); }
+    size_t pixel_bytes() const { return floats.empty() ? bytes.size() : floats.size() * sizeof(float); }
 };
 
 // Throws RecognizeError (script_recognizer.h) with the reason when the file cannot be read or is not a PNG this reader knows.

@@ -532,6 +532,16 @@ int TextureTable::image(const std::string& path, bool linear) {
     return (int)images.size() - 1;
 }
 
+int TextureTable::float_image(const std::string& path) {
+    for (size_t i = 0; i < image_keys.size(); ++i) if (image_keys[i].first == path && images[i].format == IGB200_IMAGE_RGBA32F) return (int)i;
+    FloatImage f = load_float_image(path);
+    DeviceImage im;
+    im.format = IGB200_IMAGE_RGBA32F; im.width = f.width; im.height = f.height; im.floats.swap(f.rgba);
+    images.push_back(std::move(im));
+    image_keys.emplace_back(path, false);
+    return (int)images.size() - 1;
+}
+
 // LoaderUtils::inlineTransformAs2d: mat3x3_identity() | make_mat3x3(col0, col1, col2) -> rows 0 and 1
 static void texture_transform(const Val& tr, float* out6, const std::string& what) {
     if (tr.kind != Val::Ctor) fail(what + ": texture transform is not a matrix");
@@ -576,13 +586,13 @@ static int texture_of(const Val& t, TextureTable* textures, const std::string& w
         else fail(what + ": image filter '" + filter.name + "' is not understood");
         const Val& img = ctor_arg(t, 2);
         if (img.kind != Val::Ctor) fail(what + ": image is not a load call");
-        if (img.name == "device.load_image_by_id" || img.name == "device.load_image")
-            fail(what + ": float image textures (EXR / HDR through device.load_image) need the runtime's image loader (IG::Image, tinyexr), which this layer does not link; the C ABI takes decoded pixels in igb200_scene_desc::images");
-        if (img.name != "device.load_packed_image_by_id") fail(what + ": image source '" + img.name + "' is not understood");
+        const bool packed = img.name == "device.load_packed_image_by_id";
+        if (!packed && img.name != "device.load_image_by_id") fail(what + ": image source '" + img.name + "' is not understood");
         const int id = (int)as_num(ctor_arg(img, 0), what + ": resource id");
-        const bool linear = as_num(ctor_arg(img, 2), what + ": linear flag") != 0;
         if (!textures->resource_map || id < 0 || (size_t)id >= textures->resource_map->size()) fail(what + ": resource id " + std::to_string(id) + " is not in the scene's resource map");
-        rec.image = textures->image((*textures->resource_map)[(size_t)id], linear);
+        const std::string& file = (*textures->resource_map)[(size_t)id];
+        // 8-bit files (PNG) stay packed bytes; float files (OpenEXR: environment maps, the sky texture) become RGBA floats -- image_io.h
+        rec.image = packed ? textures->image(file, as_num(ctor_arg(img, 2), what + ": linear flag") != 0) : textures->float_image(file);
         texture_transform(ctor_arg(t, 3), rec.transform, what);
     } else fail(what + ": texture constructor '" + t.name + "' is not supported by this device");
     return textures->add(rec);
@@ -664,13 +674,51 @@ igb200_material resolve_material(const StageDescriptor& hit, const Registries& r
     return m;
 }
 
-static igb200_light resolve_light(Eval& ev, const std::string& binding) {
+// transform of an environment light: make_mat3x3(c0, c1, c2) -> 9 floats, column major
+static void env_transform(const Val& m, float* dst) {
+    if (m.kind != Val::Ctor || m.name != "make_mat3x3") fail("environment light transform is not make_mat3x3(...)");
+    for (int c = 0; c < 3; ++c) put3(dst + 3 * c, as_vec(ctor_arg(m, c), "environment transform column"));
+}
+
+static igb200_light resolve_light(Eval& ev, const std::string& binding, TextureTable* textures) {
     const Val l = ev.binding(binding);
     if (l.kind != Val::Ctor) fail(binding + " is not a light constructor");
     igb200_light out;
     std::memset(&out, 0, sizeof(out));
     out.entity_id = -1;
-    if (l.name == "make_environment_light") {       // EnvironmentLight.cpp:103-110; light/env.art:161-164: colour = scale * texture
+    if (l.name == "make_environment_light" && ctor_arg(l, 3).kind == Val::Ctor) {
+        // EnvironmentLight.cpp:94-101: a textured environment without a cdf (`cdf: none`, or a 1 x 1 bake): sampled uniformly, light/env.art:161-167
+        out.type = IGB200_LIGHT_ENV_TEX;
+        put3(out.p, as_vec(ctor_arg(l, 2), "environment scale"));
+        env_transform(ctor_arg(l, 4), out.p + 3);
+        const int32_t tex = texture_of(ctor_arg(l, 3), textures, "environment radiance");
+        std::memcpy(&out.p[12], &tex, 4);
+    } else if (l.name == "make_environment_light_textured") {
+        // EnvironmentLight.cpp:62-93 (cdf = conditional) and SkyLight.cpp:62-72: (id, bbox, scale, tex, cdf::make_cdf_2d_from_buffer(
+        // device.load_buffer_by_id(<resource>), size_x, size_y), transform); the buffer is [marginal | conditional rows] as CDF::computeForImage wrote it
+        out.type = IGB200_LIGHT_ENV_TEXTURED;
+        put3(out.p, as_vec(ctor_arg(l, 2), "environment scale"));
+        env_transform(ctor_arg(l, 5), out.p + 3);
+        const int32_t tex = texture_of(ctor_arg(l, 3), textures, "environment radiance");
+        const Val& cdf = ctor_arg(l, 4);
+        if (cdf.kind != Val::Ctor || cdf.name != "cdf::make_cdf_2d_from_buffer") fail("environment cdf '" + (cdf.kind == Val::Ctor ? cdf.name : std::string("?")) + "' is not supported by this device (cdf::make_cdf_2d_from_buffer: conditional)");
+        const Val& buf = ctor_arg(cdf, 0);
+        if (buf.kind != Val::Ctor || buf.name != "device.load_buffer_by_id") fail("environment cdf buffer is not device.load_buffer_by_id(<resource>)");
+        const int id = (int)as_num(ctor_arg(buf, 0), "cdf resource id");
+        const int32_t sx = (int32_t)as_num(ctor_arg(cdf, 1), "cdf size_x"), sy = (int32_t)as_num(ctor_arg(cdf, 2), "cdf size_y");
+        if (!textures->resource_map || id < 0 || (size_t)id >= textures->resource_map->size()) fail("cdf resource id " + std::to_string(id) + " is not in the scene's resource map");
+        const std::string& file = (*textures->resource_map)[(size_t)id];
+        const size_t words = (size_t)sy + (size_t)sy * (size_t)sx;
+        const int32_t first = (int32_t)textures->aux.size();
+        textures->aux.resize(textures->aux.size() + words);
+        FILE* f = std::fopen(file.c_str(), "rb");
+        if (!f) fail("cannot open the environment cdf '" + file + "'");
+        const size_t got = std::fread(textures->aux.data() + first, 4, words, f);
+        std::fclose(f);
+        if (got != words || sx < 1 || sy < 1) fail("environment cdf '" + file + "' does not hold " + std::to_string(sy) + " + " + std::to_string(sy) + " x " + std::to_string(sx) + " values");
+        const int32_t tail[4] = {tex, first, sx, sy};
+        std::memcpy(&out.p[12], tail, sizeof(tail));
+    } else if (l.name == "make_environment_light") {       // EnvironmentLight.cpp:103-110; light/env.art:161-164: colour = scale * texture
         const Val c = Eval::arith('*', as_vec(ctor_arg(l, 2), "environment scale"), as_vec(ctor_arg(l, 3), "environment radiance"));
         out.type = IGB200_LIGHT_ENV_CONST;
         put3(out.p, c);
@@ -762,12 +810,12 @@ static igb200_light embedded_light(const std::string& name, const IG::SceneDatab
     return out;
 }
 
-void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vector<igb200_light>& infinite, std::vector<igb200_light>& finite, const IG::SceneDatabase* db) {
+void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vector<igb200_light>& infinite, std::vector<igb200_light>& finite, const IG::SceneDatabase* db, TextureTable* textures) {
     if (!stage.has_lights) fail(stage.function + " carries no light tables");
     Eval ev{stage, r};
     infinite.clear(); finite.clear();
-    for (const std::string& b : stage.infinite_lights) infinite.push_back(resolve_light(ev, b));
-    for (const std::string& b : stage.finite_lights) finite.push_back(!b.empty() && b[0] == '@' ? embedded_light(b, db) : resolve_light(ev, b));
+    for (const std::string& b : stage.infinite_lights) infinite.push_back(resolve_light(ev, b, textures));
+    for (const std::string& b : stage.finite_lights) finite.push_back(!b.empty() && b[0] == '@' ? embedded_light(b, db) : resolve_light(ev, b, textures));
 }
 
 igb200_technique resolve_technique(const StageDescriptor& stage, const Registries& r, std::vector<float>& selector_data) {

@@ -64,13 +64,19 @@ struct TextureTable {
     const std::vector<std::string>* resource_map = nullptr;
     std::vector<DeviceImage> images;
     std::vector<std::pair<std::string, bool>> image_keys;
-    int image(const std::string& path, bool linear);   // throws RecognizeError
+    int image(const std::string& path, bool linear);   // 8-bit file (PNG); throws RecognizeError
+    int float_image(const std::string& path);          // OpenEXR file
+    // 32-bit words of further buffers the descriptors point into (igb200_scene_desc::aux_data): the 2-D cdfs of textured environment lights
+    std::vector<float> aux;
 };
 // textures: null = the stage must not use any (an error otherwise)
 igb200_material resolve_material(const StageDescriptor& hit, const Registries& r, TextureTable* textures = nullptr);     // throws RecognizeError
 // db: the scene database, needed when the finite lights come from embedded fix-tables (load_simple_point_lights reads FixTables["SimplePointLight"],
 // LoaderLight.cpp:171-236,397-422; light/point.art:20-36); null = such tables are an error
-void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vector<igb200_light>& infinite, std::vector<igb200_light>& finite, const IG::SceneDatabase* db = nullptr);
+// textures: needed when an environment light is textured (environment maps, the sky): its texture, image and 2-D cdf (the buffer file named through
+// the resource map) are entered there; null = such lights are an error. Resolve the lights BEFORE the materials to number textures as the loader does.
+void resolve_lights(const StageDescriptor& stage, const Registries& r, std::vector<igb200_light>& infinite, std::vector<igb200_light>& finite, const IG::SceneDatabase* db = nullptr,
+                    TextureTable* textures = nullptr);
 // selector_data: contents of the buffer the cdf / hierarchy light selector reads (igb200_scene_desc::selector_data), empty for uniform
 igb200_technique resolve_technique(const StageDescriptor& stage, const Registries& r, std::vector<float>& selector_data);
 igb200_camera resolve_camera(const StageDescriptor& raygen, const Registries& r);

@@ -25,7 +25,7 @@ SYMBOLS = ["ig_get_interface", "igbh_last_error", "igbh_interface_version", "igb
            "igbh_device_destroy", "igbh_device_assign", "igbh_assign_release", "igbh_device_render", "igbh_device_resize", "igbh_device_framebuffer",
            "igbh_device_clear", "igbh_device_stats", "igbh_device_gpu_count", "igbh_textures_create", "igbh_textures_destroy", "igbh_textures_count",
            "igbh_textures_get", "igbh_describe_material_tex", "igbh_describe_lights_db", "igbh_textures_set_resources", "igbh_textures_image_count",
-           "igbh_textures_image", "igbh_srgb_lut", "igbh_device_assign_res", "igbh_load_float_image"]
+           "igbh_textures_image", "igbh_srgb_lut", "igbh_device_assign_res", "igbh_load_float_image", "igbh_textures_aux", "igbh_describe_lights_tex"]
 
 
 def lib():
@@ -85,6 +85,9 @@ def lib():
         L.igbh_textures_image.restype = C.POINTER(C.c_uint8)
         L.igbh_textures_image.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
         L.igbh_srgb_lut.restype = C.POINTER(C.c_uint8)
+        L.igbh_textures_aux.restype = C.POINTER(C.c_float)
+        L.igbh_textures_aux.argtypes = [vp, C.POINTER(C.c_size_t)]
+        L.igbh_describe_lights_tex.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp, C.POINTER(C.c_int), C.c_int]
         L.igbh_load_float_image.restype = C.c_long
         L.igbh_load_float_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.c_long]
         L.igbh_device_assign_res.restype = vp
@@ -162,8 +165,17 @@ class TextureTable:
             fmt, w, h, n = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
             p = lib().igbh_textures_image(self.h, i, C.byref(fmt), C.byref(w), C.byref(h), C.byref(n))
             a = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
-            out.append((fmt.value, a.reshape(h.value, w.value) if n.value == w.value * h.value else a.reshape(h.value, w.value, 4)))
+            if n.value == w.value * h.value * 16:   # RGBA32F
+                out.append((fmt.value, a.view(np.float32).reshape(h.value, w.value, 4)))
+            else:
+                out.append((fmt.value, a.reshape(h.value, w.value) if n.value == w.value * h.value else a.reshape(h.value, w.value, 4)))
         return out
+
+    def aux(self) -> np.ndarray:
+        """The words of igb200_scene_desc::aux_data collected so far (2-D cdfs of textured environment lights)."""
+        n = C.c_size_t()
+        p = lib().igbh_textures_aux(self.h, C.byref(n))
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.float32)
 
     def records(self) -> np.ndarray:
         from .scene import TEXTURE_DTYPE
@@ -201,11 +213,12 @@ class CompiledStage:
             raise DeviceError(_err())
         return out
 
-    def lights(self, global_params: Params, db=None):
-        """db: an igbh_db handle holding the embedded light fix-tables, when the stage's finite lights come from them."""
+    def lights(self, global_params: Params, db=None, textures=None):
+        """db: an igbh_db handle holding the embedded light fix-tables, when the stage's finite lights come from them; textures: the scene's
+        TextureTable, when environment lights are textured (their texture, image and cdf are entered there)."""
         inf, fin = np.zeros(64, LIGHT_DTYPE), np.zeros(64, LIGHT_DTYPE)
         ni, nf = C.c_int(), C.c_int()
-        if lib().igbh_describe_lights_db(self.handle, self.local.h, global_params.h, db.h if db is not None else None, inf.ctypes.data, C.byref(ni), fin.ctypes.data, C.byref(nf), 64):
+        if lib().igbh_describe_lights_tex(self.handle, self.local.h, global_params.h, db.h if db is not None else None, textures.h if textures is not None else None, inf.ctypes.data, C.byref(ni), fin.ctypes.data, C.byref(nf), 64):
             raise DeviceError(_err())
         return inf[:ni.value].copy(), fin[:nf.value].copy()
 

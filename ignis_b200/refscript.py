@@ -15,7 +15,9 @@ after the generators:
   textures                              src/runtime/pattern/CheckerBoardPattern.cpp:13-33, ImagePattern.cpp:15-73 (8-bit files: resource id in the
                                         LocalRegistry + device.load_packed_image_by_id), loader/ShadingTree.cpp:375-405,795-840 and
                                         Transpiler.cpp:991,1301 (a texture name inside a colour -> `vec4_to_color(color_to_vec4(tex_<id>(ctx)))`);
-                                        float images (EXR / HDR) are decoded by the runtime's image loader: not reconstructed
+                                        float images travel as OpenEXR files (device.load_image_by_id)
+  textured environments, sky            src/runtime/light/EnvironmentLight.cpp:40-110, SkyLight.cpp:49-76, LoaderUtils.cpp:108-132 (cdf file),
+                                        CDF.cpp:71-151
   lights + tables                       src/runtime/light/{AreaLight.cpp:115-220, PointLight.cpp:44-62, EnvironmentLight.cpp:103-110},
                                         src/runtime/loader/LoaderLight.cpp:106-247,423-453; embedded simple point lights
                                         (>= 10 simple lights, LoaderLight.h:27): LoaderLight.cpp:171-236,397-422, PointLight.cpp:64-78
@@ -33,7 +35,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from .scene import (BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_DIFFUSE, LIGHT_ENV_CONST, LIGHT_PLANE_AREA, LIGHT_POINT, LIGHT_SHAPE_AREA, LIGHT_SPHERE_AREA, LIGHT_SPOT,
-                    IMAGE_RGBA32F, MAP_BUMP, MAP_NONE, MICROFACET_VNDF_GGX, SHAPE_SPHERE, TEX_CHECKERBOARD, SceneTables)
+                    IMAGE_RGBA32F, LIGHT_ENV_TEX, LIGHT_ENV_TEXTURED, MAP_BUMP, MAP_NONE, MICROFACET_VNDF_GGX, SHAPE_SPHERE, TEX_CHECKERBOARD, SceneTables)
 
 STD_LIB_STUB = "// <the Artic standard library (ig_api[], ScriptCompiler.cpp:36-51) precedes every stage>\nfn @make_dummy() = 0;\n\n"
 
@@ -72,12 +74,36 @@ def _stream(x: float) -> str:
     return f"{float(x):.6g}"   # operator<<(ostream&, float), default precision
 
 
+def write_exr(path: str, rgb: np.ndarray) -> None:
+    """(H, W, 3) float32, rows top-down -> an uncompressed single-part scanline OpenEXR file with FLOAT channels B, G, R: the simplest file the
+    format allows (what the reference's loader would find on disk is whatever wrote the user's environment map; the host layer's reader is
+    checked against every compression separately, tests/test_plugin_host.py::test_host_exr_reader)."""
+    import struct
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    h, w, _ = rgb.shape
+
+    def attr(name, ty, body):
+        return name.encode() + b"\0" + ty.encode() + b"\0" + struct.pack("<i", len(body)) + body
+    chlist = b"".join(c + b"\0" + struct.pack("<iB3xii", 2, 0, 1, 1) for c in (b"B", b"G", b"R")) + b"\0"
+    box = struct.pack("<4i", 0, 0, w - 1, h - 1)
+    head = (struct.pack("<II", 20000630, 2) + attr("channels", "chlist", chlist) + attr("compression", "compression", b"\0") + attr("dataWindow", "box2i", box)
+            + attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", b"\0") + attr("pixelAspectRatio", "float", struct.pack("<f", 1.0))
+            + attr("screenWindowCenter", "v2f", struct.pack("<2f", 0, 0)) + attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + b"\0")
+    line = 8 + 12 * w
+    first = len(head) + 8 * h
+    with open(path, "wb") as fh:
+        fh.write(head + b"".join(struct.pack("<Q", first + y * line) for y in range(h)))
+        for y in range(h):
+            fh.write(struct.pack("<ii", y, 12 * w) + rgb[y, :, 2].tobytes() + rgb[y, :, 1].tobytes() + rgb[y, :, 0].tobytes())
+
+
 class _Tree:
     """ShadingTree: closure ids + the inline-or-registry decision."""
 
     def __init__(self, local: Registry, specialization: str):
         self.local, self.mode, self.ids, self.header, self.textures = local, specialization, {}, [], set()
         self.resources: list = []   # LoaderContext::registerExternalResource: shared by all stages of a scene (set by generate())
+        self.cache_dir = None       # the loader's cache directory: float images (EXR) and cdf buffers are files there
 
     def resource(self, path: str) -> int:
         if path not in self.resources:
@@ -145,18 +171,44 @@ class _Tree:
             else:   # ImagePattern.cpp:15-73: the file travels as a resource id in the stage's LocalRegistry, the device loads it
                 fmt, arr = t.images[int(rec["image"])]
                 ref = t.image_files[int(rec["image"])]
-                if fmt == IMAGE_RGBA32F or ref is None or not ref[0].lower().endswith(".png"):
-                    raise ValueError("float images (EXR / HDR fixtures) are outside the script path: the runtime's image loader decodes them (refscript.py header)")
-                self.local.ints[f"img_{cid}"] = self.resource(ref[0])
+                if ref is None:
+                    raise ValueError("the sky texture is written by its light (SkyLight.cpp:28-47), not referenced as a texture")
+                file = ref[0] if fmt != IMAGE_RGBA32F else self.float_image_file(t, int(rec["image"]))
+                self.local.ints[f"img_{cid}"] = self.resource(file)
                 wraps = ["make_repeat_border()", "make_clamp_border()", "make_mirror_border()"]
                 wu, wv = wraps[int(rec["border_u"])], wraps[int(rec["border_v"])]
                 wrap = wu if wu == wv else f"make_split_border({wu}, {wv})"
                 filt = ["make_nearest_filter()", "make_bilinear_filter()", "make_bicubic_filter()"][int(rec["filter"])]
                 channels = 1 if arr.ndim == 2 else 4   # Image::loadResolution(filename).Channels == 1 ? 1 : 4
+                load = (f"device.load_image_by_id(img_{cid}_res_id, {channels})" if fmt == IMAGE_RGBA32F      # Image::isPacked: 8-bit formats only
+                        else f"device.load_packed_image_by_id(img_{cid}_res_id, {channels}, {'true' if ref[1] else 'false'})")
                 self.header.append(f'  let img_{cid}_res_id = registry::get_local_parameter_i32("img_{cid}", 0);\n'
-                                   f"  let img_{cid} = device.load_packed_image_by_id(img_{cid}_res_id, {channels}, {'true' if ref[1] else 'false'});\n"
+                                   f"  let img_{cid} = {load};\n"
                                    f"  let tex_{cid} : Texture = make_image_texture({wrap}, {filt}, img_{cid}, {tr});\n")
         return f"vec4_to_color(color_to_vec4(tex_{cid}(ctx)))"
+
+    def float_image_file(self, t: SceneTables, image: int, stem: str | None = None) -> str:
+        """The OpenEXR file a float image of the tables stands for: the fixtures are .npy / .npz arrays (or the baked sky), the reference's loader
+        and device deal in files, so the pixels are written into the cache directory as the simplest EXR there is."""
+        import os
+        if self.cache_dir is None:
+            raise ValueError("float images need a cache directory to live in as files (refscript.generate(cache_dir=...))")
+        path = os.path.join(self.cache_dir, (stem or f"image_{image}") + ".exr")
+        if not os.path.exists(path):
+            write_exr(path, t.images[image][1][::-1, :, :3])   # the tables hold rows bottom-up (Image::flipY); the file is top-down
+        return path
+
+    def cdf_file(self, t: SceneTables, light) -> tuple:
+        """(file, size_x, size_y) of a textured environment light's 2-D cdf as CDF::computeForImage writes it (CDF.cpp:71-151): marginal, then the
+        conditional rows, raw floats."""
+        import os
+        if self.cache_dir is None:
+            raise ValueError("environment cdfs need a cache directory (refscript.generate(cache_dir=...))")
+        first, sx, sy = (int(x) for x in light["p"][13:16].view(np.int32))
+        path = os.path.join(self.cache_dir, f"cdf_{first}.bin")
+        if not os.path.exists(path):
+            np.ascontiguousarray(t.aux_data[first:first + sy + sy * sx], np.float32).tofile(path)
+        return path, sx, sy
 
     def pull_header(self) -> str:
         h, self.header = "".join(self.header), []
@@ -208,6 +260,27 @@ def _lights(t: SceneTables, tree: _Tree) -> str:
                 col = tree.color(cid, "irradiance", colour)
                 direction = tree.vector(cid, "direction", raw_dir)
                 s += tree.pull_header() + f"  let light_{cid} = make_directional_light({i}, vec3_normalize({direction}), scene_bbox, {col});\n"
+            inf_names.append(f"light_{cid}")
+            continue
+        if int(l["type"]) in (LIGHT_ENV_TEXTURED, LIGHT_ENV_TEX):
+            tex = int(l["p"][12:13].view(np.int32)[0])
+            scale = tree.color(cid, "scale", l["p"][0:3])
+            tr = "make_mat3x3(" + ",".join(tree.vector(cid, f"_transform_c{k}", l["p"][3 + 3 * k:6 + 3 * k]) for k in range(3)) + ")"   # ShadingTree::getInlineMatrix3
+            image = int(t.textures[tex]["image"])
+            if t.image_files[image] is None:   # SkyLight.cpp:49-76: the baked sky model, its texture and cdf bound right here, resources by literal id
+                file = tree.float_image_file(t, image, f"skytex_{i}")
+                cdf, sx, sy = tree.cdf_file(t, l)
+                s += tree.pull_header() + (f"  let sky_tex_{cid} = make_image_texture(make_repeat_border(), make_bilinear_filter(), device.load_image_by_id({tree.resource(file)}, 4), mat3x3_identity());\n"
+                                           f"  let sky_cdf_{cid} = cdf::make_cdf_2d_from_buffer(device.load_buffer_by_id({tree.resource(cdf)}), {sx}, {sy});\n"
+                                           f"  let light_{cid}   = make_environment_light_textured({i}, {bbox}, {scale}, sky_tex_{cid}, sky_cdf_{cid}, {tr});\n")
+            else:                              # EnvironmentLight.cpp:40-110: radiance is a texture (ShadingTree::addTexture, the string case)
+                rad = f"@|ctx:ShadingContext|->Color{{maybe_unused(ctx); {tree.texture(t, tex)}}}"
+                if int(l["type"]) == LIGHT_ENV_TEXTURED:
+                    cdf, sx, sy = tree.cdf_file(t, l)
+                    s += tree.pull_header() + (f"  let cdf_{cid}   = cdf::make_cdf_2d_from_buffer(device.load_buffer_by_id({tree.resource(cdf)}), {sx}, {sy});\n"
+                                               f"  let light_{cid} = make_environment_light_textured({i}, {bbox}, {scale}, {rad}, cdf_{cid}, {tr});\n")
+                else:
+                    s += tree.pull_header() + f"  let light_{cid} = make_environment_light({i}, {bbox}, {scale}, {rad}, {tr});\n"
             inf_names.append(f"light_{cid}")
             continue
         assert int(l["type"]) == LIGHT_ENV_CONST
@@ -431,7 +504,7 @@ def generate(t: SceneTables, specialization: str = "default", std_aovs: bool = T
     resources: list = []
     local = Registry()
     tree = _Tree(local, specialization)
-    tree.resources = resources
+    tree.resources, tree.cache_dir = resources, cache_dir
     s = STD_LIB_STUB + "#[export] fn ig_miss_shader(settings: &Settings, first: i32, last: i32) -> () {\n" + prologue
     s += _lights(t, tree) + "\n" + _technique(t, std_aovs, cache_dir) + "\n"
     s += "  let use_framebuffer = true;\n  device.handle_miss_shader(full_technique, payload_info, first, last, use_framebuffer);\n}\n"
@@ -442,7 +515,7 @@ def generate(t: SceneTables, specialization: str = "default", std_aovs: bool = T
     for mat_id in range(int(t.materials.shape[0])):
         local = Registry()
         tree = _Tree(local, specialization)
-        tree.resources = resources
+        tree.resources, tree.cache_dir = resources, cache_dir
         s = STD_LIB_STUB + "#[export] fn ig_hit_shader(settings: &Settings, mat_id: i32, first: i32, last: i32) -> () {\n" + prologue
         s += _database(has_sphere) + _lights(t, tree) + "\n" + _bsdf(t, mat_id, tree) + _technique(t, std_aovs, cache_dir) + "\n"
         s += "  let use_framebuffer = true;\n  device.handle_hit_shader(shader, scene, full_technique, payload_info, first, last, use_framebuffer);\n}\n"
