@@ -422,7 +422,7 @@ def _perturb(script: str, rng) -> str:
     return "\n".join(res)
 
 
-@pytest.mark.parametrize("name", ["diamond_scene.json", "evaluation/multilight-hierarchy.json", "<spot>", "<distant>", "<procedural>", "<bitmaps>", "evaluation/sphere-light-pure.json"])
+@pytest.mark.parametrize("name", ["diamond_scene.json", "evaluation/multilight-hierarchy.json", "<spot>", "<distant>", "<procedural>", "<bitmaps>", "many_point_lights.json", "evaluation/env4k-conditional.json", "evaluation/sphere-light-pure.json"])
 def test_recogniser_does_not_depend_on_trivia(name, tmp_path):
     """the stage text has only ever come from this repository's reconstruction of the generators, so at least the
     recogniser must not depend on how that text is laid out: whitespace, comments, no-op statements and the order of independent bindings."""
@@ -435,12 +435,12 @@ def test_recogniser_does_not_depend_on_trivia(name, tmp_path):
     def describe(stages):
         tex = plugin.TextureTable(stages.resource_map)
         hits = [plugin.CompiledStage(s) for s in stages.hits]
-        mats = [h.material_tex(g, tex).tobytes() for h in hits]
         miss = plugin.CompiledStage(stages.miss)
-        inf, fin = miss.lights(g, db)
+        inf, fin = miss.lights(g, db, tex)
+        mats = [h.material_tex(g, tex).tobytes() for h in hits]
         tech = miss.technique(g)
         cam = plugin.CompiledStage(stages.raygen).camera(g)
-        return mats, tex.records().tobytes(), inf.tobytes(), fin.tobytes(), tech.tobytes(), miss.selector_data.tobytes(), cam.tobytes()
+        return mats, tex.records().tobytes(), tex.aux().tobytes(), inf.tobytes(), fin.tobytes(), tech.tobytes(), miss.selector_data.tobytes(), cam.tobytes()
     ref = describe(st)
     for _ in range(4):
         pert = refscript.StageSet(refscript.Stage(st.raygen.function, _perturb(st.raygen.script, rng), st.raygen.local),
