@@ -6,8 +6,7 @@
 // grey files kept as one byte per pixel, everything else as RGBA bytes, and -- unless the texture says `linear` -- every colour byte mapped from
 // sRGB to linear with byte_color_to_linear (Image.cpp:40-51). A plugin built inside the reference tree would call IG::Image itself; this
 // repository's build has no ig_runtime to link, so the one 8-bit format the reference's scenes use -- PNG -- is decoded here (own inflate,
-// filters 0-4, grey / grey+alpha / RGB / RGBA / palette, 8 bits, non-interlaced). Float images (EXR / HDR: `device.load_image_by_id`) are not
-// decoded here and are reported by the recogniser.
+// filters 0-4, grey / grey+alpha / RGB / RGBA / palette, 8 bits, non-interlaced), and so are float images in OpenEXR files (below).
 #pragma once
 
 #include <cstdint>
