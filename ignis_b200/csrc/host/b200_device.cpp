@@ -91,7 +91,7 @@ bool B200Device::forAll(const std::function<int(igb200_ctx*, int)>& f, const cha
 
 // Device.cpp:1667-1670: borrowed pointers, valid for the device's lifetime (Runtime.cpp:532-541). The upload itself waits
 // for the first render(): the material / light / camera descriptors only arrive with the shader set.
-void B200Device::assignScene(const SceneSettings& settings) { mScene = settings; mSceneDirty = true; }
+void B200Device::assignScene(const SceneSettings& settings) { mScene = settings; mSceneDirty = true; mFiles = ImageCache(); }
 
 void B200Device::resize(size_t width, size_t height) {
     if (!mCtx) return;
@@ -100,7 +100,7 @@ void B200Device::resize(size_t width, size_t height) {
 }
 
 // Device.cpp:1684-1690 drops cached uploads; the next render() re-uploads the scene.
-void B200Device::releaseAll() { mSceneDirty = true; }
+void B200Device::releaseAll() { mSceneDirty = true; mFiles = ImageCache(); }
 
 bool B200Device::setPartition(int rank, int world, int tile) {
     if (mCtxs.size() > 1) { error("setPartition: this device already spreads the frame over its own GPUs (IGB200_GPUS)"); return false; }
@@ -120,6 +120,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     std::vector<float> selector_data;
     TextureTable textures;   // filled by the materials in order of first use (script_recognizer.h)
     textures.resource_map = mScene.resource_map;
+    textures.cache = &mFiles;   // decoded image / buffer files live as long as the scene is assigned: render() resolves the descriptors at every call
     try {
         if (set.HitShaders.size() != mScene.entity_per_material->size()) throw RecognizeError{"one hit shader per material expected"};
         // the stage that carries the light tables: the miss shader, else the first hit shader that has them
@@ -155,7 +156,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     append(bytes, &technique, sizeof(technique));
     append(bytes, selector_data.data(), selector_data.size() * sizeof(float));
     append(bytes, textures.records.data(), textures.records.size() * sizeof(igb200_texture));
-    for (const DeviceImage& im : textures.images) append(bytes, im.pixels(), im.pixel_bytes());
+    for (const std::string& key : textures.image_keys) append(bytes, key.data(), key.size() + 1);   // which files, not their pixels (cached: mFiles)
     append(bytes, textures.aux.data(), textures.aux.size() * sizeof(float));
     if (!mSceneDirty && bytes == mDescriptorBytes) return true;
 
@@ -186,7 +187,7 @@ bool B200Device::uploadScene(const IG::TechniqueVariantShaderSet& set, const IG:
     d.selector_data = selector_data.empty() ? nullptr : selector_data.data(); d.n_selector_data = (int32_t)selector_data.size();
     d.textures = textures.records.empty() ? nullptr : textures.records.data(); d.n_textures = (int32_t)textures.records.size();
     std::vector<igb200_image> images;   // 8-bit files decoded by image_io as the reference's device keeps them
-    for (const DeviceImage& im : textures.images) { igb200_image ii; ii.format = im.format; ii.width = im.width; ii.height = im.height; ii.reserved = 0; ii.pixels = im.pixels(); images.push_back(ii); }
+    for (const auto& im : textures.images) { igb200_image ii; ii.format = im->format; ii.width = im->width; ii.height = im->height; ii.reserved = 0; ii.pixels = im->pixels(); images.push_back(ii); }
     d.images = images.empty() ? nullptr : images.data(); d.n_images = (int32_t)images.size();
     d.aux_data = textures.aux.empty() ? nullptr : textures.aux.data(); d.n_aux_data = (int32_t)textures.aux.size();   // 2-D cdfs of textured environment lights
     for (int k = 0; k < 3; ++k) { d.bbox_min[k] = db.SceneBBox.min(k); d.bbox_max[k] = db.SceneBBox.max(k); }

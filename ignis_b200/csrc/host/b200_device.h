@@ -84,6 +84,7 @@ private:
     bool mSceneDirty = true;
     int mStdAovs = -1;                       // Normals / Albedo AOVs currently enabled on the device (-1: not set yet)
     std::vector<uint8_t> mDescriptorBytes;   // materials + lights + camera + technique of the scene on the device
+    ImageCache mFiles;                       // decoded image / buffer files the stage text names (dropped with the scene)
     std::vector<float> mHostFramebuffer;     // what getFramebufferForHost handed out, for syncFramebufferHostToDevice
     std::unordered_map<std::string, float*> mHostPtrs;   // per AOV ("" = Color): the context-owned host buffer last handed out
     IG::Statistics mStats;

@@ -77,7 +77,7 @@ void igbh_textures_set_resources(igbh::TextureTable* t, const char* const* paths
 }
 int igbh_textures_image_count(const igbh::TextureTable* t) { return (int)t->images.size(); }
 const uint8_t* igbh_textures_image(const igbh::TextureTable* t, int i, int* format, int* width, int* height, size_t* bytes) {
-    const igbh::DeviceImage& im = t->images[(size_t)i];
+    const igbh::DeviceImage& im = *t->images[(size_t)i];
     *format = im.format; *width = im.width; *height = im.height; *bytes = im.pixel_bytes();
     return static_cast<const uint8_t*>(im.pixels());
 }

@@ -1,6 +1,8 @@
 // script_recognizer.cpp -- see script_recognizer.h. Host-only C++17, no CUDA.
 #include "script_recognizer.h"
 
+#include <functional>
+
 #include <cstdio>
 
 #include <cctype>
@@ -525,21 +527,38 @@ int TextureTable::add(const igb200_texture& t) {
     return (int)records.size() - 1;
 }
 
+static int enter_image(TextureTable& t, const std::string& key, const std::function<DeviceImage()>& decode) {
+    for (size_t i = 0; i < t.image_keys.size(); ++i) if (t.image_keys[i] == key) return (int)i;
+    std::shared_ptr<const DeviceImage> im;
+    if (t.cache) { const auto it = t.cache->images.find(key); if (it != t.cache->images.end()) im = it->second; }
+    if (!im) { im = std::make_shared<const DeviceImage>(decode()); if (t.cache) t.cache->images[key] = im; }
+    t.images.push_back(im);
+    t.image_keys.push_back(key);
+    return (int)t.images.size() - 1;
+}
 int TextureTable::image(const std::string& path, bool linear) {
-    for (size_t i = 0; i < image_keys.size(); ++i) if (image_keys[i].first == path && image_keys[i].second == linear) return (int)i;
-    images.push_back(load_packed_image(path, linear));
-    image_keys.emplace_back(path, linear);
-    return (int)images.size() - 1;
+    return enter_image(*this, path + (linear ? "|linear" : "|srgb"), [&] { return load_packed_image(path, linear); });
+}
+std::shared_ptr<const std::vector<float>> TextureTable::buffer(const std::string& path) {
+    if (cache) { const auto it = cache->buffers.find(path); if (it != cache->buffers.end()) return it->second; }
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) fail("cannot open the buffer '" + path + "'");
+    std::fseek(f, 0, SEEK_END); const long bytes = std::ftell(f); std::fseek(f, 0, SEEK_SET);
+    auto data = std::make_shared<std::vector<float>>((size_t)std::max(0L, bytes) / 4);
+    const size_t got = data->empty() ? 0 : std::fread(data->data(), 4, data->size(), f);
+    std::fclose(f);
+    if (got != data->size()) fail("cannot read the buffer '" + path + "'");
+    if (cache) cache->buffers[path] = data;
+    return data;
 }
 
 int TextureTable::float_image(const std::string& path) {
-    for (size_t i = 0; i < image_keys.size(); ++i) if (image_keys[i].first == path && images[i].format == IGB200_IMAGE_RGBA32F) return (int)i;
-    FloatImage f = load_float_image(path);
-    DeviceImage im;
-    im.format = IGB200_IMAGE_RGBA32F; im.width = f.width; im.height = f.height; im.floats.swap(f.rgba);
-    images.push_back(std::move(im));
-    image_keys.emplace_back(path, false);
-    return (int)images.size() - 1;
+    return enter_image(*this, path + "|float", [&] {
+        FloatImage f = load_float_image(path);
+        DeviceImage im;
+        im.format = IGB200_IMAGE_RGBA32F; im.width = f.width; im.height = f.height; im.floats.swap(f.rgba);
+        return im;
+    });
 }
 
 // LoaderUtils::inlineTransformAs2d: mat3x3_identity() | make_mat3x3(col0, col1, col2) -> rows 0 and 1
@@ -710,12 +729,9 @@ static igb200_light resolve_light(Eval& ev, const std::string& binding, TextureT
         const std::string& file = (*textures->resource_map)[(size_t)id];
         const size_t words = (size_t)sy + (size_t)sy * (size_t)sx;
         const int32_t first = (int32_t)textures->aux.size();
-        textures->aux.resize(textures->aux.size() + words);
-        FILE* f = std::fopen(file.c_str(), "rb");
-        if (!f) fail("cannot open the environment cdf '" + file + "'");
-        const size_t got = std::fread(textures->aux.data() + first, 4, words, f);
-        std::fclose(f);
-        if (got != words || sx < 1 || sy < 1) fail("environment cdf '" + file + "' does not hold " + std::to_string(sy) + " + " + std::to_string(sy) + " x " + std::to_string(sx) + " values");
+        const std::shared_ptr<const std::vector<float>> data = textures->buffer(file);
+        if (sx < 1 || sy < 1 || data->size() < words) fail("environment cdf '" + file + "' does not hold " + std::to_string(sy) + " + " + std::to_string(sy) + " x " + std::to_string(sx) + " values");
+        textures->aux.insert(textures->aux.end(), data->begin(), data->begin() + (long)words);
         const int32_t tail[4] = {tex, first, sx, sy};
         std::memcpy(&out.p[12], tail, sizeof(tail));
     } else if (l.name == "make_environment_light") {       // EnvironmentLight.cpp:103-110; light/env.art:161-164: colour = scale * texture

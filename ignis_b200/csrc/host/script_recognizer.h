@@ -14,6 +14,7 @@
 #pragma once
 
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -56,16 +57,25 @@ struct Registries { const IG::ParameterSet* local; const IG::ParameterSet* globa
 // The scene's texture table as it builds up while the materials are resolved (hit stages in material order): a texture gets the index of
 // its first use, as in the loader (ignis_b200/scene.py texture_id); the same texture met again in another stage (its `tex_<id>` binding may
 // carry another closure id there) is found by its contents.
+// Decoded files kept across the render() calls of a device (the descriptors are resolved at every call to notice changed parameters; the files
+// behind resource ids do not change while a scene is assigned): key = path + how it was read.
+struct ImageCache {
+    std::map<std::string, std::shared_ptr<const DeviceImage>> images;
+    std::map<std::string, std::shared_ptr<const std::vector<float>>> buffers;
+};
+
 struct TextureTable {
     std::vector<igb200_texture> records;
     int add(const igb200_texture& t);
     // image textures: the files named by the stage text through resource ids (IRenderDevice::SceneSettings::resource_map), decoded as the
     // reference's device keeps them (image_io.h); one entry per (file, linear flag), numbered by first use
     const std::vector<std::string>* resource_map = nullptr;
-    std::vector<DeviceImage> images;
-    std::vector<std::pair<std::string, bool>> image_keys;
+    ImageCache* cache = nullptr;                        // optional: decoded files are looked up / kept there
+    std::vector<std::shared_ptr<const DeviceImage>> images;
+    std::vector<std::string> image_keys;                // "<path>|srgb", "<path>|linear", "<path>|float"
     int image(const std::string& path, bool linear);   // 8-bit file (PNG); throws RecognizeError
     int float_image(const std::string& path);          // OpenEXR file
+    std::shared_ptr<const std::vector<float>> buffer(const std::string& path);   // raw 32-bit words of a buffer file
     // 32-bit words of further buffers the descriptors point into (igb200_scene_desc::aux_data): the 2-D cdfs of textured environment lights
     std::vector<float> aux;
 };
