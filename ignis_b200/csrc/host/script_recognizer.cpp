@@ -353,7 +353,7 @@ struct Eval {
                     std::vector<std::string> names; std::string cur;
                     for (char ch : pat) { if (ident_char(ch)) cur += ch; else { if (!cur.empty()) names.push_back(cur); cur.clear(); } }
                     if (!cur.empty()) names.push_back(cur);
-                    if (v.kind == Val::Vec) for (size_t k = 0; k < names.size() && (int)k < v.n; ++k) { Val c = Val::num(v.f[k]); c.known = v.known; scopes.back()[names[k]] = c; }
+                    if (v.kind == Val::Vec) for (size_t k = 0; k < names.size() && (int)k < v.n; ++k) { Val comp = Val::num(v.f[k]); comp.known = v.known; scopes.back()[names[k]] = comp; }
                 } else {
                     const size_t colon = pat.find(':');
                     if (colon != std::string::npos) pat = trim(pat.substr(0, colon));
@@ -790,10 +790,10 @@ static igb200_light resolve_light(Eval& ev, const std::string& binding, TextureT
             // evaluated in double and rounded once (ignis_b200/scene.py: ellipsoid_area does the same)
             const Val& gm = ctor_arg(ent, 3);
             if (gm.kind != Val::Ctor || gm.name != "make_mat3x4") fail("sphere light: global_mat is not make_mat3x4(...)");
-            double l[3];
-            for (int k = 0; k < 3; ++k) { const Val c = as_vec(ctor_arg(gm, k), "global matrix column"); l[k] = 0; for (int i = 0; i < 3; ++i) { const double x = (double)c.f[i] * (double)radius; l[k] += x * x; } }
+            double axis[3];
+            for (int k = 0; k < 3; ++k) { const Val c = as_vec(ctor_arg(gm, k), "global matrix column"); axis[k] = 0; for (int i = 0; i < 3; ++i) { const double x = (double)c.f[i] * (double)radius; axis[k] += x * x; } }
             const double P = (double)1.6f;
-            out.p[7] = (float)(4 * (double)3.14159265359f * std::pow((std::pow(l[0] * l[1], P / 2) + std::pow(l[0] * l[2], P / 2) + std::pow(l[1] * l[2], P / 2)) / 3, 1 / P));
+            out.p[7] = (float)(4 * (double)3.14159265359f * std::pow((std::pow(axis[0] * axis[1], P / 2) + std::pow(axis[0] * axis[2], P / 2) + std::pow(axis[1] * axis[2], P / 2)) / 3, 1 / P));
         } else {
             fail("area emitter '" + ae.name + "' is not supported by this device");
         }
