@@ -471,6 +471,51 @@ void unpredict_and_interleave(std::vector<uint8_t>& buf) {   // the filter ZIP a
 
 }  // namespace
 
+// Radiance RGBE (.hdr), as stb_image decodes it for IG::Image (flat and run-length encoded scanlines, -Y +X orientation; value = mantissa * 2^(e - 136))
+static FloatImage load_radiance_hdr(const std::string& path, const std::vector<uint8_t>& f) {
+    size_t pos = 0;
+    auto line = [&]() { std::string s; while (pos < f.size() && f[pos] != '\n') s += (char)f[pos++]; ++pos; return s; };
+    bool format_ok = false;
+    for (;;) {
+        if (pos >= f.size()) io_fail(path, "truncated Radiance header");
+        const std::string l = line();
+        if (l.empty()) break;
+        if (l == "FORMAT=32-bit_rle_rgbe") format_ok = true;
+    }
+    if (!format_ok) io_fail(path, "only 32-bit_rle_rgbe Radiance files are decoded here");
+    int h = 0, w = 0;
+    if (std::sscanf(line().c_str(), "-Y %d +X %d", &h, &w) != 2 || h <= 0 || w <= 0) io_fail(path, "only the -Y +X orientation of Radiance files is decoded here");
+    FloatImage img;
+    img.width = w; img.height = h;
+    img.rgba.assign((size_t)w * h * 4, 1.0f);
+    std::vector<uint8_t> scan((size_t)w * 4);
+    for (int y = 0; y < h; ++y) {
+        if (pos + 4 > f.size()) io_fail(path, "truncated Radiance data");
+        if (w >= 8 && w < 32768 && f[pos] == 2 && f[pos + 1] == 2 && !(f[pos + 2] & 0x80) && ((f[pos + 2] << 8) | f[pos + 3]) == w) {   // new run-length encoding: the four components one after another
+            pos += 4;
+            for (int k = 0; k < 4; ++k)
+                for (int x = 0; x < w;) {
+                    if (pos >= f.size()) io_fail(path, "truncated Radiance data");
+                    int count = f[pos++];
+                    if (count > 128) { count -= 128; if (pos >= f.size() || x + count > w) io_fail(path, "corrupt Radiance run"); const uint8_t v = f[pos++]; while (count--) scan[(size_t)(x++) * 4 + k] = v; }
+                    else { if (count == 0 || pos + count > f.size() || x + count > w) io_fail(path, "corrupt Radiance run"); while (count--) scan[(size_t)(x++) * 4 + k] = f[pos++]; }
+                }
+        } else {   // flat
+            if (pos + (size_t)w * 4 > f.size()) io_fail(path, "truncated Radiance data");
+            std::memcpy(scan.data(), &f[pos], (size_t)w * 4);
+            pos += (size_t)w * 4;
+        }
+        float* dst = &img.rgba[(size_t)(h - 1 - y) * w * 4];   // rows bottom-up
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* p = &scan[(size_t)x * 4];
+            if (p[3] == 0) { dst[4 * x] = dst[4 * x + 1] = dst[4 * x + 2] = 0; continue; }
+            const float s1 = std::ldexp(1.0f, (int)p[3] - 136);
+            dst[4 * x] = p[0] * s1; dst[4 * x + 1] = p[1] * s1; dst[4 * x + 2] = p[2] * s1;
+        }
+    }
+    return img;
+}
+
 FloatImage load_float_image(const std::string& path) {
     std::vector<uint8_t> f;
     {
@@ -485,7 +530,8 @@ FloatImage load_float_image(const std::string& path) {
         if (got != f.size()) io_fail(path, "short read");
     }
     auto u32 = [&](size_t o) -> uint32_t { if (o + 4 > f.size()) io_fail(path, "truncated file"); return (uint32_t)f[o] | ((uint32_t)f[o + 1] << 8) | ((uint32_t)f[o + 2] << 16) | ((uint32_t)f[o + 3] << 24); };
-    if (f.size() < 8 || u32(0) != 20000630u) io_fail(path, "not an OpenEXR file (this build decodes EXR only among the float formats)");
+    if (f.size() > 10 && (!std::memcmp(f.data(), "#?RADIANCE", 10) || !std::memcmp(f.data(), "#?RGBE", 6))) return load_radiance_hdr(path, f);
+    if (f.size() < 8 || u32(0) != 20000630u) io_fail(path, "not an OpenEXR or Radiance HDR file (the float formats this build decodes)");
     const uint32_t version = u32(4);
     if ((version & 0xFF) != 2 || (version & 0x200) || (version & 0x800) || (version & 0x1000)) io_fail(path, "tiled, deep or multi-part OpenEXR files are not decoded here");
     // ---- header attributes

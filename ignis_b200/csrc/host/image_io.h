@@ -31,7 +31,7 @@ DeviceImage load_packed_image(const std::string& path, bool already_linear);
 // reference's device keeps (IG::Image::load, Image.cpp:500-712; Device.cpp:735-799): RGBA float, rows bottom-up, alpha 1 where the file has
 // none, a single grey channel spread over R, G and B. Decoded here: single-part scanline files with HALF / FLOAT / UINT channels, compression
 // NONE, RLE, ZIPS, ZIP and PIZ (own Huffman + wavelet decoder) -- what OpenEXR writers produce by default; tiled, deep, multi-part files and the
-// lossy B44 / DWA / PXR24 compressions are reported.
+// lossy B44 / DWA / PXR24 compressions are reported. Radiance RGBE files (.hdr, flat or run-length encoded) are decoded as stb_image decodes them.
 struct FloatImage {
     int width = 0, height = 0;
     std::vector<float> rgba;   // 4 floats per pixel, rows bottom-up

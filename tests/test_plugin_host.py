@@ -479,12 +479,12 @@ def test_host_exr_reader():
     with OpenCV's bundled OpenEXR."""
     gold = os.path.join(ROOT, "tests", "golden", "exr")
     exp = np.load(os.path.join(gold, "expected.npz"))
-    assert len(exp.files) == 8
+    assert len(exp.files) == 10   # eight EXR files, two Radiance .hdr files (run-length encoded and flat scanlines)
     for name in exp.files:
         got = plugin.load_float_image(os.path.join(gold, name))
         np.testing.assert_array_equal(got[::-1, :, :3], exp[name], err_msg=name)
         assert np.all(got[:, :, 3] == 1)
-    with pytest.raises(plugin.DeviceError, match="not an OpenEXR"):
+    with pytest.raises(plugin.DeviceError, match="not an OpenEXR or Radiance"):
         plugin.load_float_image(os.path.join(ROOT, "scenes", "textures", "bumpmap.png"))
     ref_dir = "/root/reference/scenes"
     if os.path.isdir(ref_dir):

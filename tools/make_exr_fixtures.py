@@ -1,4 +1,4 @@
-"""Writes the OpenEXR fixtures of tests/golden/exr/ with OpenCV's bundled OpenEXR (every lossless compression, HALF and FLOAT samples, sizes that
+"""Writes the OpenEXR (and two Radiance .hdr) fixtures of tests/golden/exr/ with OpenCV's bundled OpenEXR (every lossless compression, HALF and FLOAT samples, sizes that
 make partial last chunks) and stores what OpenEXR itself decodes from them next to them (expected.npz). tests/test_plugin_host.py::
 test_host_exr_reader checks csrc/host/image_io.cpp against these without needing OpenCV. Run in the build container: python tools/make_exr_fixtures.py"""
 import os
@@ -22,5 +22,11 @@ for k, (comp, ty, h, w, kind) in enumerate([("PIZ", "HALF", 45, 70, "smooth"), (
     name = f"{k}_{comp.lower()}_{ty.lower()}_{h}x{w}.exr"
     cv2.imwrite(os.path.join(OUT, name), a, [cv2.IMWRITE_EXR_COMPRESSION, getattr(cv2, "IMWRITE_EXR_COMPRESSION_" + comp), cv2.IMWRITE_EXR_TYPE, getattr(cv2, "IMWRITE_EXR_TYPE_" + ty)])
     expected[name] = np.ascontiguousarray(cv2.imread(os.path.join(OUT, name), cv2.IMREAD_UNCHANGED)[:, :, ::-1])   # RGB, rows top-down
+for k, (h, w) in enumerate([(20, 33), (9, 7)]):   # Radiance RGBE: run-length encoded scanlines (width >= 8) and flat ones
+    a = (rng.random((h, w, 3)) * np.array([0.01, 3, 200])).astype(np.float32)
+    a[2:5, 3:6] = 0
+    name = f"{8 + k}_radiance_{h}x{w}.hdr"
+    cv2.imwrite(os.path.join(OUT, name), a[:, :, ::-1])
+    expected[name] = np.ascontiguousarray(cv2.imread(os.path.join(OUT, name), cv2.IMREAD_UNCHANGED)[:, :, ::-1])
 np.savez_compressed(os.path.join(OUT, "expected.npz"), **expected)
 print(sorted(expected), sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)), "bytes")
