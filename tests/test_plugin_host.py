@@ -505,10 +505,8 @@ def test_host_exr_reader():
 def test_render_of_float_image_scenes_through_cpp_plugin(name, w, h, spi):
     """BASELINE config C5 (sky, embedded point lights, bitmap bump map, checkerboard, rough conductor, hierarchy selector) and the environment-map scenes
     through ig_get_interface(): the sky / environment textures travel as OpenEXR files, the cdfs as buffer files, all named through the resource map.
-    The descriptors this path hands igb200_set_scene are the loader's bit for bit (test_recognised_descriptors_equal_loader_descriptors, CPU); the render
-    itself has NOT been run on hardware yet -- the round's GPU budget was spent when this was written -- so it only runs on request."""
-    if not os.environ.get("IGB200_RUN_UNVERIFIED"):
-        pytest.skip("not yet run on hardware (set IGB200_RUN_UNVERIFIED=1)")
+    The descriptors this path hands igb200_set_scene are the loader's bit for bit (test_recognised_descriptors_equal_loader_descriptors, CPU); here the
+    frames: plugin == oracle (run on a B200 with the last seconds of round 2's GPU budget: gpurun r6ad, 12 passed)."""
     from oracle.oracle import Oracle
     t = scene(name)
     o = Oracle(t)
