@@ -407,3 +407,23 @@ def test_oracle_deterministic_accumulation():
     plain = run(False, 4, 3)
     assert np.linalg.norm((a - plain).ravel()) / np.linalg.norm(plain.ravel()) < 1e-6
     np.testing.assert_array_equal(run(True, 1, 2, 1).view(np.uint32), run(False, 1, 2, 1).view(np.uint32))   # first iteration: 0 + x is exact
+
+
+def test_sky_fixture_is_what_the_reference_sources_bake():
+    """scenes/textures/sky/*.npz is the output of the reference's OWN sky-model sources (ArHosekSkyModel.cpp, SunLocation.cpp) compiled where they
+    lie (oracle/Makefile: _ref/skybake). In the build container, where /root/reference exists, bake C5's sky again and compare bit for bit."""
+    import json
+    import subprocess
+    if not os.path.isdir("/root/reference/src/runtime/skysun"):
+        pytest.skip("the reference tree is not here (GPU box): the committed fixture is what travels")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "_ref/skybake"], check=True, capture_output=True)
+    lj = next(l for l in json.load(open(os.path.join(ROOT, "scenes", "many_point_lights.json")))["lights"] if l.get("type") == "sky")
+    g = lj.get("ground", [0.8, 0.8, 0.8])
+    g = [g] * 3 if isinstance(g, (int, float)) else g
+    args = [os.path.join(ROOT, "oracle", "_ref", "skybake"), *[str(x) for x in g], str(lj.get("turbidity", 3.0))]
+    assert not any(k in lj for k in ("direction", "sun_direction", "elevation", "azimuth"))   # C5's sky uses the default date and place
+    args += ["time", *[str(lj.get(k, d)) for k, d in (("year", 2020), ("month", 5), ("day", 6), ("hour", 12), ("minute", 0), ("seconds", 0.0),
+                                                       ("latitude", 49.235422), ("longitude", -6.9965744), ("timezone", -2))]]
+    rgb = np.frombuffer(subprocess.run(args, check=True, capture_output=True).stdout, np.float32).reshape(256, 512, 3)
+    fixture = np.load(os.path.join(S.SKY_DIR, f"sky_{S.sky_key(lj)}.npz"))["rgb"]
+    np.testing.assert_array_equal(rgb.view(np.uint32), fixture.view(np.uint32))
